@@ -1,0 +1,130 @@
+/* skagpu.h -- C ABI of libskagpu.so, the B200 (sm_100a) split-k-mer engine.
+ *
+ * Drop-in boundary for the hot path of bacpop/ska.rust v0.5.2.  The
+ * reference has no FFI for this path; each entry point below replaces one Rust call site, cited as
+ * file:line in /root/reference.  Plain C: a Rust host binds it with an `extern "C"` block
+ * (INTEGRATION.md shows the block), this repo's C++ host (ska.rust_b200/host) and Python
+ * (ska.rust_b200/api.py, ctypes) bind the same symbols.
+ *
+ * Conventions (mirroring the reference's ownership/error behaviour):
+ *  - every function returns 0 on success, non-zero on failure; the message is then available from
+ *    skagpu_last_error() (thread-local).  Nothing aborts; where the reference panics (invalid k,
+ *    empty sample, ...) the same condition is reported here as an error.
+ *  - ska_array_t is an opaque, device-resident MergeSkaArray (merge_ska_array.rs:108-126):
+ *    created by skagpu_build / skagpu_array_from_host, mutated in place by skagpu_filter
+ *    (`&mut self`), read by the rest (`&self`), released by skagpu_free.
+ *  - all pointer arguments are HOST pointers unless the name says `_dev`; host buffers may be
+ *    pageable or pinned (pinned is faster; skagpu_host_alloc returns pinned memory).
+ *  - row order of a built array is ascending split-k-mer key (the reference's order is hashbrown
+ *    iteration order, i.e. unspecified; its tests compare as sets).
+ *  - single calling thread per handle; the library owns its CUDA stream(s).
+ */
+#ifndef SKAGPU_H
+#define SKAGPU_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct ska_array ska_array_t;
+typedef struct ska_seqbatch ska_seqbatch_t;
+
+/* One sample = InputFastx (merge_ska_dict.rs:25) after host-side parsing (needletail's job,
+ * ska_dict.rs:131-147): all records of file 1 followed by all records of file 2, newlines
+ * stripped, concatenated; rec_off has n_rec+1 entries.  qual == NULL <=> FASTA input. */
+typedef struct {
+    const uint8_t* seq;
+    const uint8_t* qual;
+    const uint64_t* rec_off;
+    uint64_t n_rec;
+    uint64_t n_rec_file1;
+} ska_input_t;
+
+/* VariantDist (merge_ska_array.rs:44-53) */
+typedef struct {
+    double distance;
+    double mismatch_prop;
+    uint64_t match_count;
+    uint64_t mismatch_count;
+} ska_dist_t;
+
+enum { SKA_QUAL_NONE = 0, SKA_QUAL_MIDDLE = 1, SKA_QUAL_STRICT = 2 };            /* cli.rs:112-123 */
+enum { SKA_FILTER_NONE = 0, SKA_FILTER_NO_CONST = 1, SKA_FILTER_NO_AMBIG = 2,    /* cli.rs:129-138 */
+       SKA_FILTER_NO_AMBIG_OR_CONST = 3 };
+
+const char* skagpu_last_error(void);
+/* Selects the CUDA device used by this process (one process per GPU). Default device 0. */
+int skagpu_set_device(int device);
+
+/* build_and_merge::<IntT>(&[InputFastx], k, rc, &QualOpts, threads, proportion_reads)
+ * (merge_ska_dict.rs:354-417; callers lib.rs:596-603, io_utils.rs:83-90) followed by
+ * MergeSkaArray::new(&dict) (merge_ska_array.rs:166-186; caller generic_modes.rs:279).
+ * proportion_reads <= 0 means None.  k odd in 5..=63 else error "Invalid k-mer length"
+ * (ska_dict.rs:342-344); a sample with no valid split k-mer is an error (ska_dict.rs:374-376). */
+int skagpu_build(const ska_input_t* inputs, size_t n_samples, uint32_t k, int rc, uint16_t min_count,
+                 uint8_t min_qual, int qual_filter, double proportion_reads, ska_array_t** out);
+
+/* Same computation with the sequence bytes already resident in HBM: upload once, build many times
+ * (what bench.py's device-resident `value` times).  The batch is not consumed. */
+int skagpu_seqbatch_upload(const ska_input_t* inputs, size_t n_samples, double proportion_reads,
+                           ska_seqbatch_t** out);
+int skagpu_build_from_batch(const ska_seqbatch_t* batch, uint32_t k, int rc, uint16_t min_count,
+                            uint8_t min_qual, int qual_filter, ska_array_t** out);
+void skagpu_seqbatch_free(ska_seqbatch_t* batch);
+
+/* MergeSkaArray::<IntT>::load (merge_ska_array.rs:199-204) once the host has decoded the .skf:
+ * keys are little-endian u64 (key_bits 64) or (lo,hi) u64 pairs (key_bits 128). n_keys may exceed
+ * n_rows only for arrays exported after a filter with update_kmers=false. */
+int skagpu_array_from_host(uint32_t k, int rc, uint32_t key_bits, uint64_t n_rows, uint64_t n_samples,
+                           const void* keys, const uint8_t* variants_rowmajor, const uint64_t* counts,
+                           ska_array_t** out);
+
+int skagpu_dims(const ska_array_t* a, uint64_t* n_rows, uint64_t* n_keys, uint64_t* n_samples, uint32_t* k,
+                int* rc, uint32_t* key_bits);
+
+/* MergeSkaArray::filter(&mut self, min_count, filter_ambig_as_missing, &FilterType, mask_ambig,
+ * ignore_const_gaps, update_kmers) -> i32   (merge_ska_array.rs:289-402; caller
+ * generic_modes.rs:123-130).  *removed = number of rows removed by the filter loop. */
+int skagpu_filter(ska_array_t* a, uint64_t min_count, int filter_ambig_as_missing, int filter_type, int mask_ambig,
+                  int ignore_const_gaps, int update_kmers, int32_t* removed);
+
+/* MergeSkaArray::distance(&self, constant, filt_ambig) (merge_ska_array.rs:416-438, variant_dist
+ * :587-632; caller generic_modes.rs:171).  out has N(N-1)/2 entries, pairs i<j in row-major order. */
+int skagpu_distance(const ska_array_t* a, double constant, int filt_ambig, ska_dist_t* out);
+
+/* Row-major export for save()/Display (merge_ska_array.rs:191-197, 649-698): keys (n_keys entries,
+ * 8 or 16 bytes each), variants (n_rows x n_samples), counts (n_rows). Any pointer may be NULL. */
+int skagpu_export(const ska_array_t* a, void* keys, uint8_t* variants_rowmajor, uint64_t* counts);
+/* write_fasta's transpose (merge_ska_array.rs:499-503): (n_samples x n_rows) row-major.
+ * samples_by_rows == NULL: the transpose is computed on the device and dropped (device-only timing). */
+int skagpu_export_transposed(const ska_array_t* a, uint8_t* samples_by_rows);
+
+void skagpu_free(ska_array_t* a);
+
+/* Pinned host memory for callers that want full-speed PCIe transfers. */
+void* skagpu_host_alloc(size_t bytes);
+void skagpu_host_free(void* p);
+
+/* ---- instrumentation (no reference counterpart) ------------------------------------------------
+ * Stage timings of the most recent build on this thread, measured with CUDA events on the
+ * library's own stream.  names[i] is a static string; returns the number of stages written. */
+int skagpu_last_timings(const char** names, float* ms, uint64_t* launches, int max_stages);
+/* CUDA-event stopwatch on the library's stream: op 0 = synchronise + start, op 1 = stop, *ms = elapsed
+ * device time between the two (what bench.py brackets its timed region with). */
+int skagpu_stream_timer(int op, float* ms);
+/* Number of kernel launches issued by this library since process start (all entry points). */
+uint64_t skagpu_launch_count(void);
+/* Raw K1 access for kernel-level parity tests and the roofline measurement: runs the extraction
+ * kernel `iters` times over a resident batch; writes one u64 record per base position
+ * (key<<4 | one-hot(middle), 0xFFFF...F for positions that start no valid window) to rec_out
+ * (host, n_positions entries, may be NULL) and reports the mean kernel time. */
+int skagpu_k1_extract(const ska_seqbatch_t* batch, uint32_t k, int rc, uint8_t min_qual, int qual_filter, int iters,
+                      uint64_t* rec_out, uint64_t* n_positions, float* mean_ms);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SKAGPU_H */

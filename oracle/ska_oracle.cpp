@@ -20,6 +20,7 @@
 // Citations are file:line in /root/reference (bacpop/ska.rust @ 99bd6e0).
 
 #include <algorithm>
+#include <atomic>
 #include <cmath>
 #include <cstdint>
 #include <cstdio>
@@ -281,34 +282,39 @@ static inline uint64_t mix64(uint64_t x) {
 static inline uint64_t hash_key(uint64_t k) { return mix64(k); }
 static inline uint64_t hash_key(u128 k) { return mix64((uint64_t)k ^ mix64((uint64_t)(k >> 64))); }
 
+// Each map instance salts its hash (as hashbrown does through ahash::RandomState): iterating one
+// map in slot order while inserting into another with the SAME hash function builds giant probe
+// clusters (quadratic time) -- exactly what MergeSkaDict::append does.
+static uint64_t next_salt() {
+    static std::atomic<uint64_t> ctr{0x243F6A8885A308D3ULL};
+    return ctr.fetch_add(0x9E3779B97F4A7C15ULL);
+}
 template <class K, class V> struct FlatMap {
-    std::vector<K> keys; std::vector<V> vals; std::vector<uint8_t> used;
+    struct Entry { K key; V val; bool used; };          // one cache line per probe, like a SwissTable bucket
+    std::vector<Entry> e;
     size_t n = 0, cap = 0;
-    void reserve_pow2(size_t c) { cap = c; keys.assign(c, K()); vals.assign(c, V()); used.assign(c, 0); n = 0; }
+    uint64_t salt = next_salt();
+    void reserve_pow2(size_t c) { cap = c; e.assign(c, Entry{K(), V(), false}); n = 0; }
     size_t size() const { return n; }
     void grow() {
-        FlatMap bigger; bigger.reserve_pow2(cap ? cap * 2 : 16);
-        for (size_t i = 0; i < cap; i++) if (used[i]) *bigger.slot(keys[i]) = std::move(vals[i]);
+        FlatMap bigger; bigger.salt = salt; bigger.reserve_pow2(cap ? cap * 2 : 16);
+        for (size_t i = 0; i < cap; i++) if (e[i].used) *bigger.slot(e[i].key) = std::move(e[i].val);
         *this = std::move(bigger);
     }
     // returns pointer to value; *inserted tells whether key was new
     V* slot(const K& k, bool* inserted = nullptr) {
         if (cap == 0 || (n + 1) * 8 > cap * 7) grow();
-        size_t m = cap - 1, i = hash_key(k) & m;
-        while (used[i]) {
-            if (keys[i] == k) { if (inserted) *inserted = false; return &vals[i]; }
+        size_t m = cap - 1, i = hash_key(k ^ (K)salt) & m;
+        while (e[i].used) {
+            if (e[i].key == k) { if (inserted) *inserted = false; return &e[i].val; }
             i = (i + 1) & m;
         }
-        used[i] = 1; keys[i] = k; n++;
+        e[i].used = true; e[i].key = k; n++;
         if (inserted) *inserted = true;
-        return &vals[i];
+        return &e[i].val;
     }
-    V* find(const K& k) {
-        if (!cap) return nullptr;
-        size_t m = cap - 1, i = hash_key(k) & m;
-        while (used[i]) { if (keys[i] == k) return &vals[i]; i = (i + 1) & m; }
-        return nullptr;
-    }
+    // iteration in slot order (the analogue of hashbrown's arbitrary iteration order)
+    template <class F> void for_each(F f) { for (size_t i = 0; i < cap; i++) if (e[i].used) f(e[i].key, e[i].val); }
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -429,12 +435,11 @@ template <class IntT> struct MergeSkaDict {
     void append(SkaDict<IntT>& other) {
         if (other.k != k) throw std::runtime_error("K-mer lengths do not match");
         if (other.rc != rc) throw std::runtime_error("Strand use inconsistent");
-        for (size_t i = 0; i < other.split_kmers.cap; i++) {
-            if (!other.split_kmers.used[i]) continue;
-            bool ins; std::vector<uint8_t>* row = split_kmers.slot(other.split_kmers.keys[i], &ins);
+        other.split_kmers.for_each([&](const IntT& key, uint8_t& base) {
+            bool ins; std::vector<uint8_t>* row = split_kmers.slot(key, &ins);
             if (ins) row->assign(n_samples, 0);
-            (*row)[other.sample_idx] = other.split_kmers.vals[i];
-        }
+            (*row)[other.sample_idx] = base;
+        });
     }
     // merge_ska_dict.rs:119-151
     void merge(MergeSkaDict& other) {
@@ -442,13 +447,11 @@ template <class IntT> struct MergeSkaDict {
         if (other.k != k) throw std::runtime_error("K-mer lengths do not match");
         if (other.rc != rc) throw std::runtime_error("Strand use inconsistent");
         if (split_kmers.size() == 0) { split_kmers = std::move(other.split_kmers); return; }
-        for (size_t i = 0; i < other.split_kmers.cap; i++) {
-            if (!other.split_kmers.used[i]) continue;
-            bool ins; std::vector<uint8_t>* row = split_kmers.slot(other.split_kmers.keys[i], &ins);
-            std::vector<uint8_t>& o = other.split_kmers.vals[i];
+        other.split_kmers.for_each([&](const IntT& key, std::vector<uint8_t>& o) {
+            bool ins; std::vector<uint8_t>* row = split_kmers.slot(key, &ins);
             if (ins) *row = std::move(o);
             else for (size_t j = 0; j < n_samples; j++) (*row)[j] |= o[j];
-        }
+        });
     }
 };
 
@@ -495,12 +498,13 @@ struct Array {          // key type erased to u128 so one handle type serves k<=
     // merge_ska_array.rs:166-186 (rows emitted in ascending key order: canonical order)
     template <class IntT> void from_dict(MergeSkaDict<IntT>& d) {
         k = d.k; rc = d.rc; n_samples = d.n_samples; key_bits = UIntOps<IntT>::BITS;
-        std::vector<std::pair<IntT, size_t>> order;
-        for (size_t i = 0; i < d.split_kmers.cap; i++) if (d.split_kmers.used[i]) order.push_back({d.split_kmers.keys[i], i});
-        std::sort(order.begin(), order.end());
+        std::vector<std::pair<IntT, std::vector<uint8_t>*>> order;
+        order.reserve(d.split_kmers.size());
+        d.split_kmers.for_each([&](const IntT& key, std::vector<uint8_t>& row) { order.push_back({key, &row}); });
+        std::sort(order.begin(), order.end(), [](const auto& a, const auto& b) { return a.first < b.first; });
         split_kmers.reserve(order.size()); variants.reserve(order.size() * n_samples);
         for (auto& kv : order) {
-            std::vector<uint8_t>& bases = d.split_kmers.vals[kv.second];
+            std::vector<uint8_t>& bases = *kv.second;
             split_kmers.push_back((u128)kv.first);
             uint64_t c = 0;
             for (uint8_t b : bases) if (b != 0 && b != '-') c++;

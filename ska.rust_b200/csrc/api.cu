@@ -1,0 +1,400 @@
+// api.cu -- the extern "C" surface of libskagpu.so (include/skagpu.h) and its host-side plumbing:
+// device context, stage timers, host->device staging of sequence batches, handle lifetime.
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <memory>
+
+#include "../../include/skagpu.h"
+#include "common.cuh"
+
+namespace ska {
+
+static Context g_ctx;
+Context& ctx() { return g_ctx; }
+void Context::ensure() {
+    if (init) return;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0)
+        throw Error(std::string("no CUDA device available (libskagpu has no CPU fallback): ") + cudaGetErrorString(e));
+    SKA_CUDA(cudaSetDevice(device));
+    cudaDeviceProp p;
+    SKA_CUDA(cudaGetDeviceProperties(&p, device));
+    if (p.major < 10) throw Error("libskagpu is built for sm_100a (B200) only; found compute capability " +
+                                  std::to_string(p.major) + "." + std::to_string(p.minor));
+    sm_count = p.multiProcessorCount;
+    smem_optin = p.sharedMemPerBlockOptin;
+    SKA_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+    // keep freed blocks in the pool: repeated builds should not pay cudaMalloc again
+    cudaMemPool_t pool;
+    SKA_CUDA(cudaDeviceGetDefaultMemPool(&pool, device));
+    uint64_t thr = UINT64_MAX;
+    SKA_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr));
+    init = true;
+}
+
+static StageTimer g_timer;
+StageTimer& timer() { return g_timer; }
+void StageTimer::clear() {
+    for (auto& s : stages) { cudaEventDestroy(s.beg); cudaEventDestroy(s.end); }
+    stages.clear();
+}
+void StageTimer::begin(const char* name) {
+    Stage s; s.name = name; s.launches = 0;
+    SKA_CUDA(cudaEventCreate(&s.beg)); SKA_CUDA(cudaEventCreate(&s.end));
+    SKA_CUDA(cudaEventRecord(s.beg, ctx().stream));
+    launch_mark = ctx().launches;
+    stages.push_back(s);
+}
+void StageTimer::end() {
+    Stage& s = stages.back();
+    SKA_CUDA(cudaEventRecord(s.end, ctx().stream));
+    s.launches = ctx().launches - launch_mark;
+}
+
+__global__ void set_start_bits_kernel(const uint64_t* __restrict__ starts, uint64_t n, uint32_t* __restrict__ bits) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint64_t p = starts[i] + FRONT_PAD;
+    atomicOr(&bits[p >> 5], 1u << (p & 31));
+}
+
+static void check_k(uint32_t k) {
+    if (k < 5 || k > 63 || (k % 2) == 0) throw Error("Invalid k-mer length");      // ska_dict.rs:342-344
+}
+
+// Host -> device staging of the parsed records of all samples.
+static std::unique_ptr<SeqBatch> upload(const ska_input_t* in, size_t n, double proportion_reads) {
+    Context& c = ctx();
+    c.ensure();
+    if (n == 0) throw Error("no input samples");
+    if (n > 65535) throw Error("at most 65535 samples per build (16-bit sample ids)");
+    std::unique_ptr<SeqBatch> b(new SeqBatch());
+    b->n_samples = n;
+    b->h_sample_off.assign(n + 1, 0);
+    bool any_qual = false, all_qual = true;
+    uint64_t n_rec_total = 0;
+    for (size_t s = 0; s < n; s++) {
+        if (in[s].n_rec == 0 || !in[s].rec_off || !in[s].seq) throw Error("Invalid FASTA/Q record");   // ska_dict.rs:358-360
+        if (in[s].n_rec_file1 > in[s].n_rec) throw Error("n_rec_file1 > n_rec");
+        b->h_sample_off[s + 1] = b->h_sample_off[s] + (in[s].rec_off[in[s].n_rec] - in[s].rec_off[0]);
+        any_qual |= in[s].qual != nullptr; all_qual &= in[s].qual != nullptr;
+        n_rec_total += in[s].n_rec;
+    }
+    if (any_qual && !all_qual) throw Error("mixed FASTA and FASTQ samples in one build are not supported on the device path");
+    b->has_qual = any_qual;
+    b->n_pos = b->h_sample_off[n];
+    const size_t padded = padded_positions(b->n_pos);
+    b->seq.alloc(padded);
+    // pads are 'N': invalid bases, so no window can reach outside the batch
+    SKA_CUDA(cudaMemsetAsync(b->seq.p, 'N', FRONT_PAD, c.stream));
+    SKA_CUDA(cudaMemsetAsync(b->seq.p + FRONT_PAD + b->n_pos, 'N', padded - FRONT_PAD - b->n_pos, c.stream));
+    if (b->has_qual) { b->qual.alloc(padded); SKA_CUDA(cudaMemsetAsync(b->qual.p, '!', padded, c.stream)); }
+
+    size_t step = 1;
+    if (proportion_reads > 0) step = (size_t)std::llround(1.0 / proportion_reads);      // ska_dict.rs:125-129
+    if (step == 0) step = 1;
+    std::vector<uint64_t> starts; starts.reserve(n_rec_total + 1);
+    for (size_t s = 0; s < n; s++) {
+        const uint64_t base = b->h_sample_off[s], r0 = in[s].rec_off[0];
+        const uint64_t len = b->h_sample_off[s + 1] - base;
+        if (step == 1) {
+            if (len) {
+                SKA_CUDA(cudaMemcpyAsync(b->seq.p + FRONT_PAD + base, in[s].seq + r0, len, cudaMemcpyHostToDevice, c.stream));
+                if (b->has_qual)
+                    SKA_CUDA(cudaMemcpyAsync(b->qual.p + FRONT_PAD + base, in[s].qual + r0, len, cudaMemcpyHostToDevice, c.stream));
+            }
+        } else {
+            // --proportion-reads: keep record i of each file iff i % step == 0 (ska_dict.rs:131-141);
+            // skipped records stay in the position space as runs of 'N' (they yield no window)
+            if (len) SKA_CUDA(cudaMemsetAsync(b->seq.p + FRONT_PAD + base, 'N', len, c.stream));
+            for (uint64_t r = 0; r < in[s].n_rec; r++) {
+                uint64_t idx_in_file = r < in[s].n_rec_file1 ? r : r - in[s].n_rec_file1;
+                if (idx_in_file % step) continue;
+                uint64_t o = in[s].rec_off[r] - r0, l = in[s].rec_off[r + 1] - in[s].rec_off[r];
+                if (!l) continue;
+                SKA_CUDA(cudaMemcpyAsync(b->seq.p + FRONT_PAD + base + o, in[s].seq + r0 + o, l, cudaMemcpyHostToDevice, c.stream));
+                if (b->has_qual)
+                    SKA_CUDA(cudaMemcpyAsync(b->qual.p + FRONT_PAD + base + o, in[s].qual + r0 + o, l, cudaMemcpyHostToDevice, c.stream));
+            }
+        }
+        for (uint64_t r = 0; r < in[s].n_rec; r++) starts.push_back(base + (in[s].rec_off[r] - r0));
+    }
+    starts.push_back(b->n_pos);                                   // end sentinel: "a record starts after the last base"
+    b->start_bits.alloc(padded / 32 + 1);
+    SKA_CUDA(cudaMemsetAsync(b->start_bits.p, 0, b->start_bits.bytes(), c.stream));
+    DevBuf<uint64_t> d_starts(starts.size());
+    SKA_CUDA(cudaMemcpyAsync(d_starts.p, starts.data(), starts.size() * 8, cudaMemcpyHostToDevice, c.stream));
+    SKA_LAUNCH(set_start_bits_kernel, (unsigned)((starts.size() + 255) / 256), 256, 0, d_starts.p, (uint64_t)starts.size(),
+               b->start_bits.p);
+    b->sample_off.alloc(n + 1);
+    SKA_CUDA(cudaMemcpyAsync(b->sample_off.p, b->h_sample_off.data(), (n + 1) * 8, cudaMemcpyHostToDevice, c.stream));
+    SKA_CUDA(cudaStreamSynchronize(c.stream));                   // `starts` (pageable) must outlive the copy
+    return b;
+}
+
+static std::unique_ptr<Array> build_from_batch(const SeqBatch& b, uint32_t k, bool rc, uint16_t min_count, uint8_t min_qual,
+                                               int qual_filter) {
+    Context& c = ctx();
+    check_k(k);
+    if (k > 31) throw Error("k > 31 (128-bit split k-mers) is not yet built on the device; use k <= 31");
+    if (b.has_qual) throw Error("FASTQ input (count/bloom filter, K2q) is not yet built on the device");
+    (void)min_count; (void)qual_filter;
+    DevBuf<uint64_t> rec(b.n_pos);
+    DevBuf<uint16_t> sid(b.n_pos);
+    DevBuf<uint32_t> valid(b.n_samples);
+    SKA_CUDA(cudaMemsetAsync(valid.p, 0, valid.bytes(), c.stream));
+    timer().begin("k1_extract");
+    launch_k1(b, k, rc, false, min_qual, rec.p, sid.p, valid.p);
+    timer().end();
+    std::vector<uint32_t> h_valid(b.n_samples);
+    SKA_CUDA(cudaMemcpyAsync(h_valid.data(), valid.p, valid.bytes(), cudaMemcpyDeviceToHost, c.stream));
+    std::unique_ptr<Array> a(new Array());
+    build_array_from_records(rec.p, sid.p, b.n_pos, b.n_samples, k, rc, *a);   // synchronises the stream
+    for (size_t s = 0; s < b.n_samples; s++)
+        if (h_valid[s] == 0) throw Error("sample " + std::to_string(s) + " has no valid sequence");   // ska_dict.rs:374-376
+    return a;
+}
+
+}  // namespace ska
+
+// =================================================================================================
+using namespace ska;
+static thread_local std::string g_err;
+#define API_TRY try {
+#define API_CATCH                                         \
+    }                                                     \
+    catch (std::exception & e) { g_err = e.what(); return 1; } \
+    catch (...) { g_err = "unknown error"; return 1; }
+
+struct ska_array { Array a; };
+struct ska_seqbatch { std::unique_ptr<SeqBatch> b; };
+
+extern "C" {
+
+const char* skagpu_last_error(void) { return g_err.c_str(); }
+
+int skagpu_set_device(int device) {
+    API_TRY
+    if (ctx().init && ctx().device != device) throw Error("device already initialised; one process per GPU");
+    ctx().device = device;
+    ctx().ensure();
+    return 0;
+    API_CATCH
+}
+
+int skagpu_seqbatch_upload(const ska_input_t* inputs, size_t n_samples, double proportion_reads, ska_seqbatch_t** out) {
+    API_TRY
+    *out = nullptr;
+    std::unique_ptr<ska_seqbatch> h(new ska_seqbatch());
+    h->b = upload(inputs, n_samples, proportion_reads);
+    *out = h.release();
+    return 0;
+    API_CATCH
+}
+
+int skagpu_build_from_batch(const ska_seqbatch_t* batch, uint32_t k, int rc, uint16_t min_count, uint8_t min_qual,
+                            int qual_filter, ska_array_t** out) {
+    API_TRY
+    *out = nullptr;
+    ctx().ensure();
+    timer().clear();
+    std::unique_ptr<Array> a = build_from_batch(*batch->b, k, rc != 0, min_count, min_qual, qual_filter);
+    std::unique_ptr<ska_array> h(new ska_array());
+    h->a = std::move(*a);
+    *out = h.release();
+    return 0;
+    API_CATCH
+}
+
+void skagpu_seqbatch_free(ska_seqbatch_t* batch) { delete batch; }
+
+int skagpu_build(const ska_input_t* inputs, size_t n_samples, uint32_t k, int rc, uint16_t min_count, uint8_t min_qual,
+                 int qual_filter, double proportion_reads, ska_array_t** out) {
+    API_TRY
+    *out = nullptr;
+    check_k(k);
+    ctx().ensure();
+    timer().clear();
+    timer().begin("h2d");
+    std::unique_ptr<SeqBatch> b = upload(inputs, n_samples, proportion_reads);
+    timer().end();
+    std::unique_ptr<Array> a = build_from_batch(*b, k, rc != 0, min_count, min_qual, qual_filter);
+    std::unique_ptr<ska_array> h(new ska_array());
+    h->a = std::move(*a);
+    *out = h.release();
+    return 0;
+    API_CATCH
+}
+
+int skagpu_array_from_host(uint32_t k, int rc, uint32_t key_bits, uint64_t n_rows, uint64_t n_samples, const void* keys,
+                           const uint8_t* variants, const uint64_t* counts, ska_array_t** out) {
+    API_TRY
+    *out = nullptr;
+    Context& c = ctx();
+    c.ensure();
+    if (key_bits != 64 && key_bits != 128) throw Error("key_bits must be 64 or 128");
+    std::unique_ptr<ska_array> h(new ska_array());
+    Array& a = h->a;
+    a.k = k; a.rc = rc != 0; a.key_bits = key_bits; a.n_rows = a.n_keys = n_rows; a.n_samples = n_samples;
+    const size_t kw = key_bits / 64;
+    a.keys.alloc(n_rows * kw); a.variants.alloc(n_rows * n_samples); a.counts.alloc(n_rows);
+    std::vector<uint32_t> c32(n_rows);
+    for (uint64_t i = 0; i < n_rows; i++) c32[i] = (uint32_t)counts[i];
+    if (n_rows) {
+        SKA_CUDA(cudaMemcpyAsync(a.keys.p, keys, n_rows * kw * 8, cudaMemcpyHostToDevice, c.stream));
+        if (n_samples) SKA_CUDA(cudaMemcpyAsync(a.variants.p, variants, n_rows * n_samples, cudaMemcpyHostToDevice, c.stream));
+        SKA_CUDA(cudaMemcpyAsync(a.counts.p, c32.data(), n_rows * 4, cudaMemcpyHostToDevice, c.stream));
+    }
+    SKA_CUDA(cudaStreamSynchronize(c.stream));
+    *out = h.release();
+    return 0;
+    API_CATCH
+}
+
+int skagpu_dims(const ska_array_t* h, uint64_t* n_rows, uint64_t* n_keys, uint64_t* n_samples, uint32_t* k, int* rc,
+                uint32_t* key_bits) {
+    API_TRY
+    if (!h) throw Error("null array");
+    if (n_rows) *n_rows = h->a.n_rows;
+    if (n_keys) *n_keys = h->a.n_keys;
+    if (n_samples) *n_samples = h->a.n_samples;
+    if (k) *k = h->a.k;
+    if (rc) *rc = h->a.rc;
+    if (key_bits) *key_bits = h->a.key_bits;
+    return 0;
+    API_CATCH
+}
+
+int skagpu_filter(ska_array_t* h, uint64_t min_count, int filter_ambig_as_missing, int filter_type, int mask_ambig,
+                  int ignore_const_gaps, int update_kmers, int32_t* removed) {
+    API_TRY
+    if (!h) throw Error("null array");
+    ctx().ensure();
+    int32_t r = filter_array(h->a, min_count, filter_ambig_as_missing != 0, filter_type, mask_ambig != 0,
+                             ignore_const_gaps != 0, update_kmers != 0);
+    if (removed) *removed = r;
+    return 0;
+    API_CATCH
+}
+
+int skagpu_distance(const ska_array_t* h, double constant, int filt_ambig, ska_dist_t* out) {
+    API_TRY
+    if (!h) throw Error("null array");
+    ctx().ensure();
+    static_assert(sizeof(ska_dist_t) == sizeof(DistOut), "layout");
+    distance_array(h->a, constant, filt_ambig != 0, reinterpret_cast<DistOut*>(out));
+    return 0;
+    API_CATCH
+}
+
+int skagpu_export(const ska_array_t* h, void* keys, uint8_t* variants, uint64_t* counts) {
+    API_TRY
+    if (!h) throw Error("null array");
+    Context& c = ctx();
+    c.ensure();
+    const Array& a = h->a;
+    std::vector<uint32_t> c32;
+    if (keys && a.n_keys) SKA_CUDA(cudaMemcpyAsync(keys, a.keys.p, a.n_keys * (a.key_bits / 64) * 8, cudaMemcpyDeviceToHost, c.stream));
+    if (variants && a.n_rows * a.n_samples)
+        SKA_CUDA(cudaMemcpyAsync(variants, a.variants.p, a.n_rows * a.n_samples, cudaMemcpyDeviceToHost, c.stream));
+    if (counts && a.n_rows) {
+        c32.resize(a.n_rows);
+        SKA_CUDA(cudaMemcpyAsync(c32.data(), a.counts.p, a.n_rows * 4, cudaMemcpyDeviceToHost, c.stream));
+    }
+    SKA_CUDA(cudaStreamSynchronize(c.stream));
+    if (counts) for (uint64_t i = 0; i < a.n_rows; i++) counts[i] = c32[i];
+    return 0;
+    API_CATCH
+}
+
+int skagpu_export_transposed(const ska_array_t* h, uint8_t* out) {
+    API_TRY
+    if (!h) throw Error("null array");
+    Context& c = ctx();
+    c.ensure();
+    const Array& a = h->a;
+    if (a.n_rows * a.n_samples == 0) return 0;
+    DevBuf<uint8_t> t(a.n_rows * a.n_samples);
+    transpose_array(a, t.p);
+    if (out) SKA_CUDA(cudaMemcpyAsync(out, t.p, t.bytes(), cudaMemcpyDeviceToHost, c.stream));
+    SKA_CUDA(cudaStreamSynchronize(c.stream));
+    return 0;
+    API_CATCH
+}
+
+void skagpu_free(ska_array_t* h) { delete h; }
+
+void* skagpu_host_alloc(size_t bytes) {
+    void* p = nullptr;
+    try { ctx().ensure(); } catch (std::exception& e) { g_err = e.what(); return nullptr; }
+    if (cudaMallocHost(&p, bytes ? bytes : 1) != cudaSuccess) { g_err = "cudaMallocHost failed"; return nullptr; }
+    return p;
+}
+void skagpu_host_free(void* p) { if (p) cudaFreeHost(p); }
+
+int skagpu_last_timings(const char** names, float* ms, uint64_t* launches, int max_stages) {
+    int n = 0;
+    for (auto& s : timer().stages) {
+        if (n >= max_stages) break;
+        float t = 0;
+        if (cudaEventSynchronize(s.end) != cudaSuccess || cudaEventElapsedTime(&t, s.beg, s.end) != cudaSuccess) t = -1.f;
+        names[n] = s.name; ms[n] = t; if (launches) launches[n] = s.launches;
+        n++;
+    }
+    return n;
+}
+
+uint64_t skagpu_launch_count(void) { return ctx().launches; }
+
+int skagpu_stream_timer(int op, float* ms) {
+    API_TRY
+    static cudaEvent_t e0 = nullptr, e1 = nullptr;
+    Context& c = ctx();
+    c.ensure();
+    if (!e0) { SKA_CUDA(cudaEventCreate(&e0)); SKA_CUDA(cudaEventCreate(&e1)); }
+    if (op == 0) {
+        SKA_CUDA(cudaStreamSynchronize(c.stream));
+        SKA_CUDA(cudaEventRecord(e0, c.stream));
+    } else {
+        SKA_CUDA(cudaEventRecord(e1, c.stream));
+        SKA_CUDA(cudaEventSynchronize(e1));
+        float t = 0;
+        SKA_CUDA(cudaEventElapsedTime(&t, e0, e1));
+        if (ms) *ms = t;
+    }
+    return 0;
+    API_CATCH
+}
+
+int skagpu_k1_extract(const ska_seqbatch_t* batch, uint32_t k, int rc, uint8_t min_qual, int qual_filter, int iters,
+                      uint64_t* rec_out, uint64_t* n_positions, float* mean_ms) {
+    API_TRY
+    Context& c = ctx();
+    c.ensure();
+    check_k(k);
+    if (k > 31) throw Error("k > 31 not yet supported on the device");
+    const SeqBatch& b = *batch->b;
+    if (n_positions) *n_positions = b.n_pos;
+    DevBuf<uint64_t> rec(b.n_pos);
+    cudaEvent_t e0, e1;
+    SKA_CUDA(cudaEventCreate(&e0)); SKA_CUDA(cudaEventCreate(&e1));
+    if (iters < 1) iters = 1;
+    launch_k1(b, k, rc != 0, qual_filter == SKA_QUAL_STRICT, min_qual, rec.p, nullptr, nullptr);   // warm-up
+    SKA_CUDA(cudaEventRecord(e0, c.stream));
+    for (int i = 0; i < iters; i++) launch_k1(b, k, rc != 0, qual_filter == SKA_QUAL_STRICT, min_qual, rec.p, nullptr, nullptr);
+    SKA_CUDA(cudaEventRecord(e1, c.stream));
+    SKA_CUDA(cudaEventSynchronize(e1));
+    float ms = 0; SKA_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    if (mean_ms) *mean_ms = ms / iters;
+    if (rec_out && b.n_pos) {
+        SKA_CUDA(cudaMemcpyAsync(rec_out, rec.p, b.n_pos * 8, cudaMemcpyDeviceToHost, c.stream));
+        SKA_CUDA(cudaStreamSynchronize(c.stream));
+    }
+    return 0;
+    API_CATCH
+}
+
+}  // extern "C"

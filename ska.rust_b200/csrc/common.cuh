@@ -1,0 +1,127 @@
+// common.cuh -- shared host/device helpers of libskagpu (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <cstdio>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+namespace ska {
+
+struct Error : std::runtime_error {
+    using std::runtime_error::runtime_error;
+};
+
+#define SKA_CUDA(call)                                                                                    \
+    do {                                                                                                  \
+        cudaError_t e__ = (call);                                                                         \
+        if (e__ != cudaSuccess)                                                                           \
+            throw ska::Error(std::string(#call) + " failed: " + cudaGetErrorString(e__) + " (" + __FILE__ + \
+                             ":" + std::to_string(__LINE__) + ")");                                       \
+    } while (0)
+
+// One context per process (one process per GPU).
+struct Context {
+    int device = 0;
+    bool init = false;
+    cudaStream_t stream = nullptr;
+    int sm_count = 148;
+    size_t smem_optin = 0;
+    uint64_t launches = 0;
+    void ensure();
+};
+Context& ctx();
+
+// Every kernel launch goes through this so the launch count claimed in bench.py is real.
+#define SKA_LAUNCH(kernel, grid, block, smem, ...)                         \
+    do {                                                                   \
+        kernel<<<(grid), (block), (smem), ska::ctx().stream>>>(__VA_ARGS__); \
+        ska::ctx().launches++;                                             \
+        SKA_CUDA(cudaGetLastError());                                      \
+    } while (0)
+
+// RAII device buffer (stream-ordered allocator keeps repeated builds cheap).
+template <class T> struct DevBuf {
+    T* p = nullptr;
+    size_t n = 0;
+    DevBuf() {}
+    explicit DevBuf(size_t count) { alloc(count); }
+    DevBuf(const DevBuf&) = delete;
+    DevBuf& operator=(const DevBuf&) = delete;
+    DevBuf(DevBuf&& o) noexcept : p(o.p), n(o.n) { o.p = nullptr; o.n = 0; }
+    DevBuf& operator=(DevBuf&& o) noexcept {
+        if (this != &o) { release(); p = o.p; n = o.n; o.p = nullptr; o.n = 0; }
+        return *this;
+    }
+    ~DevBuf() { release(); }
+    void alloc(size_t count) {
+        release();
+        n = count;
+        if (count) SKA_CUDA(cudaMallocAsync((void**)&p, count * sizeof(T), ctx().stream));
+    }
+    void release() {
+        if (p) cudaFreeAsync(p, ctx().stream);
+        p = nullptr; n = 0;
+    }
+    size_t bytes() const { return n * sizeof(T); }
+};
+
+// Stage timer: CUDA events on the library stream.
+struct StageTimer {
+    struct Stage { const char* name; cudaEvent_t beg, end; uint64_t launches; };
+    std::vector<Stage> stages;
+    uint64_t launch_mark = 0;
+    void clear();
+    void begin(const char* name);
+    void end();
+    ~StageTimer() { clear(); }
+};
+StageTimer& timer();
+
+static constexpr uint64_t REC_SENTINEL = ~0ULL;   // "no valid window starts here"
+static constexpr int FRONT_PAD = 128;             // bytes of 'N' before position 0 of a batch
+
+// Device-resident sequence batch: all samples' records concatenated in one position space.
+struct SeqBatch {
+    uint64_t n_pos = 0;               // total bases over all samples
+    uint64_t n_samples = 0;
+    bool has_qual = false;
+    DevBuf<uint8_t> seq;              // padded_positions(n_pos) bytes, pads are 'N'
+    DevBuf<uint8_t> qual;             // same layout when has_qual
+    DevBuf<uint32_t> start_bits;      // bit p set <=> a record starts at position p; bit n_pos set
+    DevBuf<uint64_t> sample_off;      // n_samples + 1 positions
+    std::vector<uint64_t> h_sample_off;
+};
+
+// Device-resident MergeSkaArray.
+struct Array {
+    uint32_t k = 0;
+    bool rc = false;
+    uint32_t key_bits = 64;
+    uint64_t n_rows = 0, n_keys = 0, n_samples = 0;
+    DevBuf<uint64_t> keys;            // n_keys * (key_bits/64) words, (lo,hi) for 128-bit
+    DevBuf<uint8_t> variants;         // n_rows * n_samples, row-major
+    DevBuf<uint32_t> counts;          // n_rows
+};
+
+// --- kernels' host launchers (one .cu each) ------------------------------------------------------
+// k1_extract.cu
+void launch_k1(const SeqBatch& b, uint32_t k, bool rc, bool strict_qual, uint8_t min_qual, uint64_t* rec_out,
+               uint16_t* sid_out, uint32_t* sample_valid);
+size_t padded_positions(uint64_t n_pos);
+// merge.cu
+void build_array_from_records(uint64_t* rec, uint16_t* sid, uint64_t n_pos, uint64_t n_samples, uint32_t k, bool rc,
+                              Array& out);
+// exclusive scan of n u32 counts into n+1 u64 offsets (off[n] = total); *max_out = max count
+void launch_scan_counts(const uint32_t* cnt, uint32_t n, uint64_t* off, uint32_t* max_out);
+// filter.cu
+int32_t filter_array(Array& a, uint64_t min_count, bool filter_ambig_as_missing, int filter_type, bool mask_ambig,
+                     bool ignore_const_gaps, bool update_kmers);
+void transpose_array(const Array& a, uint8_t* d_out);
+// distance.cu
+struct DistOut { double distance, mismatch_prop; uint64_t match_count, mismatch_count; };
+void distance_array(const Array& a, double constant, bool filt_ambig, DistOut* h_out);
+
+}  // namespace ska

@@ -1,0 +1,228 @@
+// filter.cu -- K4: column-wise variant filter + order-preserving row compaction, and the
+// (rows x samples) -> (samples x rows) transpose used to write the alignment.
+//
+// Replaces MergeSkaArray::filter + update_counts (src/merge_ska_array.rs:289-402, 139-163; caller
+// apply_filters, src/generic_modes.rs:112-131) and the transpose in write_fasta
+// (src/merge_ska_array.rs:499-503).  The reference walks rows on one thread and allocates a
+// HashSet per row; here one warp classifies one row with ballots, a scan gives every surviving
+// row its destination, and a second kernel moves rows (applying --ambig-mask on the way).
+//
+// Semantics kept exactly:
+//  * filter_ambig_as_missing: recount non-missing as "not '-' and not ambiguous", drop rows with
+//    zero count *and their keys* first (update_counts always compacts split_kmers);
+//  * row kept iff count >= min_count and
+//      NoFilter: always | NoConst: >1 distinct byte values ('-' counts unless ignore_const_gaps)
+//      NoAmbig: no byte outside {A,C,G,T,U,-} case-insensitively
+//      NoAmbigOrConst: >1 distinct byte values among {ACGTUacgtu} (+ '-' unless ignore_const_gaps)
+//  * keys are compacted by the filter loop only if update_kmers; returned count = rows the filter
+//    loop removed (rows dropped by update_counts are not counted).
+// Roofline: HBM-bound, reads N+4 B per row twice, writes N B per surviving row.
+#include "common.cuh"
+
+namespace ska {
+
+constexpr int FL_THREADS = 256;
+constexpr int FL_ROWS = 128;   // rows per CTA (16 per warp)
+
+__device__ __forceinline__ bool is_ambig_dev(uint32_t b) {   // bit_encoding.rs:58-61
+    b |= 0x20u;
+    return !(b == 'a' || b == 'c' || b == 'g' || b == 't' || b == 'u' || b == '-');
+}
+// bit index among the 11 byte values that matter to NoAmbigOrConst, or 32 if none
+__device__ __forceinline__ uint32_t acgtu_bit(uint32_t b) {
+    switch (b) {
+        case 'A': return 0; case 'C': return 1; case 'G': return 2; case 'T': return 3; case 'U': return 4;
+        case 'a': return 5; case 'c': return 6; case 'g': return 7; case 't': return 8; case 'u': return 9;
+        case '-': return 10; default: return 32;
+    }
+}
+
+// flags[r]: bit0 = survives update_counts stage, bit1 = survives the filter as well
+__global__ void __launch_bounds__(FL_THREADS)
+filter_flags_kernel(const uint8_t* __restrict__ var, const uint32_t* __restrict__ cnt, uint64_t n_rows, uint32_t n_samples,
+                    uint64_t min_count, int ambig_missing, int ftype, int ignore_gaps, uint8_t* __restrict__ flags,
+                    uint32_t* __restrict__ new_cnt, uint32_t* __restrict__ cta_keep1, uint32_t* __restrict__ cta_keep2) {
+    __shared__ uint32_t s_k1, s_k2;
+    if (threadIdx.x == 0) { s_k1 = 0; s_k2 = 0; }
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint64_t r0 = (uint64_t)blockIdx.x * FL_ROWS;
+    uint32_t k1 = 0, k2 = 0;
+    for (int rr = warp; rr < FL_ROWS; rr += FL_THREADS / 32) {
+        const uint64_t r = r0 + rr;
+        if (r >= n_rows) break;
+        const uint8_t* row = var + r * n_samples;
+        uint32_t good = 0;          // not '-' and not ambiguous
+        uint32_t any_ambig = 0;
+        uint32_t setbits = 0;       // NoAmbigOrConst value set
+        uint32_t first = 0xFFFFFFFFu;   // first considered byte value seen by this lane (NoConst)
+        uint32_t differs = 0;
+        for (uint32_t s = lane; s < n_samples; s += 32) {
+            uint32_t b = row[s];
+            bool amb = is_ambig_dev(b);
+            any_ambig |= amb;
+            good += (b != '-' && !amb);
+            uint32_t bit = acgtu_bit(b);
+            if (bit < 32) setbits |= 1u << bit;
+            if (!ignore_gaps || b != '-') {
+                if (first == 0xFFFFFFFFu) first = b; else differs |= (b != first);
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            good += __shfl_xor_sync(0xFFFFFFFFu, good, o);
+            setbits |= __shfl_xor_sync(0xFFFFFFFFu, setbits, o);
+        }
+        any_ambig = __any_sync(0xFFFFFFFFu, any_ambig);
+        // NoConst: reference value = first considered byte of the lowest lane that has one
+        uint32_t have = __ballot_sync(0xFFFFFFFFu, first != 0xFFFFFFFFu);
+        uint32_t ref = have ? __shfl_sync(0xFFFFFFFFu, first, __ffs(have) - 1) : 0xFFFFFFFFu;
+        differs |= (first != 0xFFFFFFFFu && first != ref);
+        bool nonconst = __any_sync(0xFFFFFFFFu, differs);
+
+        uint32_t count = ambig_missing ? good : cnt[r];
+        bool keep1 = !ambig_missing || good > 0;
+        bool keep2 = false;
+        if (keep1 && (uint64_t)count >= min_count) {
+            switch (ftype) {
+                case 0: keep2 = true; break;
+                case 1: keep2 = nonconst; break;
+                case 2: keep2 = !any_ambig; break;
+                default: {
+                    uint32_t relevant = ignore_gaps ? 0x3FFu : 0x7FFu;
+                    keep2 = __popc(setbits & relevant) > 1;
+                }
+            }
+        }
+        if (lane == 0) {
+            flags[r] = (uint8_t)((keep1 ? 1 : 0) | (keep2 ? 2 : 0));
+            new_cnt[r] = count;
+            k1 += keep1; k2 += keep2;
+        }
+    }
+    if (lane == 0) { atomicAdd(&s_k1, k1); atomicAdd(&s_k2, k2); }
+    __syncthreads();
+    if (threadIdx.x == 0) { cta_keep1[blockIdx.x] = s_k1; cta_keep2[blockIdx.x] = s_k2; }
+}
+
+// moves surviving rows/counts/keys to their compacted positions (order preserving)
+__global__ void __launch_bounds__(FL_THREADS)
+filter_scatter_kernel(const uint8_t* __restrict__ var, const uint32_t* __restrict__ new_cnt, const uint64_t* __restrict__ keys,
+                      const uint8_t* __restrict__ flags, const uint64_t* __restrict__ off1, const uint64_t* __restrict__ off2,
+                      uint64_t n_rows, uint64_t n_keys_in, uint32_t n_samples, int key_words, int key_mode /*0 none,1 stage1,2 stage2*/,
+                      int mask_ambig, uint8_t* __restrict__ out_var, uint32_t* __restrict__ out_cnt,
+                      uint64_t* __restrict__ out_keys) {
+    __shared__ uint32_t s_pos1[FL_ROWS], s_pos2[FL_ROWS];
+    const uint64_t r0 = (uint64_t)blockIdx.x * FL_ROWS;
+    // in-CTA exclusive prefix of the two flag bits (FL_ROWS = 128 rows -> 4 warps of ballots)
+    __shared__ uint32_t s_w1[4], s_w2[4];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t f = 0;
+    if (threadIdx.x < FL_ROWS && r0 + threadIdx.x < n_rows) f = flags[r0 + threadIdx.x];
+    if (threadIdx.x < FL_ROWS) {
+        uint32_t b1 = __ballot_sync(0xFFFFFFFFu, f & 1), b2 = __ballot_sync(0xFFFFFFFFu, f & 2);
+        uint32_t lt = (1u << lane) - 1u;
+        s_pos1[threadIdx.x] = __popc(b1 & lt);
+        s_pos2[threadIdx.x] = __popc(b2 & lt);
+        if (lane == 0) { s_w1[warp] = __popc(b1); s_w2[warp] = __popc(b2); }
+    }
+    __syncthreads();
+    if (threadIdx.x < FL_ROWS) {
+        uint32_t a1 = 0, a2 = 0;
+        for (int w = 0; w < warp; w++) { a1 += s_w1[w]; a2 += s_w2[w]; }
+        s_pos1[threadIdx.x] += a1; s_pos2[threadIdx.x] += a2;
+    }
+    __syncthreads();
+    const uint64_t base1 = off1[blockIdx.x], base2 = off2[blockIdx.x];
+    // keys + counts: one thread per row
+    if (threadIdx.x < FL_ROWS) {
+        uint64_t r = r0 + threadIdx.x;
+        if (r < n_rows) {
+            if ((f & 2)) out_cnt[base2 + s_pos2[threadIdx.x]] = new_cnt[r];
+            if (out_keys && r < n_keys_in) {
+                bool kk = key_mode == 1 ? (f & 1) : (key_mode == 2 ? (f & 2) : false);
+                uint64_t dstk = key_mode == 1 ? base1 + s_pos1[threadIdx.x] : base2 + s_pos2[threadIdx.x];
+                if (kk) for (int w = 0; w < key_words; w++) out_keys[dstk * key_words + w] = keys[r * key_words + w];
+            }
+        }
+    }
+    // rows: one warp per row
+    for (int rr = warp; rr < FL_ROWS; rr += FL_THREADS / 32) {
+        uint64_t r = r0 + rr;
+        if (r >= n_rows) break;
+        if (!(flags[r] & 2)) continue;
+        const uint8_t* src = var + r * n_samples;
+        uint8_t* dst = out_var + (base2 + s_pos2[rr]) * n_samples;
+        for (uint32_t s = lane; s < n_samples; s += 32) {
+            uint32_t b = src[s];
+            if (mask_ambig && is_ambig_dev(b)) b = 'N';          // merge_ska_array.rs:388-399
+            dst[s] = (uint8_t)b;
+        }
+    }
+}
+
+int32_t filter_array(Array& a, uint64_t min_count, bool filter_ambig_as_missing, int filter_type, bool mask_ambig,
+                     bool ignore_const_gaps, bool update_kmers) {
+    Context& c = ctx();
+    if (filter_type < 0 || filter_type > 3) throw Error("invalid filter type");
+    const uint64_t R = a.n_rows;
+    const uint32_t N = (uint32_t)a.n_samples;
+    const int kw = a.key_bits / 64;
+    if (R == 0) return 0;
+    const uint32_t n_cta = (uint32_t)((R + FL_ROWS - 1) / FL_ROWS);
+    DevBuf<uint8_t> flags(R);
+    DevBuf<uint32_t> new_cnt(R), keep1(n_cta), keep2(n_cta), scratch(1);
+    DevBuf<uint64_t> off1(n_cta + 1), off2(n_cta + 1);
+    SKA_LAUNCH(filter_flags_kernel, n_cta, FL_THREADS, 0, a.variants.p, a.counts.p, R, N, min_count,
+               filter_ambig_as_missing ? 1 : 0, filter_type, ignore_const_gaps ? 1 : 0, flags.p, new_cnt.p, keep1.p, keep2.p);
+    launch_scan_counts(keep1.p, n_cta, off1.p, scratch.p);
+    launch_scan_counts(keep2.p, n_cta, off2.p, scratch.p);
+    uint64_t n1 = 0, n2 = 0;
+    SKA_CUDA(cudaMemcpyAsync(&n1, off1.p + n_cta, 8, cudaMemcpyDeviceToHost, c.stream));
+    SKA_CUDA(cudaMemcpyAsync(&n2, off2.p + n_cta, 8, cudaMemcpyDeviceToHost, c.stream));
+    SKA_CUDA(cudaStreamSynchronize(c.stream));
+
+    // which key compaction applies: the filter loop's (update_kmers) wins over update_counts'
+    const bool keys_match_rows = a.n_keys == a.n_rows;   // false only after an earlier update_kmers=false filter
+    int key_mode = update_kmers ? 2 : (filter_ambig_as_missing ? 1 : 0);
+    if (key_mode && !keys_match_rows)
+        throw Error("cannot compact split k-mers: keys no longer correspond to rows (earlier filter ran with update_kmers=false)");
+    DevBuf<uint8_t> out_var(n2 * N);
+    DevBuf<uint32_t> out_cnt(n2);
+    DevBuf<uint64_t> out_keys;
+    uint64_t n_keys_out = a.n_keys;
+    if (key_mode) { n_keys_out = key_mode == 1 ? n1 : n2; out_keys.alloc(n_keys_out * kw); }
+    SKA_LAUNCH(filter_scatter_kernel, n_cta, FL_THREADS, 0, a.variants.p, new_cnt.p, a.keys.p, flags.p, off1.p, off2.p, R,
+               a.n_keys, N, kw, key_mode, mask_ambig ? 1 : 0, out_var.p, out_cnt.p, key_mode ? out_keys.p : (uint64_t*)nullptr);
+    a.variants = std::move(out_var);
+    a.counts = std::move(out_cnt);
+    if (key_mode) { a.keys = std::move(out_keys); a.n_keys = n_keys_out; }
+    a.n_rows = n2;
+    return (int32_t)(n1 - n2);
+}
+
+// ---- transpose (rows x samples) -> (samples x rows)
+constexpr int TP_TILE = 64;
+__global__ void __launch_bounds__(256)
+transpose_kernel(const uint8_t* __restrict__ in, uint64_t n_rows, uint32_t n_samples, uint8_t* __restrict__ out) {
+    __shared__ uint8_t tile[TP_TILE][TP_TILE + 4];
+    const uint64_t r0 = (uint64_t)blockIdx.x * TP_TILE;
+    const uint32_t s0 = blockIdx.y * TP_TILE;
+    for (int idx = threadIdx.x; idx < TP_TILE * TP_TILE; idx += 256) {
+        int r = idx / TP_TILE, s = idx % TP_TILE;
+        if (r0 + r < n_rows && s0 + s < n_samples) tile[r][s] = in[(r0 + r) * n_samples + s0 + s];
+    }
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < TP_TILE * TP_TILE; idx += 256) {
+        int s = idx / TP_TILE, r = idx % TP_TILE;
+        if (r0 + r < n_rows && s0 + s < n_samples) out[(uint64_t)(s0 + s) * n_rows + r0 + r] = tile[r][s];
+    }
+}
+
+void transpose_array(const Array& a, uint8_t* d_out) {
+    if (a.n_rows == 0 || a.n_samples == 0) return;
+    dim3 grid((unsigned)((a.n_rows + TP_TILE - 1) / TP_TILE), (unsigned)((a.n_samples + TP_TILE - 1) / TP_TILE));
+    SKA_LAUNCH(transpose_kernel, grid, 256, 0, a.variants.p, a.n_rows, (uint32_t)a.n_samples, d_out);
+}
+
+}  // namespace ska

@@ -1,0 +1,264 @@
+// k1_extract.cu -- K1: split-k-mer extraction with canonical strand select (sm_100a).
+//
+// Replaces the per-base hot loop of the reference: SplitKmer::build / roll_fwd / update_rc /
+// get_curr_kmer (src/ska_dict/split_kmer.rs:78-217, 281-295) driven by SkaDict::add_file_kmers
+// (src/ska_dict.rs:118-180), with the 2-bit codec of src/ska_dict/bit_encoding.rs:34-54.
+//
+// Formulation: every window is a pure function of its k bases, so there is
+// no sequential roll.  One CTA owns a tile of K1_T consecutive window-start positions of the
+// batch's global position space:
+//   1. TMA bulk copy (cp.async.bulk -> UBLKCP) of the tile's ASCII bytes + halo into shared memory;
+//   2. pack: 32 bases/thread -> 2-bit words in BOTH orientations (LE: base i at bits 2i, BE: first
+//      base most significant) + an "invalid base" bit mask (N/n test `b & 0xF == 14`, optionally
+//      the strict quality test `qual-33 > min_qual`);
+//   3. window-validity words by sliding-OR bit tricks over the invalid mask and the record-start
+//      mask (windows may not contain an invalid base nor span a record boundary; a run of exactly
+//      k valid bases that ends at its record's end yields nothing -- split_kmer.rs:89,121);
+//   4. extract: lane l of a warp takes window 32j+l, so the 8-byte record stores are coalesced;
+//      forward k-mer = funnel shift out of the BE stream, reverse complement = funnel shift out of
+//      the LE stream XOR 0b10 per base (no bit reversal per window); key = k-mer with the middle
+//      base squeezed out; canonical = min(key, rc_key), ties keep forward (split_kmer.rs:290).
+// Output: one u64 per position, rec = key << 4 | 1 << middle_code, or REC_SENTINEL.
+//
+// Roofline: HBM-bound, 1 B read + 8 B written per base (DESIGN.md "K1").
+#include "common.cuh"
+
+namespace ska {
+
+constexpr int K1_T = 4096;                       // window-start positions per CTA
+constexpr int K1_THREADS = 256;
+constexpr int K1_LEAD = 32;                      // staged bytes before the tile
+constexpr int K1_TAIL = 96;                      // staged bytes after the tile (>= k for k <= 63, 32-aligned)
+constexpr int K1_BYTES = K1_LEAD + K1_T + K1_TAIL;
+constexpr int K1_G32 = K1_BYTES / 32;            // groups of 32 bases in the staged region
+
+size_t padded_positions(uint64_t n_pos) { return FRONT_PAD + ((n_pos + K1_T - 1) / K1_T) * K1_T + 256; }
+
+struct B128 { uint64_t lo, hi; };
+__device__ __forceinline__ B128 shr128(B128 v, int n) {   // 0 <= n < 64
+    B128 r;
+    r.lo = n ? (v.lo >> n) | (v.hi << (64 - n)) : v.lo;
+    r.hi = v.hi >> n;
+    return r;
+}
+__device__ __forceinline__ B128 or128(B128 a, B128 b) { return {a.lo | b.lo, a.hi | b.hi}; }
+// bit n of result = OR of v[n .. n+len-1]
+__device__ __forceinline__ B128 slide_or(B128 v, int len) {
+    int covered = 1;
+    while (covered * 2 <= len) { v = or128(v, shr128(v, covered)); covered *= 2; }
+    if (covered < len) v = or128(v, shr128(v, len - covered));
+    return v;
+}
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void tma_load_1d(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* mbar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(
+                     smem_u32(smem_dst)),
+                 "l"(gsrc), "r"(bytes), "r"(smem_u32(mbar))
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_init(uint64_t* mbar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(mbar)), "r"(count));
+    asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* mbar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(mbar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* mbar, uint32_t parity) {
+    uint32_t done;
+    do {
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, p;\n"
+            "}\n"
+            : "=r"(done)
+            : "r"(smem_u32(mbar)), "r"(parity)
+            : "memory");
+    } while (!done);
+}
+
+// 4 ASCII bases in a u32 -> 8 bits of 2-bit codes, base i at bits 2i   ((b >> 1) & 3, bit_encoding.rs:34-36)
+__device__ __forceinline__ uint32_t pack4(uint32_t w) {
+    uint32_t c = (w >> 1) & 0x03030303u;
+    uint32_t x = c | (c >> 6);
+    return (x | (x >> 12)) & 0xFFu;
+}
+// 4 ASCII bases -> 4 bits, bit i set iff base i is invalid ((b & 0xF) == 14, bit_encoding.rs:52-54)
+__device__ __forceinline__ uint32_t bad4(uint32_t w) {
+    uint32_t t = (w & 0x0F0F0F0Fu) ^ 0x0E0E0E0Eu;            // zero byte <=> invalid
+    uint32_t z = ~(t + 0x7F7F7F7Fu) & 0x80808080u;           // bit 7 of byte set <=> byte was zero
+    uint32_t m = z >> 7;
+    m |= m >> 7;
+    return (m | (m >> 14)) & 0xFu;
+}
+// 4 quality bytes -> 4 bits, bit i set iff NOT (qual - 33 > min_qual)   (split_kmer.rs:66-71, u8 wrap)
+__device__ __forceinline__ uint32_t badq4(uint32_t q, uint32_t min_qual) {
+    uint32_t r = 0;
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        uint32_t v = ((q >> (8 * i)) - 33u) & 0xFFu;
+        r |= (v > min_qual ? 0u : 1u) << i;
+    }
+    return r;
+}
+// 16 bases LE (base i at bits 2i) -> BE (base i at bits 30-2i)
+__device__ __forceinline__ uint32_t le_to_be(uint32_t x) {
+    uint32_t y = __brev(x);
+    return ((y & 0x55555555u) << 1) | ((y >> 1) & 0x55555555u);
+}
+
+template <bool HAS_QUAL>
+__global__ void __launch_bounds__(K1_THREADS)
+k1_extract_kernel(const uint8_t* __restrict__ seq, const uint8_t* __restrict__ qual,
+                  const uint32_t* __restrict__ start_bits, const uint64_t* __restrict__ sample_off,
+                  uint32_t n_samples, uint64_t n_pos, int k, int rc, uint32_t min_qual,
+                  uint64_t* __restrict__ rec_out, uint16_t* __restrict__ sid_out, uint32_t* __restrict__ sample_valid) {
+    __shared__ __align__(128) uint8_t s_ascii[K1_BYTES];
+    __shared__ __align__(128) uint8_t s_qual[HAS_QUAL ? K1_BYTES : 16];
+    __shared__ uint32_t s_le[2 * K1_G32 + 2];
+    __shared__ uint32_t s_be[2 * K1_G32 + 2];
+    __shared__ uint32_t s_bad[K1_G32];
+    __shared__ uint32_t s_start[K1_G32];
+    __shared__ uint32_t s_ok[K1_T / 32];
+    __shared__ __align__(8) uint64_t s_mbar;
+    __shared__ uint32_t s_sid[2];
+    __shared__ uint32_t s_nvalid;
+
+    const int tid = threadIdx.x;
+    const uint64_t t0 = (uint64_t)blockIdx.x * K1_T;        // first window-start position of this tile
+    // staged region covers positions [t0 - K1_LEAD, t0 + K1_T + K1_TAIL); position p lives at seq[FRONT_PAD + p]
+    const uint8_t* gsrc = seq + FRONT_PAD + t0 - K1_LEAD;
+
+    if (tid == 0) {
+        mbar_init(&s_mbar, 1);
+        s_nvalid = 0;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        mbar_expect_tx(&s_mbar, HAS_QUAL ? 2 * K1_BYTES : K1_BYTES);
+        tma_load_1d(s_ascii, gsrc, K1_BYTES, &s_mbar);
+        if (HAS_QUAL) tma_load_1d(s_qual, qual + FRONT_PAD + t0 - K1_LEAD, K1_BYTES, &s_mbar);
+        // sample ids of the first and last window of the tile (binary search over sample_off)
+        uint64_t pf = t0, pl = min(t0 + K1_T - 1, n_pos - 1);
+        uint32_t lo = 0, hi = n_samples;                    // find s with off[s] <= pf < off[s+1]
+        while (hi - lo > 1) { uint32_t m = (lo + hi) >> 1; if (sample_off[m] <= pf) lo = m; else hi = m; }
+        s_sid[0] = lo;
+        hi = n_samples;
+        while (hi - lo > 1) { uint32_t m = (lo + hi) >> 1; if (sample_off[m] <= pl) lo = m; else hi = m; }
+        s_sid[1] = lo;
+    }
+    // record-start bits for the staged region (word w <-> positions t0 - 32 + 32w ...)
+    if (tid < K1_G32) s_start[tid] = start_bits[(t0 + FRONT_PAD - K1_LEAD) / 32 + tid];
+    mbar_wait(&s_mbar, 0);
+
+    // ---- pack: 32 bases per thread
+    for (int g = tid; g < K1_G32; g += K1_THREADS) {
+        const uint4* src = reinterpret_cast<const uint4*>(s_ascii + 32 * g);
+        uint4 a = src[0], b = src[1];
+        uint32_t w[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+        uint32_t le0 = 0, le1 = 0, bad = 0;
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            le0 |= pack4(w[i]) << (8 * i);
+            le1 |= pack4(w[4 + i]) << (8 * i);
+            bad |= bad4(w[i]) << (4 * i);
+            bad |= bad4(w[4 + i]) << (16 + 4 * i);
+        }
+        if (HAS_QUAL) {
+            const uint4* qs = reinterpret_cast<const uint4*>(s_qual + 32 * g);
+            uint4 qa = qs[0], qb = qs[1];
+            uint32_t q[8] = {qa.x, qa.y, qa.z, qa.w, qb.x, qb.y, qb.z, qb.w};
+#pragma unroll
+            for (int i = 0; i < 8; i++) bad |= badq4(q[i], min_qual) << (4 * i);
+        }
+        s_le[2 * g] = le0; s_le[2 * g + 1] = le1;
+        s_be[2 * g] = le_to_be(le0); s_be[2 * g + 1] = le_to_be(le1);
+        s_bad[g] = bad;
+    }
+    if (tid < 2) { s_le[2 * K1_G32 + tid] = 0; s_be[2 * K1_G32 + tid] = 0; }
+    __syncthreads();
+
+    // ---- window validity: thread j -> windows at staged bits [32(j+1), 32(j+1)+32)
+    if (tid < K1_T / 32) {
+        const int j = tid;
+        B128 bad = {(uint64_t)s_bad[j] | ((uint64_t)s_bad[j + 1] << 32), (uint64_t)s_bad[j + 2] | ((uint64_t)s_bad[j + 3] << 32)};
+        B128 st = {(uint64_t)s_start[j] | ((uint64_t)s_start[j + 1] << 32), (uint64_t)s_start[j + 2] | ((uint64_t)s_start[j + 3] << 32)};
+        B128 bad_any = slide_or(bad, k);                          // any invalid base in [n, n+k)
+        B128 st_any = shr128(slide_or(st, k - 1), 1);             // any record start in (n, n+k)
+        B128 bad_prev = {bad.lo << 1, (bad.hi << 1) | (bad.lo >> 63)};   // bad[n-1]
+        B128 run_start = or128(st, bad_prev);                     // a valid run begins at n
+        B128 rec_end = shr128(st, k);                             // record ends right after the window
+        uint64_t not_ok = bad_any.lo | st_any.lo | (run_start.lo & rec_end.lo);   // split_kmer.rs:89,121
+        uint32_t ok = ~(uint32_t)(not_ok >> 32);
+        // windows at or beyond n_pos do not exist
+        uint64_t p0 = t0 + 32ull * j;
+        if (p0 >= n_pos) ok = 0;
+        else if (p0 + 32 > n_pos) ok &= (1u << (uint32_t)(n_pos - p0)) - 1u;
+        s_ok[j] = ok;
+        if (ok) atomicAdd(&s_nvalid, (uint32_t)__popc(ok));
+    }
+    __syncthreads();
+
+    // ---- extract
+    const int lane = tid & 31, warp = tid >> 5;
+    const int h = (k - 1) >> 1;
+    const uint64_t mask2k = (k == 32) ? ~0ULL : ((1ULL << (2 * k)) - 1ULL);
+    const uint64_t lm = (1ULL << (2 * h)) - 1ULL;                 // lower-arm mask
+    const uint64_t aa = 0xAAAAAAAAAAAAAAAAULL & mask2k;
+    const uint32_t sid_first = s_sid[0], sid_last = s_sid[1];
+    for (int j = warp; j < K1_T / 32; j += K1_THREADS / 32) {
+        const uint64_t p = t0 + 32ull * j + lane;
+        if (p >= n_pos) break;
+        const uint32_t ok = s_ok[j];
+        uint64_t rec = REC_SENTINEL;
+        if ((ok >> lane) & 1u) {
+            const int r = K1_LEAD + 32 * j + lane;                // staged index of the window's first base
+            const int wi = r >> 4, sh = 2 * (r & 15);
+            // forward k-mer, first base most significant
+            uint32_t b0 = s_be[wi], b1 = s_be[wi + 1], b2 = s_be[wi + 2];
+            uint64_t top = ((uint64_t)__funnelshift_l(b1, b0, sh) << 32) | __funnelshift_l(b2, b1, sh);
+            uint64_t F = top >> (64 - 2 * k);
+            // LE window: base r at bit 0 -> XOR 0b10 per base = reverse complement, first base most significant
+            uint32_t l0 = s_le[wi], l1 = s_le[wi + 1], l2 = s_le[wi + 2];
+            uint64_t V = (((uint64_t)__funnelshift_r(l1, l2, sh) << 32) | __funnelshift_r(l0, l1, sh)) & mask2k;
+            uint64_t key = (F & lm) | ((F >> 2) & ~lm);
+            uint32_t mid = (uint32_t)(F >> (2 * h)) & 3u;
+            if (rc) {
+                uint64_t R = V ^ aa;
+                uint64_t rkey = (R & lm) | ((R >> 2) & ~lm);
+                if (key > rkey) { key = rkey; mid ^= 2u; }       // ties keep forward (split_kmer.rs:290)
+            }
+            rec = (key << 4) | (1ull << mid);
+        }
+        rec_out[p] = rec;
+        uint32_t s = sid_first;
+        if (sid_first != sid_last) {                              // tile straddles samples (rare)
+            uint32_t lo = sid_first, hi = sid_last + 1;
+            while (hi - lo > 1) { uint32_t m = (lo + hi) >> 1; if (sample_off[m] <= p) lo = m; else hi = m; }
+            s = lo;
+            if (sample_valid && rec != REC_SENTINEL) atomicAdd(&sample_valid[s], 1u);
+        }
+        if (sid_out) sid_out[p] = (uint16_t)s;
+    }
+    // accepted windows per sample (a sample with none is an error, ska_dict.rs:374-376)
+    if (tid == 0 && sample_valid && sid_first == sid_last && s_nvalid) atomicAdd(&sample_valid[sid_first], s_nvalid);
+}
+
+void launch_k1(const SeqBatch& b, uint32_t k, bool rc, bool strict_qual, uint8_t min_qual, uint64_t* rec_out,
+               uint16_t* sid_out, uint32_t* sample_valid) {
+    if (b.n_pos == 0) return;
+    unsigned grid = (unsigned)((b.n_pos + K1_T - 1) / K1_T);
+    if (b.has_qual && strict_qual) {
+        SKA_LAUNCH(k1_extract_kernel<true>, grid, K1_THREADS, 0, b.seq.p, b.qual.p, b.start_bits.p, b.sample_off.p,
+                   (uint32_t)b.n_samples, b.n_pos, (int)k, rc ? 1 : 0, (uint32_t)min_qual, rec_out, sid_out, sample_valid);
+    } else {
+        SKA_LAUNCH(k1_extract_kernel<false>, grid, K1_THREADS, 0, b.seq.p, (const uint8_t*)nullptr, b.start_bits.p,
+                   b.sample_off.p, (uint32_t)b.n_samples, b.n_pos, (int)k, rc ? 1 : 0, (uint32_t)min_qual, rec_out, sid_out,
+                   sample_valid);
+    }
+}
+
+}  // namespace ska

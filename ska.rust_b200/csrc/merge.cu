@@ -1,0 +1,324 @@
+// merge.cu -- K2/K3: per-sample de-duplication with IUPAC merge + multi-sample merge into the dense
+// (n_kmers x n_samples) middle-base array, in ONE step.
+//
+// Replaces SkaDict::add_to_dict / add_palindrome_to_dict (src/ska_dict.rs:76-113, one hash-map probe
+// per base), MergeSkaDict::append / merge (src/merge_ska_dict.rs:77-151, one Vec<u8> per k-mer) and
+// MergeSkaArray::new (src/merge_ska_array.rs:166-186).
+//
+// Why one step: the per-sample IUPAC merge is a set union (bit_encoding.rs:354-369) and the
+// multi-sample merge is a byte-OR of disjoint columns, so both are the same commutative reduction
+// "OR the 4-bit base set of every window into cell (key, sample)".  The records K1 wrote
+// (key << 4 | one-hot middle, plus the sample id) are
+//   (1) partitioned by the top P bits of the key into 2^P buckets that are contiguous in HBM,
+//   (2) each bucket is reduced by one CTA in shared memory: open-addressing table key -> slot
+//       (atomicCAS), 4-bit set matrix slot x sample (atomicOr), then the bucket's distinct keys are
+//       sorted (bitonic) and written out as finished rows: key, N letters, non-missing count.
+// Because buckets are key ranges and rows inside a bucket are sorted, the array comes out in
+// ascending key order -- the canonical row order -- with no global sort of rows.
+// A first pass (count) sizes the output exactly and gives each bucket its row offset.
+//
+// Step (1) currently uses cub::DeviceRadixSort restricted to the P prefix bits (library code,
+// round-1 scaffolding; DESIGN.md "partition" lists its replacement).  Steps (2) are hand-written.
+#include <cub/cub.cuh>
+
+#include "common.cuh"
+
+namespace ska {
+
+constexpr int MG_THREADS = 256;
+constexpr int COUNT_CAP = 4096;             // key slots of the counting pass (32 KB)
+constexpr uint64_t KEY_EMPTY = ~0ULL;
+
+__device__ __forceinline__ uint32_t hash_slot(uint64_t key, int log_cap) {
+    return (uint32_t)((key * 0x9E3779B97F4A7C15ULL) >> (64 - log_cap));
+}
+
+// bucket boundaries in the prefix-sorted record array: off[b] = first i with bucket(rec[i]) >= b
+__global__ void bucket_offsets_kernel(const uint64_t* __restrict__ rec, uint64_t n, int shift, uint32_t n_buckets,
+                                      uint64_t* __restrict__ off) {
+    uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b > n_buckets) return;
+    if (b == n_buckets) { off[b] = n; return; }
+    uint64_t lo = 0, hi = n;                         // first index whose bucket >= b
+    const uint64_t mask = (uint64_t)n_buckets - 1;
+    while (lo < hi) {
+        uint64_t m = (lo + hi) >> 1;
+        if (((rec[m] >> shift) & mask) < b) lo = m + 1; else hi = m;
+    }
+    off[b] = lo;
+}
+
+// ---- pass 1: distinct keys per bucket
+__global__ void __launch_bounds__(MG_THREADS)
+bucket_count_kernel(const uint64_t* __restrict__ rec, const uint64_t* __restrict__ off, uint32_t* __restrict__ n_rows,
+                    uint32_t* __restrict__ overflow) {
+    __shared__ uint64_t s_tab[COUNT_CAP];
+    __shared__ uint32_t s_n;
+    const uint32_t b = blockIdx.x;
+    const uint64_t beg = off[b], end = off[b + 1];
+    for (int i = threadIdx.x; i < COUNT_CAP; i += MG_THREADS) s_tab[i] = KEY_EMPTY;
+    if (threadIdx.x == 0) s_n = 0;
+    __syncthreads();
+    uint32_t mine = 0;
+    for (uint64_t i = beg + threadIdx.x; i < end; i += MG_THREADS) {
+        uint64_t r = rec[i];
+        if (r == REC_SENTINEL) continue;
+        uint64_t key = r >> 4;
+        uint32_t slot = hash_slot(key, 12);
+        int probes = 0;
+        while (true) {
+            unsigned long long old = atomicCAS((unsigned long long*)&s_tab[slot], KEY_EMPTY, key);
+            if (old == KEY_EMPTY) { mine++; break; }
+            if (old == key) break;
+            slot = (slot + 1) & (COUNT_CAP - 1);
+            if (++probes >= COUNT_CAP) { atomicExch(overflow, 1u); break; }
+        }
+    }
+    if (mine) atomicAdd(&s_n, mine);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        n_rows[b] = s_n;
+        if (s_n > COUNT_CAP - COUNT_CAP / 8) atomicExch(overflow, 1u);   // too full to trust probing cost
+    }
+}
+
+// exclusive scan of n u32 counts into u64 offsets (single CTA; n is at most a few million)
+__global__ void scan_counts_kernel(const uint32_t* __restrict__ cnt, uint32_t n, uint64_t* __restrict__ off,
+                                   uint32_t* __restrict__ max_out) {
+    __shared__ uint64_t s_sum[1024];
+    __shared__ uint32_t s_max[1024];
+    const uint32_t t = threadIdx.x, T = blockDim.x;
+    const uint32_t per = (n + T - 1) / T;
+    const uint32_t b = min(n, t * per), e = min(n, b + per);
+    uint64_t sum = 0; uint32_t mx = 0;
+    for (uint32_t i = b; i < e; i++) { sum += cnt[i]; mx = max(mx, cnt[i]); }
+    s_sum[t] = sum; s_max[t] = mx;
+    __syncthreads();
+    if (t == 0) {
+        uint64_t run = 0; uint32_t m = 0;
+        for (uint32_t i = 0; i < T; i++) { uint64_t v = s_sum[i]; s_sum[i] = run; run += v; m = max(m, s_max[i]); }
+        off[n] = run; *max_out = m;
+    }
+    __syncthreads();
+    uint64_t run = s_sum[t];
+    for (uint32_t i = b; i < e; i++) { off[i] = run; run += cnt[i]; }
+}
+
+void launch_scan_counts(const uint32_t* cnt, uint32_t n, uint64_t* off, uint32_t* max_out) {
+    SKA_LAUNCH(scan_counts_kernel, 1, 1024, 0, cnt, n, off, max_out);
+}
+
+// reverse complement of a (k-1)-base packed key (bit_encoding.rs:182-195)
+__device__ __forceinline__ uint64_t revcomp_key(uint64_t x, int n_bases) {
+    x = __brevll(x);
+    x = ((x & 0x5555555555555555ULL) << 1) | ((x >> 1) & 0x5555555555555555ULL);
+    x ^= 0xAAAAAAAAAAAAAAAAULL;
+    return x >> (64 - 2 * n_bases);
+}
+
+// 4-bit base set (bit = 2-bit code: A=1 C=2 T=4 G=8) -> IUPAC letter, 0 -> '-'   (bit_encoding.rs:354-453)
+__device__ __forceinline__ uint32_t iupac_letter(uint32_t m) {
+    // index:      0    1    2    3    4    5    6    7    8    9   10   11   12   13   14   15
+    // letter:    '-'  'A'  'C'  'M'  'T'  'W'  'Y'  'H'  'G'  'R'  'S'  'V'  'K'  'D'  'B'  'N'
+    const uint64_t t0 = ((uint64_t)'-') | ((uint64_t)'A' << 8) | ((uint64_t)'C' << 16) | ((uint64_t)'M' << 24) |
+                        ((uint64_t)'T' << 32) | ((uint64_t)'W' << 40) | ((uint64_t)'Y' << 48) | ((uint64_t)'H' << 56);
+    const uint64_t t1 = ((uint64_t)'G') | ((uint64_t)'R' << 8) | ((uint64_t)'S' << 16) | ((uint64_t)'V' << 24) |
+                        ((uint64_t)'K' << 32) | ((uint64_t)'D' << 40) | ((uint64_t)'B' << 48) | ((uint64_t)'N' << 56);
+    return (uint32_t)(((m & 8u) ? t1 : t0) >> (8 * (m & 7u))) & 0xFFu;
+}
+// palindromic key: only {A,T} seen -> W, only {C,G} -> S, both -> N   (ska_dict.rs:85-113)
+__device__ __forceinline__ uint32_t pal_letter(uint32_t m) {
+    if (!m) return '-';
+    bool at = m & 5u, cg = m & 10u;
+    return at && cg ? 'N' : (at ? 'W' : 'S');
+}
+
+// ---- pass 2: reduce a bucket in shared memory and emit its rows in key order
+// dynamic smem layout: tab u64[cap] | list_key u64[cap] | mat u32[cap * n8] | list_slot u16[cap]
+__global__ void __launch_bounds__(MG_THREADS)
+bucket_emit_kernel(const uint64_t* __restrict__ rec, const uint16_t* __restrict__ sid, const uint64_t* __restrict__ off,
+                   const uint64_t* __restrict__ row_off, int log_cap, uint32_t n_samples, int k, int rc,
+                   uint64_t* __restrict__ out_keys, uint8_t* __restrict__ out_var, uint32_t* __restrict__ out_cnt) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    const uint32_t cap = 1u << log_cap;
+    const uint32_t n8 = (n_samples + 7) / 8;                 // u32 words of 8 nibbles per row
+    uint64_t* s_tab = reinterpret_cast<uint64_t*>(smem);
+    uint64_t* s_lkey = s_tab + cap;
+    uint32_t* s_mat = reinterpret_cast<uint32_t*>(s_lkey + cap);
+    uint16_t* s_lslot = reinterpret_cast<uint16_t*>(s_mat + (size_t)cap * n8);
+    __shared__ uint32_t s_u;
+
+    const uint32_t b = blockIdx.x;
+    const uint64_t beg = off[b], end = off[b + 1];
+    const uint64_t row_base = row_off[b];
+    const uint32_t u_expect = (uint32_t)(row_off[b + 1] - row_base);
+    if (u_expect == 0) return;
+
+    for (uint32_t i = threadIdx.x; i < cap; i += MG_THREADS) s_tab[i] = KEY_EMPTY;
+    for (uint32_t i = threadIdx.x; i < cap * n8; i += MG_THREADS) s_mat[i] = 0;
+    if (threadIdx.x == 0) s_u = 0;
+    __syncthreads();
+
+    // phase 1: insert
+    for (uint64_t i = beg + threadIdx.x; i < end; i += MG_THREADS) {
+        uint64_t r = rec[i];
+        if (r == REC_SENTINEL) continue;
+        uint32_t s = sid[i];
+        uint64_t key = r >> 4;
+        uint32_t slot = hash_slot(key, log_cap);
+        while (true) {
+            unsigned long long old = atomicCAS((unsigned long long*)&s_tab[slot], KEY_EMPTY, key);
+            if (old == KEY_EMPTY || old == key) break;
+            slot = (slot + 1) & (cap - 1);
+        }
+        atomicOr(&s_mat[slot * n8 + (s >> 3)], (uint32_t)(r & 0xF) << (4 * (s & 7)));
+    }
+    __syncthreads();
+
+    // phase 2: compact occupied slots, then bitonic sort by key
+    for (uint32_t i = threadIdx.x; i < cap; i += MG_THREADS) {
+        uint64_t key = s_tab[i];
+        if (key != KEY_EMPTY) {
+            uint32_t pos = atomicAdd(&s_u, 1u);
+            s_lkey[pos] = key;
+            s_lslot[pos] = (uint16_t)i;
+        }
+    }
+    __syncthreads();
+    const uint32_t u = s_u;                                  // == u_expect
+    uint32_t np2 = 1; while (np2 < u) np2 <<= 1;
+    for (uint32_t i = u + threadIdx.x; i < np2; i += MG_THREADS) { s_lkey[i] = KEY_EMPTY; s_lslot[i] = 0; }
+    __syncthreads();
+    for (uint32_t size = 2; size <= np2; size <<= 1) {
+        for (uint32_t stride = size >> 1; stride > 0; stride >>= 1) {
+            for (uint32_t t = threadIdx.x; t < np2 / 2; t += MG_THREADS) {
+                uint32_t lo = 2 * t - (t & (stride - 1));    // index with bit `stride` clear
+                uint32_t hi = lo + stride;
+                bool up = ((lo & size) == 0);
+                uint64_t a = s_lkey[lo], c = s_lkey[hi];
+                if ((a > c) == up) {
+                    s_lkey[lo] = c; s_lkey[hi] = a;
+                    uint16_t sa = s_lslot[lo]; s_lslot[lo] = s_lslot[hi]; s_lslot[hi] = sa;
+                }
+            }
+            __syncthreads();
+        }
+    }
+
+    // phase 3a: keys, counts, palindrome flag (bit 15 of the slot entry)
+    for (uint32_t i = threadIdx.x; i < u; i += MG_THREADS) {
+        uint64_t key = s_lkey[i];
+        uint32_t slot = s_lslot[i] & 0x7FFFu;
+        uint32_t c = 0;
+        for (uint32_t w = 0; w < n8; w++) {
+            uint32_t v = s_mat[slot * n8 + w];
+            c += __popc((v | (v >> 1) | (v >> 2) | (v >> 3)) & 0x11111111u);
+        }
+        out_keys[row_base + i] = key;
+        out_cnt[row_base + i] = c;
+        bool pal = rc && (revcomp_key(key, k - 1) == key);
+        s_lslot[i] = (uint16_t)(slot | (pal ? 0x8000u : 0u));
+    }
+    __syncthreads();
+
+    // phase 3b: letters, row-major, coalesced
+    uint8_t* dst = out_var + row_base * n_samples;
+    if ((n_samples & 3u) == 0) {
+        const uint32_t g_per_row = n_samples >> 2;
+        uint32_t* dst32 = reinterpret_cast<uint32_t*>(dst);   // row_base*n_samples is a multiple of 4
+        for (uint32_t idx = threadIdx.x; idx < u * g_per_row; idx += MG_THREADS) {
+            uint32_t i = idx / g_per_row, g = idx - i * g_per_row;
+            uint32_t e = s_lslot[i];
+            uint32_t slot = e & 0x7FFFu; bool pal = e & 0x8000u;
+            uint32_t nib = (s_mat[slot * n8 + (g >> 1)] >> (16 * (g & 1))) & 0xFFFFu;
+            uint32_t word = 0;
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                uint32_t m = (nib >> (4 * q)) & 0xFu;
+                word |= (pal ? pal_letter(m) : iupac_letter(m)) << (8 * q);
+            }
+            dst32[idx] = word;
+        }
+    } else {
+        for (uint32_t idx = threadIdx.x; idx < u * n_samples; idx += MG_THREADS) {
+            uint32_t i = idx / n_samples, s = idx - i * n_samples;
+            uint32_t e = s_lslot[i];
+            uint32_t slot = e & 0x7FFFu; bool pal = e & 0x8000u;
+            uint32_t m = (s_mat[slot * n8 + (s >> 3)] >> (4 * (s & 7))) & 0xFu;
+            dst[idx] = (uint8_t)(pal ? pal_letter(m) : iupac_letter(m));
+        }
+    }
+}
+
+static int choose_prefix_bits(uint64_t n_pos, int key_bits) {
+    int p = 0;
+    while ((n_pos >> p) > 4096 && p < key_bits && p < 22) p++;
+    return p;
+}
+
+void build_array_from_records(uint64_t* rec, uint16_t* sid, uint64_t n_pos, uint64_t n_samples, uint32_t k, bool rc,
+                              Array& out) {
+    Context& c = ctx();
+    const int key_bits = 2 * ((int)k - 1);
+    const int P = choose_prefix_bits(n_pos, key_bits);
+    const uint32_t n_buckets = 1u << P;
+    const int shift = 4 + key_bits - P;
+
+    // (1) partition by key prefix
+    timer().begin("partition");
+    DevBuf<uint64_t> rec_alt; DevBuf<uint16_t> sid_alt; DevBuf<uint8_t> tmp;
+    uint64_t* rec_sorted = rec; uint16_t* sid_sorted = sid;
+    if (P > 0) {
+        rec_alt.alloc(n_pos); sid_alt.alloc(n_pos);
+        cub::DoubleBuffer<uint64_t> dk(rec, rec_alt.p);
+        cub::DoubleBuffer<uint16_t> dv(sid, sid_alt.p);
+        size_t tmp_bytes = 0;
+        SKA_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, dk, dv, (int64_t)n_pos, shift, shift + P, c.stream));
+        tmp.alloc(tmp_bytes);
+        SKA_CUDA(cub::DeviceRadixSort::SortPairs(tmp.p, tmp_bytes, dk, dv, (int64_t)n_pos, shift, shift + P, c.stream));
+        c.launches += (P + 7) / 8 + 1;   // onesweep: one histogram + one pass per 8 bits (library kernels)
+        rec_sorted = dk.Current(); sid_sorted = dv.Current();
+    }
+    timer().end();
+
+    timer().begin("bucket_offsets");
+    DevBuf<uint64_t> off(n_buckets + 1);
+    SKA_LAUNCH(bucket_offsets_kernel, (n_buckets + 1 + 255) / 256, 256, 0, rec_sorted, n_pos, shift, n_buckets, off.p);
+    timer().end();
+
+    // (2a) distinct keys per bucket -> row offsets
+    timer().begin("count");
+    DevBuf<uint32_t> n_rows(n_buckets), flags(2);
+    DevBuf<uint64_t> row_off(n_buckets + 1);
+    SKA_CUDA(cudaMemsetAsync(flags.p, 0, 8, c.stream));
+    SKA_LAUNCH(bucket_count_kernel, n_buckets, MG_THREADS, 0, rec_sorted, off.p, n_rows.p, flags.p);
+    SKA_LAUNCH(scan_counts_kernel, 1, 1024, 0, n_rows.p, n_buckets, row_off.p, flags.p + 1);
+    uint32_t h_flags[2]; uint64_t total_rows = 0;
+    SKA_CUDA(cudaMemcpyAsync(h_flags, flags.p, 8, cudaMemcpyDeviceToHost, c.stream));
+    SKA_CUDA(cudaMemcpyAsync(&total_rows, row_off.p + n_buckets, 8, cudaMemcpyDeviceToHost, c.stream));
+    SKA_CUDA(cudaStreamSynchronize(c.stream));
+    timer().end();
+    if (h_flags[0]) throw Error("bucket overflow in count pass: too many distinct split k-mers share a key prefix");
+    const uint32_t max_u = h_flags[1];
+
+    // (2b) emit
+    timer().begin("emit");
+    out.k = k; out.rc = rc; out.key_bits = 64; out.n_samples = n_samples;
+    out.n_rows = out.n_keys = total_rows;
+    out.keys.alloc(total_rows); out.variants.alloc(total_rows * n_samples); out.counts.alloc(total_rows);
+    if (total_rows) {
+        int log_cap = 6;
+        while ((1u << log_cap) < 2 * max_u) log_cap++;
+        const uint32_t n8 = (uint32_t)((n_samples + 7) / 8);
+        size_t smem = ((size_t)1 << log_cap) * (8 + 8 + 4 * (size_t)n8 + 2);
+        if (log_cap > 15 || smem > c.smem_optin)
+            throw Error("bucket too large for shared-memory merge (distinct keys " + std::to_string(max_u) + ", samples " +
+                        std::to_string(n_samples) + ")");
+        SKA_CUDA(cudaFuncSetAttribute(bucket_emit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        SKA_LAUNCH(bucket_emit_kernel, n_buckets, MG_THREADS, smem, rec_sorted, sid_sorted, off.p, row_off.p, log_cap,
+                   (uint32_t)n_samples, (int)k, rc ? 1 : 0, out.keys.p, out.variants.p, out.counts.p);
+    }
+    timer().end();
+}
+
+}  // namespace ska

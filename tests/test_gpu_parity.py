@@ -1,0 +1,417 @@
+"""GPU parity tests: the CUDA path (through the C ABI of libskagpu.so) against the CPU oracle and
+against the reference's own golden outputs.  Bit-exact everywhere (integer/byte work); the only
+floating-point output -- the `--allow-ambiguous` distance -- is compared to 1e-9 and, as printed
+text (`{:.2}`), exactly.  Run on the B200 box:  python -m pytest tests -m gpu
+"""
+import io
+import os
+
+import numpy as np
+import pytest
+
+import ska_rust_b200 as S
+from oracle import oracle as O
+from oracle import skf_py
+
+pytestmark = pytest.mark.gpu
+
+SENT = np.uint64(0xFFFFFFFFFFFFFFFF)
+
+
+# ------------------------------------------------------------------ helpers
+def gpu_build_files(files, k=31, rc=True, names=None, **kw):
+    inputs = []
+    for i, f in enumerate(files):
+        f1, f2 = (f, None) if isinstance(f, str) else f
+        inputs.append(((names[i] if names else O.sample_name(f1)), f1, f2))
+    prop = kw.pop("proportion_reads", None)
+    return S.build_and_merge(inputs, k, rc, S.QualOpts(**kw), proportion_reads=prop)
+
+
+def ora_from_gpu_samples(samples, names, k, rc):
+    osamples = []
+    for s in samples:
+        recs = [(bytes(s.seq[int(s.rec_off[i]):int(s.rec_off[i + 1])]), None) for i in range(s.n_rec)]
+        osamples.append(O.SampleData(recs))
+    return O.OracleArray.build(osamples, names, k=k, rc=rc)
+
+
+def assert_same_array(g, o):
+    gd, od = g.dims(), o.dims()
+    assert gd == od, (gd, od)
+    gk, gv, gc = g.export()
+    ok, ov, oc = o.export()
+    assert [int(x) for x in gk] == ok
+    assert np.array_equal(gv, ov)
+    assert np.array_equal(gc, oc)
+
+
+def random_records(rng, n_rec, max_len, p_n=0.02, lower=True):
+    recs = []
+    alphabet = np.frombuffer(b"ACGTacgtNnRY", dtype=np.uint8)
+    probs = np.array([0.24, 0.24, 0.24, 0.24, 0.002, 0.002, 0.002, 0.002, p_n / 2, p_n / 2, 0.001, 0.001])
+    probs = probs / probs.sum()
+    for _ in range(n_rec):
+        ln = int(rng.integers(0, max_len))
+        recs.append(rng.choice(alphabet, size=ln, p=probs).tobytes())
+    return recs
+
+
+def expected_records(samples_records, k, rc):
+    """per-position K1 records from the oracle's rolling iterator"""
+    out = []
+    for recs in samples_records:
+        for r in recs:
+            e = np.full(len(r), SENT, dtype=np.uint64)
+            w = O.windows(r, k, rc=rc)
+            h = (k - 1) // 2
+            for i in range(w["n"]):
+                start = int(w["mid_pos"][i]) - h
+                e[start] = np.uint64((w["key"][i] << 4) | (1 << int(w["mid"][i])))
+            out.append(e)
+    return np.concatenate(out) if out else np.zeros(0, dtype=np.uint64)
+
+
+# ------------------------------------------------------------------ K1
+@pytest.mark.parametrize("k,rc", [(5, True), (7, False), (9, True), (15, True), (15, False), (21, True), (31, True), (31, False)])
+def test_k1_windows_match_rolling_iterator(k, rc):
+    rng = np.random.default_rng(1234 + k)
+    samples_records = [random_records(rng, int(rng.integers(1, 6)), 3000) for _ in range(5)]
+    # edge cases: record of exactly k, k+1, k-1 bases, empty record, run of exactly k after an N at the end
+    core = bytes(rng.choice(np.frombuffer(b"ACGT", dtype=np.uint8), size=k + 1))
+    samples_records.append([core[:k], core, core[:k - 1], b"", core + b"N" + core[:k], core[:k] + b"N" + core,
+                            b"N" * 40, core * 3])
+    samples = [S.Sample.from_records(r) for r in samples_records]
+    batch = S.SeqBatch(samples)
+    rec, _ms = batch.k1_extract(k, rc=rc)
+    exp = expected_records(samples_records, k, rc)
+    assert rec.shape == exp.shape
+    bad = np.nonzero(rec != exp)[0]
+    assert bad.size == 0, f"{bad.size} mismatching positions, first at {bad[:5]}"
+
+
+def test_k1_tile_boundaries_long_record():
+    """windows that straddle the 4096-position tiles of the kernel, N runs at tile edges"""
+    rng = np.random.default_rng(7)
+    seq = bytearray(rng.choice(np.frombuffer(b"ACGT", dtype=np.uint8), size=20000).tobytes())
+    for p in (4090, 4095, 4096, 4097, 8191, 8192, 12287 + 31, 16384 - 31):
+        seq[p] = ord("N")
+    recs = [[bytes(seq)], [bytes(seq[:4096])], [bytes(seq[:4096 + 30])], [bytes(seq[100:4196])]]
+    batch = S.SeqBatch([S.Sample.from_records(r) for r in recs])
+    for k in (31, 9):
+        rec, _ = batch.k1_extract(k, rc=True)
+        assert np.array_equal(rec, expected_records(recs, k, True))
+
+
+def test_k1_strict_quality_mask():
+    """split_kmer.rs:66-71,98-101: with QualFilter::Strict a base is valid only if qual-33 > min_qual"""
+    rng = np.random.default_rng(11)
+    n = 5000
+    seq = rng.choice(np.frombuffer(b"ACGTN", dtype=np.uint8), size=n, p=[.245, .245, .245, .245, .02])
+    qual = rng.choice(np.array([33 + 2, 33 + 20, 33 + 21, 33 + 40], dtype=np.uint8), size=n, p=[.02, .02, .06, .9])
+    off = np.array([0, 1700, 1700, 3300, n], dtype=np.uint64)
+    s = S.Sample(seq, off, qual)
+    batch = S.SeqBatch([s])
+    k = 15
+    rec, _ = batch.k1_extract(k, rc=True, min_qual=20, qual_filter="strict")
+    exp = []
+    for i in range(4):
+        a, b = int(off[i]), int(off[i + 1])
+        e = np.full(b - a, SENT, dtype=np.uint64)
+        w = O.windows(seq[a:b].tobytes(), k, rc=True, qual=qual[a:b].tobytes(), min_qual=20, qual_filter="strict", is_reads=True)
+        for j in range(w["n"]):
+            e[int(w["mid_pos"][j]) - 7] = np.uint64((w["key"][j] << 4) | (1 << int(w["mid"][j])))
+        exp.append(e)
+    assert np.array_equal(rec, np.concatenate(exp))
+
+
+# ------------------------------------------------------------------ build: reference fixtures
+SKF_RECIPES = {
+    "multidist.skf": (9, ["N_test_1.fa", "N_test_2.fa", "ambig_test_1.fa", "ambig_test_2.fa", "test_1.fa", "test_2.fa"]),
+    "merge_k9.skf": (9, ["test_1.fa", "test_2.fa"]),
+    "merge.skf": (17, ["test_1.fa", "test_2.fa"]),
+}
+
+
+@pytest.mark.parametrize("fixture", sorted(SKF_RECIPES))
+def test_build_reproduces_reference_skf(gold_in, fixture):
+    k, files = SKF_RECIPES[fixture]
+    ref = skf_py.load_skf(gold_in(fixture))
+    var = np.frombuffer(ref["variants"], dtype=np.uint8).reshape(ref["n_rows"], ref["n_samples"])
+    ref_map = {key: bytes(var[i]) for i, key in enumerate(ref["split_kmers"])}
+    ref_cnt = {key: ref["variant_count"][i] for i, key in enumerate(ref["split_kmers"])}
+    g = gpu_build_files([gold_in(f) for f in files], k=k)
+    assert g.names() == ref["names"]
+    keys, gv, gc = g.export()
+    assert list(keys) == sorted(keys)
+    assert {int(key): bytes(gv[i]) for i, key in enumerate(keys)} == ref_map
+    assert {int(key): int(gc[i]) for i, key in enumerate(keys)} == ref_cnt
+
+
+def aln(arr, **kw):
+    buf = io.BytesIO()
+    S.api.align(arr, buf, **kw)
+    return buf.getvalue()
+
+
+def dist(arr, **kw):
+    buf = io.BytesIO()
+    S.api.distance(arr, buf, **kw)
+    return buf.getvalue()
+
+
+def test_align_goldens(gold_in, gold_ok):
+    """tests/fasta_input.rs: align_n, repeats, palindromes -- byte-exact stdout"""
+    b = lambda names, **kw: gpu_build_files([gold_in(n) for n in names], **kw)
+    assert aln(b(["N_test_1.fa", "N_test_2.fa"])) == gold_ok("align_N.stdout")
+    assert aln(b(["dup_test_1.fa", "dup_test_2.fa"], k=9, rc=False)) == gold_ok("dup_ss.stdout")
+    assert aln(b(["dup_test_1.fa", "dup_test_2.fa"], k=9)) == gold_ok("dup_rc.stdout")
+    assert aln(b(["palindrome_1.fa", "palindrome_2.fa"], k=15), filter_type="no-filter") == gold_ok("palindrome.stdout")
+    assert aln(b(["palindrome_1.fa", "palindrome_2.fa"], k=15, rc=False)) == gold_ok("palindrome_norc.stdout")
+    assert aln(b(["palindrome_reps_1.fa", "palindrome_reps_2.fa"], k=15), filter_type="no-filter") == gold_ok("palindrome_reps.stdout")
+
+
+def test_align_column_sets(gold_in):
+    """tests/align.rs:86-115,168-183; tests/fasta_input.rs:60-154"""
+    b = lambda names, **kw: gpu_build_files([gold_in(n) for n in names], **kw)
+    assert O.var_hash(aln(b(["test_1.fa", "test_2.fa"], k=15))) == {("A", "T"), ("C", "T")}
+    assert O.var_hash(aln(b(["test_1.fa", "test_2.fa"]))) == {("A", "T"), ("C", "T")}
+    assert O.var_hash(aln(b(["test_1.fa", "test_2_rc.fa"], k=15))) == {("A", "T"), ("C", "T")}
+    assert O.var_hash(aln(b(["test_1.fa", "test_2_rc.fa"], k=15, rc=False))) == set()
+
+
+def test_nk_golden(gold_in, gold_ok):
+    g = gpu_build_files([gold_in("test_1.fa"), gold_in("test_2.fa")], k=31)
+    assert g.display().split("\n", 1)[1] == gold_ok("merge_nk.stdout").decode().split("\n", 1)[1]
+    g = gpu_build_files([gold_in("dup_test_1.fa"), gold_in("dup_test_2.fa")], k=9, rc=False)
+    g.filter(2, False, "no-const", False, False, True)
+    assert g.display(full_info=True).split("\n", 1)[1] == gold_ok("dup_ss_nk.stdout").decode().split("\n", 1)[1]
+
+
+def test_proportion_reads(gold_in):
+    g = gpu_build_files([gold_in("proportion_reads.fa")], k=17, rc=False, proportion_reads=0.5)
+    o = O.OracleArray.build_from_files([gold_in("proportion_reads.fa")], k=17, rc=False, proportion_reads=0.5)
+    assert_same_array(g, o)
+    assert g.dims()["n_rows"] == 2
+
+
+def test_parallel_align_45_samples(gold_in):
+    """tests/align.rs:349-397 -- 45 gz copies; result independent of scheduling"""
+    d = gold_in("par_test")
+    files = sorted(os.path.join(d, f) for f in os.listdir(d))
+    g = gpu_build_files(files, k=15)
+    o = O.OracleArray.build_from_files(files, k=15, threads=4)
+    assert_same_array(g, o)
+    assert aln(g) == o.align()
+
+
+def test_errors(gold_in):
+    f = [gold_in("test_1.fa"), gold_in("test_2.fa")]
+    for bad_k in (65, 30, 3):
+        with pytest.raises(S.SkaError, match="Invalid k-mer length"):
+            gpu_build_files(f, k=bad_k)
+    with pytest.raises(S.SkaError, match="no valid sequence"):          # ska_dict.rs:374-376
+        S.build_from_samples([S.Sample.from_records([b"ACGTNACGTNACGT"]), S.Sample.from_records([b"ACGTACGTACGTAAA"])],
+                             ["a", "b"], 9, True)
+    with pytest.raises(S.SkaError):
+        gpu_build_files(["/nonexistent/x.fa"], k=9)
+
+
+# ------------------------------------------------------------------ build: synthetic, vs oracle
+@pytest.mark.parametrize("n,length,k,rc", [(4, 100_000, 31, True), (6, 30_000, 15, False), (3, 50_000, 21, True),
+                                           (9, 20_011, 9, True), (130, 3_001, 31, True)])
+def test_build_synthetic_matches_oracle(n, length, k, rc):
+    """BASELINE config 1 (4 x 100 kbp, k=31) and config-5-shaped (k=15 single strand) inputs"""
+    from ska_rust_b200 import synth
+    genomes = synth.star_genomes(n, length, seed=0x5CA20001 + k, snp_rate=0.002)
+    samples = [S.Sample.from_records([g.tobytes()]) for g in genomes]
+    names = [f"s{i}" for i in range(n)]
+    g = S.build_from_samples(samples, names, k, rc)
+    o = ora_from_gpu_samples(samples, names, k, rc)
+    assert_same_array(g, o)
+
+
+def test_build_multi_record_with_ns_and_repeats():
+    rng = np.random.default_rng(99)
+    samples_records = []
+    for _ in range(7):
+        recs = random_records(rng, int(rng.integers(1, 30)), 2500, p_n=0.01)
+        recs.append(recs[0] * 2)                       # repeats -> IUPAC merges within a sample
+        recs.append(b"ACGT" * 50)                      # low complexity: same key with several middles, palindromes
+        samples_records.append(recs)
+    samples = [S.Sample.from_records(r) for r in samples_records]
+    names = [f"s{i}" for i in range(len(samples))]
+    for k, rc in ((9, True), (7, True), (11, False), (31, True)):
+        g = S.build_from_samples(samples, names, k, rc)
+        assert_same_array(g, ora_from_gpu_samples(samples, names, k, rc))
+
+
+def test_build_properties_medium():
+    """size-independent properties on 16 x 1 Mbp: sorted unique keys, counts == non-gap cells,
+    idempotence, column permutation equivariance"""
+    from ska_rust_b200 import synth
+    n, length, k = 16, 1_000_000, 31
+    genomes = synth.star_genomes(n, length, seed=0x5CA20002)
+    samples = [S.Sample.from_records([g.tobytes()]) for g in genomes]
+    names = [f"s{i}" for i in range(n)]
+    g = S.build_from_samples(samples, names, k, True)
+    keys, var, cnt = g.export()
+    assert np.all(keys[1:] > keys[:-1])
+    assert np.array_equal((var != ord("-")).sum(axis=1), cnt)
+    assert int(keys.max()) < (1 << 60)
+    # every sample sees ~length distinct split k-mers
+    per_sample = (var != ord("-")).sum(axis=0)
+    assert np.all(per_sample > 0.99 * (length - k + 1)) and np.all(per_sample <= length - k + 1)
+    g2 = S.build_from_samples(samples, names, k, True)
+    k2, v2, c2 = g2.export()
+    assert np.array_equal(keys, k2) and np.array_equal(var, v2) and np.array_equal(cnt, c2)
+    perm = np.random.default_rng(5).permutation(n)
+    g3 = S.build_from_samples([samples[i] for i in perm], [names[i] for i in perm], k, True)
+    k3, v3, _ = g3.export()
+    assert np.array_equal(keys, k3) and np.array_equal(var[:, perm], v3)
+    # one sample against the oracle
+    o = ora_from_gpu_samples(samples[:2], names[:2], k, True)
+    g4 = S.build_from_samples(samples[:2], names[:2], k, True)
+    assert_same_array(g4, o)
+
+
+# ------------------------------------------------------------------ filter
+def load_pair(gold_in, name):
+    d = skf_py.load_skf(gold_in(name))
+    var = np.frombuffer(d["variants"], dtype=np.uint8).reshape(d["n_rows"], d["n_samples"])
+    key_bits = 64 if all(v < (1 << 64) for v in d["split_kmers"]) else 128
+    g = S.MergeSkaArray.from_arrays(d["k"], d["rc"], key_bits, d["split_kmers"], var, d["variant_count"], d["names"])
+    o = O.OracleArray.from_arrays(d["k"], d["rc"], key_bits, d["split_kmers"], var, d["variant_count"], d["names"])
+    return g, o
+
+
+FILTER_CASES = [
+    (dict(filter_type="no-filter", ignore_const_gaps=True), "len", 38),
+    (dict(filter_type="no-ambig", filter_ambig_as_missing=True), "len", 37),
+    (dict(filter_type="no-const"), "set", {("T", "A"), ("C", "T"), ("S", "G")}),
+    (dict(filter_type="no-ambig-or-const"), "set", {("T", "A"), ("C", "T")}),
+    (dict(filter_type="no-const", mask_ambig=True), "set", {("T", "A"), ("C", "T"), ("N", "G")}),
+    (dict(filter_type="no-const", min_freq=0), "len", 33),
+    (dict(filter_type="no-const", min_freq=0, ignore_const_gaps=True), "len", 3),
+    (dict(filter_type="no-ambig-or-const", min_freq=0), "len", 32),
+    (dict(filter_type="no-ambig-or-const", min_freq=0, ignore_const_gaps=True), "len", 2),
+]
+
+
+@pytest.mark.parametrize("kw,kind,want", FILTER_CASES)
+def test_filter_matrix_merge_k9(gold_in, kw, kind, want):
+    """tests/align.rs:186-347"""
+    g, _ = load_pair(gold_in, "merge_k9.skf")
+    out = aln(g, **kw)
+    if kind == "len":
+        assert O.aln_length(out) == [want, want]
+    else:
+        assert O.var_hash(out) == want
+
+
+def random_array(rng, n_rows, n_samples):
+    alphabet = np.frombuffer(b"ACGT-ACGT-ACGT-RYSWKMBDHVNacgtuU", dtype=np.uint8)
+    base = rng.choice(np.frombuffer(b"ACGT", dtype=np.uint8), size=(n_rows, 1))
+    var = np.repeat(base, n_samples, axis=1)
+    noise = rng.random((n_rows, n_samples)) < 0.08
+    var[noise] = rng.choice(alphabet, size=int(noise.sum()))
+    gaps = rng.random((n_rows, n_samples)) < 0.05
+    var[gaps] = ord("-")
+    var[rng.random(n_rows) < 0.02] = ord("-")                       # all-gap rows
+    cnt = (var != ord("-")).sum(axis=1).astype(np.uint64)
+    keys = np.sort(rng.choice(1 << 40, size=n_rows, replace=False)).astype(np.uint64)
+    return keys, var, cnt
+
+
+@pytest.mark.parametrize("n_rows,n_samples", [(1000, 7), (5000, 128), (3001, 33), (300, 200)])
+def test_filter_random_arrays_match_oracle(n_rows, n_samples):
+    rng = np.random.default_rng(n_rows + n_samples)
+    keys, var, cnt = random_array(rng, n_rows, n_samples)
+    names = [f"s{i}" for i in range(n_samples)]
+    for ft in ("no-filter", "no-const", "no-ambig", "no-ambig-or-const"):
+        for ambig_missing in (False, True):
+            for gaps in (False, True):
+                for mask in (False, True):
+                    for upd in (False, True):
+                        for min_count in (0, n_samples // 2, n_samples):
+                            g = S.MergeSkaArray.from_arrays(31, True, 64, keys, var, cnt, names)
+                            o = O.OracleArray.from_arrays(31, True, 64, [int(x) for x in keys], var, cnt, names)
+                            rg = g.filter(min_count, ambig_missing, ft, mask, gaps, upd)
+                            ro = o.filter(min_count, ambig_missing, ft, mask, gaps, upd)
+                            assert rg == ro, (ft, ambig_missing, gaps, mask, upd, min_count)
+                            assert_same_array(g, o)
+
+
+def test_transpose_matches_write_fasta():
+    rng = np.random.default_rng(3)
+    for n_rows, n_samples in ((1, 1), (63, 5), (64, 64), (1000, 129), (4097, 128)):
+        keys, var, cnt = random_array(rng, n_rows, n_samples)
+        g = S.MergeSkaArray.from_arrays(31, True, 64, keys, var, cnt, [f"s{i}" for i in range(n_samples)])
+        assert np.array_equal(g.transposed(), var.T)
+
+
+# ------------------------------------------------------------------ distance
+DIST_CASES = [
+    ("merge.skf", {}, "merge.dist.stdout"),
+    ("merge_k41.skf", {}, "merge_k41.dist.stdout"),
+    ("merge_k9.skf", {"filt_ambig": False}, "merge_k9.dist.stdout"),
+    ("merge_k9.skf", {}, "merge_k9_no_ambig.dist.stdout"),
+    ("merge_k9.skf", {"min_freq": 1.0}, "merge_k9_min_freq.dist.stdout"),
+    ("multidist.skf", {}, "multidist.stdout"),
+    ("multidist.skf", {"min_freq": 0.9}, "multidist.minfreq.stdout"),
+    ("multidist.skf", {"filt_ambig": False}, "multidist.ambig.stdout"),
+]
+
+
+@pytest.mark.parametrize("skf,kw,golden", DIST_CASES)
+def test_distance_goldens(gold_in, gold_ok, skf, kw, golden):
+    """tests/distance.rs -- byte-exact stdout, including the u128 fixture merge_k41.skf"""
+    g, _ = load_pair(gold_in, skf)
+    assert dist(g, **kw) == gold_ok(golden)
+
+
+def test_distance_after_gpu_build_multidist(gold_in, gold_ok):
+    k, files = SKF_RECIPES["multidist.skf"]
+    g = gpu_build_files([gold_in(f) for f in files], k=k)
+    assert dist(g) == gold_ok("multidist.stdout")
+
+
+@pytest.mark.parametrize("n_rows,n_samples", [(5000, 5), (20000, 40), (1000, 129), (33, 17), (0, 4)])
+@pytest.mark.parametrize("filt_ambig", [True, False])
+def test_distance_random_arrays_match_oracle(n_rows, n_samples, filt_ambig):
+    rng = np.random.default_rng(17 + n_rows)
+    if n_rows:
+        keys, var, cnt = random_array(rng, n_rows, n_samples)
+        if filt_ambig and n_rows == 20000:      # plain upper-case alphabet -> exercises the bit-plane kernel
+            var = np.where(np.isin(var, np.frombuffer(b"acgtuU", dtype=np.uint8)), np.uint8(ord("A")), var)
+    else:
+        keys, var, cnt = np.zeros(0, np.uint64), np.zeros((0, n_samples), np.uint8), np.zeros(0, np.uint64)
+    names = [f"s{i}" for i in range(n_samples)]
+    g = S.MergeSkaArray.from_arrays(31, True, 64, keys, var, cnt, names)
+    o = O.OracleArray.from_arrays(31, True, 64, [int(x) for x in keys], var, cnt, names)
+    dg = g.distance(12.0, filt_ambig)
+    do = o.distance_raw(12.0, filt_ambig, threads=4)
+    assert len(dg) == len(do)
+    for a, b in zip(dg, do):
+        assert a[2] == b[2] and a[3] == b[3]
+        if filt_ambig:
+            assert a[0] == b[0] and a[1] == b[1]
+        else:
+            assert abs(a[0] - b[0]) < 1e-9 and a[1] == b[1]
+            assert f"{a[0]:.2f}" == f"{b[0]:.2f}"
+
+
+def test_distance_bitplane_path_large():
+    """upper-case-only array big enough to split rows over many CTAs"""
+    rng = np.random.default_rng(21)
+    n_rows, n_samples = 200_000, 24
+    base = rng.choice(np.frombuffer(b"ACGT", dtype=np.uint8), size=(n_rows, 1))
+    var = np.repeat(base, n_samples, axis=1)
+    noise = rng.random((n_rows, n_samples)) < 0.05
+    var[noise] = rng.choice(np.frombuffer(b"ACGT-RYN", dtype=np.uint8), size=int(noise.sum()))
+    cnt = (var != ord("-")).sum(axis=1).astype(np.uint64)
+    keys = np.arange(n_rows, dtype=np.uint64)
+    names = [f"s{i}" for i in range(n_samples)]
+    g = S.MergeSkaArray.from_arrays(31, True, 64, keys, var, cnt, names)
+    o = O.OracleArray.from_arrays(31, True, 64, list(range(n_rows)), var, cnt, names)
+    assert g.distance(3.0, True) == o.distance_raw(3.0, True, threads=8)
