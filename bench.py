@@ -24,6 +24,13 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+_T0 = time.time()
+
+
+def log(msg):
+    if os.environ.get("RANK", "0") == "0":
+        print(f"[bench {time.time() - _T0:7.1f}s] {msg}", file=sys.stderr, flush=True)
+
 
 METRIC = "genomes/sec build+align (k=31)"
 UNIT = "genomes/s"
@@ -129,6 +136,7 @@ def run_ours(args, rank, world, local_rank):
     import ska_rust_b200 as S
     from ska_rust_b200 import synth
 
+    log("torch imported")
     torch.cuda.set_device(local_rank)
     S.set_device(local_rank)
     dist = None
@@ -157,6 +165,7 @@ def run_ours(args, rank, world, local_rank):
     for s, g in zip(samples, genomes):
         assert s.seq.ctypes.data == g.ctypes.data
     names = [f"s{rank * G + i}" for i in range(G)]
+    log(f"generated {G} x {L} bp genomes in pinned memory")
     n_bases = G * L
     threshold = int(np.ceil(G * 0.9))                  # generic_modes.rs:121 with cli.rs default min_freq 0.9
 
@@ -166,10 +175,12 @@ def run_ours(args, rank, world, local_rank):
 
     # ---------------- device-resident arm
     batch = S.SeqBatch(samples)
+    log("batch uploaded")
     for _ in range(args.warmup):
         arr = S.api.build_from_batch(batch, names, k, True)
         align_device(arr)
         del arr
+    log(f"device warm-up done; stages {S.api.last_timings()}")
     barrier()
     l0 = S.api.launch_count()
     with ClockSampler(local_rank) as clocks:
@@ -187,6 +198,7 @@ def run_ours(args, rank, world, local_rank):
     ms_dev = max_over_ranks(ms_dev)
     value = args.steps * G * world / (ms_dev * 1e-3)
 
+    log(f"device arm: {ms_dev / args.steps:.2f} ms/step, rows built {rows_built}, aligned {rows_aligned}")
     # ---------------- K1 alone (the kernel the roofline is quoted on), CUDA events inside the library
     _rec, k1_ms = batch.k1_extract(k, rc=True, iters=10, want_records=False)
     del batch
@@ -211,6 +223,7 @@ def run_ours(args, rank, world, local_rank):
     ms_e2e = S.api.timer_stop()
     barrier()
     ms_e2e = max_over_ranks(ms_e2e)
+    log(f"e2e arm: {ms_e2e / args.steps:.2f} ms/step")
     e2e_value = args.steps * G * world / (ms_e2e * 1e-3)
     h2d = n_bases + 8 * (2 * G + 1)                    # sequence bytes + record starts + sample offsets
     d2h = G * rows_aligned + 4 * G + 24                # alignment + per-sample valid counts + scalars
@@ -260,6 +273,10 @@ def run_ours(args, rank, world, local_rank):
 
 
 def main():
+    import faulthandler
+    faulthandler.enable()
+    if os.environ.get("BENCH_DUMP_AFTER"):
+        faulthandler.dump_traceback_later(int(os.environ["BENCH_DUMP_AFTER"]), repeat=True)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)

@@ -48,37 +48,61 @@ __global__ void bucket_offsets_kernel(const uint64_t* __restrict__ rec, uint64_t
     off[b] = lo;
 }
 
-// ---- pass 1: distinct keys per bucket
+// A work item = a contiguous record range (one prefix bucket) restricted to an inclusive key range.
+// Level-0 items cover their whole bucket; a bucket with too many distinct keys for shared memory is
+// split by further key bits into several items that each re-scan the bucket (rare path).
+struct Item { uint64_t beg, end, key_lo, key_hi; };
+constexpr uint32_t COUNT_OVERFLOW = 0xFFFFFFFFu;
+
+__global__ void make_items_kernel(const uint64_t* __restrict__ off, uint32_t n_buckets, int key_bits, int P,
+                                  Item* __restrict__ items) {
+    uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= n_buckets) return;
+    const int low = key_bits - P;                          // key bits below the bucket prefix
+    Item it;
+    it.beg = off[b]; it.end = off[b + 1];
+    it.key_lo = (uint64_t)b << low;
+    it.key_hi = it.key_lo | ((low >= 64) ? ~0ULL : ((1ULL << low) - 1ULL));
+    if (b == n_buckets - 1) it.key_hi = ~0ULL >> 4;       // top bucket also holds nothing above the key space
+    items[b] = it;
+}
+
+// ---- pass 1: distinct keys per item
 __global__ void __launch_bounds__(MG_THREADS)
-bucket_count_kernel(const uint64_t* __restrict__ rec, const uint64_t* __restrict__ off, uint32_t* __restrict__ n_rows,
-                    uint32_t* __restrict__ overflow) {
+bucket_count_kernel(const uint64_t* __restrict__ rec, const Item* __restrict__ items, uint32_t limit,
+                    uint32_t* __restrict__ n_rows, uint32_t* __restrict__ need_split) {
     __shared__ uint64_t s_tab[COUNT_CAP];
-    __shared__ uint32_t s_n;
-    const uint32_t b = blockIdx.x;
-    const uint64_t beg = off[b], end = off[b + 1];
+    __shared__ uint32_t s_n, s_over;
+    const Item it = items[blockIdx.x];
     for (int i = threadIdx.x; i < COUNT_CAP; i += MG_THREADS) s_tab[i] = KEY_EMPTY;
-    if (threadIdx.x == 0) s_n = 0;
+    if (threadIdx.x == 0) { s_n = 0; s_over = 0; }
     __syncthreads();
     uint32_t mine = 0;
-    for (uint64_t i = beg + threadIdx.x; i < end; i += MG_THREADS) {
+    for (uint64_t i = it.beg + threadIdx.x; i < it.end; i += MG_THREADS) {
         uint64_t r = rec[i];
         if (r == REC_SENTINEL) continue;
         uint64_t key = r >> 4;
+        if (key < it.key_lo || key > it.key_hi) continue;
+        if (*(volatile uint32_t*)&s_over) break;
         uint32_t slot = hash_slot(key, 12);
         int probes = 0;
         while (true) {
             unsigned long long old = atomicCAS((unsigned long long*)&s_tab[slot], KEY_EMPTY, key);
-            if (old == KEY_EMPTY) { mine++; break; }
+            if (old == KEY_EMPTY) {
+                mine++;
+                if (atomicAdd(&s_n, 1u) >= COUNT_CAP - COUNT_CAP / 4) s_over = 1;   // keep the table sparse enough to probe
+                break;
+            }
             if (old == key) break;
             slot = (slot + 1) & (COUNT_CAP - 1);
-            if (++probes >= COUNT_CAP) { atomicExch(overflow, 1u); break; }
+            if (++probes >= COUNT_CAP) { s_over = 1; break; }
         }
     }
-    if (mine) atomicAdd(&s_n, mine);
     __syncthreads();
     if (threadIdx.x == 0) {
-        n_rows[b] = s_n;
-        if (s_n > COUNT_CAP - COUNT_CAP / 8) atomicExch(overflow, 1u);   // too full to trust probing cost
+        uint32_t n = s_over ? COUNT_OVERFLOW : s_n;
+        n_rows[blockIdx.x] = n;
+        if (n > limit) atomicExch(need_split, 1u);
     }
 }
 
@@ -136,7 +160,7 @@ __device__ __forceinline__ uint32_t pal_letter(uint32_t m) {
 // ---- pass 2: reduce a bucket in shared memory and emit its rows in key order
 // dynamic smem layout: tab u64[cap] | list_key u64[cap] | mat u32[cap * n8] | list_slot u16[cap]
 __global__ void __launch_bounds__(MG_THREADS)
-bucket_emit_kernel(const uint64_t* __restrict__ rec, const uint16_t* __restrict__ sid, const uint64_t* __restrict__ off,
+bucket_emit_kernel(const uint64_t* __restrict__ rec, const uint16_t* __restrict__ sid, const Item* __restrict__ items,
                    const uint64_t* __restrict__ row_off, int log_cap, uint32_t n_samples, int k, int rc,
                    uint64_t* __restrict__ out_keys, uint8_t* __restrict__ out_var, uint32_t* __restrict__ out_cnt) {
     extern __shared__ __align__(16) uint8_t smem[];
@@ -149,7 +173,8 @@ bucket_emit_kernel(const uint64_t* __restrict__ rec, const uint16_t* __restrict_
     __shared__ uint32_t s_u;
 
     const uint32_t b = blockIdx.x;
-    const uint64_t beg = off[b], end = off[b + 1];
+    const Item it = items[b];
+    const uint64_t beg = it.beg, end = it.end;
     const uint64_t row_base = row_off[b];
     const uint32_t u_expect = (uint32_t)(row_off[b + 1] - row_base);
     if (u_expect == 0) return;
@@ -163,8 +188,9 @@ bucket_emit_kernel(const uint64_t* __restrict__ rec, const uint16_t* __restrict_
     for (uint64_t i = beg + threadIdx.x; i < end; i += MG_THREADS) {
         uint64_t r = rec[i];
         if (r == REC_SENTINEL) continue;
-        uint32_t s = sid[i];
         uint64_t key = r >> 4;
+        if (key < it.key_lo || key > it.key_hi) continue;
+        uint32_t s = sid[i];
         uint32_t slot = hash_slot(key, log_cap);
         while (true) {
             unsigned long long old = atomicCAS((unsigned long long*)&s_tab[slot], KEY_EMPTY, key);
@@ -250,9 +276,9 @@ bucket_emit_kernel(const uint64_t* __restrict__ rec, const uint16_t* __restrict_
     }
 }
 
-static int choose_prefix_bits(uint64_t n_pos, int key_bits) {
+static int choose_prefix_bits(uint64_t n_pos, int key_bits, uint64_t target) {
     int p = 0;
-    while ((n_pos >> p) > 4096 && p < key_bits && p < 22) p++;
+    while ((n_pos >> p) > target && p < key_bits && p < 24) p++;
     return p;
 }
 
@@ -260,7 +286,20 @@ void build_array_from_records(uint64_t* rec, uint16_t* sid, uint64_t n_pos, uint
                               Array& out) {
     Context& c = ctx();
     const int key_bits = 2 * ((int)k - 1);
-    const int P = choose_prefix_bits(n_pos, key_bits);
+    const uint32_t n8 = (uint32_t)((n_samples + 7) / 8);
+    const size_t slot_bytes = 8 + 8 + 4 * (size_t)n8 + 2;
+    // largest table the emit kernel may use, and therefore the most distinct keys an item may hold
+    int max_log_cap = 6;
+    while (max_log_cap < 15 && ((size_t)2 << max_log_cap) * slot_bytes <= c.smem_optin - 1024) max_log_cap++;
+    if (((size_t)1 << max_log_cap) * slot_bytes > c.smem_optin - 1024)
+        throw Error("too many samples for the shared-memory merge (" + std::to_string(n_samples) + ")");
+    const uint32_t limit = std::min<uint32_t>((1u << max_log_cap) / 2, COUNT_CAP - COUNT_CAP / 4 - 1);
+
+    // records per bucket: small enough that distinct keys per bucket normally stay under `limit`
+    // (canonical k-mers crowd the low prefixes about 2x), but keep to 2 radix passes when possible
+    uint64_t target = std::min<uint64_t>(4096, std::max<uint64_t>(256, (uint64_t)limit));
+    int P = choose_prefix_bits(n_pos, key_bits, target);
+    if (P > 16 && (n_pos >> 16) <= 4 * target) P = 16;
     const uint32_t n_buckets = 1u << P;
     const int shift = 4 + key_bits - P;
 
@@ -284,21 +323,56 @@ void build_array_from_records(uint64_t* rec, uint16_t* sid, uint64_t n_pos, uint
     timer().begin("bucket_offsets");
     DevBuf<uint64_t> off(n_buckets + 1);
     SKA_LAUNCH(bucket_offsets_kernel, (n_buckets + 1 + 255) / 256, 256, 0, rec_sorted, n_pos, shift, n_buckets, off.p);
+    uint32_t n_items = n_buckets;
+    DevBuf<Item> items(n_items);
+    SKA_LAUNCH(make_items_kernel, (n_buckets + 255) / 256, 256, 0, off.p, n_buckets, key_bits, P, items.p);
     timer().end();
 
-    // (2a) distinct keys per bucket -> row offsets
+    // (2a) distinct keys per item -> row offsets; split items that do not fit shared memory
     timer().begin("count");
-    DevBuf<uint32_t> n_rows(n_buckets), flags(2);
-    DevBuf<uint64_t> row_off(n_buckets + 1);
-    SKA_CUDA(cudaMemsetAsync(flags.p, 0, 8, c.stream));
-    SKA_LAUNCH(bucket_count_kernel, n_buckets, MG_THREADS, 0, rec_sorted, off.p, n_rows.p, flags.p);
-    SKA_LAUNCH(scan_counts_kernel, 1, 1024, 0, n_rows.p, n_buckets, row_off.p, flags.p + 1);
-    uint32_t h_flags[2]; uint64_t total_rows = 0;
+    DevBuf<uint32_t> n_rows(n_items), flags(2);
+    uint32_t h_flags[2];
+    for (int round = 0;; round++) {
+        SKA_CUDA(cudaMemsetAsync(flags.p, 0, 8, c.stream));
+        SKA_LAUNCH(bucket_count_kernel, n_items, MG_THREADS, 0, rec_sorted, items.p, limit, n_rows.p, flags.p);
+        SKA_CUDA(cudaMemcpyAsync(h_flags, flags.p, 8, cudaMemcpyDeviceToHost, c.stream));
+        SKA_CUDA(cudaStreamSynchronize(c.stream));
+        if (!h_flags[0]) break;
+        if (round > 40) throw Error("bucket splitting did not converge");
+        std::vector<Item> h_items(n_items), next;
+        std::vector<uint32_t> h_rows(n_items);
+        SKA_CUDA(cudaMemcpyAsync(h_items.data(), items.p, n_items * sizeof(Item), cudaMemcpyDeviceToHost, c.stream));
+        SKA_CUDA(cudaMemcpyAsync(h_rows.data(), n_rows.p, n_items * 4, cudaMemcpyDeviceToHost, c.stream));
+        SKA_CUDA(cudaStreamSynchronize(c.stream));
+        next.reserve(n_items + 64);
+        for (uint32_t i = 0; i < n_items; i++) {
+            const Item& it = h_items[i];
+            if (h_rows[i] <= limit) { next.push_back(it); continue; }
+            uint64_t width = it.key_hi - it.key_lo;                       // inclusive range is width+1 keys
+            if (width == 0) throw Error("internal: single-key item overflow");
+            int parts = 16;
+            if (h_rows[i] != COUNT_OVERFLOW) { parts = 2; while ((uint64_t)parts * limit < 2ull * h_rows[i]) parts *= 2; }
+            uint64_t step = width / parts + 1;                            // ceil((width+1)/parts) keeps children ordered, disjoint
+            for (uint64_t lo = it.key_lo;; lo += step) {
+                Item ch = it; ch.key_lo = lo;
+                bool last = (it.key_hi - lo) < step;
+                ch.key_hi = last ? it.key_hi : lo + step - 1;
+                next.push_back(ch);
+                if (last) break;
+            }
+        }
+        n_items = (uint32_t)next.size();
+        items.alloc(n_items); n_rows.alloc(n_items);
+        SKA_CUDA(cudaMemcpyAsync(items.p, next.data(), n_items * sizeof(Item), cudaMemcpyHostToDevice, c.stream));
+        SKA_CUDA(cudaStreamSynchronize(c.stream));
+    }
+    DevBuf<uint64_t> row_off(n_items + 1);
+    launch_scan_counts(n_rows.p, n_items, row_off.p, flags.p + 1);
+    uint64_t total_rows = 0;
     SKA_CUDA(cudaMemcpyAsync(h_flags, flags.p, 8, cudaMemcpyDeviceToHost, c.stream));
-    SKA_CUDA(cudaMemcpyAsync(&total_rows, row_off.p + n_buckets, 8, cudaMemcpyDeviceToHost, c.stream));
+    SKA_CUDA(cudaMemcpyAsync(&total_rows, row_off.p + n_items, 8, cudaMemcpyDeviceToHost, c.stream));
     SKA_CUDA(cudaStreamSynchronize(c.stream));
     timer().end();
-    if (h_flags[0]) throw Error("bucket overflow in count pass: too many distinct split k-mers share a key prefix");
     const uint32_t max_u = h_flags[1];
 
     // (2b) emit
@@ -309,13 +383,10 @@ void build_array_from_records(uint64_t* rec, uint16_t* sid, uint64_t n_pos, uint
     if (total_rows) {
         int log_cap = 6;
         while ((1u << log_cap) < 2 * max_u) log_cap++;
-        const uint32_t n8 = (uint32_t)((n_samples + 7) / 8);
-        size_t smem = ((size_t)1 << log_cap) * (8 + 8 + 4 * (size_t)n8 + 2);
-        if (log_cap > 15 || smem > c.smem_optin)
-            throw Error("bucket too large for shared-memory merge (distinct keys " + std::to_string(max_u) + ", samples " +
-                        std::to_string(n_samples) + ")");
+        size_t smem = ((size_t)1 << log_cap) * slot_bytes;
+        if (log_cap > max_log_cap) throw Error("internal: item larger than the shared-memory table");
         SKA_CUDA(cudaFuncSetAttribute(bucket_emit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        SKA_LAUNCH(bucket_emit_kernel, n_buckets, MG_THREADS, smem, rec_sorted, sid_sorted, off.p, row_off.p, log_cap,
+        SKA_LAUNCH(bucket_emit_kernel, n_items, MG_THREADS, smem, rec_sorted, sid_sorted, items.p, row_off.p, log_cap,
                    (uint32_t)n_samples, (int)k, rc ? 1 : 0, out.keys.p, out.variants.p, out.counts.p);
     }
     timer().end();
