@@ -218,9 +218,13 @@ def run_ours(args, rank, world, local_rank):
         e2e_step()
     barrier()
     S.api.timer_start()
+    walls = []
     for _ in range(args.steps):
+        tw = time.perf_counter()
         e2e_step()
+        walls.append(round((time.perf_counter() - tw) * 1e3, 1))
     ms_e2e = S.api.timer_stop()
+    log(f"e2e per-step wall ms: {walls}; last build stages {[(s, round(ms, 2)) for s, ms, _ in S.api.last_timings()]}")
     barrier()
     ms_e2e = max_over_ranks(ms_e2e)
     log(f"e2e arm: {ms_e2e / args.steps:.2f} ms/step")

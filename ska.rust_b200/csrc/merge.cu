@@ -21,6 +21,8 @@
 // round-1 scaffolding; DESIGN.md "partition" lists its replacement).  Steps (2) are hand-written.
 #include <cub/cub.cuh>
 
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace ska {
@@ -157,51 +159,57 @@ __device__ __forceinline__ uint32_t pal_letter(uint32_t m) {
     return at && cg ? 'N' : (at ? 'W' : 'S');
 }
 
-// ---- pass 2: reduce a bucket in shared memory and emit its rows in key order
-// dynamic smem layout: tab u64[cap] | list_key u64[cap] | mat u32[cap * n8] | list_slot u16[cap]
+// ---- pass 2: reduce one item and emit its rows in key order.
+// Phases (one CTA per item, all phases separated by CTA barriers):
+//   1. insert the item's keys into a shared-memory open-addressing table (atomicCAS)
+//   2. compact the occupied slots and bitonic-sort them by key -> rank of every slot
+//   3. write the sorted keys; zero the item's rows of the output matrix (they are L2-resident:
+//      a few hundred rows x N bytes)
+//   4. stream the records again (L2 hits): probe the table read-only, OR the record's 4-bit base
+//      set into byte (row, sample) of the OUTPUT matrix with a 32-bit global RED.OR
+//   5. convert the item's rows in place from base sets to IUPAC letters ('-' for empty; W/S/N for
+//      palindromic keys, ska_dict.rs:85-113) and count the non-missing cells per row.
+// dynamic smem: tab u64[cap] | lkey u64[cap/2] | rank u16[cap] | lslot u16[cap/2] | cnt u32[cap/2]
 __global__ void __launch_bounds__(MG_THREADS)
 bucket_emit_kernel(const uint64_t* __restrict__ rec, const uint16_t* __restrict__ sid, const Item* __restrict__ items,
                    const uint64_t* __restrict__ row_off, int log_cap, uint32_t n_samples, int k, int rc,
                    uint64_t* __restrict__ out_keys, uint8_t* __restrict__ out_var, uint32_t* __restrict__ out_cnt) {
     extern __shared__ __align__(16) uint8_t smem[];
-    const uint32_t cap = 1u << log_cap;
-    const uint32_t n8 = (n_samples + 7) / 8;                 // u32 words of 8 nibbles per row
+    const uint32_t cap = 1u << log_cap, half = cap >> 1;
     uint64_t* s_tab = reinterpret_cast<uint64_t*>(smem);
     uint64_t* s_lkey = s_tab + cap;
-    uint32_t* s_mat = reinterpret_cast<uint32_t*>(s_lkey + cap);
-    uint16_t* s_lslot = reinterpret_cast<uint16_t*>(s_mat + (size_t)cap * n8);
+    uint32_t* s_cnt = reinterpret_cast<uint32_t*>(s_lkey + half);
+    uint16_t* s_rank = reinterpret_cast<uint16_t*>(s_cnt + half);
+    uint16_t* s_lslot = s_rank + cap;
     __shared__ uint32_t s_u;
 
     const uint32_t b = blockIdx.x;
     const Item it = items[b];
     const uint64_t beg = it.beg, end = it.end;
     const uint64_t row_base = row_off[b];
-    const uint32_t u_expect = (uint32_t)(row_off[b + 1] - row_base);
-    if (u_expect == 0) return;
+    const uint32_t u = (uint32_t)(row_off[b + 1] - row_base);     // distinct keys, from the count pass
+    if (u == 0) return;
 
     for (uint32_t i = threadIdx.x; i < cap; i += MG_THREADS) s_tab[i] = KEY_EMPTY;
-    for (uint32_t i = threadIdx.x; i < cap * n8; i += MG_THREADS) s_mat[i] = 0;
     if (threadIdx.x == 0) s_u = 0;
     __syncthreads();
 
-    // phase 1: insert
+    // phase 1
     for (uint64_t i = beg + threadIdx.x; i < end; i += MG_THREADS) {
         uint64_t r = rec[i];
         if (r == REC_SENTINEL) continue;
         uint64_t key = r >> 4;
         if (key < it.key_lo || key > it.key_hi) continue;
-        uint32_t s = sid[i];
         uint32_t slot = hash_slot(key, log_cap);
         while (true) {
             unsigned long long old = atomicCAS((unsigned long long*)&s_tab[slot], KEY_EMPTY, key);
             if (old == KEY_EMPTY || old == key) break;
             slot = (slot + 1) & (cap - 1);
         }
-        atomicOr(&s_mat[slot * n8 + (s >> 3)], (uint32_t)(r & 0xF) << (4 * (s & 7)));
     }
     __syncthreads();
 
-    // phase 2: compact occupied slots, then bitonic sort by key
+    // phase 2
     for (uint32_t i = threadIdx.x; i < cap; i += MG_THREADS) {
         uint64_t key = s_tab[i];
         if (key != KEY_EMPTY) {
@@ -211,14 +219,13 @@ bucket_emit_kernel(const uint64_t* __restrict__ rec, const uint16_t* __restrict_
         }
     }
     __syncthreads();
-    const uint32_t u = s_u;                                  // == u_expect
     uint32_t np2 = 1; while (np2 < u) np2 <<= 1;
     for (uint32_t i = u + threadIdx.x; i < np2; i += MG_THREADS) { s_lkey[i] = KEY_EMPTY; s_lslot[i] = 0; }
     __syncthreads();
     for (uint32_t size = 2; size <= np2; size <<= 1) {
         for (uint32_t stride = size >> 1; stride > 0; stride >>= 1) {
             for (uint32_t t = threadIdx.x; t < np2 / 2; t += MG_THREADS) {
-                uint32_t lo = 2 * t - (t & (stride - 1));    // index with bit `stride` clear
+                uint32_t lo = 2 * t - (t & (stride - 1));
                 uint32_t hi = lo + stride;
                 bool up = ((lo & size) == 0);
                 uint64_t a = s_lkey[lo], c = s_lkey[hi];
@@ -231,49 +238,75 @@ bucket_emit_kernel(const uint64_t* __restrict__ rec, const uint16_t* __restrict_
         }
     }
 
-    // phase 3a: keys, counts, palindrome flag (bit 15 of the slot entry)
+    // phase 3: ranks, keys, palindrome flags (bit 15 of lslot), zero the rows
     for (uint32_t i = threadIdx.x; i < u; i += MG_THREADS) {
         uint64_t key = s_lkey[i];
-        uint32_t slot = s_lslot[i] & 0x7FFFu;
-        uint32_t c = 0;
-        for (uint32_t w = 0; w < n8; w++) {
-            uint32_t v = s_mat[slot * n8 + w];
-            c += __popc((v | (v >> 1) | (v >> 2) | (v >> 3)) & 0x11111111u);
-        }
+        uint32_t slot = s_lslot[i];
+        s_rank[slot] = (uint16_t)i;
         out_keys[row_base + i] = key;
-        out_cnt[row_base + i] = c;
         bool pal = rc && (revcomp_key(key, k - 1) == key);
-        s_lslot[i] = (uint16_t)(slot | (pal ? 0x8000u : 0u));
+        s_lslot[i] = (uint16_t)(pal ? 1u : 0u);
+        s_cnt[i] = 0;
     }
+    const uint64_t byte_beg = row_base * n_samples, byte_end = (row_base + u) * n_samples;
+    const uint64_t w_beg = byte_beg >> 2, w_end = (byte_end + 3) >> 2;    // 32-bit words touching the rows
+    uint32_t* out32 = reinterpret_cast<uint32_t*>(out_var);
+    const bool aligned = ((n_samples & 3u) == 0);
+    if (aligned) {
+        for (uint64_t w = w_beg + threadIdx.x; w < w_end; w += MG_THREADS) out32[w] = 0u;
+    } else {
+        // rows of neighbouring items may share the boundary words: clear bytes with atomics there
+        for (uint64_t o = byte_beg + threadIdx.x; o < byte_end; o += MG_THREADS)
+            atomicAnd(&out32[o >> 2], ~(0xFFu << (8 * (o & 3))));
+    }
+    __threadfence();
     __syncthreads();
 
-    // phase 3b: letters, row-major, coalesced
-    uint8_t* dst = out_var + row_base * n_samples;
-    if ((n_samples & 3u) == 0) {
-        const uint32_t g_per_row = n_samples >> 2;
-        uint32_t* dst32 = reinterpret_cast<uint32_t*>(dst);   // row_base*n_samples is a multiple of 4
-        for (uint32_t idx = threadIdx.x; idx < u * g_per_row; idx += MG_THREADS) {
-            uint32_t i = idx / g_per_row, g = idx - i * g_per_row;
-            uint32_t e = s_lslot[i];
-            uint32_t slot = e & 0x7FFFu; bool pal = e & 0x8000u;
-            uint32_t nib = (s_mat[slot * n8 + (g >> 1)] >> (16 * (g & 1))) & 0xFFFFu;
-            uint32_t word = 0;
+    // phase 4
+    for (uint64_t i = beg + threadIdx.x; i < end; i += MG_THREADS) {
+        uint64_t r = rec[i];
+        if (r == REC_SENTINEL) continue;
+        uint64_t key = r >> 4;
+        if (key < it.key_lo || key > it.key_hi) continue;
+        uint32_t s = sid[i];
+        uint32_t slot = hash_slot(key, log_cap);
+        while (s_tab[slot] != key) slot = (slot + 1) & (cap - 1);
+        uint64_t o = (row_base + s_rank[slot]) * n_samples + s;
+        atomicOr(&out32[o >> 2], (uint32_t)(r & 0xF) << (8 * (o & 3)));
+    }
+    __threadfence();
+    __syncthreads();
+
+    // phase 5
+    if (aligned) {
+        const uint32_t wpr = n_samples >> 2;
+        for (uint64_t w = w_beg + threadIdx.x; w < w_end; w += MG_THREADS) {
+            uint32_t i = (uint32_t)((w - w_beg) / wpr);
+            uint32_t v = __ldcg(&out32[w]);
+            bool pal = s_lslot[i];
+            uint32_t word = 0, nz = 0;
 #pragma unroll
             for (int q = 0; q < 4; q++) {
-                uint32_t m = (nib >> (4 * q)) & 0xFu;
+                uint32_t m = (v >> (8 * q)) & 0xFu;
+                nz += (m != 0);
                 word |= (pal ? pal_letter(m) : iupac_letter(m)) << (8 * q);
             }
-            dst32[idx] = word;
+            out32[w] = word;
+            if (nz) atomicAdd(&s_cnt[i], nz);
         }
     } else {
-        for (uint32_t idx = threadIdx.x; idx < u * n_samples; idx += MG_THREADS) {
-            uint32_t i = idx / n_samples, s = idx - i * n_samples;
-            uint32_t e = s_lslot[i];
-            uint32_t slot = e & 0x7FFFu; bool pal = e & 0x8000u;
-            uint32_t m = (s_mat[slot * n8 + (s >> 3)] >> (4 * (s & 7))) & 0xFu;
-            dst[idx] = (uint8_t)(pal ? pal_letter(m) : iupac_letter(m));
+        for (uint64_t o = byte_beg + threadIdx.x; o < byte_end; o += MG_THREADS) {
+            uint32_t i = (uint32_t)((o - byte_beg) / n_samples);
+            uint32_t m = (__ldcg(&out32[o >> 2]) >> (8 * (o & 3))) & 0xFu;
+            bool pal = s_lslot[i];
+            if (m) atomicAdd(&s_cnt[i], 1u);
+            uint32_t letter = pal ? pal_letter(m) : iupac_letter(m);
+            // byte store; neighbouring bytes of the word may belong to another item's rows
+            out_var[o] = (uint8_t)letter;
         }
     }
+    __syncthreads();
+    for (uint32_t i = threadIdx.x; i < u; i += MG_THREADS) out_cnt[row_base + i] = s_cnt[i];
 }
 
 static int choose_prefix_bits(uint64_t n_pos, int key_bits, uint64_t target) {
@@ -286,20 +319,16 @@ void build_array_from_records(uint64_t* rec, uint16_t* sid, uint64_t n_pos, uint
                               Array& out) {
     Context& c = ctx();
     const int key_bits = 2 * ((int)k - 1);
-    const uint32_t n8 = (uint32_t)((n_samples + 7) / 8);
-    const size_t slot_bytes = 8 + 8 + 4 * (size_t)n8 + 2;
-    // largest table the emit kernel may use, and therefore the most distinct keys an item may hold
-    int max_log_cap = 6;
-    while (max_log_cap < 15 && ((size_t)2 << max_log_cap) * slot_bytes <= c.smem_optin - 1024) max_log_cap++;
-    if (((size_t)1 << max_log_cap) * slot_bytes > c.smem_optin - 1024)
-        throw Error("too many samples for the shared-memory merge (" + std::to_string(n_samples) + ")");
-    const uint32_t limit = std::min<uint32_t>((1u << max_log_cap) / 2, COUNT_CAP - COUNT_CAP / 4 - 1);
+    // bytes of shared memory per table slot in the emit kernel: tab 8 + rank 2 + (lkey 8 + lslot 2 + cnt 4)/2
+    const size_t slot_bytes = 17;
+    const int max_log_cap = 13;                                   // 8192 slots = 136 KB
+    const uint32_t limit = COUNT_CAP - COUNT_CAP / 4 - 1;         // most distinct keys one item may hold (3071)
 
-    // records per bucket: small enough that distinct keys per bucket normally stay under `limit`
-    // (canonical k-mers crowd the low prefixes about 2x), but keep to 2 radix passes when possible
-    uint64_t target = std::min<uint64_t>(4096, std::max<uint64_t>(256, (uint64_t)limit));
-    int P = choose_prefix_bits(n_pos, key_bits, target);
-    if (P > 16 && (n_pos >> 16) <= 4 * target) P = 16;
+    // records per bucket ~4096, but stay at 16 prefix bits (two 8-bit radix passes) while buckets
+    // remain small enough for the shared-memory tables
+    int P = choose_prefix_bits(n_pos, key_bits, 4096);
+    if (P > 16 && (n_pos >> 16) <= 16384) P = 16;
+    if (const char* e = getenv("SKA_PREFIX_BITS")) { int v = atoi(e); if (v >= 0 && v <= key_bits && v <= 24) P = v; }   // tuning/tests
     const uint32_t n_buckets = 1u << P;
     const int shift = 4 + key_bits - P;
 
