@@ -110,11 +110,12 @@ __device__ __forceinline__ uint32_t le_to_be(uint32_t x) {
     return ((y & 0x55555555u) << 1) | ((y >> 1) & 0x55555555u);
 }
 
-template <bool HAS_QUAL>
+// KT > 0: k fixed at compile time (all shifts/masks become immediates); KT == 0: runtime k.
+template <int KT, bool HAS_QUAL>
 __global__ void __launch_bounds__(K1_THREADS)
 k1_extract_kernel(const uint8_t* __restrict__ seq, const uint8_t* __restrict__ qual,
                   const uint32_t* __restrict__ start_bits, const uint64_t* __restrict__ sample_off,
-                  uint32_t n_samples, uint64_t n_pos, int k, int rc, uint32_t min_qual,
+                  uint32_t n_samples, uint64_t n_pos, int k_rt, int rc, uint32_t min_qual,
                   uint64_t* __restrict__ rec_out, uint16_t* __restrict__ sid_out, uint32_t* __restrict__ sample_valid) {
     __shared__ __align__(128) uint8_t s_ascii[K1_BYTES];
     __shared__ __align__(128) uint8_t s_qual[HAS_QUAL ? K1_BYTES : 16];
@@ -127,6 +128,7 @@ k1_extract_kernel(const uint8_t* __restrict__ seq, const uint8_t* __restrict__ q
     __shared__ uint32_t s_sid[2];
     __shared__ uint32_t s_nvalid;
 
+    const int k = KT ? KT : k_rt;
     const int tid = threadIdx.x;
     const uint64_t t0 = (uint64_t)blockIdx.x * K1_T;        // first window-start position of this tile
     // staged region covers positions [t0 - K1_LEAD, t0 + K1_T + K1_TAIL); position p lives at seq[FRONT_PAD + p]
@@ -186,13 +188,16 @@ k1_extract_kernel(const uint8_t* __restrict__ seq, const uint8_t* __restrict__ q
         const int j = tid;
         B128 bad = {(uint64_t)s_bad[j] | ((uint64_t)s_bad[j + 1] << 32), (uint64_t)s_bad[j + 2] | ((uint64_t)s_bad[j + 3] << 32)};
         B128 st = {(uint64_t)s_start[j] | ((uint64_t)s_start[j + 1] << 32), (uint64_t)s_start[j + 2] | ((uint64_t)s_start[j + 3] << 32)};
-        B128 bad_any = slide_or(bad, k);                          // any invalid base in [n, n+k)
-        B128 st_any = shr128(slide_or(st, k - 1), 1);             // any record start in (n, n+k)
-        B128 bad_prev = {bad.lo << 1, (bad.hi << 1) | (bad.lo >> 63)};   // bad[n-1]
-        B128 run_start = or128(st, bad_prev);                     // a valid run begins at n
-        B128 rec_end = shr128(st, k);                             // record ends right after the window
-        uint64_t not_ok = bad_any.lo | st_any.lo | (run_start.lo & rec_end.lo);   // split_kmer.rs:89,121
-        uint32_t ok = ~(uint32_t)(not_ok >> 32);
+        uint32_t ok = 0xFFFFFFFFu;
+        if ((bad.lo | bad.hi | st.lo | st.hi) != 0) {            // fast path: clean sequence, no boundary nearby
+            B128 bad_any = slide_or(bad, k);                          // any invalid base in [n, n+k)
+            B128 st_any = shr128(slide_or(st, k - 1), 1);             // any record start in (n, n+k)
+            B128 bad_prev = {bad.lo << 1, (bad.hi << 1) | (bad.lo >> 63)};   // bad[n-1]
+            B128 run_start = or128(st, bad_prev);                     // a valid run begins at n
+            B128 rec_end = shr128(st, k);                             // record ends right after the window
+            uint64_t not_ok = bad_any.lo | st_any.lo | (run_start.lo & rec_end.lo);   // split_kmer.rs:89,121
+            ok = ~(uint32_t)(not_ok >> 32);
+        }
         // windows at or beyond n_pos do not exist
         uint64_t p0 = t0 + 32ull * j;
         if (p0 >= n_pos) ok = 0;
@@ -202,63 +207,76 @@ k1_extract_kernel(const uint8_t* __restrict__ seq, const uint8_t* __restrict__ q
     }
     __syncthreads();
 
-    // ---- extract
+    // ---- extract: lane l of warp w takes windows 32j + l, j = w, w+8, ...
     const int lane = tid & 31, warp = tid >> 5;
     const int h = (k - 1) >> 1;
-    const uint64_t mask2k = (k == 32) ? ~0ULL : ((1ULL << (2 * k)) - 1ULL);
+    const uint64_t mask2k = (1ULL << (2 * k)) - 1ULL;             // k <= 31
     const uint64_t lm = (1ULL << (2 * h)) - 1ULL;                 // lower-arm mask
     const uint64_t aa = 0xAAAAAAAAAAAAAAAAULL & mask2k;
     const uint32_t sid_first = s_sid[0], sid_last = s_sid[1];
+    const bool uniform = sid_first == sid_last;
+    const bool full = (t0 + K1_T <= n_pos);
+    const int sh = 2 * (lane & 15);
+    const uint32_t* be = s_be + ((K1_LEAD + lane) >> 4);          // word holding this lane's first base for j = 0
+    const uint32_t* le = s_le + ((K1_LEAD + lane) >> 4);
+    uint64_t* out = rec_out + t0 + lane;
+    uint16_t* sout = sid_out ? sid_out + t0 + lane : nullptr;
+#pragma unroll 4
     for (int j = warp; j < K1_T / 32; j += K1_THREADS / 32) {
-        const uint64_t p = t0 + 32ull * j + lane;
-        if (p >= n_pos) break;
+        if (!full && t0 + 32ull * j + lane >= n_pos) break;
         const uint32_t ok = s_ok[j];
-        uint64_t rec = REC_SENTINEL;
-        if ((ok >> lane) & 1u) {
-            const int r = K1_LEAD + 32 * j + lane;                // staged index of the window's first base
-            const int wi = r >> 4, sh = 2 * (r & 15);
-            // forward k-mer, first base most significant
-            uint32_t b0 = s_be[wi], b1 = s_be[wi + 1], b2 = s_be[wi + 2];
-            uint64_t top = ((uint64_t)__funnelshift_l(b1, b0, sh) << 32) | __funnelshift_l(b2, b1, sh);
-            uint64_t F = top >> (64 - 2 * k);
-            // LE window: base r at bit 0 -> XOR 0b10 per base = reverse complement, first base most significant
-            uint32_t l0 = s_le[wi], l1 = s_le[wi + 1], l2 = s_le[wi + 2];
-            uint64_t V = (((uint64_t)__funnelshift_r(l1, l2, sh) << 32) | __funnelshift_r(l0, l1, sh)) & mask2k;
-            uint64_t key = (F & lm) | ((F >> 2) & ~lm);
-            uint32_t mid = (uint32_t)(F >> (2 * h)) & 3u;
-            if (rc) {
-                uint64_t R = V ^ aa;
-                uint64_t rkey = (R & lm) | ((R >> 2) & ~lm);
-                if (key > rkey) { key = rkey; mid ^= 2u; }       // ties keep forward (split_kmer.rs:290)
-            }
-            rec = (key << 4) | (1ull << mid);
+        // forward k-mer (first base most significant) out of the BE stream
+        const uint32_t b0 = be[2 * j], b1 = be[2 * j + 1], b2 = be[2 * j + 2];
+        const uint64_t top = ((uint64_t)__funnelshift_l(b1, b0, sh) << 32) | __funnelshift_l(b2, b1, sh);
+        const uint64_t F = top >> (64 - 2 * k);
+        uint64_t key = (F & lm) | ((F >> 2) & ~lm);
+        uint32_t mid = (uint32_t)(F >> (2 * h)) & 3u;
+        if (rc) {
+            // LE window (base at bit 0) XOR 0b10 per base = reverse complement, first base most significant
+            const uint32_t l0 = le[2 * j], l1 = le[2 * j + 1], l2 = le[2 * j + 2];
+            const uint64_t V = (((uint64_t)__funnelshift_r(l1, l2, sh) << 32) | __funnelshift_r(l0, l1, sh)) & mask2k;
+            const uint64_t R = V ^ aa;
+            const uint64_t rkey = (R & lm) | ((R >> 2) & ~lm);
+            if (key > rkey) { key = rkey; mid ^= 2u; }            // ties keep forward (split_kmer.rs:290)
         }
-        rec_out[p] = rec;
-        uint32_t s = sid_first;
-        if (sid_first != sid_last) {                              // tile straddles samples (rare)
+        const uint32_t klo = (uint32_t)key, khi = (uint32_t)(key >> 32);
+        uint64_t rec = ((uint64_t)__funnelshift_l(klo, khi, 4) << 32) | ((klo << 4) | (1u << mid));
+        if (!((ok >> lane) & 1u)) rec = REC_SENTINEL;
+        out[32 * j] = rec;
+        if (uniform) {
+            if (sout) sout[32 * j] = (uint16_t)sid_first;
+        } else {                                                  // tile straddles samples (rare)
+            const uint64_t p = t0 + 32ull * j + lane;
             uint32_t lo = sid_first, hi = sid_last + 1;
             while (hi - lo > 1) { uint32_t m = (lo + hi) >> 1; if (sample_off[m] <= p) lo = m; else hi = m; }
-            s = lo;
-            if (sample_valid && rec != REC_SENTINEL) atomicAdd(&sample_valid[s], 1u);
+            if (sample_valid && rec != REC_SENTINEL) atomicAdd(&sample_valid[lo], 1u);
+            if (sout) sout[32 * j] = (uint16_t)lo;
         }
-        if (sid_out) sid_out[p] = (uint16_t)s;
     }
     // accepted windows per sample (a sample with none is an error, ska_dict.rs:374-376)
-    if (tid == 0 && sample_valid && sid_first == sid_last && s_nvalid) atomicAdd(&sample_valid[sid_first], s_nvalid);
+    if (tid == 0 && sample_valid && uniform && s_nvalid) atomicAdd(&sample_valid[sid_first], s_nvalid);
+}
+
+template <int KT>
+static void launch_k1_kt(const SeqBatch& b, uint32_t k, bool rc, bool strict_qual, uint8_t min_qual, uint64_t* rec_out,
+                         uint16_t* sid_out, uint32_t* sample_valid) {
+    unsigned grid = (unsigned)((b.n_pos + K1_T - 1) / K1_T);
+    if (b.has_qual && strict_qual) {
+        SKA_LAUNCH((k1_extract_kernel<KT, true>), grid, K1_THREADS, 0, b.seq.p, b.qual.p, b.start_bits.p, b.sample_off.p,
+                   (uint32_t)b.n_samples, b.n_pos, (int)k, rc ? 1 : 0, (uint32_t)min_qual, rec_out, sid_out, sample_valid);
+    } else {
+        SKA_LAUNCH((k1_extract_kernel<KT, false>), grid, K1_THREADS, 0, b.seq.p, (const uint8_t*)nullptr, b.start_bits.p,
+                   b.sample_off.p, (uint32_t)b.n_samples, b.n_pos, (int)k, rc ? 1 : 0, (uint32_t)min_qual, rec_out, sid_out,
+                   sample_valid);
+    }
 }
 
 void launch_k1(const SeqBatch& b, uint32_t k, bool rc, bool strict_qual, uint8_t min_qual, uint64_t* rec_out,
                uint16_t* sid_out, uint32_t* sample_valid) {
     if (b.n_pos == 0) return;
-    unsigned grid = (unsigned)((b.n_pos + K1_T - 1) / K1_T);
-    if (b.has_qual && strict_qual) {
-        SKA_LAUNCH(k1_extract_kernel<true>, grid, K1_THREADS, 0, b.seq.p, b.qual.p, b.start_bits.p, b.sample_off.p,
-                   (uint32_t)b.n_samples, b.n_pos, (int)k, rc ? 1 : 0, (uint32_t)min_qual, rec_out, sid_out, sample_valid);
-    } else {
-        SKA_LAUNCH(k1_extract_kernel<false>, grid, K1_THREADS, 0, b.seq.p, (const uint8_t*)nullptr, b.start_bits.p,
-                   b.sample_off.p, (uint32_t)b.n_samples, b.n_pos, (int)k, rc ? 1 : 0, (uint32_t)min_qual, rec_out, sid_out,
-                   sample_valid);
-    }
+    // the default k of `ska build` (cli.rs:9) gets a compile-time specialisation
+    if (k == 31) launch_k1_kt<31>(b, k, rc, strict_qual, min_qual, rec_out, sid_out, sample_valid);
+    else launch_k1_kt<0>(b, k, rc, strict_qual, min_qual, rec_out, sid_out, sample_valid);
 }
 
 }  // namespace ska

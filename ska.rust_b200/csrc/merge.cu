@@ -28,6 +28,7 @@
 namespace ska {
 
 constexpr int MG_THREADS = 256;
+constexpr int MG_UNROLL = 4;               // records loaded per thread before any is processed
 constexpr int COUNT_CAP = 4096;             // key slots of the counting pass (32 KB)
 constexpr uint64_t KEY_EMPTY = ~0ULL;
 
@@ -79,25 +80,32 @@ bucket_count_kernel(const uint64_t* __restrict__ rec, const Item* __restrict__ i
     for (int i = threadIdx.x; i < COUNT_CAP; i += MG_THREADS) s_tab[i] = KEY_EMPTY;
     if (threadIdx.x == 0) { s_n = 0; s_over = 0; }
     __syncthreads();
-    uint32_t mine = 0;
-    for (uint64_t i = it.beg + threadIdx.x; i < it.end; i += MG_THREADS) {
-        uint64_t r = rec[i];
-        if (r == REC_SENTINEL) continue;
-        uint64_t key = r >> 4;
-        if (key < it.key_lo || key > it.key_hi) continue;
-        if (*(volatile uint32_t*)&s_over) break;
-        uint32_t slot = hash_slot(key, 12);
-        int probes = 0;
-        while (true) {
-            unsigned long long old = atomicCAS((unsigned long long*)&s_tab[slot], KEY_EMPTY, key);
-            if (old == KEY_EMPTY) {
-                mine++;
-                if (atomicAdd(&s_n, 1u) >= COUNT_CAP - COUNT_CAP / 4) s_over = 1;   // keep the table sparse enough to probe
-                break;
+    for (uint64_t base = it.beg + threadIdx.x; base < it.end; base += MG_UNROLL * MG_THREADS) {
+        uint64_t rr[MG_UNROLL];
+#pragma unroll
+        for (int j = 0; j < MG_UNROLL; j++) {                      // all loads first: memory-level parallelism
+            uint64_t i = base + (uint64_t)j * MG_THREADS;
+            rr[j] = i < it.end ? rec[i] : REC_SENTINEL;
+        }
+#pragma unroll
+        for (int j = 0; j < MG_UNROLL; j++) {
+            uint64_t r = rr[j];
+            if (r == REC_SENTINEL) continue;
+            uint64_t key = r >> 4;
+            if (key < it.key_lo || key > it.key_hi) continue;
+            if (*(volatile uint32_t*)&s_over) break;
+            uint32_t slot = hash_slot(key, 12);
+            int probes = 0;
+            while (true) {
+                unsigned long long old = atomicCAS((unsigned long long*)&s_tab[slot], KEY_EMPTY, key);
+                if (old == KEY_EMPTY) {
+                    if (atomicAdd(&s_n, 1u) >= COUNT_CAP - COUNT_CAP / 4) s_over = 1;   // keep the table sparse enough to probe
+                    break;
+                }
+                if (old == key) break;
+                slot = (slot + 1) & (COUNT_CAP - 1);
+                if (++probes >= COUNT_CAP) { s_over = 1; break; }
             }
-            if (old == key) break;
-            slot = (slot + 1) & (COUNT_CAP - 1);
-            if (++probes >= COUNT_CAP) { s_over = 1; break; }
         }
     }
     __syncthreads();
@@ -195,16 +203,25 @@ bucket_emit_kernel(const uint64_t* __restrict__ rec, const uint16_t* __restrict_
     __syncthreads();
 
     // phase 1
-    for (uint64_t i = beg + threadIdx.x; i < end; i += MG_THREADS) {
-        uint64_t r = rec[i];
-        if (r == REC_SENTINEL) continue;
-        uint64_t key = r >> 4;
-        if (key < it.key_lo || key > it.key_hi) continue;
-        uint32_t slot = hash_slot(key, log_cap);
-        while (true) {
-            unsigned long long old = atomicCAS((unsigned long long*)&s_tab[slot], KEY_EMPTY, key);
-            if (old == KEY_EMPTY || old == key) break;
-            slot = (slot + 1) & (cap - 1);
+    for (uint64_t base = beg + threadIdx.x; base < end; base += MG_UNROLL * MG_THREADS) {
+        uint64_t rr[MG_UNROLL];
+#pragma unroll
+        for (int j = 0; j < MG_UNROLL; j++) {
+            uint64_t i = base + (uint64_t)j * MG_THREADS;
+            rr[j] = i < end ? rec[i] : REC_SENTINEL;
+        }
+#pragma unroll
+        for (int j = 0; j < MG_UNROLL; j++) {
+            uint64_t r = rr[j];
+            if (r == REC_SENTINEL) continue;
+            uint64_t key = r >> 4;
+            if (key < it.key_lo || key > it.key_hi) continue;
+            uint32_t slot = hash_slot(key, log_cap);
+            while (true) {
+                unsigned long long old = atomicCAS((unsigned long long*)&s_tab[slot], KEY_EMPTY, key);
+                if (old == KEY_EMPTY || old == key) break;
+                slot = (slot + 1) & (cap - 1);
+            }
         }
     }
     __syncthreads();
@@ -263,36 +280,57 @@ bucket_emit_kernel(const uint64_t* __restrict__ rec, const uint16_t* __restrict_
     __syncthreads();
 
     // phase 4
-    for (uint64_t i = beg + threadIdx.x; i < end; i += MG_THREADS) {
-        uint64_t r = rec[i];
-        if (r == REC_SENTINEL) continue;
-        uint64_t key = r >> 4;
-        if (key < it.key_lo || key > it.key_hi) continue;
-        uint32_t s = sid[i];
-        uint32_t slot = hash_slot(key, log_cap);
-        while (s_tab[slot] != key) slot = (slot + 1) & (cap - 1);
-        uint64_t o = (row_base + s_rank[slot]) * n_samples + s;
-        atomicOr(&out32[o >> 2], (uint32_t)(r & 0xF) << (8 * (o & 3)));
+    for (uint64_t base = beg + threadIdx.x; base < end; base += MG_UNROLL * MG_THREADS) {
+        uint64_t rr[MG_UNROLL]; uint32_t ss[MG_UNROLL];
+#pragma unroll
+        for (int j = 0; j < MG_UNROLL; j++) {
+            uint64_t i = base + (uint64_t)j * MG_THREADS;
+            bool in = i < end;
+            rr[j] = in ? rec[i] : REC_SENTINEL;
+            ss[j] = in ? sid[i] : 0;
+        }
+#pragma unroll
+        for (int j = 0; j < MG_UNROLL; j++) {
+            uint64_t r = rr[j];
+            if (r == REC_SENTINEL) continue;
+            uint64_t key = r >> 4;
+            if (key < it.key_lo || key > it.key_hi) continue;
+            uint32_t slot = hash_slot(key, log_cap);
+            while (s_tab[slot] != key) slot = (slot + 1) & (cap - 1);
+            uint64_t o = (row_base + s_rank[slot]) * n_samples + ss[j];
+            atomicOr(&out32[o >> 2], (uint32_t)(r & 0xF) << (8 * (o & 3)));
+        }
     }
     __threadfence();
     __syncthreads();
 
     // phase 5
     if (aligned) {
-        const uint32_t wpr = n_samples >> 2;
-        for (uint64_t w = w_beg + threadIdx.x; w < w_end; w += MG_THREADS) {
-            uint32_t i = (uint32_t)((w - w_beg) / wpr);
-            uint32_t v = __ldcg(&out32[w]);
-            bool pal = s_lslot[i];
-            uint32_t word = 0, nz = 0;
+        const uint32_t wpr = n_samples >> 2;                      // words per row
+        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+        for (uint32_t i = warp; i < u; i += MG_THREADS / 32) {     // one warp per row
+            const bool pal = s_lslot[i];
+            uint32_t* rowp = out32 + w_beg + (uint64_t)i * wpr;
+            uint32_t nz = 0;
+            for (uint32_t w0 = lane; w0 < wpr; w0 += 32 * MG_UNROLL) {
+                uint32_t vv[MG_UNROLL];
 #pragma unroll
-            for (int q = 0; q < 4; q++) {
-                uint32_t m = (v >> (8 * q)) & 0xFu;
-                nz += (m != 0);
-                word |= (pal ? pal_letter(m) : iupac_letter(m)) << (8 * q);
+                for (int j = 0; j < MG_UNROLL; j++) vv[j] = (w0 + 32 * j < wpr) ? __ldcg(&rowp[w0 + 32 * j]) : 0u;
+#pragma unroll
+                for (int j = 0; j < MG_UNROLL; j++) {
+                    if (w0 + 32 * j >= wpr) break;
+                    uint32_t v = vv[j], word = 0;
+#pragma unroll
+                    for (int q = 0; q < 4; q++) {
+                        uint32_t m = (v >> (8 * q)) & 0xFu;
+                        nz += (m != 0);
+                        word |= (pal ? pal_letter(m) : iupac_letter(m)) << (8 * q);
+                    }
+                    rowp[w0 + 32 * j] = word;
+                }
             }
-            out32[w] = word;
-            if (nz) atomicAdd(&s_cnt[i], nz);
+            nz = __reduce_add_sync(0xFFFFFFFFu, nz);
+            if (lane == 0) s_cnt[i] = nz;
         }
     } else {
         for (uint64_t o = byte_beg + threadIdx.x; o < byte_end; o += MG_THREADS) {
