@@ -239,6 +239,7 @@ int32_t filter_array(Array& a, uint64_t min_count, bool filter_ambig_as_missing,
     const int kw = a.key_bits / 64;
     if (R == 0) return 0;
     const uint32_t n_cta = (uint32_t)((R + FL_ROWS - 1) / FL_ROWS);
+    timer().begin("filter");
     DevBuf<uint8_t> flags(R);
     DevBuf<uint32_t> new_cnt(R), keep1(n_cta), keep2(n_cta), scratch(1);
     DevBuf<uint64_t> off1(n_cta + 1), off2(n_cta + 1);
@@ -267,6 +268,7 @@ int32_t filter_array(Array& a, uint64_t min_count, bool filter_ambig_as_missing,
     if (key_mode) { n_keys_out = key_mode == 1 ? n1 : n2; out_keys.alloc(n_keys_out * kw); }
     SKA_LAUNCH(filter_scatter_kernel, n_cta, FL_THREADS, 0, a.variants.p, new_cnt.p, a.keys.p, flags.p, off1.p, off2.p, R,
                a.n_keys, N, kw, key_mode, mask_ambig ? 1 : 0, out_var.p, out_cnt.p, key_mode ? out_keys.p : (uint64_t*)nullptr);
+    timer().end();
     a.variants = std::move(out_var);
     a.counts = std::move(out_cnt);
     if (key_mode) { a.keys = std::move(out_keys); a.n_keys = n_keys_out; }
@@ -295,7 +297,9 @@ transpose_kernel(const uint8_t* __restrict__ in, uint64_t n_rows, uint32_t n_sam
 void transpose_array(const Array& a, uint8_t* d_out) {
     if (a.n_rows == 0 || a.n_samples == 0) return;
     dim3 grid((unsigned)((a.n_rows + TP_TILE - 1) / TP_TILE), (unsigned)((a.n_samples + TP_TILE - 1) / TP_TILE));
+    timer().begin("transpose");
     SKA_LAUNCH(transpose_kernel, grid, 256, 0, a.variants.p, a.n_rows, (uint32_t)a.n_samples, d_out);
+    timer().end();
 }
 
 }  // namespace ska

@@ -97,7 +97,11 @@ bucket_count_kernel(const uint64_t* __restrict__ rec, const Item* __restrict__ i
             uint32_t slot = hash_slot(key, 12);
             int probes = 0;
             while (true) {
-                unsigned long long old = atomicCAS((unsigned long long*)&s_tab[slot], KEY_EMPTY, key);
+                // most records repeat a key that is already in the table (one per sample): a plain
+                // load settles those; only an empty slot needs the atomic
+                unsigned long long old = *(volatile unsigned long long*)&s_tab[slot];
+                if (old == key) break;
+                if (old == KEY_EMPTY) old = atomicCAS((unsigned long long*)&s_tab[slot], KEY_EMPTY, key);
                 if (old == KEY_EMPTY) {
                     if (atomicAdd(&s_n, 1u) >= COUNT_CAP - COUNT_CAP / 4) s_over = 1;   // keep the table sparse enough to probe
                     break;
@@ -218,7 +222,9 @@ bucket_emit_kernel(const uint64_t* __restrict__ rec, const uint16_t* __restrict_
             if (key < it.key_lo || key > it.key_hi) continue;
             uint32_t slot = hash_slot(key, log_cap);
             while (true) {
-                unsigned long long old = atomicCAS((unsigned long long*)&s_tab[slot], KEY_EMPTY, key);
+                unsigned long long old = *(volatile unsigned long long*)&s_tab[slot];
+                if (old == key) break;
+                if (old == KEY_EMPTY) old = atomicCAS((unsigned long long*)&s_tab[slot], KEY_EMPTY, key);
                 if (old == KEY_EMPTY || old == key) break;
                 slot = (slot + 1) & (cap - 1);
             }
@@ -308,29 +314,39 @@ bucket_emit_kernel(const uint64_t* __restrict__ rec, const uint16_t* __restrict_
     if (aligned) {
         const uint32_t wpr = n_samples >> 2;                      // words per row
         const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-        for (uint32_t i = warp; i < u; i += MG_THREADS / 32) {     // one warp per row
-            const bool pal = s_lslot[i];
-            uint32_t* rowp = out32 + w_beg + (uint64_t)i * wpr;
-            uint32_t nz = 0;
-            for (uint32_t w0 = lane; w0 < wpr; w0 += 32 * MG_UNROLL) {
+        constexpr int NW = MG_THREADS / 32;
+        for (uint32_t i0 = warp; i0 < u; i0 += MG_UNROLL * NW) {   // one warp per row, MG_UNROLL rows in flight
+            uint32_t nz[MG_UNROLL];
+#pragma unroll
+            for (int j = 0; j < MG_UNROLL; j++) nz[j] = 0;
+            for (uint32_t w0 = lane; w0 < wpr; w0 += 32) {
                 uint32_t vv[MG_UNROLL];
 #pragma unroll
-                for (int j = 0; j < MG_UNROLL; j++) vv[j] = (w0 + 32 * j < wpr) ? __ldcg(&rowp[w0 + 32 * j]) : 0u;
+                for (int j = 0; j < MG_UNROLL; j++) {
+                    uint32_t i = i0 + j * NW;
+                    vv[j] = i < u ? __ldcg(&out32[w_beg + (uint64_t)i * wpr + w0]) : 0u;
+                }
 #pragma unroll
                 for (int j = 0; j < MG_UNROLL; j++) {
-                    if (w0 + 32 * j >= wpr) break;
+                    uint32_t i = i0 + j * NW;
+                    if (i >= u) break;
+                    const bool pal = s_lslot[i];
                     uint32_t v = vv[j], word = 0;
 #pragma unroll
                     for (int q = 0; q < 4; q++) {
                         uint32_t m = (v >> (8 * q)) & 0xFu;
-                        nz += (m != 0);
+                        nz[j] += (m != 0);
                         word |= (pal ? pal_letter(m) : iupac_letter(m)) << (8 * q);
                     }
-                    rowp[w0 + 32 * j] = word;
+                    out32[w_beg + (uint64_t)i * wpr + w0] = word;
                 }
             }
-            nz = __reduce_add_sync(0xFFFFFFFFu, nz);
-            if (lane == 0) s_cnt[i] = nz;
+#pragma unroll
+            for (int j = 0; j < MG_UNROLL; j++) {
+                uint32_t i = i0 + j * NW;
+                uint32_t t = __reduce_add_sync(0xFFFFFFFFu, nz[j]);
+                if (lane == 0 && i < u) s_cnt[i] = t;
+            }
         }
     } else {
         for (uint64_t o = byte_beg + threadIdx.x; o < byte_end; o += MG_THREADS) {
