@@ -2,7 +2,9 @@
 #pragma once
 #include <cuda_runtime.h>
 
+#include <chrono>
 #include <cstdint>
+#include <cstdlib>
 #include <cstdio>
 #include <stdexcept>
 #include <string>
@@ -59,7 +61,12 @@ template <class T> struct DevBuf {
     void alloc(size_t count) {
         release();
         n = count;
-        if (count) SKA_CUDA(cudaMallocAsync((void**)&p, count * sizeof(T), ctx().stream));
+        if (count) {
+            auto t0 = std::chrono::steady_clock::now();
+            SKA_CUDA(cudaMallocAsync((void**)&p, count * sizeof(T), ctx().stream));
+            double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+            if (ms > 1.0 && getenv("SKA_DEBUG_ALLOC")) fprintf(stderr, "[skagpu] slow alloc %.1f MB: %.2f ms\n", count * sizeof(T) / 1e6, ms);
+        }
     }
     void release() {
         if (p) cudaFreeAsync(p, ctx().stream);

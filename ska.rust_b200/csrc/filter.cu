@@ -109,14 +109,21 @@ filter_flags_kernel(const uint8_t* __restrict__ var, const uint32_t* __restrict_
 // ~10x fewer instructions than the warp-per-row kernel because nothing is reduced across lanes.  The
 // 32 rows a warp touches are 32 separate 128-byte lines; each line is fetched once and its remaining
 // sectors are served from L1 by the following loads of the same thread.
+// per byte value: bits 0-10 = one-hot of the NoAmbigOrConst value set, bit 16 = ambiguous, bit 17 = "good"
+// (neither '-' nor ambiguous)
+__device__ __forceinline__ uint32_t class_entry(uint32_t b) {
+    uint32_t bit = acgtu_bit(b);
+    bool amb = is_ambig_dev(b);
+    return (bit < 32 ? 1u << bit : 0u) | (amb ? 1u << 16 : 0u) | ((b != '-' && !amb) ? 1u << 17 : 0u);
+}
 struct RowState {
     uint32_t good, any_ambig, setbits, first, differs, ignore_gaps;
+    const uint32_t* lut;
     __device__ __forceinline__ void byte(uint32_t b) {
-        bool amb = is_ambig_dev(b);
-        any_ambig |= amb;
-        good += (b != '-' && !amb);
-        uint32_t bit = acgtu_bit(b);
-        if (bit < 32) setbits |= 1u << bit;
+        uint32_t e = lut[b];
+        any_ambig |= e >> 16 & 1u;
+        good += e >> 17;
+        setbits |= e & 0x7FFu;
         if (!ignore_gaps || b != '-') {
             if (first == 0xFFFFFFFFu) first = b; else differs |= (b != first);
         }
@@ -137,13 +144,15 @@ filter_flags_rows_kernel(const uint8_t* __restrict__ var, const uint32_t* __rest
                          uint64_t min_count, int ambig_missing, int ftype, int ignore_gaps, uint8_t* __restrict__ flags,
                          uint32_t* __restrict__ new_cnt, uint32_t* __restrict__ cta_keep1, uint32_t* __restrict__ cta_keep2) {
     __shared__ uint32_t s_k1, s_k2;
+    __shared__ uint32_t s_lut[256];
     if (threadIdx.x == 0) { s_k1 = 0; s_k2 = 0; }
+    for (uint32_t b = threadIdx.x; b < 256; b += FL_ROWS) s_lut[b] = class_entry(b);
     __syncthreads();
     const uint64_t r = (uint64_t)blockIdx.x * FL_ROWS + threadIdx.x;
     bool keep1 = false, keep2 = false;
     if (r < n_rows) {
         const uint4* row = reinterpret_cast<const uint4*>(var + r * n_samples);
-        RowState st = {0, 0, 0, 0xFFFFFFFFu, 0, (uint32_t)ignore_gaps};
+        RowState st = {0, 0, 0, 0xFFFFFFFFu, 0, (uint32_t)ignore_gaps, s_lut};
         const uint32_t n16 = n_samples >> 4;
         for (uint32_t c0 = 0; c0 < n16; c0 += 8) {
             uint4 v[8];

@@ -87,18 +87,25 @@ bucket_count_kernel(const uint64_t* __restrict__ rec, const Item* __restrict__ i
             uint64_t i = base + (uint64_t)j * MG_THREADS;
             rr[j] = i < it.end ? rec[i] : REC_SENTINEL;
         }
+        // probe the MG_UNROLL records together: independent shared loads overlap their latency; a key
+        // already present (the common case: one record per sample per key) needs nothing else
+        uint64_t kk[MG_UNROLL], cur[MG_UNROLL]; uint32_t sl[MG_UNROLL];
 #pragma unroll
         for (int j = 0; j < MG_UNROLL; j++) {
-            uint64_t r = rr[j];
-            if (r == REC_SENTINEL) continue;
-            uint64_t key = r >> 4;
-            if (key < it.key_lo || key > it.key_hi) continue;
+            kk[j] = rr[j] >> 4;
+            sl[j] = hash_slot(kk[j], 12);
+            if (rr[j] == REC_SENTINEL || kk[j] < it.key_lo || kk[j] > it.key_hi) kk[j] = KEY_EMPTY;   // skip marker
+        }
+#pragma unroll
+        for (int j = 0; j < MG_UNROLL; j++) cur[j] = *(volatile unsigned long long*)&s_tab[sl[j]];
+#pragma unroll
+        for (int j = 0; j < MG_UNROLL; j++) {
+            const uint64_t key = kk[j];
+            if (key == KEY_EMPTY || cur[j] == key) continue;
             if (*(volatile uint32_t*)&s_over) break;
-            uint32_t slot = hash_slot(key, 12);
+            uint32_t slot = sl[j];
             int probes = 0;
             while (true) {
-                // most records repeat a key that is already in the table (one per sample): a plain
-                // load settles those; only an empty slot needs the atomic
                 unsigned long long old = *(volatile unsigned long long*)&s_tab[slot];
                 if (old == key) break;
                 if (old == KEY_EMPTY) old = atomicCAS((unsigned long long*)&s_tab[slot], KEY_EMPTY, key);
@@ -214,13 +221,20 @@ bucket_emit_kernel(const uint64_t* __restrict__ rec, const uint16_t* __restrict_
             uint64_t i = base + (uint64_t)j * MG_THREADS;
             rr[j] = i < end ? rec[i] : REC_SENTINEL;
         }
+        uint64_t kk[MG_UNROLL], cur[MG_UNROLL]; uint32_t sl[MG_UNROLL];
 #pragma unroll
         for (int j = 0; j < MG_UNROLL; j++) {
-            uint64_t r = rr[j];
-            if (r == REC_SENTINEL) continue;
-            uint64_t key = r >> 4;
-            if (key < it.key_lo || key > it.key_hi) continue;
-            uint32_t slot = hash_slot(key, log_cap);
+            kk[j] = rr[j] >> 4;
+            sl[j] = hash_slot(kk[j], log_cap);
+            if (rr[j] == REC_SENTINEL || kk[j] < it.key_lo || kk[j] > it.key_hi) kk[j] = KEY_EMPTY;
+        }
+#pragma unroll
+        for (int j = 0; j < MG_UNROLL; j++) cur[j] = *(volatile unsigned long long*)&s_tab[sl[j]];
+#pragma unroll
+        for (int j = 0; j < MG_UNROLL; j++) {
+            const uint64_t key = kk[j];
+            if (key == KEY_EMPTY || cur[j] == key) continue;
+            uint32_t slot = sl[j];
             while (true) {
                 unsigned long long old = *(volatile unsigned long long*)&s_tab[slot];
                 if (old == key) break;
@@ -295,16 +309,25 @@ bucket_emit_kernel(const uint64_t* __restrict__ rec, const uint16_t* __restrict_
             rr[j] = in ? rec[i] : REC_SENTINEL;
             ss[j] = in ? sid[i] : 0;
         }
+        uint64_t kk[MG_UNROLL], cur[MG_UNROLL]; uint32_t sl[MG_UNROLL], rk[MG_UNROLL];
 #pragma unroll
         for (int j = 0; j < MG_UNROLL; j++) {
-            uint64_t r = rr[j];
-            if (r == REC_SENTINEL) continue;
-            uint64_t key = r >> 4;
-            if (key < it.key_lo || key > it.key_hi) continue;
-            uint32_t slot = hash_slot(key, log_cap);
-            while (s_tab[slot] != key) slot = (slot + 1) & (cap - 1);
-            uint64_t o = (row_base + s_rank[slot]) * n_samples + ss[j];
-            atomicOr(&out32[o >> 2], (uint32_t)(r & 0xF) << (8 * (o & 3)));
+            kk[j] = rr[j] >> 4;
+            sl[j] = hash_slot(kk[j], log_cap);
+            if (rr[j] == REC_SENTINEL || kk[j] < it.key_lo || kk[j] > it.key_hi) kk[j] = KEY_EMPTY;
+        }
+#pragma unroll
+        for (int j = 0; j < MG_UNROLL; j++) cur[j] = s_tab[sl[j]];
+#pragma unroll
+        for (int j = 0; j < MG_UNROLL; j++)                       // collisions: walk on (rare)
+            if (kk[j] != KEY_EMPTY) while (cur[j] != kk[j]) { sl[j] = (sl[j] + 1) & (cap - 1); cur[j] = s_tab[sl[j]]; }
+#pragma unroll
+        for (int j = 0; j < MG_UNROLL; j++) rk[j] = s_rank[sl[j]];
+#pragma unroll
+        for (int j = 0; j < MG_UNROLL; j++) {
+            if (kk[j] == KEY_EMPTY) continue;
+            uint64_t o = (row_base + rk[j]) * n_samples + ss[j];
+            atomicOr(&out32[o >> 2], (uint32_t)(rr[j] & 0xF) << (8 * (o & 3)));
         }
     }
     __threadfence();
