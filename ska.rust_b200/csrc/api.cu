@@ -34,6 +34,34 @@ void Context::ensure() {
     init = true;
 }
 
+static Arena g_arena;
+Arena& arena() { return g_arena; }
+void Arena::reset() {
+    if (slabs.size() > 1) {             // the previous build had to grow: merge into one slab of the total size
+        size_t total = 0;
+        for (auto& s : slabs) total += s.cap;
+        SKA_CUDA(cudaStreamSynchronize(ctx().stream));
+        release_all();
+        Slab s{nullptr, total, 0};
+        SKA_CUDA(cudaMalloc((void**)&s.p, total));
+        slabs.push_back(s);
+    }
+    for (auto& s : slabs) s.used = 0;
+}
+void* Arena::take(size_t bytes) {
+    bytes = (bytes + 255) & ~(size_t)255;
+    for (auto& s : slabs)
+        if (s.cap - s.used >= bytes) { void* r = s.p + s.used; s.used += bytes; return r; }
+    Slab s{nullptr, std::max<size_t>(bytes, (size_t)64 << 20), bytes};
+    SKA_CUDA(cudaMalloc((void**)&s.p, s.cap));
+    slabs.push_back(s);
+    return s.p;
+}
+void Arena::release_all() {
+    for (auto& s : slabs) cudaFree(s.p);
+    slabs.clear();
+}
+
 static StageTimer g_timer;
 StageTimer& timer() { return g_timer; }
 void StageTimer::clear() {
@@ -141,17 +169,18 @@ static std::unique_ptr<Array> build_from_batch(const SeqBatch& b, uint32_t k, bo
     if (k > 31) throw Error("k > 31 (128-bit split k-mers) is not yet built on the device; use k <= 31");
     if (b.has_qual) throw Error("FASTQ input (count/bloom filter, K2q) is not yet built on the device");
     (void)min_count; (void)qual_filter;
-    DevBuf<uint64_t> rec(b.n_pos);
-    DevBuf<uint16_t> sid(b.n_pos);
-    DevBuf<uint32_t> valid(b.n_samples);
-    SKA_CUDA(cudaMemsetAsync(valid.p, 0, valid.bytes(), c.stream));
+    arena().reset();
+    uint64_t* rec = arena().take_n<uint64_t>(b.n_pos);
+    uint16_t* sid = arena().take_n<uint16_t>(b.n_pos);
+    uint32_t* valid = arena().take_n<uint32_t>(b.n_samples);
+    SKA_CUDA(cudaMemsetAsync(valid, 0, b.n_samples * 4, c.stream));
     timer().begin("k1_extract");
-    launch_k1(b, k, rc, false, min_qual, rec.p, sid.p, valid.p);
+    launch_k1(b, k, rc, false, min_qual, rec, sid, valid);
     timer().end();
     std::vector<uint32_t> h_valid(b.n_samples);
-    SKA_CUDA(cudaMemcpyAsync(h_valid.data(), valid.p, valid.bytes(), cudaMemcpyDeviceToHost, c.stream));
+    SKA_CUDA(cudaMemcpyAsync(h_valid.data(), valid, b.n_samples * 4, cudaMemcpyDeviceToHost, c.stream));
     std::unique_ptr<Array> a(new Array());
-    build_array_from_records(rec.p, sid.p, b.n_pos, b.n_samples, k, rc, *a);   // synchronises the stream
+    build_array_from_records(rec, sid, b.n_pos, b.n_samples, k, rc, *a);   // synchronises the stream
     for (size_t s = 0; s < b.n_samples; s++)
         if (h_valid[s] == 0) throw Error("sample " + std::to_string(s) + " has no valid sequence");   // ska_dict.rs:374-376
     return a;

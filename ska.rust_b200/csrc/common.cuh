@@ -75,6 +75,19 @@ template <class T> struct DevBuf {
     size_t bytes() const { return n * sizeof(T); }
 };
 
+// Grow-only workspace for the temporaries of a build (records, partition double buffers, bucket
+// tables).  Allocating ~13 GB through the stream-ordered pool on every build cost up to tens of
+// milliseconds at unpredictable moments; the arena is carved with a bump pointer and kept.
+struct Arena {
+    struct Slab { uint8_t* p; size_t cap, used; };
+    std::vector<Slab> slabs;
+    void reset();                       // start of a build: everything is free again (coalesces slabs)
+    void* take(size_t bytes);
+    template <class T> T* take_n(size_t n) { return static_cast<T*>(take(n * sizeof(T))); }
+    void release_all();
+};
+Arena& arena();
+
 // Stage timer: CUDA events on the library stream.
 struct StageTimer {
     struct Stage { const char* name; cudaEvent_t beg, end; uint64_t launches; };

@@ -221,10 +221,7 @@ k1_extract_kernel(const uint8_t* __restrict__ seq, const uint8_t* __restrict__ q
     const uint32_t* le = s_le + ((K1_LEAD + lane) >> 4);
     uint64_t* out = rec_out + t0 + lane;
     uint16_t* sout = sid_out ? sid_out + t0 + lane : nullptr;
-#pragma unroll 4
-    for (int j = warp; j < K1_T / 32; j += K1_THREADS / 32) {
-        if (!full && t0 + 32ull * j + lane >= n_pos) break;
-        const uint32_t ok = s_ok[j];
+    auto window = [&](int j) -> uint64_t {
         // forward k-mer (first base most significant) out of the BE stream
         const uint32_t b0 = be[2 * j], b1 = be[2 * j + 1], b2 = be[2 * j + 2];
         const uint64_t top = ((uint64_t)__funnelshift_l(b1, b0, sh) << 32) | __funnelshift_l(b2, b1, sh);
@@ -241,15 +238,26 @@ k1_extract_kernel(const uint8_t* __restrict__ seq, const uint8_t* __restrict__ q
         }
         const uint32_t klo = (uint32_t)key, khi = (uint32_t)(key >> 32);
         uint64_t rec = ((uint64_t)__funnelshift_l(klo, khi, 4) << 32) | ((klo << 4) | (1u << mid));
-        if (!((ok >> lane) & 1u)) rec = REC_SENTINEL;
-        out[32 * j] = rec;
-        if (uniform) {
-            if (sout) sout[32 * j] = (uint16_t)sid_first;
-        } else {                                                  // tile straddles samples (rare)
+        if (!((s_ok[j] >> lane) & 1u)) rec = REC_SENTINEL;
+        return rec;
+    };
+    if (full && uniform) {                                        // interior tile of one sample: no per-window checks
+        if (sout) {
+#pragma unroll 4
+            for (int j = warp; j < K1_T / 32; j += K1_THREADS / 32) { out[32 * j] = window(j); sout[32 * j] = (uint16_t)sid_first; }
+        } else {
+#pragma unroll 4
+            for (int j = warp; j < K1_T / 32; j += K1_THREADS / 32) out[32 * j] = window(j);
+        }
+    } else {
+        for (int j = warp; j < K1_T / 32; j += K1_THREADS / 32) {
             const uint64_t p = t0 + 32ull * j + lane;
-            uint32_t lo = sid_first, hi = sid_last + 1;
+            if (p >= n_pos) break;
+            const uint64_t rec = window(j);
+            out[32 * j] = rec;
+            uint32_t lo = sid_first, hi = sid_last + 1;           // tile straddles samples or the end of the batch
             while (hi - lo > 1) { uint32_t m = (lo + hi) >> 1; if (sample_off[m] <= p) lo = m; else hi = m; }
-            if (sample_valid && rec != REC_SENTINEL) atomicAdd(&sample_valid[lo], 1u);
+            if (!uniform && sample_valid && rec != REC_SENTINEL) atomicAdd(&sample_valid[lo], 1u);
             if (sout) sout[32 * j] = (uint16_t)lo;
         }
     }

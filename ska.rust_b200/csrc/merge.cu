@@ -411,44 +411,45 @@ void build_array_from_records(uint64_t* rec, uint16_t* sid, uint64_t n_pos, uint
 
     // (1) partition by key prefix
     timer().begin("partition");
-    DevBuf<uint64_t> rec_alt; DevBuf<uint16_t> sid_alt; DevBuf<uint8_t> tmp;
     uint64_t* rec_sorted = rec; uint16_t* sid_sorted = sid;
     if (P > 0) {
-        rec_alt.alloc(n_pos); sid_alt.alloc(n_pos);
-        cub::DoubleBuffer<uint64_t> dk(rec, rec_alt.p);
-        cub::DoubleBuffer<uint16_t> dv(sid, sid_alt.p);
+        uint64_t* rec_alt = arena().take_n<uint64_t>(n_pos);
+        uint16_t* sid_alt = arena().take_n<uint16_t>(n_pos);
+        cub::DoubleBuffer<uint64_t> dk(rec, rec_alt);
+        cub::DoubleBuffer<uint16_t> dv(sid, sid_alt);
         size_t tmp_bytes = 0;
         SKA_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, dk, dv, (int64_t)n_pos, shift, shift + P, c.stream));
-        tmp.alloc(tmp_bytes);
-        SKA_CUDA(cub::DeviceRadixSort::SortPairs(tmp.p, tmp_bytes, dk, dv, (int64_t)n_pos, shift, shift + P, c.stream));
+        void* tmp = arena().take(tmp_bytes);
+        SKA_CUDA(cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, dk, dv, (int64_t)n_pos, shift, shift + P, c.stream));
         c.launches += (P + 7) / 8 + 1;   // onesweep: one histogram + one pass per 8 bits (library kernels)
         rec_sorted = dk.Current(); sid_sorted = dv.Current();
     }
     timer().end();
 
     timer().begin("bucket_offsets");
-    DevBuf<uint64_t> off(n_buckets + 1);
-    SKA_LAUNCH(bucket_offsets_kernel, (n_buckets + 1 + 255) / 256, 256, 0, rec_sorted, n_pos, shift, n_buckets, off.p);
+    uint64_t* off = arena().take_n<uint64_t>(n_buckets + 1);
+    SKA_LAUNCH(bucket_offsets_kernel, (n_buckets + 1 + 255) / 256, 256, 0, rec_sorted, n_pos, shift, n_buckets, off);
     uint32_t n_items = n_buckets;
-    DevBuf<Item> items(n_items);
-    SKA_LAUNCH(make_items_kernel, (n_buckets + 255) / 256, 256, 0, off.p, n_buckets, key_bits, P, items.p);
+    Item* items = arena().take_n<Item>(n_items);
+    SKA_LAUNCH(make_items_kernel, (n_buckets + 255) / 256, 256, 0, off, n_buckets, key_bits, P, items);
     timer().end();
 
     // (2a) distinct keys per item -> row offsets; split items that do not fit shared memory
     timer().begin("count");
-    DevBuf<uint32_t> n_rows(n_items), flags(2);
+    uint32_t* n_rows = arena().take_n<uint32_t>(n_items);
+    uint32_t* flags = arena().take_n<uint32_t>(2);
     uint32_t h_flags[2];
     for (int round = 0;; round++) {
-        SKA_CUDA(cudaMemsetAsync(flags.p, 0, 8, c.stream));
-        SKA_LAUNCH(bucket_count_kernel, n_items, MG_THREADS, 0, rec_sorted, items.p, limit, n_rows.p, flags.p);
-        SKA_CUDA(cudaMemcpyAsync(h_flags, flags.p, 8, cudaMemcpyDeviceToHost, c.stream));
+        SKA_CUDA(cudaMemsetAsync(flags, 0, 8, c.stream));
+        SKA_LAUNCH(bucket_count_kernel, n_items, MG_THREADS, 0, rec_sorted, items, limit, n_rows, flags);
+        SKA_CUDA(cudaMemcpyAsync(h_flags, flags, 8, cudaMemcpyDeviceToHost, c.stream));
         SKA_CUDA(cudaStreamSynchronize(c.stream));
         if (!h_flags[0]) break;
         if (round > 40) throw Error("bucket splitting did not converge");
         std::vector<Item> h_items(n_items), next;
         std::vector<uint32_t> h_rows(n_items);
-        SKA_CUDA(cudaMemcpyAsync(h_items.data(), items.p, n_items * sizeof(Item), cudaMemcpyDeviceToHost, c.stream));
-        SKA_CUDA(cudaMemcpyAsync(h_rows.data(), n_rows.p, n_items * 4, cudaMemcpyDeviceToHost, c.stream));
+        SKA_CUDA(cudaMemcpyAsync(h_items.data(), items, n_items * sizeof(Item), cudaMemcpyDeviceToHost, c.stream));
+        SKA_CUDA(cudaMemcpyAsync(h_rows.data(), n_rows, n_items * 4, cudaMemcpyDeviceToHost, c.stream));
         SKA_CUDA(cudaStreamSynchronize(c.stream));
         next.reserve(n_items + 64);
         for (uint32_t i = 0; i < n_items; i++) {
@@ -468,15 +469,15 @@ void build_array_from_records(uint64_t* rec, uint16_t* sid, uint64_t n_pos, uint
             }
         }
         n_items = (uint32_t)next.size();
-        items.alloc(n_items); n_rows.alloc(n_items);
-        SKA_CUDA(cudaMemcpyAsync(items.p, next.data(), n_items * sizeof(Item), cudaMemcpyHostToDevice, c.stream));
+        items = arena().take_n<Item>(n_items); n_rows = arena().take_n<uint32_t>(n_items);
+        SKA_CUDA(cudaMemcpyAsync(items, next.data(), n_items * sizeof(Item), cudaMemcpyHostToDevice, c.stream));
         SKA_CUDA(cudaStreamSynchronize(c.stream));
     }
-    DevBuf<uint64_t> row_off(n_items + 1);
-    launch_scan_counts(n_rows.p, n_items, row_off.p, flags.p + 1);
+    uint64_t* row_off = arena().take_n<uint64_t>(n_items + 1);
+    launch_scan_counts(n_rows, n_items, row_off, flags + 1);
     uint64_t total_rows = 0;
-    SKA_CUDA(cudaMemcpyAsync(h_flags, flags.p, 8, cudaMemcpyDeviceToHost, c.stream));
-    SKA_CUDA(cudaMemcpyAsync(&total_rows, row_off.p + n_items, 8, cudaMemcpyDeviceToHost, c.stream));
+    SKA_CUDA(cudaMemcpyAsync(h_flags, flags, 8, cudaMemcpyDeviceToHost, c.stream));
+    SKA_CUDA(cudaMemcpyAsync(&total_rows, row_off + n_items, 8, cudaMemcpyDeviceToHost, c.stream));
     SKA_CUDA(cudaStreamSynchronize(c.stream));
     timer().end();
     const uint32_t max_u = h_flags[1];
@@ -492,7 +493,7 @@ void build_array_from_records(uint64_t* rec, uint16_t* sid, uint64_t n_pos, uint
         size_t smem = ((size_t)1 << log_cap) * slot_bytes;
         if (log_cap > max_log_cap) throw Error("internal: item larger than the shared-memory table");
         SKA_CUDA(cudaFuncSetAttribute(bucket_emit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        SKA_LAUNCH(bucket_emit_kernel, n_items, MG_THREADS, smem, rec_sorted, sid_sorted, items.p, row_off.p, log_cap,
+        SKA_LAUNCH(bucket_emit_kernel, n_items, MG_THREADS, smem, rec_sorted, sid_sorted, items, row_off, log_cap,
                    (uint32_t)n_samples, (int)k, rc ? 1 : 0, out.keys.p, out.variants.p, out.counts.p);
     }
     timer().end();
