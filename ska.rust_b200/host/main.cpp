@@ -1,0 +1,144 @@
+// main.cpp -- `ska` command line for the hot path: build / align / distance / nk, with the reference's
+// flags and defaults (src/cli.rs:153-431, dispatch src/lib.rs:557-892).  stdout carries only results
+// (alignment, distance table, nk text); banner and timing go to stderr as in the reference
+// (lib.rs:565,886-890).  Any error exits with status 101, the status of a Rust panic.
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "ska_host.hpp"
+
+using namespace ska;
+
+[[noreturn]] static void usage_error(const std::string& msg) {
+    fprintf(stderr, "error: %s\n\nUsage: ska <build|align|distance|nk> [OPTIONS]\n", msg.c_str());
+    exit(2);                                               // clap's exit status for argument errors
+}
+
+struct Args {
+    std::vector<std::string> pos;
+    std::vector<std::pair<std::string, std::string>> opts;
+    bool has(const std::string& k) const { for (auto& o : opts) if (o.first == k) return true; return false; }
+    std::string get(const std::string& k, const std::string& dflt = "") const { for (auto& o : opts) if (o.first == k) return o.second; return dflt; }
+};
+
+static Args parse(int argc, char** argv, int start, const std::vector<std::string>& value_opts, const std::vector<std::string>& flag_opts) {
+    Args a;
+    for (int i = start; i < argc; i++) {
+        std::string s = argv[i];
+        if (s == "-v" || s == "--verbose") { a.opts.emplace_back("--verbose", "1"); continue; }
+        bool is_val = false, is_flag = false;
+        for (auto& v : value_opts) if (s == v) is_val = true;
+        for (auto& f : flag_opts) if (s == f) is_flag = true;
+        if (is_val) { if (i + 1 >= argc) usage_error("a value is required for '" + s + "'"); a.opts.emplace_back(s, argv[++i]); }
+        else if (is_flag) a.opts.emplace_back(s, "1");
+        else if (s.size() > 1 && s[0] == '-' && s != "-") usage_error("unexpected argument '" + s + "'");
+        else a.pos.push_back(s);
+    }
+    return a;
+}
+
+static size_t parse_k(const std::string& s) {              // cli.rs:38-47
+    char* e; long k = strtol(s.c_str(), &e, 10);
+    if (*e || s.empty()) usage_error("`" + s + "` isn't a valid k-mer");
+    if (k < 5 || k > 63 || k % 2 == 0) usage_error("K-mer must be an odd number between 5 and 63 (inclusive)");
+    return (size_t)k;
+}
+static double parse_01(const std::string& s, const char* what) {   // cli.rs:50-71
+    char* e; double f = strtod(s.c_str(), &e);
+    if (*e || s.empty()) usage_error("`" + s + "` isn't a valid " + what);
+    if (f < 0.0 || f > 1.0) usage_error("Frequency must be between 0 and 1 (inclusive)");
+    return f;
+}
+static size_t parse_threads(const std::string& s) {        // cli.rs:74-83
+    char* e; long t = strtol(s.c_str(), &e, 10);
+    if (*e || s.empty()) usage_error("`" + s + "` isn't a valid number of cores");
+    if (t < 1) usage_error("Threads must be one or higher");
+    if ((unsigned long)t > std::thread::hardware_concurrency() && std::thread::hardware_concurrency())
+        fprintf(stderr, "WARN %ld threads is greater than available cores %u\n", t, std::thread::hardware_concurrency());
+    return (size_t)t;
+}
+static FilterType parse_filter(const std::string& s) {
+    if (s == "no-filter") return FilterType::NoFilter;
+    if (s == "no-const") return FilterType::NoConst;
+    if (s == "no-ambig") return FilterType::NoAmbig;
+    if (s == "no-ambig-or-const") return FilterType::NoAmbigOrConst;
+    usage_error("invalid value '" + s + "' for '--filter <FILTER>'");
+}
+static QualFilter parse_qual_filter(const std::string& s) {
+    if (s == "no-filter") return QualFilter::NoFilter;
+    if (s == "middle") return QualFilter::Middle;
+    if (s == "strict") return QualFilter::Strict;
+    usage_error("invalid value '" + s + "' for '--qual-filter <QUAL_FILTER>'");
+}
+
+int main(int argc, char** argv) {
+    if (argc < 2) usage_error("a subcommand is required");
+    const std::string cmd = argv[1];
+    fprintf(stderr, "SKA: Split K-mer Analysis (the alignment-free aligner)\n");
+    auto start = std::chrono::steady_clock::now();
+    try {
+        if (cmd == "build") {
+            Args a = parse(argc, argv, 2, {"-f", "-o", "-k", "--proportion-reads", "--min-count", "--min-qual", "--qual-filter", "--threads"},
+                           {"--single-strand"});
+            if (!a.has("-o")) usage_error("the following required arguments were not provided: -o <OUTPUT>");
+            if (a.has("-f") == !a.pos.empty()) usage_error("exactly one of <SEQ_FILES> or -f <FILE_LIST> is required");
+            size_t k = parse_k(a.get("-k", "31"));
+            size_t threads = parse_threads(a.get("--threads", "1"));
+            QualOpts q;
+            q.min_qual = (uint8_t)atoi(a.get("--min-qual", "20").c_str());
+            q.qual_filter = parse_qual_filter(a.get("--qual-filter", "strict"));
+            if (a.has("--min-count")) {                    // kmer_min_cutoff (io_utils.rs:175-212); "auto" needs `ska cov` (out of scope)
+                std::string mc = a.get("--min-count");
+                if (mc == "auto") throw SkaError("--min-count auto (coverage model fit) is outside this engine's scope; pass a number");
+                int v = atoi(mc.c_str());
+                if (v < 1) usage_error("Minimum kmer count must be >= 1");
+                q.min_count = (uint16_t)v;
+            }
+            double prop = a.has("--proportion-reads") ? parse_01(a.get("--proportion-reads"), "proportion") : 0.0;
+            auto inputs = io_utils::get_input_list(a.get("-f"), a.pos);
+            MergeSkaArray arr = build_and_merge(inputs, k, !a.has("--single-strand"), q, threads, prop);
+            generic_modes::save_skf(arr, a.get("-o"), (int)threads);
+        } else if (cmd == "align") {
+            Args a = parse(argc, argv, 2, {"-o", "-m", "--min-freq", "--filter", "--threads"},
+                           {"--filter-ambig-as-missing", "--ambig-mask", "--no-gap-only-sites"});
+            if (a.pos.empty()) usage_error("the following required arguments were not provided: <INPUT>...");
+            double min_freq = parse_01(a.has("-m") ? a.get("-m") : a.get("--min-freq", "0.9"), "frequency");
+            size_t threads = parse_threads(a.get("--threads", "1"));
+            MergeSkaArray arr = io_utils::load_array(a.pos, threads);
+            generic_modes::align(arr, a.get("-o"), parse_filter(a.get("--filter", "no-const")), a.has("--ambig-mask"),
+                                 a.has("--no-gap-only-sites"), min_freq, a.has("--filter-ambig-as-missing"));
+        } else if (cmd == "distance") {
+            Args a = parse(argc, argv, 2, {"-o", "-m", "--min-freq", "--threads"}, {"--allow-ambiguous"});
+            if (a.pos.size() != 1) usage_error("the following required arguments were not provided: <SKF_FILE>");
+            double min_freq = parse_01(a.has("-m") ? a.get("-m") : a.get("--min-freq", "0"), "frequency");
+            parse_threads(a.get("--threads", "1"));        // only sanity-checked by the reference too (lib.rs:714)
+            MergeSkaArray arr = MergeSkaArray::load(a.pos[0]);
+            generic_modes::distance(arr, a.get("-o"), min_freq, !a.has("--allow-ambiguous"));
+        } else if (cmd == "nk") {
+            Args a = parse(argc, argv, 2, {}, {"--full-info"});
+            if (a.pos.size() != 1) usage_error("the following required arguments were not provided: <SKF_FILE>");
+            MergeSkaArray arr = MergeSkaArray::load(a.pos[0]);
+            std::string s = arr.display(a.has("--full-info"));
+            fwrite(s.data(), 1, s.size(), stdout);
+        } else if (cmd == "recode") {
+            // host-only helper (no device): decode a .skf and write it again with this codec
+            Args a = parse(argc, argv, 2, {"--threads"}, {});
+            if (a.pos.size() != 2) usage_error("usage: ska recode <IN.skf> <OUT.skf>");
+            skf::save(skf::load(a.pos[0]), a.pos[1], (int)parse_threads(a.get("--threads", "1")));
+        } else {
+            usage_error("unrecognized subcommand '" + cmd + "' (this engine provides build, align, distance, nk)");
+        }
+    } catch (std::exception& e) {
+        fprintf(stderr, "thread 'main' panicked:\n%s\n", e.what());
+        return 101;
+    }
+    double secs = std::chrono::duration<double>(std::chrono::steady_clock::now() - start).count();
+    fprintf(stderr, "SKA done in %gs\n", secs);
+    fprintf(stderr, "\xE2\xAC\x9B\xE2\xAC\x9C\xE2\xAC\x9B\xE2\xAC\x9C\xE2\xAC\x9B\xE2\xAC\x9C\xE2\xAC\x9B\n\xE2\xAC\x9C\xE2\xAC\x9B\xE2\xAC\x9C\xE2\xAC\x9B\xE2\xAC\x9C\xE2\xAC\x9B\xE2\xAC\x9C\n");
+    return 0;
+}

@@ -1,0 +1,83 @@
+// ska_host.hpp -- C++ host-side mirror of the reference's interface for the hot path, on top of the
+// C ABI (include/skagpu.h).  Same names and argument meaning as the Rust API it stands in for:
+//   MergeSkaArray::{load, save, filter, distance, write_fasta, Display/Debug}   src/merge_ska_array.rs
+//   build_and_merge                                                             src/merge_ska_dict.rs:354-417
+//   generic_modes::{align, distance, apply_filters, save_skf}                   src/generic_modes.rs
+//   io_utils::{read_input_fastas, get_input_list, load_array}                   src/io_utils.rs
+// Errors are C++ exceptions carrying the reference's panic text; the CLI turns them into exit code 101.
+#pragma once
+#include <cstdint>
+#include <cstdio>
+#include <stdexcept>
+#include <string>
+#include <tuple>
+#include <vector>
+
+#include "../../include/skagpu.h"
+#include "skf_codec.hpp"
+
+namespace ska {
+
+struct SkaError : std::runtime_error { using std::runtime_error::runtime_error; };
+
+enum class QualFilter { NoFilter = 0, Middle = 1, Strict = 2 };                      // cli.rs:112-123
+enum class FilterType { NoFilter = 0, NoConst = 1, NoAmbig = 2, NoAmbigOrConst = 3 };  // cli.rs:129-138
+struct QualOpts { uint16_t min_count = 5; uint8_t min_qual = 20; QualFilter qual_filter = QualFilter::Strict; };  // lib.rs:533-540
+typedef std::tuple<std::string, std::string, std::string> InputFastx;                // (name, file1, file2 or "")
+
+class MergeSkaArray {
+  public:
+    MergeSkaArray() {}
+    MergeSkaArray(ska_array_t* h, std::vector<std::string> names, std::string version = "0.5.2")
+        : h_(h), names_(std::move(names)), version_(std::move(version)) {}
+    MergeSkaArray(MergeSkaArray&& o) noexcept { *this = std::move(o); }
+    MergeSkaArray& operator=(MergeSkaArray&& o) noexcept {
+        if (this != &o) { reset(); h_ = o.h_; o.h_ = nullptr; names_ = std::move(o.names_); version_ = std::move(o.version_); }
+        return *this;
+    }
+    MergeSkaArray(const MergeSkaArray&) = delete;
+    MergeSkaArray& operator=(const MergeSkaArray&) = delete;
+    ~MergeSkaArray() { reset(); }
+
+    static MergeSkaArray load(const std::string& filename);                  // merge_ska_array.rs:199-204
+    void save(const std::string& filename, int threads = 1) const;           // merge_ska_array.rs:191-197
+    int32_t filter(size_t min_count, bool filter_ambig_as_missing, FilterType filter, bool mask_ambig,
+                   bool ignore_const_gaps, bool update_kmers);               // merge_ska_array.rs:289-402
+    std::vector<ska_dist_t> distance(double constant, bool filt_ambig) const;  // merge_ska_array.rs:416-438
+    void write_fasta(FILE* f) const;                                         // merge_ska_array.rs:499-517
+    std::string display(bool full_info) const;                               // merge_ska_array.rs:649-698
+
+    size_t nsamples() const;
+    size_t ksize() const;
+    size_t kmer_len() const;
+    bool rc() const;
+    uint32_t k_bits() const;
+    const std::vector<std::string>& names() const { return names_; }
+    skf::Array to_host() const;
+
+  private:
+    void reset() { if (h_) skagpu_free(h_); h_ = nullptr; }
+    ska_array_t* h_ = nullptr;
+    std::vector<std::string> names_;
+    std::string version_;
+};
+
+MergeSkaArray build_and_merge(const std::vector<InputFastx>& input_files, size_t k, bool rc, const QualOpts& qual,
+                              size_t threads, double proportion_reads /* <= 0: None */);
+
+namespace io_utils {
+std::vector<InputFastx> read_input_fastas(const std::vector<std::string>& seq_files);               // io_utils.rs:31-46
+std::vector<InputFastx> get_input_list(const std::string& file_list, const std::vector<std::string>& seq_files);  // :116-146
+MergeSkaArray load_array(const std::vector<std::string>& input, size_t threads);                    // io_utils.rs:60-93
+}  // namespace io_utils
+
+namespace generic_modes {
+int32_t apply_filters(MergeSkaArray& a, double min_freq, bool filter_ambig_as_missing, FilterType filter, bool ambig_mask,
+                      bool ignore_const_gaps);                                                       // generic_modes.rs:112-131
+void align(MergeSkaArray& a, const std::string& output /* "" = stdout */, FilterType filter, bool mask_ambig,
+           bool ignore_const_gaps, double min_freq, bool filter_ambig_as_missing);                   // generic_modes.rs:22-50
+void distance(MergeSkaArray& a, const std::string& output, double min_freq, bool filt_ambig);        // generic_modes.rs:136-189
+void save_skf(const MergeSkaArray& a, const std::string& output, int threads);                       // generic_modes.rs:270-283
+}  // namespace generic_modes
+
+}  // namespace ska

@@ -1,0 +1,119 @@
+"""The C++ host (`ska` CLI + .skf codec) driven like the reference's snapbox tests (tests/*.rs).
+CPU part: the codec alone.  GPU part: build / align / distance / nk end to end against the goldens."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from oracle import oracle as O
+from oracle import skf_py
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+SKA = os.path.join(ROOT, "ska.rust_b200", "ska")
+
+
+def run(args, cwd=None, check=True):
+    p = subprocess.run([SKA] + args, cwd=cwd, capture_output=True)
+    if check:
+        assert p.returncode == 0, p.stderr.decode()
+    return p
+
+
+# ------------------------------------------------------------------ codec (no GPU)
+@pytest.mark.parametrize("fixture", ["merge.skf", "merge_k9.skf", "merge_k41.skf", "multidist.skf"])
+def test_cpp_codec_recode_matches_python_decoder(gold_in, tmp_path, fixture):
+    out = tmp_path / "re.skf"
+    run(["recode", gold_in(fixture), str(out)])
+    a, b = skf_py.load_skf(gold_in(fixture)), skf_py.load_skf(str(out))
+    assert a == b
+    # the re-encoded CBOR payload is byte-identical to what ciborium wrote (same shortest-form heads)
+    with open(gold_in(fixture), "rb") as f1, open(out, "rb") as f2:
+        assert skf_py.snappy_frame_decode(f1.read()) == skf_py.snappy_frame_decode(f2.read())
+
+
+def test_cpp_codec_large_random_roundtrip(tmp_path):
+    """several 64 KiB chunks, compressible and incompressible regions, u128 keys"""
+    rng = np.random.default_rng(1)
+    n_rows, n_samples = 40_000, 9
+    var = rng.choice(np.frombuffer(b"ACGT-NRY", dtype=np.uint8), size=(n_rows, n_samples)).astype(np.uint8)
+    var[:20000] = ord("A")
+    keys = sorted(int(x) for x in rng.integers(0, 1 << 62, size=n_rows))
+    keys[-1] = (1 << 100) + 12345
+    cnt = [int(c) for c in (var != ord("-")).sum(axis=1)]
+    names = [f"sample {i}" for i in range(n_samples)]
+    src = tmp_path / "a.skf"
+    src.write_bytes(skf_py.dump_skf_bytes(41, False, names, keys, var.tobytes(), n_rows, n_samples, cnt, "0.5.2", 128))
+    out = tmp_path / "b.skf"
+    run(["recode", str(src), str(out), "--threads", "4"])
+    assert skf_py.load_skf(str(src)) == skf_py.load_skf(str(out))
+    assert os.path.getsize(out) < os.path.getsize(src) // 2       # the C++ writer really compresses
+
+
+def test_cli_errors_without_touching_the_device(tmp_path):
+    assert run(["build", "-k", "30", "-o", "x", "a.fa"], check=False).returncode == 2      # clap validator (cli.rs:38-47)
+    assert run(["build", "-k", "65", "-o", "x", "a.fa"], check=False).returncode == 2
+    assert run(["frobnicate"], check=False).returncode == 2
+    bad = tmp_path / "bad.skf"
+    bad.write_bytes(b"not a snappy stream")
+    assert run(["nk", str(bad)], check=False).returncode == 101                            # load error -> panic (lib.rs:660)
+
+
+# ------------------------------------------------------------------ end to end (GPU)
+def g(gold_in, *names):
+    return [gold_in(n) for n in names]
+
+
+@pytest.mark.gpu
+def test_cli_build_nk_align_distance(gold_in, gold_ok, tmp_path):
+    wd = str(tmp_path)
+    # tests/fasta_input.rs:12-32 align_n (also: no ".skf.skf")
+    run(["build"] + g(gold_in, "N_test_1.fa", "N_test_2.fa") + ["-o", "N_test.skf"], cwd=wd)
+    assert os.path.exists(tmp_path / "N_test.skf") and not os.path.exists(tmp_path / "N_test.skf.skf")
+    assert run(["align", "N_test.skf"], cwd=wd).stdout == gold_ok("align_N.stdout")
+    # tests/skf_ops.rs / merge_nk.stdout
+    run(["build"] + g(gold_in, "test_1.fa", "test_2.fa") + ["-o", "merge"], cwd=wd)
+    nk = run(["nk", "merge.skf"], cwd=wd).stdout.decode()
+    assert nk.split("\n", 1)[1] == gold_ok("merge_nk.stdout").decode().split("\n", 1)[1]
+    # the file we wrote is what the reference's loader expects: decode it independently, compare with the oracle build
+    d = skf_py.load_skf(str(tmp_path / "merge.skf"))
+    o = O.OracleArray.build_from_files(g(gold_in, "test_1.fa", "test_2.fa"), k=31)
+    keys, var, cnt = o.export()
+    assert d["split_kmers"] == keys and d["variants"] == var.tobytes() and d["variant_count"] == [int(c) for c in cnt]
+    assert d["names"] == ["test_1", "test_2"] and d["k"] == 31 and d["rc"] is True and d["k_bits"] == 64
+    # tests/fasta_input.rs:157-220 repeats; :222-291 palindromes
+    run(["build", "-k", "9"] + g(gold_in, "dup_test_1.fa", "dup_test_2.fa") + ["-o", "dup_ss", "--single-strand"], cwd=wd)
+    assert run(["align", "dup_ss.skf"], cwd=wd).stdout == gold_ok("dup_ss.stdout")
+    run(["build", "-k", "15"] + g(gold_in, "palindrome_1.fa", "palindrome_2.fa") + ["-o", "otto", "-v"], cwd=wd)
+    assert run(["align", "otto.skf", "--filter", "no-filter"], cwd=wd).stdout == gold_ok("palindrome.stdout")
+    # one-shot align from FASTA (io_utils.rs:75-92) and -o
+    run(["align"] + g(gold_in, "test_1.fa", "test_2.fa") + ["-o", "basic.aln", "--filter", "no-filter", "--min-freq", "0", "--threads", "2"], cwd=wd)
+    assert O.aln_length((tmp_path / "basic.aln").read_bytes()) == [62, 62]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("skf,extra,golden", [
+    ("merge.skf", ["-v", "--threads", "2"], "merge.dist.stdout"),
+    ("merge_k41.skf", [], "merge_k41.dist.stdout"),
+    ("merge_k9.skf", ["--allow-ambiguous"], "merge_k9.dist.stdout"),
+    ("merge_k9.skf", [], "merge_k9_no_ambig.dist.stdout"),
+    ("merge_k9.skf", ["--min-freq", "1"], "merge_k9_min_freq.dist.stdout"),
+    ("multidist.skf", ["--min-freq", "0.9"], "multidist.minfreq.stdout"),
+    ("multidist.skf", ["--allow-ambiguous"], "multidist.ambig.stdout"),
+])
+def test_cli_distance_goldens(gold_in, gold_ok, tmp_path, skf, extra, golden):
+    """tests/distance.rs: the reference's own .skf fixtures through our loader, byte-exact stdout"""
+    assert run(["distance", gold_in(skf)] + extra).stdout == gold_ok(golden)
+    run(["distance", gold_in(skf), "-o", "d.txt"] + extra, cwd=str(tmp_path))
+    assert (tmp_path / "d.txt").read_bytes() == gold_ok(golden)
+
+
+@pytest.mark.gpu
+def test_cli_rfile_and_failures(gold_in, tmp_path):
+    """tests/align.rs:13-31 build_cli (-f rfile), :155-166 (k=65 fails)"""
+    rfile = tmp_path / "rfile"
+    rfile.write_text(f"test_1\t{gold_in('test_1.fa')}\ntest_2\t{gold_in('test_2.fa')}\n")
+    run(["build", "-f", str(rfile), "-o", "basic_build_opts", "-v", "--threads", "2", "-k", "31"], cwd=str(tmp_path))
+    assert os.path.exists(tmp_path / "basic_build_opts.skf")
+    assert run(["build", "-o", "x", "-k", "33", gold_in("test_1.fa"), gold_in("test_2.fa")], cwd=str(tmp_path), check=False).returncode == 101
+    assert run(["build", "-o", "x", gold_in("nonexistent.fa")], cwd=str(tmp_path), check=False).returncode == 101
