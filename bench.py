@@ -173,11 +173,22 @@ def run_ours(args, rank, world, local_rank):
         arr.filter(threshold, False, "no-const", False, False, False)
         arr.transpose_on_device()
 
+    if world > 1:
+        import ska_rust_b200.distributed as D
+        backend = D.GpuBackend()
+        names = [f"s{i}" for i in range(G * world)]          # every slab has all N = G*world columns
+        threshold = int(np.ceil(G * world * 0.9))
+
+    def build_device(batch):
+        if world == 1:
+            return S.api.build_from_batch(batch, names, k, True)
+        return D.build_and_merge_sharded(backend, batch, names, rank * G, k, True, prefix_bits=16)
+
     # ---------------- device-resident arm
     batch = S.SeqBatch(samples)
     log("batch uploaded")
     for _ in range(args.warmup):
-        arr = S.api.build_from_batch(batch, names, k, True)
+        arr = build_device(batch)
         align_device(arr)
         del arr
     log(f"device warm-up done; stages {S.api.last_timings()}")
@@ -186,7 +197,7 @@ def run_ours(args, rank, world, local_rank):
     with ClockSampler(local_rank) as clocks:
         S.api.timer_start()
         for _ in range(args.steps):
-            arr = S.api.build_from_batch(batch, names, k, True)
+            arr = build_device(batch)
             rows_built = arr.dims()["n_rows"]
             align_device(arr)
             stages = S.api.last_timings()
@@ -204,10 +215,13 @@ def run_ours(args, rank, world, local_rank):
     del batch
 
     # ---------------- end-to-end arm: pinned host buffers in, alignment bytes out
-    out_host = torch.empty((G, max(1, rows_aligned)), dtype=torch.uint8, pin_memory=True).numpy()
+    out_host = torch.empty((G * world, max(1, rows_aligned)), dtype=torch.uint8, pin_memory=True).numpy()
 
     def e2e_step():
-        arr = S.build_from_samples(samples, names, k, True)
+        if world == 1:
+            arr = S.build_from_samples(samples, names, k, True)
+        else:
+            arr = build_device(S.SeqBatch(samples))          # H2D of this rank's genomes, then the sharded build
         arr.filter(threshold, False, "no-const", False, False, False)
         r = arr.dims()["n_rows"]
         assert r == rows_aligned
@@ -230,7 +244,7 @@ def run_ours(args, rank, world, local_rank):
     log(f"e2e arm: {ms_e2e / args.steps:.2f} ms/step")
     e2e_value = args.steps * G * world / (ms_e2e * 1e-3)
     h2d = n_bases + 8 * (2 * G + 1)                    # sequence bytes + record starts + sample offsets
-    d2h = G * rows_aligned + 4 * G + 24                # alignment + per-sample valid counts + scalars
+    d2h = G * world * rows_aligned + 4 * G + 24        # this rank's alignment slab + per-sample valid counts + scalars
 
     # ---------------- CPU baseline beside it (rank 0, N=1 only): bounded sample of the same workload
     cpu_baseline = None
@@ -257,7 +271,9 @@ def run_ours(args, rank, world, local_rank):
                                    "(BASELINE configs[1])", "k": k, "rc": True, "genomes_per_gpu": G, "genome_bp": L,
                        "population": "star model, 0.1% SNPs/sample", "align": "min_freq 0.9, filter no-const",
                        "l2": "inputs (640 MB/128 genomes) larger than L2; no flush",
-                       "parallelism": "1 GPU" if world == 1 else f"{world} ranks, sample-sharded, per-rank arrays",
+                       "parallelism": "1 GPU" if world == 1 else
+                       f"{world} ranks: samples sharded for extraction, one NCCL all-to-all of records by key range, "
+                       f"rows sharded for merge/filter ({G * world} columns per slab)",
                        "rows_built": rows_built, "rows_aligned": rows_aligned},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": ms_e2e / args.steps},

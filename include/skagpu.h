@@ -31,6 +31,7 @@ extern "C" {
 
 typedef struct ska_array ska_array_t;
 typedef struct ska_seqbatch ska_seqbatch_t;
+typedef struct ska_records ska_records_t;
 
 /* One sample = InputFastx (merge_ska_dict.rs:25) after host-side parsing (needletail's job,
  * ska_dict.rs:131-147): all records of file 1 followed by all records of file 2, newlines
@@ -103,6 +104,31 @@ int skagpu_export(const ska_array_t* a, void* keys, uint8_t* variants_rowmajor, 
 int skagpu_export_transposed(const ska_array_t* a, uint8_t* samples_by_rows);
 
 void skagpu_free(ska_array_t* a);
+
+/* ---- row-sharded build across GPUs (one process per GPU) -------------------
+ * The reference is single-node shared-memory (README.md:124); these entry points split
+ * build_and_merge (merge_ska_dict.rs:354-417) at its one exchange point so that the caller -- one
+ * process per GPU, torch.distributed/NCCL for the transport -- can co-locate identical split k-mers:
+ *   1. skagpu_extract_records: K1 over this rank's samples (global sample ids = sample_id_base + i),
+ *      records sorted by the top `prefix_bits` bits of the key; bucket offsets tell how many records
+ *      fall in every key-prefix bucket (summed over ranks they give balanced key-range owners);
+ *   2. the caller exchanges, per owner, the contiguous record range of its buckets (all-to-all);
+ *   3. skagpu_merge_records_dev: merges the received records (device pointers, u64 records and u16
+ *      sample ids) into this rank's slab of rows, with all n_samples_total columns.
+ * Slabs are key ranges in rank order, so their concatenation is the canonical (ascending key) array.
+ * Record buffers stay valid until the next extract/build/merge call on this process. */
+int skagpu_extract_records(const ska_seqbatch_t* batch, uint32_t k, int rc, uint32_t sample_id_base, int prefix_bits,
+                           ska_records_t** out);
+int skagpu_records_info(const ska_records_t* r, uint64_t* n, const void** rec_dev, const void** sid_dev,
+                        uint64_t* bucket_offsets);
+void skagpu_records_free(ska_records_t* r);
+int skagpu_merge_records_dev(void* rec_dev, void* sid_dev, uint64_t n, uint64_t n_samples_total, uint32_t k, int rc,
+                             int key_space_shift /* this shard holds ~2^-shift of the key space (log2 of #ranks) */,
+                             ska_array_t** out);
+/* Per-pair partial sums of variant_dist (merge_ska_array.rs:599-620) over this array's rows, 4 x u64 per
+ * pair {mismatches, matches, dist_int, n_both}: integers, so row shards add up exactly (all-reduce);
+ * distance = dist_int (filt_ambig) or n_both - dist_int/36 (allow-ambiguous), matches += constant. */
+int skagpu_distance_counters(const ska_array_t* a, int filt_ambig, uint64_t* counters);
 
 /* Pinned host memory for callers that want full-speed PCIe transfers. */
 void* skagpu_host_alloc(size_t bytes);

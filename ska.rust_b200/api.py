@@ -30,7 +30,8 @@ EXPORTS = [
     "skagpu_last_error", "skagpu_set_device", "skagpu_build", "skagpu_seqbatch_upload", "skagpu_build_from_batch",
     "skagpu_seqbatch_free", "skagpu_array_from_host", "skagpu_dims", "skagpu_filter", "skagpu_distance", "skagpu_export",
     "skagpu_export_transposed", "skagpu_free", "skagpu_host_alloc", "skagpu_host_free", "skagpu_last_timings",
-    "skagpu_launch_count", "skagpu_k1_extract", "skagpu_stream_timer",
+    "skagpu_launch_count", "skagpu_k1_extract", "skagpu_stream_timer", "skagpu_extract_records", "skagpu_records_info",
+    "skagpu_records_free", "skagpu_merge_records_dev", "skagpu_distance_counters",
 ]
 
 
@@ -76,6 +77,12 @@ def lib():
         L.skagpu_last_timings.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
         L.skagpu_launch_count.restype = C.c_uint64
         L.skagpu_stream_timer.argtypes = [C.c_int, C.c_void_p]
+        L.skagpu_extract_records.argtypes = [C.c_void_p, C.c_uint32, C.c_int, C.c_uint32, C.c_int, C.c_void_p]
+        L.skagpu_records_info.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.skagpu_records_free.argtypes = [C.c_void_p]
+        L.skagpu_merge_records_dev.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint32, C.c_int, C.c_int,
+                                               C.c_void_p]
+        L.skagpu_distance_counters.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
         L.skagpu_k1_extract.argtypes = [C.c_void_p, C.c_uint32, C.c_int, C.c_uint8, C.c_int, C.c_int, C.c_void_p,
                                         C.c_void_p, C.c_void_p]
         _lib = L
@@ -344,6 +351,13 @@ class MergeSkaArray:
         out = (_Dist * max(1, n * (n - 1) // 2))()
         _check(lib().skagpu_distance(self._h, float(constant), int(filt_ambig), out))
         return [(d.distance, d.mismatch_prop, d.match_count, d.mismatch_count) for d in out[:n * (n - 1) // 2]]
+
+    def distance_counters(self, filt_ambig):
+        """(n_pairs, 4) uint64 partial sums {mismatches, matches, dist_int, n_both} over this array's rows"""
+        n = self.nsamples()
+        out = np.zeros((max(1, n * (n - 1) // 2), 4), dtype=np.uint64)
+        _check(lib().skagpu_distance_counters(self._h, int(filt_ambig), out.ctypes.data))
+        return out[:n * (n - 1) // 2]
 
     # ---- MergeSkaArray::write_fasta (merge_ska_array.rs:499-517)
     def transpose_on_device(self):

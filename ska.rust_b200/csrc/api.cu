@@ -199,6 +199,11 @@ static thread_local std::string g_err;
 
 struct ska_array { Array a; };
 struct ska_seqbatch { std::unique_ptr<SeqBatch> b; };
+struct ska_records {            // K1 output of one rank, sorted by key prefix; lives in the arena until the next build
+    uint64_t* rec = nullptr; uint16_t* sid = nullptr; uint64_t n = 0;
+    uint32_t k = 0; bool rc = false; int prefix_bits = 0;
+    std::vector<uint64_t> off;  // 2^prefix_bits + 1 bucket offsets
+};
 
 extern "C" {
 
@@ -354,6 +359,85 @@ int skagpu_export_transposed(const ska_array_t* h, uint8_t* out) {
 }
 
 void skagpu_free(ska_array_t* h) { delete h; }
+
+// ---- row-sharded (multi-GPU) build: extract + local partition | exchange (caller) | merge ----------
+int skagpu_extract_records(const ska_seqbatch_t* batch, uint32_t k, int rc, uint32_t sample_id_base, int prefix_bits,
+                           ska_records_t** out) {
+    API_TRY
+    *out = nullptr;
+    Context& c = ctx();
+    c.ensure();
+    check_k(k);
+    if (k > 31) throw Error("k > 31 (128-bit split k-mers) is not yet built on the device; use k <= 31");
+    const SeqBatch& b = *batch->b;
+    if (b.has_qual) throw Error("FASTQ input (count/bloom filter, K2q) is not yet built on the device");
+    if (sample_id_base + b.n_samples > 65536) throw Error("at most 65536 samples in total (16-bit sample ids)");
+    if (prefix_bits < 0 || prefix_bits > 24 || prefix_bits > 2 * ((int)k - 1)) throw Error("bad prefix_bits");
+    timer().clear();
+    arena().reset();
+    std::unique_ptr<ska_records> r(new ska_records());
+    r->k = k; r->rc = rc != 0; r->prefix_bits = prefix_bits; r->n = b.n_pos;
+    uint64_t* rec = arena().take_n<uint64_t>(b.n_pos);
+    uint16_t* sid = arena().take_n<uint16_t>(b.n_pos);
+    uint32_t* valid = arena().take_n<uint32_t>(b.n_samples);
+    SKA_CUDA(cudaMemsetAsync(valid, 0, b.n_samples * 4, c.stream));
+    timer().begin("k1_extract");
+    launch_k1(b, k, rc != 0, false, 0, rec, sid, valid, sample_id_base);
+    timer().end();
+    std::vector<uint32_t> h_valid(b.n_samples);
+    SKA_CUDA(cudaMemcpyAsync(h_valid.data(), valid, b.n_samples * 4, cudaMemcpyDeviceToHost, c.stream));
+    r->off.resize(((size_t)1 << prefix_bits) + 1);
+    timer().begin("partition_by_owner");
+    sort_records_by_prefix(rec, sid, b.n_pos, k, prefix_bits, &r->rec, &r->sid, r->off.data());   // synchronises
+    timer().end();
+    for (size_t s = 0; s < b.n_samples; s++)
+        if (h_valid[s] == 0) throw Error("sample " + std::to_string(sample_id_base + s) + " has no valid sequence");
+    *out = r.release();
+    return 0;
+    API_CATCH
+}
+
+int skagpu_records_info(const ska_records_t* r, uint64_t* n, const void** rec_dev, const void** sid_dev,
+                        uint64_t* bucket_offsets /* 2^prefix_bits + 1, may be NULL */) {
+    API_TRY
+    if (!r) throw Error("null records");
+    if (n) *n = r->n;
+    if (rec_dev) *rec_dev = r->rec;
+    if (sid_dev) *sid_dev = r->sid;
+    if (bucket_offsets) memcpy(bucket_offsets, r->off.data(), r->off.size() * 8);
+    return 0;
+    API_CATCH
+}
+
+void skagpu_records_free(ska_records_t* r) { delete r; }
+
+int skagpu_merge_records_dev(void* rec_dev, void* sid_dev, uint64_t n, uint64_t n_samples_total, uint32_t k, int rc,
+                             int key_space_shift, ska_array_t** out) {
+    API_TRY
+    *out = nullptr;
+    Context& c = ctx();
+    c.ensure();
+    check_k(k);
+    if (k > 31) throw Error("k > 31 not yet supported on the device");
+    // the caller's buffers may have been filled on another stream (NCCL): order after everything
+    SKA_CUDA(cudaDeviceSynchronize());
+    arena().reset();
+    std::unique_ptr<ska_array> h(new ska_array());
+    if (key_space_shift < 0 || key_space_shift > 16) throw Error("bad key_space_shift");
+    build_array_from_records((uint64_t*)rec_dev, (uint16_t*)sid_dev, n, n_samples_total, k, rc != 0, h->a, key_space_shift);
+    *out = h.release();
+    return 0;
+    API_CATCH
+}
+
+int skagpu_distance_counters(const ska_array_t* h, int filt_ambig, uint64_t* counters) {
+    API_TRY
+    if (!h) throw Error("null array");
+    ctx().ensure();
+    distance_counters(h->a, filt_ambig != 0, counters);
+    return 0;
+    API_CATCH
+}
 
 void* skagpu_host_alloc(size_t bytes) {
     void* p = nullptr;

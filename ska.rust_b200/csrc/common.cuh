@@ -129,11 +129,15 @@ struct Array {
 // --- kernels' host launchers (one .cu each) ------------------------------------------------------
 // k1_extract.cu
 void launch_k1(const SeqBatch& b, uint32_t k, bool rc, bool strict_qual, uint8_t min_qual, uint64_t* rec_out,
-               uint16_t* sid_out, uint32_t* sample_valid);
+               uint16_t* sid_out, uint32_t* sample_valid, uint32_t sid_base = 0);
 size_t padded_positions(uint64_t n_pos);
 // merge.cu
 void build_array_from_records(uint64_t* rec, uint16_t* sid, uint64_t n_pos, uint64_t n_samples, uint32_t k, bool rc,
-                              Array& out);
+                              Array& out, int extra_prefix_bits = 0);
+// sorts (rec, sid) by the top `prefix_bits` of the key (in place or into arena buffers) and writes the
+// 2^prefix_bits + 1 bucket offsets to h_off; returns where the sorted arrays live
+void sort_records_by_prefix(uint64_t* rec, uint16_t* sid, uint64_t n, uint32_t k, int prefix_bits, uint64_t** rec_sorted,
+                            uint16_t** sid_sorted, uint64_t* h_off);
 // exclusive scan of n u32 counts into n+1 u64 offsets (off[n] = total); *max_out = max count
 void launch_scan_counts(const uint32_t* cnt, uint32_t n, uint64_t* off, uint32_t* max_out);
 // filter.cu
@@ -143,5 +147,8 @@ void transpose_array(const Array& a, uint8_t* d_out);
 // distance.cu
 struct DistOut { double distance, mismatch_prop; uint64_t match_count, mismatch_count; };
 void distance_array(const Array& a, double constant, bool filt_ambig, DistOut* h_out);
+// raw per-pair counters {mismatches, matches, dist_int, n_both} (dist_int: differing unambiguous pairs, or
+// 36 x summed overlap when !filt_ambig); partial sums over this array's rows, addable across row shards
+void distance_counters(const Array& a, bool filt_ambig, uint64_t* h_counters);
 
 }  // namespace ska

@@ -15,6 +15,8 @@
 // `--allow-ambiguous` (filt_ambig = false) and arrays whose unambiguous symbols are not plain
 // upper-case ACGT use an exact byte-wise kernel: per pair and row, overlap of the two IUPAC sets
 // is accumulated as the integer 36*|a&b|/(|a||b|) (bit_encoding.rs:65-85: N and unknown -> empty).
+#include <cstring>
+
 #include "common.cuh"
 
 namespace ska {
@@ -179,7 +181,7 @@ static void finish(double constant, double distance, uint64_t match_rows, uint64
     o.mismatch_count = (uint64_t)mismatches;
 }
 
-void distance_array(const Array& a, double constant, bool filt_ambig, DistOut* h_out) {
+void distance_counters(const Array& a, bool filt_ambig, uint64_t* h_counters) {
     Context& c = ctx();
     const uint32_t N = (uint32_t)a.n_samples;
     if (N < 2) return;
@@ -189,6 +191,7 @@ void distance_array(const Array& a, double constant, bool filt_ambig, DistOut* h
     const uint32_t n_tile_pairs = n_tiles * (n_tiles + 1) / 2;
     bool use_planes = filt_ambig && R > 0;
     std::vector<unsigned long long> h_acc;
+    memset(h_counters, 0, n_pairs * 4 * sizeof(uint64_t));
 
     if (use_planes) {
         const uint64_t n_words = (R + 31) / 32;
@@ -217,8 +220,10 @@ void distance_array(const Array& a, double constant, bool filt_ambig, DistOut* h
             h_acc.resize(3 * n_pairs);
             SKA_CUDA(cudaMemcpyAsync(h_acc.data(), acc.p, acc.bytes(), cudaMemcpyDeviceToHost, c.stream));
             SKA_CUDA(cudaStreamSynchronize(c.stream));
-            for (uint64_t p = 0; p < n_pairs; p++)
-                finish(constant, (double)h_acc[3 * p + 2], h_acc[3 * p + 1], h_acc[3 * p + 0], h_out[p]);
+            for (uint64_t p = 0; p < n_pairs; p++) {
+                h_counters[4 * p + 0] = h_acc[3 * p + 0]; h_counters[4 * p + 1] = h_acc[3 * p + 1];
+                h_counters[4 * p + 2] = h_acc[3 * p + 2]; h_counters[4 * p + 3] = 0;
+            }
             return;
         }
     }
@@ -234,14 +239,21 @@ void distance_array(const Array& a, double constant, bool filt_ambig, DistOut* h
         dim3 grid(n_tile_pairs, (unsigned)splits);
         SKA_LAUNCH(pair_bytes_kernel, grid, 256, 0, a.variants.p, R, N, n_tiles, rows_per_split, filt_ambig ? 1 : 0, acc.p);
     }
-    h_acc.resize(4 * n_pairs);
-    SKA_CUDA(cudaMemcpyAsync(h_acc.data(), acc.p, acc.bytes(), cudaMemcpyDeviceToHost, c.stream));
+    static_assert(sizeof(unsigned long long) == sizeof(uint64_t), "");
+    SKA_CUDA(cudaMemcpyAsync(h_counters, acc.p, acc.bytes(), cudaMemcpyDeviceToHost, c.stream));
     SKA_CUDA(cudaStreamSynchronize(c.stream));
+}
+
+void distance_array(const Array& a, double constant, bool filt_ambig, DistOut* h_out) {
+    const uint32_t N = (uint32_t)a.n_samples;
+    if (N < 2) return;
+    const uint64_t n_pairs = (uint64_t)N * (N - 1) / 2;
+    std::vector<uint64_t> cnt(4 * n_pairs);
+    distance_counters(a, filt_ambig, cnt.data());
     for (uint64_t p = 0; p < n_pairs; p++) {
-        double d;
-        if (filt_ambig) d = (double)h_acc[4 * p + 2];
-        else d = (double)h_acc[4 * p + 3] - (double)h_acc[4 * p + 2] / 36.0;   // sum of (1 - overlap), exact rational
-        finish(constant, d, h_acc[4 * p + 1], h_acc[4 * p + 0], h_out[p]);
+        double d = filt_ambig ? (double)cnt[4 * p + 2]
+                              : (double)cnt[4 * p + 3] - (double)cnt[4 * p + 2] / 36.0;   // sum of (1 - overlap), exact rational
+        finish(constant, d, cnt[4 * p + 1], cnt[4 * p + 0], h_out[p]);
     }
 }
 

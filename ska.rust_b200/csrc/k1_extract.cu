@@ -116,7 +116,8 @@ __global__ void __launch_bounds__(K1_THREADS)
 k1_extract_kernel(const uint8_t* __restrict__ seq, const uint8_t* __restrict__ qual,
                   const uint32_t* __restrict__ start_bits, const uint64_t* __restrict__ sample_off,
                   uint32_t n_samples, uint64_t n_pos, int k_rt, int rc, uint32_t min_qual,
-                  uint64_t* __restrict__ rec_out, uint16_t* __restrict__ sid_out, uint32_t* __restrict__ sample_valid) {
+                  uint64_t* __restrict__ rec_out, uint16_t* __restrict__ sid_out, uint32_t* __restrict__ sample_valid,
+                  uint32_t sid_base) {
     __shared__ __align__(128) uint8_t s_ascii[K1_BYTES];
     __shared__ __align__(128) uint8_t s_qual[HAS_QUAL ? K1_BYTES : 16];
     __shared__ uint32_t s_le[2 * K1_G32 + 2];
@@ -244,7 +245,7 @@ k1_extract_kernel(const uint8_t* __restrict__ seq, const uint8_t* __restrict__ q
     if (full && uniform) {                                        // interior tile of one sample: no per-window checks
         if (sout) {
 #pragma unroll 4
-            for (int j = warp; j < K1_T / 32; j += K1_THREADS / 32) { out[32 * j] = window(j); sout[32 * j] = (uint16_t)sid_first; }
+            for (int j = warp; j < K1_T / 32; j += K1_THREADS / 32) { out[32 * j] = window(j); sout[32 * j] = (uint16_t)(sid_first + sid_base); }
         } else {
 #pragma unroll 4
             for (int j = warp; j < K1_T / 32; j += K1_THREADS / 32) out[32 * j] = window(j);
@@ -258,7 +259,7 @@ k1_extract_kernel(const uint8_t* __restrict__ seq, const uint8_t* __restrict__ q
             uint32_t lo = sid_first, hi = sid_last + 1;           // tile straddles samples or the end of the batch
             while (hi - lo > 1) { uint32_t m = (lo + hi) >> 1; if (sample_off[m] <= p) lo = m; else hi = m; }
             if (!uniform && sample_valid && rec != REC_SENTINEL) atomicAdd(&sample_valid[lo], 1u);
-            if (sout) sout[32 * j] = (uint16_t)lo;
+            if (sout) sout[32 * j] = (uint16_t)(lo + sid_base);
         }
     }
     // accepted windows per sample (a sample with none is an error, ska_dict.rs:374-376)
@@ -267,24 +268,24 @@ k1_extract_kernel(const uint8_t* __restrict__ seq, const uint8_t* __restrict__ q
 
 template <int KT>
 static void launch_k1_kt(const SeqBatch& b, uint32_t k, bool rc, bool strict_qual, uint8_t min_qual, uint64_t* rec_out,
-                         uint16_t* sid_out, uint32_t* sample_valid) {
+                         uint16_t* sid_out, uint32_t* sample_valid, uint32_t sid_base) {
     unsigned grid = (unsigned)((b.n_pos + K1_T - 1) / K1_T);
     if (b.has_qual && strict_qual) {
         SKA_LAUNCH((k1_extract_kernel<KT, true>), grid, K1_THREADS, 0, b.seq.p, b.qual.p, b.start_bits.p, b.sample_off.p,
-                   (uint32_t)b.n_samples, b.n_pos, (int)k, rc ? 1 : 0, (uint32_t)min_qual, rec_out, sid_out, sample_valid);
+                   (uint32_t)b.n_samples, b.n_pos, (int)k, rc ? 1 : 0, (uint32_t)min_qual, rec_out, sid_out, sample_valid, sid_base);
     } else {
         SKA_LAUNCH((k1_extract_kernel<KT, false>), grid, K1_THREADS, 0, b.seq.p, (const uint8_t*)nullptr, b.start_bits.p,
                    b.sample_off.p, (uint32_t)b.n_samples, b.n_pos, (int)k, rc ? 1 : 0, (uint32_t)min_qual, rec_out, sid_out,
-                   sample_valid);
+                   sample_valid, sid_base);
     }
 }
 
 void launch_k1(const SeqBatch& b, uint32_t k, bool rc, bool strict_qual, uint8_t min_qual, uint64_t* rec_out,
-               uint16_t* sid_out, uint32_t* sample_valid) {
+               uint16_t* sid_out, uint32_t* sample_valid, uint32_t sid_base) {
     if (b.n_pos == 0) return;
     // the default k of `ska build` (cli.rs:9) gets a compile-time specialisation
-    if (k == 31) launch_k1_kt<31>(b, k, rc, strict_qual, min_qual, rec_out, sid_out, sample_valid);
-    else launch_k1_kt<0>(b, k, rc, strict_qual, min_qual, rec_out, sid_out, sample_valid);
+    if (k == 31) launch_k1_kt<31>(b, k, rc, strict_qual, min_qual, rec_out, sid_out, sample_valid, sid_base);
+    else launch_k1_kt<0>(b, k, rc, strict_qual, min_qual, rec_out, sid_out, sample_valid, sid_base);
 }
 
 }  // namespace ska

@@ -77,6 +77,7 @@ bucket_count_kernel(const uint64_t* __restrict__ rec, const Item* __restrict__ i
     __shared__ uint64_t s_tab[COUNT_CAP];
     __shared__ uint32_t s_n, s_over;
     const Item it = items[blockIdx.x];
+    if (it.beg == it.end) { if (threadIdx.x == 0) n_rows[blockIdx.x] = 0; return; }
     for (int i = threadIdx.x; i < COUNT_CAP; i += MG_THREADS) s_tab[i] = KEY_EMPTY;
     if (threadIdx.x == 0) { s_n = 0; s_over = 0; }
     __syncthreads();
@@ -386,6 +387,32 @@ bucket_emit_kernel(const uint64_t* __restrict__ rec, const uint16_t* __restrict_
     for (uint32_t i = threadIdx.x; i < u; i += MG_THREADS) out_cnt[row_base + i] = s_cnt[i];
 }
 
+void sort_records_by_prefix(uint64_t* rec, uint16_t* sid, uint64_t n, uint32_t k, int prefix_bits, uint64_t** rec_sorted,
+                            uint16_t** sid_sorted, uint64_t* h_off) {
+    Context& c = ctx();
+    const int key_bits = 2 * ((int)k - 1);
+    if (prefix_bits > key_bits) throw Error("prefix_bits exceeds the key width");
+    const int shift = 4 + key_bits - prefix_bits;
+    const uint32_t n_buckets = 1u << prefix_bits;
+    *rec_sorted = rec; *sid_sorted = sid;
+    if (prefix_bits > 0 && n > 0) {
+        uint64_t* rec_alt = arena().take_n<uint64_t>(n);
+        uint16_t* sid_alt = arena().take_n<uint16_t>(n);
+        cub::DoubleBuffer<uint64_t> dk(rec, rec_alt);
+        cub::DoubleBuffer<uint16_t> dv(sid, sid_alt);
+        size_t tmp_bytes = 0;
+        SKA_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, dk, dv, (int64_t)n, shift, shift + prefix_bits, c.stream));
+        void* tmp = arena().take(tmp_bytes);
+        SKA_CUDA(cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, dk, dv, (int64_t)n, shift, shift + prefix_bits, c.stream));
+        c.launches += (prefix_bits + 7) / 8 + 1;
+        *rec_sorted = dk.Current(); *sid_sorted = dv.Current();
+    }
+    uint64_t* off = arena().take_n<uint64_t>(n_buckets + 1);
+    SKA_LAUNCH(bucket_offsets_kernel, (n_buckets + 1 + 255) / 256, 256, 0, *rec_sorted, n, shift, n_buckets, off);
+    SKA_CUDA(cudaMemcpyAsync(h_off, off, (n_buckets + 1) * 8, cudaMemcpyDeviceToHost, c.stream));
+    SKA_CUDA(cudaStreamSynchronize(c.stream));
+}
+
 static int choose_prefix_bits(uint64_t n_pos, int key_bits, uint64_t target) {
     int p = 0;
     while ((n_pos >> p) > target && p < key_bits && p < 24) p++;
@@ -393,7 +420,7 @@ static int choose_prefix_bits(uint64_t n_pos, int key_bits, uint64_t target) {
 }
 
 void build_array_from_records(uint64_t* rec, uint16_t* sid, uint64_t n_pos, uint64_t n_samples, uint32_t k, bool rc,
-                              Array& out) {
+                              Array& out, int extra_prefix_bits) {
     Context& c = ctx();
     const int key_bits = 2 * ((int)k - 1);
     // bytes of shared memory per table slot in the emit kernel: tab 8 + rank 2 + (lkey 8 + lslot 2 + cnt 4)/2
@@ -405,6 +432,8 @@ void build_array_from_records(uint64_t* rec, uint16_t* sid, uint64_t n_pos, uint
     // remain small enough for the shared-memory tables
     int P = choose_prefix_bits(n_pos, key_bits, 4096);
     if (P > 16 && (n_pos >> 16) <= 16384) P = 16;
+    // a row shard holds only ~2^-extra of the key space: refine so that occupied buckets keep their size
+    P = std::min(std::min(P + extra_prefix_bits, 24), key_bits);
     if (const char* e = getenv("SKA_PREFIX_BITS")) { int v = atoi(e); if (v >= 0 && v <= key_bits && v <= 24) P = v; }   // tuning/tests
     const uint32_t n_buckets = 1u << P;
     const int shift = 4 + key_bits - P;

@@ -1,0 +1,165 @@
+"""Row-sharded build / align / distance over several GPUs: one process per GPU, torch.distributed for
+the transport (NCCL on GPUs; gloo in the CPU tests).
+
+The reference is single-node shared memory (README.md:124); its build_and_merge
+(src/merge_ska_dict.rs:354-417) has exactly one point where data from different samples must meet --
+rows of the merged dictionary are keyed by split k-mer.  Here:
+
+  1. every rank extracts the records of ITS samples (K1) and sorts them by the top `prefix_bits` bits of
+     the key; the per-bucket record counts are summed over ranks (all-reduce) and cut into `world`
+     contiguous key ranges of equal record count -> owner of every bucket;
+  2. ONE all-to-all moves each record range to its owner (records u64, sample ids u16);
+  3. every rank merges what it received into its slab of rows with ALL samples' columns.  Filters are
+     row-local; distances are per-pair integer sums over rows, so slabs add up with one all-reduce.
+
+Slabs are ascending key ranges in rank order: concatenating them gives the canonical array, which is
+how results are compared with the single-GPU path (identical, not merely equivalent).
+
+`backend` abstracts the three device steps so the same orchestration runs on CPU in the tests
+(tests/test_distributed_gloo.py injects an oracle-backed backend); the product backend is GpuBackend.
+"""
+import math
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from . import api
+
+
+class _CudaView:
+    """zero-copy torch view of library-owned device memory"""
+
+    def __init__(self, ptr, n, typestr):
+        self.__cuda_array_interface__ = {"shape": (n,), "typestr": typestr, "data": (ptr, False), "version": 2}
+
+
+class GpuBackend:
+    """The product backend: libskagpu through its C ABI."""
+    device = "cuda"
+
+    def extract(self, samples, k, rc, sample_base, prefix_bits):
+        import ctypes as C
+        batch = samples if isinstance(samples, api.SeqBatch) else api.SeqBatch(samples)
+        h = C.c_void_p()
+        api._check(api.lib().skagpu_extract_records(batch._h, k, int(rc), sample_base, prefix_bits, C.byref(h)))
+        n = C.c_uint64()
+        rec_p, sid_p = C.c_void_p(), C.c_void_p()
+        off = np.zeros((1 << prefix_bits) + 1, dtype=np.uint64)
+        api._check(api.lib().skagpu_records_info(h, C.byref(n), C.byref(rec_p), C.byref(sid_p), off.ctypes.data))
+        api.lib().skagpu_records_free(h)        # frees only the handle; buffers live in the arena until the next build
+        n = n.value
+        if n:
+            rec = torch.as_tensor(_CudaView(rec_p.value, n, "<i8"), device="cuda")
+            sid = torch.as_tensor(_CudaView(sid_p.value, n, "<i2"), device="cuda")
+        else:
+            rec = torch.empty(0, dtype=torch.int64, device="cuda")
+            sid = torch.empty(0, dtype=torch.int16, device="cuda")
+        return rec, sid, off
+
+    def merge(self, rec, sid, n_samples_total, k, rc, names, world=1):
+        import ctypes as C
+        h = C.c_void_p()
+        shift = max(0, math.ceil(math.log2(world)))
+        api._check(api.lib().skagpu_merge_records_dev(rec.data_ptr(), sid.data_ptr(), rec.numel(), n_samples_total, k,
+                                                      int(rc), shift, C.byref(h)))
+        return api.MergeSkaArray(h, names)
+
+
+def plan_owners(global_bucket_counts, world):
+    """Cut the buckets (ascending key prefix) into `world` contiguous ranges of near-equal record count.
+    -> int array of world+1 bucket indices.  Deterministic given the counts."""
+    c = np.asarray(global_bucket_counts, dtype=np.uint64)
+    cum = np.concatenate([[0], np.cumsum(c)])
+    total = int(cum[-1])
+    cuts = [0]
+    for g in range(1, world):
+        target = total * g // world
+        b = int(np.searchsorted(cum, target, side="left"))
+        cuts.append(min(max(b, cuts[-1]), len(c)))
+    cuts.append(len(c))
+    return np.array(cuts, dtype=np.int64)
+
+
+def build_and_merge_sharded(backend, samples_local, names_all, sample_base, k, rc, prefix_bits=16, group=None,
+                            timings=None):
+    """-> this rank's slab (a MergeSkaArray with len(names_all) columns).  Collective over `group`."""
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    key_bits = 2 * (k - 1)
+    prefix_bits = min(prefix_bits, key_bits)
+    dev = backend.device
+    rec, sid, off = backend.extract(samples_local, k, rc, sample_base, prefix_bits)
+    counts = torch.from_numpy(np.diff(off).astype(np.int64)).to(dev)
+    dist.all_reduce(counts, group=group)
+    cuts = plan_owners(counts.cpu().numpy(), world)
+    bounds = off[cuts].astype(np.int64)                   # record index where each owner's range starts
+    send_counts = np.diff(bounds)
+    sc = torch.from_numpy(send_counts).to(dev)
+    rc_ = torch.empty_like(sc)
+    dist.all_to_all_single(rc_, sc, group=group)
+    recv_counts = rc_.cpu().numpy()
+    n_recv = int(recv_counts.sum())
+    recv_rec = torch.empty(n_recv, dtype=torch.int64, device=dev)
+    recv_sid = torch.empty(n_recv, dtype=torch.int16, device=dev)
+    # records are sorted by prefix, so each owner's share is one contiguous range starting at bounds[0] == 0
+    dist.all_to_all_single(recv_rec, rec[:int(bounds[-1])], list(map(int, recv_counts)), list(map(int, send_counts)), group=group)
+    # sample ids travel as raw bytes (gloo has no 16-bit integer all-to-all)
+    dist.all_to_all_single(recv_sid.view(torch.uint8), sid[:int(bounds[-1])].view(torch.uint8),
+                           [2 * int(c) for c in recv_counts], [2 * int(c) for c in send_counts], group=group)
+    if timings is not None:
+        timings["sent_records"] = int(send_counts.sum() - send_counts[rank])
+        timings["recv_records"] = n_recv
+    return backend.merge(recv_rec, recv_sid, len(names_all), k, rc, names_all, world)
+
+
+def align_sharded(arr, filter_type="no-const", mask_ambig=False, ignore_const_gaps=False, min_freq=0.9,
+                  filter_ambig_as_missing=False):
+    """generic_modes.rs:22-50 on a slab: filters are row-local (merge_ska_array.rs:312-379).
+    -> (n_samples, rows_of_this_slab) uint8; column blocks concatenate in rank order."""
+    api.apply_filters(arr, min_freq, filter_ambig_as_missing, filter_type, mask_ambig, ignore_const_gaps)
+    return arr.transposed()
+
+
+def gather_alignment(slab_t, names, group=None, dst=0):
+    """Concatenate the ranks' column blocks on `dst` and format the FASTA (merge_ska_array.rs:499-517)."""
+    world = dist.get_world_size(group)
+    parts = [None] * world if dist.get_rank(group) == dst else None
+    dist.gather_object(np.ascontiguousarray(slab_t), parts, dst=dst, group=group)
+    if parts is None:
+        return None
+    full = np.concatenate(parts, axis=1)
+    return b"".join(b">" + n.encode() + b"\n" + full[i].tobytes() + b"\n" for i, n in enumerate(names))
+
+
+def distance_sharded(arr, min_freq=0.0, filt_ambig=True, group=None):
+    """generic_modes.rs:136-189 on slabs: -> [(distance, mismatch_prop, matches, mismatches)] for all pairs,
+    identical on every rank."""
+    n = arr.nsamples()
+    dev = "cuda" if torch.cuda.is_available() and dist.get_backend(group) == "nccl" else "cpu"
+    if min_freq * n >= 1.0:
+        api.apply_filters(arr, min_freq, False, "no-filter", False, False)
+    constant = api.apply_filters(arr, 0.0, False, "no-const", False, False)
+    cnt = arr.distance_counters(filt_ambig).astype(np.int64)
+    t = torch.from_numpy(np.concatenate([cnt.reshape(-1), np.array([constant], dtype=np.int64)])).to(dev)
+    dist.all_reduce(t, group=group)
+    t = t.cpu().numpy()
+    cnt, constant = t[:-1].reshape(-1, 4), float(t[-1])
+    out = []
+    for mism, match, dint, nboth in cnt:
+        d = float(dint) if filt_ambig else float(nboth) - float(dint) / 36.0
+        matches = constant + float(match)                 # merge_ska_array.rs:598
+        mismatches = float(mism)
+        prop = 0.0 if matches + mismatches == 0.0 else mismatches / (matches + mismatches)
+        out.append((d, prop, int(matches), int(mismatches)))
+    return out
+
+
+def format_distances(names, dists):
+    lines = ["Sample1\tSample2\tDistance\tMismatches (proportion)\tMatch count\tMismatch count"]
+    it = iter(dists)
+    for i in range(len(names)):
+        for j in range(i + 1, len(names)):
+            d, p, m, mm = next(it)
+            lines.append(f"{names[i]}\t{names[j]}\t{d:.2f}\t{p:.5f}\t{m}\t{mm}")
+    return ("\n".join(lines) + "\n").encode()

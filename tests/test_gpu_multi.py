@@ -1,0 +1,82 @@
+"""Row-sharded build across 2 GPUs (NCCL) must reproduce the single-GPU array exactly.  Skipped unless the
+box has >= 2 GPUs (run with `gpurun --gpus 2`)."""
+import io
+import os
+import socket
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def worker(rank, world, port, n, length, k, ret):
+    import torch
+    import torch.distributed as dist
+
+    import ska_rust_b200 as S
+    import ska_rust_b200.distributed as D
+    from ska_rust_b200 import synth
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    S.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        genomes = synth.star_genomes(n, length, seed=0x5CA20009, snp_rate=0.002)
+        # a few N runs and a second contig so sentinels and record boundaries cross the exchange too
+        seqs = []
+        for i, g in enumerate(genomes):
+            g = g.copy()
+            g[1000 * (i + 1):1000 * (i + 1) + 37] = ord("N")
+            seqs.append([g[:length // 2].tobytes(), g[length // 2:].tobytes()])
+        names = [f"s{i}" for i in range(n)]
+        per = n // world
+        lo, hi = rank * per, (rank + 1) * per if rank < world - 1 else n
+        local = [S.Sample.from_records(seqs[i]) for i in range(lo, hi)]
+        backend = D.GpuBackend()
+        slab = D.build_and_merge_sharded(backend, local, names, lo, k, True, prefix_bits=12)
+        keys, var, cnt = slab.export()
+        parts = [None] * world if rank == 0 else None
+        dist.gather_object((np.asarray(keys), var, cnt), parts, dst=0)
+        slab_d = D.build_and_merge_sharded(backend, local, names, lo, k, True, prefix_bits=12)
+        dists = D.distance_sharded(slab_d, filt_ambig=True)
+        aln = D.gather_alignment(D.align_sharded(slab), names)
+        if rank == 0:
+            full = S.build_from_samples([S.Sample.from_records(s) for s in seqs], names, k, True)
+            fk, fv, fc = full.export()
+            ok = (np.array_equal(np.concatenate([p[0] for p in parts]), fk) and
+                  np.array_equal(np.concatenate([p[1] for p in parts]), fv) and
+                  np.array_equal(np.concatenate([p[2] for p in parts]), fc))
+            buf = io.BytesIO()
+            S.api.align(full, buf)
+            full2 = S.build_from_samples([S.Sample.from_records(s) for s in seqs], names, k, True)
+            dbuf = io.BytesIO()
+            S.api.distance(full2, dbuf)
+            ret["array_equal"] = bool(ok)
+            ret["rows"] = [int(len(p[0])) for p in parts]
+            ret["aln_equal"] = aln == buf.getvalue()
+            ret["dist_equal"] = D.format_distances(names, dists) == dbuf.getvalue()
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_gpu_build_matches_single_gpu():
+    import torch
+    import torch.multiprocessing as mp
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(worker, args=(2, free_port(), 8, 200_000, 31, ret), nprocs=2, join=True)
+    assert ret["array_equal"], "concatenated slabs differ from the single-GPU array"
+    assert min(ret["rows"]) > 0.3 * max(ret["rows"]), f"unbalanced slabs {ret['rows']}"
+    assert ret["aln_equal"] and ret["dist_equal"]
