@@ -16,7 +16,7 @@ Slabs are ascending key ranges in rank order: concatenating them gives the canon
 how results are compared with the single-GPU path (identical, not merely equivalent).
 
 `backend` abstracts the three device steps so the same orchestration runs on CPU in the tests
-(tests/test_distributed_gloo.py injects an oracle-backed backend); the product backend is GpuBackend.
+(tests/test_distributed_gloo.py injects a CPU stand-in); the product backend is GpuBackend.
 """
 import math
 
