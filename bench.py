@@ -182,7 +182,7 @@ def run_ours(args, rank, world, local_rank):
     def build_device(batch):
         if world == 1:
             return S.api.build_from_batch(batch, names, k, True)
-        return D.build_and_merge_sharded(backend, batch, names, rank * G, k, True, prefix_bits=16)
+        return D.build_and_merge_sharded(backend, batch, names, rank * G, k, True)
 
     # ---------------- device-resident arm
     batch = S.SeqBatch(samples)

@@ -31,7 +31,7 @@ EXPORTS = [
     "skagpu_seqbatch_free", "skagpu_array_from_host", "skagpu_dims", "skagpu_filter", "skagpu_distance", "skagpu_export",
     "skagpu_export_transposed", "skagpu_free", "skagpu_host_alloc", "skagpu_host_free", "skagpu_last_timings",
     "skagpu_launch_count", "skagpu_k1_extract", "skagpu_stream_timer", "skagpu_extract_records", "skagpu_records_info",
-    "skagpu_records_free", "skagpu_merge_records_dev", "skagpu_distance_counters",
+    "skagpu_records_free", "skagpu_merge_records_dev", "skagpu_distance_counters", "skagpu_merge_prefix_bits",
 ]
 
 
@@ -80,8 +80,9 @@ def lib():
         L.skagpu_extract_records.argtypes = [C.c_void_p, C.c_uint32, C.c_int, C.c_uint32, C.c_int, C.c_void_p]
         L.skagpu_records_info.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.skagpu_records_free.argtypes = [C.c_void_p]
-        L.skagpu_merge_records_dev.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint32, C.c_int, C.c_int,
-                                               C.c_void_p]
+        L.skagpu_merge_records_dev.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_uint32, C.c_uint32, C.c_int,
+                                               C.c_uint64, C.c_uint32, C.c_int, C.c_void_p]
+        L.skagpu_merge_prefix_bits.argtypes = [C.c_uint64, C.c_uint32]
         L.skagpu_distance_counters.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
         L.skagpu_k1_extract.argtypes = [C.c_void_p, C.c_uint32, C.c_int, C.c_uint8, C.c_int, C.c_int, C.c_void_p,
                                         C.c_void_p, C.c_void_p]

@@ -411,24 +411,28 @@ int skagpu_records_info(const ska_records_t* r, uint64_t* n, const void** rec_de
 
 void skagpu_records_free(ska_records_t* r) { delete r; }
 
-int skagpu_merge_records_dev(void* rec_dev, void* sid_dev, uint64_t n, uint64_t n_samples_total, uint32_t k, int rc,
-                             int key_space_shift, ska_array_t** out) {
+int skagpu_merge_records_dev(const void* rec_dev, const void* sid_dev, int n_runs, const uint64_t* run_offsets,
+                             uint32_t bucket_lo, uint32_t bucket_hi, int prefix_bits, uint64_t n_samples_total, uint32_t k,
+                             int rc, ska_array_t** out) {
     API_TRY
     *out = nullptr;
     Context& c = ctx();
     c.ensure();
     check_k(k);
     if (k > 31) throw Error("k > 31 not yet supported on the device");
+    if (bucket_hi < bucket_lo || bucket_hi > (1ull << prefix_bits)) throw Error("bad bucket range");
     // the caller's buffers may have been filled on another stream (NCCL): order after everything
     SKA_CUDA(cudaDeviceSynchronize());
     arena().reset();
     std::unique_ptr<ska_array> h(new ska_array());
-    if (key_space_shift < 0 || key_space_shift > 16) throw Error("bad key_space_shift");
-    build_array_from_records((uint64_t*)rec_dev, (uint16_t*)sid_dev, n, n_samples_total, k, rc != 0, h->a, key_space_shift);
+    build_array_from_runs((const uint64_t*)rec_dev, (const uint16_t*)sid_dev, n_runs, run_offsets, bucket_lo, bucket_hi, prefix_bits,
+                          n_samples_total, k, rc != 0, h->a);
     *out = h.release();
     return 0;
     API_CATCH
 }
+
+int skagpu_merge_prefix_bits(uint64_t n_records_total, uint32_t k) { return merge_prefix_bits(n_records_total, k, 1); }
 
 int skagpu_distance_counters(const ska_array_t* h, int filt_ambig, uint64_t* counters) {
     API_TRY

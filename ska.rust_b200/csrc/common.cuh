@@ -133,7 +133,12 @@ void launch_k1(const SeqBatch& b, uint32_t k, bool rc, bool strict_qual, uint8_t
 size_t padded_positions(uint64_t n_pos);
 // merge.cu
 void build_array_from_records(uint64_t* rec, uint16_t* sid, uint64_t n_pos, uint64_t n_samples, uint32_t k, bool rc,
-                              Array& out, int extra_prefix_bits = 0);
+                              Array& out);
+// row shard: `n_runs` received runs, each sorted by the same prefix_bits-bit key prefix over buckets [lo, hi)
+void build_array_from_runs(const uint64_t* rec, const uint16_t* sid, int n_runs, const uint64_t* run_off, uint32_t bucket_lo,
+                           uint32_t bucket_hi, int prefix_bits, uint64_t n_samples, uint32_t k, bool rc, Array& out);
+// prefix bits the merge wants for `n_records_total` records in the whole key space
+int merge_prefix_bits(uint64_t n_records_total, uint32_t k, int n_shards);
 // sorts (rec, sid) by the top `prefix_bits` of the key (in place or into arena buffers) and writes the
 // 2^prefix_bits + 1 bucket offsets to h_off; returns where the sorted arrays live
 void sort_records_by_prefix(uint64_t* rec, uint16_t* sid, uint64_t n, uint32_t k, int prefix_bits, uint64_t** rec_sorted,

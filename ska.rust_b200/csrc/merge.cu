@@ -54,7 +54,27 @@ __global__ void bucket_offsets_kernel(const uint64_t* __restrict__ rec, uint64_t
 // A work item = a contiguous record range (one prefix bucket) restricted to an inclusive key range.
 // Level-0 items cover their whole bucket; a bucket with too many distinct keys for shared memory is
 // split by further key bits into several items that each re-scan the bucket (rare path).
-struct Item { uint64_t beg, end, key_lo, key_hi; };
+// beg/end are VIRTUAL record indices.  On one GPU they are physical too.  On a row shard the bucket's
+// records arrive as one sorted run per source rank; the runs of a bucket are laid end to end in the
+// virtual index space and (seg_voff, seg_pstart)[seg0 .. seg0 + n_runs] translate to physical.
+struct Item { uint64_t beg, end, key_lo, key_hi; uint64_t seg0; };
+constexpr int MAX_RUNS = 8;
+struct SegMap { int w; uint64_t v[MAX_RUNS + 1]; uint64_t p[MAX_RUNS]; };
+__device__ __forceinline__ void segmap_load(SegMap& m, const Item& it, const uint64_t* __restrict__ seg_voff,
+                                            const uint64_t* __restrict__ seg_pstart, int n_runs) {
+    m.w = n_runs;
+    if (n_runs > 1 && threadIdx.x <= (unsigned)n_runs) {
+        m.v[threadIdx.x] = seg_voff[it.seg0 + threadIdx.x];
+        if (threadIdx.x < (unsigned)n_runs) m.p[threadIdx.x] = seg_pstart[it.seg0 + threadIdx.x];
+    }
+}
+__device__ __forceinline__ uint64_t seg_phys(const SegMap& m, uint64_t vi) {
+    if (m.w <= 1) return vi;
+    int r = 0;
+#pragma unroll
+    for (int j = 1; j < MAX_RUNS; j++) r += (j < m.w && vi >= m.v[j]) ? 1 : 0;
+    return m.p[r] + (vi - m.v[r]);
+}
 constexpr uint32_t COUNT_OVERFLOW = 0xFFFFFFFFu;
 
 __global__ void make_items_kernel(const uint64_t* __restrict__ off, uint32_t n_buckets, int key_bits, int P,
@@ -67,17 +87,21 @@ __global__ void make_items_kernel(const uint64_t* __restrict__ off, uint32_t n_b
     it.key_lo = (uint64_t)b << low;
     it.key_hi = it.key_lo | ((low >= 64) ? ~0ULL : ((1ULL << low) - 1ULL));
     if (b == n_buckets - 1) it.key_hi = ~0ULL >> 4;       // top bucket also holds nothing above the key space
+    it.seg0 = 0;
     items[b] = it;
 }
 
 // ---- pass 1: distinct keys per item
 __global__ void __launch_bounds__(MG_THREADS)
-bucket_count_kernel(const uint64_t* __restrict__ rec, const Item* __restrict__ items, uint32_t limit,
+bucket_count_kernel(const uint64_t* __restrict__ rec, const Item* __restrict__ items, const uint64_t* __restrict__ seg_voff,
+                    const uint64_t* __restrict__ seg_pstart, int n_runs, uint32_t limit,
                     uint32_t* __restrict__ n_rows, uint32_t* __restrict__ need_split) {
     __shared__ uint64_t s_tab[COUNT_CAP];
     __shared__ uint32_t s_n, s_over;
+    __shared__ SegMap s_map;
     const Item it = items[blockIdx.x];
     if (it.beg == it.end) { if (threadIdx.x == 0) n_rows[blockIdx.x] = 0; return; }
+    segmap_load(s_map, it, seg_voff, seg_pstart, n_runs);
     for (int i = threadIdx.x; i < COUNT_CAP; i += MG_THREADS) s_tab[i] = KEY_EMPTY;
     if (threadIdx.x == 0) { s_n = 0; s_over = 0; }
     __syncthreads();
@@ -86,7 +110,7 @@ bucket_count_kernel(const uint64_t* __restrict__ rec, const Item* __restrict__ i
 #pragma unroll
         for (int j = 0; j < MG_UNROLL; j++) {                      // all loads first: memory-level parallelism
             uint64_t i = base + (uint64_t)j * MG_THREADS;
-            rr[j] = i < it.end ? rec[i] : REC_SENTINEL;
+            rr[j] = i < it.end ? rec[seg_phys(s_map, i)] : REC_SENTINEL;
         }
         // probe the MG_UNROLL records together: independent shared loads overlap their latency; a key
         // already present (the common case: one record per sample per key) needs nothing else
@@ -192,6 +216,7 @@ __device__ __forceinline__ uint32_t pal_letter(uint32_t m) {
 // dynamic smem: tab u64[cap] | lkey u64[cap/2] | rank u16[cap] | lslot u16[cap/2] | cnt u32[cap/2]
 __global__ void __launch_bounds__(MG_THREADS)
 bucket_emit_kernel(const uint64_t* __restrict__ rec, const uint16_t* __restrict__ sid, const Item* __restrict__ items,
+                   const uint64_t* __restrict__ seg_voff, const uint64_t* __restrict__ seg_pstart, int n_runs,
                    const uint64_t* __restrict__ row_off, int log_cap, uint32_t n_samples, int k, int rc,
                    uint64_t* __restrict__ out_keys, uint8_t* __restrict__ out_var, uint32_t* __restrict__ out_cnt) {
     extern __shared__ __align__(16) uint8_t smem[];
@@ -202,6 +227,7 @@ bucket_emit_kernel(const uint64_t* __restrict__ rec, const uint16_t* __restrict_
     uint16_t* s_rank = reinterpret_cast<uint16_t*>(s_cnt + half);
     uint16_t* s_lslot = s_rank + cap;
     __shared__ uint32_t s_u;
+    __shared__ SegMap s_map;
 
     const uint32_t b = blockIdx.x;
     const Item it = items[b];
@@ -209,6 +235,7 @@ bucket_emit_kernel(const uint64_t* __restrict__ rec, const uint16_t* __restrict_
     const uint64_t row_base = row_off[b];
     const uint32_t u = (uint32_t)(row_off[b + 1] - row_base);     // distinct keys, from the count pass
     if (u == 0) return;
+    segmap_load(s_map, it, seg_voff, seg_pstart, n_runs);
 
     for (uint32_t i = threadIdx.x; i < cap; i += MG_THREADS) s_tab[i] = KEY_EMPTY;
     if (threadIdx.x == 0) s_u = 0;
@@ -220,7 +247,7 @@ bucket_emit_kernel(const uint64_t* __restrict__ rec, const uint16_t* __restrict_
 #pragma unroll
         for (int j = 0; j < MG_UNROLL; j++) {
             uint64_t i = base + (uint64_t)j * MG_THREADS;
-            rr[j] = i < end ? rec[i] : REC_SENTINEL;
+            rr[j] = i < end ? rec[seg_phys(s_map, i)] : REC_SENTINEL;
         }
         uint64_t kk[MG_UNROLL], cur[MG_UNROLL]; uint32_t sl[MG_UNROLL];
 #pragma unroll
@@ -307,8 +334,9 @@ bucket_emit_kernel(const uint64_t* __restrict__ rec, const uint16_t* __restrict_
         for (int j = 0; j < MG_UNROLL; j++) {
             uint64_t i = base + (uint64_t)j * MG_THREADS;
             bool in = i < end;
-            rr[j] = in ? rec[i] : REC_SENTINEL;
-            ss[j] = in ? sid[i] : 0;
+            uint64_t pi = in ? seg_phys(s_map, i) : 0;
+            rr[j] = in ? rec[pi] : REC_SENTINEL;
+            ss[j] = in ? sid[pi] : 0;
         }
         uint64_t kk[MG_UNROLL], cur[MG_UNROLL]; uint32_t sl[MG_UNROLL], rk[MG_UNROLL];
 #pragma unroll
@@ -419,58 +447,23 @@ static int choose_prefix_bits(uint64_t n_pos, int key_bits, uint64_t target) {
     return p;
 }
 
-void build_array_from_records(uint64_t* rec, uint16_t* sid, uint64_t n_pos, uint64_t n_samples, uint32_t k, bool rc,
-                              Array& out, int extra_prefix_bits) {
+// (2) of the file header: count distinct keys per item (splitting items that do not fit shared memory),
+// scan to row offsets, emit rows.  `items` is a device array in ascending key order.
+static void merge_items(const uint64_t* rec, const uint16_t* sid, Item* items, uint32_t n_items, const uint64_t* seg_voff,
+                        const uint64_t* seg_pstart, int n_runs, uint64_t n_samples, uint32_t k, bool rc, Array& out) {
     Context& c = ctx();
-    const int key_bits = 2 * ((int)k - 1);
     // bytes of shared memory per table slot in the emit kernel: tab 8 + rank 2 + (lkey 8 + lslot 2 + cnt 4)/2
     const size_t slot_bytes = 17;
     const int max_log_cap = 13;                                   // 8192 slots = 136 KB
     const uint32_t limit = COUNT_CAP - COUNT_CAP / 4 - 1;         // most distinct keys one item may hold (3071)
 
-    // records per bucket ~4096, but stay at 16 prefix bits (two 8-bit radix passes) while buckets
-    // remain small enough for the shared-memory tables
-    int P = choose_prefix_bits(n_pos, key_bits, 4096);
-    if (P > 16 && (n_pos >> 16) <= 16384) P = 16;
-    // a row shard holds only ~2^-extra of the key space: refine so that occupied buckets keep their size
-    P = std::min(std::min(P + extra_prefix_bits, 24), key_bits);
-    if (const char* e = getenv("SKA_PREFIX_BITS")) { int v = atoi(e); if (v >= 0 && v <= key_bits && v <= 24) P = v; }   // tuning/tests
-    const uint32_t n_buckets = 1u << P;
-    const int shift = 4 + key_bits - P;
-
-    // (1) partition by key prefix
-    timer().begin("partition");
-    uint64_t* rec_sorted = rec; uint16_t* sid_sorted = sid;
-    if (P > 0) {
-        uint64_t* rec_alt = arena().take_n<uint64_t>(n_pos);
-        uint16_t* sid_alt = arena().take_n<uint16_t>(n_pos);
-        cub::DoubleBuffer<uint64_t> dk(rec, rec_alt);
-        cub::DoubleBuffer<uint16_t> dv(sid, sid_alt);
-        size_t tmp_bytes = 0;
-        SKA_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, dk, dv, (int64_t)n_pos, shift, shift + P, c.stream));
-        void* tmp = arena().take(tmp_bytes);
-        SKA_CUDA(cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, dk, dv, (int64_t)n_pos, shift, shift + P, c.stream));
-        c.launches += (P + 7) / 8 + 1;   // onesweep: one histogram + one pass per 8 bits (library kernels)
-        rec_sorted = dk.Current(); sid_sorted = dv.Current();
-    }
-    timer().end();
-
-    timer().begin("bucket_offsets");
-    uint64_t* off = arena().take_n<uint64_t>(n_buckets + 1);
-    SKA_LAUNCH(bucket_offsets_kernel, (n_buckets + 1 + 255) / 256, 256, 0, rec_sorted, n_pos, shift, n_buckets, off);
-    uint32_t n_items = n_buckets;
-    Item* items = arena().take_n<Item>(n_items);
-    SKA_LAUNCH(make_items_kernel, (n_buckets + 255) / 256, 256, 0, off, n_buckets, key_bits, P, items);
-    timer().end();
-
-    // (2a) distinct keys per item -> row offsets; split items that do not fit shared memory
     timer().begin("count");
-    uint32_t* n_rows = arena().take_n<uint32_t>(n_items);
+    uint32_t* n_rows = arena().take_n<uint32_t>(std::max<uint32_t>(n_items, 1));
     uint32_t* flags = arena().take_n<uint32_t>(2);
-    uint32_t h_flags[2];
-    for (int round = 0;; round++) {
+    uint32_t h_flags[2] = {0, 0};
+    for (int round = 0; n_items > 0; round++) {
         SKA_CUDA(cudaMemsetAsync(flags, 0, 8, c.stream));
-        SKA_LAUNCH(bucket_count_kernel, n_items, MG_THREADS, 0, rec_sorted, items, limit, n_rows, flags);
+        SKA_LAUNCH(bucket_count_kernel, n_items, MG_THREADS, 0, rec, items, seg_voff, seg_pstart, n_runs, limit, n_rows, flags);
         SKA_CUDA(cudaMemcpyAsync(h_flags, flags, 8, cudaMemcpyDeviceToHost, c.stream));
         SKA_CUDA(cudaStreamSynchronize(c.stream));
         if (!h_flags[0]) break;
@@ -503,15 +496,16 @@ void build_array_from_records(uint64_t* rec, uint16_t* sid, uint64_t n_pos, uint
         SKA_CUDA(cudaStreamSynchronize(c.stream));
     }
     uint64_t* row_off = arena().take_n<uint64_t>(n_items + 1);
-    launch_scan_counts(n_rows, n_items, row_off, flags + 1);
     uint64_t total_rows = 0;
-    SKA_CUDA(cudaMemcpyAsync(h_flags, flags, 8, cudaMemcpyDeviceToHost, c.stream));
-    SKA_CUDA(cudaMemcpyAsync(&total_rows, row_off + n_items, 8, cudaMemcpyDeviceToHost, c.stream));
-    SKA_CUDA(cudaStreamSynchronize(c.stream));
+    if (n_items) {
+        launch_scan_counts(n_rows, n_items, row_off, flags + 1);
+        SKA_CUDA(cudaMemcpyAsync(h_flags, flags, 8, cudaMemcpyDeviceToHost, c.stream));
+        SKA_CUDA(cudaMemcpyAsync(&total_rows, row_off + n_items, 8, cudaMemcpyDeviceToHost, c.stream));
+        SKA_CUDA(cudaStreamSynchronize(c.stream));
+    }
     timer().end();
     const uint32_t max_u = h_flags[1];
 
-    // (2b) emit
     timer().begin("emit");
     out.k = k; out.rc = rc; out.key_bits = 64; out.n_samples = n_samples;
     out.n_rows = out.n_keys = total_rows;
@@ -522,10 +516,104 @@ void build_array_from_records(uint64_t* rec, uint16_t* sid, uint64_t n_pos, uint
         size_t smem = ((size_t)1 << log_cap) * slot_bytes;
         if (log_cap > max_log_cap) throw Error("internal: item larger than the shared-memory table");
         SKA_CUDA(cudaFuncSetAttribute(bucket_emit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        SKA_LAUNCH(bucket_emit_kernel, n_items, MG_THREADS, smem, rec_sorted, sid_sorted, items, row_off, log_cap,
+        SKA_LAUNCH(bucket_emit_kernel, n_items, MG_THREADS, smem, rec, sid, items, seg_voff, seg_pstart, n_runs, row_off, log_cap,
                    (uint32_t)n_samples, (int)k, rc ? 1 : 0, out.keys.p, out.variants.p, out.counts.p);
     }
     timer().end();
+}
+
+int merge_prefix_bits(uint64_t n_records_total, uint32_t k, int n_shards) {
+    const int key_bits = 2 * ((int)k - 1);
+    // records per bucket ~4096, but stay at 16 prefix bits (two 8-bit radix passes) while buckets
+    // remain small enough for the shared-memory tables
+    int P = choose_prefix_bits(n_records_total, key_bits, 4096);
+    if (P > 16 && (n_records_total >> 16) <= 16384) P = 16;
+    (void)n_shards;
+    if (const char* e = getenv("SKA_PREFIX_BITS")) { int v = atoi(e); if (v >= 0 && v <= key_bits && v <= 24) P = v; }   // tuning/tests
+    return std::min(std::min(P, 24), key_bits);
+}
+
+void build_array_from_records(uint64_t* rec, uint16_t* sid, uint64_t n_pos, uint64_t n_samples, uint32_t k, bool rc,
+                              Array& out) {
+    Context& c = ctx();
+    const int key_bits = 2 * ((int)k - 1);
+    const int P = merge_prefix_bits(n_pos, k, 1);
+    const uint32_t n_buckets = 1u << P;
+    const int shift = 4 + key_bits - P;
+
+    // (1) partition by key prefix
+    timer().begin("partition");
+    uint64_t* rec_sorted = rec; uint16_t* sid_sorted = sid;
+    if (P > 0) {
+        uint64_t* rec_alt = arena().take_n<uint64_t>(n_pos);
+        uint16_t* sid_alt = arena().take_n<uint16_t>(n_pos);
+        cub::DoubleBuffer<uint64_t> dk(rec, rec_alt);
+        cub::DoubleBuffer<uint16_t> dv(sid, sid_alt);
+        size_t tmp_bytes = 0;
+        SKA_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, dk, dv, (int64_t)n_pos, shift, shift + P, c.stream));
+        void* tmp = arena().take(tmp_bytes);
+        SKA_CUDA(cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, dk, dv, (int64_t)n_pos, shift, shift + P, c.stream));
+        c.launches += (P + 7) / 8 + 1;   // onesweep: one histogram + one pass per 8 bits (library kernels)
+        rec_sorted = dk.Current(); sid_sorted = dv.Current();
+    }
+    timer().end();
+
+    timer().begin("bucket_offsets");
+    uint64_t* off = arena().take_n<uint64_t>(n_buckets + 1);
+    SKA_LAUNCH(bucket_offsets_kernel, (n_buckets + 1 + 255) / 256, 256, 0, rec_sorted, n_pos, shift, n_buckets, off);
+    Item* items = arena().take_n<Item>(n_buckets);
+    SKA_LAUNCH(make_items_kernel, (n_buckets + 255) / 256, 256, 0, off, n_buckets, key_bits, P, items);
+    timer().end();
+
+    merge_items(rec_sorted, sid_sorted, items, n_buckets, nullptr, nullptr, 1, n_samples, k, rc, out);
+}
+
+// Row shard: the received records are `n_runs` runs (one per source rank), each sorted by the same
+// `prefix_bits`-bit key prefix and covering buckets [bucket_lo, bucket_hi).  run_off[r * (nb + 1) + j]
+// is the offset, inside the receive buffer, of bucket (bucket_lo + j) of run r (nb = bucket_hi - bucket_lo).
+void build_array_from_runs(const uint64_t* rec, const uint16_t* sid, int n_runs, const uint64_t* run_off, uint32_t bucket_lo,
+                           uint32_t bucket_hi, int prefix_bits, uint64_t n_samples, uint32_t k, bool rc, Array& out) {
+    Context& c = ctx();
+    if (n_runs < 1 || n_runs > MAX_RUNS) throw Error("row shard supports 1.." + std::to_string(MAX_RUNS) + " source ranks");
+    const int key_bits = 2 * ((int)k - 1);
+    const int low = key_bits - prefix_bits;
+    const uint32_t nb = bucket_hi - bucket_lo;
+    const int W = std::max(n_runs, 2);                    // the map is only consulted for W > 1: pad with an empty run
+    std::vector<Item> h_items(nb);
+    std::vector<uint64_t> h_voff((size_t)nb * (W + 1)), h_pstart((size_t)nb * (W + 1));
+    uint64_t v = 0;
+    for (uint32_t j = 0; j < nb; j++) {
+        Item& it = h_items[j];
+        const uint64_t b = (uint64_t)bucket_lo + j;
+        it.key_lo = b << low;
+        it.key_hi = it.key_lo | ((low >= 64) ? ~0ULL : ((1ULL << low) - 1ULL));
+        if (b == (1ull << prefix_bits) - 1) it.key_hi = ~0ULL >> 4;
+        it.seg0 = (uint64_t)j * (W + 1);
+        it.beg = v;
+        for (int r = 0; r < W; r++) {
+            h_voff[it.seg0 + r] = v;
+            if (r < n_runs) {
+                const uint64_t* ro = run_off + (size_t)r * (nb + 1);
+                h_pstart[it.seg0 + r] = ro[j];
+                v += ro[j + 1] - ro[j];
+            } else h_pstart[it.seg0 + r] = 0;
+        }
+        h_voff[it.seg0 + W] = v;
+        h_pstart[it.seg0 + W] = 0;
+        it.end = v;
+    }
+    timer().begin("bucket_offsets");
+    Item* items = arena().take_n<Item>(std::max<uint32_t>(nb, 1));
+    uint64_t* d_voff = arena().take_n<uint64_t>(std::max<size_t>(h_voff.size(), 1));
+    uint64_t* d_pstart = arena().take_n<uint64_t>(std::max<size_t>(h_pstart.size(), 1));
+    if (nb) {
+        SKA_CUDA(cudaMemcpyAsync(items, h_items.data(), nb * sizeof(Item), cudaMemcpyHostToDevice, c.stream));
+        SKA_CUDA(cudaMemcpyAsync(d_voff, h_voff.data(), h_voff.size() * 8, cudaMemcpyHostToDevice, c.stream));
+        SKA_CUDA(cudaMemcpyAsync(d_pstart, h_pstart.data(), h_pstart.size() * 8, cudaMemcpyHostToDevice, c.stream));
+        SKA_CUDA(cudaStreamSynchronize(c.stream));
+    }
+    timer().end();
+    merge_items(rec, sid, items, nb, d_voff, d_pstart, W, n_samples, k, rc, out);
 }
 
 }  // namespace ska

@@ -57,13 +57,21 @@ class GpuBackend:
             sid = torch.empty(0, dtype=torch.int16, device="cuda")
         return rec, sid, off
 
-    def merge(self, rec, sid, n_samples_total, k, rc, names, world=1):
+    def merge(self, rec, sid, run_offsets, bucket_lo, bucket_hi, prefix_bits, n_samples_total, k, rc, names):
         import ctypes as C
         h = C.c_void_p()
-        shift = max(0, math.ceil(math.log2(world)))
-        api._check(api.lib().skagpu_merge_records_dev(rec.data_ptr(), sid.data_ptr(), rec.numel(), n_samples_total, k,
-                                                      int(rc), shift, C.byref(h)))
+        ro = np.ascontiguousarray(run_offsets, dtype=np.uint64)
+        api._check(api.lib().skagpu_merge_records_dev(rec.data_ptr(), sid.data_ptr(), ro.shape[0], ro.ctypes.data, bucket_lo,
+                                                      bucket_hi, prefix_bits, n_samples_total, k, int(rc), C.byref(h)))
         return api.MergeSkaArray(h, names)
+
+    def n_positions(self, samples):
+        if isinstance(samples, api.SeqBatch):
+            samples = samples._keep
+        return int(sum(len(s.seq) for s in samples))
+
+    def prefix_bits(self, n_records_total, k):
+        return int(api.lib().skagpu_merge_prefix_bits(int(n_records_total), k))
 
 
 def plan_owners(global_bucket_counts, world):
@@ -81,14 +89,18 @@ def plan_owners(global_bucket_counts, world):
     return np.array(cuts, dtype=np.int64)
 
 
-def build_and_merge_sharded(backend, samples_local, names_all, sample_base, k, rc, prefix_bits=16, group=None,
+def build_and_merge_sharded(backend, samples_local, names_all, sample_base, k, rc, prefix_bits=None, group=None,
                             timings=None):
     """-> this rank's slab (a MergeSkaArray with len(names_all) columns).  Collective over `group`."""
     world = dist.get_world_size(group)
     rank = dist.get_rank(group)
     key_bits = 2 * (k - 1)
-    prefix_bits = min(prefix_bits, key_bits)
     dev = backend.device
+    if prefix_bits is None:                               # bucket granularity from the GLOBAL record count
+        tot = torch.tensor([backend.n_positions(samples_local)], dtype=torch.int64, device=dev)
+        dist.all_reduce(tot, group=group)
+        prefix_bits = backend.prefix_bits(int(tot.item()), k)
+    prefix_bits = min(prefix_bits, key_bits)
     rec, sid, off = backend.extract(samples_local, k, rc, sample_base, prefix_bits)
     counts = torch.from_numpy(np.diff(off).astype(np.int64)).to(dev)
     dist.all_reduce(counts, group=group)
@@ -107,10 +119,20 @@ def build_and_merge_sharded(backend, samples_local, names_all, sample_base, k, r
     # sample ids travel as raw bytes (gloo has no 16-bit integer all-to-all)
     dist.all_to_all_single(recv_sid.view(torch.uint8), sid[:int(bounds[-1])].view(torch.uint8),
                            [2 * int(c) for c in recv_counts], [2 * int(c) for c in send_counts], group=group)
+    # every run stays sorted by prefix: ship its bucket offsets (relative to the run) so the owner never re-sorts
+    nb_send = np.diff(cuts) + 1                           # offsets per owner: nb_g + 1
+    rel = np.concatenate([off[cuts[g]:cuts[g + 1] + 1].astype(np.int64) - bounds[g] for g in range(world)])
+    nb_mine = int(cuts[rank + 1] - cuts[rank])
+    recv_off = torch.empty(world * (nb_mine + 1), dtype=torch.int64, device=dev)
+    dist.all_to_all_single(recv_off, torch.from_numpy(rel).to(dev), [nb_mine + 1] * world, list(map(int, nb_send)), group=group)
+    run_base = np.concatenate([[0], np.cumsum(recv_counts)[:-1]]).astype(np.int64)
+    run_offsets = (recv_off.cpu().numpy().reshape(world, nb_mine + 1) + run_base[:, None]).astype(np.uint64)
     if timings is not None:
         timings["sent_records"] = int(send_counts.sum() - send_counts[rank])
         timings["recv_records"] = n_recv
-    return backend.merge(recv_rec, recv_sid, len(names_all), k, rc, names_all, world)
+        timings["prefix_bits"] = prefix_bits
+    return backend.merge(recv_rec, recv_sid, run_offsets, int(cuts[rank]), int(cuts[rank + 1]), prefix_bits, len(names_all),
+                         k, rc, names_all)
 
 
 def align_sharded(arr, filter_type="no-const", mask_ambig=False, ignore_const_gaps=False, min_freq=0.9,

@@ -94,9 +94,24 @@ class OracleBackend:
         off = np.searchsorted(prefix, np.arange((1 << prefix_bits) + 1)).astype(np.uint64)
         return torch.from_numpy(rec.view(np.int64)), torch.from_numpy(sid), off
 
-    def merge(self, rec, sid, n_samples_total, k, rc, names, world=1):
+    def n_positions(self, samples):
+        return sum(len(r) for recs in samples for r in recs)
+
+    def prefix_bits(self, n_records_total, k):
+        return min(6, 2 * (k - 1))
+
+    def merge(self, rec, sid, run_offsets, bucket_lo, bucket_hi, prefix_bits, n_samples_total, k, rc, names):
         rec = rec.numpy().view(np.uint64)
         sid = sid.numpy()
+        # the exchange plan must describe the receive buffer exactly: every run sorted by prefix, buckets in range
+        shift = 4 + 2 * (k - 1) - prefix_bits
+        nb = bucket_hi - bucket_lo
+        assert run_offsets.shape[1] == nb + 1
+        for r in range(run_offsets.shape[0]):
+            for j in range(nb):
+                seg = rec[int(run_offsets[r, j]):int(run_offsets[r, j + 1])]
+                assert np.all((seg >> np.uint64(shift)) == np.uint64(bucket_lo + j))
+        assert int(run_offsets[-1, -1]) == len(rec)
         keys = sorted(set(int(r) >> 4 for r in rec))
         row = {key: i for i, key in enumerate(keys)}
         mask = np.zeros((len(keys), n_samples_total), dtype=np.uint8)
@@ -148,7 +163,7 @@ def worker(rank, world, port, k, rc, ret):
         per = (n + world - 1) // world
         lo, hi = rank * per, min(n, (rank + 1) * per)
         backend = OracleBackend()
-        slab = D.build_and_merge_sharded(backend, pops[lo:hi], names, lo, k, rc, prefix_bits=6)
+        slab = D.build_and_merge_sharded(backend, pops[lo:hi], names, lo, k, rc)
         keys, var, cnt = slab.export()
         parts = [None] * world if rank == 0 else None
         dist.gather_object((keys, var, cnt), parts, dst=0)

@@ -43,11 +43,11 @@ def worker(rank, world, port, n, length, k, ret):
         lo, hi = rank * per, (rank + 1) * per if rank < world - 1 else n
         local = [S.Sample.from_records(seqs[i]) for i in range(lo, hi)]
         backend = D.GpuBackend()
-        slab = D.build_and_merge_sharded(backend, local, names, lo, k, True, prefix_bits=12)
+        slab = D.build_and_merge_sharded(backend, local, names, lo, k, True)
         keys, var, cnt = slab.export()
         parts = [None] * world if rank == 0 else None
         dist.gather_object((np.asarray(keys), var, cnt), parts, dst=0)
-        slab_d = D.build_and_merge_sharded(backend, local, names, lo, k, True, prefix_bits=12)
+        slab_d = D.build_and_merge_sharded(backend, local, names, lo, k, True, prefix_bits=10)
         dists = D.distance_sharded(slab_d, filt_ambig=True)
         aln = D.gather_alignment(D.align_sharded(slab), names)
         if rank == 0:
