@@ -179,10 +179,13 @@ def run_ours(args, rank, world, local_rank):
         names = [f"s{i}" for i in range(G * world)]          # every slab has all N = G*world columns
         threshold = int(np.ceil(G * world * 0.9))
 
+    shard_t = {}
+
     def build_device(batch):
         if world == 1:
             return S.api.build_from_batch(batch, names, k, True)
-        return D.build_and_merge_sharded(backend, batch, names, rank * G, k, True)
+        return D.build_and_merge_sharded(backend, batch, names, rank * G, k, True,
+                                         timings=shard_t if os.environ.get("BENCH_SHARD_TIMINGS") else None)
 
     # ---------------- device-resident arm
     batch = S.SeqBatch(samples)
@@ -210,6 +213,8 @@ def run_ours(args, rank, world, local_rank):
     value = args.steps * G * world / (ms_dev * 1e-3)
 
     log(f"device arm: {ms_dev / args.steps:.2f} ms/step, rows built {rows_built}, aligned {rows_aligned}")
+    if shard_t:
+        log("sharded build phases (ms, summed over all calls so far): " + str({k_: round(v, 1) if isinstance(v, float) else v for k_, v in shard_t.items()}))
     # ---------------- K1 alone (the kernel the roofline is quoted on), CUDA events inside the library
     _rec, k1_ms = batch.k1_extract(k, rc=True, iters=10, want_records=False)
     del batch

@@ -92,16 +92,29 @@ def plan_owners(global_bucket_counts, world):
 def build_and_merge_sharded(backend, samples_local, names_all, sample_base, k, rc, prefix_bits=None, group=None,
                             timings=None):
     """-> this rank's slab (a MergeSkaArray with len(names_all) columns).  Collective over `group`."""
+    import time
     world = dist.get_world_size(group)
     rank = dist.get_rank(group)
     key_bits = 2 * (k - 1)
     dev = backend.device
+    t_last = [time.perf_counter()]
+
+    def lap(name):
+        if timings is not None:
+            if dev == "cuda":
+                torch.cuda.synchronize()
+            now = time.perf_counter()
+            timings[name] = timings.get(name, 0.0) + (now - t_last[0]) * 1e3
+            t_last[0] = now
+
     if prefix_bits is None:                               # bucket granularity from the GLOBAL record count
         tot = torch.tensor([backend.n_positions(samples_local)], dtype=torch.int64, device=dev)
         dist.all_reduce(tot, group=group)
         prefix_bits = backend.prefix_bits(int(tot.item()), k)
     prefix_bits = min(prefix_bits, key_bits)
+    lap("plan_ms")
     rec, sid, off = backend.extract(samples_local, k, rc, sample_base, prefix_bits)
+    lap("extract_ms")
     counts = torch.from_numpy(np.diff(off).astype(np.int64)).to(dev)
     dist.all_reduce(counts, group=group)
     cuts = plan_owners(counts.cpu().numpy(), world)
@@ -114,11 +127,13 @@ def build_and_merge_sharded(backend, samples_local, names_all, sample_base, k, r
     n_recv = int(recv_counts.sum())
     recv_rec = torch.empty(n_recv, dtype=torch.int64, device=dev)
     recv_sid = torch.empty(n_recv, dtype=torch.int16, device=dev)
+    lap("owners_ms")
     # records are sorted by prefix, so each owner's share is one contiguous range starting at bounds[0] == 0
     dist.all_to_all_single(recv_rec, rec[:int(bounds[-1])], list(map(int, recv_counts)), list(map(int, send_counts)), group=group)
     # sample ids travel as raw bytes (gloo has no 16-bit integer all-to-all)
     dist.all_to_all_single(recv_sid.view(torch.uint8), sid[:int(bounds[-1])].view(torch.uint8),
                            [2 * int(c) for c in recv_counts], [2 * int(c) for c in send_counts], group=group)
+    lap("all_to_all_ms")
     # every run stays sorted by prefix: ship its bucket offsets (relative to the run) so the owner never re-sorts
     nb_send = np.diff(cuts) + 1                           # offsets per owner: nb_g + 1
     rel = np.concatenate([off[cuts[g]:cuts[g + 1] + 1].astype(np.int64) - bounds[g] for g in range(world)])
@@ -127,12 +142,15 @@ def build_and_merge_sharded(backend, samples_local, names_all, sample_base, k, r
     dist.all_to_all_single(recv_off, torch.from_numpy(rel).to(dev), [nb_mine + 1] * world, list(map(int, nb_send)), group=group)
     run_base = np.concatenate([[0], np.cumsum(recv_counts)[:-1]]).astype(np.int64)
     run_offsets = (recv_off.cpu().numpy().reshape(world, nb_mine + 1) + run_base[:, None]).astype(np.uint64)
+    lap("offsets_ms")
+    arr = backend.merge(recv_rec, recv_sid, run_offsets, int(cuts[rank]), int(cuts[rank + 1]), prefix_bits, len(names_all),
+                        k, rc, names_all)
+    lap("merge_ms")
     if timings is not None:
         timings["sent_records"] = int(send_counts.sum() - send_counts[rank])
         timings["recv_records"] = n_recv
         timings["prefix_bits"] = prefix_bits
-    return backend.merge(recv_rec, recv_sid, run_offsets, int(cuts[rank]), int(cuts[rank + 1]), prefix_bits, len(names_all),
-                         k, rc, names_all)
+    return arr
 
 
 def align_sharded(arr, filter_type="no-const", mask_ambig=False, ignore_const_gaps=False, min_freq=0.9,
