@@ -214,7 +214,7 @@ def run_ours(args, rank, world, local_rank):
 
     log(f"device arm: {ms_dev / args.steps:.2f} ms/step, rows built {rows_built}, aligned {rows_aligned}")
     if shard_t:
-        log("sharded build phases (ms, summed over all calls so far): " + str({k_: round(v, 1) if isinstance(v, float) else v for k_, v in shard_t.items()}))
+        log("sharded build phases of the last call (ms): " + str({k_: round(v, 1) if isinstance(v, float) else v for k_, v in shard_t.items()}))
     # ---------------- K1 alone (the kernel the roofline is quoted on), CUDA events inside the library
     _rec, k1_ms = batch.k1_extract(k, rc=True, iters=10, want_records=False)
     del batch

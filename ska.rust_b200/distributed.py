@@ -104,7 +104,7 @@ def build_and_merge_sharded(backend, samples_local, names_all, sample_base, k, r
             if dev == "cuda":
                 torch.cuda.synchronize()
             now = time.perf_counter()
-            timings[name] = timings.get(name, 0.0) + (now - t_last[0]) * 1e3
+            timings[name] = (now - t_last[0]) * 1e3
             t_last[0] = now
 
     if prefix_bits is None:                               # bucket granularity from the GLOBAL record count
