@@ -77,12 +77,12 @@ def lib():
         L.skagpu_last_timings.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
         L.skagpu_launch_count.restype = C.c_uint64
         L.skagpu_stream_timer.argtypes = [C.c_int, C.c_void_p]
-        L.skagpu_extract_records.argtypes = [C.c_void_p, C.c_uint32, C.c_int, C.c_uint32, C.c_int, C.c_void_p]
+        L.skagpu_extract_records.argtypes = [C.c_void_p, C.c_uint32, C.c_int, C.c_uint32, C.c_uint64, C.c_int, C.c_void_p]
         L.skagpu_records_info.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.skagpu_records_free.argtypes = [C.c_void_p]
-        L.skagpu_merge_records_dev.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_uint32, C.c_uint32, C.c_int,
+        L.skagpu_merge_records_dev.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_uint32, C.c_uint32, C.c_int,
                                                C.c_uint64, C.c_uint32, C.c_int, C.c_void_p]
-        L.skagpu_merge_prefix_bits.argtypes = [C.c_uint64, C.c_uint32]
+        L.skagpu_merge_prefix_bits.argtypes = [C.c_uint64, C.c_uint32, C.c_uint64]
         L.skagpu_distance_counters.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
         L.skagpu_k1_extract.argtypes = [C.c_void_p, C.c_uint32, C.c_int, C.c_uint8, C.c_int, C.c_int, C.c_void_p,
                                         C.c_void_p, C.c_void_p]

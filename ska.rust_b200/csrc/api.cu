@@ -171,16 +171,15 @@ static std::unique_ptr<Array> build_from_batch(const SeqBatch& b, uint32_t k, bo
     (void)min_count; (void)qual_filter;
     arena().reset();
     uint64_t* rec = arena().take_n<uint64_t>(b.n_pos);
-    uint16_t* sid = arena().take_n<uint16_t>(b.n_pos);
     uint32_t* valid = arena().take_n<uint32_t>(b.n_samples);
     SKA_CUDA(cudaMemsetAsync(valid, 0, b.n_samples * 4, c.stream));
     timer().begin("k1_extract");
-    launch_k1(b, k, rc, false, min_qual, rec, sid, valid);
+    launch_k1(b, k, rc, false, min_qual, rec, nullptr, valid);
     timer().end();
     std::vector<uint32_t> h_valid(b.n_samples);
     SKA_CUDA(cudaMemcpyAsync(h_valid.data(), valid, b.n_samples * 4, cudaMemcpyDeviceToHost, c.stream));
     std::unique_ptr<Array> a(new Array());
-    build_array_from_records(rec, sid, b.n_pos, b.n_samples, k, rc, *a);   // synchronises the stream
+    build_array_from_records(rec, b, 0, b.n_samples, k, rc, *a);   // synchronises the stream
     for (size_t s = 0; s < b.n_samples; s++)
         if (h_valid[s] == 0) throw Error("sample " + std::to_string(s) + " has no valid sequence");   // ska_dict.rs:374-376
     return a;
@@ -199,10 +198,10 @@ static thread_local std::string g_err;
 
 struct ska_array { Array a; };
 struct ska_seqbatch { std::unique_ptr<SeqBatch> b; };
-struct ska_records {            // K1 output of one rank, sorted by key prefix; lives in the arena until the next build
-    uint64_t* rec = nullptr; uint16_t* sid = nullptr; uint64_t n = 0;
-    uint32_t k = 0; bool rc = false; int prefix_bits = 0;
-    std::vector<uint64_t> off;  // 2^prefix_bits + 1 bucket offsets
+struct ska_records {            // packed records of one rank, grouped by key prefix; arena memory, valid until the next build
+    uint64_t* rec = nullptr; uint64_t n = 0;
+    uint32_t k = 0; bool rc = false; PartPlan plan;
+    std::vector<uint64_t> off;  // 2^P + 1 bucket offsets
 };
 
 extern "C" {
@@ -361,8 +360,8 @@ int skagpu_export_transposed(const ska_array_t* h, uint8_t* out) {
 void skagpu_free(ska_array_t* h) { delete h; }
 
 // ---- row-sharded (multi-GPU) build: extract + local partition | exchange (caller) | merge ----------
-int skagpu_extract_records(const ska_seqbatch_t* batch, uint32_t k, int rc, uint32_t sample_id_base, int prefix_bits,
-                           ska_records_t** out) {
+int skagpu_extract_records(const ska_seqbatch_t* batch, uint32_t k, int rc, uint32_t sample_id_base, uint64_t n_samples_total,
+                           int prefix_bits, ska_records_t** out) {
     API_TRY
     *out = nullptr;
     Context& c = ctx();
@@ -371,25 +370,28 @@ int skagpu_extract_records(const ska_seqbatch_t* batch, uint32_t k, int rc, uint
     if (k > 31) throw Error("k > 31 (128-bit split k-mers) is not yet built on the device; use k <= 31");
     const SeqBatch& b = *batch->b;
     if (b.has_qual) throw Error("FASTQ input (count/bloom filter, K2q) is not yet built on the device");
-    if (sample_id_base + b.n_samples > 65536) throw Error("at most 65536 samples in total (16-bit sample ids)");
-    if (prefix_bits < 0 || prefix_bits > 24 || prefix_bits > 2 * ((int)k - 1)) throw Error("bad prefix_bits");
+    if (sample_id_base + b.n_samples > n_samples_total) throw Error("sample ids exceed n_samples_total");
     timer().clear();
     arena().reset();
     std::unique_ptr<ska_records> r(new ska_records());
-    r->k = k; r->rc = rc != 0; r->prefix_bits = prefix_bits; r->n = b.n_pos;
+    r->k = k; r->rc = rc != 0;
+    r->plan = make_part_plan(k, prefix_bits, n_samples_total);
     uint64_t* rec = arena().take_n<uint64_t>(b.n_pos);
-    uint16_t* sid = arena().take_n<uint16_t>(b.n_pos);
     uint32_t* valid = arena().take_n<uint32_t>(b.n_samples);
     SKA_CUDA(cudaMemsetAsync(valid, 0, b.n_samples * 4, c.stream));
     timer().begin("k1_extract");
-    launch_k1(b, k, rc != 0, false, 0, rec, sid, valid, sample_id_base);
+    launch_k1(b, k, rc != 0, false, 0, rec, nullptr, valid);
     timer().end();
     std::vector<uint32_t> h_valid(b.n_samples);
     SKA_CUDA(cudaMemcpyAsync(h_valid.data(), valid, b.n_samples * 4, cudaMemcpyDeviceToHost, c.stream));
-    r->off.resize(((size_t)1 << prefix_bits) + 1);
-    timer().begin("partition_by_owner");
-    sort_records_by_prefix(rec, sid, b.n_pos, k, prefix_bits, &r->rec, &r->sid, r->off.data());   // synchronises
+    timer().begin("partition");
+    uint64_t* d_off = nullptr;
+    partition_records(rec, b.n_pos, b.sample_off.p, (uint32_t)b.n_samples, sample_id_base, r->plan, rec, &r->rec, &d_off);
+    r->off.resize(((size_t)1 << r->plan.P) + 1);
+    SKA_CUDA(cudaMemcpyAsync(r->off.data(), d_off, r->off.size() * 8, cudaMemcpyDeviceToHost, c.stream));
+    SKA_CUDA(cudaStreamSynchronize(c.stream));
     timer().end();
+    r->n = r->off.back();
     for (size_t s = 0; s < b.n_samples; s++)
         if (h_valid[s] == 0) throw Error("sample " + std::to_string(sample_id_base + s) + " has no valid sequence");
     *out = r.release();
@@ -397,13 +399,13 @@ int skagpu_extract_records(const ska_seqbatch_t* batch, uint32_t k, int rc, uint
     API_CATCH
 }
 
-int skagpu_records_info(const ska_records_t* r, uint64_t* n, const void** rec_dev, const void** sid_dev,
+int skagpu_records_info(const ska_records_t* r, uint64_t* n, const void** rec_dev, int* prefix_bits,
                         uint64_t* bucket_offsets /* 2^prefix_bits + 1, may be NULL */) {
     API_TRY
     if (!r) throw Error("null records");
     if (n) *n = r->n;
     if (rec_dev) *rec_dev = r->rec;
-    if (sid_dev) *sid_dev = r->sid;
+    if (prefix_bits) *prefix_bits = r->plan.P;
     if (bucket_offsets) memcpy(bucket_offsets, r->off.data(), r->off.size() * 8);
     return 0;
     API_CATCH
@@ -411,28 +413,31 @@ int skagpu_records_info(const ska_records_t* r, uint64_t* n, const void** rec_de
 
 void skagpu_records_free(ska_records_t* r) { delete r; }
 
-int skagpu_merge_records_dev(const void* rec_dev, const void* sid_dev, int n_runs, const uint64_t* run_offsets,
-                             uint32_t bucket_lo, uint32_t bucket_hi, int prefix_bits, uint64_t n_samples_total, uint32_t k,
-                             int rc, ska_array_t** out) {
+int skagpu_merge_records_dev(const void* rec_dev, int n_runs, const uint64_t* run_offsets, uint32_t bucket_lo, uint32_t bucket_hi,
+                             int prefix_bits, uint64_t n_samples_total, uint32_t k, int rc, ska_array_t** out) {
     API_TRY
     *out = nullptr;
     Context& c = ctx();
     c.ensure();
     check_k(k);
     if (k > 31) throw Error("k > 31 not yet supported on the device");
-    if (bucket_hi < bucket_lo || bucket_hi > (1ull << prefix_bits)) throw Error("bad bucket range");
+    const PartPlan pl = make_part_plan(k, prefix_bits, n_samples_total);
+    if (pl.P != prefix_bits) throw Error("prefix_bits does not match the record plan (use skagpu_merge_prefix_bits)");
+    if (bucket_hi < bucket_lo || bucket_hi > (1ull << pl.P)) throw Error("bad bucket range");
     // the caller's buffers may have been filled on another stream (NCCL): order after everything
     SKA_CUDA(cudaDeviceSynchronize());
     arena().reset();
     std::unique_ptr<ska_array> h(new ska_array());
-    build_array_from_runs((const uint64_t*)rec_dev, (const uint16_t*)sid_dev, n_runs, run_offsets, bucket_lo, bucket_hi, prefix_bits,
-                          n_samples_total, k, rc != 0, h->a);
+    build_array_from_runs((const uint64_t*)rec_dev, n_runs, run_offsets, bucket_lo, bucket_hi, pl, n_samples_total, k, rc != 0, h->a);
     *out = h.release();
     return 0;
     API_CATCH
 }
 
-int skagpu_merge_prefix_bits(uint64_t n_records_total, uint32_t k) { return merge_prefix_bits(n_records_total, k, 1); }
+int skagpu_merge_prefix_bits(uint64_t n_records_total, uint32_t k, uint64_t n_samples_total) {
+    try { return make_part_plan(k, merge_prefix_bits(n_records_total, k), n_samples_total).P; }
+    catch (std::exception& e) { g_err = e.what(); return -1; }
+}
 
 int skagpu_distance_counters(const ska_array_t* h, int filt_ambig, uint64_t* counters) {
     API_TRY

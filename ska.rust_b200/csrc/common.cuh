@@ -131,18 +131,22 @@ struct Array {
 void launch_k1(const SeqBatch& b, uint32_t k, bool rc, bool strict_qual, uint8_t min_qual, uint64_t* rec_out,
                uint16_t* sid_out, uint32_t* sample_valid, uint32_t sid_base = 0);
 size_t padded_positions(uint64_t n_pos);
+// partition.cu: how records are grouped and packed.  P = P1 + P2 prefix bits of the key select the bucket;
+// inside a bucket a record is  key_low << (sb+2) | sample_id << 2 | middle_code  (key_low = key without its top P1 bits)
+struct PartPlan { int key_bits, sb, P, P1, P2, low_bits; };
+PartPlan make_part_plan(uint32_t k, int prefix_bits, uint64_t n_samples_total);
+void partition_records(const uint64_t* rec, uint64_t n_pos, const uint64_t* d_sample_off, uint32_t n_samples_local, uint32_t sid_base,
+                       const PartPlan& pl, uint64_t* scratch, uint64_t** out, uint64_t** d_off);
 // merge.cu
-void build_array_from_records(uint64_t* rec, uint16_t* sid, uint64_t n_pos, uint64_t n_samples, uint32_t k, bool rc,
+// K1 records (linear, one per position of `b`) -> array; sample ids are sid_base + local index
+void build_array_from_records(uint64_t* rec, const SeqBatch& b, uint32_t sid_base, uint64_t n_samples_total, uint32_t k, bool rc,
                               Array& out);
-// row shard: `n_runs` received runs, each sorted by the same prefix_bits-bit key prefix over buckets [lo, hi)
-void build_array_from_runs(const uint64_t* rec, const uint16_t* sid, int n_runs, const uint64_t* run_off, uint32_t bucket_lo,
-                           uint32_t bucket_hi, int prefix_bits, uint64_t n_samples, uint32_t k, bool rc, Array& out);
+// row shard: `n_runs` received runs of packed records, each grouped by the same plan over buckets [lo, hi)
+void build_array_from_runs(const uint64_t* prec, int n_runs, const uint64_t* run_off, uint32_t bucket_lo, uint32_t bucket_hi,
+                           const PartPlan& pl, uint64_t n_samples, uint32_t k, bool rc, Array& out);
 // prefix bits the merge wants for `n_records_total` records in the whole key space
-int merge_prefix_bits(uint64_t n_records_total, uint32_t k, int n_shards);
-// sorts (rec, sid) by the top `prefix_bits` of the key (in place or into arena buffers) and writes the
-// 2^prefix_bits + 1 bucket offsets to h_off; returns where the sorted arrays live
-void sort_records_by_prefix(uint64_t* rec, uint16_t* sid, uint64_t n, uint32_t k, int prefix_bits, uint64_t** rec_sorted,
-                            uint16_t** sid_sorted, uint64_t* h_off);
+int merge_prefix_bits(uint64_t n_records_total, uint32_t k);
+
 // exclusive scan of n u32 counts into n+1 u64 offsets (off[n] = total); *max_out = max count
 void launch_scan_counts(const uint32_t* cnt, uint32_t n, uint64_t* off, uint32_t* max_out);
 // filter.cu

@@ -17,10 +17,7 @@
 // ascending key order -- the canonical row order -- with no global sort of rows.
 // A first pass (count) sizes the output exactly and gives each bucket its row offset.
 //
-// Step (1) currently uses cub::DeviceRadixSort restricted to the P prefix bits (library code,
-// round-1 scaffolding; DESIGN.md "partition" lists its replacement).  Steps (2) are hand-written.
-#include <cub/cub.cuh>
-
+// Step (1) is partition.cu (two MSD passes, packed 8-byte records that carry the sample id).
 #include <cstdlib>
 
 #include "common.cuh"
@@ -36,28 +33,13 @@ __device__ __forceinline__ uint32_t hash_slot(uint64_t key, int log_cap) {
     return (uint32_t)((key * 0x9E3779B97F4A7C15ULL) >> (64 - log_cap));
 }
 
-// bucket boundaries in the prefix-sorted record array: off[b] = first i with bucket(rec[i]) >= b
-__global__ void bucket_offsets_kernel(const uint64_t* __restrict__ rec, uint64_t n, int shift, uint32_t n_buckets,
-                                      uint64_t* __restrict__ off) {
-    uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
-    if (b > n_buckets) return;
-    if (b == n_buckets) { off[b] = n; return; }
-    uint64_t lo = 0, hi = n;                         // first index whose bucket >= b
-    const uint64_t mask = (uint64_t)n_buckets - 1;
-    while (lo < hi) {
-        uint64_t m = (lo + hi) >> 1;
-        if (((rec[m] >> shift) & mask) < b) lo = m + 1; else hi = m;
-    }
-    off[b] = lo;
-}
-
 // A work item = a contiguous record range (one prefix bucket) restricted to an inclusive key range.
 // Level-0 items cover their whole bucket; a bucket with too many distinct keys for shared memory is
 // split by further key bits into several items that each re-scan the bucket (rare path).
 // beg/end are VIRTUAL record indices.  On one GPU they are physical too.  On a row shard the bucket's
 // records arrive as one sorted run per source rank; the runs of a bucket are laid end to end in the
 // virtual index space and (seg_voff, seg_pstart)[seg0 .. seg0 + n_runs] translate to physical.
-struct Item { uint64_t beg, end, key_lo, key_hi; uint64_t seg0; };
+struct Item { uint64_t beg, end, key_lo, key_hi; uint64_t seg0; uint64_t key_base; };   // key = key_base | (prec >> (sb+2))
 constexpr int MAX_RUNS = 8;
 struct SegMap { int w; uint64_t v[MAX_RUNS + 1]; uint64_t p[MAX_RUNS]; };
 __device__ __forceinline__ void segmap_load(SegMap& m, const Item& it, const uint64_t* __restrict__ seg_voff,
@@ -77,7 +59,7 @@ __device__ __forceinline__ uint64_t seg_phys(const SegMap& m, uint64_t vi) {
 }
 constexpr uint32_t COUNT_OVERFLOW = 0xFFFFFFFFu;
 
-__global__ void make_items_kernel(const uint64_t* __restrict__ off, uint32_t n_buckets, int key_bits, int P,
+__global__ void make_items_kernel(const uint64_t* __restrict__ off, uint32_t n_buckets, int key_bits, int P, int P2, int low_bits,
                                   Item* __restrict__ items) {
     uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= n_buckets) return;
@@ -88,13 +70,14 @@ __global__ void make_items_kernel(const uint64_t* __restrict__ off, uint32_t n_b
     it.key_hi = it.key_lo | ((low >= 64) ? ~0ULL : ((1ULL << low) - 1ULL));
     if (b == n_buckets - 1) it.key_hi = ~0ULL >> 4;       // top bucket also holds nothing above the key space
     it.seg0 = 0;
+    it.key_base = (uint64_t)(b >> P2) << low_bits;
     items[b] = it;
 }
 
 // ---- pass 1: distinct keys per item
 __global__ void __launch_bounds__(MG_THREADS)
 bucket_count_kernel(const uint64_t* __restrict__ rec, const Item* __restrict__ items, const uint64_t* __restrict__ seg_voff,
-                    const uint64_t* __restrict__ seg_pstart, int n_runs, uint32_t limit,
+                    const uint64_t* __restrict__ seg_pstart, int n_runs, int sb, uint32_t limit,
                     uint32_t* __restrict__ n_rows, uint32_t* __restrict__ need_split) {
     __shared__ uint64_t s_tab[COUNT_CAP];
     __shared__ uint32_t s_n, s_over;
@@ -110,16 +93,16 @@ bucket_count_kernel(const uint64_t* __restrict__ rec, const Item* __restrict__ i
 #pragma unroll
         for (int j = 0; j < MG_UNROLL; j++) {                      // all loads first: memory-level parallelism
             uint64_t i = base + (uint64_t)j * MG_THREADS;
-            rr[j] = i < it.end ? rec[seg_phys(s_map, i)] : REC_SENTINEL;
+            rr[j] = i < it.end ? rec[seg_phys(s_map, i)] : 0;
         }
         // probe the MG_UNROLL records together: independent shared loads overlap their latency; a key
         // already present (the common case: one record per sample per key) needs nothing else
         uint64_t kk[MG_UNROLL], cur[MG_UNROLL]; uint32_t sl[MG_UNROLL];
 #pragma unroll
         for (int j = 0; j < MG_UNROLL; j++) {
-            kk[j] = rr[j] >> 4;
+            kk[j] = it.key_base | (rr[j] >> (sb + 2));
             sl[j] = hash_slot(kk[j], 12);
-            if (rr[j] == REC_SENTINEL || kk[j] < it.key_lo || kk[j] > it.key_hi) kk[j] = KEY_EMPTY;   // skip marker
+            if (base + (uint64_t)j * MG_THREADS >= it.end || kk[j] < it.key_lo || kk[j] > it.key_hi) kk[j] = KEY_EMPTY;   // skip marker
         }
 #pragma unroll
         for (int j = 0; j < MG_UNROLL; j++) cur[j] = *(volatile unsigned long long*)&s_tab[sl[j]];
@@ -215,8 +198,8 @@ __device__ __forceinline__ uint32_t pal_letter(uint32_t m) {
 //      palindromic keys, ska_dict.rs:85-113) and count the non-missing cells per row.
 // dynamic smem: tab u64[cap] | lkey u64[cap/2] | rank u16[cap] | lslot u16[cap/2] | cnt u32[cap/2]
 __global__ void __launch_bounds__(MG_THREADS)
-bucket_emit_kernel(const uint64_t* __restrict__ rec, const uint16_t* __restrict__ sid, const Item* __restrict__ items,
-                   const uint64_t* __restrict__ seg_voff, const uint64_t* __restrict__ seg_pstart, int n_runs,
+bucket_emit_kernel(const uint64_t* __restrict__ rec, const Item* __restrict__ items,
+                   const uint64_t* __restrict__ seg_voff, const uint64_t* __restrict__ seg_pstart, int n_runs, int sb,
                    const uint64_t* __restrict__ row_off, int log_cap, uint32_t n_samples, int k, int rc,
                    uint64_t* __restrict__ out_keys, uint8_t* __restrict__ out_var, uint32_t* __restrict__ out_cnt) {
     extern __shared__ __align__(16) uint8_t smem[];
@@ -247,14 +230,14 @@ bucket_emit_kernel(const uint64_t* __restrict__ rec, const uint16_t* __restrict_
 #pragma unroll
         for (int j = 0; j < MG_UNROLL; j++) {
             uint64_t i = base + (uint64_t)j * MG_THREADS;
-            rr[j] = i < end ? rec[seg_phys(s_map, i)] : REC_SENTINEL;
+            rr[j] = i < end ? rec[seg_phys(s_map, i)] : 0;
         }
         uint64_t kk[MG_UNROLL], cur[MG_UNROLL]; uint32_t sl[MG_UNROLL];
 #pragma unroll
         for (int j = 0; j < MG_UNROLL; j++) {
-            kk[j] = rr[j] >> 4;
+            kk[j] = it.key_base | (rr[j] >> (sb + 2));
             sl[j] = hash_slot(kk[j], log_cap);
-            if (rr[j] == REC_SENTINEL || kk[j] < it.key_lo || kk[j] > it.key_hi) kk[j] = KEY_EMPTY;
+            if (base + (uint64_t)j * MG_THREADS >= end || kk[j] < it.key_lo || kk[j] > it.key_hi) kk[j] = KEY_EMPTY;
         }
 #pragma unroll
         for (int j = 0; j < MG_UNROLL; j++) cur[j] = *(volatile unsigned long long*)&s_tab[sl[j]];
@@ -328,22 +311,20 @@ bucket_emit_kernel(const uint64_t* __restrict__ rec, const uint16_t* __restrict_
     __syncthreads();
 
     // phase 4
+    const uint32_t sid_mask = (1u << sb) - 1u;
     for (uint64_t base = beg + threadIdx.x; base < end; base += MG_UNROLL * MG_THREADS) {
-        uint64_t rr[MG_UNROLL]; uint32_t ss[MG_UNROLL];
+        uint64_t rr[MG_UNROLL];
 #pragma unroll
         for (int j = 0; j < MG_UNROLL; j++) {
             uint64_t i = base + (uint64_t)j * MG_THREADS;
-            bool in = i < end;
-            uint64_t pi = in ? seg_phys(s_map, i) : 0;
-            rr[j] = in ? rec[pi] : REC_SENTINEL;
-            ss[j] = in ? sid[pi] : 0;
+            rr[j] = i < end ? rec[seg_phys(s_map, i)] : 0;
         }
         uint64_t kk[MG_UNROLL], cur[MG_UNROLL]; uint32_t sl[MG_UNROLL], rk[MG_UNROLL];
 #pragma unroll
         for (int j = 0; j < MG_UNROLL; j++) {
-            kk[j] = rr[j] >> 4;
+            kk[j] = it.key_base | (rr[j] >> (sb + 2));
             sl[j] = hash_slot(kk[j], log_cap);
-            if (rr[j] == REC_SENTINEL || kk[j] < it.key_lo || kk[j] > it.key_hi) kk[j] = KEY_EMPTY;
+            if (base + (uint64_t)j * MG_THREADS >= end || kk[j] < it.key_lo || kk[j] > it.key_hi) kk[j] = KEY_EMPTY;
         }
 #pragma unroll
         for (int j = 0; j < MG_UNROLL; j++) cur[j] = s_tab[sl[j]];
@@ -355,8 +336,9 @@ bucket_emit_kernel(const uint64_t* __restrict__ rec, const uint16_t* __restrict_
 #pragma unroll
         for (int j = 0; j < MG_UNROLL; j++) {
             if (kk[j] == KEY_EMPTY) continue;
-            uint64_t o = (row_base + rk[j]) * n_samples + ss[j];
-            atomicOr(&out32[o >> 2], (uint32_t)(rr[j] & 0xF) << (8 * (o & 3)));
+            const uint32_t smp = (uint32_t)(rr[j] >> 2) & sid_mask;
+            uint64_t o = (row_base + rk[j]) * n_samples + smp;
+            atomicOr(&out32[o >> 2], (1u << (uint32_t)(rr[j] & 3)) << (8 * (o & 3)));
         }
     }
     __threadfence();
@@ -415,32 +397,6 @@ bucket_emit_kernel(const uint64_t* __restrict__ rec, const uint16_t* __restrict_
     for (uint32_t i = threadIdx.x; i < u; i += MG_THREADS) out_cnt[row_base + i] = s_cnt[i];
 }
 
-void sort_records_by_prefix(uint64_t* rec, uint16_t* sid, uint64_t n, uint32_t k, int prefix_bits, uint64_t** rec_sorted,
-                            uint16_t** sid_sorted, uint64_t* h_off) {
-    Context& c = ctx();
-    const int key_bits = 2 * ((int)k - 1);
-    if (prefix_bits > key_bits) throw Error("prefix_bits exceeds the key width");
-    const int shift = 4 + key_bits - prefix_bits;
-    const uint32_t n_buckets = 1u << prefix_bits;
-    *rec_sorted = rec; *sid_sorted = sid;
-    if (prefix_bits > 0 && n > 0) {
-        uint64_t* rec_alt = arena().take_n<uint64_t>(n);
-        uint16_t* sid_alt = arena().take_n<uint16_t>(n);
-        cub::DoubleBuffer<uint64_t> dk(rec, rec_alt);
-        cub::DoubleBuffer<uint16_t> dv(sid, sid_alt);
-        size_t tmp_bytes = 0;
-        SKA_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, dk, dv, (int64_t)n, shift, shift + prefix_bits, c.stream));
-        void* tmp = arena().take(tmp_bytes);
-        SKA_CUDA(cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, dk, dv, (int64_t)n, shift, shift + prefix_bits, c.stream));
-        c.launches += (prefix_bits + 7) / 8 + 1;
-        *rec_sorted = dk.Current(); *sid_sorted = dv.Current();
-    }
-    uint64_t* off = arena().take_n<uint64_t>(n_buckets + 1);
-    SKA_LAUNCH(bucket_offsets_kernel, (n_buckets + 1 + 255) / 256, 256, 0, *rec_sorted, n, shift, n_buckets, off);
-    SKA_CUDA(cudaMemcpyAsync(h_off, off, (n_buckets + 1) * 8, cudaMemcpyDeviceToHost, c.stream));
-    SKA_CUDA(cudaStreamSynchronize(c.stream));
-}
-
 static int choose_prefix_bits(uint64_t n_pos, int key_bits, uint64_t target) {
     int p = 0;
     while ((n_pos >> p) > target && p < key_bits && p < 24) p++;
@@ -449,8 +405,8 @@ static int choose_prefix_bits(uint64_t n_pos, int key_bits, uint64_t target) {
 
 // (2) of the file header: count distinct keys per item (splitting items that do not fit shared memory),
 // scan to row offsets, emit rows.  `items` is a device array in ascending key order.
-static void merge_items(const uint64_t* rec, const uint16_t* sid, Item* items, uint32_t n_items, const uint64_t* seg_voff,
-                        const uint64_t* seg_pstart, int n_runs, uint64_t n_samples, uint32_t k, bool rc, Array& out) {
+static void merge_items(const uint64_t* rec, Item* items, uint32_t n_items, const uint64_t* seg_voff, const uint64_t* seg_pstart,
+                        int n_runs, int sb, uint64_t n_samples, uint32_t k, bool rc, Array& out) {
     Context& c = ctx();
     // bytes of shared memory per table slot in the emit kernel: tab 8 + rank 2 + (lkey 8 + lslot 2 + cnt 4)/2
     const size_t slot_bytes = 17;
@@ -463,7 +419,7 @@ static void merge_items(const uint64_t* rec, const uint16_t* sid, Item* items, u
     uint32_t h_flags[2] = {0, 0};
     for (int round = 0; n_items > 0; round++) {
         SKA_CUDA(cudaMemsetAsync(flags, 0, 8, c.stream));
-        SKA_LAUNCH(bucket_count_kernel, n_items, MG_THREADS, 0, rec, items, seg_voff, seg_pstart, n_runs, limit, n_rows, flags);
+        SKA_LAUNCH(bucket_count_kernel, n_items, MG_THREADS, 0, rec, items, seg_voff, seg_pstart, n_runs, sb, limit, n_rows, flags);
         SKA_CUDA(cudaMemcpyAsync(h_flags, flags, 8, cudaMemcpyDeviceToHost, c.stream));
         SKA_CUDA(cudaStreamSynchronize(c.stream));
         if (!h_flags[0]) break;
@@ -516,67 +472,46 @@ static void merge_items(const uint64_t* rec, const uint16_t* sid, Item* items, u
         size_t smem = ((size_t)1 << log_cap) * slot_bytes;
         if (log_cap > max_log_cap) throw Error("internal: item larger than the shared-memory table");
         SKA_CUDA(cudaFuncSetAttribute(bucket_emit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        SKA_LAUNCH(bucket_emit_kernel, n_items, MG_THREADS, smem, rec, sid, items, seg_voff, seg_pstart, n_runs, row_off, log_cap,
+        SKA_LAUNCH(bucket_emit_kernel, n_items, MG_THREADS, smem, rec, items, seg_voff, seg_pstart, n_runs, sb, row_off, log_cap,
                    (uint32_t)n_samples, (int)k, rc ? 1 : 0, out.keys.p, out.variants.p, out.counts.p);
     }
     timer().end();
 }
 
-int merge_prefix_bits(uint64_t n_records_total, uint32_t k, int n_shards) {
+int merge_prefix_bits(uint64_t n_records_total, uint32_t k) {
     const int key_bits = 2 * ((int)k - 1);
-    // records per bucket ~4096, but stay at 16 prefix bits (two 8-bit radix passes) while buckets
-    // remain small enough for the shared-memory tables
-    int P = choose_prefix_bits(n_records_total, key_bits, 4096);
-    if (P > 16 && (n_records_total >> 16) <= 16384) P = 16;
-    (void)n_shards;
-    if (const char* e = getenv("SKA_PREFIX_BITS")) { int v = atoi(e); if (v >= 0 && v <= key_bits && v <= 24) P = v; }   // tuning/tests
-    return std::min(std::min(P, 24), key_bits);
+    int P = choose_prefix_bits(n_records_total, key_bits, 8192);   // ~4-8 K records per bucket
+    if (const char* e = getenv("SKA_PREFIX_BITS")) { int v = atoi(e); if (v >= 0 && v <= key_bits && v <= 22) P = v; }   // tuning/tests
+    return std::min(std::min(P, 22), key_bits);
 }
 
-void build_array_from_records(uint64_t* rec, uint16_t* sid, uint64_t n_pos, uint64_t n_samples, uint32_t k, bool rc,
+void build_array_from_records(uint64_t* rec, const SeqBatch& b, uint32_t sid_base, uint64_t n_samples_total, uint32_t k, bool rc,
                               Array& out) {
-    Context& c = ctx();
-    const int key_bits = 2 * ((int)k - 1);
-    const int P = merge_prefix_bits(n_pos, k, 1);
-    const uint32_t n_buckets = 1u << P;
-    const int shift = 4 + key_bits - P;
+    const PartPlan pl = make_part_plan(k, merge_prefix_bits(b.n_pos, k), n_samples_total);
+    const uint32_t n_buckets = 1u << pl.P;
 
     // (1) partition by key prefix
     timer().begin("partition");
-    uint64_t* rec_sorted = rec; uint16_t* sid_sorted = sid;
-    if (P > 0) {
-        uint64_t* rec_alt = arena().take_n<uint64_t>(n_pos);
-        uint16_t* sid_alt = arena().take_n<uint16_t>(n_pos);
-        cub::DoubleBuffer<uint64_t> dk(rec, rec_alt);
-        cub::DoubleBuffer<uint16_t> dv(sid, sid_alt);
-        size_t tmp_bytes = 0;
-        SKA_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, dk, dv, (int64_t)n_pos, shift, shift + P, c.stream));
-        void* tmp = arena().take(tmp_bytes);
-        SKA_CUDA(cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, dk, dv, (int64_t)n_pos, shift, shift + P, c.stream));
-        c.launches += (P + 7) / 8 + 1;   // onesweep: one histogram + one pass per 8 bits (library kernels)
-        rec_sorted = dk.Current(); sid_sorted = dv.Current();
-    }
+    uint64_t* prec = nullptr; uint64_t* off = nullptr;
+    partition_records(rec, b.n_pos, b.sample_off.p, (uint32_t)b.n_samples, sid_base, pl, rec, &prec, &off);
     timer().end();
 
     timer().begin("bucket_offsets");
-    uint64_t* off = arena().take_n<uint64_t>(n_buckets + 1);
-    SKA_LAUNCH(bucket_offsets_kernel, (n_buckets + 1 + 255) / 256, 256, 0, rec_sorted, n_pos, shift, n_buckets, off);
     Item* items = arena().take_n<Item>(n_buckets);
-    SKA_LAUNCH(make_items_kernel, (n_buckets + 255) / 256, 256, 0, off, n_buckets, key_bits, P, items);
+    SKA_LAUNCH(make_items_kernel, (n_buckets + 255) / 256, 256, 0, off, n_buckets, pl.key_bits, pl.P, pl.P2, pl.low_bits, items);
     timer().end();
 
-    merge_items(rec_sorted, sid_sorted, items, n_buckets, nullptr, nullptr, 1, n_samples, k, rc, out);
+    merge_items(prec, items, n_buckets, nullptr, nullptr, 1, pl.sb, n_samples_total, k, rc, out);
 }
 
-// Row shard: the received records are `n_runs` runs (one per source rank), each sorted by the same
-// `prefix_bits`-bit key prefix and covering buckets [bucket_lo, bucket_hi).  run_off[r * (nb + 1) + j]
-// is the offset, inside the receive buffer, of bucket (bucket_lo + j) of run r (nb = bucket_hi - bucket_lo).
-void build_array_from_runs(const uint64_t* rec, const uint16_t* sid, int n_runs, const uint64_t* run_off, uint32_t bucket_lo,
-                           uint32_t bucket_hi, int prefix_bits, uint64_t n_samples, uint32_t k, bool rc, Array& out) {
+// Row shard: the received records are `n_runs` runs (one per source rank), each grouped by the same plan
+// and covering buckets [bucket_lo, bucket_hi).  run_off[r * (nb + 1) + j] is the offset, inside the receive
+// buffer, of bucket (bucket_lo + j) of run r (nb = bucket_hi - bucket_lo).
+void build_array_from_runs(const uint64_t* prec, int n_runs, const uint64_t* run_off, uint32_t bucket_lo, uint32_t bucket_hi,
+                           const PartPlan& pl, uint64_t n_samples, uint32_t k, bool rc, Array& out) {
     Context& c = ctx();
     if (n_runs < 1 || n_runs > MAX_RUNS) throw Error("row shard supports 1.." + std::to_string(MAX_RUNS) + " source ranks");
-    const int key_bits = 2 * ((int)k - 1);
-    const int low = key_bits - prefix_bits;
+    const int low = pl.key_bits - pl.P;
     const uint32_t nb = bucket_hi - bucket_lo;
     const int W = std::max(n_runs, 2);                    // the map is only consulted for W > 1: pad with an empty run
     std::vector<Item> h_items(nb);
@@ -587,7 +522,8 @@ void build_array_from_runs(const uint64_t* rec, const uint16_t* sid, int n_runs,
         const uint64_t b = (uint64_t)bucket_lo + j;
         it.key_lo = b << low;
         it.key_hi = it.key_lo | ((low >= 64) ? ~0ULL : ((1ULL << low) - 1ULL));
-        if (b == (1ull << prefix_bits) - 1) it.key_hi = ~0ULL >> 4;
+        if (b == (1ull << pl.P) - 1) it.key_hi = ~0ULL >> 4;
+        it.key_base = (b >> pl.P2) << pl.low_bits;
         it.seg0 = (uint64_t)j * (W + 1);
         it.beg = v;
         for (int r = 0; r < W; r++) {
@@ -613,7 +549,7 @@ void build_array_from_runs(const uint64_t* rec, const uint16_t* sid, int n_runs,
         SKA_CUDA(cudaStreamSynchronize(c.stream));
     }
     timer().end();
-    merge_items(rec, sid, items, nb, d_voff, d_pstart, W, n_samples, k, rc, out);
+    merge_items(prec, items, nb, d_voff, d_pstart, W, pl.sb, n_samples, k, rc, out);
 }
 
 }  // namespace ska

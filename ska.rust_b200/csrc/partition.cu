@@ -1,0 +1,319 @@
+// partition.cu -- groups K1's records by the top P bits of the split-k-mer key: the step that lets one
+// CTA merge one key range in shared memory (merge.cu).  Hand-written replacement for the library radix
+// sort used earlier in this round (DESIGN.md "partition").
+//
+// Two MSD passes of P1 and P2 bits (any widths up to 11, so P = 19..21 for row shards is still two
+// passes), each pass = histogram + scatter:
+//   * records move as ONE packed u64: after the first digit is implied by the bucket, its bits hold the
+//     sample id:   prec = key_low << (SB+2) | sample_id << 2 | middle_code,
+//     key_low = key without its top P1 bits, SB = bits of a sample id.  16 B of traffic per record and pass
+//     instead of 20 B for (u64 record, u16 sample id) pairs;
+//   * the partition is UNSTABLE on purpose: order inside a bucket is irrelevant to the merge (a set
+//     union), so a tile reserves its slice of every destination bucket with one global atomicAdd per
+//     digit instead of a decoupled look-back;
+//   * ranking inside a tile uses warp ballots (peers with the same digit) and warp-private counters --
+//     no shared-memory atomics on the hot path; records are staged in shared memory in digit order so
+//     the global stores are coalesced runs.
+// Roofline: HBM; 8 B read by each histogram, 8 B read + 8 B written by each scatter, per record.
+#include "common.cuh"
+
+namespace ska {
+
+constexpr int PT_THREADS = 512;
+constexpr int PT_ITEMS = 8;
+constexpr int PT_TILE = PT_THREADS * PT_ITEMS;      // 4096 records per tile
+constexpr int PT_WARPS = PT_THREADS / 32;
+constexpr int PT_MAX_BITS = 11;
+constexpr uint32_t PT_NONE = 0xFFFFFFFFu;
+
+// lanes of the warp whose (valid) digit equals mine
+__device__ __forceinline__ uint32_t match_digit(uint32_t digit, int bits, bool valid) {
+    uint32_t peers = __ballot_sync(0xFFFFFFFFu, valid);
+    for (int b = 0; b < bits; b++) {
+        const bool bit = (digit >> b) & 1u;
+        const uint32_t m = __ballot_sync(0xFFFFFFFFu, bit);
+        peers &= bit ? m : ~m;
+    }
+    return peers;
+}
+
+// ---------------------------------------------------------------------------------------------- histograms
+// src: K1 records (pass 1) or packed records (pass 2).  For pass 2 tiles are enumerated per region so that a
+// tile never straddles two first-level buckets: tile_pref[d1] = number of tiles before region d1.
+struct DigitFn {
+    int pass;            // 1: digit = rec >> shift (K1 record, REC_SENTINEL skipped); 2: digit = (prec >> shift) & mask
+    int shift;
+    uint32_t mask;
+    __device__ __forceinline__ uint32_t operator()(uint64_t r) const {
+        if (pass == 1) return r == REC_SENTINEL ? PT_NONE : (uint32_t)(r >> shift);
+        return (uint32_t)(r >> shift) & mask;
+    }
+};
+
+__device__ __forceinline__ void tile_range(uint64_t tile, const uint64_t* __restrict__ tile_pref, const uint64_t* __restrict__ region_off,
+                                           uint32_t n_regions, uint64_t n_total, uint64_t& beg, uint64_t& end, uint32_t& region) {
+    if (!tile_pref) { beg = tile * PT_TILE; end = min(n_total, beg + PT_TILE); region = 0; return; }
+    uint32_t lo = 0, hi = n_regions;                        // last region with tile_pref[region] <= tile
+    while (hi - lo > 1) { uint32_t m = (lo + hi) >> 1; if (tile_pref[m] <= tile) lo = m; else hi = m; }
+    region = lo;
+    beg = region_off[lo] + (tile - tile_pref[lo]) * PT_TILE;
+    end = min(region_off[lo + 1], beg + PT_TILE);
+}
+
+__global__ void __launch_bounds__(PT_THREADS)
+part_hist_kernel(const uint64_t* __restrict__ src, uint64_t n_total, uint64_t n_tiles, const uint64_t* __restrict__ tile_pref,
+                 const uint64_t* __restrict__ region_off, uint32_t n_regions, DigitFn fn, int bits,
+                 unsigned long long* __restrict__ hist /* [n_regions or 1][1 << bits] */) {
+    extern __shared__ uint32_t s_cnt[];                     // [PT_WARPS][D]
+    const uint32_t D = 1u << bits;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t* my = s_cnt + (size_t)warp * D;
+    // a CTA takes a contiguous chunk of tiles; with regions it flushes whenever the region changes
+    const uint64_t per = (n_tiles + gridDim.x - 1) / gridDim.x;
+    const uint64_t t_beg = min(n_tiles, (uint64_t)blockIdx.x * per), t_end = min(n_tiles, t_beg + per);
+    uint32_t cur_region = PT_NONE;
+    for (uint32_t i = threadIdx.x; i < PT_WARPS * D; i += PT_THREADS) s_cnt[i] = 0;
+    __syncthreads();
+    auto flush = [&](uint32_t region) {
+        __syncthreads();
+        for (uint32_t d = threadIdx.x; d < D; d += PT_THREADS) {
+            uint32_t tot = 0;
+            for (int w = 0; w < PT_WARPS; w++) { tot += s_cnt[(size_t)w * D + d]; s_cnt[(size_t)w * D + d] = 0; }
+            if (tot) atomicAdd(&hist[(size_t)region * D + d], (unsigned long long)tot);
+        }
+        __syncthreads();
+    };
+    for (uint64_t t = t_beg; t < t_end; t++) {
+        uint64_t beg, end; uint32_t region;
+        tile_range(t, tile_pref, region_off, n_regions, n_total, beg, end, region);
+        if (region != cur_region) { if (cur_region != PT_NONE) flush(cur_region); cur_region = region; }
+        uint64_t rr[PT_ITEMS];
+#pragma unroll
+        for (int j = 0; j < PT_ITEMS; j++) {
+            uint64_t i = beg + (uint64_t)j * PT_THREADS + threadIdx.x;
+            rr[j] = i < end ? src[i] : REC_SENTINEL;
+        }
+#pragma unroll
+        for (int j = 0; j < PT_ITEMS; j++) {
+            uint64_t i = beg + (uint64_t)j * PT_THREADS + threadIdx.x;
+            uint32_t d = i < end ? fn(rr[j]) : PT_NONE;
+            bool valid = d != PT_NONE;
+            uint32_t peers = match_digit(d, bits, valid);
+            if (valid && (peers & ((1u << lane) - 1u)) == 0) my[d] += __popc(peers);   // one leader per digit per warp
+            __syncwarp();
+        }
+    }
+    if (cur_region != PT_NONE) flush(cur_region);
+}
+
+// ---------------------------------------------------------------------------------------------- scatter
+struct PackFn {               // pass 1: K1 record -> packed record (needs the sample id of the position)
+    int sb;                   // bits of a sample id
+    uint64_t low_mask;        // key bits kept (key without its top P1 bits)
+    uint32_t sid_base;
+};
+
+template <int PASS>
+__global__ void __launch_bounds__(PT_THREADS)
+part_scatter_kernel(const uint64_t* __restrict__ src, uint64_t n_total, const uint64_t* __restrict__ tile_pref,
+                    const uint64_t* __restrict__ region_off, uint32_t n_regions, DigitFn fn, int bits, PackFn pk,
+                    const uint64_t* __restrict__ sample_off, uint32_t n_samples,
+                    unsigned long long* __restrict__ cursor /* [n_regions or 1][1 << bits], preset to bucket starts */,
+                    uint64_t* __restrict__ dst) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    const uint32_t D = 1u << bits;
+    uint64_t* s_stage = reinterpret_cast<uint64_t*>(smem);                       // [PT_TILE]
+    unsigned long long* s_gbase = reinterpret_cast<unsigned long long*>(s_stage + PT_TILE);   // [D]
+    uint32_t* s_doff = reinterpret_cast<uint32_t*>(s_gbase + D);                 // [D + 1]
+    uint16_t* s_wcnt = reinterpret_cast<uint16_t*>(s_doff + D + 1 + ((D + 1) & 1));   // [PT_WARPS][D]
+    uint16_t* s_sdig = s_wcnt + (size_t)PT_WARPS * D;                            // [PT_TILE]
+    __shared__ uint32_t s_sid[2];
+
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint64_t beg, end; uint32_t region;
+    tile_range(blockIdx.x, tile_pref, region_off, n_regions, n_total, beg, end, region);
+    for (uint32_t i = threadIdx.x; i < PT_WARPS * D; i += PT_THREADS) s_wcnt[i] = 0;
+    if (PASS == 1 && threadIdx.x == 0) {                     // sample ids of the tile's first and last position
+        uint64_t pf = beg, pl = end - 1;
+        uint32_t lo = 0, hi = n_samples;
+        while (hi - lo > 1) { uint32_t m = (lo + hi) >> 1; if (sample_off[m] <= pf) lo = m; else hi = m; }
+        s_sid[0] = lo; hi = n_samples;
+        while (hi - lo > 1) { uint32_t m = (lo + hi) >> 1; if (sample_off[m] <= pl) lo = m; else hi = m; }
+        s_sid[1] = lo;
+    }
+    __syncthreads();
+
+    // 1. load, digit, rank among the warp's earlier records of the same digit
+    uint64_t out[PT_ITEMS]; uint32_t dig[PT_ITEMS]; uint32_t pre[PT_ITEMS];
+    uint64_t rr[PT_ITEMS];
+#pragma unroll
+    for (int j = 0; j < PT_ITEMS; j++) {
+        uint64_t i = beg + (uint64_t)j * PT_THREADS + threadIdx.x;
+        rr[j] = i < end ? src[i] : REC_SENTINEL;
+    }
+    uint16_t* my = s_wcnt + (size_t)warp * D;
+#pragma unroll
+    for (int j = 0; j < PT_ITEMS; j++) {
+        const uint64_t i = beg + (uint64_t)j * PT_THREADS + threadIdx.x;
+        const uint64_t r = rr[j];
+        uint32_t d = i < end ? fn(r) : PT_NONE;
+        const bool valid = d != PT_NONE;
+        if (PASS == 1) {
+            uint32_t s = s_sid[0];
+            if (valid && s_sid[0] != s_sid[1]) {             // tile straddles samples (rare)
+                uint32_t lo = s_sid[0], hi = s_sid[1] + 1;
+                while (hi - lo > 1) { uint32_t m = (lo + hi) >> 1; if (sample_off[m] <= i) lo = m; else hi = m; }
+                s = lo;
+            }
+            const uint64_t key = r >> 4;
+            const uint32_t mid = (uint32_t)__ffs((uint32_t)(r & 0xF)) - 1u;
+            out[j] = ((key & pk.low_mask) << (pk.sb + 2)) | ((uint64_t)(s + pk.sid_base) << 2) | mid;
+        } else {
+            out[j] = r;
+        }
+        const uint32_t peers = match_digit(d, bits, valid);
+        const uint32_t lt = (1u << lane) - 1u;
+        uint32_t old = 0;
+        if (valid && (peers & lt) == 0) { old = my[d]; my[d] = (uint16_t)(old + __popc(peers)); }
+        old = __shfl_sync(0xFFFFFFFFu, old, valid ? __ffs(peers) - 1 : lane);
+        pre[j] = old + __popc(peers & lt);
+        dig[j] = d;
+        __syncwarp();
+    }
+    __syncthreads();
+
+    // 2. per digit: exclusive prefix over warps (in place) and tile total
+    for (uint32_t d = threadIdx.x; d < D; d += PT_THREADS) {
+        uint32_t tot = 0;
+        for (int w = 0; w < PT_WARPS; w++) { uint32_t t = s_wcnt[(size_t)w * D + d]; s_wcnt[(size_t)w * D + d] = (uint16_t)tot; tot += t; }
+        s_doff[d] = tot;
+    }
+    __syncthreads();
+    // 3. exclusive scan over digits (warp 0: 32 lanes x D/32 consecutive digits), global reservation
+    if (warp == 0) {
+        const uint32_t per = (D + 31) / 32, b0 = lane * per, e0 = min(D, b0 + per);
+        uint32_t sum = 0;
+        for (uint32_t d = b0; d < e0; d++) sum += s_doff[d];
+        uint32_t inc = sum;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { uint32_t v = __shfl_up_sync(0xFFFFFFFFu, inc, o); if (lane >= o) inc += v; }
+        uint32_t run = inc - sum;
+        for (uint32_t d = b0; d < e0; d++) { uint32_t t = s_doff[d]; s_doff[d] = run; run += t; }
+        if (lane == 31) s_doff[D] = inc;
+    }
+    __syncthreads();
+    for (uint32_t d = threadIdx.x; d < D; d += PT_THREADS) {
+        uint32_t tot = s_doff[d + 1] - s_doff[d];
+        if (tot) s_gbase[d] = atomicAdd(&cursor[(size_t)region * D + d], (unsigned long long)tot) - s_doff[d];
+    }
+    // 4. stage in digit order
+#pragma unroll
+    for (int j = 0; j < PT_ITEMS; j++) {
+        if (dig[j] == PT_NONE) continue;
+        uint32_t slot = s_doff[dig[j]] + s_wcnt[(size_t)warp * D + dig[j]] + pre[j];
+        s_stage[slot] = out[j];
+        s_sdig[slot] = (uint16_t)dig[j];
+    }
+    __syncthreads();
+    // 5. coalesced runs out
+    const uint32_t n_valid = s_doff[D];
+    for (uint32_t slot = threadIdx.x; slot < n_valid; slot += PT_THREADS) dst[s_gbase[s_sdig[slot]] + slot] = s_stage[slot];
+}
+
+// ---------------------------------------------------------------------------------------------- small helpers
+// exclusive scan of u64 counts -> offsets[n+1]; also cursors[i] = offsets[i]; single CTA
+__global__ void part_scan_kernel(const unsigned long long* __restrict__ cnt, uint32_t n, uint64_t* __restrict__ off,
+                                 unsigned long long* __restrict__ cursor, uint64_t* __restrict__ tile_pref /* may be null */) {
+    __shared__ uint64_t s_sum[1024], s_tiles[1024];
+    const uint32_t t = threadIdx.x, T = blockDim.x;
+    const uint32_t per = (n + T - 1) / T, b = min(n, t * per), e = min(n, b + per);
+    uint64_t sum = 0, tiles = 0;
+    for (uint32_t i = b; i < e; i++) { sum += cnt[i]; tiles += (cnt[i] + PT_TILE - 1) / PT_TILE; }
+    s_sum[t] = sum; s_tiles[t] = tiles;
+    __syncthreads();
+    if (t == 0) {
+        uint64_t run = 0, trun = 0;
+        for (uint32_t i = 0; i < T; i++) { uint64_t v = s_sum[i]; s_sum[i] = run; run += v; uint64_t w = s_tiles[i]; s_tiles[i] = trun; trun += w; }
+        off[n] = run;
+        if (tile_pref) tile_pref[n] = trun;
+    }
+    __syncthreads();
+    uint64_t run = s_sum[t], trun = s_tiles[t];
+    for (uint32_t i = b; i < e; i++) {
+        off[i] = run; if (cursor) cursor[i] = run; if (tile_pref) tile_pref[i] = trun;
+        run += cnt[i]; trun += (cnt[i] + PT_TILE - 1) / PT_TILE;
+    }
+}
+
+static size_t scatter_smem(int bits) {
+    const size_t D = (size_t)1 << bits;
+    return PT_TILE * 8 + D * 8 + (D + 2) * 4 + PT_WARPS * D * 2 + PT_TILE * 2 + 64;
+}
+
+PartPlan make_part_plan(uint32_t k, int prefix_bits, uint64_t n_samples_total) {
+    PartPlan pl;
+    pl.key_bits = 2 * ((int)k - 1);
+    pl.sb = 1; while ((1ull << pl.sb) < n_samples_total) pl.sb++;
+    const int need1 = std::max(0, pl.key_bits + pl.sb + 2 - 64);       // the first digit must free room for the sample id
+    pl.P = std::min(std::max(prefix_bits, need1), pl.key_bits);
+    if (pl.P > 2 * PT_MAX_BITS) pl.P = 2 * PT_MAX_BITS;
+    pl.P1 = std::max((pl.P + 1) / 2, need1);
+    if (pl.P1 > PT_MAX_BITS || pl.P1 > pl.P) throw Error("too many samples for the packed record format at this k");
+    pl.P2 = pl.P - pl.P1;
+    pl.low_bits = pl.key_bits - pl.P1;
+    return pl;
+}
+
+// rec: K1 output (n_pos entries, linear).  Returns the packed records grouped by the P-bit prefix in `*out`
+// (arena memory) and the 2^P + 1 bucket offsets on the device in `*d_off`.
+void partition_records(const uint64_t* rec, uint64_t n_pos, const uint64_t* d_sample_off, uint32_t n_samples_local, uint32_t sid_base,
+                       const PartPlan& pl, uint64_t* scratch /* n_pos u64, may alias nothing */, uint64_t** out, uint64_t** d_off) {
+    Context& c = ctx();
+    const uint32_t D1 = 1u << pl.P1, D2 = 1u << pl.P2, NB = 1u << pl.P;
+    unsigned long long* hist1 = arena().take_n<unsigned long long>(D1);
+    unsigned long long* cur1 = arena().take_n<unsigned long long>(D1);
+    uint64_t* off1 = arena().take_n<uint64_t>(D1 + 1);
+    uint64_t* tile_pref = arena().take_n<uint64_t>(D1 + 1);
+    uint64_t* bucket_off = arena().take_n<uint64_t>((size_t)NB + 1);
+    SKA_CUDA(cudaMemsetAsync(hist1, 0, D1 * 8, c.stream));
+    const uint64_t n_tiles1 = (n_pos + PT_TILE - 1) / PT_TILE;
+    DigitFn f1{1, 4 + pl.key_bits - pl.P1, 0xFFFFFFFFu};
+    PackFn pk{pl.sb, pl.low_bits >= 64 ? ~0ULL : ((1ULL << pl.low_bits) - 1ULL), sid_base};
+    const unsigned hist_grid = (unsigned)std::min<uint64_t>(std::max<uint64_t>(n_tiles1, 1), (uint64_t)c.sm_count * 4);
+    SKA_CUDA(cudaFuncSetAttribute(part_hist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PT_WARPS * (1 << PT_MAX_BITS) * 4));
+    SKA_CUDA(cudaFuncSetAttribute(part_scatter_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)scatter_smem(PT_MAX_BITS)));
+    SKA_CUDA(cudaFuncSetAttribute(part_scatter_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)scatter_smem(PT_MAX_BITS)));
+    if (n_pos) {
+        SKA_LAUNCH(part_hist_kernel, hist_grid, PT_THREADS, PT_WARPS * D1 * 4, rec, n_pos, n_tiles1, (const uint64_t*)nullptr,
+                   (const uint64_t*)nullptr, 1u, f1, pl.P1, hist1);
+    }
+    SKA_LAUNCH(part_scan_kernel, 1, 1024, 0, hist1, D1, off1, cur1, tile_pref);
+    uint64_t* a = arena().take_n<uint64_t>(std::max<uint64_t>(n_pos, 1));
+    if (n_pos) {
+        SKA_LAUNCH((part_scatter_kernel<1>), (unsigned)n_tiles1, PT_THREADS, scatter_smem(pl.P1), rec, n_pos, (const uint64_t*)nullptr,
+                   (const uint64_t*)nullptr, 1u, f1, pl.P1, pk, d_sample_off, n_samples_local, cur1, a);
+    }
+    if (pl.P2 == 0) { *out = a; *d_off = off1; return; }
+
+    // second level: every first-level region is partitioned by the next P2 bits
+    unsigned long long* hist2 = arena().take_n<unsigned long long>(NB);
+    unsigned long long* cur2 = arena().take_n<unsigned long long>(NB);
+    SKA_CUDA(cudaMemsetAsync(hist2, 0, (size_t)NB * 8, c.stream));
+    uint64_t n_tiles2 = 0;
+    SKA_CUDA(cudaMemcpyAsync(&n_tiles2, tile_pref + D1, 8, cudaMemcpyDeviceToHost, c.stream));
+    SKA_CUDA(cudaStreamSynchronize(c.stream));
+    DigitFn f2{2, pl.sb + 2 + pl.low_bits - pl.P2, D2 - 1};
+    if (n_tiles2) {
+        const unsigned g2 = (unsigned)std::min<uint64_t>(n_tiles2, (uint64_t)c.sm_count * 4);
+        SKA_LAUNCH(part_hist_kernel, g2, PT_THREADS, PT_WARPS * D2 * 4, a, n_pos, n_tiles2, tile_pref, off1, D1, f2, pl.P2, hist2);
+    }
+    SKA_LAUNCH(part_scan_kernel, 1, 1024, 0, hist2, NB, bucket_off, cur2, (uint64_t*)nullptr);
+    uint64_t* b = scratch ? scratch : arena().take_n<uint64_t>(std::max<uint64_t>(n_pos, 1));
+    if (n_tiles2) {
+        SKA_LAUNCH((part_scatter_kernel<2>), (unsigned)n_tiles2, PT_THREADS, scatter_smem(pl.P2), a, n_pos, tile_pref, off1, D1, f2, pl.P2,
+                   pk, (const uint64_t*)nullptr, 0u, cur2, b);
+    }
+    *out = b; *d_off = bucket_off;
+}
+
+}  // namespace ska

@@ -8,7 +8,7 @@ rows of the merged dictionary are keyed by split k-mer.  Here (SURVEY.md section
   1. every rank extracts the records of ITS samples (K1) and sorts them by the top `prefix_bits` bits of
      the key; the per-bucket record counts are summed over ranks (all-reduce) and cut into `world`
      contiguous key ranges of equal record count -> owner of every bucket;
-  2. ONE all-to-all moves each record range to its owner (records u64, sample ids u16);
+  2. ONE all-to-all moves each record range to its owner (one packed u64 per record, sample id inside);
   3. every rank merges what it received into its slab of rows with ALL samples' columns.  Filters are
      row-local; distances are per-pair integer sums over rows, so slabs add up with one all-reduce.
 
@@ -38,31 +38,31 @@ class GpuBackend:
     """The product backend: libskagpu through its C ABI."""
     device = "cuda"
 
-    def extract(self, samples, k, rc, sample_base, prefix_bits):
+    def extract(self, samples, k, rc, sample_base, n_samples_total, prefix_bits):
+        """-> (packed records int64 tensor grouped by key prefix, bucket offsets uint64[2^P + 1])"""
         import ctypes as C
         batch = samples if isinstance(samples, api.SeqBatch) else api.SeqBatch(samples)
         h = C.c_void_p()
-        api._check(api.lib().skagpu_extract_records(batch._h, k, int(rc), sample_base, prefix_bits, C.byref(h)))
+        api._check(api.lib().skagpu_extract_records(batch._h, k, int(rc), sample_base, n_samples_total, prefix_bits, C.byref(h)))
         n = C.c_uint64()
-        rec_p, sid_p = C.c_void_p(), C.c_void_p()
+        rec_p = C.c_void_p()
+        pb = C.c_int()
+        api._check(api.lib().skagpu_records_info(h, C.byref(n), C.byref(rec_p), C.byref(pb), None))
+        assert pb.value == prefix_bits, "prefix_bits must come from prefix_bits()"
         off = np.zeros((1 << prefix_bits) + 1, dtype=np.uint64)
-        api._check(api.lib().skagpu_records_info(h, C.byref(n), C.byref(rec_p), C.byref(sid_p), off.ctypes.data))
+        api._check(api.lib().skagpu_records_info(h, None, None, None, off.ctypes.data))
         api.lib().skagpu_records_free(h)        # frees only the handle; buffers live in the arena until the next build
         n = n.value
-        if n:
-            rec = torch.as_tensor(_CudaView(rec_p.value, n, "<i8"), device="cuda")
-            sid = torch.as_tensor(_CudaView(sid_p.value, n, "<i2"), device="cuda")
-        else:
-            rec = torch.empty(0, dtype=torch.int64, device="cuda")
-            sid = torch.empty(0, dtype=torch.int16, device="cuda")
-        return rec, sid, off
+        rec = (torch.as_tensor(_CudaView(rec_p.value, n, "<i8"), device="cuda") if n
+               else torch.empty(0, dtype=torch.int64, device="cuda"))
+        return rec, off
 
-    def merge(self, rec, sid, run_offsets, bucket_lo, bucket_hi, prefix_bits, n_samples_total, k, rc, names):
+    def merge(self, rec, run_offsets, bucket_lo, bucket_hi, prefix_bits, n_samples_total, k, rc, names):
         import ctypes as C
         h = C.c_void_p()
         ro = np.ascontiguousarray(run_offsets, dtype=np.uint64)
-        api._check(api.lib().skagpu_merge_records_dev(rec.data_ptr(), sid.data_ptr(), ro.shape[0], ro.ctypes.data, bucket_lo,
-                                                      bucket_hi, prefix_bits, n_samples_total, k, int(rc), C.byref(h)))
+        api._check(api.lib().skagpu_merge_records_dev(rec.data_ptr(), ro.shape[0], ro.ctypes.data, bucket_lo, bucket_hi,
+                                                      prefix_bits, n_samples_total, k, int(rc), C.byref(h)))
         return api.MergeSkaArray(h, names)
 
     def n_positions(self, samples):
@@ -70,8 +70,11 @@ class GpuBackend:
             samples = samples._keep
         return int(sum(len(s.seq) for s in samples))
 
-    def prefix_bits(self, n_records_total, k):
-        return int(api.lib().skagpu_merge_prefix_bits(int(n_records_total), k))
+    def prefix_bits(self, n_records_total, k, n_samples_total):
+        p = int(api.lib().skagpu_merge_prefix_bits(int(n_records_total), k, n_samples_total))
+        if p < 0:
+            raise api.SkaError(api.lib().skagpu_last_error().decode())
+        return p
 
 
 def plan_owners(global_bucket_counts, world):
@@ -110,10 +113,10 @@ def build_and_merge_sharded(backend, samples_local, names_all, sample_base, k, r
     if prefix_bits is None:                               # bucket granularity from the GLOBAL record count
         tot = torch.tensor([backend.n_positions(samples_local)], dtype=torch.int64, device=dev)
         dist.all_reduce(tot, group=group)
-        prefix_bits = backend.prefix_bits(int(tot.item()), k)
+        prefix_bits = backend.prefix_bits(int(tot.item()), k, len(names_all))
     prefix_bits = min(prefix_bits, key_bits)
     lap("plan_ms")
-    rec, sid, off = backend.extract(samples_local, k, rc, sample_base, prefix_bits)
+    rec, off = backend.extract(samples_local, k, rc, sample_base, len(names_all), prefix_bits)
     lap("extract_ms")
     counts = torch.from_numpy(np.diff(off).astype(np.int64)).to(dev)
     dist.all_reduce(counts, group=group)
@@ -126,13 +129,10 @@ def build_and_merge_sharded(backend, samples_local, names_all, sample_base, k, r
     recv_counts = rc_.cpu().numpy()
     n_recv = int(recv_counts.sum())
     recv_rec = torch.empty(n_recv, dtype=torch.int64, device=dev)
-    recv_sid = torch.empty(n_recv, dtype=torch.int16, device=dev)
     lap("owners_ms")
-    # records are sorted by prefix, so each owner's share is one contiguous range starting at bounds[0] == 0
+    # records are grouped by prefix, so each owner's share is one contiguous range starting at bounds[0] == 0;
+    # one packed u64 per record (the sample id travels inside it)
     dist.all_to_all_single(recv_rec, rec[:int(bounds[-1])], list(map(int, recv_counts)), list(map(int, send_counts)), group=group)
-    # sample ids travel as raw bytes (gloo has no 16-bit integer all-to-all)
-    dist.all_to_all_single(recv_sid.view(torch.uint8), sid[:int(bounds[-1])].view(torch.uint8),
-                           [2 * int(c) for c in recv_counts], [2 * int(c) for c in send_counts], group=group)
     lap("all_to_all_ms")
     # every run stays sorted by prefix: ship its bucket offsets (relative to the run) so the owner never re-sorts
     nb_send = np.diff(cuts) + 1                           # offsets per owner: nb_g + 1
@@ -143,7 +143,7 @@ def build_and_merge_sharded(backend, samples_local, names_all, sample_base, k, r
     run_base = np.concatenate([[0], np.cumsum(recv_counts)[:-1]]).astype(np.int64)
     run_offsets = (recv_off.cpu().numpy().reshape(world, nb_mine + 1) + run_base[:, None]).astype(np.uint64)
     lap("offsets_ms")
-    arr = backend.merge(recv_rec, recv_sid, run_offsets, int(cuts[rank]), int(cuts[rank + 1]), prefix_bits, len(names_all),
+    arr = backend.merge(recv_rec, run_offsets, int(cuts[rank]), int(cuts[rank + 1]), prefix_bits, len(names_all),
                         k, rc, names_all)
     lap("merge_ms")
     if timings is not None:

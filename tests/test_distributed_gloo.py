@@ -77,34 +77,32 @@ class OracleSlab:
 class OracleBackend:
     device = "cpu"
 
-    def extract(self, samples, k, rc, sample_base, prefix_bits):
-        recs, sids = [], []
+    # stand-in record: key << 12 | sample << 4 | one-hot middle  (keys here are <= 28 bits)
+    def extract(self, samples, k, rc, sample_base, n_samples_total, prefix_bits):
+        recs = []
         for i, records in enumerate(samples):
             for r in records:
                 w = O.windows(r, k, rc=rc)
                 for key, mid in zip(w["key"], w["mid"]):
-                    recs.append((key << 4) | (1 << int(mid)))
-                    sids.append(sample_base + i)
+                    recs.append((key << 12) | ((sample_base + i) << 4) | (1 << int(mid)))
         rec = np.array(recs, dtype=np.uint64)
-        sid = np.array(sids, dtype=np.int16)
-        shift = 4 + 2 * (k - 1) - prefix_bits
+        shift = 12 + 2 * (k - 1) - prefix_bits
         prefix = (rec >> np.uint64(shift)).astype(np.int64)
         order = np.argsort(prefix, kind="stable")
-        rec, sid, prefix = rec[order], sid[order], prefix[order]
+        rec, prefix = rec[order], prefix[order]
         off = np.searchsorted(prefix, np.arange((1 << prefix_bits) + 1)).astype(np.uint64)
-        return torch.from_numpy(rec.view(np.int64)), torch.from_numpy(sid), off
+        return torch.from_numpy(rec.view(np.int64)), off
 
     def n_positions(self, samples):
         return sum(len(r) for recs in samples for r in recs)
 
-    def prefix_bits(self, n_records_total, k):
+    def prefix_bits(self, n_records_total, k, n_samples_total):
         return min(6, 2 * (k - 1))
 
-    def merge(self, rec, sid, run_offsets, bucket_lo, bucket_hi, prefix_bits, n_samples_total, k, rc, names):
+    def merge(self, rec, run_offsets, bucket_lo, bucket_hi, prefix_bits, n_samples_total, k, rc, names):
         rec = rec.numpy().view(np.uint64)
-        sid = sid.numpy()
         # the exchange plan must describe the receive buffer exactly: every run sorted by prefix, buckets in range
-        shift = 4 + 2 * (k - 1) - prefix_bits
+        shift = 12 + 2 * (k - 1) - prefix_bits
         nb = bucket_hi - bucket_lo
         assert run_offsets.shape[1] == nb + 1
         for r in range(run_offsets.shape[0]):
@@ -112,11 +110,11 @@ class OracleBackend:
                 seg = rec[int(run_offsets[r, j]):int(run_offsets[r, j + 1])]
                 assert np.all((seg >> np.uint64(shift)) == np.uint64(bucket_lo + j))
         assert int(run_offsets[-1, -1]) == len(rec)
-        keys = sorted(set(int(r) >> 4 for r in rec))
+        keys = sorted(set(int(r) >> 12 for r in rec))
         row = {key: i for i, key in enumerate(keys)}
         mask = np.zeros((len(keys), n_samples_total), dtype=np.uint8)
-        for r, s in zip(rec, sid):
-            mask[row[int(r) >> 4], int(s)] |= int(r) & 0xF
+        for r in rec:
+            mask[row[int(r) >> 12], (int(r) >> 4) & 0xFF] |= int(r) & 0xF
         var = LETTERS[mask]
         for i, key in enumerate(keys):
             if rc and revcomp_key(key, k - 1) == key:
