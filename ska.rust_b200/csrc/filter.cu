@@ -134,6 +134,10 @@ struct RowState {
             if (!ignore_gaps) { if (first == 0xFFFFFFFFu) first = '-'; else differs |= (first != '-'); }
             return;
         }
+        if (first < 256u && first != '-' && w == first * 0x01010101u) {            // four copies of the row's first value: nothing new
+            good += 4u * (lut[first] >> 17);
+            return;
+        }
 #pragma unroll
         for (int q = 0; q < 4; q++) byte((w >> (8 * q)) & 0xFFu);
     }

@@ -135,26 +135,52 @@ bucket_count_kernel(const uint64_t* __restrict__ rec, const Item* __restrict__ i
     }
 }
 
-// exclusive scan of n u32 counts into u64 offsets (single CTA; n is at most a few million)
-__global__ void scan_counts_kernel(const uint32_t* __restrict__ cnt, uint32_t n, uint64_t* __restrict__ off,
-                                   uint32_t* __restrict__ max_out) {
-    __shared__ uint64_t s_sum[1024];
-    __shared__ uint32_t s_max[1024];
-    const uint32_t t = threadIdx.x, T = blockDim.x;
-    const uint32_t per = (n + T - 1) / T;
-    const uint32_t b = min(n, t * per), e = min(n, b + per);
-    uint64_t sum = 0; uint32_t mx = 0;
-    for (uint32_t i = b; i < e; i++) { sum += cnt[i]; mx = max(mx, cnt[i]); }
-    s_sum[t] = sum; s_max[t] = mx;
+// exclusive scan of n u32 counts into u64 offsets (single CTA; n is at most a few million).  Coalesced:
+// the CTA walks tiles of 1024 x 4 elements, scans each with warp shuffles and carries the running total.
+__global__ void __launch_bounds__(1024)
+scan_counts_kernel(const uint32_t* __restrict__ cnt, uint32_t n, uint64_t* __restrict__ off, uint32_t* __restrict__ max_out) {
+    __shared__ uint64_t s_warp[32];
+    __shared__ uint64_t s_carry;
+    __shared__ uint32_t s_max[32];
+    const uint32_t t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    if (t == 0) s_carry = 0;
+    uint32_t mx = 0;
+    __syncthreads();
+    for (uint32_t base = 0; base < n; base += 4096) {
+        uint32_t v[4]; uint64_t sum = 0;
+#pragma unroll
+        for (int j = 0; j < 4; j++) { uint32_t i = base + 4 * t + j; v[j] = i < n ? cnt[i] : 0u; sum += v[j]; mx = max(mx, v[j]); }
+        uint64_t inc = sum;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { uint64_t u = __shfl_up_sync(0xFFFFFFFFu, inc, o); if (lane >= (uint32_t)o) inc += u; }
+        if (lane == 31) s_warp[warp] = inc;
+        __syncthreads();
+        if (warp == 0) {
+            uint64_t w = s_warp[lane], winc = w;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { uint64_t u = __shfl_up_sync(0xFFFFFFFFu, winc, o); if (lane >= (uint32_t)o) winc += u; }
+            s_warp[lane] = winc - w;                         // exclusive prefix of the warp totals
+        }
+        __syncthreads();
+        const uint64_t carry = s_carry;
+        uint64_t run = carry + s_warp[warp] + (inc - sum);
+#pragma unroll
+        for (int j = 0; j < 4; j++) { uint32_t i = base + 4 * t + j; if (i < n) off[i] = run; run += v[j]; }
+        __syncthreads();
+        if (t == 1023) s_carry = run;                        // thread 1023 holds the tile's inclusive total
+        __syncthreads();
+    }
+    // maximum
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = max(mx, __shfl_xor_sync(0xFFFFFFFFu, mx, o));
+    if (lane == 0) s_max[warp] = mx;
     __syncthreads();
     if (t == 0) {
-        uint64_t run = 0; uint32_t m = 0;
-        for (uint32_t i = 0; i < T; i++) { uint64_t v = s_sum[i]; s_sum[i] = run; run += v; m = max(m, s_max[i]); }
-        off[n] = run; *max_out = m;
+        uint32_t m = 0;
+        for (int w = 0; w < 32; w++) m = max(m, s_max[w]);
+        *max_out = m;
+        off[n] = s_carry;
     }
-    __syncthreads();
-    uint64_t run = s_sum[t];
-    for (uint32_t i = b; i < e; i++) { off[i] = run; run += cnt[i]; }
 }
 
 void launch_scan_counts(const uint32_t* cnt, uint32_t n, uint64_t* off, uint32_t* max_out) {

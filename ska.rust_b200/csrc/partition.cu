@@ -197,28 +197,51 @@ part_scatter_kernel(const uint64_t* __restrict__ src, uint64_t n_total, const ui
 }
 
 // ---------------------------------------------------------------------------------------------- small helpers
-// exclusive scan of u64 counts -> offsets[n+1]; also cursors[i] = offsets[i]; single CTA
-__global__ void part_scan_kernel(const unsigned long long* __restrict__ cnt, uint32_t n, uint64_t* __restrict__ off,
-                                 unsigned long long* __restrict__ cursor, uint64_t* __restrict__ tile_pref /* may be null */) {
-    __shared__ uint64_t s_sum[1024], s_tiles[1024];
-    const uint32_t t = threadIdx.x, T = blockDim.x;
-    const uint32_t per = (n + T - 1) / T, b = min(n, t * per), e = min(n, b + per);
-    uint64_t sum = 0, tiles = 0;
-    for (uint32_t i = b; i < e; i++) { sum += cnt[i]; tiles += (cnt[i] + PT_TILE - 1) / PT_TILE; }
-    s_sum[t] = sum; s_tiles[t] = tiles;
+// exclusive scan of u64 counts -> offsets[n+1]; also cursors[i] = offsets[i] and, for the second level, the
+// number of tiles before every region.  Single CTA, coalesced tiles of 1024 x 4 elements.
+__global__ void __launch_bounds__(1024)
+part_scan_kernel(const unsigned long long* __restrict__ cnt, uint32_t n, uint64_t* __restrict__ off,
+                 unsigned long long* __restrict__ cursor, uint64_t* __restrict__ tile_pref /* may be null */) {
+    __shared__ uint64_t s_warp[2][32];
+    __shared__ uint64_t s_carry[2];
+    const uint32_t t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    if (t < 2) s_carry[t] = 0;
     __syncthreads();
-    if (t == 0) {
-        uint64_t run = 0, trun = 0;
-        for (uint32_t i = 0; i < T; i++) { uint64_t v = s_sum[i]; s_sum[i] = run; run += v; uint64_t w = s_tiles[i]; s_tiles[i] = trun; trun += w; }
-        off[n] = run;
-        if (tile_pref) tile_pref[n] = trun;
+    for (uint32_t base = 0; base < n; base += 4096) {
+        uint64_t v[4], tl[4], sum = 0, tsum = 0;
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            uint32_t i = base + 4 * t + j;
+            v[j] = i < n ? cnt[i] : 0ull; tl[j] = (v[j] + PT_TILE - 1) / PT_TILE;
+            sum += v[j]; tsum += tl[j];
+        }
+        uint64_t inc = sum, tinc = tsum;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            uint64_t u = __shfl_up_sync(0xFFFFFFFFu, inc, o), w = __shfl_up_sync(0xFFFFFFFFu, tinc, o);
+            if (lane >= (uint32_t)o) { inc += u; tinc += w; }
+        }
+        if (lane == 31) { s_warp[0][warp] = inc; s_warp[1][warp] = tinc; }
+        __syncthreads();
+        if (warp < 2) {
+            uint64_t w = s_warp[warp][lane], winc = w;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { uint64_t u = __shfl_up_sync(0xFFFFFFFFu, winc, o); if (lane >= (uint32_t)o) winc += u; }
+            s_warp[warp][lane] = winc - w;
+        }
+        __syncthreads();
+        uint64_t run = s_carry[0] + s_warp[0][warp] + (inc - sum), trun = s_carry[1] + s_warp[1][warp] + (tinc - tsum);
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            uint32_t i = base + 4 * t + j;
+            if (i < n) { off[i] = run; if (cursor) cursor[i] = run; if (tile_pref) tile_pref[i] = trun; }
+            run += v[j]; trun += tl[j];
+        }
+        __syncthreads();
+        if (t == 1023) { s_carry[0] = run; s_carry[1] = trun; }
+        __syncthreads();
     }
-    __syncthreads();
-    uint64_t run = s_sum[t], trun = s_tiles[t];
-    for (uint32_t i = b; i < e; i++) {
-        off[i] = run; if (cursor) cursor[i] = run; if (tile_pref) tile_pref[i] = trun;
-        run += cnt[i]; trun += (cnt[i] + PT_TILE - 1) / PT_TILE;
-    }
+    if (t == 0) { off[n] = s_carry[0]; if (tile_pref) tile_pref[n] = s_carry[1]; }
 }
 
 static size_t scatter_smem(int bits) {
