@@ -167,9 +167,12 @@ static std::unique_ptr<Array> build_from_batch(const SeqBatch& b, uint32_t k, bo
     Context& c = ctx();
     check_k(k);
     if (k > 31) throw Error("k > 31 (128-bit split k-mers) is not yet built on the device; use k <= 31");
-    if (b.has_qual) throw Error("FASTQ input (count/bloom filter, K2q) is not yet built on the device");
-    (void)min_count; (void)qual_filter;
     arena().reset();
+    if (b.has_qual) {                                              // reads: quality masks + count filter (k1q_reads.cu)
+        std::unique_ptr<Array> a(new Array());
+        build_array_from_reads(b, k, rc, min_count, min_qual, qual_filter, *a);
+        return a;
+    }
     uint64_t* rec = arena().take_n<uint64_t>(b.n_pos);
     uint32_t* valid = arena().take_n<uint32_t>(b.n_samples);
     SKA_CUDA(cudaMemsetAsync(valid, 0, b.n_samples * 4, c.stream));
@@ -179,7 +182,7 @@ static std::unique_ptr<Array> build_from_batch(const SeqBatch& b, uint32_t k, bo
     std::vector<uint32_t> h_valid(b.n_samples);
     SKA_CUDA(cudaMemcpyAsync(h_valid.data(), valid, b.n_samples * 4, cudaMemcpyDeviceToHost, c.stream));
     std::unique_ptr<Array> a(new Array());
-    build_array_from_records(rec, b, 0, b.n_samples, k, rc, *a);   // synchronises the stream
+    build_array_from_records(rec, b.n_pos, b.sample_off.p, (uint32_t)b.n_samples, 0, b.n_samples, k, rc, *a);   // synchronises
     for (size_t s = 0; s < b.n_samples; s++)
         if (h_valid[s] == 0) throw Error("sample " + std::to_string(s) + " has no valid sequence");   // ska_dict.rs:374-376
     return a;

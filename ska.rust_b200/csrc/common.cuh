@@ -138,9 +138,12 @@ PartPlan make_part_plan(uint32_t k, int prefix_bits, uint64_t n_samples_total);
 void partition_records(const uint64_t* rec, uint64_t n_pos, const uint64_t* d_sample_off, uint32_t n_samples_local, uint32_t sid_base,
                        const PartPlan& pl, uint64_t* scratch, uint64_t** out, uint64_t** d_off);
 // merge.cu
-// K1 records (linear, one per position of `b`) -> array; sample ids are sid_base + local index
-void build_array_from_records(uint64_t* rec, const SeqBatch& b, uint32_t sid_base, uint64_t n_samples_total, uint32_t k, bool rc,
-                              Array& out);
+// K1 records (n_rec entries; sample s owns entries [sample_off[s], sample_off[s+1]); REC_SENTINEL entries are
+// skipped) -> array; sample ids are sid_base + local index.  `rec` is overwritten (partition scratch).
+void build_array_from_records(uint64_t* rec, uint64_t n_rec, const uint64_t* d_sample_off, uint32_t n_samples_local, uint32_t sid_base,
+                              uint64_t n_samples_total, uint32_t k, bool rc, Array& out);
+// k1q_reads.cu: FASTQ samples (quality masks, ntHash, exact count-filter emulation) -> array
+void build_array_from_reads(const SeqBatch& b, uint32_t k, bool rc, uint16_t min_count, uint8_t min_qual, int qual_filter, Array& out);
 // row shard: `n_runs` received runs of packed records, each grouped by the same plan over buckets [lo, hi)
 void build_array_from_runs(const uint64_t* prec, int n_runs, const uint64_t* run_off, uint32_t bucket_lo, uint32_t bucket_hi,
                            const PartPlan& pl, uint64_t n_samples, uint32_t k, bool rc, Array& out);

@@ -116,30 +116,41 @@ __device__ __forceinline__ uint32_t class_entry(uint32_t b) {
     bool amb = is_ambig_dev(b);
     return (bit < 32 ? 1u << bit : 0u) | (amb ? 1u << 16 : 0u) | ((b != '-' && !amb) ? 1u << 17 : 0u);
 }
+// bit 7 of every byte of the result is set iff that byte of x equals the byte c (exact, no carries between bytes)
+__device__ __forceinline__ uint32_t eq_bytes(uint32_t x, uint32_t c4) {
+    uint32_t t = x ^ c4;
+    return ~(((t & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | t) & 0x80808080u;
+}
+// Row classification state.  Values are tracked as a SET: bits 0-10 for the eleven byte values that matter to
+// the filters (A C G T U a c g t u -), plus the first byte value outside that set and whether a second,
+// different one was seen -- enough to answer "more than one distinct value" without per-byte branches.
 struct RowState {
-    uint32_t good, any_ambig, setbits, first, differs, ignore_gaps;
+    uint32_t good, any_ambig, setbits, other_first, other_differs;
     const uint32_t* lut;
     __device__ __forceinline__ void byte(uint32_t b) {
         uint32_t e = lut[b];
         any_ambig |= e >> 16 & 1u;
         good += e >> 17;
         setbits |= e & 0x7FFu;
-        if (!ignore_gaps || b != '-') {
-            if (first == 0xFFFFFFFFu) first = b; else differs |= (b != first);
-        }
+        if (!(e & 0x7FFu)) { if (other_first == 0xFFFFFFFFu) other_first = b; else other_differs |= (b != other_first); }
     }
     __device__ __forceinline__ void word(uint32_t w) {
-        if (w == 0x2D2D2D2Du) {                                    // four gaps: the common case in sparse rows
-            setbits |= 1u << 10;
-            if (!ignore_gaps) { if (first == 0xFFFFFFFFu) first = '-'; else differs |= (first != '-'); }
-            return;
-        }
-        if (first < 256u && first != '-' && w == first * 0x01010101u) {            // four copies of the row's first value: nothing new
-            good += 4u * (lut[first] >> 17);
+        // branch-free for words made of A, C, G, T and '-' (every lane of the warp is a different row, so a
+        // data-dependent branch here would make the whole warp pay for the slowest row)
+        const uint32_t a = eq_bytes(w, 0x41414141u), c = eq_bytes(w, 0x43434343u), g = eq_bytes(w, 0x47474747u),
+                       t = eq_bytes(w, 0x54545454u), gap = eq_bytes(w, 0x2D2D2D2Du);
+        const uint32_t acgt = a | c | g | t;
+        if ((acgt | gap) == 0x80808080u) {
+            good += __popc(acgt);
+            setbits |= (a ? 1u : 0u) | (c ? 2u : 0u) | (g ? 4u : 0u) | (t ? 8u : 0u) | (gap ? 1u << 10 : 0u);
             return;
         }
 #pragma unroll
-        for (int q = 0; q < 4; q++) byte((w >> (8 * q)) & 0xFFu);
+        for (int q = 0; q < 4; q++) byte((w >> (8 * q)) & 0xFFu);     // IUPAC codes, lower case, U: rare
+    }
+    __device__ __forceinline__ bool nonconst(bool ignore_gaps) const {
+        uint32_t n = __popc(setbits & (ignore_gaps ? 0x3FFu : 0x7FFu)) + (other_first != 0xFFFFFFFFu) + (other_differs != 0);
+        return n > 1;
     }
 };
 
@@ -156,7 +167,7 @@ filter_flags_rows_kernel(const uint8_t* __restrict__ var, const uint32_t* __rest
     bool keep1 = false, keep2 = false;
     if (r < n_rows) {
         const uint4* row = reinterpret_cast<const uint4*>(var + r * n_samples);
-        RowState st = {0, 0, 0, 0xFFFFFFFFu, 0, (uint32_t)ignore_gaps, s_lut};
+        RowState st = {0, 0, 0, 0xFFFFFFFFu, 0, s_lut};
         const uint32_t n16 = n_samples >> 4;
         for (uint32_t c0 = 0; c0 < n16; c0 += 8) {
             uint4 v[8];
@@ -173,7 +184,7 @@ filter_flags_rows_kernel(const uint8_t* __restrict__ var, const uint32_t* __rest
         if (keep1 && (uint64_t)count >= min_count) {
             switch (ftype) {
                 case 0: keep2 = true; break;
-                case 1: keep2 = st.differs != 0; break;
+                case 1: keep2 = st.nonconst(ignore_gaps != 0); break;
                 case 2: keep2 = !st.any_ambig; break;
                 default: keep2 = __popc(st.setbits & (ignore_gaps ? 0x3FFu : 0x7FFu)) > 1;
             }

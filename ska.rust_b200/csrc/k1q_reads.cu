@@ -1,0 +1,393 @@
+// k1q_reads.cu -- the FASTQ path of `ska build` on the device (K1q + K2q): quality masks, ntHash, and an
+// EXACT emulation of the reference's sequential count filter (blocked bloom + counts table).
+//
+// Replaces, for read input: SplitKmer's quality tests (src/ska_dict/split_kmer.rs:66-71, 98-101, 328-339),
+// NtHashIterator (src/ska_dict/nthash.rs:12-77), KmerFilter (src/ska_dict/bloom_filter.rs:35-148) and the
+// `middle_base_qual() && filter()==Equal` gate of SkaDict::add_file_kmers (src/ska_dict.rs:155-177).
+//
+// The reference filter is stateful and order dependent: an observation (a window whose middle base passes
+// the quality test) is looked up in a 24 MiB blocked bloom filter; a bloom hit moves it to an exact counts
+// table, and the split k-mer is inserted at the moment its count reaches min_count.  A k-mer whose FIRST
+// observation is a bloom false positive is counted one higher.  Batch form, per sample:
+//   observations in stream order (file 1 then file 2 == position order of the batch), hash = ntHash1
+//   (canonical), K = cheap_mix(hash) (a bijection, so grouping by K groups by hash AND orders by bloom word,
+//   word = (K * 3145728) >> 64);  for each distinct K: c = #observations, t = first position;
+//   FP(K) = fingerprint(hash) is covered by the OR of the fingerprints of the distinct hashes of the same
+//   word with smaller t;   observation number j (1-based, stream order) of K is inserted iff
+//     min_count == 2 :  j >= 2 or FP            min_count >= 3 :  min(j + FP, 65535) == min_count and (j >= 2 or FP)
+// Steps: (1) k1q_kernel<OBS>: per window validity (N, optional strict quality, record ends), middle-base
+// quality, ntHash by a prefix-XOR scan (the hash is a XOR of rotated per-base constants, so
+// fh(s) = rotl(G(s+k)^G(s), s+k-1) for the prefix G of rotr(H[e_j], j); no sequential roll); (2) stable radix sort
+// of (K, position) -- cub::DeviceRadixSort, library scaffolding; (3) runs -> distinct entries (word, t); sort
+// by (word, t); one thread walks each bloom word's entries in t order OR-ing fingerprints -> FP; (4) the
+// accepted observations set bits in a per-position accept mask; (5) k1q_kernel<EMIT> recomputes the split
+// k-mer of every accepted position and writes compacted records, which then take the normal
+// partition + merge path (partition.cu, merge.cu).  min_count <= 1 skips (2)-(4): every observation is accepted.
+#include <cub/cub.cuh>
+
+#include "k1_helpers.cuh"
+
+namespace ska {
+
+enum { RQ_MASK = 0, RQ_OBS = 1, RQ_EMIT = 2 };
+constexpr uint64_t BLOOM_WORDS = 3145728;                     // bloom_filter.rs:15-20,93-96
+constexpr uint64_t MIX_MUL = 0x85D059AA333121CFULL;           // bloom_filter.rs:56-58
+constexpr uint64_t MIX_INV = 0x756DE8DBB3C2452FULL;           // MIX_MUL^-1 mod 2^64
+
+__device__ __forceinline__ uint64_t rotl64(uint64_t x, uint32_t r) { r &= 63u; return r ? (x << r) | (x >> (64u - r)) : x; }
+__device__ __forceinline__ uint64_t rotr64(uint64_t x, uint32_t r) { r &= 63u; return r ? (x >> r) | (x << (64u - r)) : x; }
+__device__ __forceinline__ uint64_t nt_seed(uint32_t e) {     // nthash.rs:12-17, index = 2-bit code A C T G
+    return e == 0 ? 0x3c8bfbb395c60474ULL : e == 1 ? 0x3193c18562a02b4cULL : e == 2 ? 0x295549f54be24456ULL : 0x20323ed082572324ULL;
+}
+__device__ __forceinline__ uint64_t cheap_mix(uint64_t h) { return (h ^ (h >> 31)) * MIX_MUL; }
+__device__ __forceinline__ uint64_t cheap_unmix(uint64_t k) { uint64_t x = k * MIX_INV; return x ^ (x >> 31) ^ (x >> 62); }
+__device__ __forceinline__ uint32_t bloom_word(uint64_t mixed) { return (uint32_t)__umul64hi(mixed, BLOOM_WORDS); }   // bloom_filter.rs:50-52,72-74
+__device__ __forceinline__ uint64_t fingerprint(uint64_t h) {                                                          // bloom_filter.rs:62-68
+    return 1ULL << (h & 63) | 1ULL << ((h >> 6) & 63) | 1ULL << ((h >> 12) & 63) | 1ULL << ((h >> 18) & 63) | 1ULL << ((h >> 24) & 63);
+}
+
+// One tile of K1_T window-start positions of ONE sample's position range [lo, hi).  mask words are indexed
+// from the first tile of the sample (tile0): word (p - tile0*K1_T) / 32.
+template <int MODE>
+__global__ void __launch_bounds__(K1_THREADS)
+k1q_kernel(const uint8_t* __restrict__ seq, const uint8_t* __restrict__ qual, const uint32_t* __restrict__ start_bits,
+           uint64_t lo, uint64_t hi, uint64_t tile0, int k, int rc, uint32_t min_qual, int qmode,
+           uint32_t* __restrict__ mask, uint64_t* __restrict__ obs_key, uint32_t* __restrict__ obs_pos,
+           unsigned long long* __restrict__ n_obs, const uint64_t* __restrict__ tile_off, uint64_t* __restrict__ rec_c) {
+    __shared__ __align__(128) uint8_t s_ascii[K1_BYTES];
+    __shared__ __align__(128) uint8_t s_qual[K1_BYTES];
+    __shared__ uint32_t s_le[2 * K1_G32 + 2];
+    __shared__ uint32_t s_be[2 * K1_G32 + 2];
+    __shared__ uint32_t s_bad[K1_G32];
+    __shared__ uint32_t s_qbad[K1_G32];
+    __shared__ uint32_t s_start[K1_G32];
+    __shared__ uint32_t s_ok[K1_T / 32];
+    __shared__ uint32_t s_pre[K1_T / 32 + 1];
+    __shared__ __align__(8) uint64_t s_mbar;
+    __shared__ uint64_t s_wx[8], s_wy[8];
+    __shared__ uint32_t s_nobs;
+    extern __shared__ __align__(16) uint8_t dyn[];                    // OBS: GX[K1_BYTES + 1], GY[K1_BYTES + 1]
+
+    const int tid = threadIdx.x;
+    const uint64_t tile = tile0 + blockIdx.x;
+    const uint64_t t0 = tile * K1_T;
+    if (tid == 0) { mbar_init(&s_mbar, 1); s_nobs = 0; }
+    __syncthreads();
+    if (tid == 0) {
+        mbar_expect_tx(&s_mbar, 2 * K1_BYTES);
+        tma_load_1d(s_ascii, seq + FRONT_PAD + t0 - K1_LEAD, K1_BYTES, &s_mbar);
+        tma_load_1d(s_qual, qual + FRONT_PAD + t0 - K1_LEAD, K1_BYTES, &s_mbar);
+    }
+    if (tid < K1_G32) s_start[tid] = start_bits[(t0 + FRONT_PAD - K1_LEAD) / 32 + tid];
+    mbar_wait(&s_mbar, 0);
+
+    // ---- pack bases and the two masks: invalid base (N; + low quality when strict) and low quality
+    for (int g = tid; g < K1_G32; g += K1_THREADS) {
+        const uint4* src = reinterpret_cast<const uint4*>(s_ascii + 32 * g);
+        const uint4* qs = reinterpret_cast<const uint4*>(s_qual + 32 * g);
+        uint4 a = src[0], b = src[1], qa = qs[0], qb = qs[1];
+        uint32_t w[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+        uint32_t q[8] = {qa.x, qa.y, qa.z, qa.w, qb.x, qb.y, qb.z, qb.w};
+        uint32_t le0 = 0, le1 = 0, bad = 0, qbad = 0;
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            le0 |= pack4(w[i]) << (8 * i);
+            le1 |= pack4(w[4 + i]) << (8 * i);
+            bad |= bad4(w[i]) << (4 * i);
+            bad |= bad4(w[4 + i]) << (16 + 4 * i);
+        }
+#pragma unroll
+        for (int i = 0; i < 8; i++) qbad |= badq4(q[i], min_qual) << (4 * i);
+        if (qmode == 2) bad |= qbad;                                  // QualFilter::Strict (split_kmer.rs:98-101)
+        s_le[2 * g] = le0; s_le[2 * g + 1] = le1;
+        s_be[2 * g] = le_to_be(le0); s_be[2 * g + 1] = le_to_be(le1);
+        s_bad[g] = bad; s_qbad[g] = qbad;
+    }
+    if (tid < 2) { s_le[2 * K1_G32 + tid] = 0; s_be[2 * K1_G32 + tid] = 0; }
+    __syncthreads();
+
+    // ---- window validity + middle-base quality (split_kmer.rs:328-339) + the sample's own position range
+    const int h = (k - 1) >> 1;
+    if (tid < K1_T / 32) {
+        const int j = tid;
+        B128 bad = {(uint64_t)s_bad[j] | ((uint64_t)s_bad[j + 1] << 32), (uint64_t)s_bad[j + 2] | ((uint64_t)s_bad[j + 3] << 32)};
+        B128 st = {(uint64_t)s_start[j] | ((uint64_t)s_start[j + 1] << 32), (uint64_t)s_start[j + 2] | ((uint64_t)s_start[j + 3] << 32)};
+        B128 bad_any = slide_or(bad, k);
+        B128 st_any = shr128(slide_or(st, k - 1), 1);
+        B128 bad_prev = {bad.lo << 1, (bad.hi << 1) | (bad.lo >> 63)};
+        B128 run_start = or128(st, bad_prev);
+        B128 rec_end = shr128(st, k);
+        uint64_t not_ok = bad_any.lo | st_any.lo | (run_start.lo & rec_end.lo);
+        if (qmode != 0) {                                             // Middle or Strict: quality of base s + h
+            B128 qb = {(uint64_t)s_qbad[j] | ((uint64_t)s_qbad[j + 1] << 32), (uint64_t)s_qbad[j + 2] | ((uint64_t)s_qbad[j + 3] << 32)};
+            not_ok |= shr128(qb, h).lo;
+        }
+        uint32_t ok = ~(uint32_t)(not_ok >> 32);
+        const uint64_t p0 = t0 + 32ull * j;                           // keep positions in [lo, hi)
+        if (p0 + 32 <= lo || p0 >= hi) ok = 0;
+        else {
+            if (p0 < lo) ok &= ~((1u << (uint32_t)(lo - p0)) - 1u);
+            if (p0 + 32 > hi) ok &= (1u << (uint32_t)(hi - p0)) - 1u;
+        }
+        if (MODE == RQ_EMIT) ok &= mask[blockIdx.x * (K1_T / 32) + j];   // accepted observations only
+        s_ok[j] = ok;
+        s_pre[j] = __popc(ok);
+        if (MODE == RQ_MASK && ok) atomicOr(&mask[blockIdx.x * (K1_T / 32) + j], ok);   // tiles at sample borders are shared
+    }
+    __syncthreads();
+    if (MODE == RQ_MASK) return;
+
+    const int lane = tid & 31, warp = tid >> 5;
+    if (MODE == RQ_OBS) {
+        // ---- ntHash by prefix XOR: X[r] = rotr(H[e_r], r), Y[r] = rotl(H[e_r ^ 2], r) over staged indices r
+        uint64_t* GX = reinterpret_cast<uint64_t*>(dyn);
+        uint64_t* GY = GX + K1_BYTES + 1;
+        constexpr int PER = (K1_BYTES + K1_THREADS - 1) / K1_THREADS;     // 17
+        const int r0 = tid * PER;
+        uint64_t xs[PER], ys[PER], tx = 0, ty = 0;
+#pragma unroll
+        for (int i = 0; i < PER; i++) {
+            const int r = r0 + i;
+            uint64_t x = 0, y = 0;
+            if (r < K1_BYTES) {
+                const uint32_t e = (s_le[r >> 4] >> (2 * (r & 15))) & 3u;
+                x = rotr64(nt_seed(e), (uint32_t)r);
+                y = rotl64(nt_seed(e ^ 2u), (uint32_t)r);
+            }
+            xs[i] = tx; ys[i] = ty;                                   // exclusive prefix inside the thread
+            tx ^= x; ty ^= y;
+        }
+        uint64_t ix = tx, iy = ty;                                    // inclusive XOR scan over the warp
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            uint64_t ux = __shfl_up_sync(0xFFFFFFFFu, ix, o), uy = __shfl_up_sync(0xFFFFFFFFu, iy, o);
+            if (lane >= o) { ix ^= ux; iy ^= uy; }
+        }
+        if (lane == 31) { s_wx[warp] = ix; s_wy[warp] = iy; }
+        __syncthreads();
+        uint64_t bx = ix ^ tx, by = iy ^ ty;                          // exclusive prefix of this thread within the warp
+        for (int w = 0; w < warp; w++) { bx ^= s_wx[w]; by ^= s_wy[w]; }
+#pragma unroll
+        for (int i = 0; i < PER; i++) {
+            const int r = r0 + i;
+            if (r <= K1_BYTES) { GX[r] = bx ^ xs[i]; GY[r] = by ^ ys[i]; }
+        }
+        __syncthreads();
+        uint32_t mine = 0;
+        for (int j = warp; j < K1_T / 32; j += K1_THREADS / 32) {
+            const uint64_t p = t0 + 32ull * j + lane;
+            if (p < lo || p >= hi) continue;
+            const int r = K1_LEAD + 32 * j + lane;
+            uint64_t key = ~0ULL; uint32_t pos = 0xFFFFFFFFu;
+            if ((s_ok[j] >> lane) & 1u) {
+                const uint64_t fh = rotl64(GX[r + k] ^ GX[r], (uint32_t)(r + k - 1));   // nthash.rs:35-41
+                uint64_t hash = fh;
+                if (rc) { const uint64_t rh = rotr64(GY[r + k] ^ GY[r], (uint32_t)r); hash = min(fh, rh); }   // nthash.rs:43-52,70-76
+                key = cheap_mix(hash);
+                pos = (uint32_t)(p - tile0 * K1_T);
+                mine++;
+            }
+            obs_key[p - lo] = key;
+            obs_pos[p - lo] = pos;
+        }
+        if (mine) atomicAdd(&s_nobs, mine);
+        __syncthreads();
+        if (tid == 0 && s_nobs) atomicAdd(n_obs, (unsigned long long)s_nobs);
+        return;
+    }
+
+    // ---- RQ_EMIT: split k-mer of every accepted position, compacted
+    if (tid == 0) { uint32_t run = 0; for (int j = 0; j < K1_T / 32; j++) { uint32_t c = s_pre[j]; s_pre[j] = run; run += c; } s_pre[K1_T / 32] = run; }
+    __syncthreads();
+    const uint64_t mask2k = (1ULL << (2 * k)) - 1ULL;
+    const uint64_t lm = (1ULL << (2 * h)) - 1ULL;
+    const uint64_t aa = 0xAAAAAAAAAAAAAAAAULL & mask2k;
+    const int sh = 2 * (lane & 15);
+    const uint32_t* be = s_be + ((K1_LEAD + lane) >> 4);
+    const uint32_t* le = s_le + ((K1_LEAD + lane) >> 4);
+    uint64_t* out = rec_c + tile_off[blockIdx.x];
+    for (int j = warp; j < K1_T / 32; j += K1_THREADS / 32) {
+        const uint32_t ok = s_ok[j];
+        if (!((ok >> lane) & 1u)) continue;
+        const uint32_t b0 = be[2 * j], b1 = be[2 * j + 1], b2 = be[2 * j + 2];
+        const uint64_t top = ((uint64_t)__funnelshift_l(b1, b0, sh) << 32) | __funnelshift_l(b2, b1, sh);
+        const uint64_t F = top >> (64 - 2 * k);
+        uint64_t key = (F & lm) | ((F >> 2) & ~lm);
+        uint32_t mid = (uint32_t)(F >> (2 * h)) & 3u;
+        if (rc) {
+            const uint32_t l0 = le[2 * j], l1 = le[2 * j + 1], l2 = le[2 * j + 2];
+            const uint64_t V = (((uint64_t)__funnelshift_r(l1, l2, sh) << 32) | __funnelshift_r(l0, l1, sh)) & mask2k;
+            const uint64_t R = V ^ aa;
+            const uint64_t rkey = (R & lm) | ((R >> 2) & ~lm);
+            if (key > rkey) { key = rkey; mid ^= 2u; }
+        }
+        out[s_pre[j] + __popc(ok & ((1u << lane) - 1u))] = (key << 4) | (1ull << mid);
+    }
+}
+
+// accepted windows per tile (popcount of the tile's 128 mask words)
+__global__ void tile_popc_kernel(const uint32_t* __restrict__ mask, uint32_t n_tiles, uint32_t* __restrict__ cnt) {
+    const uint32_t tile = blockIdx.x * (blockDim.x / 32) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (tile >= n_tiles) return;
+    uint32_t c = 0;
+    for (int j = lane; j < K1_T / 32; j += 32) c += __popc(mask[(size_t)tile * (K1_T / 32) + j]);
+    c = __reduce_add_sync(0xFFFFFFFFu, c);
+    if (lane == 0) cnt[tile] = c;
+}
+
+// runs of equal K in the sorted observations -> one distinct entry each: key (word << 32 | first position),
+// value (run start << 32 | min(run length, 2^32 - 1)).  Stable sort => the first element of a run is the earliest.
+__global__ void q_runs_kernel(const uint64_t* __restrict__ K, const uint32_t* __restrict__ pos, uint64_t n_obs,
+                              uint64_t* __restrict__ dkey, uint64_t* __restrict__ dval, unsigned long long* __restrict__ n_distinct) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_obs) return;
+    const uint64_t key = K[i];
+    if (i > 0 && K[i - 1] == key) return;
+    uint64_t c = 1;
+    while (i + c < n_obs && K[i + c] == key) c++;
+    const unsigned long long d = atomicAdd(n_distinct, 1ULL);
+    dkey[d] = ((uint64_t)bloom_word(key) << 32) | pos[i];
+    dval[d] = (i << 32) | (c > 0xFFFFFFFFULL ? 0xFFFFFFFFULL : c);
+}
+
+// entries sorted by (word, first position): the thread at the head of a word's segment replays that word
+// of the bloom filter (bloom_filter.rs:77-86) in first-occurrence order
+__global__ void q_bloom_kernel(const uint64_t* __restrict__ dkey, const uint64_t* __restrict__ dval, const uint64_t* __restrict__ K,
+                               uint64_t n_distinct, uint8_t* __restrict__ fp_flag) {
+    const uint64_t d = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (d >= n_distinct) return;
+    const uint32_t word = (uint32_t)(dkey[d] >> 32);
+    if (d > 0 && (uint32_t)(dkey[d - 1] >> 32) == word) return;
+    uint64_t state = 0;
+    for (uint64_t e = d; e < n_distinct && (uint32_t)(dkey[e] >> 32) == word; e++) {
+        const uint64_t f = fingerprint(cheap_unmix(K[dval[e] >> 32]));
+        const bool seen = (state & f) == f;
+        if (!seen) state |= f;
+        fp_flag[e] = seen;
+    }
+}
+
+// which observations of every distinct k-mer reach the dictionary (bloom_filter.rs:116-148)
+__global__ void q_accept_kernel(const uint64_t* __restrict__ dval, const uint8_t* __restrict__ fp_flag, const uint32_t* __restrict__ pos,
+                                uint64_t n_distinct, uint32_t min_count, uint32_t* __restrict__ mask) {
+    const uint64_t e = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n_distinct) return;
+    const uint64_t i0 = dval[e] >> 32, c = dval[e] & 0xFFFFFFFFULL;
+    const uint64_t fp = fp_flag[e];
+    uint64_t j_lo, j_hi;                                              // accepted 1-based observation numbers [j_lo, j_hi]
+    if (min_count == 2) { j_lo = fp ? 1 : 2; j_hi = c; }
+    else {
+        j_lo = j_hi = (uint64_t)min_count - fp;                       // count after observation j is j + fp
+        if (min_count == 65535) j_hi = c;                             // saturating_add keeps the count at u16::MAX
+        if (j_lo < 2 - fp) j_lo = 2 - fp;
+    }
+    for (uint64_t j = j_lo; j <= j_hi && j <= c; j++) {
+        const uint32_t p = pos[i0 + j - 1];
+        atomicOr(&mask[p >> 5], 1u << (p & 31));
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ host driver
+struct ArenaMark { std::vector<size_t> used; };
+static ArenaMark arena_mark() { ArenaMark m; for (auto& s : arena().slabs) m.used.push_back(s.used); return m; }
+static void arena_rewind(const ArenaMark& m) {
+    auto& sl = arena().slabs;
+    for (size_t i = 0; i < sl.size(); i++) sl[i].used = i < m.used.size() ? m.used[i] : 0;
+}
+
+void build_array_from_reads(const SeqBatch& b, uint32_t k, bool rc, uint16_t min_count, uint8_t min_qual, int qual_filter, Array& out) {
+    Context& c = ctx();
+    const uint64_t N = b.n_samples;
+    const size_t obs_smem = 2 * (size_t)(K1_BYTES + 1) * 8;
+    SKA_CUDA(cudaFuncSetAttribute(k1q_kernel<RQ_OBS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)obs_smem));
+    std::vector<uint32_t*> masks(N);
+    std::vector<uint64_t*> tile_offs(N);
+    std::vector<uint64_t> n_tiles(N), tile_lo(N), accepted(N);
+    unsigned long long* d_counter = arena().take_n<unsigned long long>(2);
+
+    timer().begin("reads_filter");
+    for (uint64_t s = 0; s < N; s++) {
+        const uint64_t lo = b.h_sample_off[s], hi = b.h_sample_off[s + 1];
+        if (hi == lo) { n_tiles[s] = 0; accepted[s] = 0; continue; }
+        tile_lo[s] = lo / K1_T;
+        n_tiles[s] = (hi - 1) / K1_T - tile_lo[s] + 1;
+        const size_t n_words = n_tiles[s] * (K1_T / 32);
+        masks[s] = arena().take_n<uint32_t>(n_words);
+        SKA_CUDA(cudaMemsetAsync(masks[s], 0, n_words * 4, c.stream));
+        if (min_count <= 1) {                                         // bloom_filter.rs:121: no filtering
+            SKA_LAUNCH(k1q_kernel<RQ_MASK>, (unsigned)n_tiles[s], K1_THREADS, 0, b.seq.p, b.qual.p, b.start_bits.p, lo, hi, tile_lo[s],
+                       (int)k, rc ? 1 : 0, (uint32_t)min_qual, qual_filter, masks[s], (uint64_t*)nullptr, (uint32_t*)nullptr,
+                       (unsigned long long*)nullptr, (const uint64_t*)nullptr, (uint64_t*)nullptr);
+        } else {
+            const ArenaMark mark = arena_mark();
+            const uint64_t n_s = hi - lo;
+            uint64_t* obs_key = arena().take_n<uint64_t>(n_s); uint64_t* obs_key2 = arena().take_n<uint64_t>(n_s);
+            uint32_t* obs_pos = arena().take_n<uint32_t>(n_s); uint32_t* obs_pos2 = arena().take_n<uint32_t>(n_s);
+            SKA_CUDA(cudaMemsetAsync(d_counter, 0, 16, c.stream));
+            SKA_LAUNCH(k1q_kernel<RQ_OBS>, (unsigned)n_tiles[s], K1_THREADS, obs_smem, b.seq.p, b.qual.p, b.start_bits.p, lo, hi, tile_lo[s],
+                       (int)k, rc ? 1 : 0, (uint32_t)min_qual, qual_filter, masks[s], obs_key, obs_pos, d_counter,
+                       (const uint64_t*)nullptr, (uint64_t*)nullptr);
+            // stable sort by K: non-observations carry K = ~0 and end up behind the n_obs real ones
+            cub::DoubleBuffer<uint64_t> dk(obs_key, obs_key2);
+            cub::DoubleBuffer<uint32_t> dv(obs_pos, obs_pos2);
+            size_t tmp_bytes = 0;
+            SKA_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, dk, dv, (int64_t)n_s, 0, 64, c.stream));
+            void* tmp = arena().take(tmp_bytes);
+            SKA_CUDA(cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, dk, dv, (int64_t)n_s, 0, 64, c.stream));
+            c.launches += 9;
+            unsigned long long h_cnt[2];
+            SKA_CUDA(cudaMemcpyAsync(h_cnt, d_counter, 16, cudaMemcpyDeviceToHost, c.stream));
+            SKA_CUDA(cudaStreamSynchronize(c.stream));
+            const uint64_t n_obs = h_cnt[0];
+            if (n_obs) {
+                const uint64_t* K = dk.Current(); const uint32_t* P = dv.Current();
+                uint64_t* dkey = dk.Alternate(); uint64_t* dval = arena().take_n<uint64_t>(n_obs);   // the alternate key buffer is free now
+                SKA_LAUNCH(q_runs_kernel, (unsigned)((n_obs + 255) / 256), 256, 0, K, P, n_obs, dkey, dval, d_counter + 1);
+                SKA_CUDA(cudaMemcpyAsync(h_cnt, d_counter, 16, cudaMemcpyDeviceToHost, c.stream));
+                SKA_CUDA(cudaStreamSynchronize(c.stream));
+                const uint64_t n_d = h_cnt[1];
+                uint64_t* dkey2 = arena().take_n<uint64_t>(n_d); uint64_t* dval2 = arena().take_n<uint64_t>(n_d);
+                cub::DoubleBuffer<uint64_t> ek(dkey, dkey2), ev(dval, dval2);
+                size_t tmp2 = 0;
+                SKA_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp2, ek, ev, (int64_t)n_d, 0, 54, c.stream));
+                void* t2 = arena().take(tmp2);
+                SKA_CUDA(cub::DeviceRadixSort::SortPairs(t2, tmp2, ek, ev, (int64_t)n_d, 0, 54, c.stream));
+                c.launches += 8;
+                uint8_t* fp_flag = arena().take_n<uint8_t>(n_d);
+                SKA_LAUNCH(q_bloom_kernel, (unsigned)((n_d + 255) / 256), 256, 0, ek.Current(), ev.Current(), K, n_d, fp_flag);
+                SKA_LAUNCH(q_accept_kernel, (unsigned)((n_d + 255) / 256), 256, 0, ev.Current(), fp_flag, P, n_d, (uint32_t)min_count, masks[s]);
+            }
+            SKA_CUDA(cudaStreamSynchronize(c.stream));
+            arena_rewind(mark);
+        }
+        // compaction offsets of the accepted windows
+        uint32_t* cnt = arena().take_n<uint32_t>(n_tiles[s]);
+        tile_offs[s] = arena().take_n<uint64_t>(n_tiles[s] + 1);
+        uint32_t* scratch = arena().take_n<uint32_t>(1);
+        SKA_LAUNCH(tile_popc_kernel, (unsigned)((n_tiles[s] + 7) / 8), 256, 0, masks[s], (uint32_t)n_tiles[s], cnt);
+        launch_scan_counts(cnt, (uint32_t)n_tiles[s], tile_offs[s], scratch);
+        SKA_CUDA(cudaMemcpyAsync(&accepted[s], tile_offs[s] + n_tiles[s], 8, cudaMemcpyDeviceToHost, c.stream));
+        SKA_CUDA(cudaStreamSynchronize(c.stream));
+        if (accepted[s] == 0) throw Error("sample " + std::to_string(s) + " has no valid sequence");   // ska_dict.rs:374-376
+    }
+    timer().end();
+
+    // compacted K1 records of the accepted windows, sample after sample
+    timer().begin("k1_extract");
+    std::vector<uint64_t> coff(N + 1, 0);
+    for (uint64_t s = 0; s < N; s++) coff[s + 1] = coff[s] + accepted[s];
+    uint64_t* rec_c = arena().take_n<uint64_t>(std::max<uint64_t>(coff[N], 1));
+    for (uint64_t s = 0; s < N; s++) {
+        if (!n_tiles[s]) continue;
+        SKA_LAUNCH(k1q_kernel<RQ_EMIT>, (unsigned)n_tiles[s], K1_THREADS, 0, b.seq.p, b.qual.p, b.start_bits.p, b.h_sample_off[s],
+                   b.h_sample_off[s + 1], tile_lo[s], (int)k, rc ? 1 : 0, (uint32_t)min_qual, qual_filter, masks[s], (uint64_t*)nullptr,
+                   (uint32_t*)nullptr, (unsigned long long*)nullptr, (const uint64_t*)tile_offs[s], rec_c + coff[s]);
+    }
+    timer().end();
+    uint64_t* d_coff = arena().take_n<uint64_t>(N + 1);
+    SKA_CUDA(cudaMemcpyAsync(d_coff, coff.data(), (N + 1) * 8, cudaMemcpyHostToDevice, c.stream));
+    SKA_CUDA(cudaStreamSynchronize(c.stream));
+    build_array_from_records(rec_c, coff[N], d_coff, (uint32_t)N, 0, N, k, rc, out);
+}
+
+}  // namespace ska

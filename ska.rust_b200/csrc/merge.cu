@@ -511,15 +511,15 @@ int merge_prefix_bits(uint64_t n_records_total, uint32_t k) {
     return std::min(std::min(P, 22), key_bits);
 }
 
-void build_array_from_records(uint64_t* rec, const SeqBatch& b, uint32_t sid_base, uint64_t n_samples_total, uint32_t k, bool rc,
-                              Array& out) {
-    const PartPlan pl = make_part_plan(k, merge_prefix_bits(b.n_pos, k), n_samples_total);
+void build_array_from_records(uint64_t* rec, uint64_t n_rec, const uint64_t* d_sample_off, uint32_t n_samples_local, uint32_t sid_base,
+                              uint64_t n_samples_total, uint32_t k, bool rc, Array& out) {
+    const PartPlan pl = make_part_plan(k, merge_prefix_bits(n_rec, k), n_samples_total);
     const uint32_t n_buckets = 1u << pl.P;
 
     // (1) partition by key prefix
     timer().begin("partition");
     uint64_t* prec = nullptr; uint64_t* off = nullptr;
-    partition_records(rec, b.n_pos, b.sample_off.p, (uint32_t)b.n_samples, sid_base, pl, rec, &prec, &off);
+    partition_records(rec, n_rec, d_sample_off, n_samples_local, sid_base, pl, rec, &prec, &off);
     timer().end();
 
     timer().begin("bucket_offsets");

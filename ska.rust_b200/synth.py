@@ -45,3 +45,32 @@ def write_fasta(path, name, seq, width=80):
         b = seq.tobytes()
         for i in range(0, len(b), width):
             fh.write(b[i:i + width] + b"\n")
+
+
+_COMP = np.zeros(256, dtype=np.uint8)
+_COMP[list(b"ACGT")] = list(b"TGCA")
+
+
+def paired_reads(genome_ascii, n_pairs, read_len=150, frag_len=400, err_rate=0.005, seed=0, lowq_prob=0.5):
+    """SURVEY.md 8d config-4 reads: forward read from the + strand, reverse read = reverse complement of the fragment
+    end; per-base substitution errors; quality 'I' (Q40) except error bases get '+' (Q10) with prob `lowq_prob`.
+    -> ((seq1, qual1, off1), (seq2, qual2, off2)) flat uint8 arrays + uint64 record offsets."""
+    rng = np.random.Generator(np.random.PCG64([seed, 0xBEAD5]))
+    g = np.asarray(genome_ascii, dtype=np.uint8)
+    starts = rng.integers(0, len(g) - frag_len + 1, size=n_pairs)
+    idx = starts[:, None] + np.arange(read_len)[None, :]
+    fwd = g[idx]
+    ridx = starts[:, None] + (frag_len - 1 - np.arange(read_len))[None, :]
+    rev = _COMP[g[ridx]]
+    out = []
+    for reads in (fwd, rev):
+        reads = reads.copy()
+        err = rng.random(reads.shape) < err_rate
+        codes = (reads >> 1) & 3                                   # A0 C1 T2 G3
+        sub = (codes + rng.integers(1, 4, size=reads.shape, dtype=np.uint8)) & 3
+        reads[err] = np.frombuffer(b"ACTG", dtype=np.uint8)[sub[err]]
+        qual = np.full(reads.shape, ord("I"), dtype=np.uint8)
+        qual[err & (rng.random(reads.shape) < lowq_prob)] = ord("+")
+        off = (np.arange(n_pairs + 1, dtype=np.uint64) * np.uint64(read_len))
+        out.append((reads.reshape(-1), qual.reshape(-1), off))
+    return out[0], out[1]

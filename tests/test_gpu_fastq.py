@@ -1,0 +1,103 @@
+"""FASTQ path on the device (quality masks, ntHash, exact emulation of the bloom + counts filter) against the
+oracle's sequential KmerFilter -- reference fixtures of tests/fastq_input.rs and synthetic reads dense enough to
+saturate bloom words, so that bloom FALSE POSITIVES (which change counts by one) are exercised."""
+import numpy as np
+import pytest
+
+import ska_rust_b200 as S
+from oracle import oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+def same(g, o):
+    assert g.dims() == o.dims(), (g.dims(), o.dims())
+    gk, gv, gc = g.export()
+    ok, ov, oc = o.export()
+    assert [int(x) for x in gk] == ok
+    assert np.array_equal(gv, ov) and np.array_equal(gc, oc)
+
+
+def pair(gold_in, prefix):
+    return [(gold_in(f"{prefix}_{i}_fwd.fastq.gz"), gold_in(f"{prefix}_{i}_rev.fastq.gz")) for i in (1, 2)]
+
+
+FIXTURE_CASES = [  # tests/fastq_input.rs
+    ("test", dict(k=9, min_count=2, min_qual=2)),                                   # align_fastq :12-55
+    ("test", dict(k=9, min_count=1, min_qual=2)),                                   # map_fastq build :196-210
+    ("test", dict(k=9, min_count=3, min_qual=2)),                                   # error_fastq :283-297
+    ("test_count", dict(k=7, min_count=1)),                                         # count_check :59-80
+    ("test_count", dict(k=7, min_count=3)),                                         # :84-109
+    ("test_quality", dict(k=9, min_count=5, qual_filter="no-filter")),              # :300-325
+    ("test_quality_base", dict(k=9, min_count=5, qual_filter="middle", min_qual=5)),   # :328-355
+    ("test_error", dict(k=9, min_count=5, min_qual=2)),                             # :358-378
+    ("test_quality", dict(k=9, min_count=5, min_qual=30)),                          # :381-401
+    ("test_quality_base", dict(k=9, min_count=5, min_qual=5, qual_filter="strict")),   # :404-431
+    ("test_quality_base", dict(k=9, min_count=5)),                                  # :434-454
+]
+
+
+@pytest.mark.parametrize("prefix,kw", FIXTURE_CASES)
+def test_fastq_fixtures_match_oracle(gold_in, prefix, kw):
+    files = pair(gold_in, prefix)
+    names = [f"{prefix}_1", f"{prefix}_2"]
+    kw = dict(kw)
+    k = kw.pop("k")
+    o = O.OracleArray.build_from_files(files, k=k, names=names, **kw)
+    g = S.build_and_merge([(n, f1, f2) for n, (f1, f2) in zip(names, files)], k, True, S.QualOpts(**kw))
+    same(g, o)
+
+
+def test_fastq_single_strand_and_fasta_equivalence(gold_in):
+    files = pair(gold_in, "test")
+    g = S.build_and_merge([("a", *files[0]), ("b", *files[1])], 9, False, S.QualOpts(min_count=2, min_qual=2))
+    o = O.OracleArray.build_from_files(files, k=9, rc=False, names=["a", "b"], min_count=2, min_qual=2)
+    same(g, o)
+    # tests/fastq_input.rs:12-55: perfect reads give the FASTA alignment
+    import io
+    gq = S.build_and_merge([("a", *files[0]), ("b", *files[1])], 9, True, S.QualOpts(min_count=2, min_qual=2))
+    gf = S.build_and_merge([("a", gold_in("test_1.fa"), None), ("b", gold_in("test_2.fa"), None)], 9, True)
+    b1, b2 = io.BytesIO(), io.BytesIO()
+    S.api.align(gq, b1)
+    S.api.align(gf, b2)
+    assert O.var_hash(b1.getvalue()) == O.var_hash(b2.getvalue())
+
+
+def make_reads_sample(genome, n_pairs, err, seed):
+    from ska_rust_b200 import synth
+    (s1, q1, o1), (s2, q2, o2) = synth.paired_reads(genome, n_pairs, err_rate=err, seed=seed)
+    seq = np.concatenate([s1, s2])
+    qual = np.concatenate([q1, q2])
+    off = np.concatenate([o1, o2[1:] + o1[-1]])
+    gs = S.Sample(seq, off, qual, n_rec_file1=n_pairs)
+    recs1 = [(s1[int(o1[i]):int(o1[i + 1])].tobytes(), q1[int(o1[i]):int(o1[i + 1])].tobytes()) for i in range(n_pairs)]
+    recs2 = [(s2[int(o2[i]):int(o2[i + 1])].tobytes(), q2[int(o2[i]):int(o2[i + 1])].tobytes()) for i in range(n_pairs)]
+    return gs, O.SampleData(recs1, recs2, is_reads=True)
+
+
+@pytest.mark.parametrize("min_count,qual_filter,min_qual", [(5, "strict", 20), (2, "middle", 20), (3, "no-filter", 0), (1, "strict", 20)])
+def test_fastq_synthetic_small(min_count, qual_filter, min_qual):
+    from ska_rust_b200 import synth
+    genomes = synth.star_genomes(2, 20_000, seed=0x5CA20004, snp_rate=0.002)
+    gs, os_ = zip(*[make_reads_sample(g, 3000, 0.01, 77 + i) for i, g in enumerate(genomes)])
+    names = ["r0", "r1"]
+    q = S.QualOpts(min_count=min_count, min_qual=min_qual, qual_filter=qual_filter)
+    g = S.build_from_samples(list(gs), names, 31, True, q)
+    o = O.OracleArray.build(list(os_), names, k=31, rc=True, min_count=min_count, min_qual=min_qual, qual_filter=qual_filter)
+    same(g, o)
+
+
+@pytest.mark.parametrize("min_count", [5, 2])
+def test_fastq_bloom_false_positives_saturated(min_count):
+    """~3.5e7 distinct hashes land in the 3.1e6 bloom words (>10 per 64-bit word): most first observations of late
+    k-mers are bloom false positives, which shifts their count by one -- the batch emulation must agree with the
+    sequential filter observation by observation."""
+    from ska_rust_b200 import synth
+    genome = synth.star_genomes(1, 300_000, seed=0x5CA20005)[0]
+    gs, os_ = make_reads_sample(genome, 200_000, 0.02, 5)           # 6e7 bases, ~1.2e6 errors -> ~3.7e7 novel k-mers
+    q = S.QualOpts(min_count=min_count, min_qual=20, qual_filter="no-filter")
+    g = S.build_from_samples([gs], ["r"], 31, True, q)
+    o = O.OracleArray.build([os_], ["r"], k=31, rc=True, min_count=min_count, min_qual=20, qual_filter="no-filter")
+    same(g, o)
+    # the effect under test must actually be present: without false positives the result differs
+    assert g.dims()["n_rows"] > 300_000
