@@ -37,6 +37,19 @@ UNIT = "genomes/s"
 K1_ALGO_BYTES_PER_BASE = 10.0     # read 1 B ASCII + write 9 B (u64 key + u8 base) per window
 
 
+def ncu_traffic(kernel):
+    """DRAM bytes per launch of `kernel` from the committed ncu --set full capture (profiles/ncu_summary_r01.json,
+    same workload: 128 x 5 Mbp), or None."""
+    p = os.path.join(ROOT, "profiles", "ncu_summary_r01.json")
+    try:
+        with open(p) as fh:
+            d = json.load(fh)[kernel]
+        unit = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+        return sum(float(d[m][0]) * unit[d[m][1]] for m in ("dram__bytes_read.sum", "dram__bytes_write.sum"))
+    except Exception:
+        return None
+
+
 def measured_peak():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -268,6 +281,14 @@ def run_ours(args, rank, world, local_rank):
         peak, peak_src = measured_peak()
         achieved = K1_ALGO_BYTES_PER_BASE * n_bases / (k1_ms * 1e-3) / 1e9
         step_ms = ms_dev / args.steps
+        st = {s_: ms for s_, ms, _ in stages}
+        # the kernel with the largest share of the step: the bucket merge (bucket_emit_kernel == stage "emit").
+        # algorithmic bytes: 9 B per record read + (8 + N + 8) B per row written
+        n_cols = G * world
+        emit_bytes = 9.0 * n_bases + rows_built * (16.0 + n_cols)
+        emit_ms = st.get("emit", float("nan"))
+        emit_achieved = emit_bytes / (emit_ms * 1e-3) / 1e9
+        full_size = (G == 128 and L == 5_000_000 and world == 1)
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64",
@@ -283,10 +304,18 @@ def run_ours(args, rank, world, local_rank):
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": launches,
-            "roofline": {"kernel": "k1_extract_kernel", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
-                         "algorithmic_bytes_per_launch": K1_ALGO_BYTES_PER_BASE * n_bases, "launch_ms": k1_ms,
-                         "frac_of_nominal_8TBs": achieved / 8000.0},
+            # dominant kernel of the step (largest share in profiles/launches_r01.csv: bucket_emit_kernel, ~1/3)
+            "roofline": {"kernel": "bucket_emit_kernel", "bound": "hbm", "achieved": emit_achieved, "peak": peak, "unit": "GB/s",
+                         "frac": emit_achieved / peak, "traffic": ncu_traffic("bucket_emit") if full_size else None,
+                         "peak_source": peak_src, "algorithmic_bytes_per_launch": emit_bytes, "launch_ms": emit_ms,
+                         "share_of_step": emit_ms / step_ms,
+                         "note": "shared-memory/L2-atomic bound, not DRAM bound (ncu: 57% SM throughput, 10% DRAM)"},
+            # the kernel the north star quotes a target for (>= 60% of HBM peak): split-k-mer extraction
+            "roofline_k1": {"kernel": "k1_extract_kernel", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                            "frac": achieved / peak, "traffic": ncu_traffic("k1_extract") if full_size else None,
+                            "peak_source": peak_src, "algorithmic_bytes_per_launch": K1_ALGO_BYTES_PER_BASE * n_bases,
+                            "launch_ms": k1_ms, "share_of_step": st.get("k1_extract", 0.0) / step_ms,
+                            "frac_of_nominal_8TBs": achieved / 8000.0},
             "stages_ms": {s: round(ms, 3) for s, ms, _ in stages},
             "clocks": clocks.summary(),
         }

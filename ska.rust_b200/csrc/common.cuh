@@ -136,7 +136,7 @@ size_t padded_positions(uint64_t n_pos);
 struct PartPlan { int key_bits, sb, P, P1, P2, low_bits; };
 PartPlan make_part_plan(uint32_t k, int prefix_bits, uint64_t n_samples_total);
 void partition_records(const uint64_t* rec, uint64_t n_pos, const uint64_t* d_sample_off, uint32_t n_samples_local, uint32_t sid_base,
-                       const PartPlan& pl, uint64_t* scratch, uint64_t** out, uint64_t** d_off);
+                       const PartPlan& pl, uint64_t* scratch, uint64_t** out, uint64_t** d_off, uint64_t** first_pass_buf = nullptr);
 // merge.cu
 // K1 records (n_rec entries; sample s owns entries [sample_off[s], sample_off[s+1]); REC_SENTINEL entries are
 // skipped) -> array; sample ids are sid_base + local index.  `rec` is overwritten (partition scratch).

@@ -39,7 +39,8 @@ __device__ __forceinline__ uint32_t hash_slot(uint64_t key, int log_cap) {
 // beg/end are VIRTUAL record indices.  On one GPU they are physical too.  On a row shard the bucket's
 // records arrive as one sorted run per source rank; the runs of a bucket are laid end to end in the
 // virtual index space and (seg_voff, seg_pstart)[seg0 .. seg0 + n_runs] translate to physical.
-struct Item { uint64_t beg, end, key_lo, key_hi; uint64_t seg0; uint64_t key_base; };   // key = key_base | (prec >> (sb+2))
+struct Item { uint64_t beg, end, key_lo, key_hi; uint64_t seg0; uint64_t key_base; uint64_t scratch; };   // key = key_base | (prec >> (sb+2))
+constexpr uint64_t NO_SCRATCH = ~0ULL;   // scratch: where the count pass leaves this item's sorted distinct keys for the emit pass
 constexpr int MAX_RUNS = 8;
 struct SegMap { int w; uint64_t v[MAX_RUNS + 1]; uint64_t p[MAX_RUNS]; };
 __device__ __forceinline__ void segmap_load(SegMap& m, const Item& it, const uint64_t* __restrict__ seg_voff,
@@ -71,6 +72,7 @@ __global__ void make_items_kernel(const uint64_t* __restrict__ off, uint32_t n_b
     if (b == n_buckets - 1) it.key_hi = ~0ULL >> 4;       // top bucket also holds nothing above the key space
     it.seg0 = 0;
     it.key_base = (uint64_t)(b >> P2) << low_bits;
+    it.scratch = it.beg;                                   // distinct keys <= records: the bucket's own offset is room enough
     items[b] = it;
 }
 
@@ -78,9 +80,10 @@ __global__ void make_items_kernel(const uint64_t* __restrict__ off, uint32_t n_b
 __global__ void __launch_bounds__(MG_THREADS)
 bucket_count_kernel(const uint64_t* __restrict__ rec, const Item* __restrict__ items, const uint64_t* __restrict__ seg_voff,
                     const uint64_t* __restrict__ seg_pstart, int n_runs, int sb, uint32_t limit,
-                    uint32_t* __restrict__ n_rows, uint32_t* __restrict__ need_split) {
+                    uint32_t* __restrict__ n_rows, uint32_t* __restrict__ need_split, uint64_t* __restrict__ scratch_keys) {
     __shared__ uint64_t s_tab[COUNT_CAP];
-    __shared__ uint32_t s_n, s_over;
+    __shared__ uint32_t s_n, s_over, s_u;
+    extern __shared__ uint64_t s_list[];                   // [COUNT_CAP]: the item's distinct keys, sorted
     __shared__ SegMap s_map;
     const Item it = items[blockIdx.x];
     if (it.beg == it.end) { if (threadIdx.x == 0) n_rows[blockIdx.x] = 0; return; }
@@ -128,11 +131,33 @@ bucket_count_kernel(const uint64_t* __restrict__ rec, const Item* __restrict__ i
         }
     }
     __syncthreads();
+    const uint32_t n = s_over ? COUNT_OVERFLOW : s_n;
     if (threadIdx.x == 0) {
-        uint32_t n = s_over ? COUNT_OVERFLOW : s_n;
         n_rows[blockIdx.x] = n;
         if (n > limit) atomicExch(need_split, 1u);
+        s_u = 0;
     }
+    if (n > limit || it.scratch == NO_SCRATCH || !scratch_keys) return;
+    // leave the sorted distinct keys for the emit pass: it then only inserts U keys instead of re-scanning the records
+    __syncthreads();
+    for (uint32_t i = threadIdx.x; i < COUNT_CAP; i += MG_THREADS) {
+        uint64_t key = s_tab[i];
+        if (key != KEY_EMPTY) s_list[atomicAdd(&s_u, 1u)] = key;
+    }
+    __syncthreads();
+    uint32_t np2 = 1; while (np2 < n) np2 <<= 1;
+    for (uint32_t i = n + threadIdx.x; i < np2; i += MG_THREADS) s_list[i] = KEY_EMPTY;
+    __syncthreads();
+    for (uint32_t size = 2; size <= np2; size <<= 1)
+        for (uint32_t stride = size >> 1; stride > 0; stride >>= 1) {
+            for (uint32_t t = threadIdx.x; t < np2 / 2; t += MG_THREADS) {
+                uint32_t lo = 2 * t - (t & (stride - 1)), hi = lo + stride;
+                uint64_t a = s_list[lo], b2 = s_list[hi];
+                if ((a > b2) == ((lo & size) == 0)) { s_list[lo] = b2; s_list[hi] = a; }
+            }
+            __syncthreads();
+        }
+    for (uint32_t i = threadIdx.x; i < n; i += MG_THREADS) scratch_keys[it.scratch + i] = s_list[i];
 }
 
 // exclusive scan of n u32 counts into u64 offsets (single CTA; n is at most a few million).  Coalesced:
@@ -205,6 +230,15 @@ __device__ __forceinline__ uint32_t iupac_letter(uint32_t m) {
                         ((uint64_t)'K' << 32) | ((uint64_t)'D' << 40) | ((uint64_t)'B' << 48) | ((uint64_t)'N' << 56);
     return (uint32_t)(((m & 8u) ? t1 : t0) >> (8 * (m & 7u))) & 0xFFu;
 }
+// four base sets (one per byte, low 4 bits) -> four IUPAC letters, with two byte-permutes over the 16-letter table
+__device__ __forceinline__ uint32_t iupac_letters4(uint32_t v) {
+    const uint32_t T0 = '-' | ('A' << 8) | ('C' << 16) | ('M' << 24), T1 = 'T' | ('W' << 8) | ('Y' << 16) | ('H' << 24);
+    const uint32_t T2 = 'G' | ('R' << 8) | ('S' << 16) | ('V' << 24), T3 = 'K' | ('D' << 8) | ('B' << 16) | ('N' << 24);
+    const uint32_t sel = (v & 0x7u) | ((v >> 4) & 0x70u) | ((v >> 8) & 0x700u) | ((v >> 12) & 0x7000u);   // one selector nibble per byte
+    const uint32_t lo = __byte_perm(T0, T1, sel), hi = __byte_perm(T2, T3, sel);
+    const uint32_t m = ((v >> 3) & 0x01010101u) * 0xFFu;          // 0xFF in bytes whose set contains G (bit 3)
+    return (hi & m) | (lo & ~m);
+}
 // palindromic key: only {A,T} seen -> W, only {C,G} -> S, both -> N   (ska_dict.rs:85-113)
 __device__ __forceinline__ uint32_t pal_letter(uint32_t m) {
     if (!m) return '-';
@@ -227,7 +261,8 @@ __global__ void __launch_bounds__(MG_THREADS)
 bucket_emit_kernel(const uint64_t* __restrict__ rec, const Item* __restrict__ items,
                    const uint64_t* __restrict__ seg_voff, const uint64_t* __restrict__ seg_pstart, int n_runs, int sb,
                    const uint64_t* __restrict__ row_off, int log_cap, uint32_t n_samples, int k, int rc,
-                   uint64_t* __restrict__ out_keys, uint8_t* __restrict__ out_var, uint32_t* __restrict__ out_cnt) {
+                   uint64_t* __restrict__ out_keys, uint8_t* __restrict__ out_var, uint32_t* __restrict__ out_cnt,
+                   const uint64_t* __restrict__ scratch_keys) {
     extern __shared__ __align__(16) uint8_t smem[];
     const uint32_t cap = 1u << log_cap, half = cap >> 1;
     uint64_t* s_tab = reinterpret_cast<uint64_t*>(smem);
@@ -250,6 +285,18 @@ bucket_emit_kernel(const uint64_t* __restrict__ rec, const Item* __restrict__ it
     if (threadIdx.x == 0) s_u = 0;
     __syncthreads();
 
+    const bool from_scratch = scratch_keys && it.scratch != NO_SCRATCH;
+    if (from_scratch) {
+        // phases 1-2 were done by the count pass: load its sorted distinct keys, insert each once with its rank
+        for (uint32_t i = threadIdx.x; i < u; i += MG_THREADS) {
+            const uint64_t key = scratch_keys[it.scratch + i];
+            s_lkey[i] = key;
+            uint32_t slot = hash_slot(key, log_cap);
+            while (atomicCAS((unsigned long long*)&s_tab[slot], KEY_EMPTY, key) != KEY_EMPTY) slot = (slot + 1) & (cap - 1);
+            s_rank[slot] = (uint16_t)i;
+        }
+        __syncthreads();
+    } else {
     // phase 1
     for (uint64_t base = beg + threadIdx.x; base < end; base += MG_UNROLL * MG_THREADS) {
         uint64_t rr[MG_UNROLL];
@@ -311,12 +358,13 @@ bucket_emit_kernel(const uint64_t* __restrict__ rec, const Item* __restrict__ it
             __syncthreads();
         }
     }
+    for (uint32_t i = threadIdx.x; i < u; i += MG_THREADS) s_rank[s_lslot[i]] = (uint16_t)i;
+    __syncthreads();
+    }   // !from_scratch
 
-    // phase 3: ranks, keys, palindrome flags (bit 15 of lslot), zero the rows
+    // phase 3: keys, palindrome flags (in lslot), zero the rows
     for (uint32_t i = threadIdx.x; i < u; i += MG_THREADS) {
         uint64_t key = s_lkey[i];
-        uint32_t slot = s_lslot[i];
-        s_rank[slot] = (uint16_t)i;
         out_keys[row_base + i] = key;
         bool pal = rc && (revcomp_key(key, k - 1) == key);
         s_lslot[i] = (uint16_t)(pal ? 1u : 0u);
@@ -390,13 +438,15 @@ bucket_emit_kernel(const uint64_t* __restrict__ rec, const Item* __restrict__ it
                 for (int j = 0; j < MG_UNROLL; j++) {
                     uint32_t i = i0 + j * NW;
                     if (i >= u) break;
-                    const bool pal = s_lslot[i];
-                    uint32_t v = vv[j], word = 0;
+                    const bool pal = s_lslot[i];                  // warp-uniform: one row per warp
+                    const uint32_t v = vv[j];
+                    uint32_t word;
+                    nz[j] += __popc((v + 0x7F7F7F7Fu) & 0x80808080u);   // non-empty cells (sets are 1..15)
+                    if (!pal) word = iupac_letters4(v);
+                    else {
+                        word = 0;
 #pragma unroll
-                    for (int q = 0; q < 4; q++) {
-                        uint32_t m = (v >> (8 * q)) & 0xFu;
-                        nz[j] += (m != 0);
-                        word |= (pal ? pal_letter(m) : iupac_letter(m)) << (8 * q);
+                        for (int q = 0; q < 4; q++) word |= pal_letter((v >> (8 * q)) & 0xFu) << (8 * q);
                     }
                     out32[w_beg + (uint64_t)i * wpr + w0] = word;
                 }
@@ -432,7 +482,7 @@ static int choose_prefix_bits(uint64_t n_pos, int key_bits, uint64_t target) {
 // (2) of the file header: count distinct keys per item (splitting items that do not fit shared memory),
 // scan to row offsets, emit rows.  `items` is a device array in ascending key order.
 static void merge_items(const uint64_t* rec, Item* items, uint32_t n_items, const uint64_t* seg_voff, const uint64_t* seg_pstart,
-                        int n_runs, int sb, uint64_t n_samples, uint32_t k, bool rc, Array& out) {
+                        int n_runs, int sb, uint64_t n_samples, uint32_t k, bool rc, Array& out, uint64_t* scratch_keys) {
     Context& c = ctx();
     // bytes of shared memory per table slot in the emit kernel: tab 8 + rank 2 + (lkey 8 + lslot 2 + cnt 4)/2
     const size_t slot_bytes = 17;
@@ -440,12 +490,14 @@ static void merge_items(const uint64_t* rec, Item* items, uint32_t n_items, cons
     const uint32_t limit = COUNT_CAP - COUNT_CAP / 4 - 1;         // most distinct keys one item may hold (3071)
 
     timer().begin("count");
+    SKA_CUDA(cudaFuncSetAttribute(bucket_count_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, COUNT_CAP * 8));
     uint32_t* n_rows = arena().take_n<uint32_t>(std::max<uint32_t>(n_items, 1));
     uint32_t* flags = arena().take_n<uint32_t>(2);
     uint32_t h_flags[2] = {0, 0};
     for (int round = 0; n_items > 0; round++) {
         SKA_CUDA(cudaMemsetAsync(flags, 0, 8, c.stream));
-        SKA_LAUNCH(bucket_count_kernel, n_items, MG_THREADS, 0, rec, items, seg_voff, seg_pstart, n_runs, sb, limit, n_rows, flags);
+        SKA_LAUNCH(bucket_count_kernel, n_items, MG_THREADS, COUNT_CAP * 8, rec, items, seg_voff, seg_pstart, n_runs, sb, limit, n_rows,
+                   flags, scratch_keys);
         SKA_CUDA(cudaMemcpyAsync(h_flags, flags, 8, cudaMemcpyDeviceToHost, c.stream));
         SKA_CUDA(cudaStreamSynchronize(c.stream));
         if (!h_flags[0]) break;
@@ -465,7 +517,7 @@ static void merge_items(const uint64_t* rec, Item* items, uint32_t n_items, cons
             if (h_rows[i] != COUNT_OVERFLOW) { parts = 2; while ((uint64_t)parts * limit < 2ull * h_rows[i]) parts *= 2; }
             uint64_t step = width / parts + 1;                            // ceil((width+1)/parts) keeps children ordered, disjoint
             for (uint64_t lo = it.key_lo;; lo += step) {
-                Item ch = it; ch.key_lo = lo;
+                Item ch = it; ch.key_lo = lo; ch.scratch = NO_SCRATCH;    // children share the parent's records: no private scratch
                 bool last = (it.key_hi - lo) < step;
                 ch.key_hi = last ? it.key_hi : lo + step - 1;
                 next.push_back(ch);
@@ -499,7 +551,7 @@ static void merge_items(const uint64_t* rec, Item* items, uint32_t n_items, cons
         if (log_cap > max_log_cap) throw Error("internal: item larger than the shared-memory table");
         SKA_CUDA(cudaFuncSetAttribute(bucket_emit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         SKA_LAUNCH(bucket_emit_kernel, n_items, MG_THREADS, smem, rec, items, seg_voff, seg_pstart, n_runs, sb, row_off, log_cap,
-                   (uint32_t)n_samples, (int)k, rc ? 1 : 0, out.keys.p, out.variants.p, out.counts.p);
+                   (uint32_t)n_samples, (int)k, rc ? 1 : 0, out.keys.p, out.variants.p, out.counts.p, (const uint64_t*)scratch_keys);
     }
     timer().end();
 }
@@ -518,8 +570,8 @@ void build_array_from_records(uint64_t* rec, uint64_t n_rec, const uint64_t* d_s
 
     // (1) partition by key prefix
     timer().begin("partition");
-    uint64_t* prec = nullptr; uint64_t* off = nullptr;
-    partition_records(rec, n_rec, d_sample_off, n_samples_local, sid_base, pl, rec, &prec, &off);
+    uint64_t* prec = nullptr; uint64_t* off = nullptr; uint64_t* part_a = nullptr;
+    partition_records(rec, n_rec, d_sample_off, n_samples_local, sid_base, pl, rec, &prec, &off, &part_a);
     timer().end();
 
     timer().begin("bucket_offsets");
@@ -527,7 +579,9 @@ void build_array_from_records(uint64_t* rec, uint64_t n_rec, const uint64_t* d_s
     SKA_LAUNCH(make_items_kernel, (n_buckets + 255) / 256, 256, 0, off, n_buckets, pl.key_bits, pl.P, pl.P2, pl.low_bits, items);
     timer().end();
 
-    merge_items(prec, items, n_buckets, nullptr, nullptr, 1, pl.sb, n_samples_total, k, rc, out);
+    // the buffer the partition no longer needs doubles as the count -> emit key scratch (same length as the records)
+    uint64_t* scratch = (prec == rec) ? part_a : rec;
+    merge_items(prec, items, n_buckets, nullptr, nullptr, 1, pl.sb, n_samples_total, k, rc, out, scratch);
 }
 
 // Row shard: the received records are `n_runs` runs (one per source rank), each grouped by the same plan
@@ -552,6 +606,7 @@ void build_array_from_runs(const uint64_t* prec, int n_runs, const uint64_t* run
         it.key_base = (b >> pl.P2) << pl.low_bits;
         it.seg0 = (uint64_t)j * (W + 1);
         it.beg = v;
+        it.scratch = v;
         for (int r = 0; r < W; r++) {
             h_voff[it.seg0 + r] = v;
             if (r < n_runs) {
@@ -575,7 +630,8 @@ void build_array_from_runs(const uint64_t* prec, int n_runs, const uint64_t* run
         SKA_CUDA(cudaStreamSynchronize(c.stream));
     }
     timer().end();
-    merge_items(prec, items, nb, d_voff, d_pstart, W, pl.sb, n_samples, k, rc, out);
+    uint64_t* scratch = arena().take_n<uint64_t>(std::max<uint64_t>(v, 1));
+    merge_items(prec, items, nb, d_voff, d_pstart, W, pl.sb, n_samples, k, rc, out, scratch);
 }
 
 }  // namespace ska

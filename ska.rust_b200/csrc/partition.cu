@@ -266,7 +266,8 @@ PartPlan make_part_plan(uint32_t k, int prefix_bits, uint64_t n_samples_total) {
 // rec: K1 output (n_pos entries, linear).  Returns the packed records grouped by the P-bit prefix in `*out`
 // (arena memory) and the 2^P + 1 bucket offsets on the device in `*d_off`.
 void partition_records(const uint64_t* rec, uint64_t n_pos, const uint64_t* d_sample_off, uint32_t n_samples_local, uint32_t sid_base,
-                       const PartPlan& pl, uint64_t* scratch /* n_pos u64, may alias nothing */, uint64_t** out, uint64_t** d_off) {
+                       const PartPlan& pl, uint64_t* scratch /* n_pos u64 for the second pass, may be rec */, uint64_t** out, uint64_t** d_off,
+                       uint64_t** first_pass_buf) {
     Context& c = ctx();
     const uint32_t D1 = 1u << pl.P1, D2 = 1u << pl.P2, NB = 1u << pl.P;
     unsigned long long* hist1 = arena().take_n<unsigned long long>(D1);
@@ -291,6 +292,7 @@ void partition_records(const uint64_t* rec, uint64_t n_pos, const uint64_t* d_sa
         SKA_LAUNCH((part_scatter_kernel<1>), (unsigned)n_tiles1, PT_THREADS, scatter_smem(pl.P1), rec, n_pos, (const uint64_t*)nullptr,
                    (const uint64_t*)nullptr, 1u, f1, pl.P1, pk, d_sample_off, n_samples_local, cur1, a);
     }
+    if (first_pass_buf) *first_pass_buf = a;
     if (pl.P2 == 0) { *out = a; *d_off = off1; return; }
 
     // second level: every first-level region is partitioned by the next P2 bits
