@@ -438,7 +438,7 @@ int skagpu_merge_records_dev(const void* rec_dev, int n_runs, const uint64_t* ru
 }
 
 int skagpu_merge_prefix_bits(uint64_t n_records_total, uint32_t k, uint64_t n_samples_total) {
-    try { return make_part_plan(k, merge_prefix_bits(n_records_total, k), n_samples_total).P; }
+    try { return make_part_plan(k, merge_prefix_bits(n_records_total, k, n_samples_total), n_samples_total).P; }
     catch (std::exception& e) { g_err = e.what(); return -1; }
 }
 

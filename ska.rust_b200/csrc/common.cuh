@@ -148,7 +148,7 @@ void build_array_from_reads(const SeqBatch& b, uint32_t k, bool rc, uint16_t min
 void build_array_from_runs(const uint64_t* prec, int n_runs, const uint64_t* run_off, uint32_t bucket_lo, uint32_t bucket_hi,
                            const PartPlan& pl, uint64_t n_samples, uint32_t k, bool rc, Array& out);
 // prefix bits the merge wants for `n_records_total` records in the whole key space
-int merge_prefix_bits(uint64_t n_records_total, uint32_t k);
+int merge_prefix_bits(uint64_t n_records_total, uint32_t k, uint64_t n_samples_total);
 
 // exclusive scan of n u32 counts into n+1 u64 offsets (off[n] = total); *max_out = max count
 void launch_scan_counts(const uint32_t* cnt, uint32_t n, uint64_t* off, uint32_t* max_out);

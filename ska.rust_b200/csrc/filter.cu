@@ -198,6 +198,65 @@ filter_flags_rows_kernel(const uint8_t* __restrict__ var, const uint32_t* __rest
     if (threadIdx.x == 0) { cta_keep1[blockIdx.x] = s_k1; cta_keep2[blockIdx.x] = s_k2; }
 }
 
+// Wide rows (n_samples >= 256, multiple of 16): one WARP per row with 16-byte loads, so a row of N bytes is read in
+// fully coalesced 512-byte steps; the per-lane states are merged with shuffles once per row.
+__global__ void __launch_bounds__(FL_THREADS)
+filter_flags_wide_kernel(const uint8_t* __restrict__ var, const uint32_t* __restrict__ cnt, uint64_t n_rows, uint32_t n_samples,
+                         uint64_t min_count, int ambig_missing, int ftype, int ignore_gaps, uint8_t* __restrict__ flags,
+                         uint32_t* __restrict__ new_cnt, uint32_t* __restrict__ cta_keep1, uint32_t* __restrict__ cta_keep2) {
+    __shared__ uint32_t s_k1, s_k2;
+    __shared__ uint32_t s_lut[256];
+    if (threadIdx.x == 0) { s_k1 = 0; s_k2 = 0; }
+    for (uint32_t b = threadIdx.x; b < 256; b += FL_THREADS) s_lut[b] = class_entry(b);
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint64_t r0 = (uint64_t)blockIdx.x * FL_ROWS;
+    const uint32_t n16 = n_samples >> 4;
+    uint32_t k1 = 0, k2 = 0;
+    for (int rr = warp; rr < FL_ROWS; rr += FL_THREADS / 32) {
+        const uint64_t r = r0 + rr;
+        if (r >= n_rows) break;
+        const uint4* row = reinterpret_cast<const uint4*>(var + r * n_samples);
+        RowState st = {0, 0, 0, 0xFFFFFFFFu, 0, s_lut};
+        for (uint32_t c0 = lane; c0 < n16; c0 += 128) {               // 4 loads in flight per lane
+            uint4 v[4];
+#pragma unroll
+            for (int j = 0; j < 4; j++) if (c0 + 32 * j < n16) v[j] = __ldg(&row[c0 + 32 * j]);
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                if (c0 + 32 * j >= n16) break;
+                st.word(v[j].x); st.word(v[j].y); st.word(v[j].z); st.word(v[j].w);
+            }
+        }
+        // merge the 32 lane states
+        uint32_t good = __reduce_add_sync(0xFFFFFFFFu, st.good);
+        uint32_t setbits = __reduce_or_sync(0xFFFFFFFFu, st.setbits);
+        uint32_t any_ambig = __any_sync(0xFFFFFFFFu, st.any_ambig != 0);
+        uint32_t have = __ballot_sync(0xFFFFFFFFu, st.other_first != 0xFFFFFFFFu);
+        uint32_t ref = have ? __shfl_sync(0xFFFFFFFFu, st.other_first, __ffs(have) - 1) : 0xFFFFFFFFu;
+        uint32_t odiff = __any_sync(0xFFFFFFFFu, st.other_differs != 0 || (st.other_first != 0xFFFFFFFFu && st.other_first != ref));
+        uint32_t count = ambig_missing ? good : cnt[r];
+        bool keep1 = !ambig_missing || good > 0;
+        bool keep2 = false;
+        if (keep1 && (uint64_t)count >= min_count) {
+            switch (ftype) {
+                case 0: keep2 = true; break;
+                case 1: keep2 = (__popc(setbits & (ignore_gaps ? 0x3FFu : 0x7FFu)) + (have != 0) + (odiff != 0)) > 1; break;
+                case 2: keep2 = !any_ambig; break;
+                default: keep2 = __popc(setbits & (ignore_gaps ? 0x3FFu : 0x7FFu)) > 1;
+            }
+        }
+        if (lane == 0) {
+            flags[r] = (uint8_t)((keep1 ? 1 : 0) | (keep2 ? 2 : 0));
+            new_cnt[r] = count;
+            k1 += keep1; k2 += keep2;
+        }
+    }
+    if (lane == 0) { atomicAdd(&s_k1, k1); atomicAdd(&s_k2, k2); }
+    __syncthreads();
+    if (threadIdx.x == 0) { cta_keep1[blockIdx.x] = s_k1; cta_keep2[blockIdx.x] = s_k2; }
+}
+
 // moves surviving rows/counts/keys to their compacted positions (order preserving)
 __global__ void __launch_bounds__(FL_THREADS)
 filter_scatter_kernel(const uint8_t* __restrict__ var, const uint32_t* __restrict__ new_cnt, const uint64_t* __restrict__ keys,
@@ -246,6 +305,12 @@ filter_scatter_kernel(const uint8_t* __restrict__ var, const uint32_t* __restric
         if (!(flags[r] & 2)) continue;
         const uint8_t* src = var + r * n_samples;
         uint8_t* dst = out_var + (base2 + s_pos2[rr]) * n_samples;
+        if (!mask_ambig && (n_samples & 15u) == 0) {              // plain row move: 16 bytes per lane
+            const uint4* s4 = reinterpret_cast<const uint4*>(src);
+            uint4* d4 = reinterpret_cast<uint4*>(dst);
+            for (uint32_t c = lane; c < (n_samples >> 4); c += 32) d4[c] = __ldg(&s4[c]);
+            continue;
+        }
         for (uint32_t s = lane; s < n_samples; s += 32) {
             uint32_t b = src[s];
             if (mask_ambig && is_ambig_dev(b)) b = 'N';          // merge_ska_array.rs:388-399
@@ -267,7 +332,10 @@ int32_t filter_array(Array& a, uint64_t min_count, bool filter_ambig_as_missing,
     DevBuf<uint8_t> flags(R);
     DevBuf<uint32_t> new_cnt(R), keep1(n_cta), keep2(n_cta), scratch(1);
     DevBuf<uint64_t> off1(n_cta + 1), off2(n_cta + 1);
-    if ((N & 15u) == 0)
+    if ((N & 15u) == 0 && N >= 256)
+        SKA_LAUNCH(filter_flags_wide_kernel, n_cta, FL_THREADS, 0, a.variants.p, a.counts.p, R, N, min_count,
+                   filter_ambig_as_missing ? 1 : 0, filter_type, ignore_const_gaps ? 1 : 0, flags.p, new_cnt.p, keep1.p, keep2.p);
+    else if ((N & 15u) == 0)
         SKA_LAUNCH(filter_flags_rows_kernel, n_cta, FL_ROWS, 0, a.variants.p, a.counts.p, R, N, min_count,
                    filter_ambig_as_missing ? 1 : 0, filter_type, ignore_const_gaps ? 1 : 0, flags.p, new_cnt.p, keep1.p, keep2.p);
     else

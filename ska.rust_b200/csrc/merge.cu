@@ -556,16 +556,19 @@ static void merge_items(const uint64_t* rec, Item* items, uint32_t n_items, cons
     timer().end();
 }
 
-int merge_prefix_bits(uint64_t n_records_total, uint32_t k) {
+int merge_prefix_bits(uint64_t n_records_total, uint32_t k, uint64_t n_samples_total) {
     const int key_bits = 2 * ((int)k - 1);
-    int P = choose_prefix_bits(n_records_total, key_bits, 8192);   // ~4-8 K records per bucket
+    // ~4-8 K records per bucket for up to 128 samples; more samples mean more records per distinct k-mer (what the
+    // shared-memory tables hold is distinct k-mers), so buckets may hold proportionally more records
+    const uint64_t scale = std::min<uint64_t>(16, std::max<uint64_t>(1, n_samples_total / 128));
+    int P = choose_prefix_bits(n_records_total, key_bits, 8192 * scale);
     if (const char* e = getenv("SKA_PREFIX_BITS")) { int v = atoi(e); if (v >= 0 && v <= key_bits && v <= 22) P = v; }   // tuning/tests
     return std::min(std::min(P, 22), key_bits);
 }
 
 void build_array_from_records(uint64_t* rec, uint64_t n_rec, const uint64_t* d_sample_off, uint32_t n_samples_local, uint32_t sid_base,
                               uint64_t n_samples_total, uint32_t k, bool rc, Array& out) {
-    const PartPlan pl = make_part_plan(k, merge_prefix_bits(n_rec, k), n_samples_total);
+    const PartPlan pl = make_part_plan(k, merge_prefix_bits(n_rec, k, n_samples_total), n_samples_total);
     const uint32_t n_buckets = 1u << pl.P;
 
     // (1) partition by key prefix

@@ -92,6 +92,21 @@ def plan_owners(global_bucket_counts, world):
     return np.array(cuts, dtype=np.int64)
 
 
+def plan_owners_t(counts, world):
+    """plan_owners on a torch tensor (stays on its device; only world+1 integers come back to the host)"""
+    cum = torch.cumsum(counts, 0)
+    total = int(cum[-1].item()) if cum.numel() else 0
+    targets = torch.tensor([total * g // world for g in range(1, world)], dtype=cum.dtype, device=cum.device)
+    # first bucket index b with (records before b) >= target:  cum0 = [0, cum...]  ->  searchsorted(cum0, target, left)
+    b = torch.searchsorted(cum, targets, right=False) + 1
+    b = torch.where(targets <= 0, torch.zeros_like(b), b).cpu().numpy() if world > 1 else np.zeros(0, dtype=np.int64)
+    cuts = [0]
+    for x in b:
+        cuts.append(min(max(int(x), cuts[-1]), counts.numel()))
+    cuts.append(counts.numel())
+    return np.array(cuts, dtype=np.int64)
+
+
 def build_and_merge_sharded(backend, samples_local, names_all, sample_base, k, rc, prefix_bits=None, group=None,
                             timings=None):
     """-> this rank's slab (a MergeSkaArray with len(names_all) columns).  Collective over `group`."""
@@ -120,7 +135,7 @@ def build_and_merge_sharded(backend, samples_local, names_all, sample_base, k, r
     lap("extract_ms")
     counts = torch.from_numpy(np.diff(off).astype(np.int64)).to(dev)
     dist.all_reduce(counts, group=group)
-    cuts = plan_owners(counts.cpu().numpy(), world)
+    cuts = plan_owners_t(counts, world)
     bounds = off[cuts].astype(np.int64)                   # record index where each owner's range starts
     send_counts = np.diff(bounds)
     sc = torch.from_numpy(send_counts).to(dev)

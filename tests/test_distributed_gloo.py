@@ -219,3 +219,7 @@ def test_plan_owners_balances_and_is_monotone():
         loads = [counts[cuts[g]:cuts[g + 1]].sum() for g in range(world)]
         assert max(loads) - min(loads) <= 2 * counts.max()
     assert list(D.plan_owners(np.zeros(16, dtype=np.int64), 4)) == [0, 0, 0, 0, 16]
+    # the torch version (used on the device) plans identically
+    for world in (1, 2, 3, 8):
+        assert list(D.plan_owners_t(torch.from_numpy(counts.astype(np.int64)), world)) == list(D.plan_owners(counts, world))
+    assert list(D.plan_owners_t(torch.zeros(16, dtype=torch.int64), 4)) == [0, 0, 0, 0, 16]

@@ -323,7 +323,7 @@ def random_array(rng, n_rows, n_samples):
     return keys, var, cnt
 
 
-@pytest.mark.parametrize("n_rows,n_samples", [(1000, 7), (5000, 128), (3001, 33), (300, 200)])
+@pytest.mark.parametrize("n_rows,n_samples", [(1000, 7), (5000, 128), (3001, 33), (300, 200), (700, 256), (257, 1024)])
 def test_filter_random_arrays_match_oracle(n_rows, n_samples):
     rng = np.random.default_rng(n_rows + n_samples)
     keys, var, cnt = random_array(rng, n_rows, n_samples)
