@@ -198,7 +198,7 @@ filter_flags_rows_kernel(const uint8_t* __restrict__ var, const uint32_t* __rest
     if (threadIdx.x == 0) { cta_keep1[blockIdx.x] = s_k1; cta_keep2[blockIdx.x] = s_k2; }
 }
 
-// Wide rows (n_samples >= 256, multiple of 16): one WARP per row with 16-byte loads, so a row of N bytes is read in
+// Wide rows (n_samples >= 512, multiple of 16): one WARP per row with 16-byte loads, so a row of N bytes is read in
 // fully coalesced 512-byte steps; the per-lane states are merged with shuffles once per row.
 __global__ void __launch_bounds__(FL_THREADS)
 filter_flags_wide_kernel(const uint8_t* __restrict__ var, const uint32_t* __restrict__ cnt, uint64_t n_rows, uint32_t n_samples,
@@ -332,7 +332,7 @@ int32_t filter_array(Array& a, uint64_t min_count, bool filter_ambig_as_missing,
     DevBuf<uint8_t> flags(R);
     DevBuf<uint32_t> new_cnt(R), keep1(n_cta), keep2(n_cta), scratch(1);
     DevBuf<uint64_t> off1(n_cta + 1), off2(n_cta + 1);
-    if ((N & 15u) == 0 && N >= 256)
+    if ((N & 15u) == 0 && N >= 512)
         SKA_LAUNCH(filter_flags_wide_kernel, n_cta, FL_THREADS, 0, a.variants.p, a.counts.p, R, N, min_count,
                    filter_ambig_as_missing ? 1 : 0, filter_type, ignore_const_gaps ? 1 : 0, flags.p, new_cnt.p, keep1.p, keep2.p);
     else if ((N & 15u) == 0)

@@ -558,10 +558,10 @@ static void merge_items(const uint64_t* rec, Item* items, uint32_t n_items, cons
 
 int merge_prefix_bits(uint64_t n_records_total, uint32_t k, uint64_t n_samples_total) {
     const int key_bits = 2 * ((int)k - 1);
-    // ~4-8 K records per bucket for up to 128 samples; more samples mean more records per distinct k-mer (what the
+    // ~8-16 K records per bucket for up to 128 samples; more samples mean more records per distinct k-mer (what the
     // shared-memory tables hold is distinct k-mers), so buckets may hold proportionally more records
     const uint64_t scale = std::min<uint64_t>(16, std::max<uint64_t>(1, n_samples_total / 128));
-    int P = choose_prefix_bits(n_records_total, key_bits, 8192 * scale);
+    int P = choose_prefix_bits(n_records_total, key_bits, 16384 * scale);
     if (const char* e = getenv("SKA_PREFIX_BITS")) { int v = atoi(e); if (v >= 0 && v <= key_bits && v <= 22) P = v; }   // tuning/tests
     return std::min(std::min(P, 22), key_bits);
 }

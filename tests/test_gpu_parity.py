@@ -231,6 +231,19 @@ def test_build_synthetic_matches_oracle(n, length, k, rc):
     assert_same_array(g, o)
 
 
+def test_build_unrelated_samples_forces_bucket_splitting():
+    """samples that share nothing: every record is a distinct row, so buckets exceed the shared-memory table and are
+    split by further key bits (merge.cu, rare path)"""
+    rng = np.random.default_rng(4242)
+    samples_records = [[rng.choice(np.frombuffer(b"ACGT", dtype=np.uint8), size=400_000).tobytes()] for _ in range(8)]
+    samples = [S.Sample.from_records(r) for r in samples_records]
+    names = [f"u{i}" for i in range(8)]
+    g = S.build_from_samples(samples, names, 31, True)
+    o = ora_from_gpu_samples(samples, names, 31, True)
+    assert_same_array(g, o)
+    assert g.dims()["n_rows"] > 3_100_000
+
+
 def test_build_multi_record_with_ns_and_repeats():
     rng = np.random.default_rng(99)
     samples_records = []
