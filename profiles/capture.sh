@@ -6,7 +6,7 @@ R=${1:-r01}
 mkdir -p gpurun_out
 timeout 600 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none --csv \
     --log-file gpurun_out/launches_${R}.csv python bench.py --steps 2 --warmup 1 --no-cpu-baseline > gpurun_out/launches_${R}.log 2>&1
-for kn in k1_extract bucket_emit bucket_count filter_flags_rows; do
+for kn in k1_extract bucket_emit bucket_count part_scatter filter_flags_rows; do
     PROF_GENOMES=128 timeout 400 ncu --set full --clock-control none --import-source on -k regex:$kn -c 1 -f \
         -o gpurun_out/${kn}_${R} python profiles/profile_driver.py > gpurun_out/${kn}_${R}.log 2>&1
     ncu -i gpurun_out/${kn}_${R}.ncu-rep --page raw --csv > gpurun_out/${kn}_${R}_raw.csv 2>/dev/null

@@ -117,3 +117,21 @@ def test_cli_rfile_and_failures(gold_in, tmp_path):
     assert os.path.exists(tmp_path / "basic_build_opts.skf")
     assert run(["build", "-o", "x", "-k", "33", gold_in("test_1.fa"), gold_in("test_2.fa")], cwd=str(tmp_path), check=False).returncode == 101
     assert run(["build", "-o", "x", gold_in("nonexistent.fa")], cwd=str(tmp_path), check=False).returncode == 101
+
+
+@pytest.mark.gpu
+def test_cli_fastq_rfile(gold_in, tmp_path):
+    """tests/fastq_input.rs:12-55 align_fastq through the CLI: 3-column rfile = paired FASTQ, --min-count/--min-qual"""
+    rfile = tmp_path / "rfile"
+    rfile.write_text("".join(f"test_{i}\t{gold_in(f'test_{i}_fwd.fastq.gz')}\t{gold_in(f'test_{i}_rev.fastq.gz')}\n" for i in (1, 2)))
+    run(["build", "-f", str(rfile), "-o", "reads", "--min-count", "2", "-v", "-k", "9", "--min-qual", "2"], cwd=str(tmp_path))
+    reads = run(["align", "reads.skf"], cwd=str(tmp_path)).stdout
+    run(["build", "-k", "9", gold_in("test_1.fa"), gold_in("test_2.fa"), "-o", "fasta_k9"], cwd=str(tmp_path))
+    fasta = run(["align", "fasta_k9.skf"], cwd=str(tmp_path)).stdout
+    assert O.var_hash(reads) == O.var_hash(fasta)
+    # count_check (fastq_input.rs:59-109)
+    rfile.write_text("".join(f"test_count_{i}\t{gold_in(f'test_count_{i}_fwd.fastq.gz')}\t{gold_in(f'test_count_{i}_rev.fastq.gz')}\n" for i in (1, 2)))
+    run(["build", "-f", str(rfile), "-o", "c1", "--min-count", "1", "-k", "7"], cwd=str(tmp_path))
+    assert O.var_hash(run(["align", "c1.skf"], cwd=str(tmp_path)).stdout) == {("C", "W")}
+    run(["build", "-f", str(rfile), "-o", "c3", "--min-count", "3", "-k", "7"], cwd=str(tmp_path))
+    assert O.var_hash(run(["align", "c3.skf"], cwd=str(tmp_path)).stdout) == {("C", "T")}
