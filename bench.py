@@ -309,7 +309,7 @@ def run_ours(args, rank, world, local_rank):
                          "frac": emit_achieved / peak, "traffic": ncu_traffic("bucket_emit") if full_size else None,
                          "peak_source": peak_src, "algorithmic_bytes_per_launch": emit_bytes, "launch_ms": emit_ms,
                          "share_of_step": emit_ms / step_ms,
-                         "note": "shared-memory/L2-atomic bound, not DRAM bound (ncu: 57% SM throughput, 10% DRAM)"},
+                         "note": "bound by L2 atomics and shared-memory probes, not by DRAM (profiles/README.md)"},
             # the kernel the north star quotes a target for (>= 60% of HBM peak): split-k-mer extraction
             "roofline_k1": {"kernel": "k1_extract_kernel", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                             "frac": achieved / peak, "traffic": ncu_traffic("k1_extract") if full_size else None,
