@@ -120,7 +120,8 @@ def run_reference(args, rank, world):
     cores = os.cpu_count() or 1
     n = args.ref_genomes
     threads = host_threads_rule(cores, n)
-    genomes = synth.star_genomes(n, args.length, seed=args.seed)
+    population = args.population if args.population != "auto" else ("star" if args.gpus == 1 else "tree")
+    genomes = synth.genomes(population, n, args.length, args.genomes * args.gpus, seed=args.seed)
     for _ in range(args.warmup if args.ref_warmup < 0 else args.ref_warmup):
         cpu_reference_step(genomes, args.k, threads)
     t0 = time.perf_counter()
@@ -135,7 +136,7 @@ def run_reference(args, rank, world):
         "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "u64", "data": "synthetic",
         "config": {"workload": f"ska build + align, {args.genomes} x {args.length} bp synthetic bacterial FASTA, k={args.k}, CPU",
-                   "k": args.k, "rc": True, "genomes_per_step": n, "genome_bp": args.length},
+                   "k": args.k, "rc": True, "genomes_per_step": n, "genome_bp": args.length, "population": population},
         "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -172,7 +173,8 @@ def run_ours(args, rank, world, local_rank):
     G, L, k = args.genomes, args.length, args.k
     # weak scaling: every rank owns G genomes of the same population (sample indices rank*G ...)
     pinned = torch.empty((G, L), dtype=torch.uint8, pin_memory=True)
-    genomes = synth.star_genomes(G, L, seed=args.seed, first=rank * G, out=pinned.numpy())
+    population = args.population if args.population != "auto" else ("star" if world == 1 else "tree")
+    genomes = synth.genomes(population, G, L, G * world, seed=args.seed, first=rank * G, out=pinned.numpy())
     off = np.array([0, L], dtype=np.uint64)
     samples = [S.Sample(g, off) for g in genomes]      # views into the pinned block, no copy
     for s, g in zip(samples, genomes):
@@ -288,14 +290,16 @@ def run_ours(args, rank, world, local_rank):
         emit_bytes = 9.0 * n_bases + rows_built * (16.0 + n_cols)
         emit_ms = st.get("emit", float("nan"))
         emit_achieved = emit_bytes / (emit_ms * 1e-3) / 1e9
-        full_size = (G == 128 and L == 5_000_000 and world == 1)
+        full_size = (G == 128 and L == 5_000_000 and world == 1 and population == "star")   # what profiles/ was captured on
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64",
             "data": "synthetic",
             "config": {"workload": f"ska build + align, {G} x {L} bp synthetic bacterial FASTA per GPU, k={k}, both strands "
                                    "(BASELINE configs[1])", "k": k, "rc": True, "genomes_per_gpu": G, "genome_bp": L,
-                       "population": "star model, 0.1% SNPs/sample", "align": "min_freq 0.9, filter no-const",
+                       "population": ("star model, 0.1% SNPs/sample" if population == "star" else
+                                      f"tree model (SURVEY 8d, configs[2]): {G * world} leaves, every leaf 0.1% from the root"),
+                       "align": "min_freq 0.9, filter no-const",
                        "l2": "inputs (640 MB/128 genomes) larger than L2; no flush",
                        "parallelism": "1 GPU" if world == 1 else
                        f"{world} ranks: samples sharded for extraction, one NCCL all-to-all of records by key range, "
@@ -344,6 +348,9 @@ def main():
     ap.add_argument("--ref-genomes", type=int, default=32, help="genomes per step of the --impl reference arm")
     ap.add_argument("--ref-warmup", type=int, default=1, help="warm-up steps of the reference arm (-1: use --warmup)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--population", default="auto", choices=["auto", "star", "tree"],
+                    help="SURVEY 8d generator: star (configs[1], the 1-GPU default) or tree (recommended there for the "
+                         "1024-genome configs[2]; the default when several GPUs share one population)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

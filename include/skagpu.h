@@ -109,24 +109,27 @@ void skagpu_free(ska_array_t* a);
  * The reference is single-node shared-memory (README.md:124); these entry points split
  * build_and_merge (merge_ska_dict.rs:354-417) at its one exchange point so that the caller -- one
  * process per GPU, torch.distributed/NCCL for the transport -- can co-locate identical split k-mers:
- *   1. skagpu_extract_records: K1 over this rank's samples (global sample ids = sample_id_base + i), then
- *      the records are grouped by the top `prefix_bits` bits of the key and packed to one u64 each (sample id
- *      inside); bucket offsets tell how many records fall in every key-prefix bucket (summed over ranks
- *      they give balanced key-range owners).  prefix_bits must come from skagpu_merge_prefix_bits with
- *      the GLOBAL record count so that all ranks use the same bucket grid;
- *   2. the caller exchanges, per owner, the contiguous record range of its buckets (one all-to-all);
- *   3. skagpu_merge_records_dev: merges the received records into this rank's slab of rows with all
- *      n_samples_total columns.  The receive buffer holds `n_runs` runs (one per source rank, in rank
- *      order), each still grouped by prefix: run_offsets[r * (nb + 1) + j] is the offset inside the
- *      buffer of bucket (bucket_lo + j) of run r, nb = bucket_hi - bucket_lo -- nothing is grouped twice.
+ *   1. skagpu_extract_records: K1 over this rank's samples (global sample ids = sample_id_base + i), then the
+ *      FIRST of the two partition passes: records are packed to one u64 each (sample id inside) and grouped by
+ *      the top `region_bits` bits of the key ("regions"; region_bits <= prefix_bits is chosen by the library and
+ *      reported by skagpu_records_info).  Region offsets tell how many records fall in every region; summed
+ *      over ranks they give balanced contiguous key-range owners.  prefix_bits must come from
+ *      skagpu_merge_prefix_bits with the GLOBAL record count so that all ranks use the same grid;
+ *   2. the caller exchanges, per owner, the contiguous record range of its regions (one all-to-all);
+ *   3. skagpu_merge_records_dev: the receive buffer holds `n_runs` runs (one per source rank, in rank order),
+ *      each grouped by region: run_offsets[w * (nr + 1) + j] is the offset inside the buffer of region
+ *      (region_lo + j) of run w, nr = region_hi - region_lo.  The SECOND partition pass runs here over all runs
+ *      at once (it also concatenates them), then the merge emits this rank's slab of rows with all
+ *      n_samples_total columns.  The receive buffer is overwritten (scratch).
  * Slabs are key ranges in rank order, so their concatenation is the canonical (ascending key) array.
  * Record buffers stay valid until the next extract/build/merge call on this process. */
 int skagpu_merge_prefix_bits(uint64_t n_records_total, uint32_t k, uint64_t n_samples_total);   /* < 0 on error */
 int skagpu_extract_records(const ska_seqbatch_t* batch, uint32_t k, int rc, uint32_t sample_id_base, uint64_t n_samples_total,
                            int prefix_bits, ska_records_t** out);
-int skagpu_records_info(const ska_records_t* r, uint64_t* n, const void** rec_dev, int* prefix_bits, uint64_t* bucket_offsets);
+int skagpu_records_info(const ska_records_t* r, uint64_t* n, const void** rec_dev, int* region_bits,
+                        uint64_t* region_offsets /* 2^region_bits + 1 entries, may be NULL */);
 void skagpu_records_free(ska_records_t* r);
-int skagpu_merge_records_dev(const void* rec_dev, int n_runs, const uint64_t* run_offsets, uint32_t bucket_lo, uint32_t bucket_hi,
+int skagpu_merge_records_dev(void* rec_dev, int n_runs, const uint64_t* run_offsets, uint32_t region_lo, uint32_t region_hi,
                              int prefix_bits, uint64_t n_samples_total, uint32_t k, int rc, ska_array_t** out);
 /* Per-pair partial sums of variant_dist (merge_ska_array.rs:599-620) over this array's rows, 4 x u64 per
  * pair {mismatches, matches, dist_int, n_both}: integers, so row shards add up exactly (all-reduce);

@@ -201,10 +201,10 @@ static thread_local std::string g_err;
 
 struct ska_array { Array a; };
 struct ska_seqbatch { std::unique_ptr<SeqBatch> b; };
-struct ska_records {            // packed records of one rank, grouped by key prefix; arena memory, valid until the next build
+struct ska_records {            // packed records of one rank, grouped by first-level region; arena memory, valid until the next build
     uint64_t* rec = nullptr; uint64_t n = 0;
     uint32_t k = 0; bool rc = false; PartPlan plan;
-    std::vector<uint64_t> off;  // 2^P + 1 bucket offsets
+    std::vector<uint64_t> off;  // 2^P1 + 1 region offsets
 };
 
 extern "C" {
@@ -362,7 +362,7 @@ int skagpu_export_transposed(const ska_array_t* h, uint8_t* out) {
 
 void skagpu_free(ska_array_t* h) { delete h; }
 
-// ---- row-sharded (multi-GPU) build: extract + local partition | exchange (caller) | merge ----------
+// ---- row-sharded (multi-GPU) build: extract + first partition pass | exchange (caller) | second pass + merge ----------
 int skagpu_extract_records(const ska_seqbatch_t* batch, uint32_t k, int rc, uint32_t sample_id_base, uint64_t n_samples_total,
                            int prefix_bits, ska_records_t** out) {
     API_TRY
@@ -388,9 +388,9 @@ int skagpu_extract_records(const ska_seqbatch_t* batch, uint32_t k, int rc, uint
     std::vector<uint32_t> h_valid(b.n_samples);
     SKA_CUDA(cudaMemcpyAsync(h_valid.data(), valid, b.n_samples * 4, cudaMemcpyDeviceToHost, c.stream));
     timer().begin("partition");
-    uint64_t* d_off = nullptr;
-    partition_records(rec, b.n_pos, b.sample_off.p, (uint32_t)b.n_samples, sample_id_base, r->plan, rec, &r->rec, &d_off);
-    r->off.resize(((size_t)1 << r->plan.P) + 1);
+    uint64_t *d_off = nullptr, *d_tiles = nullptr;
+    partition_coarse(rec, b.n_pos, b.sample_off.p, (uint32_t)b.n_samples, sample_id_base, r->plan, &r->rec, &d_off, &d_tiles);
+    r->off.resize(((size_t)1 << r->plan.P1) + 1);
     SKA_CUDA(cudaMemcpyAsync(r->off.data(), d_off, r->off.size() * 8, cudaMemcpyDeviceToHost, c.stream));
     SKA_CUDA(cudaStreamSynchronize(c.stream));
     timer().end();
@@ -402,21 +402,21 @@ int skagpu_extract_records(const ska_seqbatch_t* batch, uint32_t k, int rc, uint
     API_CATCH
 }
 
-int skagpu_records_info(const ska_records_t* r, uint64_t* n, const void** rec_dev, int* prefix_bits,
-                        uint64_t* bucket_offsets /* 2^prefix_bits + 1, may be NULL */) {
+int skagpu_records_info(const ska_records_t* r, uint64_t* n, const void** rec_dev, int* region_bits,
+                        uint64_t* region_offsets /* 2^region_bits + 1, may be NULL */) {
     API_TRY
     if (!r) throw Error("null records");
     if (n) *n = r->n;
     if (rec_dev) *rec_dev = r->rec;
-    if (prefix_bits) *prefix_bits = r->plan.P;
-    if (bucket_offsets) memcpy(bucket_offsets, r->off.data(), r->off.size() * 8);
+    if (region_bits) *region_bits = r->plan.P1;
+    if (region_offsets) memcpy(region_offsets, r->off.data(), r->off.size() * 8);
     return 0;
     API_CATCH
 }
 
 void skagpu_records_free(ska_records_t* r) { delete r; }
 
-int skagpu_merge_records_dev(const void* rec_dev, int n_runs, const uint64_t* run_offsets, uint32_t bucket_lo, uint32_t bucket_hi,
+int skagpu_merge_records_dev(void* rec_dev, int n_runs, const uint64_t* run_offsets, uint32_t region_lo, uint32_t region_hi,
                              int prefix_bits, uint64_t n_samples_total, uint32_t k, int rc, ska_array_t** out) {
     API_TRY
     *out = nullptr;
@@ -426,12 +426,18 @@ int skagpu_merge_records_dev(const void* rec_dev, int n_runs, const uint64_t* ru
     if (k > 31) throw Error("k > 31 not yet supported on the device");
     const PartPlan pl = make_part_plan(k, prefix_bits, n_samples_total);
     if (pl.P != prefix_bits) throw Error("prefix_bits does not match the record plan (use skagpu_merge_prefix_bits)");
-    if (bucket_hi < bucket_lo || bucket_hi > (1ull << pl.P)) throw Error("bad bucket range");
+    if (region_hi < region_lo || region_hi > (1ull << pl.P1)) throw Error("bad region range");
+    if (n_runs < 1 || !run_offsets) throw Error("row shard needs at least one run");
+    const uint32_t nr = region_hi - region_lo;
+    uint64_t n_rec = 0;
+    for (int w = 0; w < n_runs; w++) n_rec = std::max(n_rec, run_offsets[(size_t)w * (nr + 1) + nr]);
+    if (n_rec && !rec_dev) throw Error("null record buffer");
     // the caller's buffers may have been filled on another stream (NCCL): order after everything
     SKA_CUDA(cudaDeviceSynchronize());
     arena().reset();
     std::unique_ptr<ska_array> h(new ska_array());
-    build_array_from_runs((const uint64_t*)rec_dev, n_runs, run_offsets, bucket_lo, bucket_hi, pl, n_samples_total, k, rc != 0, h->a);
+    timer().clear();
+    build_array_from_runs((uint64_t*)rec_dev, n_rec, n_runs, run_offsets, region_lo, region_hi, pl, n_samples_total, k, rc != 0, h->a);
     *out = h.release();
     return 0;
     API_CATCH

@@ -137,6 +137,11 @@ struct PartPlan { int key_bits, sb, P, P1, P2, low_bits; };
 PartPlan make_part_plan(uint32_t k, int prefix_bits, uint64_t n_samples_total);
 void partition_records(const uint64_t* rec, uint64_t n_pos, const uint64_t* d_sample_off, uint32_t n_samples_local, uint32_t sid_base,
                        const PartPlan& pl, uint64_t* scratch, uint64_t** out, uint64_t** d_off, uint64_t** first_pass_buf = nullptr);
+// first pass only (what a rank does before the exchange) / second pass over received runs (what the owner does after it)
+void partition_coarse(const uint64_t* rec, uint64_t n_pos, const uint64_t* d_sample_off, uint32_t n_samples_local, uint32_t sid_base,
+                      const PartPlan& pl, uint64_t** out, uint64_t** d_off1, uint64_t** d_tile_pref);
+void partition_runs(const uint64_t* src, int n_runs, const uint64_t* h_run_off, uint32_t n_regions, const PartPlan& pl, uint64_t* dst,
+                    uint64_t** d_bucket_off);
 // merge.cu
 // K1 records (n_rec entries; sample s owns entries [sample_off[s], sample_off[s+1]); REC_SENTINEL entries are
 // skipped) -> array; sample ids are sid_base + local index.  `rec` is overwritten (partition scratch).
@@ -144,8 +149,8 @@ void build_array_from_records(uint64_t* rec, uint64_t n_rec, const uint64_t* d_s
                               uint64_t n_samples_total, uint32_t k, bool rc, Array& out);
 // k1q_reads.cu: FASTQ samples (quality masks, ntHash, exact count-filter emulation) -> array
 void build_array_from_reads(const SeqBatch& b, uint32_t k, bool rc, uint16_t min_count, uint8_t min_qual, int qual_filter, Array& out);
-// row shard: `n_runs` received runs of packed records, each grouped by the same plan over buckets [lo, hi)
-void build_array_from_runs(const uint64_t* prec, int n_runs, const uint64_t* run_off, uint32_t bucket_lo, uint32_t bucket_hi,
+// row shard: `n_runs` received runs of first-pass records covering first-level regions [lo, hi); `prec` is overwritten
+void build_array_from_runs(uint64_t* prec, uint64_t n_rec, int n_runs, const uint64_t* run_off, uint32_t region_lo, uint32_t region_hi,
                            const PartPlan& pl, uint64_t n_samples, uint32_t k, bool rc, Array& out);
 // prefix bits the merge wants for `n_records_total` records in the whole key space
 int merge_prefix_bits(uint64_t n_records_total, uint32_t k, uint64_t n_samples_total);

@@ -36,58 +36,36 @@ __device__ __forceinline__ uint32_t hash_slot(uint64_t key, int log_cap) {
 // A work item = a contiguous record range (one prefix bucket) restricted to an inclusive key range.
 // Level-0 items cover their whole bucket; a bucket with too many distinct keys for shared memory is
 // split by further key bits into several items that each re-scan the bucket (rare path).
-// beg/end are VIRTUAL record indices.  On one GPU they are physical too.  On a row shard the bucket's
-// records arrive as one sorted run per source rank; the runs of a bucket are laid end to end in the
-// virtual index space and (seg_voff, seg_pstart)[seg0 .. seg0 + n_runs] translate to physical.
-struct Item { uint64_t beg, end, key_lo, key_hi; uint64_t seg0; uint64_t key_base; uint64_t scratch; };   // key = key_base | (prec >> (sb+2))
+struct Item { uint64_t beg, end, key_lo, key_hi; uint64_t key_base; uint64_t scratch; };   // key = key_base | (prec >> (sb+2))
 constexpr uint64_t NO_SCRATCH = ~0ULL;   // scratch: where the count pass leaves this item's sorted distinct keys for the emit pass
-constexpr int MAX_RUNS = 8;
-struct SegMap { int w; uint64_t v[MAX_RUNS + 1]; uint64_t p[MAX_RUNS]; };
-__device__ __forceinline__ void segmap_load(SegMap& m, const Item& it, const uint64_t* __restrict__ seg_voff,
-                                            const uint64_t* __restrict__ seg_pstart, int n_runs) {
-    m.w = n_runs;
-    if (n_runs > 1 && threadIdx.x <= (unsigned)n_runs) {
-        m.v[threadIdx.x] = seg_voff[it.seg0 + threadIdx.x];
-        if (threadIdx.x < (unsigned)n_runs) m.p[threadIdx.x] = seg_pstart[it.seg0 + threadIdx.x];
-    }
-}
-__device__ __forceinline__ uint64_t seg_phys(const SegMap& m, uint64_t vi) {
-    if (m.w <= 1) return vi;
-    int r = 0;
-#pragma unroll
-    for (int j = 1; j < MAX_RUNS; j++) r += (j < m.w && vi >= m.v[j]) ? 1 : 0;
-    return m.p[r] + (vi - m.v[r]);
-}
 constexpr uint32_t COUNT_OVERFLOW = 0xFFFFFFFFu;
 
-__global__ void make_items_kernel(const uint64_t* __restrict__ off, uint32_t n_buckets, int key_bits, int P, int P2, int low_bits,
+// bucket j of this array is prefix bucket b0 + j of the whole key space (b0 > 0 on a row shard)
+__global__ void make_items_kernel(const uint64_t* __restrict__ off, uint32_t n_buckets, uint64_t b0, int key_bits, int P, int P2, int low_bits,
                                   Item* __restrict__ items) {
-    uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
-    if (b >= n_buckets) return;
+    uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n_buckets) return;
+    const uint64_t b = b0 + j;
     const int low = key_bits - P;                          // key bits below the bucket prefix
     Item it;
-    it.beg = off[b]; it.end = off[b + 1];
-    it.key_lo = (uint64_t)b << low;
+    it.beg = off[j]; it.end = off[j + 1];
+    it.key_lo = b << low;
     it.key_hi = it.key_lo | ((low >= 64) ? ~0ULL : ((1ULL << low) - 1ULL));
-    if (b == n_buckets - 1) it.key_hi = ~0ULL >> 4;       // top bucket also holds nothing above the key space
-    it.seg0 = 0;
-    it.key_base = (uint64_t)(b >> P2) << low_bits;
+    if (b == (1ULL << P) - 1ULL) it.key_hi = ~0ULL >> 4;  // top bucket also holds nothing above the key space
+    it.key_base = (b >> P2) << low_bits;
     it.scratch = it.beg;                                   // distinct keys <= records: the bucket's own offset is room enough
-    items[b] = it;
+    items[j] = it;
 }
 
 // ---- pass 1: distinct keys per item
 __global__ void __launch_bounds__(MG_THREADS)
-bucket_count_kernel(const uint64_t* __restrict__ rec, const Item* __restrict__ items, const uint64_t* __restrict__ seg_voff,
-                    const uint64_t* __restrict__ seg_pstart, int n_runs, int sb, uint32_t limit,
+bucket_count_kernel(const uint64_t* __restrict__ rec, const Item* __restrict__ items, int sb, uint32_t limit,
                     uint32_t* __restrict__ n_rows, uint32_t* __restrict__ need_split, uint64_t* __restrict__ scratch_keys) {
     __shared__ uint64_t s_tab[COUNT_CAP];
     __shared__ uint32_t s_n, s_over, s_u;
     extern __shared__ uint64_t s_list[];                   // [COUNT_CAP]: the item's distinct keys, sorted
-    __shared__ SegMap s_map;
     const Item it = items[blockIdx.x];
     if (it.beg == it.end) { if (threadIdx.x == 0) n_rows[blockIdx.x] = 0; return; }
-    segmap_load(s_map, it, seg_voff, seg_pstart, n_runs);
     for (int i = threadIdx.x; i < COUNT_CAP; i += MG_THREADS) s_tab[i] = KEY_EMPTY;
     if (threadIdx.x == 0) { s_n = 0; s_over = 0; }
     __syncthreads();
@@ -96,7 +74,7 @@ bucket_count_kernel(const uint64_t* __restrict__ rec, const Item* __restrict__ i
 #pragma unroll
         for (int j = 0; j < MG_UNROLL; j++) {                      // all loads first: memory-level parallelism
             uint64_t i = base + (uint64_t)j * MG_THREADS;
-            rr[j] = i < it.end ? rec[seg_phys(s_map, i)] : 0;
+            rr[j] = i < it.end ? rec[i] : 0;
         }
         // probe the MG_UNROLL records together: independent shared loads overlap their latency; a key
         // already present (the common case: one record per sample per key) needs nothing else
@@ -258,8 +236,7 @@ __device__ __forceinline__ uint32_t pal_letter(uint32_t m) {
 //      palindromic keys, ska_dict.rs:85-113) and count the non-missing cells per row.
 // dynamic smem: tab u64[cap] | lkey u64[cap/2] | rank u16[cap] | lslot u16[cap/2] | cnt u32[cap/2]
 __global__ void __launch_bounds__(MG_THREADS)
-bucket_emit_kernel(const uint64_t* __restrict__ rec, const Item* __restrict__ items,
-                   const uint64_t* __restrict__ seg_voff, const uint64_t* __restrict__ seg_pstart, int n_runs, int sb,
+bucket_emit_kernel(const uint64_t* __restrict__ rec, const Item* __restrict__ items, int sb,
                    const uint64_t* __restrict__ row_off, int log_cap, uint32_t n_samples, int k, int rc,
                    uint64_t* __restrict__ out_keys, uint8_t* __restrict__ out_var, uint32_t* __restrict__ out_cnt,
                    const uint64_t* __restrict__ scratch_keys) {
@@ -271,7 +248,6 @@ bucket_emit_kernel(const uint64_t* __restrict__ rec, const Item* __restrict__ it
     uint16_t* s_rank = reinterpret_cast<uint16_t*>(s_cnt + half);
     uint16_t* s_lslot = s_rank + cap;
     __shared__ uint32_t s_u;
-    __shared__ SegMap s_map;
 
     const uint32_t b = blockIdx.x;
     const Item it = items[b];
@@ -279,7 +255,6 @@ bucket_emit_kernel(const uint64_t* __restrict__ rec, const Item* __restrict__ it
     const uint64_t row_base = row_off[b];
     const uint32_t u = (uint32_t)(row_off[b + 1] - row_base);     // distinct keys, from the count pass
     if (u == 0) return;
-    segmap_load(s_map, it, seg_voff, seg_pstart, n_runs);
 
     for (uint32_t i = threadIdx.x; i < cap; i += MG_THREADS) s_tab[i] = KEY_EMPTY;
     if (threadIdx.x == 0) s_u = 0;
@@ -303,7 +278,7 @@ bucket_emit_kernel(const uint64_t* __restrict__ rec, const Item* __restrict__ it
 #pragma unroll
         for (int j = 0; j < MG_UNROLL; j++) {
             uint64_t i = base + (uint64_t)j * MG_THREADS;
-            rr[j] = i < end ? rec[seg_phys(s_map, i)] : 0;
+            rr[j] = i < end ? rec[i] : 0;
         }
         uint64_t kk[MG_UNROLL], cur[MG_UNROLL]; uint32_t sl[MG_UNROLL];
 #pragma unroll
@@ -391,7 +366,7 @@ bucket_emit_kernel(const uint64_t* __restrict__ rec, const Item* __restrict__ it
 #pragma unroll
         for (int j = 0; j < MG_UNROLL; j++) {
             uint64_t i = base + (uint64_t)j * MG_THREADS;
-            rr[j] = i < end ? rec[seg_phys(s_map, i)] : 0;
+            rr[j] = i < end ? rec[i] : 0;
         }
         uint64_t kk[MG_UNROLL], cur[MG_UNROLL]; uint32_t sl[MG_UNROLL], rk[MG_UNROLL];
 #pragma unroll
@@ -481,8 +456,7 @@ static int choose_prefix_bits(uint64_t n_pos, int key_bits, uint64_t target) {
 
 // (2) of the file header: count distinct keys per item (splitting items that do not fit shared memory),
 // scan to row offsets, emit rows.  `items` is a device array in ascending key order.
-static void merge_items(const uint64_t* rec, Item* items, uint32_t n_items, const uint64_t* seg_voff, const uint64_t* seg_pstart,
-                        int n_runs, int sb, uint64_t n_samples, uint32_t k, bool rc, Array& out, uint64_t* scratch_keys) {
+static void merge_items(const uint64_t* rec, Item* items, uint32_t n_items, int sb, uint64_t n_samples, uint32_t k, bool rc, Array& out, uint64_t* scratch_keys) {
     Context& c = ctx();
     // bytes of shared memory per table slot in the emit kernel: tab 8 + rank 2 + (lkey 8 + lslot 2 + cnt 4)/2
     const size_t slot_bytes = 17;
@@ -496,8 +470,7 @@ static void merge_items(const uint64_t* rec, Item* items, uint32_t n_items, cons
     uint32_t h_flags[2] = {0, 0};
     for (int round = 0; n_items > 0; round++) {
         SKA_CUDA(cudaMemsetAsync(flags, 0, 8, c.stream));
-        SKA_LAUNCH(bucket_count_kernel, n_items, MG_THREADS, COUNT_CAP * 8, rec, items, seg_voff, seg_pstart, n_runs, sb, limit, n_rows,
-                   flags, scratch_keys);
+        SKA_LAUNCH(bucket_count_kernel, n_items, MG_THREADS, COUNT_CAP * 8, rec, items, sb, limit, n_rows, flags, scratch_keys);
         SKA_CUDA(cudaMemcpyAsync(h_flags, flags, 8, cudaMemcpyDeviceToHost, c.stream));
         SKA_CUDA(cudaStreamSynchronize(c.stream));
         if (!h_flags[0]) break;
@@ -550,7 +523,7 @@ static void merge_items(const uint64_t* rec, Item* items, uint32_t n_items, cons
         size_t smem = ((size_t)1 << log_cap) * slot_bytes;
         if (log_cap > max_log_cap) throw Error("internal: item larger than the shared-memory table");
         SKA_CUDA(cudaFuncSetAttribute(bucket_emit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        SKA_LAUNCH(bucket_emit_kernel, n_items, MG_THREADS, smem, rec, items, seg_voff, seg_pstart, n_runs, sb, row_off, log_cap,
+        SKA_LAUNCH(bucket_emit_kernel, n_items, MG_THREADS, smem, rec, items, sb, row_off, log_cap,
                    (uint32_t)n_samples, (int)k, rc ? 1 : 0, out.keys.p, out.variants.p, out.counts.p, (const uint64_t*)scratch_keys);
     }
     timer().end();
@@ -558,10 +531,13 @@ static void merge_items(const uint64_t* rec, Item* items, uint32_t n_items, cons
 
 int merge_prefix_bits(uint64_t n_records_total, uint32_t k, uint64_t n_samples_total) {
     const int key_bits = 2 * ((int)k - 1);
-    // ~8-16 K records per bucket for up to 128 samples; more samples mean more records per distinct k-mer (what the
-    // shared-memory tables hold is distinct k-mers), so buckets may hold proportionally more records
-    const uint64_t scale = std::min<uint64_t>(16, std::max<uint64_t>(1, n_samples_total / 128));
-    int P = choose_prefix_bits(n_records_total, key_bits, 16384 * scale);
+    (void)n_samples_total;
+    // ~8-16 K records per bucket whatever the number of samples (measured, profiles/README.md "wide rows": with 1024
+    // columns the same bucket size keeps the rows a CTA ORs into L2-resident; larger buckets thrash, smaller ones
+    // cost more in the partition).  Past 2^16 buckets a partition pass would need more than 8 bits per digit, which
+    // costs more than it saves: let buckets grow to 32 K records first.
+    int P = choose_prefix_bits(n_records_total, key_bits, 16384);
+    if (P > 16) P = std::max(16, choose_prefix_bits(n_records_total, key_bits, 32768));
     if (const char* e = getenv("SKA_PREFIX_BITS")) { int v = atoi(e); if (v >= 0 && v <= key_bits && v <= 22) P = v; }   // tuning/tests
     return std::min(std::min(P, 22), key_bits);
 }
@@ -579,62 +555,36 @@ void build_array_from_records(uint64_t* rec, uint64_t n_rec, const uint64_t* d_s
 
     timer().begin("bucket_offsets");
     Item* items = arena().take_n<Item>(n_buckets);
-    SKA_LAUNCH(make_items_kernel, (n_buckets + 255) / 256, 256, 0, off, n_buckets, pl.key_bits, pl.P, pl.P2, pl.low_bits, items);
+    SKA_LAUNCH(make_items_kernel, (n_buckets + 255) / 256, 256, 0, off, n_buckets, (uint64_t)0, pl.key_bits, pl.P, pl.P2, pl.low_bits, items);
     timer().end();
 
     // the buffer the partition no longer needs doubles as the count -> emit key scratch (same length as the records)
     uint64_t* scratch = (prec == rec) ? part_a : rec;
-    merge_items(prec, items, n_buckets, nullptr, nullptr, 1, pl.sb, n_samples_total, k, rc, out, scratch);
+    merge_items(prec, items, n_buckets, pl.sb, n_samples_total, k, rc, out, scratch);
 }
 
-// Row shard: the received records are `n_runs` runs (one per source rank), each grouped by the same plan
-// and covering buckets [bucket_lo, bucket_hi).  run_off[r * (nb + 1) + j] is the offset, inside the receive
-// buffer, of bucket (bucket_lo + j) of run r (nb = bucket_hi - bucket_lo).
-void build_array_from_runs(const uint64_t* prec, int n_runs, const uint64_t* run_off, uint32_t bucket_lo, uint32_t bucket_hi,
+// Row shard: the received records are `n_runs` runs (one per source rank) of first-pass output, each holding
+// its pieces of the first-level regions [region_lo, region_hi) in order.  run_off[w * (nr + 1) + j] is the offset,
+// inside the receive buffer, of region (region_lo + j) of run w (nr = region_hi - region_lo).  The second
+// partition pass runs here, over all runs at once, so the merge below sees one run.  `prec` is overwritten
+// (it becomes the count -> emit key scratch).
+void build_array_from_runs(uint64_t* prec, uint64_t n_rec, int n_runs, const uint64_t* run_off, uint32_t region_lo, uint32_t region_hi,
                            const PartPlan& pl, uint64_t n_samples, uint32_t k, bool rc, Array& out) {
-    Context& c = ctx();
-    if (n_runs < 1 || n_runs > MAX_RUNS) throw Error("row shard supports 1.." + std::to_string(MAX_RUNS) + " source ranks");
-    const int low = pl.key_bits - pl.P;
-    const uint32_t nb = bucket_hi - bucket_lo;
-    const int W = std::max(n_runs, 2);                    // the map is only consulted for W > 1: pad with an empty run
-    std::vector<Item> h_items(nb);
-    std::vector<uint64_t> h_voff((size_t)nb * (W + 1)), h_pstart((size_t)nb * (W + 1));
-    uint64_t v = 0;
-    for (uint32_t j = 0; j < nb; j++) {
-        Item& it = h_items[j];
-        const uint64_t b = (uint64_t)bucket_lo + j;
-        it.key_lo = b << low;
-        it.key_hi = it.key_lo | ((low >= 64) ? ~0ULL : ((1ULL << low) - 1ULL));
-        if (b == (1ull << pl.P) - 1) it.key_hi = ~0ULL >> 4;
-        it.key_base = (b >> pl.P2) << pl.low_bits;
-        it.seg0 = (uint64_t)j * (W + 1);
-        it.beg = v;
-        it.scratch = v;
-        for (int r = 0; r < W; r++) {
-            h_voff[it.seg0 + r] = v;
-            if (r < n_runs) {
-                const uint64_t* ro = run_off + (size_t)r * (nb + 1);
-                h_pstart[it.seg0 + r] = ro[j];
-                v += ro[j + 1] - ro[j];
-            } else h_pstart[it.seg0 + r] = 0;
-        }
-        h_voff[it.seg0 + W] = v;
-        h_pstart[it.seg0 + W] = 0;
-        it.end = v;
-    }
+    if (n_runs < 1) throw Error("row shard needs at least one run");
+    const uint32_t nr = region_hi - region_lo;
+    const uint32_t nb = nr << pl.P2;
+    timer().begin("partition");
+    uint64_t* part = arena().take_n<uint64_t>(std::max<uint64_t>(n_rec, 1));
+    uint64_t* off = nullptr;
+    partition_runs(prec, n_runs, run_off, nr, pl, part, &off);
+    timer().end();
     timer().begin("bucket_offsets");
     Item* items = arena().take_n<Item>(std::max<uint32_t>(nb, 1));
-    uint64_t* d_voff = arena().take_n<uint64_t>(std::max<size_t>(h_voff.size(), 1));
-    uint64_t* d_pstart = arena().take_n<uint64_t>(std::max<size_t>(h_pstart.size(), 1));
-    if (nb) {
-        SKA_CUDA(cudaMemcpyAsync(items, h_items.data(), nb * sizeof(Item), cudaMemcpyHostToDevice, c.stream));
-        SKA_CUDA(cudaMemcpyAsync(d_voff, h_voff.data(), h_voff.size() * 8, cudaMemcpyHostToDevice, c.stream));
-        SKA_CUDA(cudaMemcpyAsync(d_pstart, h_pstart.data(), h_pstart.size() * 8, cudaMemcpyHostToDevice, c.stream));
-        SKA_CUDA(cudaStreamSynchronize(c.stream));
-    }
+    if (nb)
+        SKA_LAUNCH(make_items_kernel, (nb + 255) / 256, 256, 0, off, nb, (uint64_t)region_lo << pl.P2, pl.key_bits, pl.P, pl.P2, pl.low_bits,
+                   items);
     timer().end();
-    uint64_t* scratch = arena().take_n<uint64_t>(std::max<uint64_t>(v, 1));
-    merge_items(prec, items, nb, d_voff, d_pstart, W, pl.sb, n_samples, k, rc, out, scratch);
+    merge_items(part, items, nb, pl.sb, n_samples, k, rc, out, prec);
 }
 
 }  // namespace ska

@@ -2,8 +2,10 @@
 // CTA merge one key range in shared memory (merge.cu).  Hand-written replacement for the library radix
 // sort used earlier in this round (DESIGN.md "partition").
 //
-// Two MSD passes of P1 and P2 bits (any widths up to 11, so P = 19..21 for row shards is still two
-// passes), each pass = histogram + scatter:
+// Two MSD passes of P1 and P2 bits (any widths up to 11), each pass = histogram + scatter.  On several GPUs
+// the exchange sits BETWEEN the passes: a rank runs pass 1 on its own samples, ships every first-level
+// region to the rank that owns it, and pass 2 runs at the owner over the regions' pieces from all source
+// ranks ("segments") -- so the second pass also concatenates the runs and the merge sees one run.
 //   * records move as ONE packed u64: after the first digit is implied by the bucket, its bits hold the
 //     sample id:   prec = key_low << (SB+2) | sample_id << 2 | middle_code,
 //     key_low = key without its top P1 bits, SB = bits of a sample id.  16 B of traffic per record and pass
@@ -30,31 +32,31 @@ constexpr int PT_MAX_BITS = 11;
 constexpr uint32_t PT_NONE = 0xFFFFFFFFu;
 
 // ---------------------------------------------------------------------------------------------- histograms
-// src: K1 records (pass 1) or packed records (pass 2).  For pass 2 tiles are enumerated per region so that a
-// tile never straddles two first-level buckets: tile_pref[d1] = number of tiles before region d1.
+// src: K1 records (pass 1) or packed records (pass 2).  For pass 2 tiles are enumerated per SEGMENT (a contiguous
+// piece of one first-level region) so that a tile never straddles two regions: tile_pref[s] = tiles before segment s.
+// On one GPU a segment is a whole region (region == NULL: region = segment index).
 struct DigitFn {
     int pass;            // 1: digit = rec >> shift (K1 record, REC_SENTINEL skipped); 2: digit = (prec >> shift) & mask
     int shift;
     uint32_t mask;
     __device__ __forceinline__ uint32_t operator()(uint64_t r) const {
         if (pass == 1) return r == REC_SENTINEL ? PT_NONE : (uint32_t)(r >> shift);
-        return (uint32_t)(r >> shift) & mask;
+        return mask ? (uint32_t)(r >> shift) & mask : 0u;
     }
 };
+struct Segs { const uint64_t* tile_pref; const uint64_t* beg; const uint64_t* end; const uint32_t* region; uint32_t n; };
 
-__device__ __forceinline__ void tile_range(uint64_t tile, const uint64_t* __restrict__ tile_pref, const uint64_t* __restrict__ region_off,
-                                           uint32_t n_regions, uint64_t n_total, uint64_t& beg, uint64_t& end, uint32_t& region) {
-    if (!tile_pref) { beg = tile * PT_TILE; end = min(n_total, beg + PT_TILE); region = 0; return; }
-    uint32_t lo = 0, hi = n_regions;                        // last region with tile_pref[region] <= tile
-    while (hi - lo > 1) { uint32_t m = (lo + hi) >> 1; if (tile_pref[m] <= tile) lo = m; else hi = m; }
-    region = lo;
-    beg = region_off[lo] + (tile - tile_pref[lo]) * PT_TILE;
-    end = min(region_off[lo + 1], beg + PT_TILE);
+__device__ __forceinline__ void tile_range(uint64_t tile, const Segs& sg, uint64_t n_total, uint64_t& beg, uint64_t& end, uint32_t& region) {
+    if (!sg.tile_pref) { beg = tile * PT_TILE; end = min(n_total, beg + PT_TILE); region = 0; return; }
+    uint32_t lo = 0, hi = sg.n;                             // last segment with tile_pref[segment] <= tile
+    while (hi - lo > 1) { uint32_t m = (lo + hi) >> 1; if (sg.tile_pref[m] <= tile) lo = m; else hi = m; }
+    region = sg.region ? sg.region[lo] : lo;
+    beg = sg.beg[lo] + (tile - sg.tile_pref[lo]) * PT_TILE;
+    end = min(sg.end[lo], beg + PT_TILE);
 }
 
 __global__ void __launch_bounds__(PT_THREADS)
-part_hist_kernel(const uint64_t* __restrict__ src, uint64_t n_total, uint64_t n_tiles, const uint64_t* __restrict__ tile_pref,
-                 const uint64_t* __restrict__ region_off, uint32_t n_regions, DigitFn fn, int bits,
+part_hist_kernel(const uint64_t* __restrict__ src, uint64_t n_total, uint64_t n_tiles, Segs sg, DigitFn fn, int bits,
                  unsigned long long* __restrict__ hist /* [n_regions or 1][1 << bits] */) {
     extern __shared__ uint32_t s_cnt[];                     // [D]
     const uint32_t D = 1u << bits;
@@ -75,7 +77,7 @@ part_hist_kernel(const uint64_t* __restrict__ src, uint64_t n_total, uint64_t n_
     };
     for (uint64_t t = t_beg; t < t_end; t++) {
         uint64_t beg, end; uint32_t region;
-        tile_range(t, tile_pref, region_off, n_regions, n_total, beg, end, region);
+        tile_range(t, sg, n_total, beg, end, region);
         if (region != cur_region) { if (cur_region != PT_NONE) flush(cur_region); cur_region = region; }
         uint64_t rr[PT_ITEMS];
 #pragma unroll
@@ -102,8 +104,7 @@ struct PackFn {               // pass 1: K1 record -> packed record (needs the s
 
 template <int PASS>
 __global__ void __launch_bounds__(PT_THREADS)
-part_scatter_kernel(const uint64_t* __restrict__ src, uint64_t n_total, const uint64_t* __restrict__ tile_pref,
-                    const uint64_t* __restrict__ region_off, uint32_t n_regions, DigitFn fn, int bits, PackFn pk,
+part_scatter_kernel(const uint64_t* __restrict__ src, uint64_t n_total, Segs sg, DigitFn fn, int bits, PackFn pk,
                     const uint64_t* __restrict__ sample_off, uint32_t n_samples,
                     unsigned long long* __restrict__ cursor /* [n_regions or 1][1 << bits], preset to bucket starts */,
                     uint64_t* __restrict__ dst) {
@@ -118,7 +119,7 @@ part_scatter_kernel(const uint64_t* __restrict__ src, uint64_t n_total, const ui
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     uint64_t beg, end; uint32_t region;
-    tile_range(blockIdx.x, tile_pref, region_off, n_regions, n_total, beg, end, region);
+    tile_range(blockIdx.x, sg, n_total, beg, end, region);
     for (uint32_t i = threadIdx.x; i < D; i += PT_THREADS) s_acnt[i] = 0;
     if (PASS == 1 && threadIdx.x == 0) {                     // sample ids of the tile's first and last position
         uint64_t pf = beg, pl = end - 1;
@@ -263,57 +264,116 @@ PartPlan make_part_plan(uint32_t k, int prefix_bits, uint64_t n_samples_total) {
     return pl;
 }
 
-// rec: K1 output (n_pos entries, linear).  Returns the packed records grouped by the P-bit prefix in `*out`
-// (arena memory) and the 2^P + 1 bucket offsets on the device in `*d_off`.
-void partition_records(const uint64_t* rec, uint64_t n_pos, const uint64_t* d_sample_off, uint32_t n_samples_local, uint32_t sid_base,
-                       const PartPlan& pl, uint64_t* scratch /* n_pos u64 for the second pass, may be rec */, uint64_t** out, uint64_t** d_off,
-                       uint64_t** first_pass_buf) {
+static void set_scatter_attrs() {
+    SKA_CUDA(cudaFuncSetAttribute(part_scatter_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)scatter_smem(PT_MAX_BITS)));
+    SKA_CUDA(cudaFuncSetAttribute(part_scatter_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)scatter_smem(PT_MAX_BITS)));
+}
+
+// pass 1.  rec: K1 output (n_pos entries, linear) -> packed records grouped by the top P1 key bits in `*out`
+// (arena), region offsets `*d_off1` [2^P1 + 1] and tiles-before-region `*d_tile_pref` [2^P1 + 1] on the device.
+void partition_coarse(const uint64_t* rec, uint64_t n_pos, const uint64_t* d_sample_off, uint32_t n_samples_local, uint32_t sid_base,
+                      const PartPlan& pl, uint64_t** out, uint64_t** d_off1, uint64_t** d_tile_pref) {
     Context& c = ctx();
-    const uint32_t D1 = 1u << pl.P1, D2 = 1u << pl.P2, NB = 1u << pl.P;
+    const uint32_t D1 = 1u << pl.P1;
     unsigned long long* hist1 = arena().take_n<unsigned long long>(D1);
     unsigned long long* cur1 = arena().take_n<unsigned long long>(D1);
     uint64_t* off1 = arena().take_n<uint64_t>(D1 + 1);
     uint64_t* tile_pref = arena().take_n<uint64_t>(D1 + 1);
-    uint64_t* bucket_off = arena().take_n<uint64_t>((size_t)NB + 1);
     SKA_CUDA(cudaMemsetAsync(hist1, 0, D1 * 8, c.stream));
     const uint64_t n_tiles1 = (n_pos + PT_TILE - 1) / PT_TILE;
     DigitFn f1{1, 4 + pl.key_bits - pl.P1, 0xFFFFFFFFu};
     PackFn pk{pl.sb, pl.low_bits >= 64 ? ~0ULL : ((1ULL << pl.low_bits) - 1ULL), sid_base};
     const unsigned hist_grid = (unsigned)std::min<uint64_t>(std::max<uint64_t>(n_tiles1, 1), (uint64_t)c.sm_count * 4);
-    SKA_CUDA(cudaFuncSetAttribute(part_scatter_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)scatter_smem(PT_MAX_BITS)));
-    SKA_CUDA(cudaFuncSetAttribute(part_scatter_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)scatter_smem(PT_MAX_BITS)));
-    if (n_pos) {
-        SKA_LAUNCH(part_hist_kernel, hist_grid, PT_THREADS, D1 * 4, rec, n_pos, n_tiles1, (const uint64_t*)nullptr,
-                   (const uint64_t*)nullptr, 1u, f1, pl.P1, hist1);
-    }
+    set_scatter_attrs();
+    const Segs none{nullptr, nullptr, nullptr, nullptr, 1u};
+    if (n_pos) SKA_LAUNCH(part_hist_kernel, hist_grid, PT_THREADS, D1 * 4, rec, n_pos, n_tiles1, none, f1, pl.P1, hist1);
     SKA_LAUNCH(part_scan_kernel, 1, 1024, 0, hist1, D1, off1, cur1, tile_pref);
     uint64_t* a = arena().take_n<uint64_t>(std::max<uint64_t>(n_pos, 1));
     if (n_pos) {
-        SKA_LAUNCH((part_scatter_kernel<1>), (unsigned)n_tiles1, PT_THREADS, scatter_smem(pl.P1), rec, n_pos, (const uint64_t*)nullptr,
-                   (const uint64_t*)nullptr, 1u, f1, pl.P1, pk, d_sample_off, n_samples_local, cur1, a);
+        SKA_LAUNCH((part_scatter_kernel<1>), (unsigned)n_tiles1, PT_THREADS, scatter_smem(pl.P1), rec, n_pos, none, f1, pl.P1, pk,
+                   d_sample_off, n_samples_local, cur1, a);
     }
+    *out = a; *d_off1 = off1; *d_tile_pref = tile_pref;
+}
+
+// pass 2.  src: packed records; the segments (device arrays) say where the pieces of each of the `n_regions`
+// regions lie.  -> dst grouped by (region, next P2 key bits), `*d_bucket_off` [n_regions * 2^P2 + 1] on the device.
+void partition_fine(const uint64_t* src, const Segs& sg, uint64_t n_tiles2, uint32_t n_regions, const PartPlan& pl, uint64_t* dst,
+                    uint64_t** d_bucket_off) {
+    Context& c = ctx();
+    const uint32_t D2 = 1u << pl.P2;
+    const size_t NB = (size_t)n_regions * D2;
+    unsigned long long* hist2 = arena().take_n<unsigned long long>(std::max<size_t>(NB, 1));
+    unsigned long long* cur2 = arena().take_n<unsigned long long>(std::max<size_t>(NB, 1));
+    uint64_t* bucket_off = arena().take_n<uint64_t>(NB + 1);
+    SKA_CUDA(cudaMemsetAsync(hist2, 0, std::max<size_t>(NB, 1) * 8, c.stream));
+    set_scatter_attrs();
+    DigitFn f2{2, pl.sb + 2 + pl.low_bits - pl.P2, D2 - 1};
+    PackFn pk{pl.sb, 0, 0};
+    if (n_tiles2) {
+        const unsigned g2 = (unsigned)std::min<uint64_t>(n_tiles2, (uint64_t)c.sm_count * 4);
+        SKA_LAUNCH(part_hist_kernel, g2, PT_THREADS, D2 * 4, src, (uint64_t)0, n_tiles2, sg, f2, pl.P2, hist2);
+    }
+    SKA_LAUNCH(part_scan_kernel, 1, 1024, 0, hist2, (uint32_t)NB, bucket_off, cur2, (uint64_t*)nullptr);
+    if (n_tiles2) {
+        SKA_LAUNCH((part_scatter_kernel<2>), (unsigned)n_tiles2, PT_THREADS, scatter_smem(pl.P2), src, (uint64_t)0, sg, f2, pl.P2, pk,
+                   (const uint64_t*)nullptr, 0u, cur2, dst);
+    }
+    *d_bucket_off = bucket_off;
+}
+
+// both passes on one GPU.  Returns the packed records grouped by the P-bit prefix in `*out` (arena memory) and the
+// 2^P + 1 bucket offsets on the device in `*d_off`.
+void partition_records(const uint64_t* rec, uint64_t n_pos, const uint64_t* d_sample_off, uint32_t n_samples_local, uint32_t sid_base,
+                       const PartPlan& pl, uint64_t* scratch /* n_pos u64 for the second pass, may be rec */, uint64_t** out, uint64_t** d_off,
+                       uint64_t** first_pass_buf) {
+    Context& c = ctx();
+    const uint32_t D1 = 1u << pl.P1;
+    uint64_t *a = nullptr, *off1 = nullptr, *tile_pref = nullptr;
+    partition_coarse(rec, n_pos, d_sample_off, n_samples_local, sid_base, pl, &a, &off1, &tile_pref);
     if (first_pass_buf) *first_pass_buf = a;
     if (pl.P2 == 0) { *out = a; *d_off = off1; return; }
-
-    // second level: every first-level region is partitioned by the next P2 bits
-    unsigned long long* hist2 = arena().take_n<unsigned long long>(NB);
-    unsigned long long* cur2 = arena().take_n<unsigned long long>(NB);
-    SKA_CUDA(cudaMemsetAsync(hist2, 0, (size_t)NB * 8, c.stream));
     uint64_t n_tiles2 = 0;
     SKA_CUDA(cudaMemcpyAsync(&n_tiles2, tile_pref + D1, 8, cudaMemcpyDeviceToHost, c.stream));
     SKA_CUDA(cudaStreamSynchronize(c.stream));
-    DigitFn f2{2, pl.sb + 2 + pl.low_bits - pl.P2, D2 - 1};
-    if (n_tiles2) {
-        const unsigned g2 = (unsigned)std::min<uint64_t>(n_tiles2, (uint64_t)c.sm_count * 4);
-        SKA_LAUNCH(part_hist_kernel, g2, PT_THREADS, D2 * 4, a, n_pos, n_tiles2, tile_pref, off1, D1, f2, pl.P2, hist2);
-    }
-    SKA_LAUNCH(part_scan_kernel, 1, 1024, 0, hist2, NB, bucket_off, cur2, (uint64_t*)nullptr);
     uint64_t* b = scratch ? scratch : arena().take_n<uint64_t>(std::max<uint64_t>(n_pos, 1));
-    if (n_tiles2) {
-        SKA_LAUNCH((part_scatter_kernel<2>), (unsigned)n_tiles2, PT_THREADS, scatter_smem(pl.P2), a, n_pos, tile_pref, off1, D1, f2, pl.P2,
-                   pk, (const uint64_t*)nullptr, 0u, cur2, b);
+    const Segs sg{tile_pref, off1, off1 + 1, nullptr, D1};
+    partition_fine(a, sg, n_tiles2, D1, pl, b, d_off);
+    *out = b;
+}
+
+// pass 2 at the owner of regions [region_lo, region_lo + nr): `n_runs` received runs, run w holding its pieces of
+// those regions in order; h_run_off[w * (nr + 1) + j] = offset in `src` of region (region_lo + j) of run w.
+// -> dst grouped by the full P-bit prefix (one run), bucket offsets [nr * 2^P2 + 1] on the device.
+void partition_runs(const uint64_t* src, int n_runs, const uint64_t* h_run_off, uint32_t nr, const PartPlan& pl, uint64_t* dst,
+                    uint64_t** d_bucket_off) {
+    Context& c = ctx();
+    std::vector<uint64_t> beg, end, pref;
+    std::vector<uint32_t> region;
+    uint64_t tiles = 0;
+    for (uint32_t r = 0; r < nr; r++)                       // region-major: a CTA's run of tiles changes region rarely
+        for (int w = 0; w < n_runs; w++) {
+            const uint64_t b0 = h_run_off[(size_t)w * (nr + 1) + r], e0 = h_run_off[(size_t)w * (nr + 1) + r + 1];
+            if (e0 < b0) throw Error("run offsets must ascend");
+            if (e0 == b0) continue;
+            beg.push_back(b0); end.push_back(e0); region.push_back(r); pref.push_back(tiles);
+            tiles += (e0 - b0 + PT_TILE - 1) / PT_TILE;
+        }
+    pref.push_back(tiles);
+    const uint32_t ns = (uint32_t)beg.size();
+    uint64_t* d_beg = arena().take_n<uint64_t>(std::max<uint32_t>(ns, 1));
+    uint64_t* d_end = arena().take_n<uint64_t>(std::max<uint32_t>(ns, 1));
+    uint64_t* d_pref = arena().take_n<uint64_t>(ns + 1);
+    uint32_t* d_region = arena().take_n<uint32_t>(std::max<uint32_t>(ns, 1));
+    if (ns) {
+        SKA_CUDA(cudaMemcpyAsync(d_beg, beg.data(), ns * 8, cudaMemcpyHostToDevice, c.stream));
+        SKA_CUDA(cudaMemcpyAsync(d_end, end.data(), ns * 8, cudaMemcpyHostToDevice, c.stream));
+        SKA_CUDA(cudaMemcpyAsync(d_region, region.data(), ns * 4, cudaMemcpyHostToDevice, c.stream));
     }
-    *out = b; *d_off = bucket_off;
+    SKA_CUDA(cudaMemcpyAsync(d_pref, pref.data(), (ns + 1) * 8, cudaMemcpyHostToDevice, c.stream));
+    const Segs sg{d_pref, d_beg, d_end, d_region, std::max<uint32_t>(ns, 1)};
+    partition_fine(src, sg, tiles, nr, pl, dst, d_bucket_off);
+    SKA_CUDA(cudaStreamSynchronize(c.stream));              // the host vectors above must outlive their copies
 }
 
 }  // namespace ska

@@ -5,12 +5,14 @@ The reference is single-node shared memory (README.md:124); its build_and_merge
 (src/merge_ska_dict.rs:354-417) has exactly one point where data from different samples must meet --
 rows of the merged dictionary are keyed by split k-mer.  Here:
 
-  1. every rank extracts the records of ITS samples (K1) and sorts them by the top `prefix_bits` bits of
-     the key; the per-bucket record counts are summed over ranks (all-reduce) and cut into `world`
-     contiguous key ranges of equal record count -> owner of every bucket;
+  1. every rank extracts the records of ITS samples (K1) and runs the FIRST of the two partition passes:
+     records grouped by the top `region_bits` bits of the key ("regions").  The ranks' region offsets are
+     all-gathered (a few KB); summed they are cut into `world` contiguous key ranges of equal record count
+     -> owner of every region; every rank derives all send/receive counts and run offsets from the same table;
   2. ONE all-to-all moves each record range to its owner (one packed u64 per record, sample id inside);
-  3. every rank merges what it received into its slab of rows with ALL samples' columns.  Filters are
-     row-local; distances are per-pair integer sums over rows, so slabs add up with one all-reduce.
+  3. the owner runs the SECOND partition pass over the runs it received (this also concatenates them) and
+     merges the buckets into its slab of rows with ALL samples' columns.  Filters are row-local; distances
+     are per-pair integer sums over rows, so slabs add up with one all-reduce.
 
 Slabs are ascending key ranges in rank order: concatenating them gives the canonical array, which is
 how results are compared with the single-GPU path (identical, not merely equivalent).
@@ -39,17 +41,16 @@ class GpuBackend:
     device = "cuda"
 
     def extract(self, samples, k, rc, sample_base, n_samples_total, prefix_bits):
-        """-> (packed records int64 tensor grouped by key prefix, bucket offsets uint64[2^P + 1])"""
+        """-> (packed records int64 tensor grouped by region, region offsets uint64[2^region_bits + 1])"""
         import ctypes as C
         batch = samples if isinstance(samples, api.SeqBatch) else api.SeqBatch(samples)
         h = C.c_void_p()
         api._check(api.lib().skagpu_extract_records(batch._h, k, int(rc), sample_base, n_samples_total, prefix_bits, C.byref(h)))
         n = C.c_uint64()
         rec_p = C.c_void_p()
-        pb = C.c_int()
-        api._check(api.lib().skagpu_records_info(h, C.byref(n), C.byref(rec_p), C.byref(pb), None))
-        assert pb.value == prefix_bits, "prefix_bits must come from prefix_bits()"
-        off = np.zeros((1 << prefix_bits) + 1, dtype=np.uint64)
+        rb = C.c_int()
+        api._check(api.lib().skagpu_records_info(h, C.byref(n), C.byref(rec_p), C.byref(rb), None))
+        off = np.zeros((1 << rb.value) + 1, dtype=np.uint64)
         api._check(api.lib().skagpu_records_info(h, None, None, None, off.ctypes.data))
         api.lib().skagpu_records_free(h)        # frees only the handle; buffers live in the arena until the next build
         n = n.value
@@ -57,11 +58,12 @@ class GpuBackend:
                else torch.empty(0, dtype=torch.int64, device="cuda"))
         return rec, off
 
-    def merge(self, rec, run_offsets, bucket_lo, bucket_hi, prefix_bits, n_samples_total, k, rc, names):
+    def merge(self, rec, run_offsets, region_lo, region_hi, prefix_bits, n_samples_total, k, rc, names):
+        """second partition pass over the received runs + merge; `rec` is consumed (scratch)"""
         import ctypes as C
         h = C.c_void_p()
         ro = np.ascontiguousarray(run_offsets, dtype=np.uint64)
-        api._check(api.lib().skagpu_merge_records_dev(rec.data_ptr(), ro.shape[0], ro.ctypes.data, bucket_lo, bucket_hi,
+        api._check(api.lib().skagpu_merge_records_dev(rec.data_ptr(), ro.shape[0], ro.ctypes.data, region_lo, region_hi,
                                                       prefix_bits, n_samples_total, k, int(rc), C.byref(h)))
         return api.MergeSkaArray(h, names)
 
@@ -92,19 +94,19 @@ def plan_owners(global_bucket_counts, world):
     return np.array(cuts, dtype=np.int64)
 
 
-def plan_owners_t(counts, world):
-    """plan_owners on a torch tensor (stays on its device; only world+1 integers come back to the host)"""
-    cum = torch.cumsum(counts, 0)
-    total = int(cum[-1].item()) if cum.numel() else 0
-    targets = torch.tensor([total * g // world for g in range(1, world)], dtype=cum.dtype, device=cum.device)
-    # first bucket index b with (records before b) >= target:  cum0 = [0, cum...]  ->  searchsorted(cum0, target, left)
-    b = torch.searchsorted(cum, targets, right=False) + 1
-    b = torch.where(targets <= 0, torch.zeros_like(b), b).cpu().numpy() if world > 1 else np.zeros(0, dtype=np.int64)
-    cuts = [0]
-    for x in b:
-        cuts.append(min(max(int(x), cuts[-1]), counts.numel()))
-    cuts.append(counts.numel())
-    return np.array(cuts, dtype=np.int64)
+def exchange_plan(all_off, world, rank):
+    """all_off: (world, n_regions + 1) region offsets of every rank's first-pass output.
+    -> (cuts, send_counts, recv_counts, run_offsets) for `rank`; identical arithmetic on every rank."""
+    all_off = np.asarray(all_off, dtype=np.int64)
+    counts = np.diff(all_off, axis=1)                      # (world, n_regions)
+    cuts = plan_owners(counts.sum(axis=0), world)          # region index where each owner's range starts
+    bounds = all_off[:, cuts]                              # (world, world + 1): record index, per source rank
+    send_counts = np.diff(bounds[rank])
+    recv_counts = bounds[:, rank + 1] - bounds[:, rank]
+    lo, hi = int(cuts[rank]), int(cuts[rank + 1])
+    run_base = np.concatenate([[0], np.cumsum(recv_counts)[:-1]])
+    run_offsets = all_off[:, lo:hi + 1] - bounds[:, rank][:, None] + run_base[:, None]
+    return cuts, send_counts, recv_counts, run_offsets.astype(np.uint64)
 
 
 def build_and_merge_sharded(backend, samples_local, names_all, sample_base, k, rc, prefix_bits=None, group=None,
@@ -133,31 +135,18 @@ def build_and_merge_sharded(backend, samples_local, names_all, sample_base, k, r
     lap("plan_ms")
     rec, off = backend.extract(samples_local, k, rc, sample_base, len(names_all), prefix_bits)
     lap("extract_ms")
-    counts = torch.from_numpy(np.diff(off).astype(np.int64)).to(dev)
-    dist.all_reduce(counts, group=group)
-    cuts = plan_owners_t(counts, world)
-    bounds = off[cuts].astype(np.int64)                   # record index where each owner's range starts
-    send_counts = np.diff(bounds)
-    sc = torch.from_numpy(send_counts).to(dev)
-    rc_ = torch.empty_like(sc)
-    dist.all_to_all_single(rc_, sc, group=group)
-    recv_counts = rc_.cpu().numpy()
+    mine = torch.from_numpy(off.astype(np.int64)).to(dev)
+    gathered = torch.empty(world * mine.numel(), dtype=torch.int64, device=dev)
+    dist.all_gather_into_tensor(gathered, mine, group=group)
+    all_off = gathered.cpu().numpy().reshape(world, -1)
+    cuts, send_counts, recv_counts, run_offsets = exchange_plan(all_off, world, rank)
     n_recv = int(recv_counts.sum())
     recv_rec = torch.empty(n_recv, dtype=torch.int64, device=dev)
     lap("owners_ms")
-    # records are grouped by prefix, so each owner's share is one contiguous range starting at bounds[0] == 0;
-    # one packed u64 per record (the sample id travels inside it)
-    dist.all_to_all_single(recv_rec, rec[:int(bounds[-1])], list(map(int, recv_counts)), list(map(int, send_counts)), group=group)
+    # records are grouped by region, so each owner's share is one contiguous range; one packed u64 per record
+    dist.all_to_all_single(recv_rec, rec[:int(all_off[rank, -1])], list(map(int, recv_counts)), list(map(int, send_counts)),
+                           group=group)
     lap("all_to_all_ms")
-    # every run stays sorted by prefix: ship its bucket offsets (relative to the run) so the owner never re-sorts
-    nb_send = np.diff(cuts) + 1                           # offsets per owner: nb_g + 1
-    rel = np.concatenate([off[cuts[g]:cuts[g + 1] + 1].astype(np.int64) - bounds[g] for g in range(world)])
-    nb_mine = int(cuts[rank + 1] - cuts[rank])
-    recv_off = torch.empty(world * (nb_mine + 1), dtype=torch.int64, device=dev)
-    dist.all_to_all_single(recv_off, torch.from_numpy(rel).to(dev), [nb_mine + 1] * world, list(map(int, nb_send)), group=group)
-    run_base = np.concatenate([[0], np.cumsum(recv_counts)[:-1]]).astype(np.int64)
-    run_offsets = (recv_off.cpu().numpy().reshape(world, nb_mine + 1) + run_base[:, None]).astype(np.uint64)
-    lap("offsets_ms")
     arr = backend.merge(recv_rec, run_offsets, int(cuts[rank]), int(cuts[rank + 1]), prefix_bits, len(names_all),
                         k, rc, names_all)
     lap("merge_ms")

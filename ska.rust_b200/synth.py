@@ -1,8 +1,14 @@
-"""Deterministic synthetic inputs: star-model bacterial genomes.
+"""Deterministic synthetic inputs: star- and tree-model bacterial genomes.
 
-ancestor = i.i.d. uniform {A,C,G,T} of length G; sample i = ancestor with every position independently
-substituted (prob `snp_rate`) by one of the three other bases.  numpy PCG64 streams seeded from
-(seed, i), so any subset of samples can be regenerated independently (used for multi-GPU sharding).
+ancestor = i.i.d. uniform {A,C,G,T} of length G.
+star: sample i = ancestor with every position independently substituted (prob `snp_rate`) by one of the
+three other bases.
+tree: the samples are the leaves of a balanced binary tree of depth D = ceil(log2(n_total)); every branch
+adds substitutions at rate `snp_rate / D`, so every leaf is `snp_rate` from the root and close relatives
+share most of their SNPs (the number of distinct split k-mers grows with the number of BRANCHES, not with
+n_samples x SNPs per sample as under the star model).
+numpy PCG64 streams seeded from (seed, i) / (seed, depth, node), so any subset of samples can be regenerated
+independently (used for multi-GPU sharding).
 """
 import numpy as np
 
@@ -37,6 +43,42 @@ def star_genomes(n_samples, length, seed=0x5CA20000, snp_rate=0.001, first=0, ou
         else:
             res.append(_BASES[codes])
     return res
+
+
+def tree_sample_codes(anc, seed, i, n_total, snp_rate=0.001):
+    depth = max(1, int(np.ceil(np.log2(max(n_total, 2)))))
+    out = anc.copy()
+    n = len(anc)
+    for d in range(1, depth + 1):
+        node = i >> (depth - d)                 # the branch above node (d, node) on the path root -> leaf i
+        rng = np.random.Generator(np.random.PCG64([seed, 0x7EE, d, node]))
+        n_snp = rng.binomial(n, snp_rate / depth)
+        pos = rng.integers(0, n, size=n_snp)
+        shift = rng.integers(1, 4, size=n_snp, dtype=np.uint8)
+        out[pos] = (out[pos] + shift) & 3
+    return out
+
+
+def tree_genomes(n_samples, length, n_total, seed=0x5CA20000, snp_rate=0.001, first=0, out=None):
+    """leaves first .. first+n_samples-1 of the n_total-leaf tree; same return convention as star_genomes"""
+    anc = ancestor(length, seed)
+    res = []
+    for j in range(n_samples):
+        codes = tree_sample_codes(anc, seed, first + j, n_total, snp_rate)
+        if out is not None:
+            np.take(_BASES, codes, out=out[j])
+            res.append(out[j])
+        else:
+            res.append(_BASES[codes])
+    return res
+
+
+def genomes(population, n_samples, length, n_total, seed=0x5CA20000, first=0, out=None):
+    if population == "star":
+        return star_genomes(n_samples, length, seed=seed, first=first, out=out)
+    if population == "tree":
+        return tree_genomes(n_samples, length, n_total, seed=seed, first=first, out=out)
+    raise ValueError(f"unknown population model {population!r}")
 
 
 def write_fasta(path, name, seq, width=80):

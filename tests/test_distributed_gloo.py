@@ -86,12 +86,19 @@ class OracleBackend:
                 for key, mid in zip(w["key"], w["mid"]):
                     recs.append((key << 12) | ((sample_base + i) << 4) | (1 << int(mid)))
         rec = np.array(recs, dtype=np.uint64)
-        shift = 12 + 2 * (k - 1) - prefix_bits
-        prefix = (rec >> np.uint64(shift)).astype(np.int64)
-        order = np.argsort(prefix, kind="stable")
-        rec, prefix = rec[order], prefix[order]
-        off = np.searchsorted(prefix, np.arange((1 << prefix_bits) + 1)).astype(np.uint64)
+        # first pass only: grouped by REGION (the top region_bits of the key), any order inside a region
+        rec = rec[np.random.default_rng(sample_base).permutation(len(rec))]
+        region_bits = self.region_bits(prefix_bits)
+        shift = 12 + 2 * (k - 1) - region_bits
+        region = (rec >> np.uint64(shift)).astype(np.int64)
+        order = np.argsort(region, kind="stable")
+        rec, region = rec[order], region[order]
+        off = np.searchsorted(region, np.arange((1 << region_bits) + 1)).astype(np.uint64)
         return torch.from_numpy(rec.view(np.int64)), off
+
+    @staticmethod
+    def region_bits(prefix_bits):
+        return (prefix_bits + 1) // 2                     # like the library: the first of two passes
 
     def n_positions(self, samples):
         return sum(len(r) for recs in samples for r in recs)
@@ -99,17 +106,20 @@ class OracleBackend:
     def prefix_bits(self, n_records_total, k, n_samples_total):
         return min(6, 2 * (k - 1))
 
-    def merge(self, rec, run_offsets, bucket_lo, bucket_hi, prefix_bits, n_samples_total, k, rc, names):
+    def merge(self, rec, run_offsets, region_lo, region_hi, prefix_bits, n_samples_total, k, rc, names):
         rec = rec.numpy().view(np.uint64)
-        # the exchange plan must describe the receive buffer exactly: every run sorted by prefix, buckets in range
-        shift = 12 + 2 * (k - 1) - prefix_bits
-        nb = bucket_hi - bucket_lo
-        assert run_offsets.shape[1] == nb + 1
+        # the exchange plan must describe the receive buffer exactly: every run grouped by region, regions in range
+        shift = 12 + 2 * (k - 1) - self.region_bits(prefix_bits)
+        nr = region_hi - region_lo
+        assert run_offsets.shape[1] == nr + 1
+        covered = 0
         for r in range(run_offsets.shape[0]):
-            for j in range(nb):
+            assert int(run_offsets[r, 0]) == covered, "runs must tile the receive buffer in rank order"
+            for j in range(nr):
                 seg = rec[int(run_offsets[r, j]):int(run_offsets[r, j + 1])]
-                assert np.all((seg >> np.uint64(shift)) == np.uint64(bucket_lo + j))
-        assert int(run_offsets[-1, -1]) == len(rec)
+                assert np.all((seg >> np.uint64(shift)) == np.uint64(region_lo + j))
+            covered = int(run_offsets[r, -1])
+        assert covered == len(rec)
         keys = sorted(set(int(r) >> 12 for r in rec))
         row = {key: i for i, key in enumerate(keys)}
         mask = np.zeros((len(keys), n_samples_total), dtype=np.uint8)
@@ -219,7 +229,25 @@ def test_plan_owners_balances_and_is_monotone():
         loads = [counts[cuts[g]:cuts[g + 1]].sum() for g in range(world)]
         assert max(loads) - min(loads) <= 2 * counts.max()
     assert list(D.plan_owners(np.zeros(16, dtype=np.int64), 4)) == [0, 0, 0, 0, 16]
-    # the torch version (used on the device) plans identically
-    for world in (1, 2, 3, 8):
-        assert list(D.plan_owners_t(torch.from_numpy(counts.astype(np.int64)), world)) == list(D.plan_owners(counts, world))
-    assert list(D.plan_owners_t(torch.zeros(16, dtype=torch.int64), 4)) == [0, 0, 0, 0, 16]
+
+
+def test_exchange_plan_is_consistent_across_ranks():
+    """what rank g expects from rank r == what rank r sends to rank g; run offsets tile the receive buffer"""
+    import ska_rust_b200.distributed as D
+    rng = np.random.default_rng(1)
+    for world in (1, 2, 5, 8):
+        counts = rng.integers(0, 50, size=(world, 64))
+        counts[:, 40:48] = 0                              # empty regions
+        all_off = np.concatenate([np.zeros((world, 1), dtype=np.int64), np.cumsum(counts, axis=1)], axis=1)
+        plans = [D.exchange_plan(all_off, world, r) for r in range(world)]
+        for g in range(world):
+            cuts, send, recv, runs = plans[g]
+            assert np.array_equal(cuts, plans[0][0])
+            assert send.sum() == all_off[g, -1]
+            assert [int(plans[r][1][g]) for r in range(world)] == [int(x) for x in recv]
+            lo, hi = int(cuts[g]), int(cuts[g + 1])
+            assert runs.shape == (world, hi - lo + 1)
+            assert int(runs[0, 0]) == 0 and int(runs[-1, -1]) == recv.sum()
+            assert np.array_equal(np.diff(runs.astype(np.int64), axis=1), counts[:, lo:hi])
+            if world > 1:
+                assert np.array_equal(runs[1:, 0], runs[:-1, -1])

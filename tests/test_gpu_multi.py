@@ -80,3 +80,54 @@ def test_two_gpu_build_matches_single_gpu():
     assert ret["array_equal"], "concatenated slabs differ from the single-GPU array"
     assert min(ret["rows"]) > 0.3 * max(ret["rows"]), f"unbalanced slabs {ret['rows']}"
     assert ret["aln_equal"] and ret["dist_equal"]
+
+
+@pytest.mark.parametrize("world,k,prefix_bits", [(3, 31, None), (2, 15, 7), (8, 31, 12), (2, 9, 0)])
+def test_shard_path_emulated_on_one_gpu(world, k, prefix_bits):
+    """The device steps of the sharded build (first pass per 'rank', exchange plan, second pass over the received
+    runs + merge) driven sequentially on ONE GPU, with the all-to-all replaced by tensor copies: the slabs must
+    concatenate to the single-GPU array.  Covers the shard kernels where only one GPU is available."""
+    import torch
+
+    import ska_rust_b200 as S
+    import ska_rust_b200.distributed as D
+    from ska_rust_b200 import synth
+    S.set_device(0)
+    n, length = 9, 60_000
+    genomes = synth.tree_genomes(n, length, n, seed=0x5CA20011, snp_rate=0.004)
+    seqs = []
+    for i, g in enumerate(genomes):
+        g = g.copy()
+        g[500 * (i + 1):500 * (i + 1) + 20] = ord("N")
+        seqs.append([g[:length // 3].tobytes(), g[length // 3:].tobytes()])
+    names = [f"s{i}" for i in range(n)]
+    backend = D.GpuBackend()
+    per = (n + world - 1) // world
+    bounds = [(min(n, r * per), min(n, (r + 1) * per)) for r in range(world)]
+    if prefix_bits is None:
+        prefix_bits = backend.prefix_bits(sum(len(a) + len(b) for a, b in seqs), k, n)
+    recs, offs = [], []
+    for lo, hi in bounds:
+        if hi == lo:                                          # a rank without samples sends nothing
+            recs.append(torch.empty(0, dtype=torch.int64, device="cuda"))
+            offs.append(None)
+            continue
+        rec, off = backend.extract([S.Sample.from_records(seqs[i]) for i in range(lo, hi)], k, True, lo, n, prefix_bits)
+        recs.append(rec.clone())                              # the library's buffer is reused by the next extract
+        offs.append(off)
+    width = next(len(o) for o in offs if o is not None)
+    all_off = np.stack([o if o is not None else np.zeros(width, dtype=np.uint64) for o in offs]).astype(np.int64)
+    parts = []
+    for g in range(world):
+        cuts, send, recv, runs = D.exchange_plan(all_off, world, g)
+        lo_r, hi_r = int(cuts[g]), int(cuts[g + 1])
+        buf = torch.cat([recs[r][int(all_off[r, lo_r]):int(all_off[r, hi_r])] for r in range(world)])
+        assert buf.numel() == int(recv.sum())
+        slab = backend.merge(buf, runs, lo_r, hi_r, prefix_bits, n, k, True, names)
+        keys, var, cnt = slab.export()
+        parts.append((np.asarray(keys), var, cnt))
+    full = S.build_from_samples([S.Sample.from_records(s) for s in seqs], names, k, True)
+    fk, fv, fc = full.export()
+    assert np.array_equal(np.concatenate([p[0] for p in parts]), fk)
+    assert np.array_equal(np.concatenate([p[1] for p in parts]), fv)
+    assert np.array_equal(np.concatenate([p[2] for p in parts]), fc)
