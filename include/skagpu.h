@@ -131,6 +131,26 @@ int skagpu_records_info(const ska_records_t* r, uint64_t* n, const void** rec_de
 void skagpu_records_free(ska_records_t* r);
 int skagpu_merge_records_dev(void* rec_dev, int n_runs, const uint64_t* run_offsets, uint32_t region_lo, uint32_t region_hi,
                              int prefix_bits, uint64_t n_samples_total, uint32_t k, int rc, ska_array_t** out);
+/* ---- row-sharded build, second form: exchange of PARTIAL ROWS (the default of ska.rust_b200/distributed.py) ------
+ * MergeSkaDict::merge (merge_ska_dict.rs:119-151) joins two partial dictionaries over disjoint samples on the split
+ * k-mer; build_and_merge's join tree (merge_ska_dict.rs:264-326) does that between threads.  Between GPUs:
+ *   1. every rank builds the array of ITS samples with skagpu_build / skagpu_build_from_batch (all its rows, its columns);
+ *   2. skagpu_key_cumulative: cum[b] = number of this array's rows whose key is below b << (2(k-1) - region_bits),
+ *      b = 0 .. 2^region_bits (cum[2^region_bits] = n_rows).  Summed over ranks this gives balanced contiguous
+ *      key-range owners, and cum itself is where this rank's rows split between them;
+ *   3. the caller sends each owner its row range: keys (u64), variants (rows x local columns), counts (u32), read in
+ *      place through skagpu_array_dev (device pointers, valid until the array is filtered or freed);
+ *   4. skagpu_merge_partial_rows_dev joins the `n_runs` received runs (run w: run_rows[w] rows of run_cols[w] columns
+ *      that go to columns [run_col_base[w], +run_cols[w]) of the slab; the three device buffers hold the runs back to
+ *      back; each run ascending in key).  Cells of samples that do not have a k-mer stay '-' (merge_ska_array.rs:175),
+ *      variant_count adds up.  The result is this rank's slab, identical to what skagpu_merge_records_dev gives.
+ * Arrays must be in ascending key order (everything this library builds is). */
+int skagpu_array_dev(const ska_array_t* a, const void** keys_dev, const void** variants_dev, const void** counts_dev);
+int skagpu_key_cumulative(const ska_array_t* a, int region_bits, uint64_t* cum /* 2^region_bits + 1 entries */);
+int skagpu_merge_partial_rows_dev(const void* keys_dev, const void* variants_dev, const void* counts_dev, int n_runs,
+                                  const uint64_t* run_rows, const uint32_t* run_cols, const uint32_t* run_col_base,
+                                  uint64_t n_samples_total, uint32_t k, int rc, ska_array_t** out);
+
 /* Per-pair partial sums of variant_dist (merge_ska_array.rs:599-620) over this array's rows, 4 x u64 per
  * pair {mismatches, matches, dist_int, n_both}: integers, so row shards add up exactly (all-reduce);
  * distance = dist_int (filt_ambig) or n_both - dist_int/36 (allow-ambiguous), matches += constant. */

@@ -32,6 +32,7 @@ EXPORTS = [
     "skagpu_export_transposed", "skagpu_free", "skagpu_host_alloc", "skagpu_host_free", "skagpu_last_timings",
     "skagpu_launch_count", "skagpu_k1_extract", "skagpu_stream_timer", "skagpu_extract_records", "skagpu_records_info",
     "skagpu_records_free", "skagpu_merge_records_dev", "skagpu_distance_counters", "skagpu_merge_prefix_bits",
+    "skagpu_array_dev", "skagpu_key_cumulative", "skagpu_merge_partial_rows_dev",
 ]
 
 
@@ -83,6 +84,10 @@ def lib():
         L.skagpu_merge_records_dev.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_uint32, C.c_uint32, C.c_int,
                                                C.c_uint64, C.c_uint32, C.c_int, C.c_void_p]
         L.skagpu_merge_prefix_bits.argtypes = [C.c_uint64, C.c_uint32, C.c_uint64]
+        L.skagpu_array_dev.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.skagpu_key_cumulative.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+        L.skagpu_merge_partial_rows_dev.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
+                                                    C.c_void_p, C.c_uint64, C.c_uint32, C.c_int, C.c_void_p]
         L.skagpu_distance_counters.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
         L.skagpu_k1_extract.argtypes = [C.c_void_p, C.c_uint32, C.c_int, C.c_uint8, C.c_int, C.c_int, C.c_void_p,
                                         C.c_void_p, C.c_void_p]
@@ -251,6 +256,9 @@ class SeqBatch:
         if getattr(self, "_h", None):
             lib().skagpu_seqbatch_free(self._h)
             self._h = None
+
+    def n_samples(self):
+        return len(self._keep)
 
     def k1_extract(self, k, rc=True, min_qual=0, qual_filter="no-filter", iters=1, want_records=True):
         """Raw K1 output: one u64 per base position (key<<4 | one-hot middle; all-ones = no window)."""

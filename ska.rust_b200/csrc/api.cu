@@ -443,6 +443,49 @@ int skagpu_merge_records_dev(void* rec_dev, int n_runs, const uint64_t* run_offs
     API_CATCH
 }
 
+// ---- row-sharded build, partial-row exchange: local arrays | exchange of rows by key range (caller) | join on the key ----
+int skagpu_array_dev(const ska_array_t* h, const void** keys_dev, const void** variants_dev, const void** counts_dev) {
+    API_TRY
+    if (!h) throw Error("null array");
+    ctx().ensure();
+    SKA_CUDA(cudaStreamSynchronize(ctx().stream));          // the caller reads these on its own stream
+    if (keys_dev) *keys_dev = h->a.keys.p;
+    if (variants_dev) *variants_dev = h->a.variants.p;
+    if (counts_dev) *counts_dev = h->a.counts.p;
+    return 0;
+    API_CATCH
+}
+
+int skagpu_key_cumulative(const ska_array_t* h, int region_bits, uint64_t* cum) {
+    API_TRY
+    if (!h || !cum) throw Error("null argument");
+    ctx().ensure();
+    key_cumulative(h->a, region_bits, cum);
+    return 0;
+    API_CATCH
+}
+
+int skagpu_merge_partial_rows_dev(const void* keys_dev, const void* variants_dev, const void* counts_dev, int n_runs,
+                                  const uint64_t* run_rows, const uint32_t* run_cols, const uint32_t* run_col_base,
+                                  uint64_t n_samples_total, uint32_t k, int rc, ska_array_t** out) {
+    API_TRY
+    *out = nullptr;
+    ctx().ensure();
+    check_k(k);
+    if (k > 31) throw Error("k > 31 not yet supported on the device");
+    if (n_runs < 1 || !run_rows || !run_cols || !run_col_base) throw Error("row shard needs at least one run");
+    // the caller's buffers may have been filled on another stream (NCCL): order after everything
+    SKA_CUDA(cudaDeviceSynchronize());
+    arena().reset();
+    timer().clear();
+    std::unique_ptr<ska_array> h(new ska_array());
+    merge_partial_rows((const uint64_t*)keys_dev, (const uint8_t*)variants_dev, (const uint32_t*)counts_dev, n_runs, run_rows, run_cols,
+                       run_col_base, n_samples_total, k, rc != 0, h->a);
+    *out = h.release();
+    return 0;
+    API_CATCH
+}
+
 int skagpu_merge_prefix_bits(uint64_t n_records_total, uint32_t k, uint64_t n_samples_total) {
     try { return make_part_plan(k, merge_prefix_bits(n_records_total, k, n_samples_total), n_samples_total).P; }
     catch (std::exception& e) { g_err = e.what(); return -1; }

@@ -146,7 +146,7 @@ void partition_runs(const uint64_t* src, int n_runs, const uint64_t* h_run_off, 
 // K1 records (n_rec entries; sample s owns entries [sample_off[s], sample_off[s+1]); REC_SENTINEL entries are
 // skipped) -> array; sample ids are sid_base + local index.  `rec` is overwritten (partition scratch).
 void build_array_from_records(uint64_t* rec, uint64_t n_rec, const uint64_t* d_sample_off, uint32_t n_samples_local, uint32_t sid_base,
-                              uint64_t n_samples_total, uint32_t k, bool rc, Array& out);
+                              uint64_t n_samples_total, uint32_t k, bool rc, Array& out, int prefix_bits = -1 /* < 0: merge_prefix_bits */);
 // k1q_reads.cu: FASTQ samples (quality masks, ntHash, exact count-filter emulation) -> array
 void build_array_from_reads(const SeqBatch& b, uint32_t k, bool rc, uint16_t min_count, uint8_t min_qual, int qual_filter, Array& out);
 // row shard: `n_runs` received runs of first-pass records covering first-level regions [lo, hi); `prec` is overwritten
@@ -157,6 +157,10 @@ int merge_prefix_bits(uint64_t n_records_total, uint32_t k, uint64_t n_samples_t
 
 // exclusive scan of n u32 counts into n+1 u64 offsets (off[n] = total); *max_out = max count
 void launch_scan_counts(const uint32_t* cnt, uint32_t n, uint64_t* off, uint32_t* max_out);
+// rowmerge.cu: multi-GPU exchange of partial rows (every rank builds its own samples' array; owners join on the key)
+void key_cumulative(const Array& a, int region_bits, uint64_t* h_cum /* 2^region_bits + 1 */);
+void merge_partial_rows(const uint64_t* keys, const uint8_t* var, const uint32_t* cnt, int n_runs, const uint64_t* run_rows,
+                        const uint32_t* run_cols, const uint32_t* run_col_base, uint64_t n_samples, uint32_t k, bool rc, Array& out);
 // filter.cu
 int32_t filter_array(Array& a, uint64_t min_count, bool filter_ambig_as_missing, int filter_type, bool mask_ambig,
                      bool ignore_const_gaps, bool update_kmers);

@@ -25,8 +25,17 @@
 namespace ska {
 
 constexpr int MG_THREADS = 256;
-constexpr int MG_UNROLL = 4;               // records loaded per thread before any is processed
-constexpr int COUNT_CAP = 4096;             // key slots of the counting pass (32 KB)
+constexpr int MG_UNROLL = 4;               // records probed together by a thread (independent shared-memory loads overlap)
+constexpr int MG_PREFETCH = 8;             // records a thread keeps in flight from HBM while it works on the previous batch
+constexpr int COUNT_CAP = 4096;             // home slots of the counting pass
+constexpr int COUNT_LOG_CAP = 12;
+constexpr int COUNT_TAIL = 256;             // slots past the last home slot: probing never wraps, so slot order follows key order
+constexpr int COUNT_SLOTS = COUNT_CAP + COUNT_TAIL;
+constexpr int COUNT_LIST = COUNT_CAP - COUNT_CAP / 4;   // most distinct keys one item may hold, plus one (3072)
+constexpr int COUNT_GROUPS = COUNT_SLOTS / 32;
+constexpr int COUNT_GPW = COUNT_GROUPS / (MG_THREADS / 32);      // slot groups per warp in the compaction
+static_assert(COUNT_GROUPS % (MG_THREADS / 32) == 0, "slot groups must divide evenly among the warps");
+constexpr size_t COUNT_SMEM = (size_t)COUNT_SLOTS * 8 + (size_t)COUNT_LIST * 2;
 constexpr uint64_t KEY_EMPTY = ~0ULL;
 
 __device__ __forceinline__ uint32_t hash_slot(uint64_t key, int log_cap) {
@@ -51,60 +60,95 @@ __global__ void make_items_kernel(const uint64_t* __restrict__ off, uint32_t n_b
     it.beg = off[j]; it.end = off[j + 1];
     it.key_lo = b << low;
     it.key_hi = it.key_lo | ((low >= 64) ? ~0ULL : ((1ULL << low) - 1ULL));
-    if (b == (1ULL << P) - 1ULL) it.key_hi = ~0ULL >> 4;  // top bucket also holds nothing above the key space
     it.key_base = (b >> P2) << low_bits;
     it.scratch = it.beg;                                   // distinct keys <= records: the bucket's own offset is room enough
     items[j] = it;
 }
 
-// ---- pass 1: distinct keys per item
-__global__ void __launch_bounds__(MG_THREADS)
+// ---- pass 1: distinct keys per item, left SORTED in `scratch_keys` for the emit pass.
+// The table is order-preserving: a key's home slot is its offset in the item's key range scaled to
+// COUNT_CAP slots, and probing never wraps (COUNT_TAIL spare slots at the end), so reading the occupied
+// slots in slot order gives the keys in key order except inside a run of adjacent occupied slots, where
+// linear probing may have displaced them.  Every key of a run has its home inside the run and homes are
+// monotone in the key, so runs are ordered among themselves: a key's rank is its position in slot order,
+// minus the larger keys before it in its run, plus the smaller keys after it in its run.  No sort.
+// dynamic smem: tab u64[COUNT_SLOTS] (compacted in place into the key list) | lslot u16[COUNT_LIST]
+__global__ void __launch_bounds__(MG_THREADS, 4)
 bucket_count_kernel(const uint64_t* __restrict__ rec, const Item* __restrict__ items, int sb, uint32_t limit,
                     uint32_t* __restrict__ n_rows, uint32_t* __restrict__ need_split, uint64_t* __restrict__ scratch_keys) {
-    __shared__ uint64_t s_tab[COUNT_CAP];
-    __shared__ uint32_t s_n, s_over, s_u;
-    extern __shared__ uint64_t s_list[];                   // [COUNT_CAP]: the item's distinct keys, sorted
+    extern __shared__ __align__(16) uint8_t smem_c[];
+    uint64_t* s_tab = reinterpret_cast<uint64_t*>(smem_c);
+    uint64_t* s_list = s_tab;                               // the compaction moves keys down in place
+    uint16_t* s_lslot = reinterpret_cast<uint16_t*>(s_tab + COUNT_SLOTS);
+    __shared__ uint32_t s_n, s_over;
+    __shared__ uint32_t s_goff[COUNT_GROUPS + 1];
     const Item it = items[blockIdx.x];
     if (it.beg == it.end) { if (threadIdx.x == 0) n_rows[blockIdx.x] = 0; return; }
-    for (int i = threadIdx.x; i < COUNT_CAP; i += MG_THREADS) s_tab[i] = KEY_EMPTY;
+    // HBM latency is hidden by depth, not occupancy: the next MG_PREFETCH records of a thread are in flight while it
+    // probes the previous ones
+    uint64_t nx[MG_PREFETCH];
+#pragma unroll
+    for (int j = 0; j < MG_PREFETCH; j++) {
+        const uint64_t i = it.beg + (uint64_t)j * MG_THREADS + threadIdx.x;
+        nx[j] = i < it.end ? rec[i] : ~0ULL;
+    }
+    {
+        uint4* t4 = reinterpret_cast<uint4*>(s_tab);
+        const uint4 e4 = make_uint4(~0u, ~0u, ~0u, ~0u);
+        for (int i = threadIdx.x; i < COUNT_SLOTS / 2; i += MG_THREADS) t4[i] = e4;
+    }
     if (threadIdx.x == 0) { s_n = 0; s_over = 0; }
+    // keys are handled without their top P1 bits (constant over the item): kl = record >> (sb+2)
+    const uint64_t lo_l = it.key_lo - it.key_base, width = it.key_hi - it.key_lo;
+    const int range_bits = width ? 64 - __clzll((long long)width) : 0;
+    const int shift = max(0, range_bits - COUNT_LOG_CAP);
     __syncthreads();
-    for (uint64_t base = it.beg + threadIdx.x; base < it.end; base += MG_UNROLL * MG_THREADS) {
-        uint64_t rr[MG_UNROLL];
+    for (uint64_t b0 = it.beg; b0 < it.end; b0 += (uint64_t)MG_PREFETCH * MG_THREADS) {
+        uint64_t rr[MG_PREFETCH];
 #pragma unroll
-        for (int j = 0; j < MG_UNROLL; j++) {                      // all loads first: memory-level parallelism
-            uint64_t i = base + (uint64_t)j * MG_THREADS;
-            rr[j] = i < it.end ? rec[i] : 0;
-        }
-        // probe the MG_UNROLL records together: independent shared loads overlap their latency; a key
-        // already present (the common case: one record per sample per key) needs nothing else
-        uint64_t kk[MG_UNROLL], cur[MG_UNROLL]; uint32_t sl[MG_UNROLL];
+        for (int j = 0; j < MG_PREFETCH; j++) rr[j] = nx[j];
+        const uint64_t b1 = b0 + (uint64_t)MG_PREFETCH * MG_THREADS;
+        if (b1 < it.end) {
 #pragma unroll
-        for (int j = 0; j < MG_UNROLL; j++) {
-            kk[j] = it.key_base | (rr[j] >> (sb + 2));
-            sl[j] = hash_slot(kk[j], 12);
-            if (base + (uint64_t)j * MG_THREADS >= it.end || kk[j] < it.key_lo || kk[j] > it.key_hi) kk[j] = KEY_EMPTY;   // skip marker
+            for (int j = 0; j < MG_PREFETCH; j++) {
+                const uint64_t i = b1 + (uint64_t)j * MG_THREADS + threadIdx.x;
+                nx[j] = i < it.end ? rec[i] : ~0ULL;
+            }
         }
 #pragma unroll
-        for (int j = 0; j < MG_UNROLL; j++) cur[j] = *(volatile unsigned long long*)&s_tab[sl[j]];
+        for (int h = 0; h < MG_PREFETCH; h += MG_UNROLL) {
+            // probe MG_UNROLL records together: independent shared loads overlap their latency; a key
+            // already present (the common case: one record per sample per key) needs nothing else
+            uint64_t kk[MG_UNROLL], cur[MG_UNROLL]; uint32_t sl[MG_UNROLL]; bool ok[MG_UNROLL];
 #pragma unroll
-        for (int j = 0; j < MG_UNROLL; j++) {
-            const uint64_t key = kk[j];
-            if (key == KEY_EMPTY || cur[j] == key) continue;
-            if (*(volatile uint32_t*)&s_over) break;
-            uint32_t slot = sl[j];
-            int probes = 0;
-            while (true) {
-                unsigned long long old = *(volatile unsigned long long*)&s_tab[slot];
-                if (old == key) break;
-                if (old == KEY_EMPTY) old = atomicCAS((unsigned long long*)&s_tab[slot], KEY_EMPTY, key);
-                if (old == KEY_EMPTY) {
-                    if (atomicAdd(&s_n, 1u) >= COUNT_CAP - COUNT_CAP / 4) s_over = 1;   // keep the table sparse enough to probe
-                    break;
+            for (int j = 0; j < MG_UNROLL; j++) {
+                kk[j] = rr[h + j] >> (sb + 2);
+                const uint64_t d = kk[j] - lo_l;                    // one unsigned compare covers both ends of the key range
+                ok[j] = (b0 + (uint64_t)(h + j) * MG_THREADS + threadIdx.x < it.end) && d <= width;
+                sl[j] = ok[j] ? (uint32_t)(d >> shift) : 0u;
+            }
+#pragma unroll
+            for (int j = 0; j < MG_UNROLL; j++) cur[j] = *(volatile unsigned long long*)&s_tab[sl[j]];
+#pragma unroll
+            for (int j = 0; j < MG_UNROLL; j++) {
+                const uint64_t key = kk[j];
+                if (!ok[j] || cur[j] == key) continue;
+                if (*(volatile uint32_t*)&s_over) break;
+                uint32_t slot = sl[j];
+                while (true) {
+                    if (slot >= (uint32_t)COUNT_SLOTS) { s_over = 1; break; }     // ran off the tail: too dense up here, split the item
+                    unsigned long long old = *(volatile unsigned long long*)&s_tab[slot];
+                    if (old == key) break;
+                    if (old == KEY_EMPTY) {
+                        old = atomicCAS((unsigned long long*)&s_tab[slot], KEY_EMPTY, key);
+                        if (old == KEY_EMPTY) {
+                            if (atomicAdd(&s_n, 1u) >= (uint32_t)COUNT_LIST) s_over = 1;   // keep the table sparse enough to probe
+                            break;
+                        }
+                        if (old == key) break;
+                    }
+                    slot++;
                 }
-                if (old == key) break;
-                slot = (slot + 1) & (COUNT_CAP - 1);
-                if (++probes >= COUNT_CAP) { s_over = 1; break; }
             }
         }
     }
@@ -113,29 +157,51 @@ bucket_count_kernel(const uint64_t* __restrict__ rec, const Item* __restrict__ i
     if (threadIdx.x == 0) {
         n_rows[blockIdx.x] = n;
         if (n > limit) atomicExch(need_split, 1u);
-        s_u = 0;
     }
     if (n > limit || it.scratch == NO_SCRATCH || !scratch_keys) return;
-    // leave the sorted distinct keys for the emit pass: it then only inserts U keys instead of re-scanning the records
-    __syncthreads();
-    for (uint32_t i = threadIdx.x; i < COUNT_CAP; i += MG_THREADS) {
-        uint64_t key = s_tab[i];
-        if (key != KEY_EMPTY) s_list[atomicAdd(&s_u, 1u)] = key;
+    // occupied slots in slot order -> list (order-preserving compaction: ballot per 32 slots, scan of the group counts)
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    constexpr int NW = MG_THREADS / 32;
+    uint64_t keep[COUNT_GPW];                                // every slot is read before any list entry is written (same memory)
+#pragma unroll
+    for (int q = 0; q < COUNT_GPW; q++) {
+        const int g = warp + q * NW;
+        keep[q] = s_tab[g * 32 + lane];
+        const uint32_t m = __ballot_sync(0xFFFFFFFFu, keep[q] != KEY_EMPTY);
+        if (lane == 0) s_goff[g] = __popc(m);
     }
     __syncthreads();
-    uint32_t np2 = 1; while (np2 < n) np2 <<= 1;
-    for (uint32_t i = n + threadIdx.x; i < np2; i += MG_THREADS) s_list[i] = KEY_EMPTY;
+    if (warp == 0) {
+        constexpr int PER = (COUNT_GROUPS + 31) / 32;
+        uint32_t v[PER], sum = 0;
+#pragma unroll
+        for (int j = 0; j < PER; j++) { int g = lane * PER + j; v[j] = g < COUNT_GROUPS ? s_goff[g] : 0u; sum += v[j]; }
+        uint32_t inc = sum;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { uint32_t t = __shfl_up_sync(0xFFFFFFFFu, inc, o); if (lane >= o) inc += t; }
+        uint32_t run = inc - sum;
+#pragma unroll
+        for (int j = 0; j < PER; j++) { int g = lane * PER + j; if (g < COUNT_GROUPS) s_goff[g] = run; run += v[j]; }
+    }
     __syncthreads();
-    for (uint32_t size = 2; size <= np2; size <<= 1)
-        for (uint32_t stride = size >> 1; stride > 0; stride >>= 1) {
-            for (uint32_t t = threadIdx.x; t < np2 / 2; t += MG_THREADS) {
-                uint32_t lo = 2 * t - (t & (stride - 1)), hi = lo + stride;
-                uint64_t a = s_list[lo], b2 = s_list[hi];
-                if ((a > b2) == ((lo & size) == 0)) { s_list[lo] = b2; s_list[hi] = a; }
-            }
-            __syncthreads();
+#pragma unroll
+    for (int q = 0; q < COUNT_GPW; q++) {
+        const int g = warp + q * NW;
+        const uint32_t m = __ballot_sync(0xFFFFFFFFu, keep[q] != KEY_EMPTY);
+        if (keep[q] != KEY_EMPTY) {
+            const uint32_t pos = s_goff[g] + __popc(m & ((1u << lane) - 1u));
+            s_list[pos] = keep[q];
+            s_lslot[pos] = (uint16_t)(g * 32 + lane);
         }
-    for (uint32_t i = threadIdx.x; i < n; i += MG_THREADS) scratch_keys[it.scratch + i] = s_list[i];
+    }
+    __syncthreads();
+    for (uint32_t i = threadIdx.x; i < n; i += MG_THREADS) {
+        const uint64_t key = s_list[i];
+        uint32_t rank = i;
+        for (uint32_t j = i; j > 0 && (uint32_t)s_lslot[j - 1] + 1u == (uint32_t)s_lslot[j]; j--) rank -= (s_list[j - 1] > key);
+        for (uint32_t j = i; j + 1 < n && (uint32_t)s_lslot[j + 1] == (uint32_t)s_lslot[j] + 1u; j++) rank += (s_list[j + 1] < key);
+        scratch_keys[it.scratch + rank] = it.key_base | key;
+    }
 }
 
 // exclusive scan of n u32 counts into u64 offsets (single CTA; n is at most a few million).  Coalesced:
@@ -448,6 +514,154 @@ bucket_emit_kernel(const uint64_t* __restrict__ rec, const Item* __restrict__ it
     for (uint32_t i = threadIdx.x; i < u; i += MG_THREADS) out_cnt[row_base + i] = s_cnt[i];
 }
 
+// ---- pass 2, shared-memory form (the default): the item's base sets are accumulated in SHARED memory, one 4-bit set
+// per (row, sample), and every row leaves the CTA exactly once as finished IUPAC letters in coalesced 8-byte stores.
+// Needs the sorted keys of the count pass (rank of a key = its index there) and  u * N/2  bytes of shared memory
+// for the item's u rows; merge_items falls back to bucket_emit_kernel when that does not fit.
+//   1. load the u sorted keys: write them out, insert each into the open-addressing table with its rank
+//   2. stream the records once: probe (read-only), atomicOr the record's base into nibble (rank, sample)
+//   3. rows out: 8 nibbles -> 8 letters ('-' for empty; W/S/N for palindromic keys, ska_dict.rs:85-113), non-missing counts
+// dynamic smem: tab u64[cap] | sets u32[max_u * stride_w] | cnt u32[max_u] | rank u16[cap] | pal u8[max_u]
+__device__ __forceinline__ uint32_t spread_nibbles4(uint32_t b16) {          // 4 nibbles -> 4 bytes
+    uint32_t v = (b16 | (b16 << 8)) & 0x00FF00FFu;
+    return (v | (v << 4)) & 0x0F0F0F0Fu;
+}
+__device__ __forceinline__ uint32_t letters4(uint32_t v, bool pal) {
+    if (!pal) return iupac_letters4(v);
+    uint32_t word = 0;
+#pragma unroll
+    for (int q = 0; q < 4; q++) word |= pal_letter((v >> (8 * q)) & 0xFu) << (8 * q);
+    return word;
+}
+
+__global__ void __launch_bounds__(MG_THREADS, 4)
+bucket_emit_smem_kernel(const uint64_t* __restrict__ rec, const Item* __restrict__ items, int sb,
+                        const uint64_t* __restrict__ row_off, int log_cap, uint32_t max_u, uint32_t n_samples, uint32_t stride_w,
+                        int k, int rc, uint64_t* __restrict__ out_keys, uint8_t* __restrict__ out_var, uint32_t* __restrict__ out_cnt,
+                        const uint64_t* __restrict__ scratch_keys) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    const uint32_t cap = 1u << log_cap;
+    uint64_t* s_tab = reinterpret_cast<uint64_t*>(smem);
+    uint32_t* s_sets = reinterpret_cast<uint32_t*>(s_tab + cap);
+    uint32_t* s_cnt = s_sets + (size_t)max_u * stride_w;
+    uint16_t* s_rank = reinterpret_cast<uint16_t*>(s_cnt + max_u);
+    uint8_t* s_pal = reinterpret_cast<uint8_t*>(s_rank + cap);
+
+    const uint32_t b = blockIdx.x;
+    const Item it = items[b];
+    const uint64_t beg = it.beg, end = it.end;
+    const uint64_t row_base = row_off[b];
+    const uint32_t u = (uint32_t)(row_off[b + 1] - row_base);     // distinct keys, from the count pass
+    if (u == 0) return;
+
+    uint64_t nx[MG_PREFETCH];                                     // first records: in flight while the table is set up
+#pragma unroll
+    for (int j = 0; j < MG_PREFETCH; j++) {
+        const uint64_t i = beg + (uint64_t)j * MG_THREADS + threadIdx.x;
+        nx[j] = i < end ? rec[i] : ~0ULL;
+    }
+    {
+        uint4* t4 = reinterpret_cast<uint4*>(s_tab);
+        const uint4 e4 = make_uint4(~0u, ~0u, ~0u, ~0u);
+        for (uint32_t i = threadIdx.x; i < cap / 2; i += MG_THREADS) t4[i] = e4;
+    }
+    for (uint32_t i = threadIdx.x; i < u * stride_w; i += MG_THREADS) s_sets[i] = 0u;
+    __syncthreads();
+    // 1. keys (sorted by the count pass); the table holds them without the item's constant top bits
+    for (uint32_t i = threadIdx.x; i < u; i += MG_THREADS) {
+        const uint64_t key = scratch_keys[it.scratch + i];
+        out_keys[row_base + i] = key;
+        s_pal[i] = (uint8_t)((rc && revcomp_key(key, k - 1) == key) ? 1 : 0);
+        s_cnt[i] = 0;
+        const uint64_t kl = key ^ it.key_base;
+        uint32_t slot = hash_slot(kl, log_cap);
+        while (atomicCAS((unsigned long long*)&s_tab[slot], KEY_EMPTY, kl) != KEY_EMPTY) slot = (slot + 1) & (cap - 1);
+        s_rank[slot] = (uint16_t)i;
+    }
+    __syncthreads();
+
+    // 2. records -> base sets
+    const uint32_t sid_mask = (1u << sb) - 1u;
+    for (uint64_t b0 = beg; b0 < end; b0 += (uint64_t)MG_PREFETCH * MG_THREADS) {
+        uint64_t rr[MG_PREFETCH];
+#pragma unroll
+        for (int j = 0; j < MG_PREFETCH; j++) rr[j] = nx[j];
+        const uint64_t b1 = b0 + (uint64_t)MG_PREFETCH * MG_THREADS;
+        if (b1 < end) {
+#pragma unroll
+            for (int j = 0; j < MG_PREFETCH; j++) {
+                const uint64_t i = b1 + (uint64_t)j * MG_THREADS + threadIdx.x;
+                nx[j] = i < end ? rec[i] : ~0ULL;
+            }
+        }
+#pragma unroll
+        for (int h = 0; h < MG_PREFETCH; h += MG_UNROLL) {
+            uint64_t kk[MG_UNROLL], cur[MG_UNROLL]; uint32_t sl[MG_UNROLL], rk[MG_UNROLL];
+#pragma unroll
+            for (int j = 0; j < MG_UNROLL; j++) {
+                kk[j] = rr[h + j] >> (sb + 2);
+                sl[j] = hash_slot(kk[j], log_cap);
+            }
+#pragma unroll
+            for (int j = 0; j < MG_UNROLL; j++) cur[j] = s_tab[sl[j]];
+#pragma unroll
+            for (int j = 0; j < MG_UNROLL; j++) {                  // collisions: walk on (rare); bounded so that a foreign key cannot hang the CTA
+                const bool live = b0 + (uint64_t)(h + j) * MG_THREADS + threadIdx.x < end;
+                uint32_t probes = 0;
+                while (live && cur[j] != kk[j] && probes < cap) { sl[j] = (sl[j] + 1) & (cap - 1); cur[j] = s_tab[sl[j]]; probes++; }
+                if (!live || cur[j] != kk[j]) kk[j] = KEY_EMPTY;
+            }
+#pragma unroll
+            for (int j = 0; j < MG_UNROLL; j++) rk[j] = s_rank[sl[j]];
+#pragma unroll
+            for (int j = 0; j < MG_UNROLL; j++) {
+                if (kk[j] == KEY_EMPTY) continue;
+                const uint32_t smp = (uint32_t)(rr[h + j] >> 2) & sid_mask;
+                atomicOr(&s_sets[rk[j] * stride_w + (smp >> 3)], (1u << (uint32_t)(rr[h + j] & 3)) << (4 * (smp & 7)));
+            }
+        }
+    }
+    __syncthreads();
+
+    // 3. rows out
+    if ((n_samples & 7u) == 0) {
+        const uint32_t wpr = n_samples >> 3;                       // set words (8 samples each) per row
+        const int lg = (wpr & (wpr - 1)) == 0 ? 31 - __clz(wpr) : -1;
+        uint2* out8 = reinterpret_cast<uint2*>(out_var + row_base * n_samples);
+        const uint32_t total = u * wpr;
+        for (uint32_t idx = threadIdx.x; idx < total; idx += MG_THREADS) {
+            const uint32_t row = lg >= 0 ? idx >> lg : idx / wpr;
+            const uint32_t w = idx - row * wpr;
+            const uint32_t x = s_sets[row * stride_w + w];
+            uint2 o = make_uint2(0x2D2D2D2Du, 0x2D2D2D2Du);        // "--------"
+            if (x) {
+                const bool pal = s_pal[row];
+                o.x = letters4(spread_nibbles4(x & 0xFFFFu), pal);
+                o.y = letters4(spread_nibbles4(x >> 16), pal);
+                const uint32_t m = (x | (x >> 1) | (x >> 2) | (x >> 3)) & 0x11111111u;
+                atomicAdd(&s_cnt[row], (uint32_t)__popc(m));
+            }
+            out8[idx] = o;
+        }
+    } else {
+        uint8_t* outb = out_var + row_base * n_samples;
+        const uint32_t total = u * n_samples;
+        for (uint32_t o = threadIdx.x; o < total; o += MG_THREADS) {
+            const uint32_t row = o / n_samples, col = o - row * n_samples;
+            const uint32_t m = (s_sets[row * stride_w + (col >> 3)] >> (4 * (col & 7))) & 0xFu;
+            if (m) atomicAdd(&s_cnt[row], 1u);
+            outb[o] = (uint8_t)(s_pal[row] ? pal_letter(m) : iupac_letter(m));
+        }
+    }
+    __syncthreads();
+    for (uint32_t i = threadIdx.x; i < u; i += MG_THREADS) out_cnt[row_base + i] = s_cnt[i];
+}
+
+static size_t emit_smem_bytes(int log_cap, uint32_t max_u, uint32_t stride_w) {
+    const size_t cap = (size_t)1 << log_cap;
+    return cap * 8 + (size_t)max_u * stride_w * 4 + (size_t)max_u * 4 + cap * 2 + max_u + 16;
+}
+
 static int choose_prefix_bits(uint64_t n_pos, int key_bits, uint64_t target) {
     int p = 0;
     while ((n_pos >> p) > target && p < key_bits && p < 24) p++;
@@ -461,16 +675,17 @@ static void merge_items(const uint64_t* rec, Item* items, uint32_t n_items, int 
     // bytes of shared memory per table slot in the emit kernel: tab 8 + rank 2 + (lkey 8 + lslot 2 + cnt 4)/2
     const size_t slot_bytes = 17;
     const int max_log_cap = 13;                                   // 8192 slots = 136 KB
-    const uint32_t limit = COUNT_CAP - COUNT_CAP / 4 - 1;         // most distinct keys one item may hold (3071)
+    const uint32_t limit = COUNT_LIST - 1;                        // most distinct keys one item may hold (3071)
+    bool all_scratch = scratch_keys != nullptr;                   // every item left its sorted keys for the emit pass
 
     timer().begin("count");
-    SKA_CUDA(cudaFuncSetAttribute(bucket_count_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, COUNT_CAP * 8));
+    SKA_CUDA(cudaFuncSetAttribute(bucket_count_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)COUNT_SMEM));
     uint32_t* n_rows = arena().take_n<uint32_t>(std::max<uint32_t>(n_items, 1));
     uint32_t* flags = arena().take_n<uint32_t>(2);
     uint32_t h_flags[2] = {0, 0};
     for (int round = 0; n_items > 0; round++) {
         SKA_CUDA(cudaMemsetAsync(flags, 0, 8, c.stream));
-        SKA_LAUNCH(bucket_count_kernel, n_items, MG_THREADS, COUNT_CAP * 8, rec, items, sb, limit, n_rows, flags, scratch_keys);
+        SKA_LAUNCH(bucket_count_kernel, n_items, MG_THREADS, COUNT_SMEM, rec, items, sb, limit, n_rows, flags, scratch_keys);
         SKA_CUDA(cudaMemcpyAsync(h_flags, flags, 8, cudaMemcpyDeviceToHost, c.stream));
         SKA_CUDA(cudaStreamSynchronize(c.stream));
         if (!h_flags[0]) break;
@@ -498,6 +713,7 @@ static void merge_items(const uint64_t* rec, Item* items, uint32_t n_items, int 
             }
         }
         n_items = (uint32_t)next.size();
+        all_scratch = false;
         items = arena().take_n<Item>(n_items); n_rows = arena().take_n<uint32_t>(n_items);
         SKA_CUDA(cudaMemcpyAsync(items, next.data(), n_items * sizeof(Item), cudaMemcpyHostToDevice, c.stream));
         SKA_CUDA(cudaStreamSynchronize(c.stream));
@@ -520,11 +736,21 @@ static void merge_items(const uint64_t* rec, Item* items, uint32_t n_items, int 
     if (total_rows) {
         int log_cap = 6;
         while ((1u << log_cap) < 2 * max_u) log_cap++;
-        size_t smem = ((size_t)1 << log_cap) * slot_bytes;
         if (log_cap > max_log_cap) throw Error("internal: item larger than the shared-memory table");
-        SKA_CUDA(cudaFuncSetAttribute(bucket_emit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        SKA_LAUNCH(bucket_emit_kernel, n_items, MG_THREADS, smem, rec, items, sb, row_off, log_cap,
-                   (uint32_t)n_samples, (int)k, rc ? 1 : 0, out.keys.p, out.variants.p, out.counts.p, (const uint64_t*)scratch_keys);
+        const uint32_t stride_w = (uint32_t)((n_samples + 7) / 8) | 1u;    // odd: rows fall on different banks
+        const size_t smem_sets = emit_smem_bytes(log_cap, max_u, stride_w);
+        const char* force_red = getenv("SKA_EMIT_GLOBAL");                  // tests: force the wide-row path
+        if (all_scratch && smem_sets <= (size_t)160 * 1024 && smem_sets + 1024 <= c.smem_optin && !(force_red && atoi(force_red))) {
+            SKA_CUDA(cudaFuncSetAttribute(bucket_emit_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_sets));
+            SKA_LAUNCH(bucket_emit_smem_kernel, n_items, MG_THREADS, smem_sets, rec, items, sb, row_off, log_cap, max_u,
+                       (uint32_t)n_samples, stride_w, (int)k, rc ? 1 : 0, out.keys.p, out.variants.p, out.counts.p,
+                       (const uint64_t*)scratch_keys);
+        } else {
+            size_t smem = ((size_t)1 << log_cap) * slot_bytes;
+            SKA_CUDA(cudaFuncSetAttribute(bucket_emit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            SKA_LAUNCH(bucket_emit_kernel, n_items, MG_THREADS, smem, rec, items, sb, row_off, log_cap,
+                       (uint32_t)n_samples, (int)k, rc ? 1 : 0, out.keys.p, out.variants.p, out.counts.p, (const uint64_t*)scratch_keys);
+        }
     }
     timer().end();
 }
@@ -543,8 +769,8 @@ int merge_prefix_bits(uint64_t n_records_total, uint32_t k, uint64_t n_samples_t
 }
 
 void build_array_from_records(uint64_t* rec, uint64_t n_rec, const uint64_t* d_sample_off, uint32_t n_samples_local, uint32_t sid_base,
-                              uint64_t n_samples_total, uint32_t k, bool rc, Array& out) {
-    const PartPlan pl = make_part_plan(k, merge_prefix_bits(n_rec, k, n_samples_total), n_samples_total);
+                              uint64_t n_samples_total, uint32_t k, bool rc, Array& out, int prefix_bits) {
+    const PartPlan pl = make_part_plan(k, prefix_bits >= 0 ? prefix_bits : merge_prefix_bits(n_rec, k, n_samples_total), n_samples_total);
     const uint32_t n_buckets = 1u << pl.P;
 
     // (1) partition by key prefix

@@ -5,6 +5,17 @@ The reference is single-node shared memory (README.md:124); its build_and_merge
 (src/merge_ska_dict.rs:354-417) has exactly one point where data from different samples must meet --
 rows of the merged dictionary are keyed by split k-mer.  Here:
 
+Two exchange strategies give the same slabs (tests compare both with the single-GPU array):
+
+"rows" (default; SURVEY 8e "local pre-merge"): every rank builds the array of ITS samples (all its rows, its own
+columns) exactly as a single GPU would; the ranks' cumulative key histograms (2^16 key ranges) are all-gathered and
+cut into `world` contiguous owner ranges of equal row count; ONE exchange (three all-to-alls: keys, variant rows,
+counts) moves every partial row to its owner; the owner joins the runs on the key (csrc/rowmerge.cu), cells of
+samples without the k-mer stay '-'.  Related genomes share most split k-mers, so a rank ships one (8 + columns + 4)-byte
+row per DISTINCT key instead of one 8-byte record per sample and key: 3-10x fewer bytes, and the merge of wide rows
+never happens on records.
+
+"records": the exchange sits between the two partition passes of one big merge:
   1. every rank extracts the records of ITS samples (K1) and runs the FIRST of the two partition passes:
      records grouped by the top `region_bits` bits of the key ("regions").  The ranks' region offsets are
      all-gathered (a few KB); summed they are cut into `world` contiguous key ranges of equal record count
@@ -67,6 +78,42 @@ class GpuBackend:
                                                       prefix_bits, n_samples_total, k, int(rc), C.byref(h)))
         return api.MergeSkaArray(h, names)
 
+    # ---- "rows" strategy
+    region_bits_max = 16
+
+    def build_local(self, samples, names_local, k, rc):
+        batch = samples if isinstance(samples, api.SeqBatch) else api.SeqBatch(samples)
+        return api.build_from_batch(batch, names_local, k, rc)
+
+    def key_cumulative(self, arr, region_bits):
+        cum = np.zeros((1 << region_bits) + 1, dtype=np.uint64)
+        api._check(api.lib().skagpu_key_cumulative(arr._h, region_bits, cum.ctypes.data))
+        return cum.astype(np.int64)
+
+    def array_tensors(self, arr):
+        """zero-copy device views (keys int64[R], variants uint8[R * cols], counts int32[R]) of a local array"""
+        import ctypes as C
+        kp, vp, cp = C.c_void_p(), C.c_void_p(), C.c_void_p()
+        api._check(api.lib().skagpu_array_dev(arr._h, C.byref(kp), C.byref(vp), C.byref(cp)))
+        d = arr.dims()
+        r, n = d["n_rows"], d["n_samples"]
+        if r == 0:
+            return (torch.empty(0, dtype=torch.int64, device="cuda"), torch.empty(0, dtype=torch.uint8, device="cuda"),
+                    torch.empty(0, dtype=torch.int32, device="cuda"))
+        return (torch.as_tensor(_CudaView(kp.value, r, "<i8"), device="cuda"),
+                torch.as_tensor(_CudaView(vp.value, r * n, "|u1"), device="cuda"),
+                torch.as_tensor(_CudaView(cp.value, r, "<i4"), device="cuda"))
+
+    def merge_partial(self, keys, var, cnt, run_rows, run_cols, run_col_base, n_samples_total, k, rc, names):
+        import ctypes as C
+        h = C.c_void_p()
+        rr = np.ascontiguousarray(run_rows, dtype=np.uint64)
+        rc_ = np.ascontiguousarray(run_cols, dtype=np.uint32)
+        rb = np.ascontiguousarray(run_col_base, dtype=np.uint32)
+        api._check(api.lib().skagpu_merge_partial_rows_dev(keys.data_ptr(), var.data_ptr(), cnt.data_ptr(), len(rr), rr.ctypes.data,
+                                                           rc_.ctypes.data, rb.ctypes.data, n_samples_total, k, int(rc), C.byref(h)))
+        return api.MergeSkaArray(h, names)
+
     def n_positions(self, samples):
         if isinstance(samples, api.SeqBatch):
             samples = samples._keep
@@ -109,9 +156,78 @@ def exchange_plan(all_off, world, rank):
     return cuts, send_counts, recv_counts, run_offsets.astype(np.uint64)
 
 
+def rows_exchange_plan(all_cum, world, rank):
+    """all_cum: (world, n_regions + 1) cumulative row counts of every rank's local array over the key regions.
+    -> (cuts, send_rows, recv_rows): region index where each owner starts, rows this rank sends to every owner,
+    rows it receives from every source.  Identical arithmetic on every rank."""
+    all_cum = np.asarray(all_cum, dtype=np.int64)
+    cuts = plan_owners(np.diff(all_cum, axis=1).sum(axis=0), world)
+    bounds = all_cum[:, cuts]                              # (world, world + 1): row index per source rank
+    send_rows = np.diff(bounds[rank])
+    recv_rows = bounds[:, rank + 1] - bounds[:, rank]
+    return cuts, send_rows, recv_rows
+
+
+def build_and_merge_sharded_rows(backend, samples_local, names_all, sample_base, k, rc, group=None, timings=None):
+    """"rows" strategy (module docstring).  -> this rank's slab.  Collective over `group`."""
+    import time
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    dev = backend.device
+    t_last = [time.perf_counter()]
+
+    def lap(name):
+        if timings is not None:
+            if dev == "cuda":
+                torch.cuda.synchronize()
+            now = time.perf_counter()
+            timings[name] = (now - t_last[0]) * 1e3
+            t_last[0] = now
+
+    n_local = samples_local.n_samples() if hasattr(samples_local, "n_samples") else len(samples_local)
+    local = backend.build_local(samples_local, names_all[sample_base:sample_base + n_local], k, rc)
+    lap("local_build_ms")
+    region_bits = min(backend.region_bits_max, 2 * (k - 1))
+    cum = backend.key_cumulative(local, region_bits)
+    mine = torch.from_numpy(np.concatenate([cum, np.array([sample_base, n_local], dtype=np.int64)])).to(dev)
+    gathered = torch.empty(world * mine.numel(), dtype=torch.int64, device=dev)
+    dist.all_gather_into_tensor(gathered, mine, group=group)
+    table = gathered.cpu().numpy().reshape(world, -1)
+    all_cum, col_base, cols = table[:, :-2], table[:, -2], table[:, -1]
+    cuts, send_rows, recv_rows = rows_exchange_plan(all_cum, world, rank)
+    lap("owners_ms")
+    keys, var, cnt = backend.array_tensors(local)
+    first = int(all_cum[rank, cuts[0]])                   # 0: the owners tile the whole key space
+    n_send = int(send_rows.sum())
+    n_recv = int(recv_rows.sum())
+    recv_keys = torch.empty(n_recv, dtype=torch.int64, device=dev)
+    recv_cnt = torch.empty(n_recv, dtype=torch.int32, device=dev)
+    recv_var = torch.empty(int((recv_rows * cols).sum()), dtype=torch.uint8, device=dev)
+    rl, sl = list(map(int, recv_rows)), list(map(int, send_rows))
+    dist.all_to_all_single(recv_keys, keys[first:first + n_send], rl, sl, group=group)
+    dist.all_to_all_single(recv_cnt, cnt[first:first + n_send], rl, sl, group=group)
+    dist.all_to_all_single(recv_var, var[first * n_local:(first + n_send) * n_local], [int(r * c) for r, c in zip(recv_rows, cols)],
+                           [int(r) * n_local for r in send_rows], group=group)
+    lap("all_to_all_ms")
+    arr = backend.merge_partial(recv_keys, recv_var, recv_cnt, recv_rows, cols, col_base, len(names_all), k, rc, names_all)
+    del local, keys, var, cnt                              # after the merge: it orders itself behind the transport
+    lap("merge_ms")
+    if timings is not None:
+        timings["sent_rows"] = int(n_send - send_rows[rank])
+        timings["recv_rows"] = n_recv
+        timings["sent_bytes"] = int((n_send - send_rows[rank]) * (12 + n_local))
+    return arr
+
+
 def build_and_merge_sharded(backend, samples_local, names_all, sample_base, k, rc, prefix_bits=None, group=None,
-                            timings=None):
-    """-> this rank's slab (a MergeSkaArray with len(names_all) columns).  Collective over `group`."""
+                            timings=None, strategy="rows"):
+    """-> this rank's slab (a MergeSkaArray with len(names_all) columns).  Collective over `group`.
+    strategy "rows" (default) exchanges partial rows after a local build, "records" exchanges records between the
+    two partition passes (module docstring); `prefix_bits` only concerns "records"."""
+    if strategy == "rows":
+        return build_and_merge_sharded_rows(backend, samples_local, names_all, sample_base, k, rc, group=group, timings=timings)
+    if strategy != "records":
+        raise ValueError(f"unknown strategy {strategy!r}")
     import time
     world = dist.get_world_size(group)
     rank = dist.get_rank(group)

@@ -106,6 +106,48 @@ class OracleBackend:
     def prefix_bits(self, n_records_total, k, n_samples_total):
         return min(6, 2 * (k - 1))
 
+    # ---- "rows" strategy stand-ins
+    region_bits_max = 5
+
+    def build_local(self, samples, names_local, k, rc):
+        arr = O.OracleArray.build([O.SampleData([(r, None) for r in recs]) for recs in samples], names_local, k=k, rc=rc)
+        keys, var, cnt = arr.export()
+        assert list(keys) == sorted(keys)
+        return OracleSlab(arr)
+
+    def key_cumulative(self, slab, region_bits):
+        keys = np.array(slab.export()[0], dtype=np.uint64)
+        k = slab.arr.dims()["k"]
+        cuts = np.arange((1 << region_bits) + 1, dtype=np.uint64) << np.uint64(2 * (k - 1) - region_bits)
+        cum = np.searchsorted(keys, cuts, side="left").astype(np.int64)
+        cum[-1] = len(keys)
+        return cum
+
+    def array_tensors(self, slab):
+        keys, var, cnt = slab.export()
+        return (torch.from_numpy(np.array(keys, dtype=np.uint64).view(np.int64)), torch.from_numpy(np.ascontiguousarray(var).reshape(-1)),
+                torch.from_numpy(np.asarray(cnt).astype(np.int32)))
+
+    def merge_partial(self, keys, var, cnt, run_rows, run_cols, run_col_base, n_samples_total, k, rc, names):
+        keys = keys.numpy().view(np.uint64)
+        var, cnt = var.numpy(), cnt.numpy()
+        assert len(keys) == int(np.sum(run_rows)) == len(cnt) and len(var) == int(np.sum(run_rows * run_cols))
+        uni = sorted(set(int(x) for x in keys))
+        row = {key: i for i, key in enumerate(uni)}
+        out = np.full((len(uni), n_samples_total), ord("-"), dtype=np.uint8)
+        oc = np.zeros(len(uni), dtype=np.uint64)
+        r0 = b0 = 0
+        for rows, cols, base in zip(map(int, run_rows), map(int, run_cols), map(int, run_col_base)):
+            rk = keys[r0:r0 + rows]
+            assert np.all(rk[1:] > rk[:-1]), "every run must be ascending in key"
+            block = var[b0:b0 + rows * cols].reshape(rows, cols)
+            for i in range(rows):
+                out[row[int(rk[i])], base:base + cols] = block[i]
+                oc[row[int(rk[i])]] += int(cnt[r0 + i])
+            r0 += rows
+            b0 += rows * cols
+        return OracleSlab(O.OracleArray.from_arrays(k, rc, 64, uni, out, oc, names))
+
     def merge(self, rec, run_offsets, region_lo, region_hi, prefix_bits, n_samples_total, k, rc, names):
         rec = rec.numpy().view(np.uint64)
         # the exchange plan must describe the receive buffer exactly: every run grouped by region, regions in range
@@ -159,7 +201,7 @@ def make_population(n, seed):
     return pops
 
 
-def worker(rank, world, port, k, rc, ret):
+def worker(rank, world, port, k, rc, strategy, ret):
     import ska_rust_b200.distributed as D
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
@@ -171,14 +213,14 @@ def worker(rank, world, port, k, rc, ret):
         per = (n + world - 1) // world
         lo, hi = rank * per, min(n, (rank + 1) * per)
         backend = OracleBackend()
-        slab = D.build_and_merge_sharded(backend, pops[lo:hi], names, lo, k, rc)
+        slab = D.build_and_merge_sharded(backend, pops[lo:hi], names, lo, k, rc, strategy=strategy)
         keys, var, cnt = slab.export()
         parts = [None] * world if rank == 0 else None
         dist.gather_object((keys, var, cnt), parts, dst=0)
         # distance on a second identical build (filters mutate the slab)
-        slab_d = D.build_and_merge_sharded(backend, pops[lo:hi], names, lo, k, rc, prefix_bits=6)
+        slab_d = D.build_and_merge_sharded(backend, pops[lo:hi], names, lo, k, rc, prefix_bits=6, strategy=strategy)
         dists = D.distance_sharded(slab_d, filt_ambig=True)
-        slab_a = D.build_and_merge_sharded(backend, pops[lo:hi], names, lo, k, rc, prefix_bits=6)
+        slab_a = D.build_and_merge_sharded(backend, pops[lo:hi], names, lo, k, rc, prefix_bits=6, strategy=strategy)
         dists_amb = D.distance_sharded(slab_a, filt_ambig=False)
         aln = D.gather_alignment(D.align_sharded(slab, min_freq=0.5), names)
         if rank == 0:
@@ -190,11 +232,12 @@ def worker(rank, world, port, k, rc, ret):
         dist.destroy_process_group()
 
 
+@pytest.mark.parametrize("strategy", ["rows", "records"])
 @pytest.mark.parametrize("world,k,rc", [(2, 9, True), (3, 15, True), (2, 11, False)])
-def test_sharded_matches_single_process(world, k, rc):
+def test_sharded_matches_single_process(world, k, rc, strategy):
     mgr = mp.Manager()
     ret = mgr.dict()
-    mp.spawn(worker, args=(world, free_port(), k, rc, ret), nprocs=world, join=True)
+    mp.spawn(worker, args=(world, free_port(), k, rc, strategy, ret), nprocs=world, join=True)
     n = 7
     pops = make_population(n, 123)
     names = [f"s{i}" for i in range(n)]
@@ -216,6 +259,23 @@ def test_sharded_matches_single_process(world, k, rc):
     for a, b in zip(ret["dists_amb"], want2.distance_raw(float(constant), False)):
         assert abs(a[0] - b[0]) < 1e-9 and a[1:] == b[1:]
     assert ret["aln"] == O.OracleArray.build(samples, names, k=k, rc=rc).align(min_freq=0.5)
+
+
+def test_rows_exchange_plan_is_consistent_across_ranks():
+    """rows strategy: what rank g expects from rank r == what rank r sends to rank g; all rows are sent exactly once"""
+    import ska_rust_b200.distributed as D
+    rng = np.random.default_rng(2)
+    for world in (1, 2, 5, 8):
+        counts = rng.integers(0, 50, size=(world, 64))
+        counts[:, 10:20] = 0
+        all_cum = np.concatenate([np.zeros((world, 1), dtype=np.int64), np.cumsum(counts, axis=1)], axis=1)
+        plans = [D.rows_exchange_plan(all_cum, world, r) for r in range(world)]
+        for g in range(world):
+            cuts, send, recv = plans[g]
+            assert np.array_equal(cuts, plans[0][0]) and cuts[0] == 0 and cuts[-1] == 64
+            assert send.sum() == all_cum[g, -1] and np.all(send >= 0)
+            assert [int(plans[r][1][g]) for r in range(world)] == [int(x) for x in recv]
+            assert recv.sum() == counts[:, cuts[g]:cuts[g + 1]].sum()
 
 
 def test_plan_owners_balances_and_is_monotone():

@@ -231,6 +231,48 @@ def test_build_synthetic_matches_oracle(n, length, k, rc):
     assert_same_array(g, o)
 
 
+@pytest.mark.parametrize("n,k,rc", [(8, 31, True), (24, 15, True), (16, 9, True), (40, 11, False), (128, 21, True)])
+@pytest.mark.parametrize("emit_global", [0, 1])
+def test_build_emit_paths(n, k, rc, emit_global, monkeypatch):
+    """sample counts that are multiples of 8 take the 8-byte row stores of bucket_emit_smem_kernel (set words per row a
+    power of two or not); SKA_EMIT_GLOBAL=1 forces the wide-row kernel (base sets OR-ed into the output in global memory)"""
+    from ska_rust_b200 import synth
+    monkeypatch.setenv("SKA_EMIT_GLOBAL", str(emit_global))
+    genomes = synth.star_genomes(n, 6_000, seed=0x5CA20100 + n, snp_rate=0.01)
+    samples = []
+    for i, g in enumerate(genomes):
+        recs = [g.tobytes(), b"ACGT" * 20, b"AATT" * 10 + b"GGCC" * 10]       # palindromic keys and IUPAC merges in every sample
+        if i % 3 == 0:
+            recs.append(g[100:400].tobytes())                                  # repeats inside a sample
+        samples.append(S.Sample.from_records(recs))
+    names = [f"s{i}" for i in range(n)]
+    g = S.build_from_samples(samples, names, k, rc)
+    assert_same_array(g, ora_from_gpu_samples(samples, names, k, rc))
+
+
+@pytest.mark.parametrize("prefix_bits", [None, 0, 6])
+def test_build_skewed_keys_long_probe_runs(prefix_bits, monkeypatch):
+    """low-complexity sequence: many distinct keys share long prefixes, so the order-preserving table of the count pass
+    has long runs of occupied slots (and, with few prefix bits, items that overflow and are split); order must survive"""
+    if prefix_bits is not None:
+        monkeypatch.setenv("SKA_PREFIX_BITS", str(prefix_bits))
+    rng = np.random.default_rng(77)
+    samples_records = []
+    for s in range(5):
+        recs = []
+        for _ in range(40):
+            head = b"A" * int(rng.integers(12, 20))                            # keys starting AAAA...: one corner of the key space
+            tail = rng.choice(np.frombuffer(b"ACGT", dtype=np.uint8), size=600).tobytes()
+            recs.append(head + tail + b"T" * 25 + tail[:50])
+        recs.append(rng.choice(np.frombuffer(b"AC", dtype=np.uint8), size=20_000).tobytes())   # two-letter alphabet
+        samples_records.append(recs)
+    samples = [S.Sample.from_records(r) for r in samples_records]
+    names = [f"s{i}" for i in range(len(samples))]
+    for k, rc in ((31, True), (15, False), (9, True)):
+        g = S.build_from_samples(samples, names, k, rc)
+        assert_same_array(g, ora_from_gpu_samples(samples, names, k, rc))
+
+
 def test_build_unrelated_samples_forces_bucket_splitting():
     """samples that share nothing: every record is a distinct row, so buckets exceed the shared-memory table and are
     split by further key bits (merge.cu, rare path)"""
