@@ -195,11 +195,12 @@ def run_ours(args, rank, world, local_rank):
         threshold = int(np.ceil(G * world * 0.9))
 
     shard_t = {}
+    strategy = os.environ.get("BENCH_STRATEGY", "rows")       # distributed.py: "rows" (default) or "records"
 
     def build_device(batch):
         if world == 1:
             return S.api.build_from_batch(batch, names, k, True)
-        return D.build_and_merge_sharded(backend, batch, names, rank * G, k, True,
+        return D.build_and_merge_sharded(backend, batch, names, rank * G, k, True, strategy=strategy,
                                          timings=shard_t if os.environ.get("BENCH_SHARD_TIMINGS") else None)
 
     # ---------------- device-resident arm
@@ -288,7 +289,7 @@ def run_ours(args, rank, world, local_rank):
         # algorithmic bytes: 9 B per record read + (8 + N + 8) B per row written
         n_cols = G * world
         emit_bytes = 9.0 * n_bases + rows_built * (16.0 + n_cols)
-        emit_ms = st.get("emit", float("nan"))
+        emit_ms = st.get("emit", 0.0) or 1e-9
         emit_achieved = emit_bytes / (emit_ms * 1e-3) / 1e9
         full_size = (G == 128 and L == 5_000_000 and world == 1 and population == "star")   # what profiles/ was captured on
         line = {
@@ -302,8 +303,10 @@ def run_ours(args, rank, world, local_rank):
                        "align": "min_freq 0.9, filter no-const",
                        "l2": "inputs (640 MB/128 genomes) larger than L2; no flush",
                        "parallelism": "1 GPU" if world == 1 else
-                       f"{world} ranks: samples sharded for extraction, one NCCL all-to-all of records by key range, "
-                       f"rows sharded for merge/filter ({G * world} columns per slab)",
+                       (f"{world} ranks: every rank builds its {G} samples, one NCCL exchange of partial rows by key range, "
+                        f"owners join on the key; rows sharded for filter/align ({G * world} columns per slab)" if strategy == "rows" else
+                        f"{world} ranks: samples sharded for extraction, one NCCL all-to-all of records by key range, "
+                        f"rows sharded for merge/filter ({G * world} columns per slab)"),
                        "rows_built": rows_built, "rows_aligned": rows_aligned},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": ms_e2e / args.steps},

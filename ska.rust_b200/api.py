@@ -19,7 +19,8 @@ import re
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libskagpu.so")
+# SKAGPU_LIB: another build of the same library (kernel tuning experiments, profiles/); never a different implementation
+LIB_PATH = os.environ.get("SKAGPU_LIB") or os.path.join(_HERE, "libskagpu.so")
 _lib = None
 
 FILTER_TYPES = {"no-filter": 0, "no-const": 1, "no-ambig": 2, "no-ambig-or-const": 3}   # cli.rs:129-138

@@ -69,6 +69,7 @@ void StageTimer::clear() {
     stages.clear();
 }
 void StageTimer::begin(const char* name) {
+    if (muted) return;
     Stage s; s.name = name; s.launches = 0;
     SKA_CUDA(cudaEventCreate(&s.beg)); SKA_CUDA(cudaEventCreate(&s.end));
     SKA_CUDA(cudaEventRecord(s.beg, ctx().stream));
@@ -76,6 +77,7 @@ void StageTimer::begin(const char* name) {
     stages.push_back(s);
 }
 void StageTimer::end() {
+    if (muted || stages.empty()) return;
     Stage& s = stages.back();
     SKA_CUDA(cudaEventRecord(s.end, ctx().stream));
     s.launches = ctx().launches - launch_mark;
@@ -476,8 +478,7 @@ int skagpu_merge_partial_rows_dev(const void* keys_dev, const void* variants_dev
     if (n_runs < 1 || !run_rows || !run_cols || !run_col_base) throw Error("row shard needs at least one run");
     // the caller's buffers may have been filled on another stream (NCCL): order after everything
     SKA_CUDA(cudaDeviceSynchronize());
-    arena().reset();
-    timer().clear();
+    arena().reset();                                        // the stage timer keeps the stages of the local build before it
     std::unique_ptr<ska_array> h(new ska_array());
     merge_partial_rows((const uint64_t*)keys_dev, (const uint8_t*)variants_dev, (const uint32_t*)counts_dev, n_runs, run_rows, run_cols,
                        run_col_base, n_samples_total, k, rc != 0, h->a);

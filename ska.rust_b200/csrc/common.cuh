@@ -93,6 +93,7 @@ struct StageTimer {
     struct Stage { const char* name; cudaEvent_t beg, end; uint64_t launches; };
     std::vector<Stage> stages;
     uint64_t launch_mark = 0;
+    bool muted = false;                 // inner builds (rowmerge.cu's key union) run under the caller's stage
     void clear();
     void begin(const char* name);
     void end();
@@ -152,6 +153,9 @@ void build_array_from_reads(const SeqBatch& b, uint32_t k, bool rc, uint16_t min
 // row shard: `n_runs` received runs of first-pass records covering first-level regions [lo, hi); `prec` is overwritten
 void build_array_from_runs(uint64_t* prec, uint64_t n_rec, int n_runs, const uint64_t* run_off, uint32_t region_lo, uint32_t region_hi,
                            const PartPlan& pl, uint64_t n_samples, uint32_t k, bool rc, Array& out);
+// sorted distinct keys of `n_runs` ascending key runs lying back to back in `keys` (h_run_off: n_runs + 1 offsets);
+// false if a key range is too crowded for the bucket tables (the caller then takes the general merge)
+bool union_sorted_runs(const uint64_t* keys, int n_runs, const uint64_t* h_run_off, uint32_t k, DevBuf<uint64_t>& out_keys, uint64_t& n_out);
 // prefix bits the merge wants for `n_records_total` records in the whole key space
 int merge_prefix_bits(uint64_t n_records_total, uint32_t k, uint64_t n_samples_total);
 

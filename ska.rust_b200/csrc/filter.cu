@@ -51,6 +51,16 @@ filter_flags_kernel(const uint8_t* __restrict__ var, const uint32_t* __restrict_
     for (int rr = warp; rr < FL_ROWS; rr += FL_THREADS / 32) {
         const uint64_t r = r0 + rr;
         if (r >= n_rows) break;
+        if (!ambig_missing) {       // the stored count decides: rows below the threshold (or NoFilter) are never read
+            const uint32_t c0 = cnt[r];
+            if ((uint64_t)c0 < min_count || ftype == 0) {
+                if (lane == 0) {
+                    const bool kp = (uint64_t)c0 >= min_count;
+                    flags[r] = (uint8_t)(1 | (kp ? 2 : 0)); new_cnt[r] = c0; k1 += 1; k2 += kp;
+                }
+                continue;
+            }
+        }
         const uint8_t* row = var + r * n_samples;
         uint32_t good = 0;          // not '-' and not ambiguous
         uint32_t any_ambig = 0;
@@ -165,7 +175,34 @@ filter_flags_rows_kernel(const uint8_t* __restrict__ var, const uint32_t* __rest
     __syncthreads();
     const uint64_t r = (uint64_t)blockIdx.x * FL_ROWS + threadIdx.x;
     bool keep1 = false, keep2 = false;
-    if (r < n_rows) {
+    const uint32_t c_stored = r < n_rows ? cnt[r] : 0u;
+    // the stored count decides rows below the threshold (and NoFilter): they are never read
+    const bool by_count = !ambig_missing && ((uint64_t)c_stored < min_count || ftype == 0);
+    if (r < n_rows && by_count) {
+        keep1 = true; keep2 = (uint64_t)c_stored >= min_count;
+        flags[r] = (uint8_t)(1 | (keep2 ? 2 : 0));
+        new_cnt[r] = c_stored;
+    } else if (r < n_rows && !ambig_missing && ftype == 1 && !ignore_gaps) {
+        // NoConst where '-' counts as a value: "more than one distinct byte" == "some byte differs from the first"
+        const uint4* row = reinterpret_cast<const uint4*>(var + r * n_samples);
+        const uint32_t n16 = n_samples >> 4;
+        uint32_t diff = 0, pat = 0;
+        for (uint32_t c0 = 0; c0 < n16; c0 += 8) {
+            uint4 v[8];
+#pragma unroll
+            for (int j = 0; j < 8; j++) if (c0 + j < n16) v[j] = __ldg(&row[c0 + j]);
+            if (c0 == 0) pat = (v[0].x & 0xFFu) * 0x01010101u;
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                if (c0 + j >= n16) break;
+                diff |= (v[j].x ^ pat) | (v[j].y ^ pat) | (v[j].z ^ pat) | (v[j].w ^ pat);
+            }
+            if (diff) break;
+        }
+        keep1 = true; keep2 = diff != 0;
+        flags[r] = (uint8_t)(1 | (keep2 ? 2 : 0));
+        new_cnt[r] = c_stored;
+    } else if (r < n_rows) {
         const uint4* row = reinterpret_cast<const uint4*>(var + r * n_samples);
         RowState st = {0, 0, 0, 0xFFFFFFFFu, 0, s_lut};
         const uint32_t n16 = n_samples >> 4;
@@ -179,7 +216,7 @@ filter_flags_rows_kernel(const uint8_t* __restrict__ var, const uint32_t* __rest
                 st.word(v[j].x); st.word(v[j].y); st.word(v[j].z); st.word(v[j].w);
             }
         }
-        uint32_t count = ambig_missing ? st.good : cnt[r];
+        uint32_t count = ambig_missing ? st.good : c_stored;
         keep1 = !ambig_missing || st.good > 0;
         if (keep1 && (uint64_t)count >= min_count) {
             switch (ftype) {
@@ -216,6 +253,16 @@ filter_flags_wide_kernel(const uint8_t* __restrict__ var, const uint32_t* __rest
     for (int rr = warp; rr < FL_ROWS; rr += FL_THREADS / 32) {
         const uint64_t r = r0 + rr;
         if (r >= n_rows) break;
+        if (!ambig_missing) {       // the stored count decides: rows below the threshold (or NoFilter) are never read
+            const uint32_t c0 = cnt[r];
+            if ((uint64_t)c0 < min_count || ftype == 0) {
+                if (lane == 0) {
+                    const bool kp = (uint64_t)c0 >= min_count;
+                    flags[r] = (uint8_t)(1 | (kp ? 2 : 0)); new_cnt[r] = c0; k1 += 1; k2 += kp;
+                }
+                continue;
+            }
+        }
         const uint4* row = reinterpret_cast<const uint4*>(var + r * n_samples);
         RowState st = {0, 0, 0, 0xFFFFFFFFu, 0, s_lut};
         for (uint32_t c0 = lane; c0 < n16; c0 += 128) {               // 4 loads in flight per lane
@@ -298,24 +345,32 @@ filter_scatter_kernel(const uint8_t* __restrict__ var, const uint32_t* __restric
             }
         }
     }
-    // rows: one warp per row
-    for (int rr = warp; rr < FL_ROWS; rr += FL_THREADS / 32) {
-        uint64_t r = r0 + rr;
-        if (r >= n_rows) break;
-        if (!(flags[r] & 2)) continue;
-        const uint8_t* src = var + r * n_samples;
-        uint8_t* dst = out_var + (base2 + s_pos2[rr]) * n_samples;
-        if (!mask_ambig && (n_samples & 15u) == 0) {              // plain row move: 16 bytes per lane
-            const uint4* s4 = reinterpret_cast<const uint4*>(src);
-            uint4* d4 = reinterpret_cast<uint4*>(dst);
-            for (uint32_t c = lane; c < (n_samples >> 4); c += 32) d4[c] = __ldg(&s4[c]);
-            continue;
+    // rows: the CTA's surviving rows are listed in shared memory and moved as one dense stream of 16-byte pieces
+    // (a surviving row's destination follows the previous one's, so the stores are contiguous)
+    __shared__ uint16_t s_keep[FL_ROWS];
+    __shared__ uint32_t s_nk;
+    if (threadIdx.x < FL_ROWS && (f & 2)) s_keep[s_pos2[threadIdx.x]] = (uint16_t)threadIdx.x;
+    if (threadIdx.x == FL_ROWS - 1) s_nk = s_pos2[FL_ROWS - 1] + ((f & 2) ? 1u : 0u);
+    __syncthreads();
+    const uint32_t nk = s_nk;
+    if (!mask_ambig && (n_samples & 15u) == 0) {
+        const uint32_t n16 = n_samples >> 4, total = nk * n16;
+        const uint4* s4 = reinterpret_cast<const uint4*>(var + r0 * n_samples);
+        uint4* d4 = reinterpret_cast<uint4*>(out_var + base2 * n_samples);
+        for (uint32_t idx = threadIdx.x; idx < total; idx += FL_THREADS) {
+            const uint32_t j = idx / n16, cidx = idx - j * n16;
+            d4[idx] = __ldg(&s4[(uint32_t)s_keep[j] * n16 + cidx]);
         }
-        for (uint32_t s = lane; s < n_samples; s += 32) {
-            uint32_t b = src[s];
-            if (mask_ambig && is_ambig_dev(b)) b = 'N';          // merge_ska_array.rs:388-399
-            dst[s] = (uint8_t)b;
-        }
+        return;
+    }
+    const uint32_t total = nk * n_samples;
+    const uint8_t* src0 = var + r0 * n_samples;
+    uint8_t* dst0 = out_var + base2 * n_samples;
+    for (uint32_t idx = threadIdx.x; idx < total; idx += FL_THREADS) {
+        const uint32_t j = idx / n_samples, cidx = idx - j * n_samples;
+        uint32_t bb = src0[(uint32_t)s_keep[j] * n_samples + cidx];
+        if (mask_ambig && is_ambig_dev(bb)) bb = 'N';            // merge_ska_array.rs:388-399
+        dst0[idx] = (uint8_t)bb;
     }
 }
 
@@ -386,8 +441,67 @@ transpose_kernel(const uint8_t* __restrict__ in, uint64_t n_rows, uint32_t n_sam
     }
 }
 
+// Word form for n_samples % 4 == 0: 128 rows x 64 samples per CTA.  Loads are 4-byte words along a row (a warp
+// reads two 64-byte row pieces), 4 x 4 byte blocks are transposed in registers with byte permutes, and every
+// sample's 128 output bytes leave as aligned 4-byte words (the first and last word of a run byte by byte, because
+// sample s starts at byte s * n_rows of the output, which is aligned only by chance).
+constexpr int TR_ROWS = 128, TR_COLS = 64;
+__global__ void __launch_bounds__(256)
+transpose_words_kernel(const uint8_t* __restrict__ in, uint64_t n_rows, uint32_t n_samples, uint8_t* __restrict__ out) {
+    __shared__ uint32_t s_in[TR_ROWS][TR_COLS / 4 + 1];
+    __shared__ uint32_t s_t[TR_COLS][TR_ROWS / 4 + 1];             // s_t[s][q] = rows 4q..4q+3 of sample s
+    const uint64_t r0 = (uint64_t)blockIdx.x * TR_ROWS;
+    const uint32_t s0 = blockIdx.y * TR_COLS;
+    const uint32_t nr = (uint32_t)min((uint64_t)TR_ROWS, n_rows - r0), ns = min((uint32_t)TR_COLS, n_samples - s0);
+    const uint32_t nw = ns >> 2;
+    const uint32_t* in32 = reinterpret_cast<const uint32_t*>(in);
+    for (uint32_t idx = threadIdx.x; idx < TR_ROWS * (TR_COLS / 4); idx += 256) {
+        const uint32_t r = idx / (TR_COLS / 4), cw = idx % (TR_COLS / 4);
+        uint32_t v = 0;
+        if (r < nr && cw < nw) v = __ldg(&in32[(((r0 + r) * n_samples + s0) >> 2) + cw]);
+        s_in[r][cw] = v;
+    }
+    __syncthreads();
+    for (uint32_t blk = threadIdx.x; blk < (TR_ROWS / 4) * (TR_COLS / 4); blk += 256) {
+        const uint32_t r4 = blk % (TR_ROWS / 4), s4 = blk / (TR_ROWS / 4);
+        const uint32_t a0 = s_in[4 * r4][s4], a1 = s_in[4 * r4 + 1][s4], a2 = s_in[4 * r4 + 2][s4], a3 = s_in[4 * r4 + 3][s4];
+        const uint32_t t0 = __byte_perm(a0, a1, 0x5140), t1 = __byte_perm(a2, a3, 0x5140);    // (x.0 y.0 x.1 y.1)
+        const uint32_t t2 = __byte_perm(a0, a1, 0x7362), t3 = __byte_perm(a2, a3, 0x7362);    // (x.2 y.2 x.3 y.3)
+        s_t[4 * s4][r4] = __byte_perm(t0, t1, 0x5410);
+        s_t[4 * s4 + 1][r4] = __byte_perm(t0, t1, 0x7632);
+        s_t[4 * s4 + 2][r4] = __byte_perm(t2, t3, 0x5410);
+        s_t[4 * s4 + 3][r4] = __byte_perm(t2, t3, 0x7632);
+    }
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (uint32_t sidx = warp; sidx < ns; sidx += 8) {
+        const uint8_t* trow = reinterpret_cast<const uint8_t*>(s_t[sidx]);
+        const uint64_t d0 = (uint64_t)(s0 + sidx) * n_rows + r0;   // byte offset of this run in the output
+        const uint32_t m = (uint32_t)(d0 & 3u);
+        uint8_t* a_out = out + (d0 - m);                          // 4-byte aligned
+        for (uint32_t wi = lane; 4 * wi < m + nr; wi += 32) {
+            const int p0 = (int)(4 * wi) - (int)m;                // tile row of the word's first byte
+            if (p0 >= 0 && p0 + 4 <= (int)nr) {
+                const uint32_t word = (uint32_t)trow[p0] | ((uint32_t)trow[p0 + 1] << 8) | ((uint32_t)trow[p0 + 2] << 16) |
+                                      ((uint32_t)trow[p0 + 3] << 24);
+                *reinterpret_cast<uint32_t*>(a_out + 4 * wi) = word;
+            } else {
+#pragma unroll
+                for (int j = 0; j < 4; j++) { const int pp = p0 + j; if (pp >= 0 && pp < (int)nr) a_out[4 * wi + j] = trow[pp]; }
+            }
+        }
+    }
+}
+
 void transpose_array(const Array& a, uint8_t* d_out) {
     if (a.n_rows == 0 || a.n_samples == 0) return;
+    if ((a.n_samples & 3u) == 0 && (reinterpret_cast<uintptr_t>(d_out) & 3u) == 0) {
+        dim3 grid((unsigned)((a.n_rows + TR_ROWS - 1) / TR_ROWS), (unsigned)((a.n_samples + TR_COLS - 1) / TR_COLS));
+        timer().begin("transpose");
+        SKA_LAUNCH(transpose_words_kernel, grid, 256, 0, a.variants.p, a.n_rows, (uint32_t)a.n_samples, d_out);
+        timer().end();
+        return;
+    }
     dim3 grid((unsigned)((a.n_rows + TP_TILE - 1) / TP_TILE), (unsigned)((a.n_samples + TP_TILE - 1) / TP_TILE));
     timer().begin("transpose");
     SKA_LAUNCH(transpose_kernel, grid, 256, 0, a.variants.p, a.n_rows, (uint32_t)a.n_samples, d_out);

@@ -755,6 +755,109 @@ static void merge_items(const uint64_t* rec, Item* items, uint32_t n_items, int 
     timer().end();
 }
 
+// ---- union of sorted key runs (the owner side of the partial-row exchange, rowmerge.cu) ---------------------------
+// Every run is ascending, so a key-range bucket is one contiguous piece of every run: its ends are found by binary
+// search (no partition pass), the pieces are copied next to each other as packed records and the count pass above
+// leaves every bucket's distinct keys sorted; a last copy closes the gaps.  Buckets are cut so that none holds more
+// records than the count table can take, hence no splitting.
+__global__ void run_cumulative_kernel(const uint64_t* __restrict__ keys, const uint64_t* __restrict__ run_off, int n_runs, int shift,
+                                      uint32_t n_cuts, uint64_t* __restrict__ cum /* [n_runs][n_cuts] */) {
+    const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+    const int w = blockIdx.y;
+    if (b >= n_cuts || w >= n_runs) return;
+    const uint64_t* a = keys + run_off[w];
+    const uint64_t n = run_off[w + 1] - run_off[w];
+    uint64_t lo = 0, hi = n;
+    if (b + 1 == n_cuts) lo = n;
+    else {
+        const uint64_t cut = (uint64_t)b << shift;
+        while (lo < hi) { uint64_t m = (lo + hi) >> 1; if (a[m] < cut) lo = m + 1; else hi = m; }
+    }
+    cum[(size_t)w * n_cuts + b] = lo;
+}
+__global__ void bucket_sizes_kernel(const uint64_t* __restrict__ cum, int n_runs, uint32_t n_buckets, uint32_t* __restrict__ sizes) {
+    const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= n_buckets) return;
+    uint64_t t = 0;
+    for (int w = 0; w < n_runs; w++) t += cum[(size_t)w * (n_buckets + 1) + b + 1] - cum[(size_t)w * (n_buckets + 1) + b];
+    sizes[b] = (uint32_t)min(t, (uint64_t)0xFFFFFFFFu);
+}
+// one warp per bucket: the runs' pieces -> packed records (key << 3: one sample, sb = 1, no middle base)
+__global__ void __launch_bounds__(256)
+gather_buckets_kernel(const uint64_t* __restrict__ keys, const uint64_t* __restrict__ run_off, const uint64_t* __restrict__ cum, int n_runs,
+                      uint32_t n_buckets, const uint64_t* __restrict__ off, uint64_t* __restrict__ prec) {
+    const uint32_t b = blockIdx.x * 8 + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (b >= n_buckets) return;
+    uint64_t dst = off[b];
+    for (int w = 0; w < n_runs; w++) {
+        const uint64_t beg = cum[(size_t)w * (n_buckets + 1) + b], end = cum[(size_t)w * (n_buckets + 1) + b + 1];
+        const uint64_t* src = keys + run_off[w];
+        for (uint64_t i = beg + lane; i < end; i += 32) prec[dst + (i - beg)] = src[i] << 3;
+        dst += end - beg;
+    }
+}
+__global__ void __launch_bounds__(128)
+compact_keys_kernel(const uint64_t* __restrict__ scratch_keys, const Item* __restrict__ items, const uint64_t* __restrict__ row_off,
+                    uint64_t* __restrict__ out_keys) {
+    const Item it = items[blockIdx.x];
+    const uint64_t r0 = row_off[blockIdx.x];
+    const uint32_t u = (uint32_t)(row_off[blockIdx.x + 1] - r0);
+    for (uint32_t i = threadIdx.x; i < u; i += 128) out_keys[r0 + i] = scratch_keys[it.scratch + i];
+}
+
+bool union_sorted_runs(const uint64_t* keys, int n_runs, const uint64_t* h_run_off, uint32_t k, DevBuf<uint64_t>& out_keys, uint64_t& n_out) {
+    Context& c = ctx();
+    const int key_bits = 2 * ((int)k - 1);
+    const uint64_t n_in = h_run_off[n_runs];
+    n_out = 0;
+    if (n_in == 0) return true;
+    const int max_bits = std::min(key_bits, 24);
+    int pbits = 0;
+    while ((n_in >> pbits) > 1024 && pbits < max_bits) pbits++;           // ~1 K records per bucket: room for a 3x crowded key range
+    uint64_t* d_run_off = arena().take_n<uint64_t>(n_runs + 1);
+    SKA_CUDA(cudaMemcpyAsync(d_run_off, h_run_off, (size_t)(n_runs + 1) * 8, cudaMemcpyHostToDevice, c.stream));
+    uint32_t* flags = arena().take_n<uint32_t>(2);
+    uint32_t h_flags[2] = {0, 0};
+    uint64_t *cum = nullptr, *off = nullptr;
+    uint32_t NB = 0;
+    while (true) {
+        NB = 1u << pbits;
+        cum = arena().take_n<uint64_t>((size_t)n_runs * (NB + 1));
+        uint32_t* sizes = arena().take_n<uint32_t>(NB);
+        off = arena().take_n<uint64_t>(NB + 1);
+        dim3 grid((NB + 1 + 255) / 256, n_runs);
+        SKA_LAUNCH(run_cumulative_kernel, grid, 256, 0, keys, d_run_off, n_runs, key_bits - pbits, NB + 1, cum);
+        SKA_LAUNCH(bucket_sizes_kernel, (NB + 255) / 256, 256, 0, cum, n_runs, NB, sizes);
+        launch_scan_counts(sizes, NB, off, flags + 1);
+        SKA_CUDA(cudaMemcpyAsync(h_flags, flags, 8, cudaMemcpyDeviceToHost, c.stream));
+        SKA_CUDA(cudaStreamSynchronize(c.stream));
+        if (h_flags[1] <= (uint32_t)COUNT_LIST - 1) break;               // every bucket fits the count table
+        if (pbits >= max_bits) return false;                               // a key range this crowded: let the general merge split it
+        pbits = std::min(max_bits, pbits + 2);
+    }
+    uint64_t* prec = arena().take_n<uint64_t>(n_in);
+    uint64_t* scratch = arena().take_n<uint64_t>(n_in);
+    SKA_LAUNCH(gather_buckets_kernel, (NB + 7) / 8, 256, 0, keys, d_run_off, cum, n_runs, NB, off, prec);
+    Item* items = arena().take_n<Item>(NB);
+    SKA_LAUNCH(make_items_kernel, (NB + 255) / 256, 256, 0, off, NB, (uint64_t)0, key_bits, pbits, pbits, key_bits, items);
+    uint32_t* n_rows = arena().take_n<uint32_t>(NB);
+    SKA_CUDA(cudaFuncSetAttribute(bucket_count_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)COUNT_SMEM));
+    SKA_CUDA(cudaMemsetAsync(flags, 0, 8, c.stream));
+    SKA_LAUNCH(bucket_count_kernel, NB, MG_THREADS, COUNT_SMEM, prec, items, 1, (uint32_t)COUNT_LIST - 1, n_rows, flags, scratch);
+    uint64_t* row_off = arena().take_n<uint64_t>(NB + 1);
+    launch_scan_counts(n_rows, NB, row_off, flags + 1);
+    uint64_t total = 0;
+    SKA_CUDA(cudaMemcpyAsync(h_flags, flags, 8, cudaMemcpyDeviceToHost, c.stream));
+    SKA_CUDA(cudaMemcpyAsync(&total, row_off + NB, 8, cudaMemcpyDeviceToHost, c.stream));
+    SKA_CUDA(cudaStreamSynchronize(c.stream));
+    if (h_flags[0]) return false;                                          // probing ran off a table's tail (very crowded corner)
+    out_keys.alloc(total);
+    if (total) SKA_LAUNCH(compact_keys_kernel, NB, 128, 0, (const uint64_t*)scratch, items, row_off, out_keys.p);
+    n_out = total;
+    return true;
+}
+
 int merge_prefix_bits(uint64_t n_records_total, uint32_t k, uint64_t n_samples_total) {
     const int key_bits = 2 * ((int)k - 1);
     (void)n_samples_total;

@@ -21,7 +21,10 @@
 
 namespace ska {
 
-constexpr int PT_THREADS = 512;
+#ifndef SKA_PT_THREADS
+#define SKA_PT_THREADS 512
+#endif
+constexpr int PT_THREADS = SKA_PT_THREADS;
 #ifndef SKA_PT_ITEMS
 #define SKA_PT_ITEMS 8
 #endif

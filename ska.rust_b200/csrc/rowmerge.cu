@@ -122,24 +122,35 @@ void merge_partial_rows(const uint64_t* keys, const uint8_t* var, const uint32_t
     if (n_in == 0) return;
     if (!keys || !var || !cnt) throw Error("null run buffers");
 
-    // 1. union of the keys: one-column records through the partition + count pass; ~2 K records per bucket because
-    //    every record may be a distinct key here (at most n_runs records share one)
+    // 1. union of the keys.  The runs are sorted, so key-range buckets are cut out of them by binary search
+    //    (union_sorted_runs, merge.cu); the general partition + merge of one-column records is only the fallback
+    //    for key ranges too crowded for the bucket tables.
     timer().begin("union_keys");
-    uint64_t* rec = arena().take_n<uint64_t>(n_in);
-    SKA_LAUNCH(keys_to_records_kernel, (unsigned)((n_in + 255) / 256), 256, 0, keys, n_in, rec);
-    uint64_t* d_off = arena().take_n<uint64_t>(2);
-    const uint64_t h_off[2] = {0, n_in};
-    SKA_CUDA(cudaMemcpyAsync(d_off, h_off, 16, cudaMemcpyHostToDevice, c.stream));
-    SKA_CUDA(cudaStreamSynchronize(c.stream));                       // h_off is a stack array
-    int pbits = 0;
-    while ((n_in >> pbits) > 2048 && pbits < 22) pbits++;
+    std::vector<uint64_t> h_run_off(n_runs + 1, 0);
+    for (int w = 0; w < n_runs; w++) h_run_off[w + 1] = h_run_off[w] + run_rows[w];
     Array uni;
-    build_array_from_records(rec, n_in, d_off, 1, 0, 1, k, rc, uni, pbits);
+    uint64_t n_uni = 0;
+    const char* force_general = getenv("SKA_UNION_GENERAL");        // tests: force the fallback
+    if ((force_general && atoi(force_general)) || !union_sorted_runs(keys, n_runs, h_run_off.data(), k, uni.keys, n_uni)) {
+        uint64_t* rec = arena().take_n<uint64_t>(n_in);
+        SKA_LAUNCH(keys_to_records_kernel, (unsigned)((n_in + 255) / 256), 256, 0, keys, n_in, rec);
+        uint64_t* d_off = arena().take_n<uint64_t>(2);
+        const uint64_t h_off[2] = {0, n_in};
+        SKA_CUDA(cudaMemcpyAsync(d_off, h_off, 16, cudaMemcpyHostToDevice, c.stream));
+        SKA_CUDA(cudaStreamSynchronize(c.stream));                   // h_off is a stack array
+        int pbits = 0;
+        while ((n_in >> pbits) > 1024 && pbits < 22) pbits++;
+        timer().muted = true;
+        try { build_array_from_records(rec, n_in, d_off, 1, 0, 1, k, rc, uni, pbits); }
+        catch (...) { timer().muted = false; throw; }
+        timer().muted = false;
+        n_uni = uni.n_rows;
+    }
     timer().end();
 
     // 2. + 3.
     timer().begin("gather_rows");
-    const uint64_t R = uni.n_rows;
+    const uint64_t R = n_uni;
     out.n_rows = out.n_keys = R;
     out.keys = std::move(uni.keys);
     out.variants.alloc(R * n_samples);

@@ -8,7 +8,7 @@ rows of the merged dictionary are keyed by split k-mer.  Here (SURVEY.md section
 Two exchange strategies give the same slabs (tests compare both with the single-GPU array):
 
 "rows" (default; SURVEY 8e "local pre-merge"): every rank builds the array of ITS samples (all its rows, its own
-columns) exactly as a single GPU would; the ranks' cumulative key histograms (2^16 key ranges) are all-gathered and
+columns) exactly as a single GPU would; the ranks' cumulative key histograms (2^12 key ranges) are all-gathered and
 cut into `world` contiguous owner ranges of equal row count; ONE exchange (three all-to-alls: keys, variant rows,
 counts) moves every partial row to its owner; the owner joins the runs on the key (csrc/rowmerge.cu), cells of
 samples without the k-mer stay '-'.  Related genomes share most split k-mers, so a rank ships one (8 + columns + 4)-byte
@@ -79,7 +79,7 @@ class GpuBackend:
         return api.MergeSkaArray(h, names)
 
     # ---- "rows" strategy
-    region_bits_max = 16
+    region_bits_max = 12          # 4096 key ranges to cut owners from: fine enough to balance 8-16 ranks, small enough to plan in microseconds
 
     def build_local(self, samples, names_local, k, rc):
         batch = samples if isinstance(samples, api.SeqBatch) else api.SeqBatch(samples)

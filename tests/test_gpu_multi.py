@@ -134,12 +134,15 @@ def test_shard_path_emulated_on_one_gpu(world, k, prefix_bits):
     assert np.array_equal(np.concatenate([p[2] for p in parts]), fc)
 
 
+@pytest.mark.parametrize("general_union", [0, 1])
 @pytest.mark.parametrize("world,k,n,rc", [(3, 31, 9, True), (2, 15, 8, False), (8, 31, 17, True), (2, 9, 5, True), (4, 21, 16, True)])
-def test_rows_path_emulated_on_one_gpu(world, k, n, rc):
+def test_rows_path_emulated_on_one_gpu(world, k, n, rc, general_union, monkeypatch):
     """"rows" strategy on ONE GPU: a local array per 'rank', the exchange plan, the all-to-all replaced by tensor
     copies, the owners' join on the key (rowmerge.cu).  Uneven column blocks (n % world != 0), word-aligned and
-    unaligned column counts, and k = 9 where every rank holds almost every key."""
+    unaligned column counts, and k = 9 where every rank holds almost every key.  SKA_UNION_GENERAL=1 forces the
+    fallback of the key union (general partition + merge instead of cutting the sorted runs)."""
     import torch
+    monkeypatch.setenv("SKA_UNION_GENERAL", str(general_union))
 
     import ska_rust_b200 as S
     import ska_rust_b200.distributed as D

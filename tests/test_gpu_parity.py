@@ -399,7 +399,8 @@ def test_filter_random_arrays_match_oracle(n_rows, n_samples):
 
 def test_transpose_matches_write_fasta():
     rng = np.random.default_rng(3)
-    for n_rows, n_samples in ((1, 1), (63, 5), (64, 64), (1000, 129), (4097, 128)):
+    for n_rows, n_samples in ((1, 1), (63, 5), (64, 64), (1000, 129), (4097, 128), (1, 4), (3, 8), (130, 68), (1027, 200),
+                              (12_345, 128), (517, 256), (2, 1024)):
         keys, var, cnt = random_array(rng, n_rows, n_samples)
         g = S.MergeSkaArray.from_arrays(31, True, 64, keys, var, cnt, [f"s{i}" for i in range(n_samples)])
         assert np.array_equal(g.transposed(), var.T)
