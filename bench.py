@@ -195,6 +195,7 @@ def run_ours(args, rank, world, local_rank):
         threshold = int(np.ceil(G * world * 0.9))
 
     shard_t = {}
+    local_rows = [None]                                       # rows strategy: rows of this rank's local build
     strategy = os.environ.get("BENCH_STRATEGY", "rows")       # distributed.py: "rows" (default) or "records"
 
     def build_device(batch):
@@ -218,6 +219,7 @@ def run_ours(args, rank, world, local_rank):
         for _ in range(args.steps):
             arr = build_device(batch)
             rows_built = arr.dims()["n_rows"]
+            local_rows[0] = getattr(arr, "local_rows", None)
             align_device(arr)
             stages = S.api.last_timings()
             rows_aligned = arr.dims()["n_rows"]
@@ -285,11 +287,15 @@ def run_ours(args, rank, world, local_rank):
         achieved = K1_ALGO_BYTES_PER_BASE * n_bases / (k1_ms * 1e-3) / 1e9
         step_ms = ms_dev / args.steps
         st = {s_: ms for s_, ms, _ in stages}
-        # the kernel with the largest share of the step: the bucket merge (bucket_emit_kernel == stage "emit").
-        # algorithmic bytes: 9 B per record read + (8 + N + 8) B per row written
-        n_cols = G * world
-        emit_bytes = 9.0 * n_bases + rows_built * (16.0 + n_cols)
-        emit_ms = st.get("emit", 0.0) or 1e-9
+        # the merge kernel: bucket_merge_kernel (stage "merge": one pass over the records) or, when the fused pass does not
+        # apply, bucket_emit_smem_kernel (stage "emit").  Algorithmic bytes: 9 B per record read +
+        # (8 + N + 8) B per row written
+        n_cols = G * world if strategy != "rows" or world == 1 else G
+        rows_local = local_rows[0] if local_rows[0] else rows_built
+        emit_bytes = 9.0 * n_bases + rows_local * (16.0 + n_cols)
+        merge_stage = "merge" if "merge" in st else "emit"
+        merge_kernel = "bucket_merge_kernel" if merge_stage == "merge" else "bucket_emit_smem_kernel"
+        emit_ms = st.get(merge_stage, 0.0) or 1e-9
         emit_achieved = emit_bytes / (emit_ms * 1e-3) / 1e9
         full_size = (G == 128 and L == 5_000_000 and world == 1 and population == "star")   # what profiles/ was captured on
         line = {
@@ -311,18 +317,26 @@ def run_ours(args, rank, world, local_rank):
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": launches,
-            # dominant kernel of the step (largest share in profiles/launches_r01.csv: bucket_emit_kernel, ~1/3)
-            "roofline": {"kernel": "bucket_emit_kernel", "bound": "hbm", "achieved": emit_achieved, "peak": peak, "unit": "GB/s",
-                         "frac": emit_achieved / peak, "traffic": ncu_traffic("bucket_emit") if full_size else None,
+            # the merge kernel (K3); the partition's scatter kernels have a larger share of the step, see stages_ms / roofline_scatter
+            "roofline": {"kernel": merge_kernel, "bound": "hbm", "achieved": emit_achieved, "peak": peak, "unit": "GB/s",
+                         "frac": emit_achieved / peak, "traffic": ncu_traffic(merge_kernel.replace("_kernel", "")) if full_size else None,
                          "peak_source": peak_src, "algorithmic_bytes_per_launch": emit_bytes, "launch_ms": emit_ms,
                          "share_of_step": emit_ms / step_ms,
-                         "note": "bound by L2 atomics and shared-memory probes, not by DRAM (profiles/README.md)"},
+                         "note": "shared-memory table probes and atomics bound it, not DRAM (profiles/README.md)"},
             # the kernel the north star quotes a target for (>= 60% of HBM peak): split-k-mer extraction
             "roofline_k1": {"kernel": "k1_extract_kernel", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                             "frac": achieved / peak, "traffic": ncu_traffic("k1_extract") if full_size else None,
                             "peak_source": peak_src, "algorithmic_bytes_per_launch": K1_ALGO_BYTES_PER_BASE * n_bases,
                             "launch_ms": k1_ms, "share_of_step": st.get("k1_extract", 0.0) / step_ms,
                             "frac_of_nominal_8TBs": achieved / 8000.0},
+            # first partition pass = one scan launch + part_scatter_kernel<1> (its histogram is counted by K1): 8 B read + 8 B
+            # written per record; the second pass (stage "partition2") adds its own histogram read
+            "roofline_scatter": {"kernel": "part_scatter_kernel<1>", "bound": "hbm", "unit": "GB/s", "peak": peak,
+                                 "achieved": 16.0 * n_bases / ((st.get("partition1", 0.0) or 1e-9) * 1e-3) / 1e9,
+                                 "frac": 16.0 * n_bases / ((st.get("partition1", 0.0) or 1e-9) * 1e-3) / 1e9 / peak,
+                                 "algorithmic_bytes_per_launch": 16.0 * n_bases, "launch_ms": st.get("partition1", 0.0),
+                                 "traffic": ncu_traffic("part_scatter") if full_size else None,
+                                 "share_of_step": st.get("partition1", 0.0) / step_ms},
             "stages_ms": {s: round(ms, 3) for s, ms, _ in stages},
             "clocks": clocks.summary(),
         }
@@ -347,8 +361,9 @@ def main():
     ap.add_argument("--length", type=int, default=5_000_000)
     ap.add_argument("--k", type=int, default=31)
     ap.add_argument("--seed", type=int, default=0x5CA20002)
-    ap.add_argument("--cpu-genomes", type=int, default=16, help="bounded CPU-baseline sample (genomes)")
-    ap.add_argument("--ref-genomes", type=int, default=32, help="genomes per step of the --impl reference arm")
+    ap.add_argument("--cpu-genomes", type=int, default=40, help="bounded CPU-baseline sample (genomes): 4 threads by the reference's rule")
+    ap.add_argument("--ref-genomes", type=int, default=80, help="genomes per step of the --impl reference arm: the smallest job for which "
+                    "the reference's rule (merge_ska_dict.rs:381-385) uses 8 threads, as it does for the full 128")
     ap.add_argument("--ref-warmup", type=int, default=1, help="warm-up steps of the reference arm (-1: use --warmup)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--population", default="auto", choices=["auto", "star", "tree"],

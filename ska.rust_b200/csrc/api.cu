@@ -178,13 +178,17 @@ static std::unique_ptr<Array> build_from_batch(const SeqBatch& b, uint32_t k, bo
     uint64_t* rec = arena().take_n<uint64_t>(b.n_pos);
     uint32_t* valid = arena().take_n<uint32_t>(b.n_samples);
     SKA_CUDA(cudaMemsetAsync(valid, 0, b.n_samples * 4, c.stream));
+    // K1 also counts the records by the first partition digit, so the partition never reads them for its histogram
+    const PartPlan pl = make_part_plan(k, merge_prefix_bits(b.n_pos, k, b.n_samples), b.n_samples);
+    unsigned long long* k1_hist = arena().take_n<unsigned long long>((size_t)K1_HIST_COPIES << pl.P1);
+    SKA_CUDA(cudaMemsetAsync(k1_hist, 0, ((size_t)K1_HIST_COPIES << pl.P1) * 8, c.stream));
     timer().begin("k1_extract");
-    launch_k1(b, k, rc, false, min_qual, rec, nullptr, valid);
+    launch_k1(b, k, rc, false, min_qual, rec, nullptr, valid, 0, k1_hist, 4 + pl.key_bits - pl.P1, pl.P1);
     timer().end();
     std::vector<uint32_t> h_valid(b.n_samples);
     SKA_CUDA(cudaMemcpyAsync(h_valid.data(), valid, b.n_samples * 4, cudaMemcpyDeviceToHost, c.stream));
     std::unique_ptr<Array> a(new Array());
-    build_array_from_records(rec, b.n_pos, b.sample_off.p, (uint32_t)b.n_samples, 0, b.n_samples, k, rc, *a);   // synchronises
+    build_array_from_records(rec, b.n_pos, b.sample_off.p, (uint32_t)b.n_samples, 0, b.n_samples, k, rc, *a, pl.P, k1_hist);   // synchronises
     for (size_t s = 0; s < b.n_samples; s++)
         if (h_valid[s] == 0) throw Error("sample " + std::to_string(s) + " has no valid sequence");   // ska_dict.rs:374-376
     return a;
@@ -389,13 +393,11 @@ int skagpu_extract_records(const ska_seqbatch_t* batch, uint32_t k, int rc, uint
     timer().end();
     std::vector<uint32_t> h_valid(b.n_samples);
     SKA_CUDA(cudaMemcpyAsync(h_valid.data(), valid, b.n_samples * 4, cudaMemcpyDeviceToHost, c.stream));
-    timer().begin("partition");
     uint64_t *d_off = nullptr, *d_tiles = nullptr;
     partition_coarse(rec, b.n_pos, b.sample_off.p, (uint32_t)b.n_samples, sample_id_base, r->plan, &r->rec, &d_off, &d_tiles);
     r->off.resize(((size_t)1 << r->plan.P1) + 1);
     SKA_CUDA(cudaMemcpyAsync(r->off.data(), d_off, r->off.size() * 8, cudaMemcpyDeviceToHost, c.stream));
     SKA_CUDA(cudaStreamSynchronize(c.stream));
-    timer().end();
     r->n = r->off.back();
     for (size_t s = 0; s < b.n_samples; s++)
         if (h_valid[s] == 0) throw Error("sample " + std::to_string(sample_id_base + s) + " has no valid sequence");
@@ -553,12 +555,18 @@ int skagpu_k1_extract(const ska_seqbatch_t* batch, uint32_t k, int rc, uint8_t m
     const SeqBatch& b = *batch->b;
     if (n_positions) *n_positions = b.n_pos;
     DevBuf<uint64_t> rec(b.n_pos);
+    // the kernel variant the build launches: FASTA batches also fill the first partition histogram
+    const PartPlan pl = make_part_plan(k, merge_prefix_bits(b.n_pos, k, b.n_samples), b.n_samples);
+    DevBuf<unsigned long long> hist((size_t)K1_HIST_COPIES << pl.P1);
+    SKA_CUDA(cudaMemsetAsync(hist.p, 0, hist.bytes(), c.stream));
+    unsigned long long* hp = b.has_qual ? nullptr : hist.p;
+    const int hshift = 4 + pl.key_bits - pl.P1;
     cudaEvent_t e0, e1;
     SKA_CUDA(cudaEventCreate(&e0)); SKA_CUDA(cudaEventCreate(&e1));
     if (iters < 1) iters = 1;
-    launch_k1(b, k, rc != 0, qual_filter == SKA_QUAL_STRICT, min_qual, rec.p, nullptr, nullptr);   // warm-up
+    launch_k1(b, k, rc != 0, qual_filter == SKA_QUAL_STRICT, min_qual, rec.p, nullptr, nullptr, 0, hp, hshift, pl.P1);   // warm-up
     SKA_CUDA(cudaEventRecord(e0, c.stream));
-    for (int i = 0; i < iters; i++) launch_k1(b, k, rc != 0, qual_filter == SKA_QUAL_STRICT, min_qual, rec.p, nullptr, nullptr);
+    for (int i = 0; i < iters; i++) launch_k1(b, k, rc != 0, qual_filter == SKA_QUAL_STRICT, min_qual, rec.p, nullptr, nullptr, 0, hp, hshift, pl.P1);
     SKA_CUDA(cudaEventRecord(e1, c.stream));
     SKA_CUDA(cudaEventSynchronize(e1));
     float ms = 0; SKA_CUDA(cudaEventElapsedTime(&ms, e0, e1));

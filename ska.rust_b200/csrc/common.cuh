@@ -129,25 +129,33 @@ struct Array {
 
 // --- kernels' host launchers (one .cu each) ------------------------------------------------------
 // k1_extract.cu
+// hist != NULL (FASTA batches): also accumulate the first partition pass's histogram -- K1_HIST_COPIES copies of
+// 2^hist_bits u64 counters (zeroed by the caller), digit = record >> hist_shift
+constexpr int K1_HIST_COPIES = 32;
+constexpr int K1_HIST_MAX_BITS = 11;
 void launch_k1(const SeqBatch& b, uint32_t k, bool rc, bool strict_qual, uint8_t min_qual, uint64_t* rec_out,
-               uint16_t* sid_out, uint32_t* sample_valid, uint32_t sid_base = 0);
+               uint16_t* sid_out, uint32_t* sample_valid, uint32_t sid_base = 0, unsigned long long* hist = nullptr,
+               int hist_shift = 0, int hist_bits = 0);
 size_t padded_positions(uint64_t n_pos);
 // partition.cu: how records are grouped and packed.  P = P1 + P2 prefix bits of the key select the bucket;
 // inside a bucket a record is  key_low << (sb+2) | sample_id << 2 | middle_code  (key_low = key without its top P1 bits)
 struct PartPlan { int key_bits, sb, P, P1, P2, low_bits; };
 PartPlan make_part_plan(uint32_t k, int prefix_bits, uint64_t n_samples_total);
+// k1_hist: the first pass's histogram as K1 left it (K1_HIST_COPIES copies), or NULL to count here
 void partition_records(const uint64_t* rec, uint64_t n_pos, const uint64_t* d_sample_off, uint32_t n_samples_local, uint32_t sid_base,
-                       const PartPlan& pl, uint64_t* scratch, uint64_t** out, uint64_t** d_off, uint64_t** first_pass_buf = nullptr);
+                       const PartPlan& pl, uint64_t* scratch, uint64_t** out, uint64_t** d_off, uint64_t** first_pass_buf = nullptr,
+                       const unsigned long long* k1_hist = nullptr);
 // first pass only (what a rank does before the exchange) / second pass over received runs (what the owner does after it)
 void partition_coarse(const uint64_t* rec, uint64_t n_pos, const uint64_t* d_sample_off, uint32_t n_samples_local, uint32_t sid_base,
-                      const PartPlan& pl, uint64_t** out, uint64_t** d_off1, uint64_t** d_tile_pref);
+                      const PartPlan& pl, uint64_t** out, uint64_t** d_off1, uint64_t** d_tile_pref, const unsigned long long* k1_hist = nullptr);
 void partition_runs(const uint64_t* src, int n_runs, const uint64_t* h_run_off, uint32_t n_regions, const PartPlan& pl, uint64_t* dst,
                     uint64_t** d_bucket_off);
 // merge.cu
 // K1 records (n_rec entries; sample s owns entries [sample_off[s], sample_off[s+1]); REC_SENTINEL entries are
 // skipped) -> array; sample ids are sid_base + local index.  `rec` is overwritten (partition scratch).
 void build_array_from_records(uint64_t* rec, uint64_t n_rec, const uint64_t* d_sample_off, uint32_t n_samples_local, uint32_t sid_base,
-                              uint64_t n_samples_total, uint32_t k, bool rc, Array& out, int prefix_bits = -1 /* < 0: merge_prefix_bits */);
+                              uint64_t n_samples_total, uint32_t k, bool rc, Array& out, int prefix_bits = -1 /* < 0: merge_prefix_bits */,
+                              const unsigned long long* k1_hist = nullptr /* histogram of the plan's first pass, from K1 */);
 // k1q_reads.cu: FASTQ samples (quality masks, ntHash, exact count-filter emulation) -> array
 void build_array_from_reads(const SeqBatch& b, uint32_t k, bool rc, uint16_t min_count, uint8_t min_qual, int qual_filter, Array& out);
 // row shard: `n_runs` received runs of first-pass records covering first-level regions [lo, hi); `prec` is overwritten

@@ -28,13 +28,17 @@ namespace ska {
 size_t padded_positions(uint64_t n_pos) { return FRONT_PAD + ((n_pos + K1_T - 1) / K1_T) * K1_T + 256; }
 
 // KT > 0: k fixed at compile time (all shifts/masks become immediates); KT == 0: runtime k.
-template <int KT, bool HAS_QUAL>
+// HIST: also count the records by the top `hist_bits` bits of the key -- the histogram of the first partition pass
+// (partition.cu), which then never re-reads the records for it.  Counts go to shared memory first and to one of
+// K1_HIST_COPIES global copies at the end of the tile (tiles are many: a single copy would serialise on its counters).
+template <int KT, bool HAS_QUAL, bool HIST>
 __global__ void __launch_bounds__(K1_THREADS)
 k1_extract_kernel(const uint8_t* __restrict__ seq, const uint8_t* __restrict__ qual,
                   const uint32_t* __restrict__ start_bits, const uint64_t* __restrict__ sample_off,
                   uint32_t n_samples, uint64_t n_pos, int k_rt, int rc, uint32_t min_qual,
                   uint64_t* __restrict__ rec_out, uint16_t* __restrict__ sid_out, uint32_t* __restrict__ sample_valid,
-                  uint32_t sid_base) {
+                  uint32_t sid_base, unsigned long long* __restrict__ hist, int hist_shift, int hist_bits) {
+    __shared__ uint32_t s_hist[HIST ? (1 << K1_HIST_MAX_BITS) : 1];
     __shared__ __align__(128) uint8_t s_ascii[K1_BYTES];
     __shared__ __align__(128) uint8_t s_qual[HAS_QUAL ? K1_BYTES : 16];
     __shared__ uint32_t s_le[2 * K1_G32 + 2];
@@ -56,6 +60,7 @@ k1_extract_kernel(const uint8_t* __restrict__ seq, const uint8_t* __restrict__ q
         mbar_init(&s_mbar, 1);
         s_nvalid = 0;
     }
+    if (HIST) for (int i = tid; i < (1 << hist_bits); i += K1_THREADS) s_hist[i] = 0;
     __syncthreads();
     if (tid == 0) {
         mbar_expect_tx(&s_mbar, HAS_QUAL ? 2 * K1_BYTES : K1_BYTES);
@@ -157,6 +162,7 @@ k1_extract_kernel(const uint8_t* __restrict__ seq, const uint8_t* __restrict__ q
         const uint32_t klo = (uint32_t)key, khi = (uint32_t)(key >> 32);
         uint64_t rec = ((uint64_t)__funnelshift_l(klo, khi, 4) << 32) | ((klo << 4) | (1u << mid));
         if (!((s_ok[j] >> lane) & 1u)) rec = REC_SENTINEL;
+        else if (HIST) atomicAdd(&s_hist[(uint32_t)(rec >> hist_shift)], 1u);
         return rec;
     };
     if (full && uniform) {                                        // interior tile of one sample: no per-window checks
@@ -181,28 +187,42 @@ k1_extract_kernel(const uint8_t* __restrict__ seq, const uint8_t* __restrict__ q
     }
     // accepted windows per sample (a sample with none is an error, ska_dict.rs:374-376)
     if (tid == 0 && sample_valid && uniform && s_nvalid) atomicAdd(&sample_valid[sid_first], s_nvalid);
+    if (HIST) {
+        __syncthreads();
+        unsigned long long* h = hist + ((size_t)(blockIdx.x % K1_HIST_COPIES) << hist_bits);
+        for (int i = tid; i < (1 << hist_bits); i += K1_THREADS) {
+            const uint32_t cnt = s_hist[i];
+            if (cnt) atomicAdd(&h[i], (unsigned long long)cnt);
+        }
+    }
 }
 
 template <int KT>
 static void launch_k1_kt(const SeqBatch& b, uint32_t k, bool rc, bool strict_qual, uint8_t min_qual, uint64_t* rec_out,
-                         uint16_t* sid_out, uint32_t* sample_valid, uint32_t sid_base) {
+                         uint16_t* sid_out, uint32_t* sample_valid, uint32_t sid_base, unsigned long long* hist, int hist_shift, int hist_bits) {
     unsigned grid = (unsigned)((b.n_pos + K1_T - 1) / K1_T);
+    unsigned long long* nohist = nullptr;
     if (b.has_qual && strict_qual) {
-        SKA_LAUNCH((k1_extract_kernel<KT, true>), grid, K1_THREADS, 0, b.seq.p, b.qual.p, b.start_bits.p, b.sample_off.p,
-                   (uint32_t)b.n_samples, b.n_pos, (int)k, rc ? 1 : 0, (uint32_t)min_qual, rec_out, sid_out, sample_valid, sid_base);
-    } else {
-        SKA_LAUNCH((k1_extract_kernel<KT, false>), grid, K1_THREADS, 0, b.seq.p, (const uint8_t*)nullptr, b.start_bits.p,
+        SKA_LAUNCH((k1_extract_kernel<KT, true, false>), grid, K1_THREADS, 0, b.seq.p, b.qual.p, b.start_bits.p, b.sample_off.p,
+                   (uint32_t)b.n_samples, b.n_pos, (int)k, rc ? 1 : 0, (uint32_t)min_qual, rec_out, sid_out, sample_valid, sid_base, nohist, 0, 0);
+    } else if (hist) {
+        SKA_LAUNCH((k1_extract_kernel<KT, false, true>), grid, K1_THREADS, 0, b.seq.p, (const uint8_t*)nullptr, b.start_bits.p,
                    b.sample_off.p, (uint32_t)b.n_samples, b.n_pos, (int)k, rc ? 1 : 0, (uint32_t)min_qual, rec_out, sid_out,
-                   sample_valid, sid_base);
+                   sample_valid, sid_base, hist, hist_shift, hist_bits);
+    } else {
+        SKA_LAUNCH((k1_extract_kernel<KT, false, false>), grid, K1_THREADS, 0, b.seq.p, (const uint8_t*)nullptr, b.start_bits.p,
+                   b.sample_off.p, (uint32_t)b.n_samples, b.n_pos, (int)k, rc ? 1 : 0, (uint32_t)min_qual, rec_out, sid_out,
+                   sample_valid, sid_base, nohist, 0, 0);
     }
 }
 
 void launch_k1(const SeqBatch& b, uint32_t k, bool rc, bool strict_qual, uint8_t min_qual, uint64_t* rec_out,
-               uint16_t* sid_out, uint32_t* sample_valid, uint32_t sid_base) {
+               uint16_t* sid_out, uint32_t* sample_valid, uint32_t sid_base, unsigned long long* hist, int hist_shift, int hist_bits) {
     if (b.n_pos == 0) return;
+    if (hist && (hist_bits < 0 || hist_bits > K1_HIST_MAX_BITS)) throw Error("internal: K1 histogram wider than its shared-memory table");
     // the default k of `ska build` (cli.rs:9) gets a compile-time specialisation
-    if (k == 31) launch_k1_kt<31>(b, k, rc, strict_qual, min_qual, rec_out, sid_out, sample_valid, sid_base);
-    else launch_k1_kt<0>(b, k, rc, strict_qual, min_qual, rec_out, sid_out, sample_valid, sid_base);
+    if (k == 31) launch_k1_kt<31>(b, k, rc, strict_qual, min_qual, rec_out, sid_out, sample_valid, sid_base, hist, hist_shift, hist_bits);
+    else launch_k1_kt<0>(b, k, rc, strict_qual, min_qual, rec_out, sid_out, sample_valid, sid_base, hist, hist_shift, hist_bits);
 }
 
 }  // namespace ska

@@ -662,6 +662,294 @@ static size_t emit_smem_bytes(int log_cap, uint32_t max_u, uint32_t stride_w) {
     return cap * 8 + (size_t)max_u * stride_w * 4 + (size_t)max_u * 4 + cap * 2 + max_u + 16;
 }
 
+// ---- fused merge: ONE pass over the records ------------------------------------------------------------------------
+// The count pass above exists only to size the output and to hand sorted keys to the emit pass.  When an item's
+// table AND its base sets fit shared memory together, one CTA can do everything for its bucket in a single read of
+// the records: order-preserving table (as in bucket_count_kernel) with the 4-bit base sets indexed by SLOT, then the
+// rows leave in key order.  What is missing is the bucket's row offset = distinct keys of all earlier buckets; it
+// comes from a decoupled look-back over per-bucket status words (buckets are taken in ticket order, so every
+// predecessor is running or done and publishes its count without waiting for anyone).  The output is allocated from
+// an estimate (distinct keys of every S-th bucket, counted by bucket_count_kernel) plus a margin; a table overflow,
+// an exceeded capacity or a stalled look-back raise an error flag and merge_items falls back to the two passes.
+// dynamic smem: tab u64[slots] (later: cnt u32[slots]) | sets u32[slots * wps] | lslot u16[slots] | order u16[slots]
+constexpr int FM_THREADS = 512;
+constexpr size_t FM_SMEM_BUDGET = 110 * 1024;             // two CTAs per SM
+constexpr uint64_t ST_AGG = 1ULL << 62, ST_PREFIX = 2ULL << 62, ST_MASK = (1ULL << 62) - 1ULL;
+enum { FM_ERR_TABLE = 1, FM_ERR_CAPACITY = 2, FM_ERR_STALL = 4 };
+struct FusedCtl { uint32_t ticket, error; unsigned long long total_rows; };
+
+__global__ void __launch_bounds__(FM_THREADS, 2)
+bucket_merge_kernel(const uint64_t* __restrict__ rec, const Item* __restrict__ items, uint32_t n_items, int sb, uint32_t slots,
+                    uint32_t home_slots, uint32_t max_keys, uint32_t n_samples, int k, int rc, uint64_t cap_rows,
+                    uint64_t* __restrict__ out_keys, uint8_t* __restrict__ out_var, uint32_t* __restrict__ out_cnt,
+                    unsigned long long* __restrict__ status, FusedCtl* __restrict__ ctl) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    const uint32_t wps = n_samples >> 3;                           // set words (8 samples each) per slot / row
+    uint64_t* s_tab = reinterpret_cast<uint64_t*>(smem);
+    uint32_t* s_sets = reinterpret_cast<uint32_t*>(s_tab + slots);
+    uint16_t* s_lslot = reinterpret_cast<uint16_t*>(s_sets + (size_t)slots * wps);
+    uint16_t* s_order = s_lslot + slots;
+    __shared__ uint32_t s_goff[160];                               // slot groups (slots <= 4096 -> <= 128 groups)
+    __shared__ uint32_t s_n, s_over, s_bid;
+    __shared__ unsigned long long s_row_base;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    constexpr int NW = FM_THREADS / 32;
+
+    if (tid == 0) { s_bid = atomicAdd(&ctl->ticket, 1u); s_n = 0; s_over = 0; }
+    __syncthreads();
+    const uint32_t bid = s_bid;
+    if (bid >= n_items) return;
+    const Item it = items[bid];
+    const uint64_t beg = it.beg, end = it.end;
+
+    uint64_t nx[MG_PREFETCH];                                     // first records: in flight while the table is set up
+#pragma unroll
+    for (int j = 0; j < MG_PREFETCH; j++) {
+        const uint64_t i = beg + (uint64_t)j * FM_THREADS + tid;
+        nx[j] = i < end ? rec[i] : ~0ULL;
+    }
+    {
+        uint4* t4 = reinterpret_cast<uint4*>(s_tab);
+        const uint4 e4 = make_uint4(~0u, ~0u, ~0u, ~0u), z4 = make_uint4(0u, 0u, 0u, 0u);
+        for (uint32_t i = tid; i < slots / 2; i += FM_THREADS) t4[i] = e4;
+        uint4* z = reinterpret_cast<uint4*>(s_sets);
+        for (uint32_t i = tid; i < slots * wps / 4; i += FM_THREADS) z[i] = z4;
+    }
+    const uint64_t lo_l = it.key_lo - it.key_base, width = it.key_hi - it.key_lo;
+    const int range_bits = width ? 64 - __clzll((long long)width) : 0;
+    const int shift = range_bits - 12;                             // offset in the key range -> 12 bits -> home slot (monotone)
+    const uint32_t sid_mask = (1u << sb) - 1u;
+    __syncthreads();
+
+    // 1. records -> table + base sets
+    for (uint64_t b0 = beg; b0 < end; b0 += (uint64_t)MG_PREFETCH * FM_THREADS) {
+        uint64_t rr[MG_PREFETCH];
+#pragma unroll
+        for (int j = 0; j < MG_PREFETCH; j++) rr[j] = nx[j];
+        const uint64_t b1 = b0 + (uint64_t)MG_PREFETCH * FM_THREADS;
+        if (b1 < end) {
+#pragma unroll
+            for (int j = 0; j < MG_PREFETCH; j++) {
+                const uint64_t i = b1 + (uint64_t)j * FM_THREADS + tid;
+                nx[j] = i < end ? rec[i] : ~0ULL;
+            }
+        }
+#pragma unroll
+        for (int h = 0; h < MG_PREFETCH; h += MG_UNROLL) {
+            uint64_t kk[MG_UNROLL], cur[MG_UNROLL]; uint32_t sl[MG_UNROLL]; bool ok[MG_UNROLL];
+#pragma unroll
+            for (int j = 0; j < MG_UNROLL; j++) {
+                kk[j] = rr[h + j] >> (sb + 2);
+                const uint64_t d = kk[j] - lo_l;
+                ok[j] = (b0 + (uint64_t)(h + j) * FM_THREADS + tid < end) && d <= width;
+                const uint32_t h12 = (uint32_t)(shift >= 0 ? d >> shift : d << -shift) & 0xFFFu;
+                sl[j] = ok[j] ? (h12 * home_slots) >> 12 : 0u;
+            }
+#pragma unroll
+            for (int j = 0; j < MG_UNROLL; j++) cur[j] = *(volatile unsigned long long*)&s_tab[sl[j]];
+#pragma unroll
+            for (int j = 0; j < MG_UNROLL; j++) {
+                if (!ok[j]) continue;
+                const uint64_t key = kk[j];
+                uint32_t slot = sl[j];
+                bool found = cur[j] == key;
+                while (!found) {
+                    if (slot >= slots || *(volatile uint32_t*)&s_over) { s_over = 1; break; }
+                    unsigned long long old = *(volatile unsigned long long*)&s_tab[slot];
+                    if (old == KEY_EMPTY) {
+                        old = atomicCAS((unsigned long long*)&s_tab[slot], KEY_EMPTY, key);
+                        if (old == KEY_EMPTY) { if (atomicAdd(&s_n, 1u) >= max_keys) s_over = 1; found = true; break; }
+                    }
+                    if (old == key) { found = true; break; }
+                    slot++;
+                }
+                if (found) {
+                    const uint32_t smp = (uint32_t)(rr[h + j] >> 2) & sid_mask;
+                    atomicOr(&s_sets[slot * wps + (smp >> 3)], (1u << (uint32_t)(rr[h + j] & 3)) << (4 * (smp & 7)));
+                }
+            }
+        }
+    }
+    __syncthreads();
+    const bool over = s_over != 0;
+    const uint32_t u = over ? 0u : s_n;
+    // publish this bucket's count at once: successors only need it to get past us
+    if (tid == 0) {
+        if (over) atomicOr(&ctl->error, (uint32_t)FM_ERR_TABLE);
+        __threadfence();
+        atomicExch(&status[bid], (bid == 0 ? ST_PREFIX : ST_AGG) | (unsigned long long)u);
+    }
+
+    // 2. occupied slots in slot order, then rank inside every run of adjacent occupied slots (see bucket_count_kernel)
+    const uint32_t groups = slots >> 5;
+    for (uint32_t g = warp; g < groups; g += NW) {
+        const uint32_t m = __ballot_sync(0xFFFFFFFFu, s_tab[g * 32 + lane] != KEY_EMPTY);
+        if (lane == 0) s_goff[g] = __popc(m);
+    }
+    __syncthreads();
+    if (warp == 0) {
+        uint32_t v[5], sum = 0;                                    // 5 x 32 = 160 groups at most
+#pragma unroll
+        for (int j = 0; j < 5; j++) { const uint32_t g = lane * 5 + j; v[j] = g < groups ? s_goff[g] : 0u; sum += v[j]; }
+        uint32_t inc = sum;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { uint32_t t = __shfl_up_sync(0xFFFFFFFFu, inc, o); if (lane >= o) inc += t; }
+        uint32_t run = inc - sum;
+#pragma unroll
+        for (int j = 0; j < 5; j++) { const uint32_t g = lane * 5 + j; if (g < groups) s_goff[g] = run; run += v[j]; }
+    }
+    __syncthreads();
+    for (uint32_t g = warp; g < groups; g += NW) {
+        const bool occ = s_tab[g * 32 + lane] != KEY_EMPTY;
+        const uint32_t m = __ballot_sync(0xFFFFFFFFu, occ);
+        if (occ) s_lslot[s_goff[g] + __popc(m & ((1u << lane) - 1u))] = (uint16_t)(g * 32 + lane);
+    }
+    __syncthreads();
+    for (uint32_t i = tid; i < u; i += FM_THREADS) {
+        const uint32_t slot = s_lslot[i];
+        const uint64_t key = s_tab[slot];
+        uint32_t rank = i;
+        for (uint32_t j = slot; j > 0 && s_tab[j - 1] != KEY_EMPTY; j--) rank -= (s_tab[j - 1] > key);
+        for (uint32_t j = slot + 1; j < slots && s_tab[j] != KEY_EMPTY; j++) rank += (s_tab[j] < key);
+        s_order[rank] = (uint16_t)slot;
+    }
+    // 3. row offset: look back over the predecessors' status words
+    if (tid == 0) {
+        unsigned long long excl = 0;
+        if (bid > 0) {
+            long long j = (long long)bid - 1;
+            uint32_t spins = 0;
+            while (true) {
+                const unsigned long long st = *(volatile unsigned long long*)&status[j];
+                const unsigned long long flag = st >> 62;
+                if (flag == 2) { excl += st & ST_MASK; break; }
+                if (flag == 1) { excl += st & ST_MASK; j--; spins = 0; if (j < 0) break; continue; }
+                if (++spins > 20000000u || (*(volatile uint32_t*)&ctl->error & FM_ERR_STALL)) { atomicOr(&ctl->error, (uint32_t)FM_ERR_STALL); break; }
+                __nanosleep(40);
+            }
+            __threadfence();
+            atomicExch(&status[bid], ST_PREFIX | (excl + u));
+        }
+        if (bid + 1 == n_items) ctl->total_rows = excl + u;
+        if (excl + u > cap_rows) atomicOr(&ctl->error, (uint32_t)FM_ERR_CAPACITY);
+        s_row_base = excl;
+    }
+    __syncthreads();
+    const uint64_t row_base = s_row_base;
+    if (u == 0 || row_base + u > cap_rows) return;
+
+    // 4. keys, palindrome flags (in lslot, which is free now)
+    for (uint32_t i = tid; i < u; i += FM_THREADS) {
+        const uint64_t key = it.key_base | s_tab[s_order[i]];
+        out_keys[row_base + i] = key;
+        s_lslot[i] = (uint16_t)((rc && revcomp_key(key, k - 1) == key) ? 1 : 0);
+    }
+    __syncthreads();
+    uint32_t* s_cnt = reinterpret_cast<uint32_t*>(s_tab);          // the table is no longer needed
+    for (uint32_t i = tid; i < u; i += FM_THREADS) s_cnt[i] = 0;
+    __syncthreads();
+    // 5. rows out: 8 base sets -> 8 letters, one 8-byte store per thread and step
+    {
+        const int lg = (wps & (wps - 1)) == 0 ? 31 - __clz(wps) : -1;
+        uint2* out8 = reinterpret_cast<uint2*>(out_var + row_base * n_samples);
+        const uint32_t total = u * wps;
+        for (uint32_t idx = tid; idx < total; idx += FM_THREADS) {
+            const uint32_t row = lg >= 0 ? idx >> lg : idx / wps;
+            const uint32_t w = idx - row * wps;
+            const uint32_t x = s_sets[(uint32_t)s_order[row] * wps + w];
+            uint2 o = make_uint2(0x2D2D2D2Du, 0x2D2D2D2Du);        // "--------"
+            if (x) {
+                const bool pal = s_lslot[row];
+                o.x = letters4(spread_nibbles4(x & 0xFFFFu), pal);
+                o.y = letters4(spread_nibbles4(x >> 16), pal);
+                const uint32_t m = (x | (x >> 1) | (x >> 2) | (x >> 3)) & 0x11111111u;
+                atomicAdd(&s_cnt[row], (uint32_t)__popc(m));
+            }
+            out8[idx] = o;
+        }
+    }
+    __syncthreads();
+    for (uint32_t i = tid; i < u; i += FM_THREADS) out_cnt[row_base + i] = s_cnt[i];
+}
+
+__global__ void sample_items_kernel(const Item* __restrict__ items, uint32_t n_items, uint32_t stride, uint32_t n_out, Item* __restrict__ out) {
+    const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n_out) return;
+    Item it = items[min((uint64_t)j * stride, (uint64_t)n_items - 1)];
+    it.scratch = NO_SCRATCH;
+    out[j] = it;
+}
+
+// -> true if `out` holds the merged array; false: nothing was produced, take the two-pass path
+static bool merge_items_fused(const uint64_t* rec, const Item* items, uint32_t n_items, int sb, uint64_t n_samples, uint32_t k, bool rc,
+                              Array& out) {
+    Context& c = ctx();
+    int mode = 2;                                                  // 0 never, 1 whenever it fits (tests), 2 large builds only
+    if (const char* e = getenv("SKA_MERGE_FUSED")) mode = atoi(e);
+    if (mode == 0 || n_items == 0 || (n_samples & 7u) || n_samples > 65535) return false;
+    if (mode == 2 && n_items < 1024) return false;                // small builds: the estimate pass would cost as much as it saves
+    const uint32_t wps = (uint32_t)(n_samples >> 3);
+    const size_t per_slot = 8 + 4 * (size_t)wps + 2 + 2;
+    uint32_t slots = (uint32_t)std::min<size_t>(4096, FM_SMEM_BUDGET / per_slot) & ~31u;
+    if (slots < 256) return false;
+    const uint32_t tail = std::max(64u, (slots / 12) & ~31u);
+    const uint32_t home_slots = slots - tail, max_keys = home_slots - home_slots / 8;
+    const size_t smem = slots * per_slot;
+    if (smem + 2048 > c.smem_optin) return false;
+
+    // distinct keys of every `stride`-th bucket -> size of the output, largest bucket
+    timer().begin("estimate");
+    const uint32_t stride = std::max(1u, n_items / 2048u), ns = (n_items + stride - 1) / stride;
+    Item* sitems = arena().take_n<Item>(ns);
+    uint32_t* s_rows = arena().take_n<uint32_t>(ns);
+    uint32_t* flags = arena().take_n<uint32_t>(2);
+    SKA_CUDA(cudaMemsetAsync(flags, 0, 8, c.stream));
+    SKA_LAUNCH(sample_items_kernel, (ns + 255) / 256, 256, 0, items, n_items, stride, ns, sitems);
+    SKA_CUDA(cudaFuncSetAttribute(bucket_count_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)COUNT_SMEM));
+    SKA_LAUNCH(bucket_count_kernel, ns, MG_THREADS, COUNT_SMEM, rec, sitems, sb, (uint32_t)COUNT_LIST - 1, s_rows, flags, (uint64_t*)nullptr);
+    std::vector<uint32_t> h_rows(ns);
+    SKA_CUDA(cudaMemcpyAsync(h_rows.data(), s_rows, (size_t)ns * 4, cudaMemcpyDeviceToHost, c.stream));
+    SKA_CUDA(cudaStreamSynchronize(c.stream));
+    timer().end();
+    uint64_t sum = 0; uint32_t mx = 0;
+    const bool dbg = getenv("SKA_DEBUG_MERGE") != nullptr;
+    for (uint32_t v : h_rows) {
+        if (v == COUNT_OVERFLOW) { if (dbg) fprintf(stderr, "[skagpu] fused merge declined: a sampled bucket overflowed the count table\n"); return false; }
+        sum += v; mx = std::max(mx, v);
+    }
+    // canonical keys crowd the low prefixes (density 2(1-p)): the sample includes bucket 0, so its maximum is close to the
+    // real one; 15 % on top.  Fuller buckets belong to the two-pass path.
+    if ((uint64_t)mx + mx * 15 / 100 + 16 > max_keys) {
+        if (dbg) fprintf(stderr, "[skagpu] fused merge declined: largest sampled bucket %u keys, table holds %u\n", mx, max_keys);
+        return false;
+    }
+    const double est = (double)sum * ((double)n_items / (double)ns);
+    const uint64_t cap_rows = (uint64_t)(est * 1.06) + 8ull * mx + 4096;
+
+    timer().begin("merge");
+    out.k = k; out.rc = rc; out.key_bits = 64; out.n_samples = n_samples;
+    out.keys.alloc(cap_rows); out.variants.alloc(cap_rows * n_samples); out.counts.alloc(cap_rows);
+    unsigned long long* status = arena().take_n<unsigned long long>(n_items);
+    FusedCtl* ctl = arena().take_n<FusedCtl>(1);
+    SKA_CUDA(cudaMemsetAsync(status, 0, (size_t)n_items * 8, c.stream));
+    SKA_CUDA(cudaMemsetAsync(ctl, 0, sizeof(FusedCtl), c.stream));
+    SKA_CUDA(cudaFuncSetAttribute(bucket_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    SKA_LAUNCH(bucket_merge_kernel, n_items, FM_THREADS, smem, rec, items, n_items, sb, slots, home_slots, max_keys, (uint32_t)n_samples,
+               (int)k, rc ? 1 : 0, cap_rows, out.keys.p, out.variants.p, out.counts.p, status, ctl);
+    FusedCtl h_ctl;
+    SKA_CUDA(cudaMemcpyAsync(&h_ctl, ctl, sizeof(FusedCtl), cudaMemcpyDeviceToHost, c.stream));
+    SKA_CUDA(cudaStreamSynchronize(c.stream));
+    timer().end();
+    if (h_ctl.error) {
+        if (dbg) fprintf(stderr, "[skagpu] fused merge gave up (error %u, rows %llu, capacity %llu): two-pass path\n",
+                                               h_ctl.error, h_ctl.total_rows, (unsigned long long)cap_rows);
+        out.keys.release(); out.variants.release(); out.counts.release();
+        return false;
+    }
+    out.n_rows = out.n_keys = h_ctl.total_rows;
+    return true;
+}
+
 static int choose_prefix_bits(uint64_t n_pos, int key_bits, uint64_t target) {
     int p = 0;
     while ((n_pos >> p) > target && p < key_bits && p < 24) p++;
@@ -672,6 +960,7 @@ static int choose_prefix_bits(uint64_t n_pos, int key_bits, uint64_t target) {
 // scan to row offsets, emit rows.  `items` is a device array in ascending key order.
 static void merge_items(const uint64_t* rec, Item* items, uint32_t n_items, int sb, uint64_t n_samples, uint32_t k, bool rc, Array& out, uint64_t* scratch_keys) {
     Context& c = ctx();
+    if (merge_items_fused(rec, items, n_items, sb, n_samples, k, rc, out)) return;
     // bytes of shared memory per table slot in the emit kernel: tab 8 + rank 2 + (lkey 8 + lslot 2 + cnt 4)/2
     const size_t slot_bytes = 17;
     const int max_log_cap = 13;                                   // 8192 slots = 136 KB
@@ -872,15 +1161,13 @@ int merge_prefix_bits(uint64_t n_records_total, uint32_t k, uint64_t n_samples_t
 }
 
 void build_array_from_records(uint64_t* rec, uint64_t n_rec, const uint64_t* d_sample_off, uint32_t n_samples_local, uint32_t sid_base,
-                              uint64_t n_samples_total, uint32_t k, bool rc, Array& out, int prefix_bits) {
+                              uint64_t n_samples_total, uint32_t k, bool rc, Array& out, int prefix_bits, const unsigned long long* k1_hist) {
     const PartPlan pl = make_part_plan(k, prefix_bits >= 0 ? prefix_bits : merge_prefix_bits(n_rec, k, n_samples_total), n_samples_total);
     const uint32_t n_buckets = 1u << pl.P;
 
-    // (1) partition by key prefix
-    timer().begin("partition");
+    // (1) partition by key prefix (stages "partition1", "partition2")
     uint64_t* prec = nullptr; uint64_t* off = nullptr; uint64_t* part_a = nullptr;
-    partition_records(rec, n_rec, d_sample_off, n_samples_local, sid_base, pl, rec, &prec, &off, &part_a);
-    timer().end();
+    partition_records(rec, n_rec, d_sample_off, n_samples_local, sid_base, pl, rec, &prec, &off, &part_a, k1_hist);
 
     timer().begin("bucket_offsets");
     Item* items = arena().take_n<Item>(n_buckets);
@@ -902,11 +1189,9 @@ void build_array_from_runs(uint64_t* prec, uint64_t n_rec, int n_runs, const uin
     if (n_runs < 1) throw Error("row shard needs at least one run");
     const uint32_t nr = region_hi - region_lo;
     const uint32_t nb = nr << pl.P2;
-    timer().begin("partition");
     uint64_t* part = arena().take_n<uint64_t>(std::max<uint64_t>(n_rec, 1));
     uint64_t* off = nullptr;
     partition_runs(prec, n_runs, run_off, nr, pl, part, &off);
-    timer().end();
     timer().begin("bucket_offsets");
     Item* items = arena().take_n<Item>(std::max<uint32_t>(nb, 1));
     if (nb)

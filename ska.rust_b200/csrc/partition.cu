@@ -205,7 +205,8 @@ part_scatter_kernel(const uint64_t* __restrict__ src, uint64_t n_total, Segs sg,
 // number of tiles before every region.  Single CTA, coalesced tiles of 1024 x 4 elements.
 __global__ void __launch_bounds__(1024)
 part_scan_kernel(const unsigned long long* __restrict__ cnt, uint32_t n, uint64_t* __restrict__ off,
-                 unsigned long long* __restrict__ cursor, uint64_t* __restrict__ tile_pref /* may be null */) {
+                 unsigned long long* __restrict__ cursor, uint64_t* __restrict__ tile_pref /* may be null */,
+                 int n_copies /* cnt holds this many histograms of n counters to be added up */) {
     __shared__ uint64_t s_warp[2][32];
     __shared__ uint64_t s_carry[2];
     const uint32_t t = threadIdx.x, lane = t & 31, warp = t >> 5;
@@ -216,7 +217,9 @@ part_scan_kernel(const unsigned long long* __restrict__ cnt, uint32_t n, uint64_
 #pragma unroll
         for (int j = 0; j < 4; j++) {
             uint32_t i = base + 4 * t + j;
-            v[j] = i < n ? cnt[i] : 0ull; tl[j] = (v[j] + PT_TILE - 1) / PT_TILE;
+            v[j] = 0ull;
+            if (i < n) for (int cpy = 0; cpy < n_copies; cpy++) v[j] += cnt[(size_t)cpy * n + i];
+            tl[j] = (v[j] + PT_TILE - 1) / PT_TILE;
             sum += v[j]; tsum += tl[j];
         }
         uint64_t inc = sum, tinc = tsum;
@@ -275,28 +278,31 @@ static void set_scatter_attrs() {
 // pass 1.  rec: K1 output (n_pos entries, linear) -> packed records grouped by the top P1 key bits in `*out`
 // (arena), region offsets `*d_off1` [2^P1 + 1] and tiles-before-region `*d_tile_pref` [2^P1 + 1] on the device.
 void partition_coarse(const uint64_t* rec, uint64_t n_pos, const uint64_t* d_sample_off, uint32_t n_samples_local, uint32_t sid_base,
-                      const PartPlan& pl, uint64_t** out, uint64_t** d_off1, uint64_t** d_tile_pref) {
+                      const PartPlan& pl, uint64_t** out, uint64_t** d_off1, uint64_t** d_tile_pref, const unsigned long long* k1_hist) {
     Context& c = ctx();
+    timer().begin("partition1");
     const uint32_t D1 = 1u << pl.P1;
     unsigned long long* hist1 = arena().take_n<unsigned long long>(D1);
     unsigned long long* cur1 = arena().take_n<unsigned long long>(D1);
     uint64_t* off1 = arena().take_n<uint64_t>(D1 + 1);
     uint64_t* tile_pref = arena().take_n<uint64_t>(D1 + 1);
-    SKA_CUDA(cudaMemsetAsync(hist1, 0, D1 * 8, c.stream));
+    if (!k1_hist) SKA_CUDA(cudaMemsetAsync(hist1, 0, D1 * 8, c.stream));
     const uint64_t n_tiles1 = (n_pos + PT_TILE - 1) / PT_TILE;
     DigitFn f1{1, 4 + pl.key_bits - pl.P1, 0xFFFFFFFFu};
     PackFn pk{pl.sb, pl.low_bits >= 64 ? ~0ULL : ((1ULL << pl.low_bits) - 1ULL), sid_base};
     const unsigned hist_grid = (unsigned)std::min<uint64_t>(std::max<uint64_t>(n_tiles1, 1), (uint64_t)c.sm_count * 4);
     set_scatter_attrs();
     const Segs none{nullptr, nullptr, nullptr, nullptr, 1u};
-    if (n_pos) SKA_LAUNCH(part_hist_kernel, hist_grid, PT_THREADS, D1 * 4, rec, n_pos, n_tiles1, none, f1, pl.P1, hist1);
-    SKA_LAUNCH(part_scan_kernel, 1, 1024, 0, hist1, D1, off1, cur1, tile_pref);
+    if (n_pos && !k1_hist) SKA_LAUNCH(part_hist_kernel, hist_grid, PT_THREADS, D1 * 4, rec, n_pos, n_tiles1, none, f1, pl.P1, hist1);
+    SKA_LAUNCH(part_scan_kernel, 1, 1024, 0, k1_hist ? k1_hist : (const unsigned long long*)hist1, D1, off1, cur1, tile_pref,
+               k1_hist ? K1_HIST_COPIES : 1);
     uint64_t* a = arena().take_n<uint64_t>(std::max<uint64_t>(n_pos, 1));
     if (n_pos) {
         SKA_LAUNCH((part_scatter_kernel<1>), (unsigned)n_tiles1, PT_THREADS, scatter_smem(pl.P1), rec, n_pos, none, f1, pl.P1, pk,
                    d_sample_off, n_samples_local, cur1, a);
     }
     *out = a; *d_off1 = off1; *d_tile_pref = tile_pref;
+    timer().end();
 }
 
 // pass 2.  src: packed records; the segments (device arrays) say where the pieces of each of the `n_regions`
@@ -304,6 +310,7 @@ void partition_coarse(const uint64_t* rec, uint64_t n_pos, const uint64_t* d_sam
 void partition_fine(const uint64_t* src, const Segs& sg, uint64_t n_tiles2, uint32_t n_regions, const PartPlan& pl, uint64_t* dst,
                     uint64_t** d_bucket_off) {
     Context& c = ctx();
+    timer().begin("partition2");
     const uint32_t D2 = 1u << pl.P2;
     const size_t NB = (size_t)n_regions * D2;
     unsigned long long* hist2 = arena().take_n<unsigned long long>(std::max<size_t>(NB, 1));
@@ -317,23 +324,24 @@ void partition_fine(const uint64_t* src, const Segs& sg, uint64_t n_tiles2, uint
         const unsigned g2 = (unsigned)std::min<uint64_t>(n_tiles2, (uint64_t)c.sm_count * 4);
         SKA_LAUNCH(part_hist_kernel, g2, PT_THREADS, D2 * 4, src, (uint64_t)0, n_tiles2, sg, f2, pl.P2, hist2);
     }
-    SKA_LAUNCH(part_scan_kernel, 1, 1024, 0, hist2, (uint32_t)NB, bucket_off, cur2, (uint64_t*)nullptr);
+    SKA_LAUNCH(part_scan_kernel, 1, 1024, 0, (const unsigned long long*)hist2, (uint32_t)NB, bucket_off, cur2, (uint64_t*)nullptr, 1);
     if (n_tiles2) {
         SKA_LAUNCH((part_scatter_kernel<2>), (unsigned)n_tiles2, PT_THREADS, scatter_smem(pl.P2), src, (uint64_t)0, sg, f2, pl.P2, pk,
                    (const uint64_t*)nullptr, 0u, cur2, dst);
     }
     *d_bucket_off = bucket_off;
+    timer().end();
 }
 
 // both passes on one GPU.  Returns the packed records grouped by the P-bit prefix in `*out` (arena memory) and the
 // 2^P + 1 bucket offsets on the device in `*d_off`.
 void partition_records(const uint64_t* rec, uint64_t n_pos, const uint64_t* d_sample_off, uint32_t n_samples_local, uint32_t sid_base,
                        const PartPlan& pl, uint64_t* scratch /* n_pos u64 for the second pass, may be rec */, uint64_t** out, uint64_t** d_off,
-                       uint64_t** first_pass_buf) {
+                       uint64_t** first_pass_buf, const unsigned long long* k1_hist) {
     Context& c = ctx();
     const uint32_t D1 = 1u << pl.P1;
     uint64_t *a = nullptr, *off1 = nullptr, *tile_pref = nullptr;
-    partition_coarse(rec, n_pos, d_sample_off, n_samples_local, sid_base, pl, &a, &off1, &tile_pref);
+    partition_coarse(rec, n_pos, d_sample_off, n_samples_local, sid_base, pl, &a, &off1, &tile_pref, k1_hist);
     if (first_pass_buf) *first_pass_buf = a;
     if (pl.P2 == 0) { *out = a; *d_off = off1; return; }
     uint64_t n_tiles2 = 0;

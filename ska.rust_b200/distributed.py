@@ -210,6 +210,7 @@ def build_and_merge_sharded_rows(backend, samples_local, names_all, sample_base,
                            [int(r) * n_local for r in send_rows], group=group)
     lap("all_to_all_ms")
     arr = backend.merge_partial(recv_keys, recv_var, recv_cnt, recv_rows, cols, col_base, len(names_all), k, rc, names_all)
+    arr.local_rows = n_send                                # rows of the local build (what its merge kernel wrote)
     del local, keys, var, cnt                              # after the merge: it orders itself behind the transport
     lap("merge_ms")
     if timings is not None:

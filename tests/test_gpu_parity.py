@@ -231,13 +231,19 @@ def test_build_synthetic_matches_oracle(n, length, k, rc):
     assert_same_array(g, o)
 
 
+MERGE_PATHS = {"fused": ("1", "0"), "two-pass": ("0", "0"), "two-pass-global": ("0", "1")}   # SKA_MERGE_FUSED, SKA_EMIT_GLOBAL
+
+
 @pytest.mark.parametrize("n,k,rc", [(8, 31, True), (24, 15, True), (16, 9, True), (40, 11, False), (128, 21, True)])
-@pytest.mark.parametrize("emit_global", [0, 1])
-def test_build_emit_paths(n, k, rc, emit_global, monkeypatch):
-    """sample counts that are multiples of 8 take the 8-byte row stores of bucket_emit_smem_kernel (set words per row a
-    power of two or not); SKA_EMIT_GLOBAL=1 forces the wide-row kernel (base sets OR-ed into the output in global memory)"""
+@pytest.mark.parametrize("path", sorted(MERGE_PATHS))
+def test_build_emit_paths(n, k, rc, path, monkeypatch):
+    """the three merge paths of merge.cu on the same inputs: the fused single pass (table + base sets in shared memory,
+    row offsets by look-back), count + shared-memory emit, count + emit with the base sets OR-ed into the output in
+    global memory (wide rows).  Sample counts are multiples of 8 (8-byte row stores; set words per row a power of
+    two or not)."""
     from ska_rust_b200 import synth
-    monkeypatch.setenv("SKA_EMIT_GLOBAL", str(emit_global))
+    monkeypatch.setenv("SKA_MERGE_FUSED", MERGE_PATHS[path][0])
+    monkeypatch.setenv("SKA_EMIT_GLOBAL", MERGE_PATHS[path][1])
     genomes = synth.star_genomes(n, 6_000, seed=0x5CA20100 + n, snp_rate=0.01)
     samples = []
     for i, g in enumerate(genomes):
@@ -250,10 +256,13 @@ def test_build_emit_paths(n, k, rc, emit_global, monkeypatch):
     assert_same_array(g, ora_from_gpu_samples(samples, names, k, rc))
 
 
+@pytest.mark.parametrize("fused", ["0", "1"])
 @pytest.mark.parametrize("prefix_bits", [None, 0, 6])
-def test_build_skewed_keys_long_probe_runs(prefix_bits, monkeypatch):
+def test_build_skewed_keys_long_probe_runs(prefix_bits, fused, monkeypatch):
     """low-complexity sequence: many distinct keys share long prefixes, so the order-preserving table of the count pass
-    has long runs of occupied slots (and, with few prefix bits, items that overflow and are split); order must survive"""
+    has long runs of occupied slots (and, with few prefix bits, items that overflow and are split); order must survive.
+    With the fused merge forced on, buckets that overflow its table make it give up and the two-pass path takes over."""
+    monkeypatch.setenv("SKA_MERGE_FUSED", fused)
     if prefix_bits is not None:
         monkeypatch.setenv("SKA_PREFIX_BITS", str(prefix_bits))
     rng = np.random.default_rng(77)
@@ -273,9 +282,11 @@ def test_build_skewed_keys_long_probe_runs(prefix_bits, monkeypatch):
         assert_same_array(g, ora_from_gpu_samples(samples, names, k, rc))
 
 
-def test_build_unrelated_samples_forces_bucket_splitting():
+@pytest.mark.parametrize("fused", ["0", "1"])
+def test_build_unrelated_samples_forces_bucket_splitting(fused, monkeypatch):
     """samples that share nothing: every record is a distinct row, so buckets exceed the shared-memory table and are
-    split by further key bits (merge.cu, rare path)"""
+    split by further key bits (merge.cu, rare path); the fused merge must decline such input"""
+    monkeypatch.setenv("SKA_MERGE_FUSED", fused)
     rng = np.random.default_rng(4242)
     samples_records = [[rng.choice(np.frombuffer(b"ACGT", dtype=np.uint8), size=400_000).tobytes()] for _ in range(8)]
     samples = [S.Sample.from_records(r) for r in samples_records]
@@ -299,6 +310,29 @@ def test_build_multi_record_with_ns_and_repeats():
     for k, rc in ((9, True), (7, True), (11, False), (31, True)):
         g = S.build_from_samples(samples, names, k, rc)
         assert_same_array(g, ora_from_gpu_samples(samples, names, k, rc))
+
+
+def test_build_fused_many_buckets_matches_two_pass(monkeypatch):
+    """24 x 700 kbp: ~1000 buckets, so the fused merge's look-back chain spans many waves of CTAs; its array must equal
+    the two-pass array bit for bit (and the oracle's on a 3-sample subset)"""
+    from ska_rust_b200 import synth
+    n, length, k = 24, 700_000, 31
+    genomes = synth.star_genomes(n, length, seed=0x5CA20033, snp_rate=0.002)
+    samples = [S.Sample.from_records([g.tobytes()]) for g in genomes]
+    names = [f"s{i}" for i in range(n)]
+    monkeypatch.setenv("SKA_PREFIX_BITS", "12")
+    monkeypatch.setenv("SKA_MERGE_FUSED", "1")
+    a = S.build_from_samples(samples, names, k, True)
+    stages = [s_ for s_, _, _ in S.api.last_timings()]
+    monkeypatch.setenv("SKA_MERGE_FUSED", "0")
+    b = S.build_from_samples(samples, names, k, True)
+    ka, va, ca = a.export()
+    kb, vb, cb = b.export()
+    assert np.array_equal(ka, kb) and np.array_equal(va, vb) and np.array_equal(ca, cb)
+    assert "merge" in stages and "emit" not in stages, f"the fused merge should not have fallen back: {stages}"
+    monkeypatch.setenv("SKA_MERGE_FUSED", "1")
+    sub = S.build_from_samples(samples[:8], names[:8], k, True)
+    assert_same_array(sub, ora_from_gpu_samples(samples[:8], names[:8], k, True))
 
 
 def test_build_properties_medium():
