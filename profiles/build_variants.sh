@@ -16,6 +16,4 @@ build() {   # name, file, defines
     $NVCC -gencode arch=compute_100a,code=sm_100a -shared -o ../variants/libskagpu_$1.so $objs
 }
 build pt256x8 partition "-DSKA_PT_THREADS=256 -DSKA_PT_ITEMS=8"
-build pt256x12 partition "-DSKA_PT_THREADS=256 -DSKA_PT_ITEMS=12"
-build pt512x4 partition "-DSKA_PT_THREADS=512 -DSKA_PT_ITEMS=4"
 ls -la ../variants/*.so

@@ -127,32 +127,40 @@ bucket_count_kernel(const uint64_t* __restrict__ rec, const Item* __restrict__ i
                 ok[j] = (b0 + (uint64_t)(h + j) * MG_THREADS + threadIdx.x < it.end) && d <= width;
                 sl[j] = ok[j] ? (uint32_t)(d >> shift) : 0u;
             }
+            // a present key sits at its home slot or, displaced once, right after it (home + 1 < COUNT_SLOTS always): both are
+            // read up front so that only new keys and rarer displacements take the divergent path below
+            uint64_t cur2[MG_UNROLL];
 #pragma unroll
-            for (int j = 0; j < MG_UNROLL; j++) cur[j] = *(volatile unsigned long long*)&s_tab[sl[j]];
+            for (int j = 0; j < MG_UNROLL; j++) {
+                cur[j] = *(volatile unsigned long long*)&s_tab[sl[j]];
+                cur2[j] = *(volatile unsigned long long*)&s_tab[sl[j] + 1];
+            }
 #pragma unroll
             for (int j = 0; j < MG_UNROLL; j++) {
                 const uint64_t key = kk[j];
-                if (!ok[j] || cur[j] == key) continue;
-                if (*(volatile uint32_t*)&s_over) break;
-                uint32_t slot = sl[j];
-                while (true) {
-                    if (slot >= (uint32_t)COUNT_SLOTS) { s_over = 1; break; }     // ran off the tail: too dense up here, split the item
-                    unsigned long long old = *(volatile unsigned long long*)&s_tab[slot];
-                    if (old == key) break;
-                    if (old == KEY_EMPTY) {
-                        old = atomicCAS((unsigned long long*)&s_tab[slot], KEY_EMPTY, key);
-                        if (old == KEY_EMPTY) {
-                            if (atomicAdd(&s_n, 1u) >= (uint32_t)COUNT_LIST) s_over = 1;   // keep the table sparse enough to probe
-                            break;
-                        }
+                if (ok[j] && cur[j] != key && cur2[j] != key && !*(volatile uint32_t*)&s_over) {
+                    uint32_t slot = sl[j];
+                    while (true) {
+                        if (slot >= (uint32_t)COUNT_SLOTS) { s_over = 1; break; }     // ran off the tail: too dense up here, split the item
+                        unsigned long long old = *(volatile unsigned long long*)&s_tab[slot];
                         if (old == key) break;
+                        if (old == KEY_EMPTY) {
+                            old = atomicCAS((unsigned long long*)&s_tab[slot], KEY_EMPTY, key);
+                            if (old == KEY_EMPTY) {
+                                if (atomicAdd(&s_n, 1u) >= (uint32_t)COUNT_LIST) s_over = 1;   // keep the table sparse enough to probe
+                                break;
+                            }
+                            if (old == key) break;
+                        }
+                        slot++;
                     }
-                    slot++;
                 }
+                __syncwarp();          // lanes that inserted rejoin the others before the next record (they would otherwise stay apart)
             }
         }
     }
     __syncthreads();
+    // (counting the keys at insertion is measured faster than counting the occupied slots afterwards: 2.90 vs 4.26 ms)
     const uint32_t n = s_over ? COUNT_OVERFLOW : s_n;
     if (threadIdx.x == 0) {
         n_rows[blockIdx.x] = n;
@@ -547,12 +555,14 @@ bucket_emit_smem_kernel(const uint64_t* __restrict__ rec, const Item* __restrict
     uint16_t* s_rank = reinterpret_cast<uint16_t*>(s_cnt + max_u);
     uint8_t* s_pal = reinterpret_cast<uint8_t*>(s_rank + cap);
 
+    __shared__ uint32_t s_anypal;
     const uint32_t b = blockIdx.x;
     const Item it = items[b];
     const uint64_t beg = it.beg, end = it.end;
     const uint64_t row_base = row_off[b];
     const uint32_t u = (uint32_t)(row_off[b + 1] - row_base);     // distinct keys, from the count pass
     if (u == 0) return;
+    if (threadIdx.x == 0) s_anypal = 0;
 
     uint64_t nx[MG_PREFETCH];                                     // first records: in flight while the table is set up
 #pragma unroll
@@ -571,7 +581,9 @@ bucket_emit_smem_kernel(const uint64_t* __restrict__ rec, const Item* __restrict
     for (uint32_t i = threadIdx.x; i < u; i += MG_THREADS) {
         const uint64_t key = scratch_keys[it.scratch + i];
         out_keys[row_base + i] = key;
-        s_pal[i] = (uint8_t)((rc && revcomp_key(key, k - 1) == key) ? 1 : 0);
+        const bool pal = rc && revcomp_key(key, k - 1) == key;
+        s_pal[i] = (uint8_t)(pal ? 1 : 0);
+        if (pal) s_anypal = 1;
         s_cnt[i] = 0;
         const uint64_t kl = key ^ it.key_base;
         uint32_t slot = hash_slot(kl, log_cap);
@@ -603,22 +615,31 @@ bucket_emit_smem_kernel(const uint64_t* __restrict__ rec, const Item* __restrict
                 sl[j] = hash_slot(kk[j], log_cap);
             }
 #pragma unroll
-            for (int j = 0; j < MG_UNROLL; j++) cur[j] = s_tab[sl[j]];
+            for (int j = 0; j < MG_UNROLL; j++) {                  // home slot and the next one, branch-free: covers ~98 % of the probes
+                const uint32_t s1 = (sl[j] + 1) & (cap - 1);
+                const uint64_t c0 = s_tab[sl[j]], c1 = s_tab[s1];
+                const bool second = c0 != kk[j] && c1 == kk[j];
+                cur[j] = second ? c1 : c0;
+                sl[j] = second ? s1 : sl[j];
+            }
 #pragma unroll
-            for (int j = 0; j < MG_UNROLL; j++) {                  // collisions: walk on (rare); bounded so that a foreign key cannot hang the CTA
+            for (int j = 0; j < MG_UNROLL; j++) {                  // longer collision chains: walk on (rare); bounded so that a foreign key cannot hang the CTA
                 const bool live = b0 + (uint64_t)(h + j) * MG_THREADS + threadIdx.x < end;
                 uint32_t probes = 0;
                 while (live && cur[j] != kk[j] && probes < cap) { sl[j] = (sl[j] + 1) & (cap - 1); cur[j] = s_tab[sl[j]]; probes++; }
                 if (!live || cur[j] != kk[j]) kk[j] = KEY_EMPTY;
+                __syncwarp();
             }
 #pragma unroll
             for (int j = 0; j < MG_UNROLL; j++) rk[j] = s_rank[sl[j]];
 #pragma unroll
             for (int j = 0; j < MG_UNROLL; j++) {
-                if (kk[j] == KEY_EMPTY) continue;
-                const uint32_t smp = (uint32_t)(rr[h + j] >> 2) & sid_mask;
-                atomicOr(&s_sets[rk[j] * stride_w + (smp >> 3)], (1u << (uint32_t)(rr[h + j] & 3)) << (4 * (smp & 7)));
+                if (kk[j] != KEY_EMPTY) {
+                    const uint32_t smp = (uint32_t)(rr[h + j] >> 2) & sid_mask;
+                    atomicOr(&s_sets[rk[j] * stride_w + (smp >> 3)], (1u << (uint32_t)(rr[h + j] & 3)) << (4 * (smp & 7)));
+                }
             }
+            __syncwarp();
         }
     }
     __syncthreads();
@@ -633,15 +654,22 @@ bucket_emit_smem_kernel(const uint64_t* __restrict__ rec, const Item* __restrict
             const uint32_t row = lg >= 0 ? idx >> lg : idx / wpr;
             const uint32_t w = idx - row * wpr;
             const uint32_t x = s_sets[row * stride_w + w];
-            uint2 o = make_uint2(0x2D2D2D2Du, 0x2D2D2D2Du);        // "--------"
-            if (x) {
-                const bool pal = s_pal[row];
-                o.x = letters4(spread_nibbles4(x & 0xFFFFu), pal);
-                o.y = letters4(spread_nibbles4(x >> 16), pal);
-                const uint32_t m = (x | (x >> 1) | (x >> 2) | (x >> 3)) & 0x11111111u;
-                atomicAdd(&s_cnt[row], (uint32_t)__popc(m));
-            }
+            // branch-free: an empty set maps to '-' by the same table; palindromic rows (rare) are redone below
+            uint2 o;
+            o.x = iupac_letters4(spread_nibbles4(x & 0xFFFFu));
+            o.y = iupac_letters4(spread_nibbles4(x >> 16));
+            const uint32_t m = (x | (x >> 1) | (x >> 2) | (x >> 3)) & 0x11111111u;
+            if (m) atomicAdd(&s_cnt[row], (uint32_t)__popc(m));
             out8[idx] = o;
+        }
+        if (s_anypal) {                                            // W/S/N for palindromic keys (ska_dict.rs:85-113)
+            __syncthreads();
+            for (uint32_t idx = threadIdx.x; idx < total; idx += MG_THREADS) {
+                const uint32_t row = lg >= 0 ? idx >> lg : idx / wpr;
+                if (!s_pal[row]) continue;
+                const uint32_t x = s_sets[row * stride_w + (idx - row * wpr)];
+                out8[idx] = make_uint2(letters4(spread_nibbles4(x & 0xFFFFu), true), letters4(spread_nibbles4(x >> 16), true));
+            }
         }
     } else {
         uint8_t* outb = out_var + row_base * n_samples;
@@ -690,12 +718,12 @@ bucket_merge_kernel(const uint64_t* __restrict__ rec, const Item* __restrict__ i
     uint16_t* s_lslot = reinterpret_cast<uint16_t*>(s_sets + (size_t)slots * wps);
     uint16_t* s_order = s_lslot + slots;
     __shared__ uint32_t s_goff[160];                               // slot groups (slots <= 4096 -> <= 128 groups)
-    __shared__ uint32_t s_n, s_over, s_bid;
+    __shared__ uint32_t s_n, s_over, s_bid, s_anypal;
     __shared__ unsigned long long s_row_base;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     constexpr int NW = FM_THREADS / 32;
 
-    if (tid == 0) { s_bid = atomicAdd(&ctl->ticket, 1u); s_n = 0; s_over = 0; }
+    if (tid == 0) { s_bid = atomicAdd(&ctl->ticket, 1u); s_n = 0; s_over = 0; s_anypal = 0; }
     __syncthreads();
     const uint32_t bid = s_bid;
     if (bid >= n_items) return;
@@ -749,38 +777,37 @@ bucket_merge_kernel(const uint64_t* __restrict__ rec, const Item* __restrict__ i
             for (int j = 0; j < MG_UNROLL; j++) cur[j] = *(volatile unsigned long long*)&s_tab[sl[j]];
 #pragma unroll
             for (int j = 0; j < MG_UNROLL; j++) {
-                if (!ok[j]) continue;
                 const uint64_t key = kk[j];
                 uint32_t slot = sl[j];
-                bool found = cur[j] == key;
-                while (!found) {
-                    if (slot >= slots || *(volatile uint32_t*)&s_over) { s_over = 1; break; }
-                    unsigned long long old = *(volatile unsigned long long*)&s_tab[slot];
-                    if (old == KEY_EMPTY) {
-                        old = atomicCAS((unsigned long long*)&s_tab[slot], KEY_EMPTY, key);
-                        if (old == KEY_EMPTY) { if (atomicAdd(&s_n, 1u) >= max_keys) s_over = 1; found = true; break; }
+                bool found = ok[j] && cur[j] == key;
+                if (ok[j] && !found) {
+                    while (true) {
+                        if (slot >= slots || *(volatile uint32_t*)&s_over) { s_over = 1; break; }
+                        unsigned long long old = *(volatile unsigned long long*)&s_tab[slot];
+                        if (old == KEY_EMPTY) {
+                            old = atomicCAS((unsigned long long*)&s_tab[slot], KEY_EMPTY, key);
+                            if (old == KEY_EMPTY) { found = true; break; }
+                        }
+                        if (old == key) { found = true; break; }
+                        slot++;
                     }
-                    if (old == key) { found = true; break; }
-                    slot++;
                 }
-                if (found) {
+                __syncwarp();          // lanes that probed or inserted rejoin the others before the next record
+                sl[j] = slot; ok[j] = found;
+            }
+#pragma unroll
+            for (int j = 0; j < MG_UNROLL; j++) {
+                if (ok[j]) {
                     const uint32_t smp = (uint32_t)(rr[h + j] >> 2) & sid_mask;
-                    atomicOr(&s_sets[slot * wps + (smp >> 3)], (1u << (uint32_t)(rr[h + j] & 3)) << (4 * (smp & 7)));
+                    atomicOr(&s_sets[sl[j] * wps + (smp >> 3)], (1u << (uint32_t)(rr[h + j] & 3)) << (4 * (smp & 7)));
                 }
             }
+            __syncwarp();
         }
     }
     __syncthreads();
-    const bool over = s_over != 0;
-    const uint32_t u = over ? 0u : s_n;
-    // publish this bucket's count at once: successors only need it to get past us
-    if (tid == 0) {
-        if (over) atomicOr(&ctl->error, (uint32_t)FM_ERR_TABLE);
-        __threadfence();
-        atomicExch(&status[bid], (bid == 0 ? ST_PREFIX : ST_AGG) | (unsigned long long)u);
-    }
-
-    // 2. occupied slots in slot order, then rank inside every run of adjacent occupied slots (see bucket_count_kernel)
+    // 2. occupied slots in slot order (their number is the bucket's row count), then rank inside every run of
+    //    adjacent occupied slots (see bucket_count_kernel)
     const uint32_t groups = slots >> 5;
     for (uint32_t g = warp; g < groups; g += NW) {
         const uint32_t m = __ballot_sync(0xFFFFFFFFu, s_tab[g * 32 + lane] != KEY_EMPTY);
@@ -797,8 +824,18 @@ bucket_merge_kernel(const uint64_t* __restrict__ rec, const Item* __restrict__ i
         uint32_t run = inc - sum;
 #pragma unroll
         for (int j = 0; j < 5; j++) { const uint32_t g = lane * 5 + j; if (g < groups) s_goff[g] = run; run += v[j]; }
+        if (lane == 31) {
+            // publish this bucket's count at once: successors only need it to get past us
+            const bool ov = *(volatile uint32_t*)&s_over != 0;
+            const uint32_t cnt = ov ? 0u : inc;
+            s_n = cnt;
+            if (ov) atomicOr(&ctl->error, (uint32_t)FM_ERR_TABLE);
+            __threadfence();
+            atomicExch(&status[bid], (bid == 0 ? ST_PREFIX : ST_AGG) | (unsigned long long)cnt);
+        }
     }
     __syncthreads();
+    const uint32_t u = s_n;
     for (uint32_t g = warp; g < groups; g += NW) {
         const bool occ = s_tab[g * 32 + lane] != KEY_EMPTY;
         const uint32_t m = __ballot_sync(0xFFFFFFFFu, occ);
@@ -813,26 +850,37 @@ bucket_merge_kernel(const uint64_t* __restrict__ rec, const Item* __restrict__ i
         for (uint32_t j = slot + 1; j < slots && s_tab[j] != KEY_EMPTY; j++) rank += (s_tab[j] < key);
         s_order[rank] = (uint16_t)slot;
     }
-    // 3. row offset: look back over the predecessors' status words
-    if (tid == 0) {
+    // 3. row offset: warp 0 looks back over the predecessors' status words, 32 at a time
+    if (warp == 0) {
         unsigned long long excl = 0;
-        if (bid > 0) {
-            long long j = (long long)bid - 1;
-            uint32_t spins = 0;
-            while (true) {
-                const unsigned long long st = *(volatile unsigned long long*)&status[j];
-                const unsigned long long flag = st >> 62;
-                if (flag == 2) { excl += st & ST_MASK; break; }
-                if (flag == 1) { excl += st & ST_MASK; j--; spins = 0; if (j < 0) break; continue; }
-                if (++spins > 20000000u || (*(volatile uint32_t*)&ctl->error & FM_ERR_STALL)) { atomicOr(&ctl->error, (uint32_t)FM_ERR_STALL); break; }
+        long long j = (long long)bid - 1;                         // nearest predecessor not yet accounted for
+        uint32_t spins = 0;
+        bool stalled = false;
+        while (j >= 0) {
+            const long long idx = j - lane;
+            const unsigned long long st = idx >= 0 ? *(volatile unsigned long long*)&status[idx] : ST_PREFIX;   // nothing before bucket 0
+            const uint32_t flag = (uint32_t)(st >> 62);
+            const uint32_t not_ready = __ballot_sync(0xFFFFFFFFu, flag == 0), prefix = __ballot_sync(0xFFFFFFFFu, flag == 2);
+            const int first_nr = not_ready ? __ffs(not_ready) - 1 : 32, first_pf = prefix ? __ffs(prefix) - 1 : 32;
+            const int take = first_pf < first_nr ? first_pf + 1 : first_nr;       // lanes 0..take-1 are usable in order
+            unsigned long long v = lane < take ? (st & ST_MASK) : 0ULL;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, o);
+            excl += v;
+            if (first_pf < first_nr) break;                       // reached an inclusive prefix: done
+            j -= take;
+            if (take == 0) {                                      // nearest predecessor has not published yet
+                if (++spins > 20000000u || (*(volatile uint32_t*)&ctl->error & FM_ERR_STALL)) { stalled = true; break; }
                 __nanosleep(40);
-            }
-            __threadfence();
-            atomicExch(&status[bid], ST_PREFIX | (excl + u));
+            } else spins = 0;
         }
-        if (bid + 1 == n_items) ctl->total_rows = excl + u;
-        if (excl + u > cap_rows) atomicOr(&ctl->error, (uint32_t)FM_ERR_CAPACITY);
-        s_row_base = excl;
+        if (lane == 0) {
+            if (stalled) atomicOr(&ctl->error, (uint32_t)FM_ERR_STALL);
+            if (bid > 0) { __threadfence(); atomicExch(&status[bid], ST_PREFIX | (excl + u)); }
+            if (bid + 1 == n_items) ctl->total_rows = excl + u;
+            if (excl + u > cap_rows) atomicOr(&ctl->error, (uint32_t)FM_ERR_CAPACITY);
+            s_row_base = excl;
+        }
     }
     __syncthreads();
     const uint64_t row_base = s_row_base;
@@ -842,7 +890,9 @@ bucket_merge_kernel(const uint64_t* __restrict__ rec, const Item* __restrict__ i
     for (uint32_t i = tid; i < u; i += FM_THREADS) {
         const uint64_t key = it.key_base | s_tab[s_order[i]];
         out_keys[row_base + i] = key;
-        s_lslot[i] = (uint16_t)((rc && revcomp_key(key, k - 1) == key) ? 1 : 0);
+        const bool pal = rc && revcomp_key(key, k - 1) == key;
+        s_lslot[i] = (uint16_t)(pal ? 1 : 0);
+        if (pal) s_anypal = 1;
     }
     __syncthreads();
     uint32_t* s_cnt = reinterpret_cast<uint32_t*>(s_tab);          // the table is no longer needed
@@ -857,15 +907,21 @@ bucket_merge_kernel(const uint64_t* __restrict__ rec, const Item* __restrict__ i
             const uint32_t row = lg >= 0 ? idx >> lg : idx / wps;
             const uint32_t w = idx - row * wps;
             const uint32_t x = s_sets[(uint32_t)s_order[row] * wps + w];
-            uint2 o = make_uint2(0x2D2D2D2Du, 0x2D2D2D2Du);        // "--------"
-            if (x) {
-                const bool pal = s_lslot[row];
-                o.x = letters4(spread_nibbles4(x & 0xFFFFu), pal);
-                o.y = letters4(spread_nibbles4(x >> 16), pal);
-                const uint32_t m = (x | (x >> 1) | (x >> 2) | (x >> 3)) & 0x11111111u;
-                atomicAdd(&s_cnt[row], (uint32_t)__popc(m));
-            }
+            uint2 o;                                               // branch-free; palindromic rows (rare) are redone below
+            o.x = iupac_letters4(spread_nibbles4(x & 0xFFFFu));
+            o.y = iupac_letters4(spread_nibbles4(x >> 16));
+            const uint32_t m = (x | (x >> 1) | (x >> 2) | (x >> 3)) & 0x11111111u;
+            if (m) atomicAdd(&s_cnt[row], (uint32_t)__popc(m));
             out8[idx] = o;
+        }
+        if (s_anypal) {
+            __syncthreads();
+            for (uint32_t idx = tid; idx < total; idx += FM_THREADS) {
+                const uint32_t row = lg >= 0 ? idx >> lg : idx / wps;
+                if (!s_lslot[row]) continue;
+                const uint32_t x = s_sets[(uint32_t)s_order[row] * wps + (idx - row * wps)];
+                out8[idx] = make_uint2(letters4(spread_nibbles4(x & 0xFFFFu), true), letters4(spread_nibbles4(x >> 16), true));
+            }
         }
     }
     __syncthreads();
@@ -884,7 +940,9 @@ __global__ void sample_items_kernel(const Item* __restrict__ items, uint32_t n_i
 static bool merge_items_fused(const uint64_t* rec, const Item* items, uint32_t n_items, int sb, uint64_t n_samples, uint32_t k, bool rc,
                               Array& out) {
     Context& c = ctx();
-    int mode = 2;                                                  // 0 never, 1 whenever it fits (tests), 2 large builds only
+    // Measured on 128 x 5 Mbp: 7.9 ms for the fused pass against 2.9 + 3.8 ms for count + emit -- reading the records
+    // twice costs less than the slot-indexed sets and the look-back; the two passes stay the default.
+    int mode = 0;                                                  // 0 never (default), 1 whenever it fits, 2 large builds only
     if (const char* e = getenv("SKA_MERGE_FUSED")) mode = atoi(e);
     if (mode == 0 || n_items == 0 || (n_samples & 7u) || n_samples > 65535) return false;
     if (mode == 2 && n_items < 1024) return false;                // small builds: the estimate pass would cost as much as it saves

@@ -16,6 +16,9 @@
 //   * ranking inside a tile is one shared-memory atomicAdd per record on a per-digit counter (measured
 //     faster on B200 than ballot-matching peers: 10.5 ms vs 17.5 ms for the whole partition of 6.4e8
 //     records); records are staged in shared memory in digit order so the global stores are coalesced runs.
+// Tried and dropped (profiles/README.md): other tile shapes (256 x 8, 256 x 12, 512 x 4 records: equal or slower --
+// shorter runs per digit cost more than the extra CTAs per SM gain) and a persistent form that keeps the next tile's
+// loads in flight (4.7 vs 4.6 ms per pass: the kernel does not wait on its loads).
 // Roofline: HBM; 8 B read by each histogram, 8 B read + 8 B written by each scatter, per record.
 #include "common.cuh"
 

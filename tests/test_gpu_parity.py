@@ -312,6 +312,29 @@ def test_build_multi_record_with_ns_and_repeats():
         assert_same_array(g, ora_from_gpu_samples(samples, names, k, rc))
 
 
+@pytest.mark.parametrize("k,rc", [(31, True), (15, False), (9, True)])
+def test_build_k1_histogram_fusion(k, rc, monkeypatch):
+    """SKA_K1_HIST=1: K1 also counts the first partition digit (the partition then skips its own histogram pass);
+    same array either way"""
+    from ska_rust_b200 import synth
+    n = 6
+    genomes = synth.star_genomes(n, 150_000, seed=0x5CA20044 + k, snp_rate=0.003)
+    samples = []
+    for i, g in enumerate(genomes):
+        g = g.copy()
+        g[700 * (i + 1):700 * (i + 1) + 40] = ord("N")
+        samples.append(S.Sample.from_records([g[:70_001].tobytes(), g[70_001:].tobytes(), b"ACGT" * 9]))
+    names = [f"s{i}" for i in range(n)]
+    monkeypatch.setenv("SKA_K1_HIST", "1")
+    a = S.build_from_samples(samples, names, k, rc)
+    monkeypatch.setenv("SKA_K1_HIST", "0")
+    b = S.build_from_samples(samples, names, k, rc)
+    ka, va, ca = a.export()
+    kb, vb, cb = b.export()
+    assert np.array_equal(ka, kb) and np.array_equal(va, vb) and np.array_equal(ca, cb)
+    assert_same_array(a, ora_from_gpu_samples(samples, names, k, rc))
+
+
 def test_build_fused_many_buckets_matches_two_pass(monkeypatch):
     """24 x 700 kbp: ~1000 buckets, so the fused merge's look-back chain spans many waves of CTAs; its array must equal
     the two-pass array bit for bit (and the oracle's on a 3-sample subset)"""
