@@ -297,6 +297,7 @@ def run_ours(args, rank, world, local_rank):
         merge_kernel = "bucket_merge_kernel" if merge_stage == "merge" else "bucket_emit_smem_kernel"
         emit_ms = st.get(merge_stage, 0.0) or 1e-9
         emit_achieved = emit_bytes / (emit_ms * 1e-3) / 1e9
+        part1_bytes = (16.0 if os.environ.get("SKA_K1_HIST", "0") not in ("", "0") else 24.0) * n_bases
         full_size = (G == 128 and L == 5_000_000 and world == 1 and population == "star")   # what profiles/ was captured on
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -329,14 +330,13 @@ def run_ours(args, rank, world, local_rank):
                             "peak_source": peak_src, "algorithmic_bytes_per_launch": K1_ALGO_BYTES_PER_BASE * n_bases,
                             "launch_ms": k1_ms, "share_of_step": st.get("k1_extract", 0.0) / step_ms,
                             "frac_of_nominal_8TBs": achieved / 8000.0},
-            # first partition pass = one scan launch + part_scatter_kernel<1> (its histogram is counted by K1): 8 B read + 8 B
-            # written per record; the second pass (stage "partition2") adds its own histogram read
-            "roofline_scatter": {"kernel": "part_scatter_kernel<1>", "bound": "hbm", "unit": "GB/s", "peak": peak,
-                                 "achieved": 16.0 * n_bases / ((st.get("partition1", 0.0) or 1e-9) * 1e-3) / 1e9,
-                                 "frac": 16.0 * n_bases / ((st.get("partition1", 0.0) or 1e-9) * 1e-3) / 1e9 / peak,
-                                 "algorithmic_bytes_per_launch": 16.0 * n_bases, "launch_ms": st.get("partition1", 0.0),
-                                 "traffic": ncu_traffic("part_scatter") if full_size else None,
-                                 "share_of_step": st.get("partition1", 0.0) / step_ms},
+            # first partition pass (stage "partition1") = part_hist_kernel + scan + part_scatter_kernel<1>: 8 B read by the
+            # histogram, 8 B read + 8 B written by the scatter, per record (with SKA_K1_HIST=1 K1 counts the histogram: 16 B)
+            "roofline_scatter": {"kernel": "part_hist_kernel + part_scatter_kernel<1>", "bound": "hbm", "unit": "GB/s", "peak": peak,
+                                 "achieved": part1_bytes / ((st.get("partition1", 0.0) or 1e-9) * 1e-3) / 1e9,
+                                 "frac": part1_bytes / ((st.get("partition1", 0.0) or 1e-9) * 1e-3) / 1e9 / peak,
+                                 "algorithmic_bytes_per_launch": part1_bytes, "launch_ms": st.get("partition1", 0.0),
+                                 "traffic": None, "share_of_step": st.get("partition1", 0.0) / step_ms},
             "stages_ms": {s: round(ms, 3) for s, ms, _ in stages},
             "clocks": clocks.summary(),
         }

@@ -81,9 +81,10 @@ class GpuBackend:
     # ---- "rows" strategy
     region_bits_max = 12          # 4096 key ranges to cut owners from: fine enough to balance 8-16 ranks, small enough to plan in microseconds
 
-    def build_local(self, samples, names_local, k, rc):
+    def build_local(self, samples, names_local, k, rc, qual=None):
+        """the rank's own samples -> its array; FASTQ samples take `qual` (api.QualOpts: min_count, min_qual, qual_filter)"""
         batch = samples if isinstance(samples, api.SeqBatch) else api.SeqBatch(samples)
-        return api.build_from_batch(batch, names_local, k, rc)
+        return api.build_from_batch(batch, names_local, k, rc, qual)
 
     def key_cumulative(self, arr, region_bits):
         cum = np.zeros((1 << region_bits) + 1, dtype=np.uint64)
@@ -168,7 +169,7 @@ def rows_exchange_plan(all_cum, world, rank):
     return cuts, send_rows, recv_rows
 
 
-def build_and_merge_sharded_rows(backend, samples_local, names_all, sample_base, k, rc, group=None, timings=None):
+def build_and_merge_sharded_rows(backend, samples_local, names_all, sample_base, k, rc, group=None, timings=None, qual=None):
     """"rows" strategy (module docstring).  -> this rank's slab.  Collective over `group`."""
     import time
     world = dist.get_world_size(group)
@@ -185,7 +186,10 @@ def build_and_merge_sharded_rows(backend, samples_local, names_all, sample_base,
             t_last[0] = now
 
     n_local = samples_local.n_samples() if hasattr(samples_local, "n_samples") else len(samples_local)
-    local = backend.build_local(samples_local, names_all[sample_base:sample_base + n_local], k, rc)
+    if qual is not None:
+        local = backend.build_local(samples_local, names_all[sample_base:sample_base + n_local], k, rc, qual)
+    else:
+        local = backend.build_local(samples_local, names_all[sample_base:sample_base + n_local], k, rc)
     lap("local_build_ms")
     region_bits = min(backend.region_bits_max, 2 * (k - 1))
     cum = backend.key_cumulative(local, region_bits)
@@ -221,14 +225,17 @@ def build_and_merge_sharded_rows(backend, samples_local, names_all, sample_base,
 
 
 def build_and_merge_sharded(backend, samples_local, names_all, sample_base, k, rc, prefix_bits=None, group=None,
-                            timings=None, strategy="rows"):
+                            timings=None, strategy="rows", qual=None):
     """-> this rank's slab (a MergeSkaArray with len(names_all) columns).  Collective over `group`.
     strategy "rows" (default) exchanges partial rows after a local build, "records" exchanges records between the
     two partition passes (module docstring); `prefix_bits` only concerns "records"."""
     if strategy == "rows":
-        return build_and_merge_sharded_rows(backend, samples_local, names_all, sample_base, k, rc, group=group, timings=timings)
+        return build_and_merge_sharded_rows(backend, samples_local, names_all, sample_base, k, rc, group=group, timings=timings,
+                                            qual=qual)
     if strategy != "records":
         raise ValueError(f"unknown strategy {strategy!r}")
+    if qual is not None:
+        raise api.SkaError("FASTQ samples (count filter) shard with strategy='rows' only")
     import time
     world = dist.get_world_size(group)
     rank = dist.get_rank(group)

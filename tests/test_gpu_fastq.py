@@ -101,3 +101,39 @@ def test_fastq_bloom_false_positives_saturated(min_count):
     same(g, o)
     # the effect under test must actually be present: without false positives the result differs
     assert g.dims()["n_rows"] > 300_000
+
+
+def test_fastq_samples_shard_by_rows():
+    """FASTQ samples through the multi-GPU "rows" path (every 'rank' builds its own reads with the count filter, the
+    owners join the partial rows), emulated on one GPU with the exchange replaced by copies: equals the oracle's array"""
+    import torch
+
+    import ska_rust_b200.distributed as D
+    from ska_rust_b200 import synth
+    genomes = synth.star_genomes(4, 12_000, seed=0x5CA20005, snp_rate=0.003)
+    gs, os_ = zip(*[make_reads_sample(g, 2500, 0.01, 91 + i) for i, g in enumerate(genomes)])
+    names = [f"r{i}" for i in range(4)]
+    k, q = 21, S.QualOpts(min_count=3, min_qual=20, qual_filter="strict")
+    backend = D.GpuBackend()
+    bounds = [(0, 1), (1, 4)]                                  # uneven ranks
+    world = len(bounds)
+    region_bits = min(backend.region_bits_max, 2 * (k - 1))
+    local = [backend.build_local(list(gs[lo:hi]), names[lo:hi], k, True, q) for lo, hi in bounds]
+    all_cum = np.stack([backend.key_cumulative(a, region_bits) for a in local])
+    tensors = [backend.array_tensors(a) for a in local]
+    cols = np.array([hi - lo for lo, hi in bounds], dtype=np.int64)
+    col_base = np.array([lo for lo, _ in bounds], dtype=np.int64)
+    parts = []
+    for g in range(world):
+        cuts, send, recv = D.rows_exchange_plan(all_cum, world, g)
+        b = all_cum[:, cuts]
+        keys = torch.cat([tensors[r][0][int(b[r, g]):int(b[r, g + 1])] for r in range(world)])
+        cnt = torch.cat([tensors[r][2][int(b[r, g]):int(b[r, g + 1])] for r in range(world)])
+        var = torch.cat([tensors[r][1][int(b[r, g]) * int(cols[r]):int(b[r, g + 1]) * int(cols[r])] for r in range(world)])
+        slab = backend.merge_partial(keys, var, cnt, recv, cols, col_base, 4, k, True, names)
+        parts.append(slab.export())
+    o = O.OracleArray.build(list(os_), names, k=k, rc=True, min_count=3, min_qual=20, qual_filter="strict")
+    ok, ov, oc = o.export()
+    assert [int(x) for p in parts for x in p[0]] == ok
+    assert np.array_equal(np.concatenate([p[1] for p in parts]), ov)
+    assert np.array_equal(np.concatenate([p[2] for p in parts]), oc)
