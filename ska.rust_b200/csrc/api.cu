@@ -26,6 +26,7 @@ void Context::ensure() {
     sm_count = p.multiProcessorCount;
     smem_optin = p.sharedMemPerBlockOptin;
     SKA_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+    SKA_CUDA(cudaStreamCreateWithFlags(&copy_stream, cudaStreamNonBlocking));
     // keep freed blocks in the pool: repeated builds should not pay cudaMalloc again
     cudaMemPool_t pool;
     SKA_CUDA(cudaDeviceGetDefaultMemPool(&pool, device));
@@ -96,8 +97,18 @@ static void check_k(uint32_t k) {
     if (k < 5 || k > 63 || (k % 2) == 0) throw Error("Invalid k-mer length");      // ska_dict.rs:342-344
 }
 
+// skagpu_build on FASTA input: the extraction kernel runs on the tiles of a chunk of samples while the next chunk is
+// still crossing PCIe (copies on their own stream, K1 on the library stream behind an event per chunk).  K1 is hidden
+// behind the copies, so it also counts the first partition histogram here (see build_from_batch for the trade-off).
+struct K1Overlap {
+    uint32_t k; bool rc; uint8_t min_qual;
+    uint64_t* rec; uint32_t* valid; unsigned long long* hist; int hist_shift, hist_bits;
+    uint64_t tiles_done = 0;
+};
+constexpr uint64_t OVERLAP_CHUNK_BYTES = 8ull << 20;
+
 // Host -> device staging of the parsed records of all samples.
-static std::unique_ptr<SeqBatch> upload(const ska_input_t* in, size_t n, double proportion_reads) {
+static std::unique_ptr<SeqBatch> upload(const ska_input_t* in, size_t n, double proportion_reads, K1Overlap* ov = nullptr) {
     Context& c = ctx();
     c.ensure();
     if (n == 0) throw Error("no input samples");
@@ -128,6 +139,53 @@ static std::unique_ptr<SeqBatch> upload(const ska_input_t* in, size_t n, double 
     if (proportion_reads > 0) step = (size_t)std::llround(1.0 / proportion_reads);      // ska_dict.rs:125-129
     if (step == 0) step = 1;
     std::vector<uint64_t> starts; starts.reserve(n_rec_total + 1);
+    if (ov && (b->has_qual || step != 1)) ov = nullptr;            // overlap is for plain FASTA batches
+    cudaEvent_t ev_prep = nullptr;
+    std::vector<cudaEvent_t> chunk_events;
+    if (ov) {
+        // everything K1 reads besides the bases goes first, on the library stream: record starts, sample offsets
+        for (size_t s = 0; s < n; s++) {
+            const uint64_t base = b->h_sample_off[s], r0 = in[s].rec_off[0];
+            for (uint64_t r = 0; r < in[s].n_rec; r++) starts.push_back(base + (in[s].rec_off[r] - r0));
+        }
+        starts.push_back(b->n_pos);
+        b->start_bits.alloc(padded / 32 + 1);
+        SKA_CUDA(cudaMemsetAsync(b->start_bits.p, 0, b->start_bits.bytes(), c.stream));
+        DevBuf<uint64_t> d_starts(starts.size());
+        SKA_CUDA(cudaMemcpyAsync(d_starts.p, starts.data(), starts.size() * 8, cudaMemcpyHostToDevice, c.stream));
+        SKA_LAUNCH(set_start_bits_kernel, (unsigned)((starts.size() + 255) / 256), 256, 0, d_starts.p, (uint64_t)starts.size(),
+                   b->start_bits.p);
+        b->sample_off.alloc(n + 1);
+        SKA_CUDA(cudaMemcpyAsync(b->sample_off.p, b->h_sample_off.data(), (n + 1) * 8, cudaMemcpyHostToDevice, c.stream));
+        SKA_CUDA(cudaEventCreateWithFlags(&ev_prep, cudaEventDisableTiming));
+        SKA_CUDA(cudaEventRecord(ev_prep, c.stream));
+        SKA_CUDA(cudaStreamWaitEvent(c.copy_stream, ev_prep, 0));   // the sequence buffer was allocated in library-stream order
+        uint64_t chunk_bytes = 0;
+        for (size_t s = 0; s < n; s++) {
+            const uint64_t base = b->h_sample_off[s], r0 = in[s].rec_off[0];
+            const uint64_t len = b->h_sample_off[s + 1] - base;
+            if (len) SKA_CUDA(cudaMemcpyAsync(b->seq.p + FRONT_PAD + base, in[s].seq + r0, len, cudaMemcpyHostToDevice, c.copy_stream));
+            chunk_bytes += len;
+            if (chunk_bytes >= OVERLAP_CHUNK_BYTES || s + 1 == n) {
+                cudaEvent_t ev;
+                SKA_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+                SKA_CUDA(cudaEventRecord(ev, c.copy_stream));
+                SKA_CUDA(cudaStreamWaitEvent(c.stream, ev, 0));
+                chunk_events.push_back(ev);
+                const uint64_t ready = (s + 1 == n) ? ~0ULL : k1_tiles_ready(b->h_sample_off[s + 1]);
+                if (ready > ov->tiles_done) {
+                    launch_k1(*b, ov->k, ov->rc, false, ov->min_qual, ov->rec, nullptr, ov->valid, 0, ov->hist, ov->hist_shift, ov->hist_bits,
+                              ov->tiles_done, ready);
+                    ov->tiles_done = ready;
+                }
+                chunk_bytes = 0;
+            }
+        }
+        SKA_CUDA(cudaStreamSynchronize(c.stream));                 // `starts` (pageable) must outlive its copy; K1 is done
+        cudaEventDestroy(ev_prep);
+        for (cudaEvent_t e : chunk_events) cudaEventDestroy(e);
+        return b;
+    }
     for (size_t s = 0; s < n; s++) {
         const uint64_t base = b->h_sample_off[s], r0 = in[s].rec_off[0];
         const uint64_t len = b->h_sample_off[s + 1] - base;
@@ -164,6 +222,18 @@ static std::unique_ptr<SeqBatch> upload(const ska_input_t* in, size_t n, double 
     SKA_CUDA(cudaMemcpyAsync(b->sample_off.p, b->h_sample_off.data(), (n + 1) * 8, cudaMemcpyHostToDevice, c.stream));
     SKA_CUDA(cudaStreamSynchronize(c.stream));                   // `starts` (pageable) must outlive the copy
     return b;
+}
+
+// records (and K1's histogram) already extracted while the batch was uploaded: partition + merge
+static std::unique_ptr<Array> build_from_extracted(const SeqBatch& b, uint32_t k, bool rc, const PartPlan& pl, const K1Overlap& ov) {
+    Context& c = ctx();
+    std::vector<uint32_t> h_valid(b.n_samples);
+    SKA_CUDA(cudaMemcpyAsync(h_valid.data(), ov.valid, b.n_samples * 4, cudaMemcpyDeviceToHost, c.stream));
+    std::unique_ptr<Array> a(new Array());
+    build_array_from_records(ov.rec, b.n_pos, b.sample_off.p, (uint32_t)b.n_samples, 0, b.n_samples, k, rc, *a, pl.P, ov.hist);   // synchronises
+    for (size_t s = 0; s < b.n_samples; s++)
+        if (h_valid[s] == 0) throw Error("sample " + std::to_string(s) + " has no valid sequence");   // ska_dict.rs:374-376
+    return a;
 }
 
 static std::unique_ptr<Array> build_from_batch(const SeqBatch& b, uint32_t k, bool rc, uint16_t min_count, uint8_t min_qual,
@@ -267,10 +337,36 @@ int skagpu_build(const ska_input_t* inputs, size_t n_samples, uint32_t k, int rc
     check_k(k);
     ctx().ensure();
     timer().clear();
-    timer().begin("h2d");
-    std::unique_ptr<SeqBatch> b = upload(inputs, n_samples, proportion_reads);
-    timer().end();
-    std::unique_ptr<Array> a = build_from_batch(*b, k, rc != 0, min_count, min_qual, qual_filter);
+    bool fasta = n_samples > 0 && k <= 31 && !(proportion_reads > 0);
+    uint64_t n_pos = 0;
+    for (size_t s = 0; fasta && s < n_samples; s++) {
+        if (inputs[s].qual || !inputs[s].rec_off || !inputs[s].n_rec) fasta = false;
+        else n_pos += inputs[s].rec_off[inputs[s].n_rec] - inputs[s].rec_off[0];
+    }
+    if (const char* e = getenv("SKA_H2D_OVERLAP")) if (atoi(e) == 0) fasta = false;     // tests / measurements: plain upload, then K1
+    std::unique_ptr<Array> a;
+    if (fasta && n_pos > 0) {
+        // FASTA: K1 runs chunk by chunk behind the copies (stage "h2d+k1")
+        arena().reset();
+        const PartPlan pl = make_part_plan(k, merge_prefix_bits(n_pos, k, n_samples), n_samples);
+        K1Overlap ov;
+        ov.k = k; ov.rc = rc != 0; ov.min_qual = min_qual;
+        ov.rec = arena().take_n<uint64_t>(n_pos);
+        ov.valid = arena().take_n<uint32_t>(n_samples);
+        ov.hist = arena().take_n<unsigned long long>((size_t)K1_HIST_COPIES << pl.P1);
+        ov.hist_shift = 4 + pl.key_bits - pl.P1; ov.hist_bits = pl.P1;
+        SKA_CUDA(cudaMemsetAsync(ov.valid, 0, n_samples * 4, ctx().stream));
+        SKA_CUDA(cudaMemsetAsync(ov.hist, 0, ((size_t)K1_HIST_COPIES << pl.P1) * 8, ctx().stream));
+        timer().begin("h2d+k1");
+        std::unique_ptr<SeqBatch> b = upload(inputs, n_samples, proportion_reads, &ov);
+        timer().end();
+        a = build_from_extracted(*b, k, rc != 0, pl, ov);
+    } else {
+        timer().begin("h2d");
+        std::unique_ptr<SeqBatch> b = upload(inputs, n_samples, proportion_reads);
+        timer().end();
+        a = build_from_batch(*b, k, rc != 0, min_count, min_qual, qual_filter);
+    }
     std::unique_ptr<ska_array> h(new ska_array());
     h->a = std::move(*a);
     *out = h.release();

@@ -29,6 +29,7 @@ struct Context {
     int device = 0;
     bool init = false;
     cudaStream_t stream = nullptr;
+    cudaStream_t copy_stream = nullptr;   // host -> device copies that overlap the extraction kernel (skagpu_build)
     int sm_count = 148;
     size_t smem_optin = 0;
     uint64_t launches = 0;
@@ -135,7 +136,8 @@ constexpr int K1_HIST_COPIES = 32;
 constexpr int K1_HIST_MAX_BITS = 11;
 void launch_k1(const SeqBatch& b, uint32_t k, bool rc, bool strict_qual, uint8_t min_qual, uint64_t* rec_out,
                uint16_t* sid_out, uint32_t* sample_valid, uint32_t sid_base = 0, unsigned long long* hist = nullptr,
-               int hist_shift = 0, int hist_bits = 0);
+               int hist_shift = 0, int hist_bits = 0, uint64_t tile_begin = 0, uint64_t tile_end = ~0ULL /* tiles of 4096 positions */);
+uint64_t k1_tiles_ready(uint64_t positions_uploaded);
 size_t padded_positions(uint64_t n_pos);
 // partition.cu: how records are grouped and packed.  P = P1 + P2 prefix bits of the key select the bucket;
 // inside a bucket a record is  key_low << (sb+2) | sample_id << 2 | middle_code  (key_low = key without its top P1 bits)

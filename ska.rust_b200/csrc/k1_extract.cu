@@ -25,6 +25,10 @@
 
 namespace ska {
 
+uint64_t k1_tiles_ready(uint64_t positions_uploaded) {      // tiles whose staged bytes (tile + tail halo) lie below that position
+    return positions_uploaded < (uint64_t)K1_T + K1_TAIL ? 0 : (positions_uploaded - K1_TAIL) / K1_T;
+}
+
 size_t padded_positions(uint64_t n_pos) { return FRONT_PAD + ((n_pos + K1_T - 1) / K1_T) * K1_T + 256; }
 
 // KT > 0: k fixed at compile time (all shifts/masks become immediates); KT == 0: runtime k.
@@ -37,7 +41,7 @@ k1_extract_kernel(const uint8_t* __restrict__ seq, const uint8_t* __restrict__ q
                   const uint32_t* __restrict__ start_bits, const uint64_t* __restrict__ sample_off,
                   uint32_t n_samples, uint64_t n_pos, int k_rt, int rc, uint32_t min_qual,
                   uint64_t* __restrict__ rec_out, uint16_t* __restrict__ sid_out, uint32_t* __restrict__ sample_valid,
-                  uint32_t sid_base, unsigned long long* __restrict__ hist, int hist_shift, int hist_bits) {
+                  uint32_t sid_base, unsigned long long* __restrict__ hist, int hist_shift, int hist_bits, uint32_t tile0) {
     __shared__ uint32_t s_hist[HIST ? (1 << K1_HIST_MAX_BITS) : 1];
     __shared__ __align__(128) uint8_t s_ascii[K1_BYTES];
     __shared__ __align__(128) uint8_t s_qual[HAS_QUAL ? K1_BYTES : 16];
@@ -52,7 +56,7 @@ k1_extract_kernel(const uint8_t* __restrict__ seq, const uint8_t* __restrict__ q
 
     const int k = KT ? KT : k_rt;
     const int tid = threadIdx.x;
-    const uint64_t t0 = (uint64_t)blockIdx.x * K1_T;        // first window-start position of this tile
+    const uint64_t t0 = ((uint64_t)blockIdx.x + tile0) * K1_T;   // first window-start position of this tile
     // staged region covers positions [t0 - K1_LEAD, t0 + K1_T + K1_TAIL); position p lives at seq[FRONT_PAD + p]
     const uint8_t* gsrc = seq + FRONT_PAD + t0 - K1_LEAD;
 
@@ -199,30 +203,36 @@ k1_extract_kernel(const uint8_t* __restrict__ seq, const uint8_t* __restrict__ q
 
 template <int KT>
 static void launch_k1_kt(const SeqBatch& b, uint32_t k, bool rc, bool strict_qual, uint8_t min_qual, uint64_t* rec_out,
-                         uint16_t* sid_out, uint32_t* sample_valid, uint32_t sid_base, unsigned long long* hist, int hist_shift, int hist_bits) {
-    unsigned grid = (unsigned)((b.n_pos + K1_T - 1) / K1_T);
+                         uint16_t* sid_out, uint32_t* sample_valid, uint32_t sid_base, unsigned long long* hist, int hist_shift, int hist_bits,
+                         uint64_t tile_begin, uint64_t tile_end) {
+    const uint64_t n_tiles = (b.n_pos + K1_T - 1) / K1_T;
+    tile_end = std::min(tile_end, n_tiles);
+    if (tile_begin >= tile_end) return;
+    const unsigned grid = (unsigned)(tile_end - tile_begin);
+    const uint32_t tile0 = (uint32_t)tile_begin;
     unsigned long long* nohist = nullptr;
     if (b.has_qual && strict_qual) {
         SKA_LAUNCH((k1_extract_kernel<KT, true, false>), grid, K1_THREADS, 0, b.seq.p, b.qual.p, b.start_bits.p, b.sample_off.p,
-                   (uint32_t)b.n_samples, b.n_pos, (int)k, rc ? 1 : 0, (uint32_t)min_qual, rec_out, sid_out, sample_valid, sid_base, nohist, 0, 0);
+                   (uint32_t)b.n_samples, b.n_pos, (int)k, rc ? 1 : 0, (uint32_t)min_qual, rec_out, sid_out, sample_valid, sid_base, nohist, 0, 0, tile0);
     } else if (hist) {
         SKA_LAUNCH((k1_extract_kernel<KT, false, true>), grid, K1_THREADS, 0, b.seq.p, (const uint8_t*)nullptr, b.start_bits.p,
                    b.sample_off.p, (uint32_t)b.n_samples, b.n_pos, (int)k, rc ? 1 : 0, (uint32_t)min_qual, rec_out, sid_out,
-                   sample_valid, sid_base, hist, hist_shift, hist_bits);
+                   sample_valid, sid_base, hist, hist_shift, hist_bits, tile0);
     } else {
         SKA_LAUNCH((k1_extract_kernel<KT, false, false>), grid, K1_THREADS, 0, b.seq.p, (const uint8_t*)nullptr, b.start_bits.p,
                    b.sample_off.p, (uint32_t)b.n_samples, b.n_pos, (int)k, rc ? 1 : 0, (uint32_t)min_qual, rec_out, sid_out,
-                   sample_valid, sid_base, nohist, 0, 0);
+                   sample_valid, sid_base, nohist, 0, 0, tile0);
     }
 }
 
 void launch_k1(const SeqBatch& b, uint32_t k, bool rc, bool strict_qual, uint8_t min_qual, uint64_t* rec_out,
-               uint16_t* sid_out, uint32_t* sample_valid, uint32_t sid_base, unsigned long long* hist, int hist_shift, int hist_bits) {
+               uint16_t* sid_out, uint32_t* sample_valid, uint32_t sid_base, unsigned long long* hist, int hist_shift, int hist_bits,
+               uint64_t tile_begin, uint64_t tile_end) {
     if (b.n_pos == 0) return;
     if (hist && (hist_bits < 0 || hist_bits > K1_HIST_MAX_BITS)) throw Error("internal: K1 histogram wider than its shared-memory table");
     // the default k of `ska build` (cli.rs:9) gets a compile-time specialisation
-    if (k == 31) launch_k1_kt<31>(b, k, rc, strict_qual, min_qual, rec_out, sid_out, sample_valid, sid_base, hist, hist_shift, hist_bits);
-    else launch_k1_kt<0>(b, k, rc, strict_qual, min_qual, rec_out, sid_out, sample_valid, sid_base, hist, hist_shift, hist_bits);
+    if (k == 31) launch_k1_kt<31>(b, k, rc, strict_qual, min_qual, rec_out, sid_out, sample_valid, sid_base, hist, hist_shift, hist_bits, tile_begin, tile_end);
+    else launch_k1_kt<0>(b, k, rc, strict_qual, min_qual, rec_out, sid_out, sample_valid, sid_base, hist, hist_shift, hist_bits, tile_begin, tile_end);
 }
 
 }  // namespace ska

@@ -335,6 +335,35 @@ def test_build_k1_histogram_fusion(k, rc, monkeypatch):
     assert_same_array(a, ora_from_gpu_samples(samples, names, k, rc))
 
 
+def test_build_overlapped_upload_matches_plain(monkeypatch):
+    """skagpu_build on FASTA input runs K1 chunk by chunk behind the host->device copies (8 MB chunks; tiles that
+    straddle a chunk boundary wait for the next chunk); SKA_H2D_OVERLAP=0 uploads first and extracts afterwards.
+    44 samples of uneven size (26 MB in all) so that several chunks and many sample boundaries are involved."""
+    from ska_rust_b200 import synth
+    rng = np.random.default_rng(12)
+    lengths = [int(x) for x in rng.integers(1_000, 1_200_000, size=44)]
+    anc = synth.star_genomes(1, 1_200_000, seed=0x5CA20055)[0]
+    samples = []
+    for i, ln in enumerate(lengths):
+        g = anc[:ln].copy()
+        pos = rng.integers(0, ln, size=max(1, ln // 800))
+        g[pos] = rng.choice(np.frombuffer(b"ACGTN", dtype=np.uint8), size=len(pos))
+        cut = ln // 3
+        samples.append(S.Sample.from_records([g[:cut].tobytes(), g[cut:].tobytes()]))
+    names = [f"s{i}" for i in range(len(samples))]
+    monkeypatch.setenv("SKA_H2D_OVERLAP", "1")
+    a = S.build_from_samples(samples, names, 31, True)
+    assert any(st == "h2d+k1" for st, _, _ in S.api.last_timings())
+    monkeypatch.setenv("SKA_H2D_OVERLAP", "0")
+    b = S.build_from_samples(samples, names, 31, True)
+    assert any(st == "h2d" for st, _, _ in S.api.last_timings())
+    ka, va, ca = a.export()
+    kb, vb, cb = b.export()
+    assert np.array_equal(ka, kb) and np.array_equal(va, vb) and np.array_equal(ca, cb)
+    sub = S.build_from_samples(samples[:5], names[:5], 31, True)
+    assert_same_array(sub, ora_from_gpu_samples(samples[:5], names[:5], 31, True))
+
+
 def test_build_fused_many_buckets_matches_two_pass(monkeypatch):
     """24 x 700 kbp: ~1000 buckets, so the fused merge's look-back chain spans many waves of CTAs; its array must equal
     the two-pass array bit for bit (and the oracle's on a 3-sample subset)"""
