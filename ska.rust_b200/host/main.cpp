@@ -130,6 +130,34 @@ int main(int argc, char** argv) {
             Args a = parse(argc, argv, 2, {"--threads"}, {});
             if (a.pos.size() != 2) usage_error("usage: ska recode <IN.skf> <OUT.skf>");
             skf::save(skf::load(a.pos[0]), a.pos[1], (int)parse_threads(a.get("--threads", "1")));
+        } else if (cmd == "codec-selftest") {
+            // host-only helper (no device): encode + decode a synthetic array of ROWS x SAMPLES and report the codec's speed
+            Args a = parse(argc, argv, 2, {"--threads"}, {});
+            if (a.pos.size() != 2) usage_error("usage: ska codec-selftest <ROWS> <SAMPLES>");
+            const size_t rows = (size_t)std::stoull(a.pos[0]), n = (size_t)std::stoull(a.pos[1]);
+            const int threads = (int)parse_threads(a.get("--threads", "1"));
+            skf::Array arr; arr.k = 31; arr.rc = true; arr.n_rows = rows; arr.n_samples = n;
+            for (size_t i = 0; i < n; i++) arr.names.push_back("s" + std::to_string(i));
+            arr.keys.resize(rows); arr.counts.resize(rows); arr.variants.resize(rows * n);
+            uint64_t x = 0x9E3779B97F4A7C15ull;
+            auto next = [&] { x ^= x << 13; x ^= x >> 7; x ^= x << 17; return x; };
+            const char L[4] = {'A', 'C', 'G', 'T'};
+            for (size_t r = 0; r < rows; r++) {
+                arr.keys[r] = next() >> 5;
+                const bool single = next() % 5 != 0; const char c = L[next() & 3];
+                for (size_t s = 0; s < n; s++) arr.variants[r * n + s] = single ? '-' : c;
+                if (single) arr.variants[r * n + next() % n] = c;
+                arr.counts[r] = single ? 1 : n;
+            }
+            auto t0 = std::chrono::steady_clock::now();
+            std::vector<uint8_t> enc = skf::encode(arr, threads);
+            auto t1 = std::chrono::steady_clock::now();
+            skf::Array back = skf::decode(enc.data(), enc.size(), threads);
+            auto t2 = std::chrono::steady_clock::now();
+            if (back.variants != arr.variants || back.keys != arr.keys || back.counts != arr.counts || back.names != arr.names)
+                throw std::runtime_error("codec self-test: round trip differs");
+            printf("rows %zu samples %zu file_bytes %zu encode_s %.3f decode_s %.3f\n", rows, n, enc.size(),
+                   std::chrono::duration<double>(t1 - t0).count(), std::chrono::duration<double>(t2 - t1).count());
         } else {
             usage_error("unrecognized subcommand '" + cmd + "' (this engine provides build, align, distance, nk)");
         }

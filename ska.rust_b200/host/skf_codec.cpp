@@ -13,6 +13,8 @@
 #include <cstdio>
 #include <cstring>
 #include <stdexcept>
+#include <memory>
+#include <mutex>
 #include <thread>
 
 namespace skf {
@@ -30,17 +32,24 @@ static uint32_t masked_crc(const uint8_t* p, size_t n) {
 }
 
 // ------------------------------------------------------------------------------------------ Snappy raw
-static void snappy_decompress(const uint8_t* in, size_t n, std::vector<uint8_t>& out) {
+// uncompressed length announced by a raw Snappy block (varint header); *hdr = bytes of the header
+static uint64_t snappy_ulen(const uint8_t* in, size_t n, size_t* hdr) {
     size_t pos = 0; uint64_t ulen = 0; int shift = 0;
     while (true) {
-        if (pos >= n) throw std::runtime_error("skf: truncated snappy block");
+        if (pos >= n || shift > 35) throw std::runtime_error("skf: truncated snappy block");
         uint8_t b = in[pos++];
         ulen |= (uint64_t)(b & 0x7F) << shift;
         if (!(b & 0x80)) break;
         shift += 7;
     }
-    const size_t start = out.size();
-    out.reserve(start + ulen);
+    *hdr = pos;
+    return ulen;
+}
+// decompresses one raw Snappy block into dst[0, ulen) (the caller sized it from snappy_ulen)
+static void snappy_decompress(const uint8_t* in, size_t n, uint8_t* dst, size_t ulen) {
+    size_t pos = 0;
+    if (snappy_ulen(in, n, &pos) != ulen) throw std::runtime_error("skf: snappy length mismatch");
+    size_t o = 0;
     while (pos < n) {
         uint8_t tag = in[pos++];
         uint32_t t = tag & 3;
@@ -54,21 +63,25 @@ static void snappy_decompress(const uint8_t* in, size_t n, std::vector<uint8_t>&
             }
             len += 1;
             if (pos + len > n) throw std::runtime_error("skf: truncated literal");
-            out.insert(out.end(), in + pos, in + pos + len);
-            pos += len;
+            if (o + len > ulen) throw std::runtime_error("skf: snappy length mismatch");
+            memcpy(dst + o, in + pos, len);
+            o += len; pos += len;
         } else {
             size_t len, off;
             if (t == 1) { if (pos >= n) throw std::runtime_error("skf: truncated copy"); len = 4 + ((tag >> 2) & 7); off = ((size_t)(tag >> 5) << 8) | in[pos]; pos += 1; }
             else if (t == 2) { if (pos + 2 > n) throw std::runtime_error("skf: truncated copy"); len = (tag >> 2) + 1; off = in[pos] | ((size_t)in[pos + 1] << 8); pos += 2; }
             else { if (pos + 4 > n) throw std::runtime_error("skf: truncated copy"); len = (tag >> 2) + 1; off = in[pos] | ((size_t)in[pos + 1] << 8) | ((size_t)in[pos + 2] << 16) | ((size_t)in[pos + 3] << 24); pos += 4; }
-            if (off == 0 || off > out.size() - start) throw std::runtime_error("skf: bad snappy copy offset");
-            size_t from = out.size() - off;
-            for (size_t i = 0; i < len; i++) out.push_back(out[from + i]);   // may overlap its own output
+            if (off == 0 || off > o) throw std::runtime_error("skf: bad snappy copy offset");
+            if (o + len > ulen) throw std::runtime_error("skf: snappy length mismatch");
+            if (off >= len) memcpy(dst + o, dst + o - off, len);
+            else for (size_t i = 0; i < len; i++) dst[o + i] = dst[o - off + i];   // overlaps its own output (run-length)
+            o += len;
         }
     }
-    if (out.size() - start != ulen) throw std::runtime_error("skf: snappy length mismatch");
+    if (o != ulen) throw std::runtime_error("skf: snappy length mismatch");
 }
 
+// ------------------------------------------------------------------------------------------ Snappy raw (compressor)
 static inline void emit_literal(std::vector<uint8_t>& out, const uint8_t* p, size_t len) {
     if (!len) return;
     size_t n = len - 1;
@@ -102,7 +115,14 @@ static void snappy_compress(const uint8_t* in, size_t n, std::vector<uint8_t>& o
         uint32_t cw; memcpy(&cw, in + cand, 4);
         if (cand < i && cw == w) {
             size_t len = 4;
-            while (i + len < n && in[cand + len] == in[i + len]) len++;
+            bool open_end = true;                               // extend the match 8 bytes at a time (runs of `18 2D` are long)
+            while (i + len + 8 <= n) {
+                uint64_t x, y; memcpy(&x, in + cand + len, 8); memcpy(&y, in + i + len, 8);
+                const uint64_t d = x ^ y;
+                if (d) { len += (size_t)(__builtin_ctzll(d) >> 3); open_end = false; break; }
+                len += 8;
+            }
+            if (open_end) while (i + len < n && in[cand + len] == in[i + len]) len++;
             emit_literal(out, in + lit, i - lit);
             emit_copy(out, i - cand, len);
             i += len; lit = i;
@@ -114,9 +134,14 @@ static void snappy_compress(const uint8_t* in, size_t n, std::vector<uint8_t>& o
 }
 
 // ------------------------------------------------------------------------------------------ framing
-static std::vector<uint8_t> frame_decode(const uint8_t* d, size_t n) {
-    std::vector<uint8_t> out;
-    size_t pos = 0; bool seen = false;
+// Chunks are independent (<= 64 KiB of payload each): a first walk over the headers sizes the payload once, then the
+// chunks are decompressed and checksummed in parallel straight into place.  (Appending chunk by chunk with an exact
+// reserve() re-copied the whole payload for every chunk: minutes for a 1 GB file.)
+struct Payload { std::unique_ptr<uint8_t[]> p; size_t n = 0; };   // uninitialised storage: the pages are first touched by the worker threads
+static Payload frame_decode(const uint8_t* d, size_t n, int threads) {
+    struct Chunk { uint8_t type; const uint8_t* body; size_t len, ulen, at; };
+    std::vector<Chunk> chunks;
+    size_t pos = 0, total = 0; bool seen = false;
     while (pos < n) {
         if (pos + 4 > n) throw std::runtime_error("skf: truncated chunk header");
         uint8_t type = d[pos];
@@ -131,11 +156,11 @@ static std::vector<uint8_t> frame_decode(const uint8_t* d, size_t n) {
         } else if (type == 0x00 || type == 0x01) {
             if (!seen) throw std::runtime_error("skf: missing stream identifier");
             if (len < 4) throw std::runtime_error("skf: short data chunk");
-            uint32_t crc; memcpy(&crc, body, 4);
-            size_t before = out.size();
-            if (type == 0x00) snappy_decompress(body + 4, len - 4, out);
-            else out.insert(out.end(), body + 4, body + len);
-            if (masked_crc(out.data() + before, out.size() - before) != crc) throw std::runtime_error("skf: checksum mismatch");
+            size_t hdr = 0;
+            const size_t ulen = type == 0x00 ? (size_t)snappy_ulen(body + 4, len - 4, &hdr) : len - 4;
+            if (ulen > (1u << 24)) throw std::runtime_error("skf: oversized chunk");
+            chunks.push_back({type, body, len, ulen, total});
+            total += ulen;
         } else if (type == 0xFE || (type >= 0x80 && type <= 0xFD)) {
             continue;
         } else {
@@ -143,19 +168,47 @@ static std::vector<uint8_t> frame_decode(const uint8_t* d, size_t n) {
         }
     }
     if (!seen) throw std::runtime_error("skf: not a snappy frame stream");
+    Payload out;
+    out.p.reset(new uint8_t[total ? total : 1]);
+    out.n = total;
+    std::atomic<size_t> next{0};
+    std::atomic<bool> failed{false};
+    std::string error;
+    std::mutex mu;
+    auto work = [&] {
+        try {
+            for (size_t c; (c = next.fetch_add(1)) < chunks.size() && !failed.load();) {
+                const Chunk& ch = chunks[c];
+                uint32_t crc; memcpy(&crc, ch.body, 4);
+                uint8_t* dst = out.p.get() + ch.at;
+                if (ch.type == 0x00) snappy_decompress(ch.body + 4, ch.len - 4, dst, ch.ulen);
+                else memcpy(dst, ch.body + 4, ch.ulen);
+                if (masked_crc(dst, ch.ulen) != crc) throw std::runtime_error("skf: checksum mismatch");
+            }
+        } catch (std::exception& e) {
+            std::lock_guard<std::mutex> g(mu);
+            if (!failed.exchange(true)) error = e.what();
+        }
+    };
+    threads = std::max(1, std::min<int>(threads, (int)std::max<size_t>(1, chunks.size() / 16)));
+    std::vector<std::thread> th;
+    for (int t = 1; t < threads; t++) th.emplace_back(work);
+    work();
+    for (auto& t : th) t.join();
+    if (failed.load()) throw std::runtime_error(error);
     return out;
 }
 
-static std::vector<uint8_t> frame_encode(const std::vector<uint8_t>& payload, int threads) {
+static std::vector<uint8_t> frame_encode(const uint8_t* payload, size_t payload_size, int threads) {
     const size_t CH = 65536;
-    const size_t n_chunks = (payload.size() + CH - 1) / CH;
+    const size_t n_chunks = (payload_size + CH - 1) / CH;
     std::vector<std::vector<uint8_t>> comp(n_chunks);
     std::atomic<size_t> next{0};
     auto work = [&] {
         std::vector<uint8_t> buf;
         for (size_t c; (c = next.fetch_add(1)) < n_chunks;) {
-            const uint8_t* p = payload.data() + c * CH;
-            size_t len = std::min(CH, payload.size() - c * CH);
+            const uint8_t* p = payload + c * CH;
+            size_t len = std::min(CH, payload_size - c * CH);
             snappy_compress(p, len, buf);
             bool raw = buf.size() >= len - len / 8;          // snap's rule of thumb: keep poorly compressible chunks raw
             size_t body = 4 + (raw ? len : buf.size());
@@ -215,9 +268,10 @@ struct Reader {
     }
 };
 
-Array decode(const uint8_t* data, size_t len) {
-    std::vector<uint8_t> payload = frame_decode(data, len);
-    Reader r{payload.data(), payload.size()};
+Array decode(const uint8_t* data, size_t len, int threads) {
+    if (threads <= 0) threads = (int)std::max(1u, std::thread::hardware_concurrency());
+    Payload payload = frame_decode(data, len, threads);
+    Reader r{payload.p.get(), payload.n};
     Array a;
     std::vector<uint64_t> lo, hi;
     bool wide = false;
@@ -238,7 +292,27 @@ Array decode(const uint8_t* data, size_t len) {
                 else if (vk == "dim") { if (r.array() != 2) throw std::runtime_error("skf: bad dim"); a.n_rows = r.uint_(); a.n_samples = r.uint_(); }
                 else if (vk == "data") {
                     uint64_t n = r.array(); a.variants.resize(n);
-                    for (uint64_t i = 0; i < n; i++) a.variants[i] = (uint8_t)r.uint_();
+                    // every middle-base byte written by ska is '-' or a letter (>= 24): exactly `18 xx` each.  Check and
+                    // take that form with all threads; anything else goes through the general integer reader.
+                    bool fixed = r.pos + 2 * n <= r.n;
+                    if (fixed && n) {
+                        const uint8_t* src = r.p + r.pos;
+                        const int nt = (int)std::max<uint64_t>(1, std::min<uint64_t>((uint64_t)threads, n >> 20));
+                        std::vector<char> ok(nt, 1);
+                        auto part = [&](int t) {
+                            const uint64_t b0 = n * t / nt, b1 = n * (t + 1) / nt;
+                            uint8_t bad = 0;
+                            for (uint64_t i = b0; i < b1; i++) { bad |= (uint8_t)(src[2 * i] ^ 0x18); a.variants[i] = src[2 * i + 1]; }
+                            ok[t] = bad == 0;
+                        };
+                        std::vector<std::thread> th;
+                        for (int t = 1; t < nt; t++) th.emplace_back(part, t);
+                        part(0);
+                        for (auto& t : th) t.join();
+                        for (char c : ok) fixed = fixed && c;
+                    }
+                    if (fixed) r.pos += 2 * n;
+                    else for (uint64_t i = 0; i < n; i++) a.variants[i] = (uint8_t)r.uint_();
                 } else throw std::runtime_error("skf: unexpected key in variants");
             }
         } else if (key == "variant_count") { uint64_t n = r.array(); a.counts.resize(n); for (uint64_t i = 0; i < n; i++) a.counts[i] = r.uint_(); }
@@ -263,7 +337,7 @@ Array load(const std::string& path) {
     size_t n;
     while ((n = fread(tmp, 1, sizeof tmp, f)) > 0) buf.insert(buf.end(), tmp, tmp + n);
     fclose(f);
-    return decode(buf.data(), buf.size());
+    return decode(buf.data(), buf.size(), 0);
 }
 
 static inline void put_head(std::vector<uint8_t>& o, int major, uint64_t v) {
@@ -275,8 +349,11 @@ static inline void put_head(std::vector<uint8_t>& o, int major, uint64_t v) {
 static inline void put_text(std::vector<uint8_t>& o, const std::string& s) { put_head(o, 3, s.size()); o.insert(o.end(), s.begin(), s.end()); }
 
 std::vector<uint8_t> encode(const Array& a, int threads) {
+    threads = std::max(1, threads);
+    // head: everything before the variant bytes; tail: everything after.  The data section between them is `18 xx`
+    // per byte (every middle-base byte is '-' (45) or a letter), written by all threads into uninitialised storage.
     std::vector<uint8_t> o;
-    o.reserve(64 + a.keys.size() * 9 + a.variants.size() * 2 + a.counts.size() * 3);
+    o.reserve(64 + a.keys.size() * 9);
     o.push_back(0xA8);
     put_text(o, "k"); put_head(o, 0, a.k);
     put_text(o, "rc"); o.push_back(a.rc ? 0xF5 : 0xF4);
@@ -295,17 +372,36 @@ std::vector<uint8_t> encode(const Array& a, int threads) {
     put_text(o, "v"); o.push_back(0x01);
     put_text(o, "dim"); o.push_back(0x82); put_head(o, 0, a.n_rows); put_head(o, 0, a.n_samples);
     put_text(o, "data"); put_head(o, 4, a.variants.size());
-    {   // every middle-base byte is '-' (45) or a letter: exactly two bytes `18 xx` each
-        size_t at = o.size();
-        o.resize(at + 2 * a.variants.size());
-        uint8_t* w = o.data() + at; size_t extra = 0;
-        for (uint8_t b : a.variants) { if (b < 24) { extra++; break; } *w++ = 0x18; *w++ = b; }
-        if (extra) { o.resize(at); for (uint8_t b : a.variants) put_head(o, 0, b); }
+    std::vector<uint8_t> tail;
+    tail.reserve(64 + a.counts.size() * 3);
+    put_text(tail, "variant_count"); put_head(tail, 4, a.counts.size()); for (uint64_t c : a.counts) put_head(tail, 0, c);
+    put_text(tail, "ska_version"); put_text(tail, a.ska_version);
+    put_text(tail, "k_bits"); put_head(tail, 0, a.key_bits);
+
+    const size_t nv = a.variants.size();
+    const uint8_t* v = a.variants.data();
+    bool small = false;                                      // a byte below 24 would be a one-byte CBOR integer
+    for (size_t i = 0; i < nv && !small; i += 4096) { uint8_t m = 0xFF; for (size_t j = i; j < std::min(nv, i + 4096); j++) m = std::min(m, v[j]); small = m < 24; }
+    if (small) {                                             // not produced by ska; general integer writer
+        for (size_t i = 0; i < nv; i++) put_head(o, 0, v[i]);
+        o.insert(o.end(), tail.begin(), tail.end());
+        return frame_encode(o.data(), o.size(), threads);
     }
-    put_text(o, "variant_count"); put_head(o, 4, a.counts.size()); for (uint64_t c : a.counts) put_head(o, 0, c);
-    put_text(o, "ska_version"); put_text(o, a.ska_version);
-    put_text(o, "k_bits"); put_head(o, 0, a.key_bits);
-    return frame_encode(o, threads);
+    const size_t total = o.size() + 2 * nv + tail.size();
+    std::unique_ptr<uint8_t[]> buf(new uint8_t[total ? total : 1]);
+    memcpy(buf.get(), o.data(), o.size());
+    uint8_t* w = buf.get() + o.size();
+    const int nt = (int)std::max<size_t>(1, std::min<size_t>((size_t)threads, nv >> 20));
+    auto part = [&](int t) {
+        const size_t b0 = nv * t / nt, b1 = nv * (t + 1) / nt;
+        for (size_t i = b0; i < b1; i++) { w[2 * i] = 0x18; w[2 * i + 1] = v[i]; }
+    };
+    std::vector<std::thread> th;
+    for (int t = 1; t < nt; t++) th.emplace_back(part, t);
+    part(0);
+    for (auto& t : th) t.join();
+    memcpy(w + 2 * nv, tail.data(), tail.size());
+    return frame_encode(buf.get(), total, threads);
 }
 
 void save(const Array& a, const std::string& path, int threads) {

@@ -25,7 +25,7 @@ struct Array {                       // host image of MergeSkaArray<IntT>
 
 // Throws std::runtime_error on malformed input (the reference returns Err -> main panics, lib.rs:660).
 Array load(const std::string& path);
-Array decode(const uint8_t* data, size_t len);
+Array decode(const uint8_t* data, size_t len, int threads = 0 /* 0: all hardware threads */);
 // Writes a file the reference loads: CBOR identical in structure to ciborium's output, Snappy frames
 // with compressed (type 0x00) chunks of <= 65536 bytes and masked CRC-32C.  `threads` compress chunks in parallel.
 void save(const Array& a, const std::string& path, int threads = 1);

@@ -50,6 +50,15 @@ def test_cpp_codec_large_random_roundtrip(tmp_path):
     assert os.path.getsize(out) < os.path.getsize(src) // 2       # the C++ writer really compresses
 
 
+def test_cpp_codec_scales_linearly_in_chunks():
+    """64 MB of middle bases = ~2000 Snappy chunks: the decoder sizes its payload once (an earlier version re-copied
+    the payload for every chunk and needed minutes for this)"""
+    p = run(["codec-selftest", "500000", "128", "--threads", "4"])
+    fields = p.stdout.decode().split()
+    enc_s, dec_s = float(fields[fields.index("encode_s") + 1]), float(fields[fields.index("decode_s") + 1])
+    assert dec_s < 20 and enc_s < 20, p.stdout
+
+
 def test_cli_errors_without_touching_the_device(tmp_path):
     assert run(["build", "-k", "30", "-o", "x", "a.fa"], check=False).returncode == 2      # clap validator (cli.rs:38-47)
     assert run(["build", "-k", "65", "-o", "x", "a.fa"], check=False).returncode == 2
