@@ -144,6 +144,39 @@ def run_reference(args, rank, world):
     print(json.dumps(line), flush=True)
 
 
+def bind_to_gpu_numa_node(local_rank):
+    """Run this rank (and first-touch its pinned buffers) on the CPUs next to its GPU: with several ranks per host the
+    host<->device copies of ranks bound to the far socket otherwise cross the inter-socket link.  Best effort."""
+    if os.environ.get("BENCH_NO_AFFINITY"):
+        return None
+    try:
+        import torch
+        prop = torch.cuda.get_device_properties(local_rank)
+        if all(hasattr(prop, a) for a in ("pci_domain_id", "pci_bus_id", "pci_device_id")):
+            bdf = f"{int(prop.pci_domain_id):04x}:{int(prop.pci_bus_id):02x}:{int(prop.pci_device_id):02x}.0"
+        else:
+            bdf = subprocess.run(["nvidia-smi", "--query-gpu=pci.bus_id", "--format=csv,noheader", "-i", str(local_rank)],
+                                 capture_output=True, text=True, timeout=10).stdout.strip().lower()
+            if bdf.count(":") == 2 and len(bdf.split(":")[0]) == 8:
+                bdf = bdf[4:]                               # nvidia-smi prints an 8-digit domain, sysfs uses 4
+        with open(f"/sys/bus/pci/devices/{bdf}/local_cpulist") as fh:
+            spec = fh.read().strip()
+        cpus = set()
+        for part in spec.split(","):
+            if "-" in part:
+                a, b = part.split("-")
+                cpus.update(range(int(a), int(b) + 1))
+            elif part:
+                cpus.add(int(part))
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return spec
+    except Exception:
+        pass
+    return None
+
+
 def run_ours(args, rank, world, local_rank):
     import torch
 
@@ -153,6 +186,7 @@ def run_ours(args, rank, world, local_rank):
     log("torch imported")
     torch.cuda.set_device(local_rank)
     S.set_device(local_rank)
+    numa = bind_to_gpu_numa_node(local_rank) if world > 1 else None
     dist = None
     if world > 1:
         import torch.distributed as dist
@@ -180,7 +214,7 @@ def run_ours(args, rank, world, local_rank):
     for s, g in zip(samples, genomes):
         assert s.seq.ctypes.data == g.ctypes.data
     names = [f"s{rank * G + i}" for i in range(G)]
-    log(f"generated {G} x {L} bp genomes in pinned memory")
+    log(f"generated {G} x {L} bp genomes in pinned memory" + (f" (rank bound to CPUs {numa})" if numa else ""))
     n_bases = G * L
     threshold = int(np.ceil(G * 0.9))                  # generic_modes.rs:121 with cli.rs default min_freq 0.9
 

@@ -546,7 +546,7 @@ __global__ void __launch_bounds__(MG_THREADS, 4)
 bucket_emit_smem_kernel(const uint64_t* __restrict__ rec, const Item* __restrict__ items, int sb,
                         const uint64_t* __restrict__ row_off, int log_cap, uint32_t max_u, uint32_t n_samples, uint32_t stride_w,
                         int k, int rc, uint64_t* __restrict__ out_keys, uint8_t* __restrict__ out_var, uint32_t* __restrict__ out_cnt,
-                        const uint64_t* __restrict__ scratch_keys) {
+                        const uint64_t* __restrict__ scratch_keys, uint32_t u_min /* this launch takes items with u_min < u <= max_u */) {
     extern __shared__ __align__(16) uint8_t smem[];
     const uint32_t cap = 1u << log_cap;
     uint64_t* s_tab = reinterpret_cast<uint64_t*>(smem);
@@ -561,7 +561,7 @@ bucket_emit_smem_kernel(const uint64_t* __restrict__ rec, const Item* __restrict
     const uint64_t beg = it.beg, end = it.end;
     const uint64_t row_base = row_off[b];
     const uint32_t u = (uint32_t)(row_off[b + 1] - row_base);     // distinct keys, from the count pass
-    if (u == 0) return;
+    if (u <= u_min || u > max_u) return;                          // empty, or another launch's size class
     if (threadIdx.x == 0) s_anypal = 0;
 
     uint64_t nx[MG_PREFETCH];                                     // first records: in flight while the table is set up
@@ -1089,9 +1089,27 @@ static void merge_items(const uint64_t* rec, Item* items, uint32_t n_items, int 
         const char* force_red = getenv("SKA_EMIT_GLOBAL");                  // tests: force the wide-row path
         if (all_scratch && smem_sets <= (size_t)160 * 1024 && smem_sets + 1024 <= c.smem_optin && !(force_red && atoi(force_red))) {
             SKA_CUDA(cudaFuncSetAttribute(bucket_emit_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_sets));
+            // Two size classes.  Canonical keys crowd the low prefixes (density 2(1-p) over the key range), so the largest
+            // bucket has ~2-3x the rows of the median one, and shared memory sized for it leaves 2 CTAs per SM.  Buckets
+            // of up to `u_small` rows (<= 48 KB: 4 CTAs per SM) go first in their own launch; the other CTAs of each
+            // launch return at once.
+            uint32_t u_small = 0;
+            int log_cap_small = log_cap;
+            if (smem_sets > (size_t)56 * 1024 && !(getenv("SKA_EMIT_ONE_CLASS") && atoi(getenv("SKA_EMIT_ONE_CLASS")))) {
+                for (int lc = 6; lc <= log_cap; lc++) {
+                    const uint32_t uu = 1u << (lc - 1);                        // table at most half full
+                    if (uu < max_u && emit_smem_bytes(lc, uu, stride_w) <= (size_t)48 * 1024) { u_small = uu; log_cap_small = lc; }
+                }
+            }
+            if (u_small) {
+                const size_t smem_small = emit_smem_bytes(log_cap_small, u_small, stride_w);
+                SKA_LAUNCH(bucket_emit_smem_kernel, n_items, MG_THREADS, smem_small, rec, items, sb, row_off, log_cap_small, u_small,
+                           (uint32_t)n_samples, stride_w, (int)k, rc ? 1 : 0, out.keys.p, out.variants.p, out.counts.p,
+                           (const uint64_t*)scratch_keys, 0u);
+            }
             SKA_LAUNCH(bucket_emit_smem_kernel, n_items, MG_THREADS, smem_sets, rec, items, sb, row_off, log_cap, max_u,
                        (uint32_t)n_samples, stride_w, (int)k, rc ? 1 : 0, out.keys.p, out.variants.p, out.counts.p,
-                       (const uint64_t*)scratch_keys);
+                       (const uint64_t*)scratch_keys, u_small);
         } else {
             size_t smem = ((size_t)1 << log_cap) * slot_bytes;
             SKA_CUDA(cudaFuncSetAttribute(bucket_emit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
