@@ -1095,10 +1095,12 @@ static void merge_items(const uint64_t* rec, Item* items, uint32_t n_items, int 
             // launch return at once.
             uint32_t u_small = 0;
             int log_cap_small = log_cap;
-            if (smem_sets > (size_t)56 * 1024 && !(getenv("SKA_EMIT_ONE_CLASS") && atoi(getenv("SKA_EMIT_ONE_CLASS")))) {
+            size_t small_bytes = (size_t)48 * 1024;
+            if (const char* e = getenv("SKA_EMIT_SMALL_BYTES")) small_bytes = (size_t)std::max(0, atoi(e));   // tests: classes at small sizes
+            if (smem_sets > small_bytes + small_bytes / 6 && !(getenv("SKA_EMIT_ONE_CLASS") && atoi(getenv("SKA_EMIT_ONE_CLASS")))) {
                 for (int lc = 6; lc <= log_cap; lc++) {
                     const uint32_t uu = 1u << (lc - 1);                        // table at most half full
-                    if (uu < max_u && emit_smem_bytes(lc, uu, stride_w) <= (size_t)48 * 1024) { u_small = uu; log_cap_small = lc; }
+                    if (uu < max_u && emit_smem_bytes(lc, uu, stride_w) <= small_bytes) { u_small = uu; log_cap_small = lc; }
                 }
             }
             if (u_small) {

@@ -335,6 +335,27 @@ def test_build_k1_histogram_fusion(k, rc, monkeypatch):
     assert_same_array(a, ora_from_gpu_samples(samples, names, k, rc))
 
 
+@pytest.mark.parametrize("small_bytes", ["1500", "4000", "20000"])
+def test_build_emit_size_classes(small_bytes, monkeypatch):
+    """bucket_emit_smem_kernel runs in two launches when shared memory sized for the largest bucket would cost
+    occupancy: buckets of up to u_small rows first, the rest after.  SKA_EMIT_SMALL_BYTES moves the class boundary down
+    so that both classes are populated at test sizes; the array must equal the one-launch array and the oracle's."""
+    from ska_rust_b200 import synth
+    n, k = 16, 31
+    genomes = synth.star_genomes(n, 120_000, seed=0x5CA20066, snp_rate=0.004)
+    samples = [S.Sample.from_records([g.tobytes(), b"ACGT" * 16]) for g in genomes]
+    names = [f"s{i}" for i in range(n)]
+    monkeypatch.setenv("SKA_PREFIX_BITS", "10")                    # ~1900 records, ~350 rows per bucket (up to ~700 at low prefixes)
+    monkeypatch.setenv("SKA_EMIT_SMALL_BYTES", small_bytes)
+    a = S.build_from_samples(samples, names, k, True)
+    monkeypatch.setenv("SKA_EMIT_ONE_CLASS", "1")
+    b = S.build_from_samples(samples, names, k, True)
+    ka, va, ca = a.export()
+    kb, vb, cb = b.export()
+    assert np.array_equal(ka, kb) and np.array_equal(va, vb) and np.array_equal(ca, cb)
+    assert_same_array(a, ora_from_gpu_samples(samples, names, k, True))
+
+
 def test_build_overlapped_upload_matches_plain(monkeypatch):
     """skagpu_build on FASTA input runs K1 chunk by chunk behind the host->device copies (8 MB chunks; tiles that
     straddle a chunk boundary wait for the next chunk); SKA_H2D_OVERLAP=0 uploads first and extracts afterwards.
