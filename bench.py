@@ -278,7 +278,7 @@ def run_ours(args, rank, world, local_rank):
         if world == 1:
             arr = S.build_from_samples(samples, names, k, True)
         else:
-            arr = build_device(S.SeqBatch(samples))          # H2D of this rank's genomes, then the sharded build
+            arr = build_device(samples)                      # H2D of this rank's genomes inside the local build, then the exchange
         arr.filter(threshold, False, "no-const", False, False, False)
         r = arr.dims()["n_rows"]
         assert r == rows_aligned

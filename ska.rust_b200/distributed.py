@@ -83,8 +83,9 @@ class GpuBackend:
 
     def build_local(self, samples, names_local, k, rc, qual=None):
         """the rank's own samples -> its array; FASTQ samples take `qual` (api.QualOpts: min_count, min_qual, qual_filter)"""
-        batch = samples if isinstance(samples, api.SeqBatch) else api.SeqBatch(samples)
-        return api.build_from_batch(batch, names_local, k, rc, qual)
+        if isinstance(samples, api.SeqBatch):                    # already resident in HBM
+            return api.build_from_batch(samples, names_local, k, rc, qual)
+        return api.build_from_samples(samples, names_local, k, rc, qual)   # host buffers: K1 overlaps the upload (skagpu_build)
 
     def key_cumulative(self, arr, region_bits):
         cum = np.zeros((1 << region_bits) + 1, dtype=np.uint64)
