@@ -357,7 +357,8 @@ def run_ours(args, rank, world, local_rank):
                          "frac": emit_achieved / peak, "traffic": ncu_traffic(merge_kernel.replace("_kernel", "")) if full_size else None,
                          "peak_source": peak_src, "algorithmic_bytes_per_launch": emit_bytes, "launch_ms": emit_ms,
                          "share_of_step": emit_ms / step_ms,
-                         "note": "shared-memory table probes and atomics bound it, not DRAM (profiles/README.md)"},
+                         "note": "instruction issue / shared-memory atomics bound it, not DRAM (profiles/README.md); launch_ms covers "
+                                 "the kernel's two launches (bucket size classes), traffic is ncu's for the single-launch form"},
             # the kernel the north star quotes a target for (>= 60% of HBM peak): split-k-mer extraction
             "roofline_k1": {"kernel": "k1_extract_kernel", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                             "frac": achieved / peak, "traffic": ncu_traffic("k1_extract") if full_size else None,
