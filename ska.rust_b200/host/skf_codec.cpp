@@ -199,16 +199,20 @@ static Payload frame_decode(const uint8_t* d, size_t n, int threads) {
     return out;
 }
 
-static std::vector<uint8_t> frame_encode(const uint8_t* payload, size_t payload_size, int threads) {
+// The payload is never held in one piece: `fill(offset, len, dst)` materialises any part of it into a worker's 64 KiB
+// buffer (for an array of 3 GB of middle bases the CBOR payload would be 6 GB of `18 xx` pairs).
+template <class Fill>
+static std::vector<uint8_t> frame_encode(size_t payload_size, int threads, Fill fill) {
     const size_t CH = 65536;
     const size_t n_chunks = (payload_size + CH - 1) / CH;
     std::vector<std::vector<uint8_t>> comp(n_chunks);
     std::atomic<size_t> next{0};
     auto work = [&] {
-        std::vector<uint8_t> buf;
+        std::vector<uint8_t> buf, piece(CH);
         for (size_t c; (c = next.fetch_add(1)) < n_chunks;) {
-            const uint8_t* p = payload + c * CH;
             size_t len = std::min(CH, payload_size - c * CH);
+            uint8_t* p = piece.data();
+            fill(c * CH, len, p);
             snappy_compress(p, len, buf);
             bool raw = buf.size() >= len - len / 8;          // snap's rule of thumb: keep poorly compressible chunks raw
             size_t body = 4 + (raw ? len : buf.size());
@@ -380,28 +384,43 @@ std::vector<uint8_t> encode(const Array& a, int threads) {
 
     const size_t nv = a.variants.size();
     const uint8_t* v = a.variants.data();
-    bool small = false;                                      // a byte below 24 would be a one-byte CBOR integer
-    for (size_t i = 0; i < nv && !small; i += 4096) { uint8_t m = 0xFF; for (size_t j = i; j < std::min(nv, i + 4096); j++) m = std::min(m, v[j]); small = m < 24; }
-    if (small) {                                             // not produced by ska; general integer writer
-        for (size_t i = 0; i < nv; i++) put_head(o, 0, v[i]);
-        o.insert(o.end(), tail.begin(), tail.end());
-        return frame_encode(o.data(), o.size(), threads);
-    }
-    const size_t total = o.size() + 2 * nv + tail.size();
-    std::unique_ptr<uint8_t[]> buf(new uint8_t[total ? total : 1]);
-    memcpy(buf.get(), o.data(), o.size());
-    uint8_t* w = buf.get() + o.size();
-    const int nt = (int)std::max<size_t>(1, std::min<size_t>((size_t)threads, nv >> 20));
-    auto part = [&](int t) {
-        const size_t b0 = nv * t / nt, b1 = nv * (t + 1) / nt;
-        for (size_t i = b0; i < b1; i++) { w[2 * i] = 0x18; w[2 * i + 1] = v[i]; }
+    const size_t H = o.size(), D = 2 * nv, total = H + D + tail.size();
+    const uint8_t* head = o.data();
+    const uint8_t* tl = tail.data();
+    // a byte below 24 would be a one-byte CBOR integer (not produced by ska): noticed while filling, then the general
+    // integer writer redoes the file
+    std::atomic<bool> small{false};
+    std::atomic<bool>* small_p = &small;
+    auto fill = [=](size_t off, size_t len, uint8_t* dst) {
+        size_t done = 0;
+        while (done < len) {
+            const size_t at = off + done;
+            if (at < H) {                                    // head
+                const size_t n = std::min(len - done, H - at);
+                memcpy(dst + done, head + at, n); done += n;
+            } else if (at < H + D) {                         // data: byte j of the section is 0x18 (j even) or variant j/2 (j odd)
+                size_t j = at - H;
+                const size_t n = std::min(len - done, D - j);
+                uint8_t* w = dst + done;
+                size_t q = 0;
+                uint8_t lt24 = 0;
+                if (j & 1) { const uint8_t b = v[j >> 1]; lt24 |= (uint8_t)(b < 24); w[q++] = b; j++; }
+                for (; q + 1 < n; q += 2, j += 2) { const uint8_t b = v[j >> 1]; lt24 |= (uint8_t)(b < 24); w[q] = 0x18; w[q + 1] = b; }
+                if (q < n) w[q++] = 0x18;
+                if (lt24) small_p->store(true);
+                done += n;
+            } else {                                         // tail
+                const size_t n = std::min(len - done, total - at);
+                memcpy(dst + done, tl + (at - H - D), n); done += n;
+            }
+        }
     };
-    std::vector<std::thread> th;
-    for (int t = 1; t < nt; t++) th.emplace_back(part, t);
-    part(0);
-    for (auto& t : th) t.join();
-    memcpy(w + 2 * nv, tail.data(), tail.size());
-    return frame_encode(buf.get(), total, threads);
+    std::vector<uint8_t> framed = frame_encode(total, threads, fill);
+    if (!small.load()) return framed;
+    for (size_t i = 0; i < nv; i++) put_head(o, 0, v[i]);
+    o.insert(o.end(), tail.begin(), tail.end());
+    const uint8_t* whole = o.data();
+    return frame_encode(o.size(), threads, [whole](size_t off, size_t len, uint8_t* dst) { memcpy(dst, whole + off, len); });
 }
 
 void save(const Array& a, const std::string& path, int threads) {

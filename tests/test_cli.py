@@ -50,6 +50,23 @@ def test_cpp_codec_large_random_roundtrip(tmp_path):
     assert os.path.getsize(out) < os.path.getsize(src) // 2       # the C++ writer really compresses
 
 
+def test_cpp_codec_small_variant_bytes_take_the_general_writer(tmp_path):
+    """variant bytes below 24 are one-byte CBOR integers: the fixed `18 xx` stride does not apply (never written by ska,
+    but a valid file); reader and writer must notice and use the general integer path"""
+    rng = np.random.default_rng(2)
+    n_rows, n_samples = 70_000, 3                                  # > 64 KiB of payload: several chunks
+    var = rng.choice(np.array([0, 7, 23, 24, 45, 65, 200], dtype=np.uint8), size=(n_rows, n_samples)).astype(np.uint8)
+    keys = sorted(int(x) for x in rng.integers(0, 1 << 40, size=n_rows))
+    cnt = [int(c) for c in (var != 45).sum(axis=1)]
+    src = tmp_path / "a.skf"
+    src.write_bytes(skf_py.dump_skf_bytes(21, True, ["a", "b", "c"], keys, var.tobytes(), n_rows, n_samples, cnt, "0.5.2", 64))
+    out = tmp_path / "b.skf"
+    run(["recode", str(src), str(out), "--threads", "3"])
+    assert skf_py.load_skf(str(src)) == skf_py.load_skf(str(out))
+    with open(src, "rb") as f1, open(out, "rb") as f2:
+        assert skf_py.snappy_frame_decode(f1.read()) == skf_py.snappy_frame_decode(f2.read())
+
+
 def test_cpp_codec_scales_linearly_in_chunks():
     """64 MB of middle bases = ~2000 Snappy chunks: the decoder sizes its payload once (an earlier version re-copied
     the payload for every chunk and needed minutes for this)"""
