@@ -118,11 +118,13 @@ def run_reference(args, rank, world):
         return
     from ska_rust_b200 import synth
     cores = os.cpu_count() or 1
-    n = args.ref_genomes
+    n_warm = args.warmup if args.ref_warmup < 0 else args.ref_warmup
+    # bounded sample: at ~2 genomes/s the whole run (warm-up + steps) stays within a few minutes whatever --steps is
+    n = max(16, min(args.ref_genomes, 480 // max(1, args.steps + n_warm)))
     threads = host_threads_rule(cores, n)
     population = args.population if args.population != "auto" else ("star" if args.gpus == 1 else "tree")
     genomes = synth.genomes(population, n, args.length, args.genomes * args.gpus, seed=args.seed)
-    for _ in range(args.warmup if args.ref_warmup < 0 else args.ref_warmup):
+    for _ in range(n_warm):
         cpu_reference_step(genomes, args.k, threads)
     t0 = time.perf_counter()
     for _ in range(args.steps):
