@@ -63,8 +63,9 @@ class ClockSampler:
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, index):
+    def __init__(self, index, interval=0.2):
         self.index, self.samples, self._stop, self._t = index, [], threading.Event(), None
+        self.interval = interval
 
     def _run(self):
         while not self._stop.is_set():
@@ -75,7 +76,7 @@ class ClockSampler:
                     self.samples.append([x.strip() for x in out.split(",")])
             except Exception:
                 pass
-            self._stop.wait(0.02)                 # back-to-back queries: the timed region of 5 steps is only ~100 ms long
+            self._stop.wait(self.interval)
 
     def __enter__(self):
         self._t = threading.Thread(target=self._run, daemon=True)
@@ -250,7 +251,8 @@ def run_ours(args, rank, world, local_rank):
     log(f"device warm-up done; stages {S.api.last_timings()}")
     barrier()
     l0 = S.api.launch_count()
-    with ClockSampler(local_rank) as clocks:
+    # one rank: back-to-back queries (the timed region of 5 steps is only ~100 ms long); several ranks: the measured cadence
+    with ClockSampler(local_rank, 0.02 if world == 1 else 0.2) as clocks:
         S.api.timer_start()
         for _ in range(args.steps):
             arr = build_device(batch)
