@@ -1,9 +1,10 @@
 #!/usr/bin/env python3
-"""bench.py -- BASELINE.json's metric on its config: genomes/s for `ska build` + `ska align`
-(k=31, both strands) over synthetic 5 Mbp bacterial genomes (star model, 0.1 % SNPs).
+"""bench.py -- BASELINE.json's metric on its configs: genomes/s for `ska build` + `ska align`
+(k=31, both strands) over synthetic 5 Mbp bacterial genomes, 0.1 % SNPs (tree model).
 
-  python bench.py [--gpus N] [--steps K] [--warmup W]            # this repo's CUDA path
+  python bench.py [--gpus N] [--steps K] [--warmup W]            # this repo's CUDA path (configs[1] per GPU)
   python bench.py --impl reference [...]                         # the reference's CPU algorithm (oracle port)
+  python bench.py --workload distance|viral|fastq|cli [...]      # the other BASELINE configs (profiles/ lines)
 
 A "step" is one pass of the hot path over one batch: build (K1 extract -> partition -> bucket merge
 into the n_kmers x n_samples array) + align (default filter: min_freq 0.9, no-const; transpose for
@@ -11,8 +12,14 @@ the FASTA writer).  `value` times K steps with the sequence bytes already reside
 events on the library's own stream); `e2e` times the same K steps through the C ABI with pinned
 HOST buffers in and out (H2D of every genome and D2H of the alignment inside the timed region).
 Inputs (640 MB per 128 genomes) are larger than the 126 MB L2, so no L2 flush is needed between steps.
+
+Every line is self-checking (`parity`): the GPU alignment of a sample of the genomes is compared byte for
+byte with the oracle's (the CPU leg that is timed anyway), the full-size array is checked for count / order
+invariants on the device, and on several ranks the joined slabs are compared, column block by column block,
+with the ranks' local builds through an order-independent checksum (skagpu_array_checksum).
 """
 import argparse
+import io
 import json
 import os
 import subprocess
@@ -38,16 +45,18 @@ K1_ALGO_BYTES_PER_BASE = 10.0     # read 1 B ASCII + write 9 B (u6
 
 
 def ncu_traffic(kernel):
-    """DRAM bytes per launch of `kernel` from the committed ncu --set full capture (profiles/ncu_summary_r01.json,
-    same workload: 128 x 5 Mbp), or None."""
-    p = os.path.join(ROOT, "profiles", "ncu_summary_r01.json")
-    try:
-        with open(p) as fh:
-            d = json.load(fh)[kernel]
-        unit = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
-        return sum(float(d[m][0]) * unit[d[m][1]] for m in ("dram__bytes_read.sum", "dram__bytes_write.sum"))
-    except Exception:
-        return None
+    """DRAM bytes per launch of `kernel` from the newest committed ncu --set full capture (profiles/ncu_summary_r*.json,
+    same workload size), or None."""
+    for rnd in ("r02", "r01"):
+        p = os.path.join(ROOT, "profiles", f"ncu_summary_{rnd}.json")
+        try:
+            with open(p) as fh:
+                d = json.load(fh)[kernel]
+            unit = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+            return sum(float(d[m][0]) * unit[d[m][1]] for m in ("dram__bytes_read.sum", "dram__bytes_write.sum"))
+        except Exception:
+            continue
+    return None
 
 
 def measured_peak():
@@ -103,46 +112,60 @@ def host_threads_rule(threads, n):
     return 1 << (m.bit_length() - 1)
 
 
-def cpu_reference_step(genomes, k, threads):
-    """One build+align step of the reference's algorithm on the host (oracle port)."""
+def population_text(population, n_total):
+    return ("star model, 0.1% SNPs/sample" if population == "star" else
+            f"tree model (SURVEY 8d): {n_total} leaves, every leaf 0.1% from the root")
+
+
+def workload_config(args, world, population):
+    """the `config` object both arms print (same keys and values: the driver compares them)"""
+    G, L, k = args.genomes, args.length, args.k
+    return {"workload": f"ska build + align, {G} x {L} bp synthetic bacterial FASTA per GPU, k={k}, both strands "
+                        "(BASELINE configs[1])", "k": k, "rc": True, "genomes_per_gpu": G, "genome_bp": L,
+            "population": population_text(population, G * world), "align": "min_freq 0.9, filter no-const",
+            "l2": f"inputs ({G * L // 1000000} MB/{G} genomes) larger than L2; no flush"}
+
+
+def cpu_reference_step(genomes, k, threads, names=None):
+    """One build+align step of the reference's algorithm on the host (oracle port) -> the alignment (FASTA bytes)."""
     from oracle import oracle as O
     samples = [O.SampleData([(g.tobytes(), None)]) for g in genomes]
-    arr = O.OracleArray.build(samples, [f"s{i}" for i in range(len(genomes))], k=k, rc=True, threads=threads)
-    out = arr.align()
-    return len(out)
+    arr = O.OracleArray.build(samples, names or [f"s{i}" for i in range(len(genomes))], k=k, rc=True, threads=threads)
+    return arr.align()
 
 
 def run_reference(args, rank, world):
-    """--impl reference: the reference's own CPU algorithm for this path (C++ restatement in oracle/,
-    kind "port": the Rust reference cannot be built here), all host threads its own rule allows."""
+    """--impl reference: the reference's own CPU algorithm for this path (C++ restatement in oracle/, kind "port": the
+    Rust reference cannot be built here) on the SAME job as our arm's rank 0 -- all `--genomes` genomes of the same
+    population, the thread count the reference's own rule gives for that many samples (merge_ska_dict.rs:381-385).  One
+    such pass takes about a minute, so the run is bounded by timing ONE pass whatever --steps/--warmup say (a CPU build
+    has no warm-up effect worth a second minute); the line reports that pass as ms_per_step."""
     if rank != 0:
         return
     from ska_rust_b200 import synth
     cores = os.cpu_count() or 1
-    n_warm = args.warmup if args.ref_warmup < 0 else args.ref_warmup
-    # bounded sample: at ~2 genomes/s the whole run (warm-up + steps) stays within a few minutes whatever --steps is
-    n = max(16, min(args.ref_genomes, 480 // max(1, args.steps + n_warm)))
+    n = args.genomes
     threads = host_threads_rule(cores, n)
-    population = args.population if args.population != "auto" else ("star" if args.gpus == 1 else "tree")
-    genomes = synth.genomes(population, n, args.length, args.genomes * args.gpus, seed=args.seed)
-    for _ in range(n_warm):
-        cpu_reference_step(genomes, args.k, threads)
+    population = args.population
+    genomes = synth.genomes(population, n, args.length, args.genomes * world, seed=args.seed)
+    cpu_reference_step(genomes[:2], args.k, 1)              # loads the library, touches the allocator
+    reps = max(1, args.ref_reps)
     t0 = time.perf_counter()
-    for _ in range(args.steps):
-        cpu_reference_step(genomes, args.k, threads)
-    dt = (time.perf_counter() - t0) / args.steps
+    for _ in range(reps):
+        out = cpu_reference_step(genomes, args.k, threads)
+    dt = (time.perf_counter() - t0) / reps
     v = n / dt
-    sample = (f"{n} of {args.genomes} genomes x {args.length} bp per step (build+align), {threads} threads = the reference's "
-              f"rule 2^floor(log2(min(cores={cores}, 1+n/10))) for n={n}")
+    sample = (f"all {n} genomes x {args.length} bp of rank 0's share, {reps} timed build+align pass(es) "
+              f"(--steps/--warmup are not repeated: one pass is ~1 min), {threads} threads = the reference's rule "
+              f"2^floor(log2(min(cores={cores}, 1+n/10))) for n={n}; alignment {len(out)} bytes")
     line = {
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "u64", "data": "synthetic",
-        "config": {"workload": f"ska build + align, {args.genomes} x {args.length} bp synthetic bacterial FASTA, k={args.k}, CPU",
-                   "k": args.k, "rc": True, "genomes_per_step": n, "genome_bp": args.length, "population": population},
+        "config": workload_config(args, world, population),
         "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "gpu_launches": 0,
+        "gpu_launches": 0, "timed_passes": reps,
     }
     print(json.dumps(line), flush=True)
 
@@ -180,6 +203,23 @@ def bind_to_gpu_numa_node(local_rank):
     return None
 
 
+# stage of the library's timers -> (kernel, algorithmic bytes per launch).  n = records (= bases), R = rows built by the
+# merge this rank ran, C = its columns, Rk = rows kept by the filter, N = columns of the filtered array.  SURVEY 8d.
+STAGE_KERNELS = {
+    "k1_extract": ("k1_extract_kernel", lambda n, R, C, Rk, N: 10.0 * n),
+    "hist1": ("part_hist_kernel", lambda n, R, C, Rk, N: 8.0 * n),
+    "scatter1": ("part_scatter_kernel<1>", lambda n, R, C, Rk, N: 16.0 * n),
+    "hist2": ("part_hist_kernel", lambda n, R, C, Rk, N: 8.0 * n),
+    "scatter2": ("part_scatter_kernel<2>", lambda n, R, C, Rk, N: 16.0 * n),
+    "count": ("bucket_count_kernel", lambda n, R, C, Rk, N: 8.0 * n + 8.0 * R),
+    "emit": ("bucket_emit_smem_kernel", lambda n, R, C, Rk, N: 9.0 * n + R * (16.0 + C)),
+    "merge": ("bucket_merge_kernel", lambda n, R, C, Rk, N: 9.0 * n + R * (16.0 + C)),
+    "transpose": ("transpose_words_kernel", lambda n, R, C, Rk, N: 2.0 * Rk * N),
+}
+NCU_NAMES = {"k1_extract_kernel": "k1_extract", "part_scatter_kernel<1>": "part_scatter", "bucket_count_kernel": "bucket_count",
+             "bucket_emit_smem_kernel": "bucket_emit_smem", "transpose_words_kernel": "transpose_words"}
+
+
 def run_ours(args, rank, world, local_rank):
     import torch
 
@@ -210,14 +250,14 @@ def run_ours(args, rank, world, local_rank):
     G, L, k = args.genomes, args.length, args.k
     # weak scaling: every rank owns G genomes of the same population (sample indices rank*G ...)
     pinned = torch.empty((G, L), dtype=torch.uint8, pin_memory=True)
-    population = args.population if args.population != "auto" else ("star" if world == 1 else "tree")
+    population = args.population
     genomes = synth.genomes(population, G, L, G * world, seed=args.seed, first=rank * G, out=pinned.numpy())
     off = np.array([0, L], dtype=np.uint64)
     samples = [S.Sample(g, off) for g in genomes]      # views into the pinned block, no copy
     for s, g in zip(samples, genomes):
         assert s.seq.ctypes.data == g.ctypes.data
     names = [f"s{rank * G + i}" for i in range(G)]
-    log(f"generated {G} x {L} bp genomes in pinned memory" + (f" (rank bound to CPUs {numa})" if numa else ""))
+    log(f"generated {G} x {L} bp genomes ({population}) in pinned memory" + (f" (rank bound to CPUs {numa})" if numa else ""))
     n_bases = G * L
     threshold = int(np.ceil(G * 0.9))                  # generic_modes.rs:121 with cli.rs default min_freq 0.9
 
@@ -248,7 +288,7 @@ def run_ours(args, rank, world, local_rank):
         arr = build_device(batch)
         align_device(arr)
         del arr
-    log(f"device warm-up done; stages {S.api.last_timings()}")
+    log(f"device warm-up done; stages {[(s_, round(ms, 3)) for s_, ms, _ in S.api.last_timings()]}")
     barrier()
     l0 = S.api.launch_count()
     # one rank: back-to-back queries (the timed region of 5 steps is only ~100 ms long); several ranks: the measured cadence
@@ -271,114 +311,145 @@ def run_ours(args, rank, world, local_rank):
     log(f"device arm: {ms_dev / args.steps:.2f} ms/step, rows built {rows_built}, aligned {rows_aligned}")
     if shard_t:
         log("sharded build phases of the last call (ms): " + str({k_: round(v, 1) if isinstance(v, float) else v for k_, v in shard_t.items()}))
-    # ---------------- K1 alone (the kernel the roofline is quoted on), CUDA events inside the library
+    # ---------------- K1 alone (the kernel the north star quotes a target on), CUDA events inside the library
     _rec, k1_ms = batch.k1_extract(k, rc=True, iters=10, want_records=False)
+
+    # ---------------- parity at full size (not timed): device-side invariants + slabs against local builds
+    parity = {"checked": True}
+    arr = build_device(batch)
+    full_sum = arr.checksum()
+    parity["full_size_rows"] = arr.dims()["n_rows"]
+    parity["rows_with_wrong_count"] = full_sum[2]
+    parity["keys_out_of_order"] = full_sum[3]
+    ok = full_sum[2] == 0 and full_sum[3] == 0
+    if world > 1:
+        # MergeSkaDict::merge only moves cells: the cells of rank r's local build == columns [r*G, (r+1)*G) of all slabs
+        local = S.api.build_from_batch(batch, names[rank * G:(rank + 1) * G], k, True)
+        mine = local.checksum()
+        del local
+        blocks = np.array([arr.checksum(r * G, (r + 1) * G)[0] for r in range(world)], dtype=np.uint64)
+        t = torch.from_numpy(blocks.view(np.int64).copy()).cuda()
+        dist.all_reduce(t)                                   # wraps mod 2^64 like the checksum itself
+        total = t.cpu().numpy().view(np.uint64)
+        flags = torch.tensor([int(int(total[rank]) == mine[0]), int(ok), int(mine[2] == 0 and mine[3] == 0)], dtype=torch.int64, device="cuda")
+        dist.all_reduce(flags, op=dist.ReduceOp.MIN)
+        fl = flags.cpu().numpy()
+        parity["slabs_vs_local_builds"] = ("cell checksums of every rank's local build equal its column block summed over all slabs"
+                                           if fl[0] else "MISMATCH")
+        ok = bool(fl.min())
+    del arr
     del batch
+    if not ok:
+        raise SystemExit(f"parity check FAILED: {parity}")
 
     # ---------------- end-to-end arm: pinned host buffers in, alignment bytes out
-    out_host = torch.empty((G * world, max(1, rows_aligned)), dtype=torch.uint8, pin_memory=True).numpy()
+    e2e = None
+    if not args.no_e2e:
+        out_host = torch.empty((G * world, max(1, rows_aligned)), dtype=torch.uint8, pin_memory=True).numpy()
 
-    def e2e_step():
-        if world == 1:
-            arr = S.build_from_samples(samples, names, k, True)
-        else:
-            arr = build_device(samples)                      # H2D of this rank's genomes inside the local build, then the exchange
-        arr.filter(threshold, False, "no-const", False, False, False)
-        r = arr.dims()["n_rows"]
-        assert r == rows_aligned
-        arr.transposed(out=out_host)
-        return r
+        def e2e_step():
+            if world == 1:
+                arr = S.build_from_samples(samples, names, k, True)
+            else:
+                arr = build_device(samples)                      # H2D of this rank's genomes inside the local build, then the exchange
+            arr.filter(threshold, False, "no-const", False, False, False)
+            r = arr.dims()["n_rows"]
+            assert r == rows_aligned
+            arr.transposed(out=out_host)
+            return r
 
-    for _ in range(min(args.warmup, 2)):
-        e2e_step()
-    barrier()
-    S.api.timer_start()
-    walls = []
-    for _ in range(args.steps):
-        tw = time.perf_counter()
-        e2e_step()
-        walls.append(round((time.perf_counter() - tw) * 1e3, 1))
-    ms_e2e = S.api.timer_stop()
-    log(f"e2e per-step wall ms: {walls}; last build stages {[(s, round(ms, 2)) for s, ms, _ in S.api.last_timings()]}")
-    barrier()
-    ms_e2e = max_over_ranks(ms_e2e)
-    log(f"e2e arm: {ms_e2e / args.steps:.2f} ms/step")
-    e2e_value = args.steps * G * world / (ms_e2e * 1e-3)
-    h2d = n_bases + 8 * (2 * G + 1)                    # sequence bytes + record starts + sample offsets
-    d2h = G * world * rows_aligned + 4 * G + 24        # this rank's alignment slab + per-sample valid counts + scalars
+        for _ in range(min(args.warmup, 2)):
+            e2e_step()
+        barrier()
+        S.api.timer_start()
+        walls = []
+        for _ in range(args.steps):
+            tw = time.perf_counter()
+            e2e_step()
+            walls.append(round((time.perf_counter() - tw) * 1e3, 1))
+        ms_e2e = S.api.timer_stop()
+        log(f"e2e per-step wall ms: {walls}; last build stages {[(s, round(ms, 2)) for s, ms, _ in S.api.last_timings()]}")
+        barrier()
+        ms_e2e = max_over_ranks(ms_e2e)
+        log(f"e2e arm: {ms_e2e / args.steps:.2f} ms/step")
+        h2d = n_bases + 8 * (2 * G + 1)                    # sequence bytes + record starts + sample offsets
+        d2h = G * world * rows_aligned + 4 * G + 24        # this rank's alignment slab + per-sample valid counts + scalars
+        e2e = {"value": args.steps * G * world / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
+               "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / args.steps}
 
-    # ---------------- CPU baseline beside it (rank 0, N=1 only): bounded sample of the same workload
+    # ---------------- CPU baseline beside it + oracle parity on the same sample (rank 0)
     cpu_baseline = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+    if rank == 0 and not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
-        n_cpu = args.cpu_genomes
+        n_cpu = args.cpu_genomes if world == 1 else min(args.cpu_genomes, 8)
         threads = host_threads_rule(cores, n_cpu)
+        sub_names = [f"s{i}" for i in range(n_cpu)]
         t0 = time.perf_counter()
-        cpu_reference_step([g for g in genomes[:n_cpu]], k, threads)
+        ref_aln = cpu_reference_step([g for g in genomes[:n_cpu]], k, threads, sub_names)
         dt = time.perf_counter() - t0
         cpu_baseline = {"value": n_cpu / dt, "unit": UNIT, "cores": threads, "kind": "port",
                         "sample": f"first {n_cpu} of the {G} genomes, one build+align pass, {threads} threads (reference's "
                                   f"own thread rule for n={n_cpu}; host has {cores} cores)"}
+        garr = S.build_from_samples(samples[:n_cpu], sub_names, k, True)
+        buf = io.BytesIO()
+        S.api.align(garr, buf)
+        same = buf.getvalue() == ref_aln
+        parity["oracle_sample"] = (f"GPU build+align of the same {n_cpu} genomes: {len(ref_aln)} alignment bytes "
+                                   + ("identical to the oracle's" if same else "DIFFER from the oracle's"))
+        del garr
+        if not same:
+            raise SystemExit(f"parity check FAILED: {parity}")
+    elif rank == 0:
+        parity["oracle_sample"] = "skipped (--no-cpu-baseline)"
 
     if rank == 0:
         peak, peak_src = measured_peak()
-        achieved = K1_ALGO_BYTES_PER_BASE * n_bases / (k1_ms * 1e-3) / 1e9
         step_ms = ms_dev / args.steps
         st = {s_: ms for s_, ms, _ in stages}
-        # the merge kernel: bucket_merge_kernel (stage "merge": one pass over the records) or, when the fused pass does not
-        # apply, bucket_emit_smem_kernel (stage "emit").  Algorithmic bytes: 9 B per record read +
-        # (8 + N + 8) B per row written
         n_cols = G * world if strategy != "rows" or world == 1 else G
         rows_local = local_rows[0] if local_rows[0] else rows_built
-        emit_bytes = 9.0 * n_bases + rows_local * (16.0 + n_cols)
-        merge_stage = "merge" if "merge" in st else "emit"
-        merge_kernel = "bucket_merge_kernel" if merge_stage == "merge" else "bucket_emit_smem_kernel"
-        emit_ms = st.get(merge_stage, 0.0) or 1e-9
-        emit_achieved = emit_bytes / (emit_ms * 1e-3) / 1e9
-        part1_bytes = (16.0 if os.environ.get("SKA_K1_HIST", "0") not in ("", "0") else 24.0) * n_bases
-        full_size = (G == 128 and L == 5_000_000 and world == 1 and population == "star")   # what profiles/ was captured on
+        full_size = (G == 128 and L == 5_000_000 and world == 1)   # what profiles/ was captured on
+
+        def roof(stage):
+            kern, fn = STAGE_KERNELS[stage]
+            ms = st.get(stage, 0.0) or 1e-9
+            by = fn(float(n_bases), float(rows_local), float(n_cols), float(rows_aligned), float(G * world))
+            return {"kernel": kern, "stage": stage, "bound": "hbm", "achieved": by / (ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                    "frac": by / (ms * 1e-3) / 1e9 / peak, "traffic": ncu_traffic(NCU_NAMES.get(kern, "")) if full_size else None,
+                    "peak_source": peak_src, "algorithmic_bytes_per_launch": by, "launch_ms": ms, "share_of_step": ms / step_ms}
+
+        # the dominant kernel = the single-kernel stage with the largest share of the step
+        dom = max((s_ for s_ in st if s_ in STAGE_KERNELS), key=lambda s_: st[s_])
+        k1 = roof("k1_extract")
+        k1.update({"achieved": K1_ALGO_BYTES_PER_BASE * n_bases / (k1_ms * 1e-3) / 1e9, "launch_ms": k1_ms,
+                   "note": "10 launches timed back to back inside the library (skagpu_k1_extract)"})
+        k1["frac"] = k1["achieved"] / peak
+        k1["frac_of_nominal_8TBs"] = k1["achieved"] / 8000.0
+        # whole step against the roofline: SURVEY 8d's algorithmic bytes of K1 + K2/K3 + K4 (the partition is overhead)
+        step_bytes = 10.0 * n_bases + 9.0 * n_bases + rows_local * (16.0 + n_cols) + rows_built * 4.0 + 2.0 * rows_aligned * (G * world) * 2
+        cfg = workload_config(args, world, population)
+        cfg.update({"parallelism": "1 GPU" if world == 1 else
+                    (f"{world} ranks: every rank builds its {G} samples, one NCCL exchange of partial rows by key range, "
+                     f"owners join on the key; rows sharded for filter/align ({G * world} columns per slab)" if strategy == "rows" else
+                     f"{world} ranks: samples sharded for extraction, one NCCL all-to-all of records by key range, "
+                     f"rows sharded for merge/filter ({G * world} columns per slab)"),
+                    "rows_built": rows_built, "rows_aligned": rows_aligned})
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64",
-            "data": "synthetic",
-            "config": {"workload": f"ska build + align, {G} x {L} bp synthetic bacterial FASTA per GPU, k={k}, both strands "
-                                   "(BASELINE configs[1])", "k": k, "rc": True, "genomes_per_gpu": G, "genome_bp": L,
-                       "population": ("star model, 0.1% SNPs/sample" if population == "star" else
-                                      f"tree model (SURVEY 8d, configs[2]): {G * world} leaves, every leaf 0.1% from the root"),
-                       "align": "min_freq 0.9, filter no-const",
-                       "l2": "inputs (640 MB/128 genomes) larger than L2; no flush",
-                       "parallelism": "1 GPU" if world == 1 else
-                       (f"{world} ranks: every rank builds its {G} samples, one NCCL exchange of partial rows by key range, "
-                        f"owners join on the key; rows sharded for filter/align ({G * world} columns per slab)" if strategy == "rows" else
-                        f"{world} ranks: samples sharded for extraction, one NCCL all-to-all of records by key range, "
-                        f"rows sharded for merge/filter ({G * world} columns per slab)"),
-                       "rows_built": rows_built, "rows_aligned": rows_aligned},
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "ms_per_step": ms_e2e / args.steps},
+            "data": "synthetic", "config": cfg,
             "gpu_launches": launches,
-            # the merge kernel (K3); the partition's scatter kernels have a larger share of the step, see stages_ms / roofline_scatter
-            "roofline": {"kernel": merge_kernel, "bound": "hbm", "achieved": emit_achieved, "peak": peak, "unit": "GB/s",
-                         "frac": emit_achieved / peak, "traffic": ncu_traffic(merge_kernel.replace("_kernel", "")) if full_size else None,
-                         "peak_source": peak_src, "algorithmic_bytes_per_launch": emit_bytes, "launch_ms": emit_ms,
-                         "share_of_step": emit_ms / step_ms,
-                         "note": "instruction issue / shared-memory atomics bound it, not DRAM (profiles/README.md); launch_ms covers "
-                                 "the kernel's two launches (bucket size classes), traffic is ncu's for the single-launch form"},
-            # the kernel the north star quotes a target for (>= 60% of HBM peak): split-k-mer extraction
-            "roofline_k1": {"kernel": "k1_extract_kernel", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                            "frac": achieved / peak, "traffic": ncu_traffic("k1_extract") if full_size else None,
-                            "peak_source": peak_src, "algorithmic_bytes_per_launch": K1_ALGO_BYTES_PER_BASE * n_bases,
-                            "launch_ms": k1_ms, "share_of_step": st.get("k1_extract", 0.0) / step_ms,
-                            "frac_of_nominal_8TBs": achieved / 8000.0},
-            # first partition pass (stage "partition1") = part_hist_kernel + scan + part_scatter_kernel<1>: 8 B read by the
-            # histogram, 8 B read + 8 B written by the scatter, per record (with SKA_K1_HIST=1 K1 counts the histogram: 16 B)
-            "roofline_scatter": {"kernel": "part_hist_kernel + part_scatter_kernel<1>", "bound": "hbm", "unit": "GB/s", "peak": peak,
-                                 "achieved": part1_bytes / ((st.get("partition1", 0.0) or 1e-9) * 1e-3) / 1e9,
-                                 "frac": part1_bytes / ((st.get("partition1", 0.0) or 1e-9) * 1e-3) / 1e9 / peak,
-                                 "algorithmic_bytes_per_launch": part1_bytes, "launch_ms": st.get("partition1", 0.0),
-                                 "traffic": None, "share_of_step": st.get("partition1", 0.0) / step_ms},
-            "stages_ms": {s: round(ms, 3) for s, ms, _ in stages},
+            "roofline": roof(dom),
+            "roofline_k1": k1,
+            "roofline_step": {"bound": "hbm", "algorithmic_bytes": step_bytes, "achieved": step_bytes / (step_ms * 1e-3) / 1e9,
+                              "peak": peak, "unit": "GB/s", "frac": step_bytes / (step_ms * 1e-3) / 1e9 / peak},
+            "roofline_stages": {s_: round(roof(s_)["frac"], 3) for s_ in st if s_ in STAGE_KERNELS},
+            "stages_ms": {s_: round(ms, 3) for s_, ms, _ in stages},
             "clocks": clocks.summary(),
+            "parity_checked": True, "parity": parity,
         }
+        if e2e:
+            line["e2e"] = e2e
         if cpu_baseline:
             line["cpu_baseline"] = cpu_baseline
         print(json.dumps(line), flush=True)
@@ -396,22 +467,28 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="align", choices=["align", "distance", "viral", "fastq", "cli"],
+                    help="align = BASELINE configs[1] (the driver's line); the others are configs[2..4] and the file-to-file CLI run")
     ap.add_argument("--genomes", type=int, default=128, help="genomes per GPU (BASELINE configs[1]: 128)")
     ap.add_argument("--length", type=int, default=5_000_000)
     ap.add_argument("--k", type=int, default=31)
     ap.add_argument("--seed", type=int, default=0x5CA20002)
-    ap.add_argument("--cpu-genomes", type=int, default=40, help="bounded CPU-baseline sample (genomes): 4 threads by the reference's rule")
-    ap.add_argument("--ref-genomes", type=int, default=80, help="genomes per step of the --impl reference arm: the smallest job for which "
-                    "the reference's rule (merge_ska_dict.rs:381-385) uses 8 threads, as it does for the full 128")
-    ap.add_argument("--ref-warmup", type=int, default=1, help="warm-up steps of the reference arm (-1: use --warmup)")
+    ap.add_argument("--cpu-genomes", type=int, default=40, help="bounded CPU-baseline sample (genomes) beside our arm: 4 threads by the reference's rule")
+    ap.add_argument("--ref-reps", type=int, default=1, help="timed passes of the --impl reference arm over the full job (~1 min each)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--population", default="auto", choices=["auto", "star", "tree"],
-                    help="SURVEY 8d generator: star (configs[1], the 1-GPU default) or tree (recommended there for the "
-                         "1024-genome configs[2]; the default when several GPUs share one population)")
+    ap.add_argument("--no-e2e", action="store_true", help="skip the end-to-end arm (kernel A/B runs)")
+    ap.add_argument("--population", default="tree", choices=["star", "tree"],
+                    help="SURVEY 8d generator.  tree (default at every N, so that the 1 -> 8 GPU curve is like for like): the "
+                         "samples are leaves of a balanced tree over all N x 128 genomes, every leaf 0.1%% from the root; "
+                         "star: every sample 0.1%% from the ancestor independently (round 1's 1-GPU population)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.workload != "align":
+        import importlib
+        mod = importlib.import_module("profiles.workloads")
+        return mod.run(args, rank, world, local_rank)
     if args.impl == "reference":
         run_reference(args, rank, world)
     else:

@@ -156,6 +156,14 @@ int skagpu_merge_partial_rows_dev(const void* keys_dev, const void* variants_dev
  * distance = dist_int (filt_ambig) or n_both - dist_int/36 (allow-ambiguous), matches += constant. */
 int skagpu_distance_counters(const ska_array_t* a, int filt_ambig, uint64_t* counters);
 
+/* Self-check of a device-resident array (no reference counterpart; bench.py's in-run parity check and the tests):
+ * out[0] = order-independent checksum over the non-'-' cells (key, column - col_lo, letter) of columns [col_lo, col_hi)
+ *          -- MergeSkaDict::merge (merge_ska_dict.rs:119-151) only moves cells, so a rank's local build and the same
+ *          columns of the joined slabs, summed over ranks (mod 2^64), must agree;
+ * out[1] = rows with at least one such cell; out[2] = rows whose variant_count is not their number of non-'-' cells
+ * (merge_ska_array.rs:172); out[3] = adjacent keys that are not strictly ascending. */
+int skagpu_array_checksum(const ska_array_t* a, uint32_t col_lo, uint32_t col_hi, uint64_t* out /* 4 */);
+
 /* Pinned host memory for callers that want full-speed PCIe transfers. */
 void* skagpu_host_alloc(size_t bytes);
 void skagpu_host_free(void* p);

@@ -10,10 +10,12 @@ FLAGS="-gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo -Xcompil
 build() {   # name, file, defines
     $NVCC $FLAGS $3 -c $2.cu -o ../variants/$2_$1.o
     objs=""
-    for f in api k1_extract k1q_reads partition merge rowmerge filter distance; do
+    for f in api k1_extract k1q_reads partition merge rowmerge filter distance verify; do
         if [ "$f" == "$2" ]; then objs="$objs ../variants/$2_$1.o"; else objs="$objs $f.o"; fi
     done
     $NVCC -gencode arch=compute_100a,code=sm_100a -shared -o ../variants/libskagpu_$1.so $objs
 }
-build pt256x8 partition "-DSKA_PT_THREADS=256 -DSKA_PT_ITEMS=8"
+build sc256_3 partition "-DSKA_SC_THREADS=256 -DSKA_SC_MIN_CTAS=3"
+build sc512_2 partition "-DSKA_SC_THREADS=512 -DSKA_SC_MIN_CTAS=2"
+build sc512_3 partition "-DSKA_SC_THREADS=512 -DSKA_SC_MIN_CTAS=3"
 ls -la ../variants/*.so

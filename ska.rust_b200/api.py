@@ -33,7 +33,7 @@ EXPORTS = [
     "skagpu_export_transposed", "skagpu_free", "skagpu_host_alloc", "skagpu_host_free", "skagpu_last_timings",
     "skagpu_launch_count", "skagpu_k1_extract", "skagpu_stream_timer", "skagpu_extract_records", "skagpu_records_info",
     "skagpu_records_free", "skagpu_merge_records_dev", "skagpu_distance_counters", "skagpu_merge_prefix_bits",
-    "skagpu_array_dev", "skagpu_key_cumulative", "skagpu_merge_partial_rows_dev",
+    "skagpu_array_dev", "skagpu_key_cumulative", "skagpu_merge_partial_rows_dev", "skagpu_array_checksum",
 ]
 
 
@@ -90,6 +90,7 @@ def lib():
         L.skagpu_merge_partial_rows_dev.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
                                                     C.c_void_p, C.c_uint64, C.c_uint32, C.c_int, C.c_void_p]
         L.skagpu_distance_counters.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+        L.skagpu_array_checksum.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p]
         L.skagpu_k1_extract.argtypes = [C.c_void_p, C.c_uint32, C.c_int, C.c_uint8, C.c_int, C.c_int, C.c_void_p,
                                         C.c_void_p, C.c_void_p]
         _lib = L
@@ -122,10 +123,10 @@ def launch_count():
 
 def last_timings():
     """[(stage, ms, kernel launches)] of the most recent build, from CUDA events on the library stream."""
-    names = (C.c_char_p * 16)()
-    ms = (C.c_float * 16)()
-    ln = (C.c_uint64 * 16)()
-    n = lib().skagpu_last_timings(names, ms, ln, 16)
+    names = (C.c_char_p * 32)()
+    ms = (C.c_float * 32)()
+    ln = (C.c_uint64 * 32)()
+    n = lib().skagpu_last_timings(names, ms, ln, 32)
     return [(names[i].decode(), float(ms[i]), int(ln[i])) for i in range(n)]
 
 
@@ -368,6 +369,13 @@ class MergeSkaArray:
         out = np.zeros((max(1, n * (n - 1) // 2), 4), dtype=np.uint64)
         _check(lib().skagpu_distance_counters(self._h, int(filt_ambig), out.ctypes.data))
         return out[:n * (n - 1) // 2]
+
+    def checksum(self, col_lo=0, col_hi=None):
+        """-> (cell checksum over columns [col_lo, col_hi), rows with a cell there, rows with a wrong count, keys out of order)"""
+        out = np.zeros(4, dtype=np.uint64)
+        hi = self.nsamples() if col_hi is None else col_hi
+        _check(lib().skagpu_array_checksum(self._h, int(col_lo), int(hi), out.ctypes.data))
+        return tuple(int(x) for x in out)
 
     # ---- MergeSkaArray::write_fasta (merge_ska_array.rs:499-517)
     def transpose_on_device(self):

@@ -91,7 +91,9 @@ __global__ void set_start_bits_kernel(const uint64_t* __restrict__ starts, uint6
     atomicOr(&bits[p >> 5], 1u << (p & 31));
 }
 
-static bool k1_hist_enabled() { const char* e = getenv("SKA_K1_HIST"); return e && atoi(e) != 0; }
+// K1 also counts the records by the first partition digit (default on; SKA_K1_HIST=0 keeps the two kernels apart for
+// A/B runs): the partition then never reads the records for its first histogram
+static bool k1_hist_enabled() { const char* e = getenv("SKA_K1_HIST"); return !e || atoi(e) != 0; }
 
 static void check_k(uint32_t k) {
     if (k < 5 || k > 63 || (k % 2) == 0) throw Error("Invalid k-mer length");      // ska_dict.rs:342-344
@@ -250,10 +252,9 @@ static std::unique_ptr<Array> build_from_batch(const SeqBatch& b, uint32_t k, bo
     uint64_t* rec = arena().take_n<uint64_t>(b.n_pos);
     uint32_t* valid = arena().take_n<uint32_t>(b.n_samples);
     SKA_CUDA(cudaMemsetAsync(valid, 0, b.n_samples * 4, c.stream));
-    // Optionally K1 also counts the records by the first partition digit, so that the partition never reads them for
-    // its histogram.  Measured on 128 x 5 Mbp: the step gets 0.67 ms shorter (partition -0.91 ms, K1 +0.24 ms) but K1
-    // drops from 0.65 to 0.57 of the HBM peak because the shared-memory atomics compete with its own staging traffic;
-    // the extraction kernel is kept at its best by default (SKA_K1_HIST=1 turns the fusion on).
+    // K1 also counts the records by the first partition digit, so that the partition never reads them for its
+    // histogram.  Measured on 128 x 5 Mbp: the step gets 0.67 ms shorter (partition -0.91 ms, K1 +0.24 ms: 4096 shared-memory
+    // atomics per tile at 3.6 SM-cycles per warp instruction, profiles/microbench/scatter_mb2.cu).
     const PartPlan pl = make_part_plan(k, merge_prefix_bits(b.n_pos, k, b.n_samples), b.n_samples);
     unsigned long long* k1_hist = nullptr;
     if (k1_hist_enabled()) {
@@ -607,6 +608,15 @@ int skagpu_distance_counters(const ska_array_t* h, int filt_ambig, uint64_t* cou
     API_CATCH
 }
 
+int skagpu_array_checksum(const ska_array_t* h, uint32_t col_lo, uint32_t col_hi, uint64_t* out) {
+    API_TRY
+    if (!h || !out) throw Error("null argument");
+    ctx().ensure();
+    array_checksum(h->a, col_lo, col_hi, out);
+    return 0;
+    API_CATCH
+}
+
 void* skagpu_host_alloc(size_t bytes) {
     void* p = nullptr;
     try { ctx().ensure(); } catch (std::exception& e) { g_err = e.what(); return nullptr; }
@@ -663,7 +673,8 @@ int skagpu_k1_extract(const ska_seqbatch_t* batch, uint32_t k, int rc, uint8_t m
     const PartPlan pl = make_part_plan(k, merge_prefix_bits(b.n_pos, k, b.n_samples), b.n_samples);
     DevBuf<unsigned long long> hist((size_t)K1_HIST_COPIES << pl.P1);
     SKA_CUDA(cudaMemsetAsync(hist.p, 0, hist.bytes(), c.stream));
-    unsigned long long* hp = (b.has_qual || !k1_hist_enabled()) ? nullptr : hist.p;
+    // the extraction kernel proper; inside a build the same kernel also fills the partition histogram (stage "k1_extract")
+    unsigned long long* hp = (getenv("SKA_K1_ROOFLINE_WITH_HIST") && !b.has_qual) ? hist.p : nullptr;
     const int hshift = 4 + pl.key_bits - pl.P1;
     cudaEvent_t e0, e1;
     SKA_CUDA(cudaEventCreate(&e0)); SKA_CUDA(cudaEventCreate(&e1));

@@ -186,4 +186,7 @@ void distance_array(const Array& a, double constant, bool filt_ambig, DistOut* h
 // 36 x summed overlap when !filt_ambig); partial sums over this array's rows, addable across row shards
 void distance_counters(const Array& a, bool filt_ambig, uint64_t* h_counters);
 
+// verify.cu: {cell checksum over columns [col_lo, col_hi), rows with a cell there, rows with a wrong count, keys out of order}
+void array_checksum(const Array& a, uint32_t col_lo, uint32_t col_hi, uint64_t* h_out);
+
 }  // namespace ska

@@ -35,6 +35,17 @@ constexpr int PT_ITEMS = SKA_PT_ITEMS;
 constexpr int PT_TILE = PT_THREADS * PT_ITEMS;      // records per tile
 constexpr int PT_WARPS = PT_THREADS / 32;
 constexpr int PT_MAX_BITS = 11;
+// scatter CTA shape (same tile): threads x records per thread
+#ifndef SKA_SC_THREADS
+#define SKA_SC_THREADS 256
+#endif
+#ifndef SKA_SC_MIN_CTAS
+#define SKA_SC_MIN_CTAS 4
+#endif
+constexpr int SC_T = SKA_SC_THREADS;
+constexpr int SC_I = PT_TILE / SC_T;
+constexpr int SC_MIN_CTAS = SKA_SC_MIN_CTAS;
+static_assert(SC_T * SC_I == PT_TILE && PT_TILE <= 65536, "scatter tile shape");
 constexpr uint32_t PT_NONE = 0xFFFFFFFFu;
 
 // ---------------------------------------------------------------------------------------------- histograms
@@ -108,13 +119,18 @@ struct PackFn {               // pass 1: K1 record -> packed record (needs the s
     uint32_t sid_base;
 };
 
-template <int PASS>
-__global__ void __launch_bounds__(PT_THREADS)
-part_scatter_kernel(const uint64_t* __restrict__ src, uint64_t n_total, Segs sg, DigitFn fn, int bits, PackFn pk,
+// Scatter of one tile of PT_TILE records.  SC_T threads x SC_I records each (256 x 16: four CTAs per SM at 64 registers;
+// measured on B200 with profiles/microbench/scatter_mb2.cu: 2.29 ms for 6.4e8 records against 2.72 ms for 512 x 8 and
+// 3.7 ms for the round-1 kernel, which zeroed its counters and waited at a barrier BEFORE issuing its loads).
+// BITS > 0: digit width fixed at compile time (the 8 + 8 split of a 128-sample build); BITS == 0: run-time width.
+template <int PASS, int BITS>
+__global__ void __launch_bounds__(SC_T, SC_MIN_CTAS)
+part_scatter_kernel(const uint64_t* __restrict__ src, uint64_t n_total, Segs sg, DigitFn fn, int bits_rt, PackFn pk,
                     const uint64_t* __restrict__ sample_off, uint32_t n_samples,
                     unsigned long long* __restrict__ cursor /* [n_regions or 1][1 << bits], preset to bucket starts */,
                     uint64_t* __restrict__ dst) {
     extern __shared__ __align__(16) uint8_t smem[];
+    const int bits = BITS ? BITS : bits_rt;
     const uint32_t D = 1u << bits;
     uint64_t* s_stage = reinterpret_cast<uint64_t*>(smem);                       // [PT_TILE]
     unsigned long long* s_gbase = reinterpret_cast<unsigned long long*>(s_stage + PT_TILE);   // [D]
@@ -126,7 +142,16 @@ part_scatter_kernel(const uint64_t* __restrict__ src, uint64_t n_total, Segs sg,
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     uint64_t beg, end; uint32_t region;
     tile_range(blockIdx.x, sg, n_total, beg, end, region);
-    for (uint32_t i = threadIdx.x; i < D; i += PT_THREADS) s_acnt[i] = 0;
+    // 1. the tile's records: in flight while the counters are cleared
+    uint64_t rr[SC_I]; uint32_t dp[SC_I];
+    const uint32_t cnt = (uint32_t)(end - beg);
+    const uint64_t* __restrict__ sp = src + beg;
+#pragma unroll
+    for (int j = 0; j < SC_I; j++) {
+        const uint32_t li = j * SC_T + threadIdx.x;
+        rr[j] = li < cnt ? __ldg(sp + li) : REC_SENTINEL;
+    }
+    for (uint32_t i = threadIdx.x; i < D; i += SC_T) s_acnt[i] = 0;
     if (PASS == 1 && threadIdx.x == 0) {                     // sample ids of the tile's first and last position
         uint64_t pf = beg, pl = end - 1;
         uint32_t lo = 0, hi = n_samples;
@@ -137,70 +162,74 @@ part_scatter_kernel(const uint64_t* __restrict__ src, uint64_t n_total, Segs sg,
     }
     __syncthreads();
 
-    // 1. load, digit, rank
-    uint64_t out[PT_ITEMS]; uint32_t dig[PT_ITEMS]; uint32_t pre[PT_ITEMS];
-    uint64_t rr[PT_ITEMS];
+    // 2. digit, packed record, rank among the tile's records of the digit (dp = digit << 16 | rank; PT_TILE <= 65536)
 #pragma unroll
-    for (int j = 0; j < PT_ITEMS; j++) {
-        uint64_t i = beg + (uint64_t)j * PT_THREADS + threadIdx.x;
-        rr[j] = i < end ? src[i] : REC_SENTINEL;
-    }
-#pragma unroll
-    for (int j = 0; j < PT_ITEMS; j++) {
-        const uint64_t i = beg + (uint64_t)j * PT_THREADS + threadIdx.x;
+    for (int j = 0; j < SC_I; j++) {
+        const uint32_t li = j * SC_T + threadIdx.x;
         const uint64_t r = rr[j];
-        uint32_t d = i < end ? fn(r) : PT_NONE;
-        const bool valid = d != PT_NONE;
+        // pass 1: padding carries the sentinel already; pass 2: packed records have no sentinel
+        const uint32_t d = PASS == 1 ? (r == REC_SENTINEL ? PT_NONE : (uint32_t)(r >> fn.shift))
+                                     : (li < cnt ? (fn.mask ? (uint32_t)(r >> fn.shift) & fn.mask : 0u) : PT_NONE);
         if (PASS == 1) {
             uint32_t s = s_sid[0];
-            if (valid && s_sid[0] != s_sid[1]) {             // tile straddles samples (rare)
+            if (d != PT_NONE && s_sid[0] != s_sid[1]) {      // tile straddles samples (rare)
+                const uint64_t i = beg + li;
                 uint32_t lo = s_sid[0], hi = s_sid[1] + 1;
                 while (hi - lo > 1) { uint32_t m = (lo + hi) >> 1; if (sample_off[m] <= i) lo = m; else hi = m; }
                 s = lo;
             }
             const uint64_t key = r >> 4;
             const uint32_t mid = (uint32_t)__ffs((uint32_t)(r & 0xF)) - 1u;
-            out[j] = ((key & pk.low_mask) << (pk.sb + 2)) | ((uint64_t)(s + pk.sid_base) << 2) | mid;
-        } else {
-            out[j] = r;
+            rr[j] = ((key & pk.low_mask) << (pk.sb + 2)) | ((uint64_t)(s + pk.sid_base) << 2) | mid;
         }
-        pre[j] = valid ? atomicAdd(&s_acnt[d], 1u) : 0u;       // rank among the tile's records of this digit
-        dig[j] = d;
+        dp[j] = d != PT_NONE ? ((d << 16) | atomicAdd(&s_acnt[d], 1u)) : PT_NONE;
     }
     __syncthreads();
 
-    // 2. tile totals per digit
-    for (uint32_t d = threadIdx.x; d < D; d += PT_THREADS) s_doff[d] = s_acnt[d];
-    __syncthreads();
     // 3. exclusive scan over digits (warp 0: 32 lanes x D/32 consecutive digits), global reservation
     if (warp == 0) {
-        const uint32_t per = (D + 31) / 32, b0 = lane * per, e0 = min(D, b0 + per);
-        uint32_t sum = 0;
-        for (uint32_t d = b0; d < e0; d++) sum += s_doff[d];
-        uint32_t inc = sum;
+        if (BITS) {
+            constexpr int per = BITS ? (1 << BITS) / 32 : 1;
+            const int b0 = lane * per;
+            uint32_t v[per], sum = 0;
 #pragma unroll
-        for (int o = 1; o < 32; o <<= 1) { uint32_t v = __shfl_up_sync(0xFFFFFFFFu, inc, o); if (lane >= o) inc += v; }
-        uint32_t run = inc - sum;
-        for (uint32_t d = b0; d < e0; d++) { uint32_t t = s_doff[d]; s_doff[d] = run; run += t; }
-        if (lane == 31) s_doff[D] = inc;
+            for (int q = 0; q < per; q++) { v[q] = s_acnt[b0 + q]; sum += v[q]; }
+            uint32_t inc = sum;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { uint32_t t = __shfl_up_sync(0xFFFFFFFFu, inc, o); if (lane >= o) inc += t; }
+            uint32_t run = inc - sum;
+#pragma unroll
+            for (int q = 0; q < per; q++) { s_doff[b0 + q] = run; run += v[q]; }
+            if (lane == 31) s_doff[D] = inc;
+        } else {
+            const uint32_t per = (D + 31) / 32, b0 = lane * per, e0 = min(D, b0 + per);
+            uint32_t sum = 0;
+            for (uint32_t d = b0; d < e0; d++) sum += s_acnt[d];
+            uint32_t inc = sum;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { uint32_t v = __shfl_up_sync(0xFFFFFFFFu, inc, o); if (lane >= o) inc += v; }
+            uint32_t run = inc - sum;
+            for (uint32_t d = b0; d < e0; d++) { uint32_t t = s_acnt[d]; s_doff[d] = run; run += t; }
+            if (lane == 31) s_doff[D] = inc;
+        }
     }
     __syncthreads();
-    for (uint32_t d = threadIdx.x; d < D; d += PT_THREADS) {
+    for (uint32_t d = threadIdx.x; d < D; d += SC_T) {
         uint32_t tot = s_doff[d + 1] - s_doff[d];
         if (tot) s_gbase[d] = atomicAdd(&cursor[(size_t)region * D + d], (unsigned long long)tot) - s_doff[d];
     }
     // 4. stage in digit order
 #pragma unroll
-    for (int j = 0; j < PT_ITEMS; j++) {
-        if (dig[j] == PT_NONE) continue;
-        uint32_t slot = s_doff[dig[j]] + pre[j];
-        s_stage[slot] = out[j];
-        s_sdig[slot] = (uint16_t)dig[j];
+    for (int j = 0; j < SC_I; j++) {
+        if (dp[j] == PT_NONE) continue;
+        const uint32_t d = dp[j] >> 16, slot = s_doff[d] + (dp[j] & 0xFFFFu);
+        s_stage[slot] = rr[j];
+        s_sdig[slot] = (uint16_t)d;
     }
     __syncthreads();
     // 5. coalesced runs out
     const uint32_t n_valid = s_doff[D];
-    for (uint32_t slot = threadIdx.x; slot < n_valid; slot += PT_THREADS) dst[s_gbase[s_sdig[slot]] + slot] = s_stage[slot];
+    for (uint32_t slot = threadIdx.x; slot < n_valid; slot += SC_T) dst[s_gbase[s_sdig[slot]] + slot] = s_stage[slot];
 }
 
 // ---------------------------------------------------------------------------------------------- small helpers
@@ -274,8 +303,13 @@ PartPlan make_part_plan(uint32_t k, int prefix_bits, uint64_t n_samples_total) {
 }
 
 static void set_scatter_attrs() {
-    SKA_CUDA(cudaFuncSetAttribute(part_scatter_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)scatter_smem(PT_MAX_BITS)));
-    SKA_CUDA(cudaFuncSetAttribute(part_scatter_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)scatter_smem(PT_MAX_BITS)));
+    static bool done = false;
+    if (done) return;
+    SKA_CUDA(cudaFuncSetAttribute(part_scatter_kernel<1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)scatter_smem(PT_MAX_BITS)));
+    SKA_CUDA(cudaFuncSetAttribute(part_scatter_kernel<2, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)scatter_smem(PT_MAX_BITS)));
+    SKA_CUDA(cudaFuncSetAttribute(part_scatter_kernel<1, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)scatter_smem(8)));
+    SKA_CUDA(cudaFuncSetAttribute(part_scatter_kernel<2, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)scatter_smem(8)));
+    done = true;
 }
 
 // pass 1.  rec: K1 output (n_pos entries, linear) -> packed records grouped by the top P1 key bits in `*out`
@@ -283,7 +317,7 @@ static void set_scatter_attrs() {
 void partition_coarse(const uint64_t* rec, uint64_t n_pos, const uint64_t* d_sample_off, uint32_t n_samples_local, uint32_t sid_base,
                       const PartPlan& pl, uint64_t** out, uint64_t** d_off1, uint64_t** d_tile_pref, const unsigned long long* k1_hist) {
     Context& c = ctx();
-    timer().begin("partition1");
+    timer().begin("hist1");
     const uint32_t D1 = 1u << pl.P1;
     unsigned long long* hist1 = arena().take_n<unsigned long long>(D1);
     unsigned long long* cur1 = arena().take_n<unsigned long long>(D1);
@@ -299,10 +333,16 @@ void partition_coarse(const uint64_t* rec, uint64_t n_pos, const uint64_t* d_sam
     if (n_pos && !k1_hist) SKA_LAUNCH(part_hist_kernel, hist_grid, PT_THREADS, D1 * 4, rec, n_pos, n_tiles1, none, f1, pl.P1, hist1);
     SKA_LAUNCH(part_scan_kernel, 1, 1024, 0, k1_hist ? k1_hist : (const unsigned long long*)hist1, D1, off1, cur1, tile_pref,
                k1_hist ? K1_HIST_COPIES : 1);
+    timer().end();
+    timer().begin("scatter1");
     uint64_t* a = arena().take_n<uint64_t>(std::max<uint64_t>(n_pos, 1));
     if (n_pos) {
-        SKA_LAUNCH((part_scatter_kernel<1>), (unsigned)n_tiles1, PT_THREADS, scatter_smem(pl.P1), rec, n_pos, none, f1, pl.P1, pk,
-                   d_sample_off, n_samples_local, cur1, a);
+        if (pl.P1 == 8)
+            SKA_LAUNCH((part_scatter_kernel<1, 8>), (unsigned)n_tiles1, SC_T, scatter_smem(pl.P1), rec, n_pos, none, f1, pl.P1, pk,
+                       d_sample_off, n_samples_local, cur1, a);
+        else
+            SKA_LAUNCH((part_scatter_kernel<1, 0>), (unsigned)n_tiles1, SC_T, scatter_smem(pl.P1), rec, n_pos, none, f1, pl.P1, pk,
+                       d_sample_off, n_samples_local, cur1, a);
     }
     *out = a; *d_off1 = off1; *d_tile_pref = tile_pref;
     timer().end();
@@ -313,7 +353,7 @@ void partition_coarse(const uint64_t* rec, uint64_t n_pos, const uint64_t* d_sam
 void partition_fine(const uint64_t* src, const Segs& sg, uint64_t n_tiles2, uint32_t n_regions, const PartPlan& pl, uint64_t* dst,
                     uint64_t** d_bucket_off) {
     Context& c = ctx();
-    timer().begin("partition2");
+    timer().begin("hist2");
     const uint32_t D2 = 1u << pl.P2;
     const size_t NB = (size_t)n_regions * D2;
     unsigned long long* hist2 = arena().take_n<unsigned long long>(std::max<size_t>(NB, 1));
@@ -328,9 +368,15 @@ void partition_fine(const uint64_t* src, const Segs& sg, uint64_t n_tiles2, uint
         SKA_LAUNCH(part_hist_kernel, g2, PT_THREADS, D2 * 4, src, (uint64_t)0, n_tiles2, sg, f2, pl.P2, hist2);
     }
     SKA_LAUNCH(part_scan_kernel, 1, 1024, 0, (const unsigned long long*)hist2, (uint32_t)NB, bucket_off, cur2, (uint64_t*)nullptr, 1);
+    timer().end();
+    timer().begin("scatter2");
     if (n_tiles2) {
-        SKA_LAUNCH((part_scatter_kernel<2>), (unsigned)n_tiles2, PT_THREADS, scatter_smem(pl.P2), src, (uint64_t)0, sg, f2, pl.P2, pk,
-                   (const uint64_t*)nullptr, 0u, cur2, dst);
+        if (pl.P2 == 8)
+            SKA_LAUNCH((part_scatter_kernel<2, 8>), (unsigned)n_tiles2, SC_T, scatter_smem(pl.P2), src, (uint64_t)0, sg, f2, pl.P2, pk,
+                       (const uint64_t*)nullptr, 0u, cur2, dst);
+        else
+            SKA_LAUNCH((part_scatter_kernel<2, 0>), (unsigned)n_tiles2, SC_T, scatter_smem(pl.P2), src, (uint64_t)0, sg, f2, pl.P2, pk,
+                       (const uint64_t*)nullptr, 0u, cur2, dst);
     }
     *d_bucket_off = bucket_off;
     timer().end();
