@@ -257,7 +257,14 @@ def run_ours(args, rank, world, local_rank):
     for s, g in zip(samples, genomes):
         assert s.seq.ctypes.data == g.ctypes.data
     names = [f"s{rank * G + i}" for i in range(G)]
-    log(f"generated {G} x {L} bp genomes ({population}) in pinned memory" + (f" (rank bound to CPUs {numa})" if numa else ""))
+    # the packing FASTA reader's output (skagpu_pack_bases): 2-bit codes + invalid mask in pinned memory, 0.375 B per base
+    pin2 = torch.empty((G, (L + 3) // 4), dtype=torch.uint8, pin_memory=True).numpy()
+    pinv = torch.empty((G, (L + 7) // 8), dtype=torch.uint8, pin_memory=True).numpy()
+    t_pack = time.perf_counter()
+    packed = [S.PackedSample.from_sample(s, pin2[i], pinv[i]) for i, s in enumerate(samples)]
+    t_pack = time.perf_counter() - t_pack
+    log(f"generated {G} x {L} bp genomes ({population}) in pinned memory, packed in {t_pack * 1e3:.0f} ms on one host thread "
+        f"({G * L / t_pack / 1e9:.2f} Gbase/s)" + (f" (rank bound to CPUs {numa})" if numa else ""))
     n_bases = G * L
     threshold = int(np.ceil(G * 0.9))                  # generic_modes.rs:121 with cli.rs default min_freq 0.9
 
@@ -282,7 +289,7 @@ def run_ours(args, rank, world, local_rank):
                                          timings=shard_t if os.environ.get("BENCH_SHARD_TIMINGS") else None)
 
     # ---------------- device-resident arm
-    batch = S.SeqBatch(samples)
+    batch = S.SeqBatch(samples if args.ascii else packed)
     log("batch uploaded")
     for _ in range(args.warmup):
         arr = build_device(batch)
@@ -344,38 +351,70 @@ def run_ours(args, rank, world, local_rank):
 
     # ---------------- end-to-end arm: pinned host buffers in, alignment bytes out
     e2e = None
+    e2e_serial = None
     if not args.no_e2e:
-        out_host = torch.empty((G * world, max(1, rows_aligned)), dtype=torch.uint8, pin_memory=True).numpy()
+        out_host = [torch.empty((G * world, max(1, rows_aligned)), dtype=torch.uint8, pin_memory=True).numpy() for _ in range(2)]
 
-        def e2e_step():
-            if world == 1:
-                arr = S.build_from_samples(samples, names, k, True)
+        prefetched = [None]
+
+        def e2e_step(i, host_samples, pipelined, last=False):
+            if pipelined and isinstance(host_samples[0], S.PackedSample):
+                # this step's batch was queued for upload during the previous step (the first one here); the NEXT step's
+                # upload is queued now, before this step's kernels, so that it crosses PCIe underneath them
+                cur = prefetched[0] or S.SeqBatch(host_samples, asynchronous=True)
+                prefetched[0] = None if last else S.SeqBatch(host_samples, asynchronous=True)
+                arr = build_device(cur)
+                del cur
+            elif world == 1:
+                arr = S.build_from_samples(host_samples, names, k, True)
             else:
-                arr = build_device(samples)                      # H2D of this rank's genomes inside the local build, then the exchange
+                arr = build_device(host_samples)                 # H2D of this rank's genomes inside the local build, then the exchange
             arr.filter(threshold, False, "no-const", False, False, False)
             r = arr.dims()["n_rows"]
             assert r == rows_aligned
-            arr.transposed(out=out_host)
+            if pipelined:
+                arr.transposed_async(out_host[i % 2])            # this copy overlaps the next step's upload and kernels
+            else:
+                arr.transposed(out=out_host[i % 2])
             return r
 
-        for _ in range(min(args.warmup, 2)):
-            e2e_step()
-        barrier()
-        S.api.timer_start()
-        walls = []
-        for _ in range(args.steps):
-            tw = time.perf_counter()
-            e2e_step()
-            walls.append(round((time.perf_counter() - tw) * 1e3, 1))
-        ms_e2e = S.api.timer_stop()
-        log(f"e2e per-step wall ms: {walls}; last build stages {[(s, round(ms, 2)) for s, ms, _ in S.api.last_timings()]}")
-        barrier()
-        ms_e2e = max_over_ranks(ms_e2e)
-        log(f"e2e arm: {ms_e2e / args.steps:.2f} ms/step")
-        h2d = n_bases + 8 * (2 * G + 1)                    # sequence bytes + record starts + sample offsets
+        def e2e_run(host_samples, pipelined, steps):
+            for i in range(min(args.warmup, 2)):
+                e2e_step(i, host_samples, pipelined, last=(i + 1 == min(args.warmup, 2)))
+            S.api.export_wait()
+            barrier()
+            S.api.timer_start()
+            walls = []
+            for i in range(steps):
+                tw = time.perf_counter()
+                e2e_step(i, host_samples, pipelined, last=(i + 1 == steps))    # exactly `steps` uploads and downloads in the timed region
+                walls.append(round((time.perf_counter() - tw) * 1e3, 1))
+            S.api.export_wait()                                  # every alignment is in host memory before the clock stops
+            ms = S.api.timer_stop()
+            log(f"e2e ({'packed' if isinstance(host_samples[0], S.PackedSample) else 'ascii'}, {'pipelined' if pipelined else 'serial'}) "
+                f"per-step wall ms: {walls}; last build stages {[(s, round(m, 2)) for s, m, _ in S.api.last_timings()]}")
+            barrier()
+            return max_over_ranks(ms) / steps
+
+        host_in = samples if args.ascii else packed
+        ms_e2e = e2e_run(host_in, True, args.steps)
+        log(f"e2e arm: {ms_e2e:.2f} ms/step")
+        in_bytes = n_bases if args.ascii else sum(len(p.packed2) + len(p.invalid) for p in packed)
+        h2d = in_bytes + 8 * (3 * G + 2)                   # sequence bytes + record boundaries + sample offsets
         d2h = G * world * rows_aligned + 4 * G + 24        # this rank's alignment slab + per-sample valid counts + scalars
-        e2e = {"value": args.steps * G * world / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
-               "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / args.steps}
+        e2e = {"value": G * world / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
+               "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e,
+               "input": ("ASCII bases in pinned memory" if args.ascii else
+                         "host-packed bases in pinned memory (2-bit codes + invalid mask, 0.375 B/base: the packing FASTA reader's "
+                         "output, skagpu_pack_bases; packing is parse work and not in the timed region)"),
+               "pipeline": "double-buffered: the upload of step i+1 (skagpu_seqbatch_upload_packed_async) and the device->host copy "
+                           "of step i-1 (skagpu_export_transposed_async) cross PCIe under the kernels of step i; every step's "
+                           "upload and download lie inside the timed region"}
+        if world == 1 and not args.ascii:
+            # round 1's form for comparison: ASCII in, every step strictly serial (upload -> kernels -> download)
+            ms_ser = e2e_run(samples, False, min(args.steps, 5))
+            e2e_serial = {"value": G / (ms_ser * 1e-3), "unit": UNIT, "ms_per_step": ms_ser, "h2d_bytes_per_step": n_bases + 8 * (2 * G + 1),
+                          "d2h_bytes_per_step": d2h, "input": "ASCII bases in pinned memory, no overlap between steps (round 1's e2e)"}
 
     # ---------------- CPU baseline beside it + oracle parity on the same sample (rank 0)
     cpu_baseline = None
@@ -418,11 +457,14 @@ def run_ours(args, rank, world, local_rank):
                     "frac": by / (ms * 1e-3) / 1e9 / peak, "traffic": ncu_traffic(NCU_NAMES.get(kern, "")) if full_size else None,
                     "peak_source": peak_src, "algorithmic_bytes_per_launch": by, "launch_ms": ms, "share_of_step": ms / step_ms}
 
+        STAGE_KERNELS["k1_extract"] = ("k1_extract_kernel", lambda n, R, C, Rk, N: (10.0 if args.ascii else 9.375) * n)
         # the dominant kernel = the single-kernel stage with the largest share of the step
         dom = max((s_ for s_ in st if s_ in STAGE_KERNELS), key=lambda s_: st[s_])
         k1 = roof("k1_extract")
-        k1.update({"achieved": K1_ALGO_BYTES_PER_BASE * n_bases / (k1_ms * 1e-3) / 1e9, "launch_ms": k1_ms,
-                   "note": "10 launches timed back to back inside the library (skagpu_k1_extract)"})
+        k1_bytes = (K1_ALGO_BYTES_PER_BASE if args.ascii else 9.375) * n_bases     # 0.375 B read per base when host-packed
+        k1.update({"achieved": k1_bytes / (k1_ms * 1e-3) / 1e9, "launch_ms": k1_ms, "algorithmic_bytes_per_launch": k1_bytes,
+                   "note": "the extraction kernel alone, 10 launches timed back to back inside the library (skagpu_k1_extract); "
+                           "inside a build the same kernel also fills the first partition histogram (stage k1_extract)"})
         k1["frac"] = k1["achieved"] / peak
         k1["frac_of_nominal_8TBs"] = k1["achieved"] / 8000.0
         # whole step against the roofline: SURVEY 8d's algorithmic bytes of K1 + K2/K3 + K4 (the partition is overhead)
@@ -450,6 +492,8 @@ def run_ours(args, rank, world, local_rank):
         }
         if e2e:
             line["e2e"] = e2e
+        if e2e_serial:
+            line["e2e_ascii_serial"] = e2e_serial
         if cpu_baseline:
             line["cpu_baseline"] = cpu_baseline
         print(json.dumps(line), flush=True)
@@ -477,6 +521,7 @@ def main():
     ap.add_argument("--ref-reps", type=int, default=1, help="timed passes of the --impl reference arm over the full job (~1 min each)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="skip the end-to-end arm (kernel A/B runs)")
+    ap.add_argument("--ascii", action="store_true", help="feed ASCII bases (1 B/base) instead of host-packed bases (0.375 B/base)")
     ap.add_argument("--population", default="tree", choices=["star", "tree"],
                     help="SURVEY 8d generator.  tree (default at every N, so that the 1 -> 8 GPU curve is like for like): the "
                          "samples are leaves of a balanced tree over all N x 128 genomes, every leaf 0.1%% from the root; "

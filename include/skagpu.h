@@ -76,6 +76,29 @@ int skagpu_build_from_batch(const ska_seqbatch_t* batch, uint32_t k, int rc, uin
                             uint8_t min_qual, int qual_filter, ska_array_t** out);
 void skagpu_seqbatch_free(ska_seqbatch_t* batch);
 
+/* The same build from HOST-PACKED assemblies: what crosses PCIe is 0.375 B per base instead of 1.  The FASTA
+ * reader (needletail's place, ska_dict.rs:131-147) packs every record as it parses it:
+ *   packed2: the 2-bit code (b >> 1) & 3 of encode_base (bit_encoding.rs:34-36), base i of the sample at bits 2(i%4) of byte i/4;
+ *   invalid: 1 bit per base, base i at bit i%8 of byte i/8, set iff (b & 0xF) == 14 -- !valid_base (bit_encoding.rs:52-54);
+ *            the unused high bits of the last byte MUST be set.
+ * Records of a sample lie back to back in base space (rec_off in bases, rec_off[0] == 0).  FASTA input only (no qualities,
+ * no --proportion-reads), k <= 31.  skagpu_pack_bases is the host helper that fills both streams for bases
+ * [first, first + n) of a sample from ASCII (buffers preset: packed2 anything, invalid 0xFF). */
+typedef struct {
+    const uint8_t* packed2;
+    const uint8_t* invalid;
+    const uint64_t* rec_off;
+    uint64_t n_rec;
+    uint64_t n_rec_file1;
+} ska_input_packed_t;
+void skagpu_pack_bases(const uint8_t* ascii, uint64_t n, uint64_t first, uint8_t* packed2, uint8_t* invalid);
+int skagpu_build_packed(const ska_input_packed_t* inputs, size_t n_samples, uint32_t k, int rc, ska_array_t** out);
+int skagpu_seqbatch_upload_packed(const ska_input_packed_t* inputs, size_t n_samples, ska_seqbatch_t** out);
+/* Pipelines of builds: the copies are queued on the library's copy stream and the call returns at once, so the batch
+ * crosses PCIe under the kernels of builds that are already queued; skagpu_build_from_batch on it waits for the bytes.
+ * The host buffers must stay valid (and unchanged) until that build has returned. */
+int skagpu_seqbatch_upload_packed_async(const ska_input_packed_t* inputs, size_t n_samples, ska_seqbatch_t** out);
+
 /* MergeSkaArray::<IntT>::load (merge_ska_array.rs:199-204) once the host has decoded the .skf:
  * keys are little-endian u64 (key_bits 64) or (lo,hi) u64 pairs (key_bits 128). n_keys may exceed
  * n_rows only for arrays exported after a filter with update_kmers=false. */
@@ -102,6 +125,14 @@ int skagpu_export(const ska_array_t* a, void* keys, uint8_t* variants_rowmajor, 
 /* write_fasta's transpose (merge_ska_array.rs:499-503): (n_samples x n_rows) row-major.
  * samples_by_rows == NULL: the transpose is computed on the device and dropped (device-only timing). */
 int skagpu_export_transposed(const ska_array_t* a, uint8_t* samples_by_rows);
+
+/* Pipelined form for a stream of builds (one batch after another, e.g. `ska align` over many batches): the transpose is
+ * queued on the library stream and the copy to `samples_by_rows` (pinned host memory, skagpu_host_alloc) on a second
+ * stream behind it; the call returns at once, so the next skagpu_build* overlaps its upload and kernels with this copy.
+ * skagpu_export_wait blocks until every pending export has reached host memory.  The array may be freed right after
+ * the call; the host buffer must stay valid until skagpu_export_wait returns. */
+int skagpu_export_transposed_async(const ska_array_t* a, uint8_t* samples_by_rows);
+int skagpu_export_wait(void);
 
 void skagpu_free(ska_array_t* a);
 

@@ -34,6 +34,8 @@ EXPORTS = [
     "skagpu_launch_count", "skagpu_k1_extract", "skagpu_stream_timer", "skagpu_extract_records", "skagpu_records_info",
     "skagpu_records_free", "skagpu_merge_records_dev", "skagpu_distance_counters", "skagpu_merge_prefix_bits",
     "skagpu_array_dev", "skagpu_key_cumulative", "skagpu_merge_partial_rows_dev", "skagpu_array_checksum",
+    "skagpu_pack_bases", "skagpu_build_packed", "skagpu_seqbatch_upload_packed", "skagpu_export_transposed_async",
+    "skagpu_export_wait", "skagpu_seqbatch_upload_packed_async",
 ]
 
 
@@ -72,6 +74,7 @@ def lib():
         L.skagpu_distance.argtypes = [C.c_void_p, C.c_double, C.c_int, C.c_void_p]
         L.skagpu_export.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.skagpu_export_transposed.argtypes = [C.c_void_p, C.c_void_p]
+        L.skagpu_export_transposed_async.argtypes = [C.c_void_p, C.c_void_p]
         L.skagpu_free.argtypes = [C.c_void_p]
         L.skagpu_host_alloc.restype = C.c_void_p
         L.skagpu_host_alloc.argtypes = [C.c_size_t]
@@ -91,6 +94,11 @@ def lib():
                                                     C.c_void_p, C.c_uint64, C.c_uint32, C.c_int, C.c_void_p]
         L.skagpu_distance_counters.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
         L.skagpu_array_checksum.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p]
+        L.skagpu_pack_bases.restype = None
+        L.skagpu_pack_bases.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.c_void_p, C.c_void_p]
+        L.skagpu_build_packed.argtypes = [C.c_void_p, C.c_size_t, C.c_uint32, C.c_int, C.c_void_p]
+        L.skagpu_seqbatch_upload_packed.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p]
+        L.skagpu_seqbatch_upload_packed_async.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p]
         L.skagpu_k1_extract.argtypes = [C.c_void_p, C.c_uint32, C.c_int, C.c_uint8, C.c_int, C.c_int, C.c_void_p,
                                         C.c_void_p, C.c_void_p]
         _lib = L
@@ -104,6 +112,10 @@ def _check(rc):
 
 def set_device(device):
     _check(lib().skagpu_set_device(int(device)))
+
+
+def export_wait():
+    _check(lib().skagpu_export_wait())
 
 
 def timer_start():
@@ -233,6 +245,45 @@ class Sample:
         return cls(np.frombuffer(b"".join(bytes(s) for s in seqs), dtype=np.uint8), off)
 
 
+class _InputPacked(C.Structure):
+    _fields_ = [("packed2", C.c_void_p), ("invalid", C.c_void_p), ("rec_off", C.c_void_p), ("n_rec", C.c_uint64),
+                ("n_rec_file1", C.c_uint64)]
+
+
+class PackedSample:
+    """One assembly as the packing FASTA reader hands it over (ska_input_packed_t): 2-bit codes, 4 bases per byte, and
+    the invalid-base mask, 8 bases per byte; records back to back in base space."""
+
+    def __init__(self, packed2, invalid, rec_off):
+        self.packed2, self.invalid = packed2, invalid
+        self.rec_off = np.ascontiguousarray(rec_off, dtype=np.uint64)
+        self.n_rec = len(self.rec_off) - 1
+        self.n_rec_file1 = self.n_rec
+        self.n_bases = int(self.rec_off[-1])
+
+    @classmethod
+    def from_sample(cls, sample, packed2=None, invalid=None):
+        """pack an ASCII Sample with the library's host helper (skagpu_pack_bases); optional preallocated (pinned) outputs"""
+        n = int(sample.rec_off[-1] - sample.rec_off[0])
+        p2 = np.zeros((n + 3) // 4, dtype=np.uint8) if packed2 is None else packed2
+        inv = np.empty((n + 7) // 8, dtype=np.uint8) if invalid is None else invalid
+        inv[:] = 0xFF
+        seq = sample.seq[int(sample.rec_off[0]):]
+        lib().skagpu_pack_bases(seq.ctypes.data, n, 0, p2.ctypes.data, inv.ctypes.data)
+        return cls(p2, inv, sample.rec_off - sample.rec_off[0])
+
+
+def _packed_inputs_array(samples):
+    arr = (_InputPacked * len(samples))()
+    for i, s in enumerate(samples):
+        arr[i].packed2 = s.packed2.ctypes.data
+        arr[i].invalid = s.invalid.ctypes.data
+        arr[i].rec_off = s.rec_off.ctypes.data
+        arr[i].n_rec = s.n_rec
+        arr[i].n_rec_file1 = s.n_rec_file1
+    return arr
+
+
 def _inputs_array(samples):
     arr = (_Input * len(samples))()
     for i, s in enumerate(samples):
@@ -247,11 +298,16 @@ def _inputs_array(samples):
 class SeqBatch:
     """Sequence bytes of a set of samples resident in HBM (skagpu_seqbatch_upload)."""
 
-    def __init__(self, samples, proportion_reads=None):
+    def __init__(self, samples, proportion_reads=None, asynchronous=False):
         h = C.c_void_p()
         self._keep = samples
-        _check(lib().skagpu_seqbatch_upload(_inputs_array(samples), len(samples),
-                                            float(proportion_reads) if proportion_reads else 0.0, C.byref(h)))
+        if samples and isinstance(samples[0], PackedSample):
+            fn = lib().skagpu_seqbatch_upload_packed_async if asynchronous else lib().skagpu_seqbatch_upload_packed
+            self._inputs = _packed_inputs_array(samples)
+            _check(fn(self._inputs, len(samples), C.byref(h)))
+        else:
+            _check(lib().skagpu_seqbatch_upload(_inputs_array(samples), len(samples),
+                                                float(proportion_reads) if proportion_reads else 0.0, C.byref(h)))
         self._h = h
 
     def __del__(self):
@@ -267,7 +323,10 @@ class SeqBatch:
         n = C.c_uint64()
         ms = C.c_float()
         qf = QUAL_FILTERS[qual_filter] if isinstance(qual_filter, str) else qual_filter
-        total = int(sum(len(s.seq) for s in self._keep))
+        if self._keep and isinstance(self._keep[0], PackedSample):      # position space with 32-aligned sample starts
+            total = int(sum((s.n_bases + 31) // 32 * 32 for s in self._keep))
+        else:
+            total = int(sum(len(s.seq) for s in self._keep))
         rec = np.empty(total, dtype=np.uint64) if want_records else None
         _check(lib().skagpu_k1_extract(self._h, k, int(rc), min_qual, qf, iters,
                                        rec.ctypes.data if rec is not None else None, C.byref(n), C.byref(ms)))
@@ -391,6 +450,10 @@ class MergeSkaArray:
         _check(lib().skagpu_export_transposed(self._h, t.ctypes.data))
         return t
 
+    def transposed_async(self, out):
+        """queue transpose + copy to the pinned array `out`; export_wait() completes it (skagpu_export_transposed_async)"""
+        _check(lib().skagpu_export_transposed_async(self._h, out.ctypes.data))
+
     def write_fasta(self, f):
         t = self.transposed()
         for i, name in enumerate(self._names):
@@ -444,6 +507,13 @@ def build_from_samples(samples, names, k, rc, qual=None, proportion_reads=None):
     qf = QUAL_FILTERS[qual.qual_filter] if isinstance(qual.qual_filter, str) else qual.qual_filter
     _check(lib().skagpu_build(_inputs_array(samples), len(samples), k, int(rc), qual.min_count, qual.min_qual, qf,
                               float(proportion_reads) if proportion_reads else 0.0, C.byref(h)))
+    return MergeSkaArray(h, names)
+
+
+def build_from_packed(samples, names, k, rc):
+    """skagpu_build_packed: host-packed assemblies (PackedSample) -> array; K1 runs behind the (4x smaller) upload"""
+    h = C.c_void_p()
+    _check(lib().skagpu_build_packed(_packed_inputs_array(samples), len(samples), k, int(rc), C.byref(h)))
     return MergeSkaArray(h, names)
 
 

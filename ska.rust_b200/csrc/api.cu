@@ -174,7 +174,7 @@ static std::unique_ptr<SeqBatch> upload(const ska_input_t* in, size_t n, double 
                 SKA_CUDA(cudaEventRecord(ev, c.copy_stream));
                 SKA_CUDA(cudaStreamWaitEvent(c.stream, ev, 0));
                 chunk_events.push_back(ev);
-                const uint64_t ready = (s + 1 == n) ? ~0ULL : k1_tiles_ready(b->h_sample_off[s + 1]);
+                const uint64_t ready = (s + 1 == n) ? ~0ULL : k1_tiles_ready(b->h_sample_off[s + 1], K1_ASCII_TAIL);
                 if (ready > ov->tiles_done) {
                     launch_k1(*b, ov->k, ov->rc, false, ov->min_qual, ov->rec, nullptr, ov->valid, 0, ov->hist, ov->hist_shift, ov->hist_bits,
                               ov->tiles_done, ready);
@@ -226,6 +226,109 @@ static std::unique_ptr<SeqBatch> upload(const ska_input_t* in, size_t n, double 
     return b;
 }
 
+// Host-packed FASTA batches (skagpu_build_packed / skagpu_seqbatch_upload_packed): 2-bit codes + invalid mask cross PCIe
+// (0.375 B per base instead of 1).  Every sample starts on a 32-position boundary of the batch's position space (so that its
+// bytes of both streams land on byte boundaries); the gaps are invalid positions, and record ENDS are marked like record
+// starts, so that "a run of exactly k valid bases at its record's end yields nothing" (split_kmer.rs:89,121) still sees
+// the end of a record that is followed by a gap.
+static std::unique_ptr<SeqBatch> upload_packed(const ska_input_packed_t* in, size_t n, K1Overlap* ov, bool async = false) {
+    Context& c = ctx();
+    c.ensure();
+    if (n == 0) throw Error("no input samples");
+    if (n > 65535) throw Error("at most 65535 samples per build (16-bit sample ids)");
+    std::unique_ptr<SeqBatch> b(new SeqBatch());
+    b->n_samples = n; b->packed = true;
+    b->h_sample_off.assign(n + 1, 0);
+    uint64_t n_rec_total = 0;
+    for (size_t s = 0; s < n; s++) {
+        if (in[s].n_rec == 0 || !in[s].rec_off || !in[s].packed2 || !in[s].invalid) throw Error("Invalid FASTA/Q record");
+        if (in[s].rec_off[0] != 0) throw Error("packed samples start at base 0 (rec_off[0] must be 0)");
+        const uint64_t len = in[s].rec_off[in[s].n_rec];
+        b->h_sample_off[s + 1] = ((b->h_sample_off[s] + len + 31) / 32) * 32;
+        n_rec_total += in[s].n_rec;
+    }
+    b->n_pos = b->h_sample_off[n];
+    const size_t padded = padded_positions(b->n_pos);
+    b->seq.alloc(padded / 4); b->qual.alloc(padded / 8);
+    SKA_CUDA(cudaMemsetAsync(b->seq.p, 0, padded / 4, c.stream));
+    SKA_CUDA(cudaMemsetAsync(b->qual.p, 0xFF, padded / 8, c.stream));          // everything invalid until a sample says otherwise
+    std::vector<uint64_t>& marks = b->h_marks;                      // lives with the batch: an asynchronous upload returns before it is copied
+    marks.reserve(2 * n_rec_total + 1);
+    for (size_t s = 0; s < n; s++) {
+        const uint64_t base = b->h_sample_off[s];
+        for (uint64_t r = 0; r < in[s].n_rec; r++) {
+            if (in[s].rec_off[r + 1] < in[s].rec_off[r]) throw Error("record offsets must ascend");
+            marks.push_back(base + in[s].rec_off[r]);
+            marks.push_back(base + in[s].rec_off[r + 1]);
+        }
+    }
+    marks.push_back(b->n_pos);
+    b->start_bits.alloc(padded / 32 + 1);
+    SKA_CUDA(cudaMemsetAsync(b->start_bits.p, 0, b->start_bits.bytes(), c.stream));
+    DevBuf<uint64_t> d_marks(marks.size());
+    SKA_CUDA(cudaMemcpyAsync(d_marks.p, marks.data(), marks.size() * 8, cudaMemcpyHostToDevice, c.stream));
+    SKA_LAUNCH(set_start_bits_kernel, (unsigned)((marks.size() + 255) / 256), 256, 0, d_marks.p, (uint64_t)marks.size(), b->start_bits.p);
+    b->sample_off.alloc(n + 1);
+    SKA_CUDA(cudaMemcpyAsync(b->sample_off.p, b->h_sample_off.data(), (n + 1) * 8, cudaMemcpyHostToDevice, c.stream));
+    cudaEvent_t ev_prep;
+    SKA_CUDA(cudaEventCreateWithFlags(&ev_prep, cudaEventDisableTiming));
+    SKA_CUDA(cudaEventRecord(ev_prep, c.stream));
+    SKA_CUDA(cudaStreamWaitEvent(c.copy_stream, ev_prep, 0));       // the buffers were allocated and cleared in library-stream order
+    std::vector<cudaEvent_t> chunk_events;
+    uint64_t chunk_bytes = 0;
+    // samples that lie back to back on both sides (one pinned block on the host, whole bytes on the device) travel as ONE copy:
+    // PCIe moves 1 MB pieces at 46 GB/s (34 with traffic in the other direction), 8 MB pieces at 54 (49)  [profiles/microbench/pcie_mb.cu]
+    struct Run { uint8_t* dst = nullptr; const uint8_t* src = nullptr; size_t bytes = 0; } run2, run1;
+    auto flush = [&](Run& r) {
+        if (r.bytes) SKA_CUDA(cudaMemcpyAsync(r.dst, r.src, r.bytes, cudaMemcpyHostToDevice, c.copy_stream));
+        r = Run();
+    };
+    auto add = [&](Run& r, uint8_t* dst, const uint8_t* src, size_t bytes) {
+        if (r.bytes && r.dst + r.bytes == dst && r.src + r.bytes == src) { r.bytes += bytes; return; }
+        flush(r);
+        r.dst = dst; r.src = src; r.bytes = bytes;
+    };
+    const uint64_t chunk_limit = ov ? OVERLAP_CHUNK_BYTES / 2 : (uint64_t)16 << 20;
+    for (size_t s = 0; s < n; s++) {
+        const uint64_t base = b->h_sample_off[s], len = in[s].rec_off[in[s].n_rec];
+        if (len) {
+            add(run2, b->seq.p + (FRONT_PAD + base) / 4, in[s].packed2, (len + 3) / 4);
+            add(run1, b->qual.p + (FRONT_PAD + base) / 8, in[s].invalid, (len + 7) / 8);
+        }
+        chunk_bytes += (len + 3) / 4 + (len + 7) / 8;
+        if (chunk_bytes >= chunk_limit || s + 1 == n) {
+            flush(run2); flush(run1);
+            if (async) { chunk_bytes = 0; continue; }
+            cudaEvent_t ev;
+            SKA_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+            SKA_CUDA(cudaEventRecord(ev, c.copy_stream));
+            SKA_CUDA(cudaStreamWaitEvent(c.stream, ev, 0));
+            chunk_events.push_back(ev);
+            if (ov) {
+                const uint64_t ready = (s + 1 == n) ? ~0ULL : k1_tiles_ready(b->h_sample_off[s + 1], K1_PACKED_TAIL);
+                if (ready > ov->tiles_done) {
+                    launch_k1(*b, ov->k, ov->rc, false, ov->min_qual, ov->rec, nullptr, ov->valid, 0, ov->hist, ov->hist_shift, ov->hist_bits,
+                              ov->tiles_done, ready);
+                    ov->tiles_done = ready;
+                }
+            }
+            chunk_bytes = 0;
+        }
+    }
+    cudaEventDestroy(ev_prep);
+    if (async) {
+        // the library stream must not wait here: builds already queued keep running while this batch crosses PCIe; the
+        // build that consumes the batch waits for `ready`
+        SKA_CUDA(cudaEventCreateWithFlags(&b->ready, cudaEventDisableTiming));
+        SKA_CUDA(cudaEventRecord(b->ready, c.copy_stream));
+        for (cudaEvent_t e : chunk_events) cudaEventDestroy(e);
+        return b;
+    }
+    SKA_CUDA(cudaStreamSynchronize(c.stream));                     // K1 (or the last copy) is done
+    for (cudaEvent_t e : chunk_events) cudaEventDestroy(e);
+    return b;
+}
+
 // records (and K1's histogram) already extracted while the batch was uploaded: partition + merge
 static std::unique_ptr<Array> build_from_extracted(const SeqBatch& b, uint32_t k, bool rc, const PartPlan& pl, const K1Overlap& ov) {
     Context& c = ctx();
@@ -243,6 +346,7 @@ static std::unique_ptr<Array> build_from_batch(const SeqBatch& b, uint32_t k, bo
     Context& c = ctx();
     check_k(k);
     if (k > 31) throw Error("k > 31 (128-bit split k-mers) is not yet built on the device; use k <= 31");
+    if (b.ready) SKA_CUDA(cudaStreamWaitEvent(c.stream, b.ready, 0));   // asynchronous upload: the bytes may still be crossing PCIe
     arena().reset();
     if (b.has_qual) {                                              // reads: quality masks + count filter (k1q_reads.cu)
         std::unique_ptr<Array> a(new Array());
@@ -375,6 +479,93 @@ int skagpu_build(const ska_input_t* inputs, size_t n_samples, uint32_t k, int rc
     API_CATCH
 }
 
+// K1 behind the copies of a host-packed batch, then partition + merge
+static std::unique_ptr<Array> build_packed(const ska_input_packed_t* inputs, size_t n_samples, uint32_t k, bool rc) {
+    check_k(k);
+    if (k > 31) throw Error("k > 31 (128-bit split k-mers): use skagpu_build (ASCII input)");
+    uint64_t n_pos = 0;
+    for (size_t s = 0; s < n_samples; s++) {
+        if (!inputs[s].rec_off || !inputs[s].n_rec) throw Error("Invalid FASTA/Q record");
+        n_pos = ((n_pos + inputs[s].rec_off[inputs[s].n_rec] + 31) / 32) * 32;
+    }
+    if (n_pos == 0) throw Error("sample 0 has no valid sequence");
+    arena().reset();
+    const PartPlan pl = make_part_plan(k, merge_prefix_bits(n_pos, k, n_samples), n_samples);
+    K1Overlap ov;
+    ov.k = k; ov.rc = rc; ov.min_qual = 0;
+    ov.rec = arena().take_n<uint64_t>(n_pos);
+    ov.valid = arena().take_n<uint32_t>(n_samples);
+    ov.hist = arena().take_n<unsigned long long>((size_t)K1_HIST_COPIES << pl.P1);
+    ov.hist_shift = 4 + pl.key_bits - pl.P1; ov.hist_bits = pl.P1;
+    SKA_CUDA(cudaMemsetAsync(ov.valid, 0, n_samples * 4, ctx().stream));
+    SKA_CUDA(cudaMemsetAsync(ov.hist, 0, ((size_t)K1_HIST_COPIES << pl.P1) * 8, ctx().stream));
+    timer().begin("h2d+k1");
+    std::unique_ptr<SeqBatch> b = upload_packed(inputs, n_samples, &ov);
+    timer().end();
+    return build_from_extracted(*b, k, rc, pl, ov);
+}
+
+int skagpu_build_packed(const ska_input_packed_t* inputs, size_t n_samples, uint32_t k, int rc, ska_array_t** out) {
+    API_TRY
+    *out = nullptr;
+    ctx().ensure();
+    timer().clear();
+    std::unique_ptr<Array> a = build_packed(inputs, n_samples, k, rc != 0);
+    std::unique_ptr<ska_array> h(new ska_array());
+    h->a = std::move(*a);
+    *out = h.release();
+    return 0;
+    API_CATCH
+}
+
+int skagpu_seqbatch_upload_packed(const ska_input_packed_t* inputs, size_t n_samples, ska_seqbatch_t** out) {
+    API_TRY
+    *out = nullptr;
+    std::unique_ptr<ska_seqbatch> h(new ska_seqbatch());
+    h->b = upload_packed(inputs, n_samples, nullptr);
+    *out = h.release();
+    return 0;
+    API_CATCH
+}
+
+int skagpu_seqbatch_upload_packed_async(const ska_input_packed_t* inputs, size_t n_samples, ska_seqbatch_t** out) {
+    API_TRY
+    *out = nullptr;
+    std::unique_ptr<ska_seqbatch> h(new ska_seqbatch());
+    h->b = upload_packed(inputs, n_samples, nullptr, true);
+    *out = h.release();
+    return 0;
+    API_CATCH
+}
+
+// CPU helper of the host side (no device work): what a FASTA reader calls on every record it parses.
+// positions first .. first + n - 1 of the sample; `first` need not be byte aligned (records are packed back to back)
+static inline void pack_one(uint8_t ch, uint64_t p, uint8_t* packed2, uint8_t* invalid) {
+    const uint8_t code = (ch >> 1) & 3;                              // bit_encoding.rs:34-36
+    const int sh2 = 2 * (int)(p & 3), sh1 = (int)(p & 7);
+    packed2[p >> 2] = (uint8_t)((packed2[p >> 2] & ~(3u << sh2)) | (code << sh2));
+    if ((ch & 0xF) == 14) invalid[p >> 3] |= (uint8_t)(1u << sh1);     // bit_encoding.rs:52-54
+    else invalid[p >> 3] &= (uint8_t)~(1u << sh1);
+}
+void skagpu_pack_bases(const uint8_t* ascii, uint64_t n, uint64_t first, uint8_t* packed2, uint8_t* invalid) {
+    uint64_t i = 0;
+    while (i < n && ((first + i) & 7)) { pack_one(ascii[i], first + i, packed2, invalid); i++; }
+    // 8 bases -> 2 bytes of codes + 1 byte of mask, SWAR on one 64-bit load
+    for (; i + 8 <= n; i += 8) {
+        uint64_t w; memcpy(&w, ascii + i, 8);
+        uint64_t c = (w >> 1) & 0x0303030303030303ULL;              // one 2-bit code per byte
+        c = (c | (c >> 6)) & 0x000F000F000F000FULL;                  // two codes per 16 bits
+        c = (c | (c >> 12)) & 0x000000FF000000FFULL;                 // four codes per 32 bits
+        const uint64_t p = first + i;
+        packed2[p >> 2] = (uint8_t)c; packed2[(p >> 2) + 1] = (uint8_t)(c >> 32);
+        const uint64_t t = (w & 0x0F0F0F0F0F0F0F0FULL) ^ 0x0E0E0E0E0E0E0E0EULL;           // zero byte <=> invalid base
+        uint64_t z = ~(t + 0x7F7F7F7F7F7F7F7FULL) & 0x8080808080808080ULL;               // (low nibbles only: no carry between bytes)
+        z = (z >> 7) * 0x0102040810204080ULL;                        // gather the 8 flags into the top byte
+        invalid[p >> 3] = (uint8_t)(z >> 56);
+    }
+    for (; i < n; i++) pack_one(ascii[i], first + i, packed2, invalid);
+}
+
 int skagpu_array_from_host(uint32_t k, int rc, uint32_t key_bits, uint64_t n_rows, uint64_t n_samples, const void* keys,
                            const uint8_t* variants, const uint64_t* counts, ska_array_t** out) {
     API_TRY
@@ -467,6 +658,84 @@ int skagpu_export_transposed(const ska_array_t* h, uint8_t* out) {
     transpose_array(a, t.p);
     if (out) SKA_CUDA(cudaMemcpyAsync(out, t.p, t.bytes(), cudaMemcpyDeviceToHost, c.stream));
     SKA_CUDA(cudaStreamSynchronize(c.stream));
+    return 0;
+    API_CATCH
+}
+
+// ---- pipelined export: the copy of one build's alignment to the host overlaps the next build's upload and kernels.
+// The bytes are pushed by a few CTAs storing straight into the (mapped) pinned host buffer, on a high-priority stream of
+// their own -- NOT by the copy engine: that engine serves its queue in order, and the few-byte read-backs of the next build
+// (bucket counts, row totals) would sit behind the whole 400 MB transfer while the GPU idles (measured: 21.5 ms per step
+// against 14.4 ms of kernels).
+__global__ void __launch_bounds__(256)
+push_to_host_kernel(const uint4* __restrict__ src, uint4* __restrict__ dst, size_t n16, const uint8_t* __restrict__ src_tail, uint8_t* __restrict__ dst_tail,
+                    uint32_t n_tail) {
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += stride) dst[i] = __ldcs(src + i);
+    if (blockIdx.x == 0 && threadIdx.x < n_tail) dst_tail[threadIdx.x] = src_tail[threadIdx.x];
+}
+
+struct PendingExport { DevBuf<uint8_t> t; cudaEvent_t done; };
+static std::vector<std::unique_ptr<PendingExport>> g_exports;
+static cudaStream_t g_d2h_stream = nullptr;
+static void reap_exports(bool all) {
+    Context& c = ctx();
+    for (size_t i = 0; i < g_exports.size();) {
+        PendingExport& e = *g_exports[i];
+        if (all) SKA_CUDA(cudaEventSynchronize(e.done));
+        else if (cudaEventQuery(e.done) != cudaSuccess) { i++; continue; }
+        SKA_CUDA(cudaStreamWaitEvent(c.stream, e.done, 0));        // the buffer goes back to the pool in library-stream order
+        cudaEventDestroy(e.done);
+        g_exports.erase(g_exports.begin() + i);
+    }
+}
+
+int skagpu_export_transposed_async(const ska_array_t* h, uint8_t* out) {
+    API_TRY
+    if (!h || !out) throw Error("null argument");
+    Context& c = ctx();
+    c.ensure();
+    if (!g_d2h_stream) {
+        int lo = 0, hi = 0;
+        SKA_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+        SKA_CUDA(cudaStreamCreateWithPriority(&g_d2h_stream, cudaStreamNonBlocking, hi));   // its few CTAs get in between the build's kernels
+    }
+    reap_exports(false);
+    while (g_exports.size() >= 3) { SKA_CUDA(cudaEventSynchronize(g_exports.front()->done)); reap_exports(false); }
+    const Array& a = h->a;
+    if (a.n_rows * a.n_samples == 0) return 0;
+    std::unique_ptr<PendingExport> e(new PendingExport());
+    e->t.alloc(a.n_rows * a.n_samples);
+    transpose_array(a, e->t.p);
+    cudaEvent_t ready;
+    SKA_CUDA(cudaEventCreateWithFlags(&ready, cudaEventDisableTiming));
+    SKA_CUDA(cudaEventRecord(ready, c.stream));
+    SKA_CUDA(cudaStreamWaitEvent(g_d2h_stream, ready, 0));
+    void* out_dev = nullptr;
+    const bool mapped = !getenv("SKA_EXPORT_COPY_ENGINE") && cudaHostGetDevicePointer(&out_dev, out, 0) == cudaSuccess && out_dev &&
+                        ((uintptr_t)out_dev & 15) == 0;
+    if (mapped) {
+        const size_t n16 = e->t.bytes() / 16;
+        push_to_host_kernel<<<32, 256, 0, g_d2h_stream>>>(reinterpret_cast<const uint4*>(e->t.p), reinterpret_cast<uint4*>(out_dev), n16,
+                                                          e->t.p + n16 * 16, (uint8_t*)out_dev + n16 * 16, (uint32_t)(e->t.bytes() - n16 * 16));
+        c.launches++;
+        SKA_CUDA(cudaGetLastError());
+    } else {
+        (void)cudaGetLastError();                                // pageable destination: the copy engine it is
+        SKA_CUDA(cudaMemcpyAsync(out, e->t.p, e->t.bytes(), cudaMemcpyDeviceToHost, g_d2h_stream));
+    }
+    SKA_CUDA(cudaEventCreateWithFlags(&e->done, cudaEventDisableTiming));
+    SKA_CUDA(cudaEventRecord(e->done, g_d2h_stream));
+    cudaEventDestroy(ready);
+    g_exports.push_back(std::move(e));
+    return 0;
+    API_CATCH
+}
+
+int skagpu_export_wait(void) {
+    API_TRY
+    ctx().ensure();
+    reap_exports(true);
     return 0;
     API_CATCH
 }

@@ -110,11 +110,19 @@ struct SeqBatch {
     uint64_t n_pos = 0;               // total bases over all samples
     uint64_t n_samples = 0;
     bool has_qual = false;
+    bool packed = false;              // host-packed batch (skagpu_build_packed): seq = 2-bit codes (4 positions per byte),
+                                      // qual = invalid-base mask (8 positions per byte); samples start on 32-position boundaries
     DevBuf<uint8_t> seq;              // padded_positions(n_pos) bytes, pads are 'N'
     DevBuf<uint8_t> qual;             // same layout when has_qual
     DevBuf<uint32_t> start_bits;      // bit p set <=> a record starts at position p; bit n_pos set
     DevBuf<uint64_t> sample_off;      // n_samples + 1 positions
     std::vector<uint64_t> h_sample_off;
+    std::vector<uint64_t> h_marks;    // record boundaries (host copy kept while an asynchronous upload reads it)
+    cudaEvent_t ready = nullptr;      // asynchronous upload: recorded behind the last copy; builds wait for it
+    SeqBatch() {}
+    SeqBatch(const SeqBatch&) = delete;
+    SeqBatch& operator=(const SeqBatch&) = delete;
+    ~SeqBatch() { if (ready) { cudaEventSynchronize(ready); cudaEventDestroy(ready); } }
 };
 
 // Device-resident MergeSkaArray.
@@ -137,7 +145,8 @@ constexpr int K1_HIST_MAX_BITS = 11;
 void launch_k1(const SeqBatch& b, uint32_t k, bool rc, bool strict_qual, uint8_t min_qual, uint64_t* rec_out,
                uint16_t* sid_out, uint32_t* sample_valid, uint32_t sid_base = 0, unsigned long long* hist = nullptr,
                int hist_shift = 0, int hist_bits = 0, uint64_t tile_begin = 0, uint64_t tile_end = ~0ULL /* tiles of 4096 positions */);
-uint64_t k1_tiles_ready(uint64_t positions_uploaded);
+constexpr int K1_ASCII_TAIL = 96, K1_PACKED_TAIL = 128;   // staged positions after a tile (k1_helpers.cuh)
+uint64_t k1_tiles_ready(uint64_t positions_uploaded, int tail);
 size_t padded_positions(uint64_t n_pos);
 // partition.cu: how records are grouped and packed.  P = P1 + P2 prefix bits of the key select the bucket;
 // inside a bucket a record is  key_low << (sb+2) | sample_id << 2 | middle_code  (key_low = key without its top P1 bits)

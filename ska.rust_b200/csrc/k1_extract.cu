@@ -25,9 +25,10 @@
 
 namespace ska {
 
-uint64_t k1_tiles_ready(uint64_t positions_uploaded) {      // tiles whose staged bytes (tile + tail halo) lie below that position
-    return positions_uploaded < (uint64_t)K1_T + K1_TAIL ? 0 : (positions_uploaded - K1_TAIL) / K1_T;
+uint64_t k1_tiles_ready(uint64_t positions_uploaded, int tail) {      // tiles whose staged bytes (tile + tail halo) lie below that position
+    return positions_uploaded < (uint64_t)K1_T + tail ? 0 : (positions_uploaded - tail) / K1_T;
 }
+static_assert(K1_ASCII_TAIL == K1_TAIL && K1_PACKED_TAIL == K1P_TAIL, "tile tails");
 
 size_t padded_positions(uint64_t n_pos) { return FRONT_PAD + ((n_pos + K1_T - 1) / K1_T) * K1_T + 256; }
 
@@ -35,7 +36,10 @@ size_t padded_positions(uint64_t n_pos) { return FRONT_PAD + ((n_pos + K1_T - 1)
 // HIST: also count the records by the top `hist_bits` bits of the key -- the histogram of the first partition pass
 // (partition.cu), which then never re-reads the records for it.  Counts go to shared memory first and to one of
 // K1_HIST_COPIES global copies at the end of the tile (tiles are many: a single copy would serialise on its counters).
-template <int KT, bool HAS_QUAL, bool HIST>
+// PACKED: the batch holds host-packed bases instead of ASCII (skagpu_build_packed: 0.375 B per base across PCIe instead
+// of 1): `seq` = 2-bit codes, 4 per byte in the kernel's own LE order, `qual` = the invalid-base bit mask; the tile is
+// staged straight into the LE stream and the mask words, the pack phase disappears.
+template <int KT, bool HAS_QUAL, bool HIST, bool PACKED>
 __global__ void __launch_bounds__(K1_THREADS)
 k1_extract_kernel(const uint8_t* __restrict__ seq, const uint8_t* __restrict__ qual,
                   const uint32_t* __restrict__ start_bits, const uint64_t* __restrict__ sample_off,
@@ -43,11 +47,15 @@ k1_extract_kernel(const uint8_t* __restrict__ seq, const uint8_t* __restrict__ q
                   uint64_t* __restrict__ rec_out, uint16_t* __restrict__ sid_out, uint32_t* __restrict__ sample_valid,
                   uint32_t sid_base, unsigned long long* __restrict__ hist, int hist_shift, int hist_bits, uint32_t tile0) {
     __shared__ uint32_t s_hist[HIST ? (1 << K1_HIST_MAX_BITS) : 1];
-    __shared__ __align__(128) uint8_t s_ascii[K1_BYTES];
+    __shared__ __align__(128) uint8_t s_ascii[PACKED ? 16 : K1_BYTES];
     __shared__ __align__(128) uint8_t s_qual[HAS_QUAL ? K1_BYTES : 16];
-    __shared__ uint32_t s_le[2 * K1_G32 + 2];
+    // packed batches are staged from K1P_LEAD positions before the tile (16-byte aligned for the bulk copy); the kernel's
+    // own arrays start K1_LEAD positions before it, i.e. (K1P_LEAD - K1_LEAD) / 16 LE words / 32 mask words further on
+    __shared__ __align__(128) uint32_t s_le_raw[PACKED ? K1P_BYTES / 16 : 2 * K1_G32 + 2];
+    __shared__ __align__(128) uint32_t s_bad_raw[PACKED ? K1P_BYTES / 32 : K1_G32];
     __shared__ uint32_t s_be[2 * K1_G32 + 2];
-    __shared__ uint32_t s_bad[K1_G32];
+    uint32_t* const s_le = s_le_raw + (PACKED ? (K1P_LEAD - K1_LEAD) / 16 : 0);
+    uint32_t* const s_bad = s_bad_raw + (PACKED ? (K1P_LEAD - K1_LEAD) / 32 : 0);
     __shared__ uint32_t s_start[K1_G32];
     __shared__ uint32_t s_ok[K1_T / 32];
     __shared__ __align__(8) uint64_t s_mbar;
@@ -67,9 +75,15 @@ k1_extract_kernel(const uint8_t* __restrict__ seq, const uint8_t* __restrict__ q
     if (HIST) for (int i = tid; i < (1 << hist_bits); i += K1_THREADS) s_hist[i] = 0;
     __syncthreads();
     if (tid == 0) {
-        mbar_expect_tx(&s_mbar, HAS_QUAL ? 2 * K1_BYTES : K1_BYTES);
-        tma_load_1d(s_ascii, gsrc, K1_BYTES, &s_mbar);
-        if (HAS_QUAL) tma_load_1d(s_qual, qual + FRONT_PAD + t0 - K1_LEAD, K1_BYTES, &s_mbar);
+        if (PACKED) {
+            mbar_expect_tx(&s_mbar, K1P_BYTES / 4 + K1P_BYTES / 8);
+            tma_load_1d(s_le_raw, seq + (FRONT_PAD + t0 - K1P_LEAD) / 4, K1P_BYTES / 4, &s_mbar);
+            tma_load_1d(s_bad_raw, qual + (FRONT_PAD + t0 - K1P_LEAD) / 8, K1P_BYTES / 8, &s_mbar);
+        } else {
+            mbar_expect_tx(&s_mbar, HAS_QUAL ? 2 * K1_BYTES : K1_BYTES);
+            tma_load_1d(s_ascii, gsrc, K1_BYTES, &s_mbar);
+            if (HAS_QUAL) tma_load_1d(s_qual, qual + FRONT_PAD + t0 - K1_LEAD, K1_BYTES, &s_mbar);
+        }
         // sample ids of the first and last window of the tile (binary search over sample_off)
         uint64_t pf = t0, pl = min(t0 + K1_T - 1, n_pos - 1);
         uint32_t lo = 0, hi = n_samples;                    // find s with off[s] <= pf < off[s+1]
@@ -83,7 +97,10 @@ k1_extract_kernel(const uint8_t* __restrict__ seq, const uint8_t* __restrict__ q
     if (tid < K1_G32) s_start[tid] = start_bits[(t0 + FRONT_PAD - K1_LEAD) / 32 + tid];
     mbar_wait(&s_mbar, 0);
 
-    // ---- pack: 32 bases per thread
+    // ---- pack: 32 bases per thread (packed batches: only the BE copy of the stream is made)
+    if (PACKED) {
+        for (int g = tid; g < 2 * K1_G32; g += K1_THREADS) s_be[g] = le_to_be(s_le[g]);
+    } else
     for (int g = tid; g < K1_G32; g += K1_THREADS) {
         const uint4* src = reinterpret_cast<const uint4*>(s_ascii + 32 * g);
         uint4 a = src[0], b = src[1];
@@ -107,7 +124,7 @@ k1_extract_kernel(const uint8_t* __restrict__ seq, const uint8_t* __restrict__ q
         s_be[2 * g] = le_to_be(le0); s_be[2 * g + 1] = le_to_be(le1);
         s_bad[g] = bad;
     }
-    if (tid < 2) { s_le[2 * K1_G32 + tid] = 0; s_be[2 * K1_G32 + tid] = 0; }
+    if (tid < 2) { if (!PACKED) s_le[2 * K1_G32 + tid] = 0; s_be[2 * K1_G32 + tid] = 0; }
     __syncthreads();
 
     // ---- window validity: thread j -> windows at staged bits [32(j+1), 32(j+1)+32)
@@ -211,15 +228,22 @@ static void launch_k1_kt(const SeqBatch& b, uint32_t k, bool rc, bool strict_qua
     const unsigned grid = (unsigned)(tile_end - tile_begin);
     const uint32_t tile0 = (uint32_t)tile_begin;
     unsigned long long* nohist = nullptr;
-    if (b.has_qual && strict_qual) {
-        SKA_LAUNCH((k1_extract_kernel<KT, true, false>), grid, K1_THREADS, 0, b.seq.p, b.qual.p, b.start_bits.p, b.sample_off.p,
+    if (b.packed) {
+        if (hist)
+            SKA_LAUNCH((k1_extract_kernel<KT, false, true, true>), grid, K1_THREADS, 0, b.seq.p, b.qual.p, b.start_bits.p, b.sample_off.p,
+                       (uint32_t)b.n_samples, b.n_pos, (int)k, rc ? 1 : 0, 0u, rec_out, sid_out, sample_valid, sid_base, hist, hist_shift, hist_bits, tile0);
+        else
+            SKA_LAUNCH((k1_extract_kernel<KT, false, false, true>), grid, K1_THREADS, 0, b.seq.p, b.qual.p, b.start_bits.p, b.sample_off.p,
+                       (uint32_t)b.n_samples, b.n_pos, (int)k, rc ? 1 : 0, 0u, rec_out, sid_out, sample_valid, sid_base, nohist, 0, 0, tile0);
+    } else if (b.has_qual && strict_qual) {
+        SKA_LAUNCH((k1_extract_kernel<KT, true, false, false>), grid, K1_THREADS, 0, b.seq.p, b.qual.p, b.start_bits.p, b.sample_off.p,
                    (uint32_t)b.n_samples, b.n_pos, (int)k, rc ? 1 : 0, (uint32_t)min_qual, rec_out, sid_out, sample_valid, sid_base, nohist, 0, 0, tile0);
     } else if (hist) {
-        SKA_LAUNCH((k1_extract_kernel<KT, false, true>), grid, K1_THREADS, 0, b.seq.p, (const uint8_t*)nullptr, b.start_bits.p,
+        SKA_LAUNCH((k1_extract_kernel<KT, false, true, false>), grid, K1_THREADS, 0, b.seq.p, (const uint8_t*)nullptr, b.start_bits.p,
                    b.sample_off.p, (uint32_t)b.n_samples, b.n_pos, (int)k, rc ? 1 : 0, (uint32_t)min_qual, rec_out, sid_out,
                    sample_valid, sid_base, hist, hist_shift, hist_bits, tile0);
     } else {
-        SKA_LAUNCH((k1_extract_kernel<KT, false, false>), grid, K1_THREADS, 0, b.seq.p, (const uint8_t*)nullptr, b.start_bits.p,
+        SKA_LAUNCH((k1_extract_kernel<KT, false, false, false>), grid, K1_THREADS, 0, b.seq.p, (const uint8_t*)nullptr, b.start_bits.p,
                    b.sample_off.p, (uint32_t)b.n_samples, b.n_pos, (int)k, rc ? 1 : 0, (uint32_t)min_qual, rec_out, sid_out,
                    sample_valid, sid_base, nohist, 0, 0, tile0);
     }

@@ -12,6 +12,12 @@ constexpr int K1_LEAD = 32;                      // staged bytes before the tile
 constexpr int K1_TAIL = 96;                      // staged bytes after the tile (>= k for k <= 63, 32-aligned)
 constexpr int K1_BYTES = K1_LEAD + K1_T + K1_TAIL;
 constexpr int K1_G32 = K1_BYTES / 32;            // groups of 32 bases in the staged region
+// host-packed batches (2-bit codes + invalid mask): staged positions [t0 - K1P_LEAD, t0 + K1_T + K1P_TAIL); both byte
+// streams (4 and 8 positions per byte) then start and end on 16-byte boundaries, as the bulk copy needs
+constexpr int K1P_LEAD = 128;
+constexpr int K1P_TAIL = 128;
+constexpr int K1P_BYTES = K1P_LEAD + K1_T + K1P_TAIL;      // positions staged
+static_assert(K1P_LEAD == FRONT_PAD && (K1P_BYTES / 8) % 16 == 0 && K1P_LEAD >= K1_LEAD && K1P_TAIL >= K1_TAIL, "packed tile geometry");
 
 
 struct B128 { uint64_t lo, hi; };

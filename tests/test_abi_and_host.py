@@ -100,3 +100,30 @@ def test_synth_is_deterministic_and_shardable():
     assert all(np.array_equal(x, y) for x, y in zip(a[2:], b))
     diff = (a[0] != a[1]).mean()
     assert 0.0005 < diff < 0.005
+
+
+def test_pack_bases_matches_numpy():
+    """skagpu_pack_bases (host helper, no device work) against a numpy restatement of encode_base / valid_base
+    (bit_encoding.rs:34-36, 52-54), including unaligned record starts"""
+    import numpy as np
+    import ska_rust_b200 as S
+    L = S.api.lib()
+    rng = np.random.default_rng(5)
+    alphabet = np.frombuffer(b"ACGTacgtNnRYKM-.>~^", dtype=np.uint8)
+    total = 10007
+    seq = rng.choice(alphabet, size=total)
+    p2 = np.zeros((total + 3) // 4, dtype=np.uint8)
+    inv = np.full((total + 7) // 8, 0xFF, dtype=np.uint8)
+    cuts = [0, 1, 8, 13, 14, 100, 1003, 4096, 4099, 9000, total]      # records packed back to back, arbitrary alignment
+    for a, b in zip(cuts[:-1], cuts[1:]):
+        rec = np.ascontiguousarray(seq[a:b])
+        L.skagpu_pack_bases(rec.ctypes.data, b - a, a, p2.ctypes.data, inv.ctypes.data)
+    codes = (seq >> 1) & 3
+    exp2 = np.zeros(len(p2) * 4, dtype=np.uint8)
+    exp2[:total] = codes
+    exp2 = (exp2[0::4] | (exp2[1::4] << 2) | (exp2[2::4] << 4) | (exp2[3::4] << 6)).astype(np.uint8)
+    bad = np.ones(len(inv) * 8, dtype=np.uint8)
+    bad[:total] = (seq & 0xF) == 14
+    expi = np.packbits(bad, bitorder="little")
+    assert np.array_equal(p2, exp2)
+    assert np.array_equal(inv, expi)

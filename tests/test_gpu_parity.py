@@ -578,3 +578,70 @@ def test_distance_bitplane_path_large():
     g = S.MergeSkaArray.from_arrays(31, True, 64, keys, var, cnt, names)
     o = O.OracleArray.from_arrays(31, True, 64, list(range(n_rows)), var, cnt, names)
     assert g.distance(3.0, True) == o.distance_raw(3.0, True, threads=8)
+
+
+# ------------------------------------------------------------------ host-packed input (skagpu_build_packed)
+@pytest.mark.parametrize("k,rc", [(9, True), (15, False), (31, True)])
+def test_packed_build_equals_ascii_build(k, rc):
+    """2-bit codes + invalid mask from the host (0.375 B/base across PCIe) give the array of the ASCII path and of the oracle:
+    N runs, lower case, IUPAC letters mis-encoded as bases, records of exactly k / k+1 bases, runs of exactly k at a record end
+    followed by the 32-position gap between samples"""
+    rng = np.random.default_rng(99 + k)
+    core = bytes(rng.choice(np.frombuffer(b"ACGT", dtype=np.uint8), size=k + 1))
+    samples_records = [random_records(rng, int(rng.integers(1, 5)), 9000) + [core * 2] for _ in range(6)]
+    samples_records.append([core[:k], core, core + b"N" + core[:k], core[:k] + b"N" + core, b"", core * 3])
+    samples_records.append([bytes(rng.choice(np.frombuffer(b"ACGT", dtype=np.uint8), size=20000)) + b"N" + core[:k]])
+    samples = [S.Sample.from_records(r) for r in samples_records]
+    names = [f"s{i}" for i in range(len(samples))]
+    packed = [S.PackedSample.from_sample(s) for s in samples]
+    g_ascii = S.build_from_samples(samples, names, k, rc)
+    g_packed = S.api.build_from_packed(packed, names, k, rc)
+    g_batch = S.api.build_from_batch(S.SeqBatch(packed), names, k, rc)
+    o = ora_from_gpu_samples(samples, names, k, rc)
+    assert_same_array(g_ascii, o)
+    assert_same_array(g_packed, o)
+    assert_same_array(g_batch, o)
+
+
+def test_packed_k1_records_single_sample():
+    rng = np.random.default_rng(3)
+    recs = random_records(rng, 7, 6000)
+    s = S.Sample.from_records(recs)
+    batch = S.SeqBatch([S.PackedSample.from_sample(s)])
+    for k in (31, 9):
+        rec, _ = batch.k1_extract(k, rc=True)
+        exp = expected_records([recs], k, True)
+        assert np.array_equal(rec[:len(exp)], exp)
+        assert np.all(rec[len(exp):] == SENT)
+
+
+def test_array_checksum_matches_numpy_and_flags_damage():
+    """skagpu_array_checksum: device cell checksum == numpy restatement; count / order damage is detected"""
+    rng = np.random.default_rng(17)
+    recs = [random_records(rng, 3, 4000) for _ in range(5)]
+    samples = [S.Sample.from_records(r) for r in recs]
+    names = [f"s{i}" for i in range(5)]
+    g = S.build_from_samples(samples, names, 15, True)
+    keys, var, cnt = g.export()
+
+    def mix(x):
+        x = np.asarray(x, dtype=np.uint64)
+        x = x ^ (x >> np.uint64(33)); x = x * np.uint64(0xff51afd7ed558ccd)
+        x = x ^ (x >> np.uint64(33)); x = x * np.uint64(0xc4ceb9fe1a85ec53)
+        return x ^ (x >> np.uint64(33))
+
+    for lo, hi in ((0, 5), (1, 3), (4, 5)):
+        tot = np.uint64(0)
+        with np.errstate(over="ignore"):
+            for c in range(lo, hi):
+                m = var[:, c] != ord("-")
+                cell = mix(keys[m] ^ mix((np.uint64(c - lo) << np.uint64(8)) | var[m, c].astype(np.uint64)))
+                tot = tot + cell.sum(dtype=np.uint64)
+        rows = int((var[:, lo:hi] != ord("-")).any(axis=1).sum())
+        assert g.checksum(lo, hi) == (int(tot), rows, 0, 0)
+    cnt2 = cnt.copy(); cnt2[3] += 1
+    bad = S.MergeSkaArray.from_arrays(15, True, 64, keys, var, cnt2, names)
+    assert bad.checksum()[2] == 1
+    keys2 = keys.copy(); keys2[[5, 6]] = keys2[[6, 5]]
+    bad = S.MergeSkaArray.from_arrays(15, True, 64, keys2, var, cnt, names)
+    assert bad.checksum()[3] >= 1
