@@ -379,8 +379,9 @@ def run_ours(args, rank, world, local_rank):
             return r
 
         def e2e_run(host_samples, pipelined, steps):
-            for i in range(min(args.warmup, 2)):
-                e2e_step(i, host_samples, pipelined, last=(i + 1 == min(args.warmup, 2)))
+            n_warm = max(args.warmup, 5) if pipelined else 2     # the pipeline's buffers (two batches, pending exports) reach their steady state
+            for i in range(n_warm):
+                e2e_step(i, host_samples, pipelined, last=(i + 1 == n_warm))
             S.api.export_wait()
             barrier()
             S.api.timer_start()

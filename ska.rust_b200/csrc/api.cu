@@ -3,7 +3,9 @@
 #include <algorithm>
 #include <cmath>
 #include <cstring>
+#include <map>
 #include <memory>
+#include <mutex>
 
 #include "../../include/skagpu.h"
 #include "common.cuh"
@@ -13,7 +15,9 @@ namespace ska {
 static Context g_ctx;
 Context& ctx() { return g_ctx; }
 void Context::ensure() {
-    if (init) return;
+    static std::mutex mu;                                   // a host may create the context on a helper thread while it parses its input
+    std::lock_guard<std::mutex> lock(mu);
+    if (init) { cudaSetDevice(device); return; }
     int n = 0;
     cudaError_t e = cudaGetDeviceCount(&n);
     if (e != cudaSuccess || n == 0)
@@ -33,6 +37,52 @@ void Context::ensure() {
     uint64_t thr = UINT64_MAX;
     SKA_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr));
     init = true;
+}
+
+// ---- DevBuf's allocator: cudaMalloc'ed blocks, cached
+namespace {
+struct DevCache {
+    std::mutex mu;
+    std::map<void*, size_t> live;                       // block -> capacity
+    std::multimap<size_t, void*> free_blocks;           // capacity -> block
+    size_t cached_bytes = 0;
+};
+DevCache& dev_cache() { static DevCache* c = new DevCache(); return *c; }   // never destroyed: buffers may outlive static teardown
+}  // namespace
+void* dev_alloc(size_t bytes) {
+    DevCache& dc = dev_cache();
+    const size_t want = (bytes + ((size_t)1 << 21) - 1) & ~(((size_t)1 << 21) - 1);      // 2 MB granules
+    std::lock_guard<std::mutex> lock(dc.mu);
+    auto it = dc.free_blocks.lower_bound(want);
+    if (it != dc.free_blocks.end() && it->first <= want + want / 4 + ((size_t)8 << 20)) {   // close enough in size: reuse
+        void* p = it->second;
+        dc.cached_bytes -= it->first;
+        dc.live[p] = it->first;
+        dc.free_blocks.erase(it);
+        return p;
+    }
+    void* p = nullptr;
+    cudaError_t e = cudaMalloc(&p, want);
+    if (e != cudaSuccess) {                               // out of memory: give the cached blocks back and try once more
+        (void)cudaGetLastError();
+        cudaDeviceSynchronize();
+        for (auto& fb : dc.free_blocks) cudaFree(fb.second);
+        dc.free_blocks.clear(); dc.cached_bytes = 0;
+        e = cudaMalloc(&p, want);
+    }
+    if (e != cudaSuccess) throw Error(std::string("cudaMalloc of ") + std::to_string(want >> 20) + " MB failed: " + cudaGetErrorString(e));
+    dc.live[p] = want;
+    return p;
+}
+void dev_free(void* p) {
+    if (!p) return;
+    DevCache& dc = dev_cache();
+    std::lock_guard<std::mutex> lock(dc.mu);
+    auto it = dc.live.find(p);
+    if (it == dc.live.end()) return;
+    dc.free_blocks.emplace(it->second, p);
+    dc.cached_bytes += it->second;
+    dc.live.erase(it);
 }
 
 static Arena g_arena;

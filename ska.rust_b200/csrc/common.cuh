@@ -45,7 +45,15 @@ Context& ctx();
         SKA_CUDA(cudaGetLastError());                                      \
     } while (0)
 
-// RAII device buffer (stream-ordered allocator keeps repeated builds cheap).
+// Device memory of DevBuf: blocks from cudaMalloc kept in a free list for the life of the process (api.cu).  The first
+// growth of CUDA's stream-ordered pool costs 0.5 s for 1.4 GB on a B200 (profiles/microbench/ctx_mb.cu) against 7 ms for a
+// 13 GB cudaMalloc -- a third of what a one-shot `ska build` process takes; repeated builds hit the free list either way.
+// A block is handed out again only to work that is ordered behind its previous user (everything runs on, or is fenced
+// against, the library stream).
+void* dev_alloc(size_t bytes);
+void dev_free(void* p);
+
+// RAII device buffer.
 template <class T> struct DevBuf {
     T* p = nullptr;
     size_t n = 0;
@@ -62,15 +70,10 @@ template <class T> struct DevBuf {
     void alloc(size_t count) {
         release();
         n = count;
-        if (count) {
-            auto t0 = std::chrono::steady_clock::now();
-            SKA_CUDA(cudaMallocAsync((void**)&p, count * sizeof(T), ctx().stream));
-            double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
-            if (ms > 1.0 && getenv("SKA_DEBUG_ALLOC")) fprintf(stderr, "[skagpu] slow alloc %.1f MB: %.2f ms\n", count * sizeof(T) / 1e6, ms);
-        }
+        if (count) p = static_cast<T*>(dev_alloc(count * sizeof(T)));
     }
     void release() {
-        if (p) cudaFreeAsync(p, ctx().stream);
+        if (p) dev_free(p);
         p = nullptr; n = 0;
     }
     size_t bytes() const { return n * sizeof(T); }

@@ -21,92 +21,147 @@
 
 namespace ska {
 
-constexpr int DT = 16;            // samples per tile side
-constexpr int DW = 32;            // row-words per staged chunk
+constexpr int DT = 16;            // samples per tile side of the exact byte-wise kernel
 
-// ---- planes: out[plane][sample][word]
+// ---- planes: out[plane][word][sample], samples padded to a multiple of 64 (SP) so that tiles of the pair kernel never
+// bound-check.  One CTA = `wpc` words (32 rows each): their rows are one contiguous 16-byte aligned block of the
+// row-major array, staged with 16-byte loads; then one thread per (word, sample) walks the 32 rows (consecutive threads
+// read consecutive bytes: no bank conflicts).  A byte is classified by ONE lookup in a 256-entry shared-memory table
+// (bits: present, unambiguous, code bit 0, code bit 1, "odd alphabet"); the four flags of row r go to nibble r of a 128-bit
+// accumulator and the nibbles are pulled apart into the four plane words once per 32 rows (~10 instructions per byte
+// against ~18 for classifying with compares).
+__device__ __forceinline__ uint32_t every_4th_bit(uint32_t acc, int i) {     // bits i, i+4, ... of acc -> low 8 bits
+    uint32_t x = (acc >> i) & 0x11111111u;
+    x = (x | (x >> 3)) & 0x03030303u;
+    x = (x | (x >> 6)) & 0x000F000Fu;
+    return (x | (x >> 12)) & 0xFFu;
+}
 __global__ void __launch_bounds__(256)
-planes_kernel(const uint8_t* __restrict__ var, uint64_t n_rows, uint32_t n_samples, uint64_t n_words,
+planes_kernel(const uint8_t* __restrict__ var, uint64_t n_rows, uint32_t n_samples, uint32_t SP, uint64_t n_words, uint32_t wpc,
               uint32_t* __restrict__ planes, uint32_t* __restrict__ odd_alphabet) {
-    extern __shared__ uint8_t s_tile[];                       // 32 rows x (n_samples + 4)
-    const uint32_t pitch = n_samples + 4;
-    const uint64_t w = blockIdx.x;
-    const uint64_t r0 = w * 32;
-    for (uint32_t idx = threadIdx.x; idx < 32 * n_samples; idx += 256) {
-        uint32_t r = idx / n_samples, s = idx - r * n_samples;
-        s_tile[r * pitch + s] = (r0 + r < n_rows) ? var[(r0 + r) * n_samples + s] : (uint8_t)'-';
+    extern __shared__ __align__(16) uint8_t s_tile[];                       // wpc x 32 rows x n_samples
+    __shared__ uint8_t s_lut[256];
+    {
+        const uint32_t b = threadIdx.x;
+        const uint32_t present = b != '-';
+        const uint32_t unamb = (b == 'A' || b == 'C' || b == 'G' || b == 'T');
+        const uint32_t lb = b | 0x20u;
+        const uint32_t ref_unamb = present & (lb == 'a' || lb == 'c' || lb == 'g' || lb == 't' || lb == 'u');   // !is_ambiguous (bit_encoding.rs:58-61)
+        const uint32_t code = (b >> 1) & 3u;
+        s_lut[b] = (uint8_t)(present | (unamb << 1) | ((unamb & code & 1u) << 2) | ((unamb & (code >> 1)) << 3) | ((ref_unamb != unamb) << 4));
     }
+    const uint64_t w0 = (uint64_t)blockIdx.x * wpc;
+    const uint64_t r0 = w0 * 32;
+    const uint32_t tile_rows = wpc * 32;
+    const uint32_t rows = (uint32_t)min((uint64_t)tile_rows, n_rows - r0);
+    const uint32_t n16 = (uint32_t)(((uint64_t)rows * n_samples) / 16);
+    const uint4* src = reinterpret_cast<const uint4*>(var + r0 * n_samples);
+    uint4* dst = reinterpret_cast<uint4*>(s_tile);
+    for (uint32_t i = threadIdx.x; i < n16; i += 256) dst[i] = __ldg(src + i);
+    for (uint32_t i = n16 * 16 + threadIdx.x; i < tile_rows * n_samples; i += 256)
+        s_tile[i] = i < rows * n_samples ? var[r0 * n_samples + i] : (uint8_t)'-';
     __syncthreads();
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const uint64_t plane_stride = (uint64_t)n_samples * n_words;
-    for (uint32_t s = warp; s < n_samples; s += 8) {
-        uint32_t b = s_tile[lane * pitch + s];
-        bool present = b != '-';
-        bool unamb = (b == 'A' || b == 'C' || b == 'G' || b == 'T');
-        uint32_t lb = b | 0x20u;
-        bool ref_unamb = present && (lb == 'a' || lb == 'c' || lb == 'g' || lb == 't' || lb == 'u');   // !is_ambiguous
-        if (ref_unamb != unamb) atomicExch(odd_alphabet, 1u);      // lower case / U: take the exact path
-        uint32_t code = (b >> 1) & 3u;
-        uint32_t mP = __ballot_sync(0xFFFFFFFFu, present);
-        uint32_t mU = __ballot_sync(0xFFFFFFFFu, unamb);
-        uint32_t m0 = __ballot_sync(0xFFFFFFFFu, unamb && (code & 1u));
-        uint32_t m1 = __ballot_sync(0xFFFFFFFFu, unamb && (code & 2u));
-        if (lane == 0) {
-            uint64_t o = (uint64_t)s * n_words + w;
-            planes[o] = mP; planes[plane_stride + o] = mU; planes[2 * plane_stride + o] = m0; planes[3 * plane_stride + o] = m1;
+    const uint64_t plane_stride = n_words * SP;
+    uint32_t odd = 0;
+    for (uint32_t item = threadIdx.x; item < wpc * SP; item += 256) {
+        const uint32_t wq = item / SP, s = item - wq * SP;
+        if (w0 + wq >= n_words) break;
+        uint32_t acc[4] = {0u, 0u, 0u, 0u};
+        if (s < n_samples) {
+            const uint8_t* col = s_tile + (size_t)wq * 32 * n_samples + s;
+#pragma unroll
+            for (int r = 0; r < 32; r++) {
+                const uint32_t v = s_lut[col[r * n_samples]];
+                odd |= v;
+                acc[r >> 3] |= (v & 0xFu) << (4 * (r & 7));
+            }
         }
+        uint32_t m[4];
+#pragma unroll
+        for (int i = 0; i < 4; i++)
+            m[i] = every_4th_bit(acc[0], i) | (every_4th_bit(acc[1], i) << 8) | (every_4th_bit(acc[2], i) << 16) | (every_4th_bit(acc[3], i) << 24);
+        const uint64_t o = (w0 + wq) * SP + s;
+        planes[o] = m[0]; planes[plane_stride + o] = m[1]; planes[2 * plane_stride + o] = m[2]; planes[3 * plane_stride + o] = m[3];
     }
+    if (odd & 16u) atomicExch(odd_alphabet, 1u);
 }
 
-// ---- pair kernel: acc[pair_index(i,j)][3] += partial sums;  grid = (tile pairs, word splits)
-__global__ void __launch_bounds__(256)
-pair_popc_kernel(const uint32_t* __restrict__ planes, uint32_t n_samples, uint64_t n_words, uint32_t n_tiles,
+// ---- pair kernel: register tile of 4 x 4 sample pairs per thread over a TS x TS tile of samples (TS = 32: 64 threads,
+// TS = 64: 256 threads), DW words staged per step; per pair and word 3 POPC + 5 LOP3, operands by 8 LDS.128 per 16 pairs.
+// POPC issues at 15.4 lanes/clk/SM on B200 (profiles/microbench/popc_mb.cu: 4.5e12 popc/s), a quarter of the LOP3 rate:
+// the kernel is bound by the popcounts.  grid = (tile pairs, word splits); partial sums by 64-bit atomics.
+constexpr int PW = 8;             // words staged per step
+template <int TS>
+__global__ void __launch_bounds__((TS / 4) * (TS / 4))
+pair_popc_kernel(const uint32_t* __restrict__ planes, uint32_t n_samples, uint32_t SP, uint64_t n_words, uint32_t n_tiles,
                  uint64_t words_per_split, unsigned long long* __restrict__ acc) {
-    __shared__ uint32_t s_i[4][DT][DW];
-    __shared__ uint32_t s_j[4][DT][DW];
-    // decode tile pair (ti <= tj) from blockIdx.x
+    constexpr int Q = TS / 4;                                   // threads per tile side
+    constexpr int NT = Q * Q;
+    __shared__ __align__(16) uint32_t s_i[4][PW][TS];
+    __shared__ __align__(16) uint32_t s_j[4][PW][TS];
     uint32_t t = blockIdx.x, ti = 0;
     while (t >= n_tiles - ti) { t -= n_tiles - ti; ti++; }
     const uint32_t tj = ti + t;
-    const uint32_t a = threadIdx.x / DT, b = threadIdx.x % DT;    // pair (ti*DT + a, tj*DT + b)
-    const uint32_t si = ti * DT + a, sj = tj * DT + b;
-    const bool active = si < n_samples && sj < n_samples && si < sj;
+    const uint32_t a = threadIdx.x / Q, b = threadIdx.x % Q;    // pairs (ti*TS + 4a + x, tj*TS + 4b + y)
+    const bool skip = (ti == tj) && (a > b);                    // every pair of the thread has i > j
     const uint64_t w_beg = (uint64_t)blockIdx.y * words_per_split;
     const uint64_t w_end = min(n_words, w_beg + words_per_split);
-    const uint64_t plane_stride = (uint64_t)n_samples * n_words;
-    const uint32_t skew = (b + DT * (a & 1u)) & (DW - 1);
-    uint32_t mism = 0, match = 0, dist = 0;
-    for (uint64_t w0 = w_beg; w0 < w_end; w0 += DW) {
-        // stage 2 x (4 planes x 16 samples x 32 words)
-        for (uint32_t idx = threadIdx.x; idx < 4 * DT * DW; idx += 256) {
-            uint32_t p = idx / (DT * DW), rem = idx - p * DT * DW, s = rem / DW, w = rem - s * DW;
-            uint64_t gw = w0 + w;
-            uint32_t gi = ti * DT + s, gj = tj * DT + s;
-            s_i[p][s][w] = (gw < w_end && gi < n_samples) ? planes[p * plane_stride + (uint64_t)gi * n_words + gw] : 0u;
-            s_j[p][s][w] = (gw < w_end && gj < n_samples) ? planes[p * plane_stride + (uint64_t)gj * n_words + gw] : 0u;
+    const uint64_t plane_stride = n_words * SP;
+    uint32_t mism[4][4], match[4][4], dist[4][4];
+#pragma unroll
+    for (int x = 0; x < 4; x++)
+#pragma unroll
+        for (int y = 0; y < 4; y++) { mism[x][y] = 0; match[x][y] = 0; dist[x][y] = 0; }
+    for (uint64_t w0 = w_beg; w0 < w_end; w0 += PW) {
+        for (uint32_t idx = threadIdx.x; idx < 4 * PW * Q; idx += NT) {
+            const uint32_t p = idx / (PW * Q), rem = idx - p * (PW * Q), w = rem / Q, q = rem - w * Q;
+            const uint64_t gw = w0 + w;
+            uint4 vi = make_uint4(0u, 0u, 0u, 0u), vj = vi;
+            if (gw < w_end) {
+                const uint32_t* base = planes + p * plane_stride + gw * SP;
+                vi = __ldg(reinterpret_cast<const uint4*>(base + ti * TS + 4 * q));
+                vj = __ldg(reinterpret_cast<const uint4*>(base + tj * TS + 4 * q));
+            }
+            *reinterpret_cast<uint4*>(&s_i[p][w][4 * q]) = vi;
+            *reinterpret_cast<uint4*>(&s_j[p][w][4 * q]) = vj;
         }
         __syncthreads();
-        if (active) {
-#pragma unroll 8
-            for (uint32_t w = 0; w < DW; w++) {
-                uint32_t ww = (w + skew) & (DW - 1);
-                uint32_t pi = s_i[0][a][ww], pj = s_j[0][b][ww];
-                uint32_t ui = s_i[1][a][ww], uj = s_j[1][b][ww];
-                uint32_t both = ui & uj;
-                uint32_t diff = (s_i[2][a][ww] ^ s_j[2][b][ww]) | (s_i[3][a][ww] ^ s_j[3][b][ww]);
-                mism += __popc(pi ^ pj);
-                match += __popc(both);
-                dist += __popc(both & diff);
+        if (!skip) {
+#pragma unroll 2
+            for (int w = 0; w < PW; w++) {
+                const uint4 Pi = *reinterpret_cast<const uint4*>(&s_i[0][w][4 * a]), Ui = *reinterpret_cast<const uint4*>(&s_i[1][w][4 * a]);
+                const uint4 Xi = *reinterpret_cast<const uint4*>(&s_i[2][w][4 * a]), Yi = *reinterpret_cast<const uint4*>(&s_i[3][w][4 * a]);
+                const uint4 Pj = *reinterpret_cast<const uint4*>(&s_j[0][w][4 * b]), Uj = *reinterpret_cast<const uint4*>(&s_j[1][w][4 * b]);
+                const uint4 Xj = *reinterpret_cast<const uint4*>(&s_j[2][w][4 * b]), Yj = *reinterpret_cast<const uint4*>(&s_j[3][w][4 * b]);
+                const uint32_t pi[4] = {Pi.x, Pi.y, Pi.z, Pi.w}, ui[4] = {Ui.x, Ui.y, Ui.z, Ui.w}, xi[4] = {Xi.x, Xi.y, Xi.z, Xi.w}, yi[4] = {Yi.x, Yi.y, Yi.z, Yi.w};
+                const uint32_t pj[4] = {Pj.x, Pj.y, Pj.z, Pj.w}, uj[4] = {Uj.x, Uj.y, Uj.z, Uj.w}, xj[4] = {Xj.x, Xj.y, Xj.z, Xj.w}, yj[4] = {Yj.x, Yj.y, Yj.z, Yj.w};
+#pragma unroll
+                for (int x = 0; x < 4; x++)
+#pragma unroll
+                    for (int y = 0; y < 4; y++) {
+                        const uint32_t both = ui[x] & uj[y];
+                        const uint32_t diff = (xi[x] ^ xj[y]) | (yi[x] ^ yj[y]);
+                        mism[x][y] += __popc(pi[x] ^ pj[y]);
+                        match[x][y] += __popc(both);
+                        dist[x][y] += __popc(both & diff);
+                    }
             }
         }
         __syncthreads();
     }
-    if (active && (mism | match | dist)) {
-        uint64_t pidx = (uint64_t)si * n_samples - (uint64_t)si * (si + 1) / 2 + (sj - si - 1);
-        atomicAdd(&acc[3 * pidx + 0], (unsigned long long)mism);
-        atomicAdd(&acc[3 * pidx + 1], (unsigned long long)match);
-        atomicAdd(&acc[3 * pidx + 2], (unsigned long long)dist);
-    }
+    if (skip) return;
+#pragma unroll
+    for (int x = 0; x < 4; x++)
+#pragma unroll
+        for (int y = 0; y < 4; y++) {
+            const uint32_t si = ti * TS + 4 * a + x, sj = tj * TS + 4 * b + y;
+            if (si < sj && sj < n_samples && (mism[x][y] | match[x][y] | dist[x][y])) {
+                const uint64_t pidx = (uint64_t)si * n_samples - (uint64_t)si * (si + 1) / 2 + (sj - si - 1);
+                if (mism[x][y]) atomicAdd(&acc[3 * pidx + 0], (unsigned long long)mism[x][y]);
+                if (match[x][y]) atomicAdd(&acc[3 * pidx + 1], (unsigned long long)match[x][y]);
+                if (dist[x][y]) atomicAdd(&acc[3 * pidx + 2], (unsigned long long)dist[x][y]);
+            }
+        }
 }
 
 // ---- exact byte-wise kernel (both modes).  acc[pair][4] = {mismatches, matches, dist_int, n_both}
@@ -185,6 +240,7 @@ void distance_counters(const Array& a, bool filt_ambig, uint64_t* h_counters) {
     Context& c = ctx();
     const uint32_t N = (uint32_t)a.n_samples;
     if (N < 2) return;
+    if (timer().stages.size() > 48) timer().clear();             // repeated distance calls without a build in between
     const uint64_t n_pairs = (uint64_t)N * (N - 1) / 2;
     const uint64_t R = a.n_rows;
     const uint32_t n_tiles = (N + DT - 1) / DT;
@@ -195,13 +251,17 @@ void distance_counters(const Array& a, bool filt_ambig, uint64_t* h_counters) {
 
     if (use_planes) {
         const uint64_t n_words = (R + 31) / 32;
-        DevBuf<uint32_t> planes(4 * (uint64_t)N * n_words), odd(1);
+        const uint32_t SP = (N + 63) / 64 * 64;
+        DevBuf<uint32_t> planes(4 * (uint64_t)SP * n_words), odd(1);
         SKA_CUDA(cudaMemsetAsync(odd.p, 0, 4, c.stream));
-        size_t smem = 32 * (size_t)(N + 4);
-        if (smem > c.smem_optin) use_planes = false;
+        const uint32_t wpc = std::max<uint32_t>(1, 32768u / (32u * N));      // words per CTA: a 32 KB tile
+        size_t smem = (size_t)wpc * 32 * N;
+        if (smem + 1024 > c.smem_optin) use_planes = false;
         else {
+            timer().begin("planes");
             SKA_CUDA(cudaFuncSetAttribute(planes_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            SKA_LAUNCH(planes_kernel, (unsigned)n_words, 256, smem, a.variants.p, R, N, n_words, planes.p, odd.p);
+            SKA_LAUNCH(planes_kernel, (unsigned)((n_words + wpc - 1) / wpc), 256, smem, a.variants.p, R, N, SP, n_words, wpc, planes.p, odd.p);
+            timer().end();
             uint32_t h_odd = 0;
             SKA_CUDA(cudaMemcpyAsync(&h_odd, odd.p, 4, cudaMemcpyDeviceToHost, c.stream));
             SKA_CUDA(cudaStreamSynchronize(c.stream));
@@ -210,13 +270,19 @@ void distance_counters(const Array& a, bool filt_ambig, uint64_t* h_counters) {
         if (use_planes) {
             DevBuf<unsigned long long> acc(3 * n_pairs);
             SKA_CUDA(cudaMemsetAsync(acc.p, 0, acc.bytes(), c.stream));
-            uint64_t chunks = (n_words + DW - 1) / DW;
-            uint64_t want_splits = std::max<uint64_t>(1, (4ull * c.sm_count + n_tile_pairs - 1) / n_tile_pairs);
-            uint64_t splits = std::min<uint64_t>(std::min<uint64_t>(chunks, want_splits), 65535);
-            uint64_t words_per_split = ((chunks + splits - 1) / splits) * DW;
+            const bool small = N <= 256;                                   // 32 x 32 tiles waste less of the diagonal
+            const uint32_t TS = small ? 32 : 64;
+            const uint32_t nt = (N + TS - 1) / TS, ntp = nt * (nt + 1) / 2;
+            const uint64_t chunks = (n_words + PW - 1) / PW;
+            const uint64_t want_ctas = (uint64_t)c.sm_count * (small ? 24 : 6);
+            uint64_t splits = std::min<uint64_t>(std::min<uint64_t>(chunks, std::max<uint64_t>(1, (want_ctas + ntp - 1) / ntp)), 65535);
+            const uint64_t words_per_split = ((chunks + splits - 1) / splits) * PW;
             splits = (n_words + words_per_split - 1) / words_per_split;
-            dim3 grid(n_tile_pairs, (unsigned)splits);
-            SKA_LAUNCH(pair_popc_kernel, grid, 256, 0, planes.p, N, n_words, n_tiles, words_per_split, acc.p);
+            dim3 grid(ntp, (unsigned)splits);
+            timer().begin("pair_popc");
+            if (small) SKA_LAUNCH((pair_popc_kernel<32>), grid, 64, 0, planes.p, N, SP, n_words, nt, words_per_split, acc.p);
+            else SKA_LAUNCH((pair_popc_kernel<64>), grid, 256, 0, planes.p, N, SP, n_words, nt, words_per_split, acc.p);
+            timer().end();
             h_acc.resize(3 * n_pairs);
             SKA_CUDA(cudaMemcpyAsync(h_acc.data(), acc.p, acc.bytes(), cudaMemcpyDeviceToHost, c.stream));
             SKA_CUDA(cudaStreamSynchronize(c.stream));

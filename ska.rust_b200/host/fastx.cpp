@@ -29,18 +29,39 @@ static std::vector<uint8_t> gunzip(const std::vector<uint8_t>& in) {
     z_stream zs;
     memset(&zs, 0, sizeof zs);
     if (inflateInit2(&zs, 15 + 32) != Z_OK) throw std::runtime_error("Invalid FASTA/Q record");
-    zs.next_in = const_cast<Bytef*>(in.data());
-    zs.avail_in = (uInt)in.size();
+    // zlib counts its input in 32 bits: feed files of any size in pieces of at most 1 GiB
+    const uint8_t* next = in.data();
+    size_t left = in.size();
+    auto refill = [&] {
+        if (zs.avail_in == 0 && left) {
+            const size_t n = left < ((size_t)1 << 30) ? left : ((size_t)1 << 30);
+            zs.next_in = const_cast<Bytef*>(next);
+            zs.avail_in = (uInt)n;
+            next += n; left -= n;
+        }
+    };
     std::vector<uint8_t> chunk(1 << 20);
     int rc;
     do {
+        refill();
         zs.next_out = chunk.data();
         zs.avail_out = (uInt)chunk.size();
         rc = inflate(&zs, Z_NO_FLUSH);
-        if (rc != Z_OK && rc != Z_STREAM_END) { inflateEnd(&zs); throw std::runtime_error("Invalid FASTA/Q record"); }
+        if (rc != Z_OK && rc != Z_STREAM_END && !(rc == Z_BUF_ERROR && (zs.avail_in || left))) {
+            inflateEnd(&zs);
+            throw std::runtime_error("Invalid FASTA/Q record");
+        }
         out.insert(out.end(), chunk.data(), chunk.data() + (chunk.size() - zs.avail_out));
-        if (rc == Z_STREAM_END && zs.avail_in > 0) inflateReset(&zs);      // concatenated gzip members
-        else if (rc == Z_STREAM_END) break;
+        if (rc == Z_STREAM_END) {
+            refill();
+            // what follows a gzip member is another member (concatenated gzip) or nothing
+            if (zs.avail_in >= 2 && zs.next_in[0] == 0x1f && zs.next_in[1] == 0x8b) inflateReset(&zs);
+            else if (zs.avail_in == 0 && left == 0) break;
+            else { inflateEnd(&zs); throw std::runtime_error("Invalid FASTA/Q record"); }
+        } else if (zs.avail_in == 0 && left == 0 && zs.avail_out != 0) {
+            inflateEnd(&zs);
+            throw std::runtime_error("Invalid FASTA/Q record");                  // truncated stream
+        }
     } while (true);
     inflateEnd(&zs);
     return out;

@@ -1,6 +1,7 @@
 #include "ska_host.hpp"
 
 #include <atomic>
+#include <chrono>
 #include <cmath>
 #include <cstring>
 #include <fstream>
@@ -14,6 +15,18 @@ namespace ska {
 
 static void check(int rc) { if (rc) throw SkaError(skagpu_last_error()); }
 
+// SKA_TIMING=1: phase times of the host side on stderr (the file-to-file benchmark reads them)
+static void lap(const char* what) {
+    static const bool on = getenv("SKA_TIMING") != nullptr;
+    static const auto t0 = std::chrono::steady_clock::now();
+    static auto last = t0;
+    if (!on) return;
+    const auto now = std::chrono::steady_clock::now();
+    fprintf(stderr, "[ska] %-28s +%.3f s  (%.3f s)\n", what, std::chrono::duration<double>(now - last).count(),
+            std::chrono::duration<double>(now - t0).count());
+    last = now;
+}
+
 // ------------------------------------------------------------------------------------------ MergeSkaArray
 static void dims(ska_array_t* h, uint64_t& rows, uint64_t& keys, uint64_t& samples, uint32_t& k, int& rc, uint32_t& bits) {
     check(skagpu_dims(h, &rows, &keys, &samples, &k, &rc, &bits));
@@ -25,9 +38,14 @@ bool MergeSkaArray::rc() const { uint64_t r, kk, s; uint32_t k, b; int rc; dims(
 uint32_t MergeSkaArray::k_bits() const { uint64_t r, kk, s; uint32_t k, b; int rc; dims(h_, r, kk, s, k, rc, b); return b; }
 
 MergeSkaArray MergeSkaArray::load(const std::string& filename) {
+    lap("start");
     skf::Array a = skf::load(filename);
+    lap("skf read + decoded");
+    check(skagpu_set_device(0));
+    lap("cuda context ready");
     ska_array_t* h = nullptr;
     check(skagpu_array_from_host(a.k, a.rc, a.key_bits, a.n_rows, a.n_samples, a.keys.data(), a.variants.data(), a.counts.data(), &h));
+    lap("array on the device");
     return MergeSkaArray(h, a.names, a.ska_version);
 }
 
@@ -37,11 +55,17 @@ skf::Array MergeSkaArray::to_host() const {
     dims(h_, rows, keys, samples, k, rc, bits);
     a.k = k; a.rc = rc != 0; a.key_bits = bits; a.n_rows = rows; a.n_samples = samples; a.names = names_; a.ska_version = version_;
     a.keys.resize(keys * (bits / 64)); a.variants.resize(rows * samples); a.counts.resize(rows);
+    skf::prefault(a.variants.data(), a.variants.size(), (int)std::thread::hardware_concurrency());
     check(skagpu_export(h_, a.keys.data(), a.variants.data(), a.counts.data()));
     return a;
 }
 
-void MergeSkaArray::save(const std::string& filename, int threads) const { skf::save(to_host(), filename, threads); }
+void MergeSkaArray::save(const std::string& filename, int threads) const {
+    skf::Array a = to_host();
+    lap("array exported to the host");
+    skf::save(a, filename, threads);
+    lap("skf encoded + written");
+}
 
 int32_t MergeSkaArray::filter(size_t min_count, bool filter_ambig_as_missing, FilterType filter, bool mask_ambig,
                               bool ignore_const_gaps, bool update_kmers) {
@@ -62,8 +86,11 @@ std::vector<ska_dist_t> MergeSkaArray::distance(double constant, bool filt_ambig
 
 void MergeSkaArray::write_fasta(FILE* f) const {
     size_t n = nsamples(), r = ksize();
-    std::vector<uint8_t> t(n * r);
+    skf::Bytes t;
+    t.resize(n * r);
+    skf::prefault(t.data(), t.size(), (int)std::thread::hardware_concurrency());
     check(skagpu_export_transposed(h_, t.empty() ? nullptr : t.data()));
+    lap("filtered + transposed + copied");
     for (size_t i = 0; i < n; i++) {                       // needletail write_fasta, Unix line ending, no wrapping
         fputc('>', f); fwrite(names_[i].data(), 1, names_[i].size(), f); fputc('\n', f);
         fwrite(t.data() + i * r, 1, r, f); fputc('\n', f);
@@ -112,36 +139,42 @@ MergeSkaArray build_and_merge(const std::vector<InputFastx>& input_files, size_t
     std::vector<uint64_t> n_file1(n);
     std::vector<std::string> errors(n);
     std::atomic<size_t> next{0};
+    // assemblies at k <= 31 take the packed path: every parsing thread also packs its file to 2-bit codes + invalid mask
+    // (skagpu_pack_bases), so 0.375 B per base cross PCIe instead of 1 and the ASCII copy is dropped at once
+    const bool try_packed = k <= 31 && !(proportion_reads > 0) && !getenv("SKA_HOST_ASCII");
+    std::vector<std::vector<uint8_t>> packed2(n), invalid(n);
     auto work = [&] {                                      // host parsing is per-file independent (needletail's job)
         for (size_t i; (i = next.fetch_add(1)) < n;) {
             try {
                 recs[i] = fastx::parse_file(std::get<1>(input_files[i]));
                 n_file1[i] = recs[i].n_rec();
                 if (!std::get<2>(input_files[i]).empty()) fastx::append(recs[i], fastx::parse_file(std::get<2>(input_files[i])));
+                if (try_packed && !recs[i].is_fastq) {
+                    const uint64_t nb = recs[i].seq.size();
+                    packed2[i].assign((nb + 3) / 4, 0);
+                    invalid[i].assign((nb + 7) / 8, 0xFF);
+                    skagpu_pack_bases(recs[i].seq.data(), nb, 0, packed2[i].data(), invalid[i].data());
+                    std::vector<uint8_t>().swap(recs[i].seq);
+                }
             } catch (std::exception& e) { errors[i] = e.what(); }
         }
     };
     size_t nt = std::max<size_t>(1, std::min<size_t>(threads, n));
+    lap("start");
     std::vector<std::thread> th;
     for (size_t t = 1; t < nt; t++) th.emplace_back(work);
     work();
     for (auto& t : th) t.join();
     for (auto& e : errors) if (!e.empty()) throw SkaError(e);
+    lap("files parsed (+ packed)");
+    check(skagpu_set_device(0));                           // the context is created on a helper thread since program start (main.cpp)
+    lap("cuda context ready");
 
-    std::vector<ska_input_t> in(n);
     std::vector<std::string> names(n);
-    for (size_t i = 0; i < n; i++) {
-        in[i].seq = recs[i].seq.data();
-        in[i].qual = recs[i].is_fastq ? recs[i].qual.data() : nullptr;
-        in[i].rec_off = recs[i].rec_off.data();
-        in[i].n_rec = recs[i].n_rec();
-        in[i].n_rec_file1 = n_file1[i];
-        names[i] = std::get<0>(input_files[i]);
-    }
-    ska_array_t* h = nullptr;
-    int rcode = skagpu_build(in.data(), n, (uint32_t)k, rc, qual.min_count, qual.min_qual, (int)qual.qual_filter, proportion_reads, &h);
-    if (rcode) {
-        std::string msg = skagpu_last_error();
+    for (size_t i = 0; i < n; i++) names[i] = std::get<0>(input_files[i]);
+    bool all_packed = try_packed;
+    for (size_t i = 0; i < n; i++) all_packed = all_packed && !recs[i].is_fastq;
+    auto fail = [&](std::string msg) {
         // "<file> has no valid sequence" names the file in the reference (ska_dict.rs:375)
         size_t p = msg.find("sample ");
         if (p == 0 && msg.find("has no valid sequence") != std::string::npos) {
@@ -149,7 +182,34 @@ MergeSkaArray build_and_merge(const std::vector<InputFastx>& input_files, size_t
             if (idx < n) msg = std::get<1>(input_files[idx]) + " has no valid sequence";
         }
         throw SkaError(msg);
+    };
+    if (all_packed) {
+        std::vector<ska_input_packed_t> pin(n);
+        for (size_t i = 0; i < n; i++) pin[i] = {packed2[i].data(), invalid[i].data(), recs[i].rec_off.data(), recs[i].n_rec(), n_file1[i]};
+        ska_array_t* h = nullptr;
+        if (skagpu_build_packed(pin.data(), n, (uint32_t)k, rc, &h)) fail(skagpu_last_error());
+        lap("built on the device");
+        return MergeSkaArray(h, names);
     }
+    if (try_packed)                                        // mixed FASTA/FASTQ input: back to bytes for the samples packed above
+        for (size_t i = 0; i < n; i++)
+            if (!recs[i].is_fastq) {
+                const uint64_t nb = recs[i].rec_off.back();
+                recs[i].seq.resize(nb);
+                for (uint64_t p = 0; p < nb; p++)
+                    recs[i].seq[p] = (invalid[i][p >> 3] >> (p & 7)) & 1 ? 'N' : "ACTG"[(packed2[i][p >> 2] >> (2 * (p & 3))) & 3];
+            }
+    std::vector<ska_input_t> in(n);
+    for (size_t i = 0; i < n; i++) {
+        in[i].seq = recs[i].seq.data();
+        in[i].qual = recs[i].is_fastq ? recs[i].qual.data() : nullptr;
+        in[i].rec_off = recs[i].rec_off.data();
+        in[i].n_rec = recs[i].n_rec();
+        in[i].n_rec_file1 = n_file1[i];
+    }
+    ska_array_t* h = nullptr;
+    if (skagpu_build(in.data(), n, (uint32_t)k, rc, qual.min_count, qual.min_qual, (int)qual.qual_filter, proportion_reads, &h))
+        fail(skagpu_last_error());
     return MergeSkaArray(h, names);
 }
 
@@ -211,6 +271,7 @@ void align(MergeSkaArray& a, const std::string& output, FilterType filter, bool 
     FILE* f = set_ostream(output);
     a.write_fasta(f);
     if (f != stdout) fclose(f); else fflush(f);
+    lap("alignment written");
 }
 
 void distance(MergeSkaArray& a, const std::string& output, double min_freq, bool filt_ambig) {

@@ -6,6 +6,7 @@
 //             ska_version, k_bits     (u128 keys >= 2^64 as tag 2 + big-endian byte string)
 #include "skf_codec.hpp"
 
+#include <emmintrin.h>
 #include <nmmintrin.h>
 
 #include <algorithm>
@@ -18,6 +19,18 @@
 #include <thread>
 
 namespace skf {
+
+void prefault(uint8_t* p, size_t n, int threads) {
+    const int nt = (int)std::max<size_t>(1, std::min<size_t>((size_t)std::max(1, threads), n >> 24));
+    auto part = [&](int t) {
+        const size_t b0 = n / nt * t, b1 = t + 1 == nt ? n : n / nt * (t + 1);
+        for (size_t i = b0; i < b1; i += 4096) ((volatile uint8_t*)p)[i] = 0;
+    };
+    std::vector<std::thread> th;
+    for (int t = 1; t < nt; t++) th.emplace_back(part, t);
+    part(0);
+    for (auto& t : th) t.join();
+}
 
 // ------------------------------------------------------------------------------------------ CRC-32C
 uint32_t crc32c(const uint8_t* p, size_t n) {
@@ -74,7 +87,19 @@ static void snappy_decompress(const uint8_t* in, size_t n, uint8_t* dst, size_t 
             if (off == 0 || off > o) throw std::runtime_error("skf: bad snappy copy offset");
             if (o + len > ulen) throw std::runtime_error("skf: snappy length mismatch");
             if (off >= len) memcpy(dst + o, dst + o - off, len);
-            else for (size_t i = 0; i < len; i++) dst[o + i] = dst[o - off + i];   // overlaps its own output (run-length)
+            else if (len < 16) for (size_t i = 0; i < len; i++) dst[o + i] = dst[o - off + i];
+            else {
+                // the copy overlaps its own output: a run of period `off` (2 for a run of one middle base).  What has been
+                // written so far repeats with that period, so pieces can be taken from ever further back: off, 2 off, 4 off ...
+                uint8_t* q = dst + o;
+                size_t rem = len, d = off;
+                while (rem) {
+                    const size_t piece = rem < d ? rem : d;
+                    memcpy(q, q - d, piece);
+                    q += piece; rem -= piece;
+                    if (d <= 16384) d *= 2;
+                }
+            }
             o += len;
         }
     }
@@ -113,6 +138,10 @@ static void snappy_compress(const uint8_t* in, size_t n, std::vector<uint8_t>& o
         size_t cand = table[h];
         table[h] = (uint16_t)i;
         uint32_t cw; memcpy(&cw, in + cand, 4);
+        if (i >= 2) {                                           // the data section is `18 xx 18 xx ...`: a run of one letter is a match at distance 2
+            uint32_t pw; memcpy(&pw, in + i - 2, 4);
+            if (pw == w) { cand = i - 2; cw = w; }
+        }
         if (cand < i && cw == w) {
             size_t len = 4;
             bool open_end = true;                               // extend the match 8 bytes at a time (runs of `18 2D` are long)
@@ -202,7 +231,7 @@ static Payload frame_decode(const uint8_t* d, size_t n, int threads) {
 // The payload is never held in one piece: `fill(offset, len, dst)` materialises any part of it into a worker's 64 KiB
 // buffer (for an array of 3 GB of middle bases the CBOR payload would be 6 GB of `18 xx` pairs).
 template <class Fill>
-static std::vector<uint8_t> frame_encode(size_t payload_size, int threads, Fill fill) {
+static std::vector<std::vector<uint8_t>> frame_encode_chunks(size_t payload_size, int threads, Fill fill) {
     const size_t CH = 65536;
     const size_t n_chunks = (payload_size + CH - 1) / CH;
     std::vector<std::vector<uint8_t>> comp(n_chunks);
@@ -229,7 +258,11 @@ static std::vector<uint8_t> frame_encode(size_t payload_size, int threads, Fill 
     for (int t = 1; t < threads; t++) th.emplace_back(work);
     work();
     for (auto& t : th) t.join();
-    std::vector<uint8_t> out = {0xFF, 0x06, 0x00, 0x00, 's', 'N', 'a', 'P', 'p', 'Y'};
+    return comp;
+}
+static const uint8_t STREAM_ID[10] = {0xFF, 0x06, 0x00, 0x00, 's', 'N', 'a', 'P', 'p', 'Y'};
+static std::vector<uint8_t> join_chunks(const std::vector<std::vector<uint8_t>>& comp) {
+    std::vector<uint8_t> out(STREAM_ID, STREAM_ID + 10);
     size_t total = out.size();
     for (auto& c : comp) total += c.size();
     out.reserve(total);
@@ -273,7 +306,8 @@ struct Reader {
 };
 
 Array decode(const uint8_t* data, size_t len, int threads) {
-    if (threads <= 0) threads = (int)std::max(1u, std::thread::hardware_concurrency());
+    // all hardware threads but one: the caller's CUDA context is usually being created on a helper thread meanwhile
+    if (threads <= 0) threads = (int)std::max(1u, std::thread::hardware_concurrency() > 2 ? std::thread::hardware_concurrency() - 1 : 1u);
     Payload payload = frame_decode(data, len, threads);
     Reader r{payload.p.get(), payload.n};
     Array a;
@@ -333,15 +367,31 @@ Array decode(const uint8_t* data, size_t len, int threads) {
     return a;
 }
 
+static std::vector<uint8_t> read_file(const std::string& path);
+Array decode_file_single_thread(const std::string& path) {
+    std::vector<uint8_t> buf = read_file(path);
+    return decode(buf.data(), buf.size(), 1);
+}
+
 Array load(const std::string& path) {
+    std::vector<uint8_t> buf = read_file(path);
+    return decode(buf.data(), buf.size(), 0);
+}
+
+static std::vector<uint8_t> read_file(const std::string& path) {
     FILE* f = fopen(path.c_str(), "rb");
     if (!f) throw std::runtime_error("No such file or directory: " + path);
     std::vector<uint8_t> buf;
+    if (fseek(f, 0, SEEK_END) == 0) {
+        const long sz = ftell(f);
+        fseek(f, 0, SEEK_SET);
+        if (sz > 0) { buf.resize((size_t)sz); buf.resize(fread(buf.data(), 1, (size_t)sz, f)); }
+    }
     uint8_t tmp[1 << 16];
     size_t n;
-    while ((n = fread(tmp, 1, sizeof tmp, f)) > 0) buf.insert(buf.end(), tmp, tmp + n);
+    while ((n = fread(tmp, 1, sizeof tmp, f)) > 0) buf.insert(buf.end(), tmp, tmp + n);   // streams that cannot seek
     fclose(f);
-    return decode(buf.data(), buf.size(), 0);
+    return buf;
 }
 
 static inline void put_head(std::vector<uint8_t>& o, int major, uint64_t v) {
@@ -352,7 +402,27 @@ static inline void put_head(std::vector<uint8_t>& o, int major, uint64_t v) {
 }
 static inline void put_text(std::vector<uint8_t>& o, const std::string& s) { put_head(o, 3, s.size()); o.insert(o.end(), s.begin(), s.end()); }
 
-std::vector<uint8_t> encode(const Array& a, int threads) {
+// CBOR unsigned integers of v[0, n) appended to `o`, encoded by `threads` workers (10^7 split k-mers are 90 MB of heads)
+template <class Put>
+static void put_parallel(std::vector<uint8_t>& o, size_t n, int threads, Put put_one) {
+    const int nt = (int)std::max<size_t>(1, std::min<size_t>((size_t)threads, n >> 16));
+    std::vector<std::vector<uint8_t>> parts(nt);
+    auto part = [&](int t) {
+        const size_t b0 = n * t / nt, b1 = n * (t + 1) / nt;
+        parts[t].reserve((b1 - b0) * 9 + 16);
+        for (size_t i = b0; i < b1; i++) put_one(parts[t], i);
+    };
+    std::vector<std::thread> th;
+    for (int t = 1; t < nt; t++) th.emplace_back(part, t);
+    part(0);
+    for (auto& t : th) t.join();
+    size_t total = o.size();
+    for (auto& p : parts) total += p.size();
+    o.reserve(total + 256);
+    for (auto& p : parts) o.insert(o.end(), p.begin(), p.end());
+}
+
+static std::vector<std::vector<uint8_t>> encode_chunks(const Array& a, int threads) {
     threads = std::max(1, threads);
     // head: everything before the variant bytes; tail: everything after.  The data section between them is `18 xx`
     // per byte (every middle-base byte is '-' (45) or a letter), written by all threads into uninitialised storage.
@@ -363,22 +433,23 @@ std::vector<uint8_t> encode(const Array& a, int threads) {
     put_text(o, "rc"); o.push_back(a.rc ? 0xF5 : 0xF4);
     put_text(o, "names"); put_head(o, 4, a.names.size()); for (auto& s : a.names) put_text(o, s);
     put_text(o, "split_kmers"); put_head(o, 4, a.n_keys());
-    if (a.key_bits == 64) for (uint64_t v : a.keys) put_head(o, 0, v);
-    else for (size_t i = 0; i < a.keys.size(); i += 2) {
-        uint64_t lo = a.keys[i], hi = a.keys[i + 1];
-        if (!hi) { put_head(o, 0, lo); continue; }
-        o.push_back(0xC2);                                  // tag 2: unsigned bignum, minimal big-endian bytes
+    if (a.key_bits == 64) put_parallel(o, a.keys.size(), threads, [&a](std::vector<uint8_t>& w, size_t i) { put_head(w, 0, a.keys[i]); });
+    else put_parallel(o, a.keys.size() / 2, threads, [&a](std::vector<uint8_t>& w, size_t j) {
+        const uint64_t lo = a.keys[2 * j], hi = a.keys[2 * j + 1];
+        if (!hi) { put_head(w, 0, lo); return; }
+        w.push_back(0xC2);                                  // tag 2: unsigned bignum, minimal big-endian bytes
         int nb = 16; while (nb > 8 && !((hi >> (8 * (nb - 9))) & 0xFF)) nb--;
-        put_head(o, 2, nb);
-        for (int b = nb - 1; b >= 0; b--) o.push_back((uint8_t)(b >= 8 ? hi >> (8 * (b - 8)) : lo >> (8 * b)));
-    }
+        put_head(w, 2, nb);
+        for (int b = nb - 1; b >= 0; b--) w.push_back((uint8_t)(b >= 8 ? hi >> (8 * (b - 8)) : lo >> (8 * b)));
+    });
     put_text(o, "variants"); o.push_back(0xA3);
     put_text(o, "v"); o.push_back(0x01);
     put_text(o, "dim"); o.push_back(0x82); put_head(o, 0, a.n_rows); put_head(o, 0, a.n_samples);
     put_text(o, "data"); put_head(o, 4, a.variants.size());
     std::vector<uint8_t> tail;
     tail.reserve(64 + a.counts.size() * 3);
-    put_text(tail, "variant_count"); put_head(tail, 4, a.counts.size()); for (uint64_t c : a.counts) put_head(tail, 0, c);
+    put_text(tail, "variant_count"); put_head(tail, 4, a.counts.size());
+    put_parallel(tail, a.counts.size(), threads, [&a](std::vector<uint8_t>& w, size_t i) { put_head(w, 0, a.counts[i]); });
     put_text(tail, "ska_version"); put_text(tail, a.ska_version);
     put_text(tail, "k_bits"); put_head(tail, 0, a.key_bits);
 
@@ -405,6 +476,17 @@ std::vector<uint8_t> encode(const Array& a, int threads) {
                 size_t q = 0;
                 uint8_t lt24 = 0;
                 if (j & 1) { const uint8_t b = v[j >> 1]; lt24 |= (uint8_t)(b < 24); w[q++] = b; j++; }
+                {                                                // 16 cells -> 32 bytes per step
+                    const __m128i c18 = _mm_set1_epi8(0x18), c24 = _mm_set1_epi8(24);
+                    __m128i ok = _mm_set1_epi8((char)0xFF);
+                    for (; q + 32 <= n; q += 32, j += 32) {
+                        const __m128i x = _mm_loadu_si128((const __m128i*)(v + (j >> 1)));
+                        ok = _mm_and_si128(ok, _mm_cmpeq_epi8(_mm_min_epu8(x, c24), c24));
+                        _mm_storeu_si128((__m128i*)(w + q), _mm_unpacklo_epi8(c18, x));
+                        _mm_storeu_si128((__m128i*)(w + q + 16), _mm_unpackhi_epi8(c18, x));
+                    }
+                    if (_mm_movemask_epi8(ok) != 0xFFFF) lt24 = 1;
+                }
                 for (; q + 1 < n; q += 2, j += 2) { const uint8_t b = v[j >> 1]; lt24 |= (uint8_t)(b < 24); w[q] = 0x18; w[q + 1] = b; }
                 if (q < n) w[q++] = 0x18;
                 if (lt24) small_p->store(true);
@@ -415,21 +497,24 @@ std::vector<uint8_t> encode(const Array& a, int threads) {
             }
         }
     };
-    std::vector<uint8_t> framed = frame_encode(total, threads, fill);
+    std::vector<std::vector<uint8_t>> framed = frame_encode_chunks(total, threads, fill);
     if (!small.load()) return framed;
     for (size_t i = 0; i < nv; i++) put_head(o, 0, v[i]);
     o.insert(o.end(), tail.begin(), tail.end());
     const uint8_t* whole = o.data();
-    return frame_encode(o.size(), threads, [whole](size_t off, size_t len, uint8_t* dst) { memcpy(dst, whole + off, len); });
+    return frame_encode_chunks(o.size(), threads, [whole](size_t off, size_t len, uint8_t* dst) { memcpy(dst, whole + off, len); });
 }
 
+std::vector<uint8_t> encode(const Array& a, int threads) { return join_chunks(encode_chunks(a, threads)); }
+
 void save(const Array& a, const std::string& path, int threads) {
-    std::vector<uint8_t> bytes = encode(a, threads);
+    const std::vector<std::vector<uint8_t>> chunks = encode_chunks(a, threads);   // written one by one: no second copy of the file
     FILE* f = fopen(path.c_str(), "wb");
     if (!f) throw std::runtime_error("cannot create " + path);
-    size_t w = fwrite(bytes.data(), 1, bytes.size(), f);
-    fclose(f);
-    if (w != bytes.size()) throw std::runtime_error("short write to " + path);
+    bool ok = fwrite(STREAM_ID, 1, 10, f) == 10;
+    for (auto& c : chunks) ok = ok && fwrite(c.data(), 1, c.size(), f) == c.size();
+    ok = fclose(f) == 0 && ok;
+    if (!ok) throw std::runtime_error("short write to " + path);
 }
 
 }  // namespace skf
