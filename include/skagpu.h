@@ -32,6 +32,7 @@ extern "C" {
 typedef struct ska_array ska_array_t;
 typedef struct ska_seqbatch ska_seqbatch_t;
 typedef struct ska_records ska_records_t;
+typedef struct ska_mapping ska_mapping_t;
 
 /* One sample = InputFastx (merge_ska_dict.rs:25) after host-side parsing (needletail's job,
  * ska_dict.rs:131-147): all records of file 1 followed by all records of file 2, newlines
@@ -186,6 +187,33 @@ int skagpu_merge_partial_rows_dev(const void* keys_dev, const void* variants_dev
  * pair {mismatches, matches, dist_int, n_both}: integers, so row shards add up exactly (all-reduce);
  * distance = dist_int (filt_ambig) or n_both - dist_int/36 (allow-ambiguous), matches += constant. */
 int skagpu_distance_counters(const ska_array_t* a, int filt_ambig, uint64_t* counters);
+
+/* ---- the other consumers of a built array: joins on the split-k-mer key ----------------
+ * Arrays are taken in ascending key order; one loaded from a reference-written .skf (hashbrown order) is sorted in place on
+ * first use -- row order is not part of an array's value (the reference's own tests compare as sets).
+ *
+ * skagpu_merge_arrays    MergeSkaDict::extend (merge_ska_dict.rs:160-193; `ska merge`, generic_modes.rs:90-106): the samples of b
+ *                        are appended to those of a, rows joined on the key, cells a sample lacks are '-'.  Errors like the
+ *                        reference's panics: "K-mer lengths do not match: {b.k} {a.k}", "Strand use inconsistent".
+ * skagpu_delete_samples  MergeSkaArray::delete_samples (merge_ska_array.rs:231-271; `ska delete`): columns sample_idx[] are
+ *                        dropped, counts recomputed, rows left without any base removed.  Name lookup stays with the host.
+ * skagpu_weed            RefSka::new(k, weed_fasta, rc, false, false) + MergeSkaArray::weed (ska_ref.rs:189-311,
+ *                        merge_ska_array.rs:452-487; `ska weed`, generic_modes.rs:218-266): rows whose split k-mer occurs in the
+ *                        weed sequences are removed (reverse: only those are kept).  weed_fasta = ONE parsed FASTA (all records).
+ * skagpu_map             RefSka::new + RefSka::map (ska_ref.rs:189-311, 508-533; `ska map`): every split k-mer of the reference,
+ *                        in reference order, is looked up in the array; a hit contributes its row, complemented with RC_IUPAC
+ *                        (bit_encoding.rs:474-507) when the reference k-mer is on the reverse strand.  skagpu_map_export gives the
+ *                        hits' middle-base positions (coordinates of the reference's records laid back to back), their rows
+ *                        (n_mapped x n_samples) and, if asked, the K1 record of every reference position (key << 4 | one-hot
+ *                        middle, all-ones = no split k-mer starts here; two words per position for k > 31) from which the host
+ *                        derives the repeat mask (ska_ref.rs:256-296).  The pseudo-alignment / VCF writers are host code. */
+int skagpu_merge_arrays(ska_array_t* a, ska_array_t* b, ska_array_t** out);
+int skagpu_delete_samples(ska_array_t* a, const uint32_t* sample_idx, size_t n_delete);
+int skagpu_weed(ska_array_t* a, const ska_input_t* weed_fasta, int reverse, uint64_t* n_weed_kmers);
+int skagpu_map(ska_array_t* a, const ska_input_t* ref_fasta, ska_mapping_t** out);
+int skagpu_map_dims(const ska_mapping_t* m, uint64_t* n_mapped, uint64_t* n_ref_kmers, uint64_t* n_samples, uint64_t* n_positions);
+int skagpu_map_export(const ska_mapping_t* m, uint64_t* middle_positions, uint8_t* variants_rowmajor, uint64_t* ref_records);
+void skagpu_map_free(ska_mapping_t* m);
 
 /* Self-check of a device-resident array (no reference counterpart; bench.py's in-run parity check and the tests):
  * out[0] = order-independent checksum over the non-'-' cells (key, column - col_lo, letter) of columns [col_lo, col_hi)

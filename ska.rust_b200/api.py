@@ -35,7 +35,8 @@ EXPORTS = [
     "skagpu_records_free", "skagpu_merge_records_dev", "skagpu_distance_counters", "skagpu_merge_prefix_bits",
     "skagpu_array_dev", "skagpu_key_cumulative", "skagpu_merge_partial_rows_dev", "skagpu_array_checksum",
     "skagpu_pack_bases", "skagpu_build_packed", "skagpu_seqbatch_upload_packed", "skagpu_export_transposed_async",
-    "skagpu_export_wait", "skagpu_seqbatch_upload_packed_async",
+    "skagpu_export_wait", "skagpu_seqbatch_upload_packed_async", "skagpu_merge_arrays", "skagpu_delete_samples", "skagpu_weed",
+    "skagpu_map", "skagpu_map_dims", "skagpu_map_export", "skagpu_map_free",
 ]
 
 
@@ -94,6 +95,13 @@ def lib():
                                                     C.c_void_p, C.c_uint64, C.c_uint32, C.c_int, C.c_void_p]
         L.skagpu_distance_counters.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
         L.skagpu_array_checksum.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p]
+        L.skagpu_merge_arrays.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        L.skagpu_delete_samples.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
+        L.skagpu_weed.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+        L.skagpu_map.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        L.skagpu_map_dims.argtypes = [C.c_void_p] + [C.c_void_p] * 4
+        L.skagpu_map_export.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.skagpu_map_free.argtypes = [C.c_void_p]
         L.skagpu_pack_bases.restype = None
         L.skagpu_pack_bases.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.c_void_p, C.c_void_p]
         L.skagpu_build_packed.argtypes = [C.c_void_p, C.c_size_t, C.c_uint32, C.c_int, C.c_void_p]
@@ -429,6 +437,43 @@ class MergeSkaArray:
         _check(lib().skagpu_distance_counters(self._h, int(filt_ambig), out.ctypes.data))
         return out[:n * (n - 1) // 2]
 
+    # ---- joins on the key
+    def delete_samples(self, del_names):
+        """MergeSkaArray::delete_samples (merge_ska_array.rs:231-271)"""
+        del_names = list(del_names)
+        if not del_names or len(del_names) == self.nsamples():
+            raise SkaError("Invalid number of samples to remove")
+        missing = [n for n in del_names if n not in self._names]
+        if missing:
+            raise SkaError(f"Could not find sample(s): {set(missing)}")
+        idx = np.array([self._names.index(n) for n in del_names], dtype=np.uint32)
+        _check(lib().skagpu_delete_samples(self._h, idx.ctypes.data, len(idx)))
+        self._names = [n for n in self._names if n not in del_names]
+
+    def weed(self, weed_sample, reverse=False):
+        """RefSka::new + MergeSkaArray::weed (merge_ska_array.rs:452-487); weed_sample: a Sample holding the weed FASTA's records
+        -> number of split k-mers in the weed sequences"""
+        n = C.c_uint64()
+        _check(lib().skagpu_weed(self._h, _inputs_array([weed_sample]), int(reverse), C.byref(n)))
+        return int(n.value)
+
+    def map(self, ref_sample, want_records=False):
+        """RefSka::new + RefSka::map (ska_ref.rs:189-311, 508-533); ref_sample: a Sample holding the reference's records ->
+        (middle positions uint64[M] in record-concatenated coordinates, mapped variants (M, N) uint8, n_ref_kmers[, K1 records])"""
+        h = C.c_void_p()
+        _check(lib().skagpu_map(self._h, _inputs_array([ref_sample]), C.byref(h)))
+        try:
+            v = [C.c_uint64() for _ in range(4)]
+            _check(lib().skagpu_map_dims(h, *[C.byref(x) for x in v]))
+            m, n_ref, n, n_pos = (x.value for x in v)
+            pos = np.zeros(m, dtype=np.uint64)
+            var = np.zeros((m, n), dtype=np.uint8)
+            rec = np.zeros(n_pos * (2 if self.kmer_len() > 31 else 1), dtype=np.uint64) if want_records else None
+            _check(lib().skagpu_map_export(h, pos.ctypes.data, var.ctypes.data, rec.ctypes.data if rec is not None else None))
+        finally:
+            lib().skagpu_map_free(h)
+        return (pos, var, n_ref, rec) if want_records else (pos, var, n_ref)
+
     def checksum(self, col_lo=0, col_hi=None):
         """-> (cell checksum over columns [col_lo, col_hi), rows with a cell there, rows with a wrong count, keys out of order)"""
         out = np.zeros(4, dtype=np.uint64)
@@ -508,6 +553,13 @@ def build_from_samples(samples, names, k, rc, qual=None, proportion_reads=None):
     _check(lib().skagpu_build(_inputs_array(samples), len(samples), k, int(rc), qual.min_count, qual.min_qual, qf,
                               float(proportion_reads) if proportion_reads else 0.0, C.byref(h)))
     return MergeSkaArray(h, names)
+
+
+def merge_arrays(a, b):
+    """MergeSkaDict::extend (merge_ska_dict.rs:160-193): samples of b appended to those of a, rows joined on the key"""
+    h = C.c_void_p()
+    _check(lib().skagpu_merge_arrays(a._h, b._h, C.byref(h)))
+    return MergeSkaArray(h, a.names() + b.names(), a.ska_version)
 
 
 def build_from_packed(samples, names, k, rc):

@@ -440,6 +440,12 @@ static thread_local std::string g_err;
 
 struct ska_array { Array a; };
 struct ska_seqbatch { std::unique_ptr<SeqBatch> b; };
+struct ska_mapping {            // RefSka after map(): hits in reference order
+    uint64_t n_samples = 0, n_ref_kmers = 0, n_pos = 0; uint32_t k = 0; int key_words = 1;
+    std::vector<uint64_t> pos;          // window-start positions of the hits (record-concatenated reference coordinates)
+    std::vector<uint64_t> records;      // K1 records of every reference position
+    DevBuf<uint8_t> rows;               // n_hits x n_samples, complemented where the reference k-mer is on the reverse strand
+};
 struct ska_records {            // packed records of one rank, grouped by first-level region; arena memory, valid until the next build
     uint64_t* rec = nullptr; uint64_t n = 0;
     uint32_t k = 0; bool rc = false; PartPlan plan;
@@ -926,6 +932,86 @@ int skagpu_distance_counters(const ska_array_t* h, int filt_ambig, uint64_t* cou
     return 0;
     API_CATCH
 }
+
+// ---- joins on the key: ska merge / delete / weed / map (setops.cu)
+int skagpu_merge_arrays(ska_array_t* a, ska_array_t* b, ska_array_t** out) {
+    API_TRY
+    *out = nullptr;
+    if (!a || !b) throw Error("null array");
+    ctx().ensure();
+    std::unique_ptr<ska_array> h(new ska_array());
+    extend_arrays(a->a, b->a, h->a);
+    *out = h.release();
+    return 0;
+    API_CATCH
+}
+
+int skagpu_delete_samples(ska_array_t* a, const uint32_t* sample_idx, size_t n_delete) {
+    API_TRY
+    if (!a) throw Error("null array");
+    ctx().ensure();
+    delete_columns(a->a, std::vector<uint32_t>(sample_idx, sample_idx + n_delete));
+    return 0;
+    API_CATCH
+}
+
+int skagpu_weed(ska_array_t* a, const ska_input_t* weed_fasta, int reverse, uint64_t* n_weed_kmers) {
+    API_TRY
+    if (!a || !weed_fasta) throw Error("null argument");
+    ctx().ensure();
+    if (weed_fasta->qual) throw Error("Cannot create reference from FASTQ files");          // ska_ref.rs:204-206
+    std::unique_ptr<SeqBatch> b = upload(weed_fasta, 1, 0.0);
+    const uint64_t n = weed_rows(a->a, *b, reverse != 0);
+    if (n_weed_kmers) *n_weed_kmers = n;
+    return 0;
+    API_CATCH
+}
+
+int skagpu_map(ska_array_t* a, const ska_input_t* ref_fasta, ska_mapping_t** out) {
+    API_TRY
+    *out = nullptr;
+    if (!a || !ref_fasta) throw Error("null argument");
+    ctx().ensure();
+    if (ref_fasta->qual) throw Error("Cannot create reference from FASTQ files");           // ska_ref.rs:204-206
+    std::unique_ptr<SeqBatch> b = upload(ref_fasta, 1, 0.0);
+    std::unique_ptr<ska_mapping> m(new ska_mapping());
+    m->n_samples = a->a.n_samples; m->k = a->a.k; m->key_words = a->a.k > 31 ? 2 : 1; m->n_pos = b->n_pos;
+    map_reference(a->a, *b, m->pos, m->rows, m->n_ref_kmers, &m->records);
+    SKA_CUDA(cudaStreamSynchronize(ctx().stream));
+    if (m->n_ref_kmers == 0) throw Error("reference has no valid sequence");                 // ska_ref.rs:253-255
+    *out = m.release();
+    return 0;
+    API_CATCH
+}
+
+int skagpu_map_dims(const ska_mapping_t* m, uint64_t* n_mapped, uint64_t* n_ref_kmers, uint64_t* n_samples, uint64_t* n_positions) {
+    API_TRY
+    if (!m) throw Error("null mapping");
+    if (n_mapped) *n_mapped = m->pos.size();
+    if (n_ref_kmers) *n_ref_kmers = m->n_ref_kmers;
+    if (n_samples) *n_samples = m->n_samples;
+    if (n_positions) *n_positions = m->n_pos;
+    return 0;
+    API_CATCH
+}
+
+int skagpu_map_export(const ska_mapping_t* m, uint64_t* middle_positions, uint8_t* variants, uint64_t* ref_records) {
+    API_TRY
+    if (!m) throw Error("null mapping");
+    Context& c = ctx();
+    c.ensure();
+    const uint64_t h = (m->k - 1) / 2;
+    if (middle_positions) for (size_t i = 0; i < m->pos.size(); i++) middle_positions[i] = m->pos[i] + h;
+    if (variants && m->rows.n) {
+        SKA_CUDA(cudaMemcpyAsync(variants, m->rows.p, m->rows.bytes(), cudaMemcpyDeviceToHost, c.stream));
+        SKA_CUDA(cudaStreamSynchronize(c.stream));
+    }
+    if (ref_records && !m->records.empty()) memcpy(ref_records, m->records.data(), m->records.size() * 8);
+    return 0;
+    API_CATCH
+}
+
+void skagpu_map_free(ska_mapping_t* m) { delete m; }
 
 int skagpu_array_checksum(const ska_array_t* h, uint32_t col_lo, uint32_t col_hi, uint64_t* out) {
     API_TRY

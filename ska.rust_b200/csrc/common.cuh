@@ -134,6 +134,7 @@ struct Array {
     bool rc = false;
     uint32_t key_bits = 64;
     uint64_t n_rows = 0, n_keys = 0, n_samples = 0;
+    bool sorted = false;              // keys known to ascend (everything built here; loaded arrays are checked / sorted on first need)
     DevBuf<uint64_t> keys;            // n_keys * (key_bits/64) words, (lo,hi) for 128-bit
     DevBuf<uint8_t> variants;         // n_rows * n_samples, row-major
     DevBuf<uint32_t> counts;          // n_rows
@@ -151,6 +152,7 @@ void launch_k1(const SeqBatch& b, uint32_t k, bool rc, bool strict_qual, uint8_t
 constexpr int K1_ASCII_TAIL = 96, K1_PACKED_TAIL = 128;   // staged positions after a tile (k1_helpers.cuh)
 uint64_t k1_tiles_ready(uint64_t positions_uploaded, int tail);
 size_t padded_positions(uint64_t n_pos);
+bool k1_wide_available();          // launch_k1 handles k > 31 (two-word records)
 // partition.cu: how records are grouped and packed.  P = P1 + P2 prefix bits of the key select the bucket;
 // inside a bucket a record is  key_low << (sb+2) | sample_id << 2 | middle_code  (key_low = key without its top P1 bits)
 struct PartPlan { int key_bits, sb, P, P1, P2, low_bits; };
@@ -198,6 +200,15 @@ void distance_array(const Array& a, double constant, bool filt_ambig, DistOut* h
 // 36 x summed overlap when !filt_ambig); partial sums over this array's rows, addable across row shards
 void distance_counters(const Array& a, bool filt_ambig, uint64_t* h_counters);
 
+// setops.cu: joins on the key (ska merge / delete / weed / map)
+bool keys_sorted(const Array& a);
+void ensure_sorted(Array& a);
+void compact_rows(Array& a, const uint8_t* d_keep);
+void delete_columns(Array& a, const std::vector<uint32_t>& del_cols);
+uint64_t weed_rows(Array& a, const SeqBatch& weed, bool reverse);
+void extend_arrays(Array& a, Array& b, Array& out);
+void map_reference(Array& a, const SeqBatch& ref, std::vector<uint64_t>& h_pos, DevBuf<uint8_t>& mapped, uint64_t& n_ref_kmers,
+                   std::vector<uint64_t>* h_records);
 // verify.cu: {cell checksum over columns [col_lo, col_hi), rows with a cell there, rows with a wrong count, keys out of order}
 void array_checksum(const Array& a, uint32_t col_lo, uint32_t col_hi, uint64_t* h_out);
 

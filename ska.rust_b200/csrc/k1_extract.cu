@@ -30,6 +30,8 @@ uint64_t k1_tiles_ready(uint64_t positions_uploaded, int tail) {      // tiles w
 }
 static_assert(K1_ASCII_TAIL == K1_TAIL && K1_PACKED_TAIL == K1P_TAIL, "tile tails");
 
+bool k1_wide_available() { return false; }
+
 size_t padded_positions(uint64_t n_pos) { return FRONT_PAD + ((n_pos + K1_T - 1) / K1_T) * K1_T + 256; }
 
 // KT > 0: k fixed at compile time (all shifts/masks become immediates); KT == 0: runtime k.

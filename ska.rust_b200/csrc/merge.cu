@@ -985,7 +985,7 @@ static bool merge_items_fused(const uint64_t* rec, const Item* items, uint32_t n
     const uint64_t cap_rows = (uint64_t)(est * 1.06) + 8ull * mx + 4096;
 
     timer().begin("merge");
-    out.k = k; out.rc = rc; out.key_bits = 64; out.n_samples = n_samples;
+    out.k = k; out.rc = rc; out.key_bits = 64; out.n_samples = n_samples; out.sorted = true;
     out.keys.alloc(cap_rows); out.variants.alloc(cap_rows * n_samples); out.counts.alloc(cap_rows);
     unsigned long long* status = arena().take_n<unsigned long long>(n_items);
     FusedCtl* ctl = arena().take_n<FusedCtl>(1);
@@ -1077,7 +1077,7 @@ static void merge_items(const uint64_t* rec, Item* items, uint32_t n_items, int 
     const uint32_t max_u = h_flags[1];
 
     timer().begin("emit");
-    out.k = k; out.rc = rc; out.key_bits = 64; out.n_samples = n_samples;
+    out.k = k; out.rc = rc; out.key_bits = 64; out.n_samples = n_samples; out.sorted = true;
     out.n_rows = out.n_keys = total_rows;
     out.keys.alloc(total_rows); out.variants.alloc(total_rows * n_samples); out.counts.alloc(total_rows);
     if (total_rows) {

@@ -118,7 +118,7 @@ void merge_partial_rows(const uint64_t* keys, const uint8_t* var, const uint32_t
         if ((uint64_t)run_col_base[w] + run_cols[w] > n_samples) throw Error("column block outside the slab");
         n_in += run_rows[w];
     }
-    out.k = k; out.rc = rc; out.key_bits = 64; out.n_samples = n_samples; out.n_rows = out.n_keys = 0;
+    out.k = k; out.rc = rc; out.key_bits = 64; out.n_samples = n_samples; out.n_rows = out.n_keys = 0; out.sorted = true;
     if (n_in == 0) return;
     if (!keys || !var || !cnt) throw Error("null run buffers");
 

@@ -67,7 +67,10 @@ static std::vector<uint8_t> gunzip(const std::vector<uint8_t>& in) {
     return out;
 }
 
-Records parse_bytes(const uint8_t* d, size_t n) {
+static Records parse_bytes_ids(const uint8_t* d, size_t n, std::vector<std::string>* ids);
+Records parse_bytes(const uint8_t* d, size_t n) { return parse_bytes_ids(d, n, nullptr); }
+
+static Records parse_bytes_ids(const uint8_t* d, size_t n, std::vector<std::string>* ids) {
     Records r;
     if (n == 0) throw std::runtime_error("Invalid FASTA/Q record");
     r.rec_off.push_back(0);
@@ -77,6 +80,11 @@ Records parse_bytes(const uint8_t* d, size_t n) {
         while (i < n) {
             // header line
             const uint8_t* nl = (const uint8_t*)memchr(d + i, '\n', n - i);
+            if (ids) {
+                size_t e = nl ? (size_t)(nl - d) : n;
+                if (e > i + 1 && d[e - 1] == '\r') e--;
+                ids->emplace_back((const char*)d + i + 1, e > i + 1 ? e - i - 1 : 0);
+            }
             i = nl ? (size_t)(nl - d) + 1 : n;
             // sequence lines until the next '>' at a line start
             while (i < n && d[i] != '>') {
@@ -107,6 +115,7 @@ Records parse_bytes(const uint8_t* d, size_t n) {
             if (hl == 0 && i >= n) break;                         // trailing newline
             if (!line(sb, sl) || !line(pb, pl) || !line(qb, ql) || d[hb] != '@' || pl == 0 || d[pb] != '+' || sl != ql)
                 throw std::runtime_error("Invalid FASTA/Q record");
+            if (ids) ids->emplace_back((const char*)d + hb + 1, hl ? hl - 1 : 0);
             r.seq.insert(r.seq.end(), d + sb, d + sb + sl);
             r.qual.insert(r.qual.end(), d + qb, d + qb + ql);
             r.rec_off.push_back(r.seq.size());
@@ -122,6 +131,14 @@ Records parse_file(const std::string& path) {
     std::vector<uint8_t> raw = read_all(path);
     if (raw.size() >= 2 && raw[0] == 0x1f && raw[1] == 0x8b) raw = gunzip(raw);
     return parse_bytes(raw.data(), raw.size());
+}
+
+NamedRecords parse_file_named(const std::string& path) {
+    std::vector<uint8_t> raw = read_all(path);
+    if (raw.size() >= 2 && raw[0] == 0x1f && raw[1] == 0x8b) raw = gunzip(raw);
+    NamedRecords out;
+    out.rec = parse_bytes_ids(raw.data(), raw.size(), &out.ids);
+    return out;
 }
 
 void append(Records& a, const Records& b) {

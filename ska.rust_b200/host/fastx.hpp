@@ -20,6 +20,9 @@ struct Records {                     // all records of one file, concatenated
 // Throws std::runtime_error("Invalid path/file: ...") / ("Invalid FASTA/Q record") like the reference's panics.
 Records parse_file(const std::string& path);
 Records parse_bytes(const uint8_t* data, size_t n);
+// With the record ids (header line without '>' / '@'), as RefSka needs chromosome names (ska_ref.rs:207-211).
+struct NamedRecords { Records rec; std::vector<std::string> ids; };
+NamedRecords parse_file_named(const std::string& path);
 // Appends `b` (file 2 of a paired sample) to `a` (file 1).
 void append(Records& a, const Records& b);
 

@@ -16,7 +16,7 @@
 using namespace ska;
 
 [[noreturn]] static void usage_error(const std::string& msg) {
-    fprintf(stderr, "error: %s\n\nUsage: ska <build|align|distance|nk> [OPTIONS]\n", msg.c_str());
+    fprintf(stderr, "error: %s\n\nUsage: ska <build|align|map|distance|merge|delete|weed|nk> [OPTIONS]\n", msg.c_str());
     exit(2);                                               // clap's exit status for argument errors
 }
 
@@ -130,6 +130,41 @@ int main(int argc, char** argv) {
             MergeSkaArray arr = MergeSkaArray::load(a.pos[0]);
             std::string s = arr.display(a.has("--full-info"));
             fwrite(s.data(), 1, s.size(), stdout);
+        } else if (cmd == "map") {                         // lib.rs:663-706
+            Args a = parse(argc, argv, 2, {"-o", "-f", "--format", "--threads"}, {"--ambig-mask", "--repeat-mask"});
+            if (a.pos.size() < 2) usage_error("the following required arguments were not provided: <REFERENCE> <INPUT>...");
+            const std::string fmt = a.has("-f") ? a.get("-f") : a.get("--format", "aln");
+            if (fmt != "aln" && fmt != "vcf") usage_error("invalid value '" + fmt + "' for '--format <FORMAT>'");
+            size_t threads = parse_threads(a.get("--threads", "1"));
+            std::vector<std::string> input(a.pos.begin() + 1, a.pos.end());
+            MergeSkaArray arr = io_utils::load_array(input, threads);
+            RefSka ska_ref(arr.kmer_len(), a.pos[0], arr.rc(), a.has("--ambig-mask"), a.has("--repeat-mask"));
+            generic_modes::map(arr, ska_ref, a.get("-o"), fmt == "vcf", threads);
+        } else if (cmd == "merge") {                       // lib.rs:728-741
+            Args a = parse(argc, argv, 2, {"-o", "--threads"}, {});
+            if (!a.has("-o")) usage_error("the following required arguments were not provided: -o <OUTPUT>");
+            if (a.pos.size() < 2) throw SkaError("Need at least two files to merge");
+            MergeSkaArray first = MergeSkaArray::load(a.pos[0]);
+            generic_modes::merge(first, std::vector<std::string>(a.pos.begin() + 1, a.pos.end()), a.get("-o"),
+                                 (int)std::thread::hardware_concurrency());
+        } else if (cmd == "delete") {                      // lib.rs:742-759
+            Args a = parse(argc, argv, 2, {"-s", "--skf-file", "-o", "-f"}, {});
+            const std::string skf_file = a.has("-s") ? a.get("-s") : a.get("--skf-file");
+            if (skf_file.empty()) usage_error("the following required arguments were not provided: --skf-file <SKF_FILE>");
+            if (a.has("-f") == !a.pos.empty()) usage_error("exactly one of <NAMES> or -f <FILE_LIST> is required");
+            std::vector<std::string> names;
+            for (auto& t : io_utils::get_input_list(a.get("-f"), a.pos)) names.push_back(std::get<0>(t));
+            MergeSkaArray arr = MergeSkaArray::load(skf_file);
+            generic_modes::delete_(arr, names, a.has("-o") ? a.get("-o") : skf_file, (int)std::thread::hardware_concurrency());
+        } else if (cmd == "weed") {                        // lib.rs:760-810
+            Args a = parse(argc, argv, 2, {"-o", "-m", "--min-freq", "--filter"},
+                           {"--reverse", "--filter-ambig-as-missing", "--ambig-mask", "--no-gap-only-sites"});
+            if (a.pos.empty() || a.pos.size() > 2) usage_error("usage: ska weed <SKF_FILE> [WEED_FILE]");
+            double min_freq = parse_01(a.has("-m") ? a.get("-m") : a.get("--min-freq", "0.9"), "frequency");
+            MergeSkaArray arr = MergeSkaArray::load(a.pos[0]);
+            generic_modes::weed(arr, a.pos.size() > 1 ? a.pos[1] : "", a.has("--reverse"), min_freq, a.has("--filter-ambig-as-missing"),
+                                parse_filter(a.get("--filter", "no-filter")), a.has("--ambig-mask"), a.has("--no-gap-only-sites"),
+                                a.has("-o") ? a.get("-o") : a.pos[0], (int)std::thread::hardware_concurrency());
         } else if (cmd == "recode") {
             // host-only helper (no device): decode a .skf and write it again with this codec
             Args a = parse(argc, argv, 2, {"--threads"}, {});
@@ -164,7 +199,7 @@ int main(int argc, char** argv) {
             printf("rows %zu samples %zu file_bytes %zu encode_s %.3f decode_s %.3f\n", rows, n, enc.size(),
                    std::chrono::duration<double>(t1 - t0).count(), std::chrono::duration<double>(t2 - t1).count());
         } else {
-            usage_error("unrecognized subcommand '" + cmd + "' (this engine provides build, align, distance, nk)");
+            usage_error("unrecognized subcommand '" + cmd + "' (this engine provides build, align, map, distance, merge, delete, weed, nk)");
         }
     } catch (std::exception& e) {
         fprintf(stderr, "thread 'main' panicked:\n%s\n", e.what());

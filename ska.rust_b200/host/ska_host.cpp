@@ -1,5 +1,6 @@
 #include "ska_host.hpp"
 
+#include <algorithm>
 #include <atomic>
 #include <chrono>
 #include <cmath>
@@ -128,6 +129,234 @@ std::string MergeSkaArray::display(bool full_info) const {
         o << '\n';
     }
     return o.str();
+}
+
+// ------------------------------------------------------------------------------------------ merge / delete / weed
+MergeSkaArray MergeSkaArray::extend(MergeSkaArray& a, MergeSkaArray& b) {
+    ska_array_t* h = nullptr;
+    check(skagpu_merge_arrays(a.h_, b.h_, &h));
+    std::vector<std::string> names = a.names_;
+    names.insert(names.end(), b.names_.begin(), b.names_.end());                    // merge_ska_dict.rs:169
+    return MergeSkaArray(h, names, a.version_);
+}
+
+void MergeSkaArray::delete_samples(const std::vector<std::string>& del_names) {
+    if (del_names.empty() || del_names.size() == nsamples()) throw SkaError("Invalid number of samples to remove");   // merge_ska_array.rs:232-234
+    std::vector<std::string> wanted = del_names, kept;
+    std::vector<uint32_t> idx;
+    for (size_t i = 0; i < names_.size(); i++) {
+        auto it = std::find(wanted.begin(), wanted.end(), names_[i]);
+        if (it != wanted.end()) { idx.push_back((uint32_t)i); wanted.erase(it); }
+        else kept.push_back(names_[i]);
+    }
+    if (!wanted.empty()) {
+        std::string msg = "Could not find sample(s): {";
+        for (size_t i = 0; i < wanted.size(); i++) msg += (i ? ", \"" : "\"") + wanted[i] + "\"";
+        throw SkaError(msg + "}");                                                  // merge_ska_array.rs:251-253
+    }
+    check(skagpu_delete_samples(h_, idx.data(), idx.size()));
+    names_ = kept;
+}
+
+uint64_t MergeSkaArray::weed(const std::string& weed_fasta, bool reverse) {
+    fastx::Records r = fastx::parse_file(weed_fasta);
+    if (r.is_fastq) throw SkaError("Cannot create reference from FASTQ files");      // ska_ref.rs:204-206
+    ska_input_t in = {r.seq.data(), nullptr, r.rec_off.data(), r.n_rec(), r.n_rec()};
+    uint64_t n_weed = 0;
+    if (skagpu_weed(h_, &in, reverse, &n_weed)) {
+        std::string msg = skagpu_last_error();
+        if (msg.find("no valid sequence") != std::string::npos) msg = weed_fasta + " has no valid sequence";
+        throw SkaError(msg);
+    }
+    return n_weed;
+}
+
+// ------------------------------------------------------------------------------------------ RefSka
+RefSka::RefSka(size_t k, const std::string& filename, bool rc, bool ambig_mask, bool repeat_mask)
+    : k_(k), rc_(rc), ambig_mask_(ambig_mask), repeat_mask_(repeat_mask) {
+    if (k < 5 || k > 63 || k % 2 == 0) throw SkaError("Invalid k-mer length");       // ska_ref.rs:190-192
+    fastx::NamedRecords r = fastx::parse_file_named(filename);
+    if (r.rec.is_fastq) throw SkaError("Cannot create reference from FASTQ files");  // ska_ref.rs:204-206
+    for (size_t i = 0; i < r.rec.n_rec(); i++) {
+        seq_.emplace_back(r.rec.seq.begin() + r.rec.rec_off[i], r.rec.seq.begin() + r.rec.rec_off[i + 1]);
+        std::string id = r.ids[i];                                                   // first whitespace-separated word (ska_ref.rs:207-211)
+        size_t b = id.find_first_not_of(" \t"), e = id.find_first_of(" \t", b == std::string::npos ? 0 : b);
+        chrom_names_.push_back(b == std::string::npos ? "" : id.substr(b, e == std::string::npos ? std::string::npos : e - b));
+    }
+    flat_ = std::move(r.rec.seq);
+    rec_off_ = std::move(r.rec.rec_off);
+}
+
+void RefSka::map(MergeSkaArray& ska_array) {
+    if (k_ != ska_array.kmer_len()) throw SkaError("K-mer sizes do not match ref:" + std::to_string(k_) + " skf:" + std::to_string(ska_array.ksize()));
+    ska_input_t in = {flat_.data(), nullptr, rec_off_.data(), rec_off_.size() - 1, rec_off_.size() - 1};
+    ska_mapping_t* m = nullptr;
+    if (skagpu_map(ska_array.handle(), &in, &m)) throw SkaError(skagpu_last_error());
+    uint64_t n_mapped = 0, n_ref = 0, n_samples = 0, n_pos = 0;
+    check(skagpu_map_dims(m, &n_mapped, &n_ref, &n_samples, &n_pos));
+    n_ref_kmers_ = n_ref;
+    std::vector<uint64_t> mid(n_mapped), records;
+    mapped_variants_.resize(n_mapped * n_samples);
+    const int kw = k_ > 31 ? 2 : 1;
+    if (repeat_mask_) records.resize(n_pos * kw);
+    check(skagpu_map_export(m, mid.data(), mapped_variants_.data(), repeat_mask_ ? records.data() : nullptr));
+    skagpu_map_free(m);
+    mapped_names_ = ska_array.names();
+    mapped_pos_.resize(n_mapped);
+    size_t chrom = 0;
+    for (size_t i = 0; i < n_mapped; i++) {                                          // reference order: chromosomes ascend
+        while (chrom + 1 < rec_off_.size() - 1 && mid[i] >= rec_off_[chrom + 1]) chrom++;
+        mapped_pos_[i] = {chrom, (size_t)(mid[i] - rec_off_[chrom])};
+    }
+    if (repeat_mask_) {
+        // split k-mers seen more than once in the reference (track_repeats, ska_ref.rs:485-496), then their spans (:256-296)
+        const size_t half = (k_ - 1) / 2;
+        std::vector<std::pair<std::pair<uint64_t, uint64_t>, size_t>> ks;            // (key, position)
+        for (size_t p = 0; p < n_pos; p++) {
+            uint64_t lo, hi;
+            if (kw == 1) { if (records[p] == ~0ULL) continue; lo = records[p] >> 4; hi = 0; }
+            else { if ((records[2 * p] & records[2 * p + 1]) == ~0ULL) continue; lo = (records[2 * p] >> 4) | (records[2 * p + 1] << 60); hi = records[2 * p + 1] >> 4; }
+            ks.push_back({{hi, lo}, p});
+        }
+        std::vector<std::pair<std::pair<uint64_t, uint64_t>, size_t>> sorted = ks;
+        std::sort(sorted.begin(), sorted.end());
+        std::vector<char> is_rep(n_pos, 0);
+        size_t n_repeats = 0;
+        for (size_t i = 0; i < sorted.size();) {
+            size_t j = i;
+            while (j < sorted.size() && sorted[j].first == sorted[i].first) j++;
+            if (j - i > 1) { n_repeats++; for (size_t q = i; q < j; q++) is_rep[sorted[q].second] = 1; }
+            i = j;
+        }
+        size_t last_end = 0;
+        for (auto& e : ks) {                                                          // window start p, middle at p + half (concatenated coordinates)
+            if (!is_rep[e.second]) continue;
+            const size_t start = e.second, end = e.second + 2 * half;
+            const size_t from = (start > last_end || start == 0) ? start : last_end + 1;
+            for (size_t pos = from; pos < end + 1; pos++) repeat_coors_.push_back(pos);
+            last_end = end;
+        }
+        (void)n_repeats;
+    }
+}
+
+namespace {
+// AlnWriter (src/ska_ref/aln_writer.rs): the pseudo-alignment of ONE sample against the reference
+struct AlnWriter {
+    size_t next_pos, curr_chrom = 0, last_mapped = 0, last_written = 0, chrom_offset = 0, half;
+    const std::vector<std::vector<uint8_t>>& ref;
+    std::vector<uint8_t> out;
+    bool mask_ambig;
+    std::vector<std::pair<uint8_t, size_t>> middle_out;
+    AlnWriter(const std::vector<std::vector<uint8_t>>& r, size_t k, bool mask) : half((k - 1) / 2), ref(r), mask_ambig(mask) {
+        size_t total = 0; for (auto& c : r) total += c.size();
+        out.assign(total, '-');
+        next_pos = half;
+    }
+    static bool is_ambiguous(uint8_t b) { b |= 0x20; return !(b == 'a' || b == 'c' || b == 'g' || b == 't' || b == 'u' || b == '-'); }   // bit_encoding.rs:58-61
+    void fill_fwd_bases(size_t maximum) {                                              // aln_writer.rs:97-111
+        if (last_written > 0) {
+            const size_t sum = last_mapped + half;
+            const size_t overhang = sum > last_written ? sum - last_written : 0;       // saturating_sub
+            const size_t start = last_written + 1;
+            const size_t end = std::min(start + overhang, maximum);
+            if (end > start) {
+                std::copy(ref[curr_chrom].begin() + start, ref[curr_chrom].begin() + end, out.begin() + start + chrom_offset);
+                last_written = end;
+            }
+        }
+    }
+    void fill_contig() {                                                               // aln_writer.rs:114-120
+        const size_t len = ref[curr_chrom].size();
+        fill_fwd_bases(len);
+        chrom_offset += len; curr_chrom += 1; next_pos = half;
+    }
+    void write_split_kmer(size_t mapped_pos, size_t mapped_chrom, uint8_t base) {      // aln_writer.rs:127-160
+        while (mapped_chrom > curr_chrom) fill_contig();
+        middle_out.push_back({(uint8_t)((is_ambiguous(base) && mask_ambig) ? 'N' : base), mapped_pos + chrom_offset});
+        if (mapped_pos < next_pos) last_mapped = mapped_pos;
+        else {
+            if (mapped_pos > next_pos) fill_fwd_bases(mapped_pos - half);
+            const size_t start = mapped_pos - half, end = mapped_pos;
+            std::copy(ref[curr_chrom].begin() + start, ref[curr_chrom].begin() + end, out.begin() + start + chrom_offset);
+            next_pos = mapped_pos + half + 1; last_mapped = mapped_pos; last_written = mapped_pos;
+        }
+    }
+    void finalise(const std::vector<size_t>& repeats) {                                // aln_writer.rs:164-181
+        while (curr_chrom < ref.size()) fill_contig();
+        for (auto& m : middle_out) out[m.second] = m.first;
+        for (size_t r : repeats) if (r < out.size() && out[r] != '-') out[r] = 'N';
+    }
+};
+}  // namespace
+
+std::vector<std::vector<uint8_t>> RefSka::pseudoalignment(size_t threads) const {
+    if (mapped_pos_.empty()) throw SkaError("No split k-mers mapped to reference");    // ska_ref.rs:556-558
+    const size_t n = mapped_names_.size();
+    std::vector<std::vector<uint8_t>> seqs(n);
+    std::atomic<size_t> next{0};
+    auto work = [&] {
+        for (size_t s; (s = next.fetch_add(1)) < n;) {
+            AlnWriter w(seq_, k_, ambig_mask_);
+            for (size_t i = 0; i < mapped_pos_.size(); i++) {
+                const uint8_t base = mapped_variants_[i * n + s];
+                if (base != '-') w.write_split_kmer(mapped_pos_[i].second, mapped_pos_[i].first, base);
+            }
+            w.finalise(repeat_coors_);
+            seqs[s] = std::move(w.out);
+        }
+    };
+    const size_t nt = std::max<size_t>(1, std::min(threads, n));
+    std::vector<std::thread> th;
+    for (size_t t = 1; t < nt; t++) th.emplace_back(work);
+    work();
+    for (auto& t : th) t.join();
+    return seqs;
+}
+
+void RefSka::write_aln(FILE* f, size_t threads) {
+    if (chrom_names_.size() > 1) fprintf(stderr, "WARN Reference contained multiple contigs, in the output they will be concatenated\n");
+    std::vector<std::vector<uint8_t>> aln = pseudoalignment(threads);
+    for (size_t s = 0; s < aln.size(); s++) {
+        fputc('>', f); fwrite(mapped_names_[s].data(), 1, mapped_names_[s].size(), f); fputc('\n', f);
+        fwrite(aln[s].data(), 1, aln[s].size(), f); fputc('\n', f);
+    }
+}
+
+void RefSka::write_vcf(FILE* f, size_t threads) {
+    std::vector<std::vector<uint8_t>> aln = pseudoalignment(threads);
+    auto base_of = [](uint8_t b) -> char { return (b == 'A' || b == 'C' || b == 'G' || b == 'T') ? (char)b : 'N'; };   // u8_to_base, ska_ref.rs:152-160
+    fputs("##fileformat=VCFv4.4\n", f);                                               // noodles-vcf's default header
+    for (auto& c : chrom_names_) fprintf(f, "##contig=<ID=%s>\n", c.c_str());
+    fputs("#CHROM\tPOS\tID\tREF\tALT\tQUAL\tFILTER\tINFO\tFORMAT", f);
+    for (auto& n : mapped_names_) fprintf(f, "\t%s", n.c_str());
+    fputc('\n', f);
+    const size_t n = aln.size();
+    size_t idx = 0;
+    std::string line;
+    for (size_t chrom = 0; chrom < seq_.size(); chrom++)
+        for (size_t pos = 0; pos < seq_[chrom].size(); pos++, idx++) {                 // IdxCheck (src/ska_ref/idx_check.rs)
+            const uint8_t ref_base = seq_[chrom][pos];
+            std::string alts; std::vector<char> alt_bases; bool variant = false;
+            line.clear();
+            for (size_t s = 0; s < n; s++) {
+                const uint8_t b = aln[s][idx];
+                line += '\t';
+                if (b == ref_base) line += '0';
+                else if (b == '-') { variant = true; line += '.'; }
+                else {
+                    variant = true;
+                    const char ab = base_of(b);
+                    size_t a = std::find(alt_bases.begin(), alt_bases.end(), ab) - alt_bases.begin();
+                    if (a == alt_bases.size()) alt_bases.push_back(ab);
+                    line += std::to_string(a + 1);
+                }
+            }
+            if (!variant) continue;
+            for (size_t a = 0; a < alt_bases.size(); a++) { if (a) alts += ','; alts += alt_bases[a]; }
+            fprintf(f, "%s\t%zu\t.\t%c\t%s\t.\t.\t.\tGT%s\n", chrom_names_[chrom].c_str(), pos + 1, base_of(ref_base),
+                    alts.empty() ? "." : alts.c_str(), line.c_str());
+        }
 }
 
 // ------------------------------------------------------------------------------------------ build_and_merge
@@ -287,6 +516,37 @@ void distance(MergeSkaArray& a, const std::string& output, double min_freq, bool
             fprintf(f, "%s\t%s\t%.2f\t%.5f\t%llu\t%llu\n", names[i].c_str(), names[j].c_str(), d[p].distance, d[p].mismatch_prop,
                     (unsigned long long)d[p].match_count, (unsigned long long)d[p].mismatch_count);
     if (f != stdout) fclose(f); else fflush(f);
+}
+
+void map(MergeSkaArray& a, RefSka& ska_ref, const std::string& output, bool vcf, size_t threads) {
+    ska_ref.map(a);
+    FILE* f = set_ostream(output);
+    if (vcf) ska_ref.write_vcf(f, threads); else ska_ref.write_aln(f, threads);
+    if (f != stdout) fclose(f); else fflush(f);
+}
+
+void merge(MergeSkaArray& first, const std::vector<std::string>& skf_files, const std::string& output, int threads) {
+    MergeSkaArray merged = std::move(first);
+    for (auto& f : skf_files) {
+        MergeSkaArray next = MergeSkaArray::load(f);
+        MergeSkaArray joined = MergeSkaArray::extend(merged, next);
+        merged = std::move(joined);
+    }
+    save_skf(merged, output, threads);
+}
+
+void delete_(MergeSkaArray& a, const std::vector<std::string>& names, const std::string& out_file, int threads) {
+    a.delete_samples(names);
+    save_skf(a, out_file, threads);                        // suffix added if missing (generic_modes.rs:200-205)
+}
+
+void weed(MergeSkaArray& a, const std::string& weed_file, bool reverse, double min_freq, bool filter_ambig_as_missing, FilterType filter,
+          bool ambig_mask, bool ignore_const_gaps, const std::string& out_file, int threads) {
+    if (!weed_file.empty()) a.weed(weed_file, reverse);
+    const size_t threshold = (size_t)std::floor((double)a.nsamples() * min_freq);        // floor here, ceil in align (generic_modes.rs:249)
+    if (threshold > 0 || filter != FilterType::NoFilter || ambig_mask || ignore_const_gaps)
+        a.filter(threshold, filter_ambig_as_missing, filter, ambig_mask, ignore_const_gaps, true);
+    a.save(out_file, threads);                             // exactly the name given (generic_modes.rs:262-265)
 }
 
 void save_skf(const MergeSkaArray& a, const std::string& output, int threads) {

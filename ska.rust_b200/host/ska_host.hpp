@@ -47,6 +47,12 @@ class MergeSkaArray {
     void write_fasta(FILE* f) const;                                         // merge_ska_array.rs:499-517
     std::string display(bool full_info) const;                               // merge_ska_array.rs:649-698
 
+    // ---- joins on the key: ska merge / delete / weed
+    static MergeSkaArray extend(MergeSkaArray& a, MergeSkaArray& b);         // MergeSkaDict::extend, merge_ska_dict.rs:160-193
+    void delete_samples(const std::vector<std::string>& del_names);          // merge_ska_array.rs:231-271
+    uint64_t weed(const std::string& weed_fasta, bool reverse);              // RefSka::new + weed, merge_ska_array.rs:452-487
+    ska_array_t* handle() const { return h_; }
+
     size_t nsamples() const;
     size_t ksize() const;
     size_t kmer_len() const;
@@ -65,6 +71,31 @@ class MergeSkaArray {
 MergeSkaArray build_and_merge(const std::vector<InputFastx>& input_files, size_t k, bool rc, const QualOpts& qual,
                               size_t threads, double proportion_reads /* <= 0: None */);
 
+// RefSka (src/ska_ref.rs): a reference FASTA, its split k-mers, and after map() the middle bases of every sample at the
+// reference positions where a split k-mer of the array occurs.  The lookup runs on the device (skagpu_map); the
+// pseudo-alignment writer (src/ska_ref/aln_writer.rs) and the VCF writer (ska_ref.rs:636-752) are host code, sample-parallel.
+class RefSka {
+  public:
+    RefSka(size_t k, const std::string& filename, bool rc, bool ambig_mask, bool repeat_mask);      // ska_ref.rs:189-311 (file part)
+    void map(MergeSkaArray& ska_array);                                                              // ska_ref.rs:508-533
+    void write_aln(FILE* f, size_t threads);                                                         // ska_ref.rs:636-660
+    void write_vcf(FILE* f, size_t threads);                                                         // ska_ref.rs:662-752
+    size_t ksize() const { return n_ref_kmers_; }
+
+  private:
+    std::vector<std::vector<uint8_t>> pseudoalignment(size_t threads) const;                        // ska_ref.rs:555-587
+    size_t k_; bool rc_, ambig_mask_, repeat_mask_;
+    std::vector<std::string> chrom_names_;
+    std::vector<std::vector<uint8_t>> seq_;
+    std::vector<uint8_t> flat_;                  // records back to back (what goes to the device)
+    std::vector<uint64_t> rec_off_;
+    std::vector<size_t> repeat_coors_;
+    size_t n_ref_kmers_ = 0;
+    std::vector<std::pair<size_t, size_t>> mapped_pos_;   // (chrom, pos)
+    std::vector<uint8_t> mapped_variants_;                // rows loci, columns samples
+    std::vector<std::string> mapped_names_;
+};
+
 namespace io_utils {
 std::vector<InputFastx> read_input_fastas(const std::vector<std::string>& seq_files);               // io_utils.rs:31-46
 std::vector<InputFastx> get_input_list(const std::string& file_list, const std::vector<std::string>& seq_files);  // :116-146
@@ -78,6 +109,11 @@ void align(MergeSkaArray& a, const std::string& output /* "" = stdout */, Filter
            bool ignore_const_gaps, double min_freq, bool filter_ambig_as_missing);                   // generic_modes.rs:22-50
 void distance(MergeSkaArray& a, const std::string& output, double min_freq, bool filt_ambig);        // generic_modes.rs:136-189
 void save_skf(const MergeSkaArray& a, const std::string& output, int threads);                       // generic_modes.rs:270-283
+void map(MergeSkaArray& a, RefSka& ska_ref, const std::string& output, bool vcf, size_t threads);    // generic_modes.rs:53-84
+void merge(MergeSkaArray& first, const std::vector<std::string>& skf_files, const std::string& output, int threads);   // :90-106
+void delete_(MergeSkaArray& a, const std::vector<std::string>& names, const std::string& out_file, int threads);      // :191-213
+void weed(MergeSkaArray& a, const std::string& weed_file, bool reverse, double min_freq, bool filter_ambig_as_missing, FilterType filter,
+          bool ambig_mask, bool ignore_const_gaps, const std::string& out_file, int threads);       // :215-266
 }  // namespace generic_modes
 
 }  // namespace ska

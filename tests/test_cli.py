@@ -161,3 +161,94 @@ def test_cli_fastq_rfile(gold_in, tmp_path):
     assert O.var_hash(run(["align", "c1.skf"], cwd=str(tmp_path)).stdout) == {("C", "W")}
     run(["build", "-f", str(rfile), "-o", "c3", "--min-count", "3", "-k", "7"], cwd=str(tmp_path))
     assert O.var_hash(run(["align", "c3.skf"], cwd=str(tmp_path)).stdout) == {("C", "T")}
+
+
+# ------------------------------------------------------------------ ska merge / delete / weed / map
+def matches(out, golden):
+    """snapbox stdout_matches_path: `[..]` in the golden matches anything up to the end of the line"""
+    import re
+    pat = "".join(".*" if part == "[..]" else re.escape(part) for part in re.split(r"(\[\.\.\])", golden.decode()))
+    return re.fullmatch(pat, out.decode(), flags=re.S) is not None
+
+
+def nk_sets(text):
+    """`ska nk --full-info`: header lines exactly, k-mer lines as a set (row order is unspecified in the reference)"""
+    head, _, body = text.partition("\n\n")
+    return head, sorted(l for l in body.splitlines() if l)
+
+
+@pytest.mark.gpu
+def test_cli_merge_delete(gold_in, gold_ok, tmp_path):
+    """tests/skf_ops.rs:11-92 merge_delete"""
+    wd = str(tmp_path)
+    run(["build", gold_in("test_1.fa"), "-o", "test_1"], cwd=wd)
+    run(["build", gold_in("test_2.fa"), "-o", "test_2"], cwd=wd)
+    run(["merge", "test_1.skf", "test_2.skf", "-o", "merge"], cwd=wd)
+    assert os.path.exists(tmp_path / "merge.skf")
+    assert matches(run(["nk", "merge.skf"], cwd=wd).stdout, gold_ok("merge_nk.stdout"))
+    # merged file == a joint build, row for row
+    joint = O.OracleArray.build_from_files([gold_in("test_1.fa"), gold_in("test_2.fa")], k=31)
+    d = skf_py.load_skf(str(tmp_path / "merge.skf"))
+    keys, var, cnt = joint.export()
+    assert d["split_kmers"] == keys and d["variants"] == var.tobytes() and d["variant_count"] == [int(c) for c in cnt]
+    assert run(["delete", "-s", "merge.skf", "test_3"], cwd=wd, check=False).returncode != 0
+    test1_nk = run(["nk", "test_1.skf"], cwd=wd).stdout
+    run(["delete", "-s", "merge.skf", "test_2"], cwd=wd)
+    assert run(["nk", "merge.skf"], cwd=wd).stdout == test1_nk
+    assert run(["delete", "-s", "merge.skf", "-f", gold_in("missing_delete.txt")], cwd=wd, check=False).returncode != 0
+
+
+@pytest.mark.gpu
+def test_cli_weed(gold_in, gold_ok, tmp_path):
+    """tests/skf_ops.rs:165-257 weed (k <= 31 part)"""
+    import shutil
+    wd = str(tmp_path)
+    shutil.copy(gold_in("merge.skf"), tmp_path / "merge.skf")
+    run(["weed", "merge.skf", gold_in("weed.fa"), "-v"], cwd=wd)
+    assert run(["align", "merge.skf"], cwd=wd).stdout == gold_ok("weed_align.stdout")
+    run(["weed", "merge.skf", "--filter", "no-const", "--min-freq", "1"], cwd=wd)
+    out = run(["nk", "merge.skf", "--full-info"], cwd=wd).stdout
+    assert matches(out, gold_ok("weed_nk.stdout"))
+    shutil.copy(gold_in("merge_k9.skf"), tmp_path / "merge_k9.skf")
+    run(["weed", "merge_k9.skf", "--ambig-mask"], cwd=wd)
+    assert matches(run(["nk", "merge_k9.skf"], cwd=wd).stdout, gold_ok("weed_nk_k9.stdout"))
+    shutil.copy(gold_in("merge.skf"), tmp_path / "merge.skf")
+    run(["weed", "merge.skf", gold_in("weed.fa"), "--reverse", "-v"], cwd=wd)
+    assert run(["align", "merge.skf"], cwd=wd).stdout == gold_ok("weed_align_reverse.stdout")
+
+
+@pytest.mark.gpu
+def test_cli_map(gold_in, gold_ok, tmp_path):
+    """tests/map.rs: map_aln, map_vcf, map_rev_comp, repeat_mask (k <= 31 cases)"""
+    wd = str(tmp_path)
+    ref, ref2 = gold_in("test_ref.fa"), gold_in("test_ref_two_chrom.fa")
+    run(["map", ref, gold_in("test_1.fa"), gold_in("test_2.fa"), "-o", "map.aln"], cwd=wd)
+    assert os.path.exists(tmp_path / "map.aln")
+    assert run(["map", ref, gold_in("merge.skf"), "-v", "--threads", "2"], cwd=wd).stdout == gold_ok("map_aln.stdout")
+    assert run(["map", ref, gold_in("merge_k9.skf")], cwd=wd).stdout == gold_ok("map_aln_k9.stdout")
+    assert run(["map", ref, gold_in("merge_k9.skf"), "--ambig-mask", "-v"], cwd=wd).stdout == gold_ok("map_aln_k9_filter.stdout")
+    assert run(["map", ref2, gold_in("merge.skf")], cwd=wd).stdout == gold_ok("map_aln_two_chrom.stdout")
+    assert run(["map", ref, gold_in("test_1.fa"), gold_in("indel_test.fa")], cwd=wd).stdout == gold_ok("map_aln_indels.stdout")
+    run(["build", "-k", "17", gold_in("ambig_test_1.fa"), gold_in("ambig_test_2.fa"), "-o", "ambig_map", "--single-strand"], cwd=wd)
+    assert run(["map", gold_in("ambig_test_ref.fa"), "ambig_map.skf"], cwd=wd).stdout == gold_ok("map_aln_ambig.stdout")
+    # vcf
+    assert matches(run(["map", ref, gold_in("merge.skf"), "-f", "vcf"], cwd=wd).stdout, gold_ok("map_vcf.stdout"))
+    assert matches(run(["map", ref2, gold_in("merge.skf"), "-f", "vcf"], cwd=wd).stdout, gold_ok("map_vcf_two_chrom.stdout"))
+    assert matches(run(["map", ref, gold_in("test_1.fa"), gold_in("indel_test.fa"), "-f", "vcf"], cwd=wd).stdout, gold_ok("map_vcf_indels.stdout"))
+    # reverse complement input == forward input; single strand
+    run(["build", "-o", "rc_build", "-k", "9", gold_in("test_1.fa"), gold_in("test_2_rc.fa")], cwd=wd)
+    rc_map = run(["map", ref, "rc_build.skf"], cwd=wd).stdout                 # (the reference's own comparison maps a file that does not
+    fwd_map = run(["map", ref, gold_in("merge_k9.skf")], cwd=wd).stdout       # exist, tests/map.rs:187-196; here: same alignment but for the
+    a, b = rc_map.split(b"\n")[1::2], fwd_map.split(b"\n")[1::2]             # record-end window that the reverse strand drops at the other end)
+    assert a[0] == b[0] and a[1][:70] == b[1][:70]
+    run(["build", "-o", "ss_map", "-k", "9", "--single-strand", gold_in("test_1.fa"), gold_in("test_2_rc.fa")], cwd=wd)
+    assert run(["map", ref, "ss_map.skf"], cwd=wd).stdout == gold_ok("map_ss.stdout")
+    assert matches(run(["map", ref, "ss_map.skf", "-f", "vcf"], cwd=wd).stdout, gold_ok("map_vcf_ss.stdout"))
+    # repeat mask
+    assert run(["map", ref, gold_in("merge_k9.skf"), "-v", "--repeat-mask"], cwd=wd).stdout == gold_ok("map_aln_k9.masked.stdout")
+    assert matches(run(["map", ref, gold_in("merge_k9.skf"), "--repeat-mask", "--format", "vcf"], cwd=wd).stdout, gold_ok("map_vcf_k9.masked.stdout"))
+    assert run(["map", ref2, gold_in("merge_k9.skf"), "--repeat-mask"], cwd=wd).stdout == gold_ok("map_all_repeats.masked.stdout")
+    ref3 = gold_in("test_ref_two_chrom_repeats.fa")
+    assert run(["map", ref3, gold_in("merge_k9.skf"), "--repeat-mask"], cwd=wd).stdout == gold_ok("map_aln_two_chrom.masked.stdout")
+    assert matches(run(["map", ref3, gold_in("merge_k9.skf"), "--repeat-mask", "--format", "vcf"], cwd=wd).stdout,
+                   gold_ok("map_vcf_two_chrom.masked.stdout"))

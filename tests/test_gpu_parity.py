@@ -645,3 +645,112 @@ def test_array_checksum_matches_numpy_and_flags_damage():
     keys2 = keys.copy(); keys2[[5, 6]] = keys2[[6, 5]]
     bad = S.MergeSkaArray.from_arrays(15, True, 64, keys2, var, cnt, names)
     assert bad.checksum()[3] >= 1
+
+
+# ------------------------------------------------------------------ joins on the key: merge / delete / weed / map
+def _rand_samples(seed, n, k, rc, shared=0.7):
+    """samples that share most split k-mers (a mutated common ancestor) so that joins have hits and misses"""
+    rng = np.random.default_rng(seed)
+    anc = rng.choice(np.frombuffer(b"ACGT", dtype=np.uint8), size=6000)
+    recs = []
+    for _ in range(n):
+        g = anc.copy()
+        pos = rng.integers(0, len(g), size=int(len(g) * (1 - shared) / 20))
+        g[pos] = rng.choice(np.frombuffer(b"ACGTN", dtype=np.uint8), size=len(pos))
+        cut = int(rng.integers(1000, 5000))
+        recs.append([g[:cut].tobytes(), g[cut:].tobytes()])
+    samples = [S.Sample.from_records(r) for r in recs]
+    names = [f"s{i}" for i in range(n)]
+    return recs, samples, names
+
+
+@pytest.mark.parametrize("k,rc", [(9, True), (21, False), (31, True)])
+def test_merge_arrays_equals_joint_build(k, rc):
+    """MergeSkaDict::extend: build(A) (+) build(B) == build(A + B), also when one side arrives in hash order (unsorted rows)"""
+    recs, samples, names = _rand_samples(50 + k, 7, k, rc)
+    a = S.build_from_samples(samples[:3], names[:3], k, rc)
+    b = S.build_from_samples(samples[3:], names[3:], k, rc)
+    joint = S.build_from_samples(samples, names, k, rc)
+    m = S.api.merge_arrays(a, b)
+    jk, jv, jc = joint.export()
+    mk, mv, mc = m.export()
+    assert np.array_equal(jk, mk) and np.array_equal(jv, mv) and np.array_equal(jc, mc)
+    assert m.names() == names
+    # the same with B's rows shuffled (as a reference-written .skf would deliver them)
+    bk, bv, bc = b.export()
+    perm = np.random.default_rng(1).permutation(len(bk))
+    b2 = S.MergeSkaArray.from_arrays(k, rc, 64, bk[perm], bv[perm], bc[perm], names[3:])
+    m2 = S.api.merge_arrays(a, b2)
+    mk, mv, mc = m2.export()
+    assert np.array_equal(jk, mk) and np.array_equal(jv, mv) and np.array_equal(jc, mc)
+    # mismatching k / strand panic in the reference
+    other = S.build_from_samples(samples[:2], names[:2], k + 2 if k < 31 else 29, rc)
+    with pytest.raises(S.SkaError, match="K-mer lengths do not match"):
+        S.api.merge_arrays(a, other)
+
+
+def test_delete_samples_equals_build_without_them():
+    k, rc = 15, True
+    recs, samples, names = _rand_samples(7, 6, k, rc)
+    full = S.build_from_samples(samples, names, k, rc)
+    full.delete_samples(["s1", "s4"])
+    keep = [0, 2, 3, 5]
+    ref = S.build_from_samples([samples[i] for i in keep], [names[i] for i in keep], k, rc)
+    assert full.names() == ref.names()
+    fk, fv, fc = full.export()
+    rk, rv, rc_ = ref.export()
+    assert np.array_equal(fk, rk) and np.array_equal(fv, rv) and np.array_equal(fc, rc_)
+    with pytest.raises(S.SkaError):
+        full.delete_samples(["nope"])
+    with pytest.raises(S.SkaError):
+        full.delete_samples(full.names())
+
+
+@pytest.mark.parametrize("reverse", [False, True])
+def test_weed_matches_set_difference(reverse):
+    k, rc = 17, True
+    recs, samples, names = _rand_samples(11, 4, k, rc)
+    arr = S.build_from_samples(samples, names, k, rc)
+    keys, var, cnt = arr.export()
+    weed_recs = [recs[0][0][100:900], recs[2][1][:700] + b"N" + recs[1][0][50:400], b"ACGT"]
+    wkeys = set()
+    n_w = 0
+    for r in weed_recs:
+        w = O.windows(r, k, rc=rc)
+        wkeys.update(w["key"])
+        n_w += w["n"]
+    n = arr.weed(S.Sample.from_records(weed_recs), reverse=reverse)
+    assert n == n_w
+    found = np.array([int(x) in wkeys for x in keys])
+    sel = found if reverse else ~found
+    k2, v2, c2 = arr.export()
+    assert np.array_equal(k2, keys[sel]) and np.array_equal(v2, var[sel]) and np.array_equal(c2, cnt[sel])
+
+
+@pytest.mark.parametrize("k,rc", [(9, True), (15, False), (31, True)])
+def test_map_lookup_matches_dictionary_walk(k, rc):
+    """RefSka::map: every reference split k-mer in reference order, rows complemented (RC_IUPAC) on reverse-strand hits"""
+    recs, samples, names = _rand_samples(23 + k, 5, k, rc)
+    arr = S.build_from_samples(samples, names, k, rc)
+    rows = arr.row_map()
+    ref_recs = [recs[1][0][:1500] + b"NN" + recs[3][1][:800], recs[0][1][200:1200]]
+    comp = {ord(a): ord(b) for a, b in zip("ABCDGHKMNRSTVWY", "TVGHCDMKNYSABWR")}
+    rc_tab = np.full(256, ord("-"), dtype=np.uint8)
+    for a, b in comp.items():
+        rc_tab[a] = b
+        rc_tab[a | 0x20] = b
+    exp_pos, exp_rows, n_ref, base = [], [], 0, 0
+    for r in ref_recs:
+        w = O.windows(r, k, rc=rc)
+        n_ref += w["n"]
+        for i in range(w["n"]):
+            key = w["key"][i]
+            if key in rows:
+                row = np.frombuffer(rows[key], dtype=np.uint8)
+                exp_rows.append(rc_tab[row] if w["is_rc"][i] else row)
+                exp_pos.append(base + int(w["mid_pos"][i]))
+        base += len(r)
+    pos, var, n = arr.map(S.Sample.from_records(ref_recs))
+    assert n == n_ref
+    assert [int(p) for p in pos] == exp_pos
+    assert np.array_equal(var, np.array(exp_rows, dtype=np.uint8).reshape(len(exp_pos), len(names)))
