@@ -335,7 +335,7 @@ class SeqBatch:
             total = int(sum((s.n_bases + 31) // 32 * 32 for s in self._keep))
         else:
             total = int(sum(len(s.seq) for s in self._keep))
-        rec = np.empty(total, dtype=np.uint64) if want_records else None
+        rec = np.empty(total * (2 if k > 31 else 1), dtype=np.uint64) if want_records else None   # k > 31: (lo, hi) per position
         _check(lib().skagpu_k1_extract(self._h, k, int(rc), min_qual, qf, iters,
                                        rec.ctypes.data if rec is not None else None, C.byref(n), C.byref(ms)))
         return rec, float(ms.value)

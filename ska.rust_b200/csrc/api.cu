@@ -379,13 +379,22 @@ static std::unique_ptr<SeqBatch> upload_packed(const ska_input_packed_t* in, siz
     return b;
 }
 
+// bucket grid of a build: narrow (k <= 31) or wide keys
+static PartPlan plan_for(uint32_t k, uint64_t n_pos, uint64_t n_samples) {
+    return make_part_plan(k, k > 31 ? merge_prefix_bits_wide(n_pos, k) : merge_prefix_bits(n_pos, k, n_samples), n_samples);
+}
+static void merge_records(uint64_t* rec, const SeqBatch& b, uint32_t k, bool rc, Array& a, const PartPlan& pl, const unsigned long long* hist) {
+    if (k > 31) build_array_from_records_wide(rec, b.n_pos, b.sample_off.p, (uint32_t)b.n_samples, 0, b.n_samples, k, rc, a, pl.P, hist);
+    else build_array_from_records(rec, b.n_pos, b.sample_off.p, (uint32_t)b.n_samples, 0, b.n_samples, k, rc, a, pl.P, hist);
+}
+
 // records (and K1's histogram) already extracted while the batch was uploaded: partition + merge
 static std::unique_ptr<Array> build_from_extracted(const SeqBatch& b, uint32_t k, bool rc, const PartPlan& pl, const K1Overlap& ov) {
     Context& c = ctx();
     std::vector<uint32_t> h_valid(b.n_samples);
     SKA_CUDA(cudaMemcpyAsync(h_valid.data(), ov.valid, b.n_samples * 4, cudaMemcpyDeviceToHost, c.stream));
     std::unique_ptr<Array> a(new Array());
-    build_array_from_records(ov.rec, b.n_pos, b.sample_off.p, (uint32_t)b.n_samples, 0, b.n_samples, k, rc, *a, pl.P, ov.hist);   // synchronises
+    merge_records(ov.rec, b, k, rc, *a, pl, ov.hist);             // synchronises
     for (size_t s = 0; s < b.n_samples; s++)
         if (h_valid[s] == 0) throw Error("sample " + std::to_string(s) + " has no valid sequence");   // ska_dict.rs:374-376
     return a;
@@ -395,7 +404,7 @@ static std::unique_ptr<Array> build_from_batch(const SeqBatch& b, uint32_t k, bo
                                                int qual_filter) {
     Context& c = ctx();
     check_k(k);
-    if (k > 31) throw Error("k > 31 (128-bit split k-mers) is not yet built on the device; use k <= 31");
+    if (k > 31 && b.packed) throw Error("k > 31 (128-bit split k-mers) takes ASCII input (skagpu_build)");
     if (b.ready) SKA_CUDA(cudaStreamWaitEvent(c.stream, b.ready, 0));   // asynchronous upload: the bytes may still be crossing PCIe
     arena().reset();
     if (b.has_qual) {                                              // reads: quality masks + count filter (k1q_reads.cu)
@@ -403,15 +412,15 @@ static std::unique_ptr<Array> build_from_batch(const SeqBatch& b, uint32_t k, bo
         build_array_from_reads(b, k, rc, min_count, min_qual, qual_filter, *a);
         return a;
     }
-    uint64_t* rec = arena().take_n<uint64_t>(b.n_pos);
+    uint64_t* rec = arena().take_n<uint64_t>(b.n_pos * (k > 31 ? 2 : 1));
     uint32_t* valid = arena().take_n<uint32_t>(b.n_samples);
     SKA_CUDA(cudaMemsetAsync(valid, 0, b.n_samples * 4, c.stream));
     // K1 also counts the records by the first partition digit, so that the partition never reads them for its
     // histogram.  Measured on 128 x 5 Mbp: the step gets 0.67 ms shorter (partition -0.91 ms, K1 +0.24 ms: 4096 shared-memory
     // atomics per tile at 3.6 SM-cycles per warp instruction, profiles/microbench/scatter_mb2.cu).
-    const PartPlan pl = make_part_plan(k, merge_prefix_bits(b.n_pos, k, b.n_samples), b.n_samples);
+    const PartPlan pl = plan_for(k, b.n_pos, b.n_samples);
     unsigned long long* k1_hist = nullptr;
-    if (k1_hist_enabled()) {
+    if (k1_hist_enabled() && k <= 31) {                      // wide keys: the partition counts its own histogram (see launch_k1)
         k1_hist = arena().take_n<unsigned long long>((size_t)K1_HIST_COPIES << pl.P1);
         SKA_CUDA(cudaMemsetAsync(k1_hist, 0, ((size_t)K1_HIST_COPIES << pl.P1) * 8, c.stream));
     }
@@ -421,7 +430,7 @@ static std::unique_ptr<Array> build_from_batch(const SeqBatch& b, uint32_t k, bo
     std::vector<uint32_t> h_valid(b.n_samples);
     SKA_CUDA(cudaMemcpyAsync(h_valid.data(), valid, b.n_samples * 4, cudaMemcpyDeviceToHost, c.stream));
     std::unique_ptr<Array> a(new Array());
-    build_array_from_records(rec, b.n_pos, b.sample_off.p, (uint32_t)b.n_samples, 0, b.n_samples, k, rc, *a, pl.P, k1_hist);   // synchronises
+    merge_records(rec, b, k, rc, *a, pl, k1_hist);                 // synchronises
     for (size_t s = 0; s < b.n_samples; s++)
         if (h_valid[s] == 0) throw Error("sample " + std::to_string(s) + " has no valid sequence");   // ska_dict.rs:374-376
     return a;
@@ -498,7 +507,7 @@ int skagpu_build(const ska_input_t* inputs, size_t n_samples, uint32_t k, int rc
     check_k(k);
     ctx().ensure();
     timer().clear();
-    bool fasta = n_samples > 0 && k <= 31 && !(proportion_reads > 0);
+    bool fasta = n_samples > 0 && !(proportion_reads > 0);
     uint64_t n_pos = 0;
     for (size_t s = 0; fasta && s < n_samples; s++) {
         if (inputs[s].qual || !inputs[s].rec_off || !inputs[s].n_rec) fasta = false;
@@ -509,15 +518,15 @@ int skagpu_build(const ska_input_t* inputs, size_t n_samples, uint32_t k, int rc
     if (fasta && n_pos > 0) {
         // FASTA: K1 runs chunk by chunk behind the copies (stage "h2d+k1")
         arena().reset();
-        const PartPlan pl = make_part_plan(k, merge_prefix_bits(n_pos, k, n_samples), n_samples);
+        const PartPlan pl = plan_for(k, n_pos, n_samples);
         K1Overlap ov;
         ov.k = k; ov.rc = rc != 0; ov.min_qual = min_qual;
-        ov.rec = arena().take_n<uint64_t>(n_pos);
+        ov.rec = arena().take_n<uint64_t>(n_pos * (k > 31 ? 2 : 1));
         ov.valid = arena().take_n<uint32_t>(n_samples);
-        ov.hist = arena().take_n<unsigned long long>((size_t)K1_HIST_COPIES << pl.P1);
+        ov.hist = k > 31 ? nullptr : arena().take_n<unsigned long long>((size_t)K1_HIST_COPIES << pl.P1);
         ov.hist_shift = 4 + pl.key_bits - pl.P1; ov.hist_bits = pl.P1;
         SKA_CUDA(cudaMemsetAsync(ov.valid, 0, n_samples * 4, ctx().stream));
-        SKA_CUDA(cudaMemsetAsync(ov.hist, 0, ((size_t)K1_HIST_COPIES << pl.P1) * 8, ctx().stream));
+        if (ov.hist) SKA_CUDA(cudaMemsetAsync(ov.hist, 0, ((size_t)K1_HIST_COPIES << pl.P1) * 8, ctx().stream));
         timer().begin("h2d+k1");
         std::unique_ptr<SeqBatch> b = upload(inputs, n_samples, proportion_reads, &ov);
         timer().end();
@@ -631,6 +640,14 @@ int skagpu_array_from_host(uint32_t k, int rc, uint32_t key_bits, uint64_t n_row
     if (key_bits != 64 && key_bits != 128) throw Error("key_bits must be 64 or 128");
     std::unique_ptr<ska_array> h(new ska_array());
     Array& a = h->a;
+    // k > 31 arrays are held with two-word keys whatever the file's integers fit in (the reference's loader tries u64 first,
+    // lib.rs:635-661; here the width follows k so that every array of one k joins with every other)
+    std::vector<uint64_t> widened;
+    if (k > 31 && key_bits == 64) {
+        widened.assign(2 * n_rows, 0);
+        for (uint64_t i = 0; i < n_rows; i++) widened[2 * i] = static_cast<const uint64_t*>(keys)[i];
+        keys = widened.data(); key_bits = 128;
+    }
     a.k = k; a.rc = rc != 0; a.key_bits = key_bits; a.n_rows = a.n_keys = n_rows; a.n_samples = n_samples;
     const size_t kw = key_bits / 64;
     a.keys.alloc(n_rows * kw); a.variants.alloc(n_rows * n_samples); a.counts.alloc(n_rows);
@@ -806,7 +823,7 @@ int skagpu_extract_records(const ska_seqbatch_t* batch, uint32_t k, int rc, uint
     Context& c = ctx();
     c.ensure();
     check_k(k);
-    if (k > 31) throw Error("k > 31 (128-bit split k-mers) is not yet built on the device; use k <= 31");
+    if (k > 31) throw Error("k > 31 (128-bit split k-mers): the record-level multi-GPU exchange is built for k <= 31 only");
     const SeqBatch& b = *batch->b;
     if (b.has_qual) throw Error("FASTQ input (count/bloom filter, K2q) is not yet built on the device");
     if (sample_id_base + b.n_samples > n_samples_total) throw Error("sample ids exceed n_samples_total");
@@ -857,7 +874,7 @@ int skagpu_merge_records_dev(void* rec_dev, int n_runs, const uint64_t* run_offs
     Context& c = ctx();
     c.ensure();
     check_k(k);
-    if (k > 31) throw Error("k > 31 not yet supported on the device");
+    if (k > 31) throw Error("k > 31 (128-bit split k-mers): the record-level multi-GPU exchange is built for k <= 31 only");
     const PartPlan pl = make_part_plan(k, prefix_bits, n_samples_total);
     if (pl.P != prefix_bits) throw Error("prefix_bits does not match the record plan (use skagpu_merge_prefix_bits)");
     if (region_hi < region_lo || region_hi > (1ull << pl.P1)) throw Error("bad region range");
@@ -906,7 +923,7 @@ int skagpu_merge_partial_rows_dev(const void* keys_dev, const void* variants_dev
     *out = nullptr;
     ctx().ensure();
     check_k(k);
-    if (k > 31) throw Error("k > 31 not yet supported on the device");
+    if (k > 31) throw Error("k > 31 (128-bit split k-mers): the partial-row multi-GPU join is built for k <= 31 only");
     if (n_runs < 1 || !run_rows || !run_cols || !run_col_base) throw Error("row shard needs at least one run");
     // the caller's buffers may have been filled on another stream (NCCL): order after everything
     SKA_CUDA(cudaDeviceSynchronize());
@@ -1070,12 +1087,12 @@ int skagpu_k1_extract(const ska_seqbatch_t* batch, uint32_t k, int rc, uint8_t m
     Context& c = ctx();
     c.ensure();
     check_k(k);
-    if (k > 31) throw Error("k > 31 not yet supported on the device");
     const SeqBatch& b = *batch->b;
+    if (k > 31 && (b.packed || b.has_qual)) throw Error("k > 31: the raw extraction entry point takes ASCII assemblies");
     if (n_positions) *n_positions = b.n_pos;
-    DevBuf<uint64_t> rec(b.n_pos);
+    DevBuf<uint64_t> rec(b.n_pos * (k > 31 ? 2 : 1));
     // the kernel variant the build launches: FASTA batches also fill the first partition histogram
-    const PartPlan pl = make_part_plan(k, merge_prefix_bits(b.n_pos, k, b.n_samples), b.n_samples);
+    const PartPlan pl = plan_for(k, b.n_pos, b.n_samples);
     DevBuf<unsigned long long> hist((size_t)K1_HIST_COPIES << pl.P1);
     SKA_CUDA(cudaMemsetAsync(hist.p, 0, hist.bytes(), c.stream));
     // the extraction kernel proper; inside a build the same kernel also fills the partition histogram (stage "k1_extract")
@@ -1093,7 +1110,7 @@ int skagpu_k1_extract(const ska_seqbatch_t* batch, uint32_t k, int rc, uint8_t m
     cudaEventDestroy(e0); cudaEventDestroy(e1);
     if (mean_ms) *mean_ms = ms / iters;
     if (rec_out && b.n_pos) {
-        SKA_CUDA(cudaMemcpyAsync(rec_out, rec.p, b.n_pos * 8, cudaMemcpyDeviceToHost, c.stream));
+        SKA_CUDA(cudaMemcpyAsync(rec_out, rec.p, rec.bytes(), cudaMemcpyDeviceToHost, c.stream));
         SKA_CUDA(cudaStreamSynchronize(c.stream));
     }
     return 0;

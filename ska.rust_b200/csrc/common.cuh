@@ -155,7 +155,7 @@ size_t padded_positions(uint64_t n_pos);
 bool k1_wide_available();          // launch_k1 handles k > 31 (two-word records)
 // partition.cu: how records are grouped and packed.  P = P1 + P2 prefix bits of the key select the bucket;
 // inside a bucket a record is  key_low << (sb+2) | sample_id << 2 | middle_code  (key_low = key without its top P1 bits)
-struct PartPlan { int key_bits, sb, P, P1, P2, low_bits; };
+struct PartPlan { int key_bits, sb, P, P1, P2, low_bits; bool wide; /* k > 31: records of two words */ };
 PartPlan make_part_plan(uint32_t k, int prefix_bits, uint64_t n_samples_total);
 // k1_hist: the first pass's histogram as K1 left it (K1_HIST_COPIES copies), or NULL to count here
 void partition_records(const uint64_t* rec, uint64_t n_pos, const uint64_t* d_sample_off, uint32_t n_samples_local, uint32_t sid_base,
@@ -172,6 +172,11 @@ void partition_runs(const uint64_t* src, int n_runs, const uint64_t* h_run_off, 
 void build_array_from_records(uint64_t* rec, uint64_t n_rec, const uint64_t* d_sample_off, uint32_t n_samples_local, uint32_t sid_base,
                               uint64_t n_samples_total, uint32_t k, bool rc, Array& out, int prefix_bits = -1 /* < 0: merge_prefix_bits */,
                               const unsigned long long* k1_hist = nullptr /* histogram of the plan's first pass, from K1 */);
+// merge128.cu: the same for k > 31 (records and keys of two words)
+int merge_prefix_bits_wide(uint64_t n_records_total, uint32_t k);
+void build_array_from_records_wide(uint64_t* rec, uint64_t n_rec, const uint64_t* d_sample_off, uint32_t n_samples_local, uint32_t sid_base,
+                                   uint64_t n_samples_total, uint32_t k, bool rc, Array& out, int prefix_bits = -1,
+                                   const unsigned long long* k1_hist = nullptr);
 // k1q_reads.cu: FASTQ samples (quality masks, ntHash, exact count-filter emulation) -> array
 void build_array_from_reads(const SeqBatch& b, uint32_t k, bool rc, uint16_t min_count, uint8_t min_qual, int qual_filter, Array& out);
 // row shard: `n_runs` received runs of first-pass records covering first-level regions [lo, hi); `prec` is overwritten

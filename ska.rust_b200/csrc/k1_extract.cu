@@ -30,7 +30,7 @@ uint64_t k1_tiles_ready(uint64_t positions_uploaded, int tail) {      // tiles w
 }
 static_assert(K1_ASCII_TAIL == K1_TAIL && K1_PACKED_TAIL == K1P_TAIL, "tile tails");
 
-bool k1_wide_available() { return false; }
+bool k1_wide_available() { return true; }
 
 size_t padded_positions(uint64_t n_pos) { return FRONT_PAD + ((n_pos + K1_T - 1) / K1_T) * K1_T + 256; }
 
@@ -41,7 +41,9 @@ size_t padded_positions(uint64_t n_pos) { return FRONT_PAD + ((n_pos + K1_T - 1)
 // PACKED: the batch holds host-packed bases instead of ASCII (skagpu_build_packed: 0.375 B per base across PCIe instead
 // of 1): `seq` = 2-bit codes, 4 per byte in the kernel's own LE order, `qual` = the invalid-base bit mask; the tile is
 // staged straight into the LE stream and the mask words, the pack phase disappears.
-template <int KT, bool HAS_QUAL, bool HIST, bool PACKED>
+// WIDE: k > 31 -- keys of up to 124 bits (UInt for u128, bit_encoding.rs:239-303); a record is two words,
+// (key << 4 | one-hot middle) as a 128-bit little-endian integer, all-ones = no window.
+template <int KT, bool HAS_QUAL, bool HIST, bool PACKED, bool WIDE = false>
 __global__ void __launch_bounds__(K1_THREADS)
 k1_extract_kernel(const uint8_t* __restrict__ seq, const uint8_t* __restrict__ qual,
                   const uint32_t* __restrict__ start_bits, const uint64_t* __restrict__ sample_off,
@@ -188,6 +190,47 @@ k1_extract_kernel(const uint8_t* __restrict__ seq, const uint8_t* __restrict__ q
         else if (HIST) atomicAdd(&s_hist[(uint32_t)(rec >> hist_shift)], 1u);
         return rec;
     };
+    if (WIDE) {
+        typedef unsigned __int128 u128;
+        const u128 one = 1;
+        const u128 mask2k_w = (one << (2 * k)) - 1;                  // k <= 63
+        const u128 lm_w = (one << (2 * h)) - 1;
+        const u128 aa_w = ((((u128)0xAAAAAAAAAAAAAAAAULL) << 64) | 0xAAAAAAAAAAAAAAAAULL) & mask2k_w;
+        ulonglong2* out2 = reinterpret_cast<ulonglong2*>(rec_out) + t0 + lane;
+        for (int j = warp; j < K1_T / 32; j += K1_THREADS / 32) {
+            const uint64_t p = t0 + 32ull * j + lane;
+            if (p >= n_pos) break;
+            const uint32_t b0 = be[2 * j], b1 = be[2 * j + 1], b2 = be[2 * j + 2], b3 = be[2 * j + 3], b4 = be[2 * j + 4];
+            const uint64_t thi = ((uint64_t)__funnelshift_l(b1, b0, sh) << 32) | __funnelshift_l(b2, b1, sh);
+            const uint64_t tlo = ((uint64_t)__funnelshift_l(b3, b2, sh) << 32) | __funnelshift_l(b4, b3, sh);
+            const u128 F = ((((u128)thi) << 64) | tlo) >> (128 - 2 * k);
+            u128 key = (F & lm_w) | ((F >> 2) & ~lm_w);
+            uint32_t mid = (uint32_t)(F >> (2 * h)) & 3u;
+            if (rc) {
+                const uint32_t l0 = le[2 * j], l1 = le[2 * j + 1], l2 = le[2 * j + 2], l3 = le[2 * j + 3], l4 = le[2 * j + 4];
+                const uint64_t vlo = ((uint64_t)__funnelshift_r(l1, l2, sh) << 32) | __funnelshift_r(l0, l1, sh);
+                const uint64_t vhi = ((uint64_t)__funnelshift_r(l3, l4, sh) << 32) | __funnelshift_r(l2, l3, sh);
+                const u128 R = (((((u128)vhi) << 64) | vlo) & mask2k_w) ^ aa_w;
+                const u128 rkey = (R & lm_w) | ((R >> 2) & ~lm_w);
+                if (key > rkey) { key = rkey; mid ^= 2u; }            // ties keep forward (split_kmer.rs:290)
+            }
+            const uint64_t klo = (uint64_t)key, khi = (uint64_t)(key >> 64);
+            unsigned long long rlo = (klo << 4) | (uint64_t)(1u << mid), rhi = (khi << 4) | (klo >> 60);
+            const bool okw = (s_ok[j] >> lane) & 1u;
+            if (!okw) { rlo = ~0ULL; rhi = ~0ULL; }
+            else if (HIST) {
+                const uint32_t d = hist_shift >= 64 ? (uint32_t)(rhi >> (hist_shift - 64))
+                                                    : (uint32_t)((rlo >> hist_shift) | (hist_shift ? rhi << (64 - hist_shift) : 0ULL));
+                atomicAdd(&s_hist[d], 1u);
+            }
+            out2[32 * j] = make_ulonglong2(rlo, rhi);
+            if (!uniform && sample_valid && okw) {
+                uint32_t lo = sid_first, hi = sid_last + 1;
+                while (hi - lo > 1) { uint32_t m = (lo + hi) >> 1; if (sample_off[m] <= p) lo = m; else hi = m; }
+                atomicAdd(&sample_valid[lo], 1u);
+            }
+        }
+    } else
     if (full && uniform) {                                        // interior tile of one sample: no per-window checks
         if (sout) {
 #pragma unroll 4
@@ -204,7 +247,15 @@ k1_extract_kernel(const uint8_t* __restrict__ seq, const uint8_t* __restrict__ q
             out[32 * j] = rec;
             uint32_t lo = sid_first, hi = sid_last + 1;           // tile straddles samples or the end of the batch
             while (hi - lo > 1) { uint32_t m = (lo + hi) >> 1; if (sample_off[m] <= p) lo = m; else hi = m; }
-            if (!uniform && sample_valid && rec != REC_SENTINEL) atomicAdd(&sample_valid[lo], 1u);
+            if (!uniform && sample_valid) {
+                // one atomic per sample and warp step, not per window: small genomes (30 kbp) put a sample boundary in every
+                // seventh tile, and 256 counters took a million contended atomics per build
+                const uint32_t act = __activemask();
+                const uint32_t vmask = __ballot_sync(act, rec != REC_SENTINEL);
+                const uint32_t peers = __match_any_sync(act, lo);
+                const uint32_t cnt_v = __popc(peers & vmask);
+                if (cnt_v && lane == __ffs(peers) - 1) atomicAdd(&sample_valid[lo], cnt_v);
+            }
             if (sout) sout[32 * j] = (uint16_t)(lo + sid_base);
         }
     }
@@ -230,7 +281,20 @@ static void launch_k1_kt(const SeqBatch& b, uint32_t k, bool rc, bool strict_qua
     const unsigned grid = (unsigned)(tile_end - tile_begin);
     const uint32_t tile0 = (uint32_t)tile_begin;
     unsigned long long* nohist = nullptr;
-    if (b.packed) {
+    if (k > 31) {
+        if (KT != 0 || b.packed || b.has_qual) throw Error("internal: wide extraction takes ASCII assemblies");
+        // the histogram-fused instantiation of the wide kernel came back from the B200 with bit 61 of some keys cleared (same
+        // source, the plain instantiation is bit-exact against the reference semantics at k = 33..63): callers count wide histograms in the partition
+        if (hist) throw Error("internal: the wide extraction kernel does not count the partition histogram");
+        if (hist)
+            SKA_LAUNCH((k1_extract_kernel<0, false, true, false, true>), grid, K1_THREADS, 0, b.seq.p, (const uint8_t*)nullptr, b.start_bits.p,
+                       b.sample_off.p, (uint32_t)b.n_samples, b.n_pos, (int)k, rc ? 1 : 0, 0u, rec_out, sid_out, sample_valid, sid_base, hist,
+                       hist_shift, hist_bits, tile0);
+        else
+            SKA_LAUNCH((k1_extract_kernel<0, false, false, false, true>), grid, K1_THREADS, 0, b.seq.p, (const uint8_t*)nullptr, b.start_bits.p,
+                       b.sample_off.p, (uint32_t)b.n_samples, b.n_pos, (int)k, rc ? 1 : 0, 0u, rec_out, sid_out, sample_valid, sid_base, nohist,
+                       0, 0, tile0);
+    } else if (b.packed) {
         if (hist)
             SKA_LAUNCH((k1_extract_kernel<KT, false, true, true>), grid, K1_THREADS, 0, b.seq.p, b.qual.p, b.start_bits.p, b.sample_off.p,
                        (uint32_t)b.n_samples, b.n_pos, (int)k, rc ? 1 : 0, 0u, rec_out, sid_out, sample_valid, sid_base, hist, hist_shift, hist_bits, tile0);
@@ -258,6 +322,7 @@ void launch_k1(const SeqBatch& b, uint32_t k, bool rc, bool strict_qual, uint8_t
     if (hist && (hist_bits < 0 || hist_bits > K1_HIST_MAX_BITS)) throw Error("internal: K1 histogram wider than its shared-memory table");
     // the default k of `ska build` (cli.rs:9) gets a compile-time specialisation
     if (k == 31) launch_k1_kt<31>(b, k, rc, strict_qual, min_qual, rec_out, sid_out, sample_valid, sid_base, hist, hist_shift, hist_bits, tile_begin, tile_end);
+    else if (k == 15) launch_k1_kt<15>(b, k, rc, strict_qual, min_qual, rec_out, sid_out, sample_valid, sid_base, hist, hist_shift, hist_bits, tile_begin, tile_end);   // BASELINE configs[4]
     else launch_k1_kt<0>(b, k, rc, strict_qual, min_qual, rec_out, sid_out, sample_valid, sid_base, hist, hist_shift, hist_bits, tile_begin, tile_end);
 }
 

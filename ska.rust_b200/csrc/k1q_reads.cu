@@ -205,7 +205,35 @@ k1q_kernel(const uint8_t* __restrict__ seq, const uint8_t* __restrict__ qual, co
     const int sh = 2 * (lane & 15);
     const uint32_t* be = s_be + ((K1_LEAD + lane) >> 4);
     const uint32_t* le = s_le + ((K1_LEAD + lane) >> 4);
-    uint64_t* out = rec_c + tile_off[blockIdx.x];
+    uint64_t* out = rec_c + tile_off[blockIdx.x] * (k > 31 ? 2 : 1);
+    if (k > 31) {                                                     // two-word records (see k1_extract.cu, WIDE)
+        typedef unsigned __int128 u128;
+        const u128 one = 1;
+        const u128 mask2k_w = (one << (2 * k)) - 1, lm_w = (one << (2 * h)) - 1;
+        const u128 aa_w = ((((u128)0xAAAAAAAAAAAAAAAAULL) << 64) | 0xAAAAAAAAAAAAAAAAULL) & mask2k_w;
+        for (int j = warp; j < K1_T / 32; j += K1_THREADS / 32) {
+            const uint32_t ok = s_ok[j];
+            if (!((ok >> lane) & 1u)) continue;
+            const uint32_t b0 = be[2 * j], b1 = be[2 * j + 1], b2 = be[2 * j + 2], b3 = be[2 * j + 3], b4 = be[2 * j + 4];
+            const uint64_t thi = ((uint64_t)__funnelshift_l(b1, b0, sh) << 32) | __funnelshift_l(b2, b1, sh);
+            const uint64_t tlo = ((uint64_t)__funnelshift_l(b3, b2, sh) << 32) | __funnelshift_l(b4, b3, sh);
+            const u128 F = ((((u128)thi) << 64) | tlo) >> (128 - 2 * k);
+            u128 key = (F & lm_w) | ((F >> 2) & ~lm_w);
+            uint32_t mid = (uint32_t)(F >> (2 * h)) & 3u;
+            if (rc) {
+                const uint32_t l0 = le[2 * j], l1 = le[2 * j + 1], l2 = le[2 * j + 2], l3 = le[2 * j + 3], l4 = le[2 * j + 4];
+                const uint64_t vlo = ((uint64_t)__funnelshift_r(l1, l2, sh) << 32) | __funnelshift_r(l0, l1, sh);
+                const uint64_t vhi = ((uint64_t)__funnelshift_r(l3, l4, sh) << 32) | __funnelshift_r(l2, l3, sh);
+                const u128 R = (((((u128)vhi) << 64) | vlo) & mask2k_w) ^ aa_w;
+                const u128 rkey = (R & lm_w) | ((R >> 2) & ~lm_w);
+                if (key > rkey) { key = rkey; mid ^= 2u; }
+            }
+            const u128 rec = (key << 4) | (u128)(1u << mid);
+            const uint32_t idx = s_pre[j] + __popc(ok & ((1u << lane) - 1u));
+            out[2 * idx] = (uint64_t)rec; out[2 * idx + 1] = (uint64_t)(rec >> 64);
+        }
+        return;
+    }
     for (int j = warp; j < K1_T / 32; j += K1_THREADS / 32) {
         const uint32_t ok = s_ok[j];
         if (!((ok >> lane) & 1u)) continue;
@@ -376,18 +404,20 @@ void build_array_from_reads(const SeqBatch& b, uint32_t k, bool rc, uint16_t min
     timer().begin("k1_extract");
     std::vector<uint64_t> coff(N + 1, 0);
     for (uint64_t s = 0; s < N; s++) coff[s + 1] = coff[s] + accepted[s];
-    uint64_t* rec_c = arena().take_n<uint64_t>(std::max<uint64_t>(coff[N], 1));
+    const int rw = k > 31 ? 2 : 1;                                    // words per record
+    uint64_t* rec_c = arena().take_n<uint64_t>(std::max<uint64_t>(coff[N], 1) * rw);
     for (uint64_t s = 0; s < N; s++) {
         if (!n_tiles[s]) continue;
         SKA_LAUNCH(k1q_kernel<RQ_EMIT>, (unsigned)n_tiles[s], K1_THREADS, 0, b.seq.p, b.qual.p, b.start_bits.p, b.h_sample_off[s],
                    b.h_sample_off[s + 1], tile_lo[s], (int)k, rc ? 1 : 0, (uint32_t)min_qual, qual_filter, masks[s], (uint64_t*)nullptr,
-                   (uint32_t*)nullptr, (unsigned long long*)nullptr, (const uint64_t*)tile_offs[s], rec_c + coff[s]);
+                   (uint32_t*)nullptr, (unsigned long long*)nullptr, (const uint64_t*)tile_offs[s], rec_c + coff[s] * rw);
     }
     timer().end();
     uint64_t* d_coff = arena().take_n<uint64_t>(N + 1);
     SKA_CUDA(cudaMemcpyAsync(d_coff, coff.data(), (N + 1) * 8, cudaMemcpyHostToDevice, c.stream));
     SKA_CUDA(cudaStreamSynchronize(c.stream));
-    build_array_from_records(rec_c, coff[N], d_coff, (uint32_t)N, 0, N, k, rc, out);
+    if (k > 31) build_array_from_records_wide(rec_c, coff[N], d_coff, (uint32_t)N, 0, N, k, rc, out);
+    else build_array_from_records(rec_c, coff[N], d_coff, (uint32_t)N, 0, N, k, rc, out);
 }
 
 }  // namespace ska

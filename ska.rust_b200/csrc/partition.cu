@@ -232,6 +232,139 @@ part_scatter_kernel(const uint64_t* __restrict__ src, uint64_t n_total, Segs sg,
     for (uint32_t slot = threadIdx.x; slot < n_valid; slot += SC_T) dst[s_gbase[s_sdig[slot]] + slot] = s_stage[slot];
 }
 
+// ---------------------------------------------------------------------------------------------- wide records (k > 31)
+// The same two passes on 16-byte records (key of up to 124 bits << 4 | one-hot middle from K1; packed records carry
+// key_low << (sb + 2) | sample << 2 | middle in 128 bits, which needs P1 >= sb - 2 exactly as the 64-bit form does).
+typedef unsigned __int128 u128;
+__device__ __forceinline__ u128 ld_rec128(const uint64_t* __restrict__ p, uint64_t i) {
+    const ulonglong2 v = __ldg(reinterpret_cast<const ulonglong2*>(p) + i);
+    return ((u128)v.y << 64) | v.x;
+}
+__device__ __forceinline__ uint32_t digit128(u128 r, int pass, int shift, uint32_t mask) {
+    if (pass == 1) return r == ~(u128)0 ? PT_NONE : (uint32_t)(r >> shift);
+    return mask ? (uint32_t)(r >> shift) & mask : 0u;
+}
+__global__ void __launch_bounds__(PT_THREADS)
+part_hist_wide_kernel(const uint64_t* __restrict__ src, uint64_t n_total, uint64_t n_tiles, Segs sg, DigitFn fn, int bits,
+                      unsigned long long* __restrict__ hist) {
+    extern __shared__ uint32_t s_cnt[];
+    const uint32_t D = 1u << bits;
+    const uint64_t per = (n_tiles + gridDim.x - 1) / gridDim.x;
+    const uint64_t t_beg = min(n_tiles, (uint64_t)blockIdx.x * per), t_end = min(n_tiles, t_beg + per);
+    uint32_t cur_region = PT_NONE;
+    for (uint32_t i = threadIdx.x; i < D; i += PT_THREADS) s_cnt[i] = 0;
+    __syncthreads();
+    auto flush = [&](uint32_t region) {
+        __syncthreads();
+        for (uint32_t d = threadIdx.x; d < D; d += PT_THREADS) {
+            uint32_t tot = s_cnt[d];
+            s_cnt[d] = 0;
+            if (tot) atomicAdd(&hist[(size_t)region * D + d], (unsigned long long)tot);
+        }
+        __syncthreads();
+    };
+    for (uint64_t t = t_beg; t < t_end; t++) {
+        uint64_t beg, end; uint32_t region;
+        tile_range(t, sg, n_total, beg, end, region);
+        if (region != cur_region) { if (cur_region != PT_NONE) flush(cur_region); cur_region = region; }
+        for (uint64_t i = beg + threadIdx.x; i < end; i += PT_THREADS) {
+            const uint32_t d = digit128(ld_rec128(src, i), fn.pass, fn.shift, fn.mask);
+            if (d != PT_NONE) atomicAdd(&s_cnt[d], 1u);
+        }
+    }
+    if (cur_region != PT_NONE) flush(cur_region);
+}
+
+struct PackWide { int sb; int low_bits; uint32_t sid_base; };
+constexpr int SCW_T = 256;
+constexpr int SCW_I = PT_TILE / SCW_T;
+template <int PASS>
+__global__ void __launch_bounds__(SCW_T, 2)
+part_scatter_wide_kernel(const uint64_t* __restrict__ src, uint64_t n_total, Segs sg, DigitFn fn, int bits, PackWide pk,
+                         const uint64_t* __restrict__ sample_off, uint32_t n_samples, unsigned long long* __restrict__ cursor,
+                         uint64_t* __restrict__ dst) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    const uint32_t D = 1u << bits;
+    ulonglong2* s_stage = reinterpret_cast<ulonglong2*>(smem);                   // [PT_TILE]
+    unsigned long long* s_gbase = reinterpret_cast<unsigned long long*>(s_stage + PT_TILE);   // [D]
+    uint32_t* s_doff = reinterpret_cast<uint32_t*>(s_gbase + D);                 // [D + 1]
+    uint32_t* s_acnt = s_doff + D + 1;                                           // [D]
+    uint16_t* s_sdig = reinterpret_cast<uint16_t*>(s_acnt + D);                  // [PT_TILE]
+    __shared__ uint32_t s_sid[2];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint64_t beg, end; uint32_t region;
+    tile_range(blockIdx.x, sg, n_total, beg, end, region);
+    const uint32_t cnt = (uint32_t)(end - beg);
+    u128 rr[SCW_I]; uint32_t dp[SCW_I];
+#pragma unroll
+    for (int j = 0; j < SCW_I; j++) {
+        const uint32_t li = j * SCW_T + threadIdx.x;
+        rr[j] = li < cnt ? ld_rec128(src, beg + li) : ~(u128)0;
+    }
+    for (uint32_t i = threadIdx.x; i < D; i += SCW_T) s_acnt[i] = 0;
+    if (PASS == 1 && threadIdx.x == 0) {
+        uint64_t pf = beg, pl = end - 1;
+        uint32_t lo = 0, hi = n_samples;
+        while (hi - lo > 1) { uint32_t m = (lo + hi) >> 1; if (sample_off[m] <= pf) lo = m; else hi = m; }
+        s_sid[0] = lo; hi = n_samples;
+        while (hi - lo > 1) { uint32_t m = (lo + hi) >> 1; if (sample_off[m] <= pl) lo = m; else hi = m; }
+        s_sid[1] = lo;
+    }
+    __syncthreads();
+    const u128 low_mask = pk.low_bits >= 128 ? ~(u128)0 : (((u128)1 << pk.low_bits) - 1);
+#pragma unroll
+    for (int j = 0; j < SCW_I; j++) {
+        const uint32_t li = j * SCW_T + threadIdx.x;
+        const u128 r = rr[j];
+        const uint32_t d = li < cnt ? digit128(r, PASS, fn.shift, fn.mask) : PT_NONE;
+        if (PASS == 1 && d != PT_NONE) {
+            uint32_t s = s_sid[0];
+            if (s_sid[0] != s_sid[1]) {
+                const uint64_t i = beg + li;
+                uint32_t lo = s_sid[0], hi = s_sid[1] + 1;
+                while (hi - lo > 1) { uint32_t m = (lo + hi) >> 1; if (sample_off[m] <= i) lo = m; else hi = m; }
+                s = lo;
+            }
+            const u128 key = r >> 4;
+            const uint32_t mid = (uint32_t)__ffs((uint32_t)r & 0xFu) - 1u;
+            rr[j] = ((key & low_mask) << (pk.sb + 2)) | ((u128)(s + pk.sid_base) << 2) | mid;
+        }
+        dp[j] = d != PT_NONE ? ((d << 16) | atomicAdd(&s_acnt[d], 1u)) : PT_NONE;
+    }
+    __syncthreads();
+    if (warp == 0) {
+        const uint32_t per = (D + 31) / 32, b0 = lane * per, e0 = min(D, b0 + per);
+        uint32_t sum = 0;
+        for (uint32_t d = b0; d < e0; d++) sum += s_acnt[d];
+        uint32_t inc = sum;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { uint32_t v = __shfl_up_sync(0xFFFFFFFFu, inc, o); if (lane >= o) inc += v; }
+        uint32_t run = inc - sum;
+        for (uint32_t d = b0; d < e0; d++) { uint32_t t = s_acnt[d]; s_doff[d] = run; run += t; }
+        if (lane == 31) s_doff[D] = inc;
+    }
+    __syncthreads();
+    for (uint32_t d = threadIdx.x; d < D; d += SCW_T) {
+        uint32_t tot = s_doff[d + 1] - s_doff[d];
+        if (tot) s_gbase[d] = atomicAdd(&cursor[(size_t)region * D + d], (unsigned long long)tot) - s_doff[d];
+    }
+#pragma unroll
+    for (int j = 0; j < SCW_I; j++) {
+        if (dp[j] == PT_NONE) continue;
+        const uint32_t d = dp[j] >> 16, slot = s_doff[d] + (dp[j] & 0xFFFFu);
+        s_stage[slot] = make_ulonglong2((unsigned long long)rr[j], (unsigned long long)(rr[j] >> 64));
+        s_sdig[slot] = (uint16_t)d;
+    }
+    __syncthreads();
+    const uint32_t n_valid = s_doff[D];
+    ulonglong2* dst2 = reinterpret_cast<ulonglong2*>(dst);
+    for (uint32_t slot = threadIdx.x; slot < n_valid; slot += SCW_T) dst2[s_gbase[s_sdig[slot]] + slot] = s_stage[slot];
+}
+static size_t scatter_wide_smem(int bits) {
+    const size_t D = (size_t)1 << bits;
+    return PT_TILE * 16 + D * 8 + (D + 1) * 4 + D * 4 + PT_TILE * 2 + 64;
+}
+
 // ---------------------------------------------------------------------------------------------- small helpers
 // exclusive scan of u64 counts -> offsets[n+1]; also cursors[i] = offsets[i] and, for the second level, the
 // number of tiles before every region.  Single CTA, coalesced tiles of 1024 x 4 elements.
@@ -291,8 +424,9 @@ static size_t scatter_smem(int bits) {
 PartPlan make_part_plan(uint32_t k, int prefix_bits, uint64_t n_samples_total) {
     PartPlan pl;
     pl.key_bits = 2 * ((int)k - 1);
+    pl.wide = k > 31;
     pl.sb = 1; while ((1ull << pl.sb) < n_samples_total) pl.sb++;
-    const int need1 = std::max(0, pl.key_bits + pl.sb + 2 - 64);       // the first digit must free room for the sample id
+    const int need1 = std::max(0, pl.key_bits + pl.sb + 2 - (pl.wide ? 128 : 64));       // the first digit must free room for the sample id
     pl.P = std::min(std::max(prefix_bits, need1), pl.key_bits);
     if (pl.P > 2 * PT_MAX_BITS) pl.P = 2 * PT_MAX_BITS;
     pl.P1 = std::max((pl.P + 1) / 2, need1);
@@ -309,6 +443,8 @@ static void set_scatter_attrs() {
     SKA_CUDA(cudaFuncSetAttribute(part_scatter_kernel<2, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)scatter_smem(PT_MAX_BITS)));
     SKA_CUDA(cudaFuncSetAttribute(part_scatter_kernel<1, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)scatter_smem(8)));
     SKA_CUDA(cudaFuncSetAttribute(part_scatter_kernel<2, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)scatter_smem(8)));
+    SKA_CUDA(cudaFuncSetAttribute(part_scatter_wide_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)scatter_wide_smem(PT_MAX_BITS)));
+    SKA_CUDA(cudaFuncSetAttribute(part_scatter_wide_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)scatter_wide_smem(PT_MAX_BITS)));
     done = true;
 }
 
@@ -330,13 +466,20 @@ void partition_coarse(const uint64_t* rec, uint64_t n_pos, const uint64_t* d_sam
     const unsigned hist_grid = (unsigned)std::min<uint64_t>(std::max<uint64_t>(n_tiles1, 1), (uint64_t)c.sm_count * 4);
     set_scatter_attrs();
     const Segs none{nullptr, nullptr, nullptr, nullptr, 1u};
-    if (n_pos && !k1_hist) SKA_LAUNCH(part_hist_kernel, hist_grid, PT_THREADS, D1 * 4, rec, n_pos, n_tiles1, none, f1, pl.P1, hist1);
+    if (n_pos && !k1_hist) {
+        if (pl.wide) SKA_LAUNCH(part_hist_wide_kernel, hist_grid, PT_THREADS, D1 * 4, rec, n_pos, n_tiles1, none, f1, pl.P1, hist1);
+        else SKA_LAUNCH(part_hist_kernel, hist_grid, PT_THREADS, D1 * 4, rec, n_pos, n_tiles1, none, f1, pl.P1, hist1);
+    }
     SKA_LAUNCH(part_scan_kernel, 1, 1024, 0, k1_hist ? k1_hist : (const unsigned long long*)hist1, D1, off1, cur1, tile_pref,
                k1_hist ? K1_HIST_COPIES : 1);
     timer().end();
     timer().begin("scatter1");
-    uint64_t* a = arena().take_n<uint64_t>(std::max<uint64_t>(n_pos, 1));
-    if (n_pos) {
+    uint64_t* a = arena().take_n<uint64_t>(std::max<uint64_t>(n_pos, 1) * (pl.wide ? 2 : 1));
+    if (n_pos && pl.wide) {
+        const PackWide pw{pl.sb, pl.low_bits, sid_base};
+        SKA_LAUNCH((part_scatter_wide_kernel<1>), (unsigned)n_tiles1, SCW_T, scatter_wide_smem(pl.P1), rec, n_pos, none, f1, pl.P1, pw,
+                   d_sample_off, n_samples_local, cur1, a);
+    } else if (n_pos) {
         if (pl.P1 == 8)
             SKA_LAUNCH((part_scatter_kernel<1, 8>), (unsigned)n_tiles1, SC_T, scatter_smem(pl.P1), rec, n_pos, none, f1, pl.P1, pk,
                        d_sample_off, n_samples_local, cur1, a);
@@ -365,12 +508,17 @@ void partition_fine(const uint64_t* src, const Segs& sg, uint64_t n_tiles2, uint
     PackFn pk{pl.sb, 0, 0};
     if (n_tiles2) {
         const unsigned g2 = (unsigned)std::min<uint64_t>(n_tiles2, (uint64_t)c.sm_count * 4);
-        SKA_LAUNCH(part_hist_kernel, g2, PT_THREADS, D2 * 4, src, (uint64_t)0, n_tiles2, sg, f2, pl.P2, hist2);
+        if (pl.wide) SKA_LAUNCH(part_hist_wide_kernel, g2, PT_THREADS, D2 * 4, src, (uint64_t)0, n_tiles2, sg, f2, pl.P2, hist2);
+        else SKA_LAUNCH(part_hist_kernel, g2, PT_THREADS, D2 * 4, src, (uint64_t)0, n_tiles2, sg, f2, pl.P2, hist2);
     }
     SKA_LAUNCH(part_scan_kernel, 1, 1024, 0, (const unsigned long long*)hist2, (uint32_t)NB, bucket_off, cur2, (uint64_t*)nullptr, 1);
     timer().end();
     timer().begin("scatter2");
-    if (n_tiles2) {
+    if (n_tiles2 && pl.wide) {
+        const PackWide pw{pl.sb, 0, 0};
+        SKA_LAUNCH((part_scatter_wide_kernel<2>), (unsigned)n_tiles2, SCW_T, scatter_wide_smem(pl.P2), src, (uint64_t)0, sg, f2, pl.P2, pw,
+                   (const uint64_t*)nullptr, 0u, cur2, dst);
+    } else if (n_tiles2) {
         if (pl.P2 == 8)
             SKA_LAUNCH((part_scatter_kernel<2, 8>), (unsigned)n_tiles2, SC_T, scatter_smem(pl.P2), src, (uint64_t)0, sg, f2, pl.P2, pk,
                        (const uint64_t*)nullptr, 0u, cur2, dst);
@@ -396,7 +544,7 @@ void partition_records(const uint64_t* rec, uint64_t n_pos, const uint64_t* d_sa
     uint64_t n_tiles2 = 0;
     SKA_CUDA(cudaMemcpyAsync(&n_tiles2, tile_pref + D1, 8, cudaMemcpyDeviceToHost, c.stream));
     SKA_CUDA(cudaStreamSynchronize(c.stream));
-    uint64_t* b = scratch ? scratch : arena().take_n<uint64_t>(std::max<uint64_t>(n_pos, 1));
+    uint64_t* b = scratch ? scratch : arena().take_n<uint64_t>(std::max<uint64_t>(n_pos, 1) * (pl.wide ? 2 : 1));
     const Segs sg{tile_pref, off1, off1 + 1, nullptr, D1};
     partition_fine(a, sg, n_tiles2, D1, pl, b, d_off);
     *out = b;

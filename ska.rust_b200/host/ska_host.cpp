@@ -47,7 +47,9 @@ MergeSkaArray MergeSkaArray::load(const std::string& filename) {
     ska_array_t* h = nullptr;
     check(skagpu_array_from_host(a.k, a.rc, a.key_bits, a.n_rows, a.n_samples, a.keys.data(), a.variants.data(), a.counts.data(), &h));
     lap("array on the device");
-    return MergeSkaArray(h, a.names, a.ska_version);
+    MergeSkaArray out(h, a.names, a.ska_version);
+    out.k_bits_field_ = a.k_bits_field;
+    return out;
 }
 
 skf::Array MergeSkaArray::to_host() const {
@@ -55,6 +57,7 @@ skf::Array MergeSkaArray::to_host() const {
     uint64_t rows, keys, samples; uint32_t k, bits; int rc;
     dims(h_, rows, keys, samples, k, rc, bits);
     a.k = k; a.rc = rc != 0; a.key_bits = bits; a.n_rows = rows; a.n_samples = samples; a.names = names_; a.ska_version = version_;
+    a.k_bits_field = k_bits_field_ ? k_bits_field_ : (k > 31 ? 128u : 64u);
     a.keys.resize(keys * (bits / 64)); a.variants.resize(rows * samples); a.counts.resize(rows);
     skf::prefault(a.variants.data(), a.variants.size(), (int)std::thread::hardware_concurrency());
     check(skagpu_export(h_, a.keys.data(), a.variants.data(), a.counts.data()));
@@ -101,7 +104,7 @@ void MergeSkaArray::write_fasta(FILE* f) const {
 std::string MergeSkaArray::display(bool full_info) const {
     skf::Array a = to_host();
     std::ostringstream o;
-    o << "ska_version=" << a.ska_version << "\nk=" << a.k << "\nk_bits=" << a.key_bits << "\nrc=" << (a.rc ? "true" : "false")
+    o << "ska_version=" << a.ska_version << "\nk=" << a.k << "\nk_bits=" << a.k_bits_field << "\nrc=" << (a.rc ? "true" : "false")
       << "\nk-mers=" << a.n_rows << "\nsamples=" << a.n_samples << "\n";
     o << "sample_names=[";
     for (size_t i = 0; i < a.names.size(); i++) o << (i ? ", " : "") << '"' << a.names[i] << '"';   // Rust {:?} of Vec<String>
@@ -137,7 +140,9 @@ MergeSkaArray MergeSkaArray::extend(MergeSkaArray& a, MergeSkaArray& b) {
     check(skagpu_merge_arrays(a.h_, b.h_, &h));
     std::vector<std::string> names = a.names_;
     names.insert(names.end(), b.names_.begin(), b.names_.end());                    // merge_ska_dict.rs:169
-    return MergeSkaArray(h, names, a.version_);
+    MergeSkaArray out(h, names, a.version_);
+    out.k_bits_field_ = a.k_bits_field_;
+    return out;
 }
 
 void MergeSkaArray::delete_samples(const std::vector<std::string>& del_names) {

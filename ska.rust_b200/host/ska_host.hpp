@@ -32,7 +32,7 @@ class MergeSkaArray {
         : h_(h), names_(std::move(names)), version_(std::move(version)) {}
     MergeSkaArray(MergeSkaArray&& o) noexcept { *this = std::move(o); }
     MergeSkaArray& operator=(MergeSkaArray&& o) noexcept {
-        if (this != &o) { reset(); h_ = o.h_; o.h_ = nullptr; names_ = std::move(o.names_); version_ = std::move(o.version_); }
+        if (this != &o) { reset(); h_ = o.h_; o.h_ = nullptr; names_ = std::move(o.names_); version_ = std::move(o.version_); k_bits_field_ = o.k_bits_field_; }
         return *this;
     }
     MergeSkaArray(const MergeSkaArray&) = delete;
@@ -66,6 +66,7 @@ class MergeSkaArray {
     ska_array_t* h_ = nullptr;
     std::vector<std::string> names_;
     std::string version_;
+    uint32_t k_bits_field_ = 0;      // what a loaded file said (informational; see skf::Array::k_bits_field)
 };
 
 MergeSkaArray build_and_merge(const std::vector<InputFastx>& input_files, size_t k, bool rc, const QualOpts& qual,

@@ -355,7 +355,7 @@ Array decode(const uint8_t* data, size_t len, int threads) {
             }
         } else if (key == "variant_count") { uint64_t n = r.array(); a.counts.resize(n); for (uint64_t i = 0; i < n; i++) a.counts[i] = r.uint_(); }
         else if (key == "ska_version") a.ska_version = r.text();
-        else if (key == "k_bits") (void)r.uint_();      // informational (merge_ska_array.rs:124-125); width follows the values
+        else if (key == "k_bits") a.k_bits_field = (uint32_t)r.uint_();   // informational (merge_ska_array.rs:124-125); width follows the values
         else throw std::runtime_error("skf: unexpected field " + key);
     }
     if (a.variants.size() != a.n_rows * a.n_samples || a.counts.size() != a.n_rows || a.names.size() != a.n_samples)
@@ -451,7 +451,7 @@ static std::vector<std::vector<uint8_t>> encode_chunks(const Array& a, int threa
     put_text(tail, "variant_count"); put_head(tail, 4, a.counts.size());
     put_parallel(tail, a.counts.size(), threads, [&a](std::vector<uint8_t>& w, size_t i) { put_head(w, 0, a.counts[i]); });
     put_text(tail, "ska_version"); put_text(tail, a.ska_version);
-    put_text(tail, "k_bits"); put_head(tail, 0, a.key_bits);
+    put_text(tail, "k_bits"); put_head(tail, 0, a.k_bits_field ? a.k_bits_field : a.key_bits);
 
     const size_t nv = a.variants.size();
     const uint8_t* v = a.variants.data();

@@ -48,6 +48,8 @@ struct Array {                       // host image of MergeSkaArray<IntT>
     Bytes variants;                  // row-major n_rows x n_samples
     std::vector<uint64_t> counts;
     std::string ska_version = "0.5.2";
+    uint32_t k_bits_field = 0;       // the file's informational k_bits (merge_ska_array.rs:124-125): a k = 33 array whose keys all fit
+                                     // 64 bits loads as u64 in the reference too, yet keeps saying 128; 0 = derive from key_bits
     uint64_t n_keys() const { return keys.size() / (key_bits / 64); }
 };
 

@@ -141,7 +141,9 @@ def test_cli_rfile_and_failures(gold_in, tmp_path):
     rfile.write_text(f"test_1\t{gold_in('test_1.fa')}\ntest_2\t{gold_in('test_2.fa')}\n")
     run(["build", "-f", str(rfile), "-o", "basic_build_opts", "-v", "--threads", "2", "-k", "31"], cwd=str(tmp_path))
     assert os.path.exists(tmp_path / "basic_build_opts.skf")
-    assert run(["build", "-o", "x", "-k", "33", gold_in("test_1.fa"), gold_in("test_2.fa")], cwd=str(tmp_path), check=False).returncode == 101
+    # k > 31 builds with 128-bit split k-mers (tests/align.rs:116-144: column set {CT, TA} at k = 33)
+    run(["build", "-o", "x", "-k", "33", gold_in("test_1.fa"), gold_in("test_2.fa")], cwd=str(tmp_path))
+    assert O.var_hash(run(["align", "x.skf"], cwd=str(tmp_path)).stdout) == {("C", "T"), ("T", "A")}
     assert run(["build", "-o", "x", gold_in("nonexistent.fa")], cwd=str(tmp_path), check=False).returncode == 101
 
 
@@ -252,3 +254,37 @@ def test_cli_map(gold_in, gold_ok, tmp_path):
     assert run(["map", ref3, gold_in("merge_k9.skf"), "--repeat-mask"], cwd=wd).stdout == gold_ok("map_aln_two_chrom.masked.stdout")
     assert matches(run(["map", ref3, gold_in("merge_k9.skf"), "--repeat-mask", "--format", "vcf"], cwd=wd).stdout,
                    gold_ok("map_vcf_two_chrom.masked.stdout"))
+
+
+@pytest.mark.gpu
+def test_cli_u128_build_merge_delete_weed_map(gold_in, gold_ok, tmp_path):
+    """k > 31 end to end: tests/skf_ops.rs:94-163 merge_delete_u128, :259-289 weed at k = 41, tests/map.rs:93-117 map_u128,
+    tests/align.rs k = 33 (k33.stdout)"""
+    import shutil
+    wd = str(tmp_path)
+    run(["build", gold_in("test_1.fa"), "-o", "test_1", "-k", "41"], cwd=wd)
+    run(["build", gold_in("test_2.fa"), "-o", "test_2", "-k", "41"], cwd=wd)
+    run(["merge", "test_1.skf", "test_2.skf", "-o", "merge", "-v"], cwd=wd)
+    # the merged file holds what the reference's merge_k41.skf holds
+    a, b = skf_py.load_skf(str(tmp_path / "merge.skf")), skf_py.load_skf(gold_in("merge_k41.skf"))
+    rows = lambda d: {k_: (d["variants"][i * d["n_samples"]:(i + 1) * d["n_samples"]], d["variant_count"][i]) for i, k_ in enumerate(d["split_kmers"])}
+    assert rows(a) == rows(b) and a["k"] == 41 and a["k_bits"] == 128
+    assert run(["delete", "-s", "merge.skf", "-f", gold_in("missing_delete.txt"), "-v"], cwd=wd, check=False).returncode != 0
+    test1_nk = run(["nk", "test_1.skf"], cwd=wd).stdout
+    run(["delete", "-s", "merge.skf", "-o", "merge_delete", "test_2", "-v"], cwd=wd)
+    assert run(["nk", "merge_delete.skf"], cwd=wd).stdout == test1_nk
+    # weed at k = 41
+    run(["build", "-o", "build_k41", "-k", "41", gold_in("test_1.fa"), gold_in("test_2.fa"), "-v"], cwd=wd)
+    run(["weed", "build_k41.skf", "--filter", "no-ambig-or-const", "--min-freq", "1", "-v"], cwd=wd)
+    assert matches(run(["nk", "build_k41.skf", "--full-info", "-v"], cwd=wd).stdout, gold_ok("weed_nk_k41.stdout"))
+    shutil.copy(gold_in("merge_k41.skf"), tmp_path / "m41.skf")
+    # weed.fa holds nothing as long as 41 bases: RefSka::new panics "has no valid sequence" (ska_ref.rs:253-255)
+    assert run(["weed", "m41.skf", gold_in("weed.fa")], cwd=wd, check=False).returncode == 101
+    run(["weed", "m41.skf", gold_in("test_ref.fa")], cwd=wd)                # key lookups on a loaded (unsorted) u128 array
+    # map against u128 arrays
+    ref = gold_in("test_ref.fa")
+    assert run(["map", ref, gold_in("merge_k41.skf"), "-v", "--threads", "2"], cwd=wd).stdout == gold_ok("map_aln_k41.stdout")
+    assert matches(run(["map", ref, gold_in("merge_k41.skf"), "-f", "vcf"], cwd=wd).stdout, gold_ok("map_vcf_k41.stdout"))
+    # k = 33 build + nk (tests/align.rs:116-153)
+    run(["build", "-o", "k33", "-k", "33", gold_in("test_1.fa"), gold_in("test_2.fa")], cwd=wd)
+    assert matches(run(["nk", "k33.skf"], cwd=wd).stdout, gold_ok("k33.stdout"))

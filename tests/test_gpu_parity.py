@@ -754,3 +754,90 @@ def test_map_lookup_matches_dictionary_walk(k, rc):
     assert n == n_ref
     assert [int(p) for p in pos] == exp_pos
     assert np.array_equal(var, np.array(exp_rows, dtype=np.uint8).reshape(len(exp_pos), len(names)))
+
+
+# ------------------------------------------------------------------ k > 31: 128-bit split k-mers (src/lib.rs:607-622)
+@pytest.mark.parametrize("k,rc", [(33, True), (41, True), (41, False), (63, True)])
+def test_wide_k1_windows_match_rolling_iterator(k, rc):
+    rng = np.random.default_rng(4321 + k)
+    samples_records = [random_records(rng, int(rng.integers(1, 5)), 3000) for _ in range(4)]
+    core = bytes(rng.choice(np.frombuffer(b"ACGT", dtype=np.uint8), size=k + 1))
+    samples_records.append([core[:k], core, core[:k - 1], b"", core + b"N" + core[:k], core[:k] + b"N" + core, b"N" * 70, core * 3])
+    long = bytearray(rng.choice(np.frombuffer(b"ACGT", dtype=np.uint8), size=9000).tobytes())
+    for p in (4090, 4096, 4097, 8191):
+        long[p] = ord("N")
+    samples_records.append([bytes(long)])
+    batch = S.SeqBatch([S.Sample.from_records(r) for r in samples_records])
+    rec, _ms = batch.k1_extract(k, rc=rc)
+    rec = rec.reshape(-1, 2)
+    got = [(int(lo) | (int(hi) << 64)) for lo, hi in rec]
+    exp = []
+    h = (k - 1) // 2
+    for recs in samples_records:
+        for r in recs:
+            e = [(1 << 128) - 1] * len(r)
+            w = O.windows(r, k, rc=rc)
+            for i in range(w["n"]):
+                e[int(w["mid_pos"][i]) - h] = (w["key"][i] << 4) | (1 << int(w["mid"][i]))
+            exp.extend(e)
+    assert len(got) == len(exp)
+    bad = [i for i, (a, b) in enumerate(zip(got, exp)) if a != b]
+    assert not bad, f"{len(bad)} mismatching positions, first at {bad[:5]}"
+
+
+def assert_same_array_wide(g, o):
+    gd, od = g.dims(), o.dims()
+    assert gd == od, (gd, od)
+    gk, gv, gc = g.export()
+    ok, ov, oc = o.export()
+    assert [int(x) for x in gk] == ok
+    assert np.array_equal(gv, ov) and np.array_equal(gc, oc)
+
+
+@pytest.mark.parametrize("k,rc", [(33, True), (41, False), (51, True), (63, True)])
+def test_wide_build_matches_oracle(k, rc):
+    recs, samples, names = _rand_samples(900 + k, 6, k, rc)
+    # repeats and IUPAC merges: a duplicated stretch with one changed middle base, a palindromic stretch
+    extra = recs[0][0][:300]
+    mutated = bytearray(extra); mutated[150] = ord("A") if extra[150] != ord("A") else ord("C")
+    recs[2].append(extra + bytes(mutated))
+    samples = [S.Sample.from_records(r) for r in recs]
+    g = S.build_from_samples(samples, names, k, rc)
+    o = ora_from_gpu_samples(samples, names, k, rc)
+    assert g.dims()["key_bits"] == 128
+    assert_same_array_wide(g, o)
+    # the batch path (device-resident input) and forced bucket splitting take the same answer
+    g2 = S.api.build_from_batch(S.SeqBatch(samples), names, k, rc)
+    assert_same_array_wide(g2, o)
+    os.environ["SKA_WIDE_LIMIT"] = "8"
+    os.environ["SKA_PREFIX_BITS_WIDE"] = "3"
+    try:
+        g3 = S.build_from_samples(samples, names, k, rc)
+    finally:
+        del os.environ["SKA_WIDE_LIMIT"], os.environ["SKA_PREFIX_BITS_WIDE"]
+    assert_same_array_wide(g3, o)
+
+
+def test_wide_build_reproduces_reference_k41_skf(gold_in):
+    """merge_k41.skf = `ska build -k 41 test_1.fa test_2.fa` written by the reference (u128 keys)"""
+    ref = skf_py.load_skf(gold_in("merge_k41.skf"))
+    var = np.frombuffer(ref["variants"], dtype=np.uint8).reshape(ref["n_rows"], ref["n_samples"])
+    want = {k_: (bytes(var[i]), ref["variant_count"][i]) for i, k_ in enumerate(ref["split_kmers"])}
+    g = gpu_build_files([gold_in("test_1.fa"), gold_in("test_2.fa")], k=41)
+    gk, gv, gc = g.export()
+    got = {int(k_): (bytes(gv[i]), int(gc[i])) for i, k_ in enumerate(gk)}
+    assert got == want
+    # distances and filters on the array we built == on the file the reference built
+    buf = io.BytesIO()
+    S.api.distance(g, buf)
+    with open(os.path.join(os.path.dirname(gold_in("x")), "..", "correct", "merge_k41.dist.stdout"), "rb") as fh:
+        assert buf.getvalue() == fh.read()
+
+
+def test_wide_fastq_count_filter_k63(gold_in):
+    """tests/fastq_input.rs:113-192 count_check_long: k = 63 reads, min-count 2 -> {GM}, min-count 3 -> {GA} (column sets)"""
+    files = [(gold_in(f"test_long_{i}_fwd.fastq.gz"), gold_in(f"test_long_{i}_rev.fastq.gz")) for i in (1, 2)]
+    for mc in (1, 2, 3):
+        g = gpu_build_files(files, k=63, names=["a", "b"], min_count=mc)
+        o = O.OracleArray.build_from_files(files, k=63, names=["a", "b"], min_count=mc)
+        assert_same_array_wide(g, o)
