@@ -215,6 +215,12 @@ int skagpu_map_dims(const ska_mapping_t* m, uint64_t* n_mapped, uint64_t* n_ref_
 int skagpu_map_export(const ska_mapping_t* m, uint64_t* middle_positions, uint8_t* variants_rowmajor, uint64_t* ref_records);
 void skagpu_map_free(ska_mapping_t* m);
 
+/* The counting half of `ska cov` and of `ska build --min-count auto` (CoverageHistogram::new + the histogram loop of
+ * fit_histogram, src/coverage.rs:70-135, 156-163): every window of every read of the sample (both files, qualities ignored)
+ * counts towards its canonical split k-mer; hist[c - 1] = number of distinct split k-mers seen exactly c times, c = 1..1000.
+ * The Poisson-mixture fit on the histogram (coverage.rs:165-213) is host code. */
+int skagpu_kmer_count_hist(const ska_input_t* reads, uint32_t k, int rc, uint64_t* hist /* 1000 bins */);
+
 /* Self-check of a device-resident array (no reference counterpart; bench.py's in-run parity check and the tests):
  * out[0] = order-independent checksum over the non-'-' cells (key, column - col_lo, letter) of columns [col_lo, col_hi)
  *          -- MergeSkaDict::merge (merge_ska_dict.rs:119-151) only moves cells, so a rank's local build and the same

@@ -36,7 +36,7 @@ EXPORTS = [
     "skagpu_array_dev", "skagpu_key_cumulative", "skagpu_merge_partial_rows_dev", "skagpu_array_checksum",
     "skagpu_pack_bases", "skagpu_build_packed", "skagpu_seqbatch_upload_packed", "skagpu_export_transposed_async",
     "skagpu_export_wait", "skagpu_seqbatch_upload_packed_async", "skagpu_merge_arrays", "skagpu_delete_samples", "skagpu_weed",
-    "skagpu_map", "skagpu_map_dims", "skagpu_map_export", "skagpu_map_free",
+    "skagpu_map", "skagpu_map_dims", "skagpu_map_export", "skagpu_map_free", "skagpu_kmer_count_hist",
 ]
 
 
@@ -102,6 +102,7 @@ def lib():
         L.skagpu_map_dims.argtypes = [C.c_void_p] + [C.c_void_p] * 4
         L.skagpu_map_export.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.skagpu_map_free.argtypes = [C.c_void_p]
+        L.skagpu_kmer_count_hist.argtypes = [C.c_void_p, C.c_uint32, C.c_int, C.c_void_p]
         L.skagpu_pack_bases.restype = None
         L.skagpu_pack_bases.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.c_void_p, C.c_void_p]
         L.skagpu_build_packed.argtypes = [C.c_void_p, C.c_size_t, C.c_uint32, C.c_int, C.c_void_p]
@@ -553,6 +554,13 @@ def build_from_samples(samples, names, k, rc, qual=None, proportion_reads=None):
     _check(lib().skagpu_build(_inputs_array(samples), len(samples), k, int(rc), qual.min_count, qual.min_qual, qf,
                               float(proportion_reads) if proportion_reads else 0.0, C.byref(h)))
     return MergeSkaArray(h, names)
+
+
+def kmer_count_hist(sample, k, rc=True):
+    """counts[c - 1] = distinct split k-mers of the read set seen c times, c = 1..1000 (coverage.rs:70-135, 156-163)"""
+    hist = np.zeros(1000, dtype=np.uint64)
+    _check(lib().skagpu_kmer_count_hist(_inputs_array([sample]), k, int(rc), hist.ctypes.data))
+    return hist
 
 
 def merge_arrays(a, b):

@@ -1030,6 +1030,20 @@ int skagpu_map_export(const ska_mapping_t* m, uint64_t* middle_positions, uint8_
 
 void skagpu_map_free(ska_mapping_t* m) { delete m; }
 
+int skagpu_kmer_count_hist(const ska_input_t* reads, uint32_t k, int rc, uint64_t* hist) {
+    API_TRY
+    if (!reads || !hist) throw Error("null argument");
+    check_k(k);
+    ctx().ensure();
+    timer().clear();
+    ska_input_t plain = *reads;
+    plain.qual = nullptr;                                  // quality scores are ignored by the counter (coverage.rs:101)
+    std::unique_ptr<SeqBatch> b = upload(&plain, 1, 0.0);
+    kmer_count_histogram(*b, k, rc != 0, hist);
+    return 0;
+    API_CATCH
+}
+
 int skagpu_array_checksum(const ska_array_t* h, uint32_t col_lo, uint32_t col_hi, uint64_t* out) {
     API_TRY
     if (!h || !out) throw Error("null argument");

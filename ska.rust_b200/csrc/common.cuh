@@ -214,6 +214,8 @@ uint64_t weed_rows(Array& a, const SeqBatch& weed, bool reverse);
 void extend_arrays(Array& a, Array& b, Array& out);
 void map_reference(Array& a, const SeqBatch& ref, std::vector<uint64_t>& h_pos, DevBuf<uint8_t>& mapped, uint64_t& n_ref_kmers,
                    std::vector<uint64_t>* h_records);
+// cov.cu: distinct split k-mers of a read set by multiplicity (1000 bins), the counting half of `ska cov`
+void kmer_count_histogram(const SeqBatch& reads, uint32_t k, bool rc, uint64_t* h_hist);
 // verify.cu: {cell checksum over columns [col_lo, col_hi), rows with a cell there, rows with a wrong count, keys out of order}
 void array_checksum(const Array& a, uint32_t col_lo, uint32_t col_hi, uint64_t* h_out);
 

@@ -84,7 +84,7 @@ int main(int argc, char** argv) {
     auto start = std::chrono::steady_clock::now();
     // CUDA context creation (~0.4 s on a B200) runs beside the host's first phase (file parsing, .skf decoding)
     std::thread cuda_init;
-    if (cmd == "build" || cmd == "align" || cmd == "distance" || cmd == "nk" || cmd == "merge" || cmd == "weed" || cmd == "delete" || cmd == "map")
+    if (cmd == "build" || cmd == "align" || cmd == "distance" || cmd == "nk" || cmd == "merge" || cmd == "weed" || cmd == "delete" || cmd == "map" || cmd == "cov")
         cuda_init = std::thread([] { skagpu_set_device(0); });
     try {
         if (cmd == "build") {
@@ -95,17 +95,20 @@ int main(int argc, char** argv) {
             size_t k = parse_k(a.get("-k", "31"));
             size_t threads = parse_threads(a.get("--threads", "1"));
             QualOpts q;
-            q.min_qual = (uint8_t)atoi(a.get("--min-qual", "20").c_str());
             q.qual_filter = parse_qual_filter(a.get("--qual-filter", "strict"));
-            if (a.has("--min-count")) {                    // kmer_min_cutoff (io_utils.rs:175-212); "auto" needs `ska cov` (out of scope)
-                std::string mc = a.get("--min-count");
-                if (mc == "auto") throw SkaError("--min-count auto (coverage model fit) is outside this engine's scope; pass a number");
-                int v = atoi(mc.c_str());
-                if (v < 1) usage_error("Minimum kmer count must be >= 1");
-                q.min_count = (uint16_t)v;
+            std::string mc = a.get("--min-count");          // valid_min_kmer (cli.rs:86-108): "auto" or an integer in 1..=65535
+            if (!mc.empty() && mc != "auto") {
+                char* e; long v = strtol(mc.c_str(), &e, 10);
+                if (*e || v < 1 || v > 65535) usage_error("`" + mc + "` isn't a valid minimum kmer count: pass 'auto' or an integer in 1..65535");
+            }
+            {
+                char* e; long v = strtol(a.get("--min-qual", "20").c_str(), &e, 10);
+                if (*e || v < 0 || v > 255) usage_error("invalid value '" + a.get("--min-qual") + "' for '--min-qual <MIN_QUAL>'");
+                q.min_qual = (uint8_t)v;
             }
             double prop = a.has("--proportion-reads") ? parse_01(a.get("--proportion-reads"), "proportion") : 0.0;
             auto inputs = io_utils::get_input_list(a.get("-f"), a.pos);
+            q.min_count = io_utils::kmer_min_cutoff(mc, inputs, k, !a.has("--single-strand"), a.has("--verbose"));   // lib.rs:592-622
             MergeSkaArray arr = build_and_merge(inputs, k, !a.has("--single-strand"), q, threads, prop);
             generic_modes::save_skf(arr, a.get("-o"), (int)threads);
         } else if (cmd == "align") {
@@ -165,6 +168,22 @@ int main(int argc, char** argv) {
             generic_modes::weed(arr, a.pos.size() > 1 ? a.pos[1] : "", a.has("--reverse"), min_freq, a.has("--filter-ambig-as-missing"),
                                 parse_filter(a.get("--filter", "no-filter")), a.has("--ambig-mask"), a.has("--no-gap-only-sites"),
                                 a.has("-o") ? a.get("-o") : a.pos[0], (int)std::thread::hardware_concurrency());
+        } else if (cmd == "cov") {                         // lib.rs:828-851
+            Args a = parse(argc, argv, 2, {"-k"}, {"--single-strand"});
+            if (a.pos.size() != 2) usage_error("the following required arguments were not provided: <FASTQ_FWD> <FASTQ_REV>");
+            size_t k = parse_k(a.get("-k", "31"));
+            CoverageHistogram cov(a.pos[0], a.pos[1], k, !a.has("--single-strand"), a.has("--verbose"));
+            const size_t cutoff = cov.fit_histogram();
+            const std::string table = cov.plot_hist();
+            fwrite(table.data(), 1, table.size(), stdout);
+            fprintf(stderr, "Estimated cutoff\t%zu\n", cutoff);
+        } else if (cmd == "fit-selftest") {
+            // host-only helper (no device): the reference's unit test of the mixture fit (coverage.rs:369-415) -> prints the cutoff
+            std::vector<uint32_t> counts;
+            for (int i = 2; i < argc; i++) counts.push_back((uint32_t)strtoul(argv[i], nullptr, 10));
+            CoverageHistogram cov(counts);
+            const size_t cutoff = cov.fit_histogram();
+            printf("cutoff %zu w0 %.6f c %.4f\n", cutoff, cov.w0(), cov.c());
         } else if (cmd == "recode") {
             // host-only helper (no device): decode a .skf and write it again with this codec
             Args a = parse(argc, argv, 2, {"--threads"}, {});

@@ -6,6 +6,7 @@
 #include <cmath>
 #include <cstring>
 #include <fstream>
+#include <limits>
 #include <regex>
 #include <sstream>
 #include <thread>
@@ -364,6 +365,125 @@ void RefSka::write_vcf(FILE* f, size_t threads) {
         }
 }
 
+// ------------------------------------------------------------------------------------------ CoverageHistogram
+namespace {
+// coverage.rs:277-302
+double lse(double a, double b) { const double x = std::max(a, b); return x + std::log(std::exp(a - x) + std::exp(b - x)); }
+double ln_dpois(double x, double lambda) { return x * std::log(lambda) - std::lgamma(x + 1.0) - lambda; }
+double comp_a(double w0, double i) { return std::log(w0) + ln_dpois(i, 1.0); }
+double comp_b(double w0, double c, double i) { return std::log(1.0 - w0) + ln_dpois(i, c); }
+double log_likelihood(const double p[2], const std::vector<double>& counts) {             // coverage.rs:305-320
+    const double w0 = p[0], c = p[1];
+    if (!(w0 >= 0.0 && w0 <= 1.0) || c < 1.0) return -std::numeric_limits<double>::max();   // f64::MIN, the 'soft' bounds
+    double ll = 0.0;
+    for (size_t i = 0; i < counts.size(); i++) ll += counts[i] * lse(comp_a(w0, (double)i + 1.0), comp_b(w0, c, (double)i + 1.0));
+    return ll;
+}
+void grad_ll(const double p[2], const std::vector<double>& counts, double g[2]) {           // coverage.rs:324-341
+    const double w0 = p[0], c = p[1];
+    g[0] = g[1] = 0.0;
+    for (size_t i = 0; i < counts.size(); i++) {
+        const double x = (double)i + 1.0, a = comp_a(w0, x), b = comp_b(w0, c, x);
+        const double dlda = 1.0 / (1.0 + std::exp(b - a)), dldb = 1.0 / (1.0 + std::exp(a - b));
+        g[0] += counts[i] * (dlda / w0 - dldb / (1.0 - w0));
+        g[1] += counts[i] * (dldb * (x / c - 1.0));
+    }
+}
+size_t find_cutoff(const double p[2], size_t max_cutoff) {                                   // coverage.rs:345-360
+    size_t cutoff = 1;
+    while (cutoff < max_cutoff) {
+        if (comp_a(p[0], (double)cutoff) - comp_b(p[0], p[1], (double)cutoff) < 0.0) break;
+        cutoff++;
+    }
+    return cutoff;
+}
+// Rust's `{:e}` for f64: shortest digits that round-trip, exponent without sign padding
+std::string rust_lower_exp(double x) {
+    if (x == 0.0) return "0e0";
+    char buf[64];
+    for (int prec = 0; prec < 18; prec++) {
+        snprintf(buf, sizeof buf, "%.*e", prec, x);
+        if (strtod(buf, nullptr) == x) break;
+    }
+    std::string s(buf);
+    const size_t e = s.find('e');
+    std::string mant = s.substr(0, e);
+    int ex = atoi(s.c_str() + e + 1);
+    if (mant.find('.') != std::string::npos) { while (mant.back() == '0') mant.pop_back(); if (mant.back() == '.') mant.pop_back(); }
+    return mant + "e" + std::to_string(ex);
+}
+}  // namespace
+
+CoverageHistogram::CoverageHistogram(const std::string& fastq1, const std::string& fastq2, size_t k, bool rc, bool verbose) : verbose_(verbose) {
+    if (k < 5 || k > 63 || k % 2 == 0) throw SkaError("Invalid k-mer length");                // coverage.rs:71-73
+    fastx::Records r1 = fastx::parse_file(fastq1), r2 = fastx::parse_file(fastq2);
+    for (auto* p : {&r1, &r2})
+        if (!p->is_fastq)
+            throw SkaError((p == &r1 ? fastq1 : fastq2) + " appears to be FASTA.\nCoverage can only be used with FASTQ files, not FASTA.");
+    fastx::append(r1, r2);
+    ska_input_t in = {r1.seq.data(), nullptr, r1.rec_off.data(), r1.n_rec(), r1.n_rec()};
+    hist_.assign(1000, 0);
+    check(skagpu_kmer_count_hist(&in, (uint32_t)k, rc, hist_.data()));
+}
+
+size_t CoverageHistogram::fit_histogram() {
+    if (fitted_) throw SkaError("Model already fitted");                                        // coverage.rs:152-154
+    if (!from_counts_) { counts_.assign(1000, 0); for (size_t i = 0; i < 1000; i++) counts_[i] = (uint32_t)std::min<uint64_t>(hist_[i], 0xFFFFFFFFu); }
+    while (!counts_.empty() && counts_.back() < 50) counts_.pop_back();                         // MIN_FREQ (coverage.rs:166-173)
+    std::vector<double> cf(counts_.begin(), counts_.end());
+    // BFGS (argmin::solver::quasinewton::BFGS) on the negative log likelihood, backtracking line search with the Armijo condition
+    // c1 = 1e-4 and contraction 0.9 (argmin's BacktrackingLineSearch defaults), inverse Hessian = identity, tolerances: gradient
+    // norm sqrt(eps), cost change 1e-6; at most 20 iterations.
+    double x[2] = {w0_, c_}, g[2], H[2][2] = {{1.0, 0.0}, {0.0, 1.0}};
+    double cost = -log_likelihood(x, cf), prev_cost = std::numeric_limits<double>::infinity();
+    grad_ll(x, cf, g); g[0] = -g[0]; g[1] = -g[1];
+    const double tol_grad = std::sqrt(std::numeric_limits<double>::epsilon()), tol_cost = 1e-6;
+    bool converged = false;
+    for (int iter = 0;; iter++) {
+        if (std::sqrt(g[0] * g[0] + g[1] * g[1]) < tol_grad || std::fabs(prev_cost - cost) < tol_cost) { converged = true; break; }
+        if (iter >= 20) break;                                                                  // max_iters(20)
+        const double p[2] = {-(H[0][0] * g[0] + H[0][1] * g[1]), -(H[1][0] * g[0] + H[1][1] * g[1])};
+        const double slope = g[0] * p[0] + g[1] * p[1];
+        double alpha = 1.0, xn[2], cn = 0.0;
+        for (int ls = 0; ls < 2000; ls++) {                                                     // f(x + a p) <= f(x) + c1 a grad.p
+            xn[0] = x[0] + alpha * p[0]; xn[1] = x[1] + alpha * p[1];
+            cn = -log_likelihood(xn, cf);
+            if (cn <= cost + 1e-4 * alpha * slope) break;
+            alpha *= 0.9;
+        }
+        double gn[2];
+        grad_ll(xn, cf, gn); gn[0] = -gn[0]; gn[1] = -gn[1];
+        const double s[2] = {xn[0] - x[0], xn[1] - x[1]}, y[2] = {gn[0] - g[0], gn[1] - g[1]};
+        const double ys = y[0] * s[0] + y[1] * s[1], rho = 1.0 / ys;
+        // H <- (I - rho s y^T) H (I - rho y s^T) + rho s s^T
+        double A[2][2] = {{1.0 - rho * s[0] * y[0], -rho * s[0] * y[1]}, {-rho * s[1] * y[0], 1.0 - rho * s[1] * y[1]}};
+        double B[2][2] = {{1.0 - rho * y[0] * s[0], -rho * y[0] * s[1]}, {-rho * y[1] * s[0], 1.0 - rho * y[1] * s[1]}};
+        double T[2][2], Hn[2][2];
+        for (int i = 0; i < 2; i++) for (int j = 0; j < 2; j++) T[i][j] = A[i][0] * H[0][j] + A[i][1] * H[1][j];
+        for (int i = 0; i < 2; i++) for (int j = 0; j < 2; j++) Hn[i][j] = T[i][0] * B[0][j] + T[i][1] * B[1][j] + rho * s[i] * s[j];
+        for (int i = 0; i < 2; i++) for (int j = 0; j < 2; j++) H[i][j] = Hn[i][j];
+        prev_cost = cost; cost = cn;
+        x[0] = xn[0]; x[1] = xn[1]; g[0] = gn[0]; g[1] = gn[1];
+        if (verbose_) fprintf(stderr, "iter %d cost %.6f w0 %.6f c %.6f\n", iter + 1, cost, x[0], x[1]);
+    }
+    if (!converged) throw SkaError("Couldn't fit coverage model: Optimiser did not converge: Maximum number of iterations reached");
+    w0_ = x[0]; c_ = x[1];
+    cutoff_ = find_cutoff(x, counts_.size());
+    fitted_ = true;
+    return cutoff_;
+}
+
+std::string CoverageHistogram::plot_hist() const {
+    if (!fitted_) throw SkaError("Model has not yet been fitted");                              // coverage.rs:221-223
+    std::string out = "Count\tK_mers\tMixture_density\tComponent\n";
+    for (size_t idx = 0; idx < counts_.size(); idx++) {
+        const double x = (double)idx + 1.0;
+        out += std::to_string(idx + 1) + "\t" + std::to_string(counts_[idx]) + "\t" + rust_lower_exp(std::exp(lse(comp_a(w0_, x), comp_b(w0_, c_, x)))) +
+               "\t" + ((idx + 1) < cutoff_ ? "Error" : "Coverage") + "\n";
+    }
+    return out;
+}
+
 // ------------------------------------------------------------------------------------------ build_and_merge
 MergeSkaArray build_and_merge(const std::vector<InputFastx>& input_files, size_t k, bool rc, const QualOpts& qual,
                               size_t threads, double proportion_reads) {
@@ -476,6 +596,18 @@ std::vector<InputFastx> get_input_list(const std::string& file_list, const std::
         else throw SkaError("Unable to parse line in file_list");
     }
     return out;
+}
+uint16_t kmer_min_cutoff(const std::string& v, const std::vector<InputFastx>& files, size_t k, bool rc, bool verbose) {
+    if (v.empty()) return 5;                                                                    // DEFAULT_MINCOUNT (cli.rs:25)
+    if (v != "auto") return (uint16_t)std::stoul(v);                                            // validated by the CLI parser
+    std::vector<std::string> fq;                                                               // get_2_fastq_path: file 1 of the first two paired samples
+    for (auto& f : files) if (!std::get<2>(f).empty() && fq.size() < 2) fq.push_back(std::get<1>(f));
+    if (fq.size() < 2) return 5;                                                               // "Not enough fastq files to fit mixture model"
+    CoverageHistogram cov(fq[0], fq[1], k, rc, verbose);
+    const size_t cutoff = cov.fit_histogram();
+    const std::string table = cov.plot_hist();
+    fwrite(table.data(), 1, table.size(), stdout);                                             // cov.plot_hist() (io_utils.rs:201)
+    return (uint16_t)cutoff;
 }
 MergeSkaArray load_array(const std::vector<std::string>& input, size_t threads) {
     if (input.size() == 1) return MergeSkaArray::load(input[0]);

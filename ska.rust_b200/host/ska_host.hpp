@@ -97,10 +97,33 @@ class RefSka {
     std::vector<std::string> mapped_names_;
 };
 
+// CoverageHistogram (src/coverage.rs): split k-mer multiplicities of one read set and the two-component Poisson mixture
+// fitted to them.  Counting runs on the device (skagpu_kmer_count_hist); the fit is the reference's: BFGS with a
+// backtracking Armijo line search (argmin's solvers restated), inverse Hessian started at identity, cost tolerance 1e-6,
+// at most 20 iterations (coverage.rs:165-213).
+class CoverageHistogram {
+  public:
+    CoverageHistogram(const std::string& fastq1, const std::string& fastq2, size_t k, bool rc, bool verbose);   // coverage.rs:70-135
+    explicit CoverageHistogram(std::vector<uint32_t> counts) : counts_(std::move(counts)), from_counts_(true) {}  // the unit test's entry
+    size_t fit_histogram();                                                                                      // coverage.rs:151-213
+    std::string plot_hist() const;                                                                               // coverage.rs:220-243
+    double w0() const { return w0_; }
+    double c() const { return c_; }
+
+  private:
+    std::vector<uint32_t> counts_;
+    std::vector<uint64_t> hist_;
+    bool from_counts_ = false, fitted_ = false, verbose_ = false;
+    double w0_ = 0.8, c_ = 20.0;         // INIT_W0, INIT_C (coverage.rs:32-33)
+    size_t cutoff_ = 0;
+};
+
 namespace io_utils {
 std::vector<InputFastx> read_input_fastas(const std::vector<std::string>& seq_files);               // io_utils.rs:31-46
 std::vector<InputFastx> get_input_list(const std::string& file_list, const std::vector<std::string>& seq_files);  // :116-146
 MergeSkaArray load_array(const std::vector<std::string>& input, size_t threads);                    // io_utils.rs:60-93
+// --min-count: a number, "auto" (coverage model on the first files of the first two paired samples), or absent (5)   io_utils.rs:175-212
+uint16_t kmer_min_cutoff(const std::string& min_count_arg, const std::vector<InputFastx>& files, size_t k, bool rc, bool verbose);
 }  // namespace io_utils
 
 namespace generic_modes {

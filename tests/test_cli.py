@@ -288,3 +288,33 @@ def test_cli_u128_build_merge_delete_weed_map(gold_in, gold_ok, tmp_path):
     # k = 33 build + nk (tests/align.rs:116-153)
     run(["build", "-o", "k33", "-k", "33", gold_in("test_1.fa"), gold_in("test_2.fa")], cwd=wd)
     assert matches(run(["nk", "k33.skf"], cwd=wd).stdout, gold_ok("k33.stdout"))
+
+
+# ------------------------------------------------------------------ ska cov
+EXAMPLE_COUNTS = [44633459, 950672, 104410, 44137, 24170, 21232, 21699, 24145, 30696, 39210, 49878, 63683, 77690, 95147, 112416, 130307,
+                  146531, 160932, 175130, 185113, 193149, 197468, 199189, 198235, 192150, 185565, 176362, 165455, 152487, 139495, 127036,
+                  112803, 103080, 90425, 80637, 70960, 62698, 54949, 46744, 41240, 35591, 30025, 25856, 22105, 19405, 16668, 14780, 12620,
+                  11074, 9807, 8517, 7731, 7112, 6846, 6126, 5696, 5233, 4779, 4288, 3873, 3519, 3406, 2994, 2859, 2650, 2394, 2376, 2260,
+                  2233, 2050, 1859, 1863, 1792, 1777, 1773, 1738, 1648]
+
+
+def test_mixture_fit_reproduces_reference_unit_test():
+    """src/coverage.rs:369-397 test_fit_histogram: the 77-bin example histogram gives cutoff 9"""
+    out = run(["fit-selftest"] + [str(c) for c in EXAMPLE_COUNTS]).stdout.decode()
+    assert "cutoff 9 " in out, out
+    assert "cutoff 1 " in run(["fit-selftest"]).stdout.decode()          # empty histogram: converged at once, cutoff 1 (what cov_check relies on)
+
+
+@pytest.mark.gpu
+def test_cli_cov_and_auto_min_count(gold_in, tmp_path):
+    """tests/fastq_input.rs:473-509 cov_check, :512-560 build_auto_check"""
+    wd = str(tmp_path)
+    p = run(["cov", gold_in("test_1_fwd.fastq.gz"), gold_in("test_1_rev.fastq.gz"), "-k", "9", "-v"], cwd=wd)
+    assert p.stdout.startswith(b"Count\tK_mers\tMixture_density\tComponent\n") and b"Estimated cutoff\t" in p.stderr
+    run(["cov", gold_in("test_long_1_fwd.fastq.gz"), gold_in("test_long_1_rev.fastq.gz"), "-k", "33", "-v"], cwd=wd)
+    assert run(["cov", gold_in("test_1.fa"), gold_in("test_2.fa"), "-k", "9", "-v"], cwd=wd, check=False).returncode != 0
+    rfile = tmp_path / "rfile"
+    rfile.write_text("".join(f"test_{i}\t{gold_in(f'test_{i}_fwd.fastq.gz')}\t{gold_in(f'test_{i}_rev.fastq.gz')}\n" for i in (1, 2)))
+    run(["build", "-f", str(rfile), "-o", "auto", "--min-count", "auto", "-k", "9", "-v"], cwd=wd)
+    assert os.path.exists(tmp_path / "auto.skf")
+    assert run(["build", "-f", str(rfile), "-o", "bad", "--min-count", "70000", "-k", "9"], cwd=wd, check=False).returncode == 2

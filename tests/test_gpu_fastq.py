@@ -137,3 +137,25 @@ def test_fastq_samples_shard_by_rows():
     assert [int(x) for p in parts for x in p[0]] == ok
     assert np.array_equal(np.concatenate([p[1] for p in parts]), ov)
     assert np.array_equal(np.concatenate([p[2] for p in parts]), oc)
+
+
+@pytest.mark.parametrize("k,rc", [(9, True), (15, False), (33, True), (63, True)])
+def test_kmer_count_histogram_matches_dictionary(gold_in, k, rc):
+    """the counting half of `ska cov` (coverage.rs:70-135, 156-163): distinct split k-mers by multiplicity, qualities ignored"""
+    import collections
+    stem = "test_long" if k > 31 else "test"
+    s = S.Sample.from_files(gold_in(f"{stem}_1_fwd.fastq.gz"), gold_in(f"{stem}_1_rev.fastq.gz"))
+    # repeat the reads a few times so that multiplicities above 1 dominate, plus a read with N
+    seq = np.concatenate([s.seq] * 3 + [np.frombuffer(b"ACGTNACGT" * 20, dtype=np.uint8)])
+    off = np.concatenate([s.rec_off, s.rec_off[1:] + s.rec_off[-1], s.rec_off[1:] + 2 * s.rec_off[-1], [3 * s.rec_off[-1] + 180]]).astype(np.uint64)
+    big = S.Sample(seq, off, np.full(len(seq), ord("!"), dtype=np.uint8))
+    counts = collections.Counter()
+    for i in range(big.n_rec):
+        w = O.windows(bytes(big.seq[int(big.rec_off[i]):int(big.rec_off[i + 1])]), k, rc=rc)
+        counts.update(w["key"])
+    exp = np.zeros(1000, dtype=np.uint64)
+    for c in counts.values():
+        if c <= 1000:
+            exp[c - 1] += 1
+    got = S.api.kmer_count_hist(big, k, rc)
+    assert np.array_equal(got, exp)
