@@ -166,6 +166,12 @@ void partition_coarse(const uint64_t* rec, uint64_t n_pos, const uint64_t* d_sam
                       const PartPlan& pl, uint64_t** out, uint64_t** d_off1, uint64_t** d_tile_pref, const unsigned long long* k1_hist = nullptr);
 void partition_runs(const uint64_t* src, int n_runs, const uint64_t* h_run_off, uint32_t n_regions, const PartPlan& pl, uint64_t* dst,
                     uint64_t** d_bucket_off);
+// plain MSD grouping of 16-byte records by P1 + P2 bits below `top_bit` (all-ones records dropped); sort128.cu finishes the sort
+void group_wide_records(const uint64_t* src, uint64_t n, int top_bit, int P1, int P2, uint64_t* buf_a, uint64_t* buf_b, uint64_t** out,
+                        uint64_t** d_off);
+// sort128.cu: ascending sort of n 16-byte records as 128-bit integers (all-ones records dropped); key_bits = significant bits of the
+// HIGH word.  buf_a / buf_b hold n records each (rec may be buf_b).  -> pointer to the sorted records, *n_out = records kept
+uint64_t* sort_records_wide(const uint64_t* rec, uint64_t n, int key_bits, uint64_t* buf_a, uint64_t* buf_b, uint64_t* n_out);
 // merge.cu
 // K1 records (n_rec entries; sample s owns entries [sample_off[s], sample_off[s+1]); REC_SENTINEL entries are
 // skipped) -> array; sample ids are sid_base + local index.  `rec` is overwritten (partition scratch).

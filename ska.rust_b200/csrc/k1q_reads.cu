@@ -17,14 +17,12 @@
 //     min_count == 2 :  j >= 2 or FP            min_count >= 3 :  min(j + FP, 65535) == min_count and (j >= 2 or FP)
 // Steps: (1) k1q_kernel<OBS>: per window validity (N, optional strict quality, record ends), middle-base
 // quality, ntHash by a prefix-XOR scan (the hash is a XOR of rotated per-base constants, so
-// fh(s) = rotl(G(s+k)^G(s), s+k-1) for the prefix G of rotr(H[e_j], j); no sequential roll); (2) stable radix sort
-// of (K, position) -- cub::DeviceRadixSort, library scaffolding; (3) runs -> distinct entries (word, t); sort
+// fh(s) = rotl(G(s+k)^G(s), s+k-1) for the prefix G of rotr(H[e_j], j); no sequential roll); (2) sort of the 16-byte
+// records (K, position) -- sort128.cu: two scatter passes by hash prefix + a warp-level bitonic sort per bucket; (3) runs -> distinct entries (word, t); sort
 // by (word, t); one thread walks each bloom word's entries in t order OR-ing fingerprints -> FP; (4) the
 // accepted observations set bits in a per-position accept mask; (5) k1q_kernel<EMIT> recomputes the split
 // k-mer of every accepted position and writes compacted records, which then take the normal
 // partition + merge path (partition.cu, merge.cu).  min_count <= 1 skips (2)-(4): every observation is accepted.
-#include <cub/cub.cuh>
-
 #include "k1_helpers.cuh"
 
 namespace ska {
@@ -52,7 +50,7 @@ template <int MODE>
 __global__ void __launch_bounds__(K1_THREADS)
 k1q_kernel(const uint8_t* __restrict__ seq, const uint8_t* __restrict__ qual, const uint32_t* __restrict__ start_bits,
            uint64_t lo, uint64_t hi, uint64_t tile0, int k, int rc, uint32_t min_qual, int qmode,
-           uint32_t* __restrict__ mask, uint64_t* __restrict__ obs_key, uint32_t* __restrict__ obs_pos,
+           uint32_t* __restrict__ mask, ulonglong2* __restrict__ obs_rec /* x = position, y = mixed hash; all-ones = no observation */,
            unsigned long long* __restrict__ n_obs, const uint64_t* __restrict__ tile_off, uint64_t* __restrict__ rec_c) {
     __shared__ __align__(128) uint8_t s_ascii[K1_BYTES];
     __shared__ __align__(128) uint8_t s_qual[K1_BYTES];
@@ -187,8 +185,7 @@ k1q_kernel(const uint8_t* __restrict__ seq, const uint8_t* __restrict__ qual, co
                 pos = (uint32_t)(p - tile0 * K1_T);
                 mine++;
             }
-            obs_key[p - lo] = key;
-            obs_pos[p - lo] = pos;
+            obs_rec[p - lo] = key == ~0ULL ? make_ulonglong2(~0ULL, ~0ULL) : make_ulonglong2((unsigned long long)pos, key);
         }
         if (mine) atomicAdd(&s_nobs, mine);
         __syncthreads();
@@ -263,54 +260,75 @@ __global__ void tile_popc_kernel(const uint32_t* __restrict__ mask, uint32_t n_t
     if (lane == 0) cnt[tile] = c;
 }
 
-// runs of equal K in the sorted observations -> one distinct entry each: key (word << 32 | first position),
-// value (run start << 32 | min(run length, 2^32 - 1)).  Stable sort => the first element of a run is the earliest.
-__global__ void q_runs_kernel(const uint64_t* __restrict__ K, const uint32_t* __restrict__ pos, uint64_t n_obs,
-                              uint64_t* __restrict__ dkey, uint64_t* __restrict__ dval, unsigned long long* __restrict__ n_distinct) {
+// runs of equal K in the sorted observations -> one distinct entry each, as a record of the second sort:
+//   y (key)   = bloom word << 32 | first position        (the sort by (K, position) puts a run's earliest observation first)
+//   x (value) = run start << 32 | min(run length, 2^32 - 1)
+// The run's end is found by binary search (a k-mer seen millions of times must not be walked by one thread).
+__global__ void q_runs_kernel(const ulonglong2* __restrict__ obs, uint64_t n_obs, ulonglong2* __restrict__ drec,
+                              unsigned long long* __restrict__ n_distinct) {
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_obs) return;
-    const uint64_t key = K[i];
-    if (i > 0 && K[i - 1] == key) return;
-    uint64_t c = 1;
-    while (i + c < n_obs && K[i + c] == key) c++;
+    const uint64_t key = obs[i].y;
+    if (i > 0 && obs[i - 1].y == key) return;
+    uint64_t lo = i + 1, hi = n_obs;                                  // first index with K > key
+    while (lo < hi) { const uint64_t m = (lo + hi) >> 1; if (obs[m].y <= key) lo = m + 1; else hi = m; }
+    const uint64_t c = lo - i;
     const unsigned long long d = atomicAdd(n_distinct, 1ULL);
-    dkey[d] = ((uint64_t)bloom_word(key) << 32) | pos[i];
-    dval[d] = (i << 32) | (c > 0xFFFFFFFFULL ? 0xFFFFFFFFULL : c);
+    drec[d] = make_ulonglong2((i << 32) | (c > 0xFFFFFFFFULL ? 0xFFFFFFFFULL : c), ((uint64_t)bloom_word(key) << 32) | obs[i].x);
 }
 
 // entries sorted by (word, first position): the thread at the head of a word's segment replays that word
-// of the bloom filter (bloom_filter.rs:77-86) in first-occurrence order
-__global__ void q_bloom_kernel(const uint64_t* __restrict__ dkey, const uint64_t* __restrict__ dval, const uint64_t* __restrict__ K,
-                               uint64_t n_distinct, uint8_t* __restrict__ fp_flag) {
+// of the bloom filter (bloom_filter.rs:77-86) in first-occurrence order (a word holds the ~30-40 hashes that map to it)
+__global__ void q_bloom_kernel(const ulonglong2* __restrict__ drec, const ulonglong2* __restrict__ obs, uint64_t n_distinct,
+                               uint8_t* __restrict__ fp_flag) {
     const uint64_t d = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (d >= n_distinct) return;
-    const uint32_t word = (uint32_t)(dkey[d] >> 32);
-    if (d > 0 && (uint32_t)(dkey[d - 1] >> 32) == word) return;
+    const uint32_t word = (uint32_t)(drec[d].y >> 32);
+    if (d > 0 && (uint32_t)(drec[d - 1].y >> 32) == word) return;
     uint64_t state = 0;
-    for (uint64_t e = d; e < n_distinct && (uint32_t)(dkey[e] >> 32) == word; e++) {
-        const uint64_t f = fingerprint(cheap_unmix(K[dval[e] >> 32]));
+    for (uint64_t e = d; e < n_distinct && (uint32_t)(drec[e].y >> 32) == word; e++) {
+        const uint64_t f = fingerprint(cheap_unmix(obs[drec[e].x >> 32].y));
         const bool seen = (state & f) == f;
         if (!seen) state |= f;
         fp_flag[e] = seen;
     }
 }
 
-// which observations of every distinct k-mer reach the dictionary (bloom_filter.rs:116-148)
-__global__ void q_accept_kernel(const uint64_t* __restrict__ dval, const uint8_t* __restrict__ fp_flag, const uint32_t* __restrict__ pos,
-                                uint64_t n_distinct, uint32_t min_count, uint32_t* __restrict__ mask) {
-    const uint64_t e = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (e >= n_distinct) return;
-    const uint64_t i0 = dval[e] >> 32, c = dval[e] & 0xFFFFFFFFULL;
-    const uint64_t fp = fp_flag[e];
-    uint64_t j_lo, j_hi;                                              // accepted 1-based observation numbers [j_lo, j_hi]
+// which observations of every distinct k-mer reach the dictionary (bloom_filter.rs:116-148); entries that accept more than
+// Q_LONG observations (min_count == 2 or 65535 on a heavily repeated k-mer) are left to q_accept_long_kernel
+constexpr uint64_t Q_LONG = 64;
+__device__ __forceinline__ void accept_range(uint64_t c, uint64_t fp, uint32_t min_count, uint64_t& j_lo, uint64_t& j_hi) {
     if (min_count == 2) { j_lo = fp ? 1 : 2; j_hi = c; }
     else {
         j_lo = j_hi = (uint64_t)min_count - fp;                       // count after observation j is j + fp
         if (min_count == 65535) j_hi = c;                             // saturating_add keeps the count at u16::MAX
         if (j_lo < 2 - fp) j_lo = 2 - fp;
     }
-    for (uint64_t j = j_lo; j <= j_hi && j <= c; j++) {
-        const uint32_t p = pos[i0 + j - 1];
+    if (j_hi > c) j_hi = c;
+}
+__global__ void q_accept_kernel(const ulonglong2* __restrict__ drec, const uint8_t* __restrict__ fp_flag, const ulonglong2* __restrict__ obs,
+                                uint64_t n_distinct, uint32_t min_count, uint32_t* __restrict__ mask, uint32_t* __restrict__ long_list,
+                                unsigned long long* __restrict__ n_long) {
+    const uint64_t e = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n_distinct) return;
+    const uint64_t i0 = drec[e].x >> 32, c = drec[e].x & 0xFFFFFFFFULL;
+    uint64_t j_lo, j_hi;                                              // accepted 1-based observation numbers [j_lo, j_hi]
+    accept_range(c, fp_flag[e], min_count, j_lo, j_hi);
+    if (j_hi >= j_lo && j_hi - j_lo >= Q_LONG) { long_list[atomicAdd(n_long, 1ULL)] = (uint32_t)e; return; }
+    for (uint64_t j = j_lo; j <= j_hi; j++) {
+        const uint32_t p = (uint32_t)obs[i0 + j - 1].x;
+        atomicOr(&mask[p >> 5], 1u << (p & 31));
+    }
+}
+__global__ void __launch_bounds__(256)
+q_accept_long_kernel(const ulonglong2* __restrict__ drec, const uint8_t* __restrict__ fp_flag, const ulonglong2* __restrict__ obs,
+                     const uint32_t* __restrict__ long_list, uint32_t min_count, uint32_t* __restrict__ mask) {
+    const uint64_t e = long_list[blockIdx.x];
+    const uint64_t i0 = drec[e].x >> 32, c = drec[e].x & 0xFFFFFFFFULL;
+    uint64_t j_lo, j_hi;
+    accept_range(c, fp_flag[e], min_count, j_lo, j_hi);
+    for (uint64_t j = j_lo + threadIdx.x; j <= j_hi; j += 256) {
+        const uint32_t p = (uint32_t)obs[i0 + j - 1].x;
         atomicOr(&mask[p >> 5], 1u << (p & 31));
     }
 }
@@ -344,46 +362,44 @@ void build_array_from_reads(const SeqBatch& b, uint32_t k, bool rc, uint16_t min
         SKA_CUDA(cudaMemsetAsync(masks[s], 0, n_words * 4, c.stream));
         if (min_count <= 1) {                                         // bloom_filter.rs:121: no filtering
             SKA_LAUNCH(k1q_kernel<RQ_MASK>, (unsigned)n_tiles[s], K1_THREADS, 0, b.seq.p, b.qual.p, b.start_bits.p, lo, hi, tile_lo[s],
-                       (int)k, rc ? 1 : 0, (uint32_t)min_qual, qual_filter, masks[s], (uint64_t*)nullptr, (uint32_t*)nullptr,
+                       (int)k, rc ? 1 : 0, (uint32_t)min_qual, qual_filter, masks[s], (ulonglong2*)nullptr,
                        (unsigned long long*)nullptr, (const uint64_t*)nullptr, (uint64_t*)nullptr);
         } else {
             const ArenaMark mark = arena_mark();
             const uint64_t n_s = hi - lo;
-            uint64_t* obs_key = arena().take_n<uint64_t>(n_s); uint64_t* obs_key2 = arena().take_n<uint64_t>(n_s);
-            uint32_t* obs_pos = arena().take_n<uint32_t>(n_s); uint32_t* obs_pos2 = arena().take_n<uint32_t>(n_s);
+            if (n_s >= 0xFFFFFFFFull) throw Error("a read set of 2^32 bases or more per sample is beyond the 32-bit positions of the count filter");
+            uint64_t* obs_rec = arena().take_n<uint64_t>(2 * n_s);            // 16-byte records (position, mixed hash)
+            uint64_t* obs_tmp = arena().take_n<uint64_t>(2 * n_s);
             SKA_CUDA(cudaMemsetAsync(d_counter, 0, 16, c.stream));
             SKA_LAUNCH(k1q_kernel<RQ_OBS>, (unsigned)n_tiles[s], K1_THREADS, obs_smem, b.seq.p, b.qual.p, b.start_bits.p, lo, hi, tile_lo[s],
-                       (int)k, rc ? 1 : 0, (uint32_t)min_qual, qual_filter, masks[s], obs_key, obs_pos, d_counter,
+                       (int)k, rc ? 1 : 0, (uint32_t)min_qual, qual_filter, masks[s], reinterpret_cast<ulonglong2*>(obs_rec), d_counter,
                        (const uint64_t*)nullptr, (uint64_t*)nullptr);
-            // stable sort by K: non-observations carry K = ~0 and end up behind the n_obs real ones
-            cub::DoubleBuffer<uint64_t> dk(obs_key, obs_key2);
-            cub::DoubleBuffer<uint32_t> dv(obs_pos, obs_pos2);
-            size_t tmp_bytes = 0;
-            SKA_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, dk, dv, (int64_t)n_s, 0, 64, c.stream));
-            void* tmp = arena().take(tmp_bytes);
-            SKA_CUDA(cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, dk, dv, (int64_t)n_s, 0, 64, c.stream));
-            c.launches += 9;
-            unsigned long long h_cnt[2];
-            SKA_CUDA(cudaMemcpyAsync(h_cnt, d_counter, 16, cudaMemcpyDeviceToHost, c.stream));
-            SKA_CUDA(cudaStreamSynchronize(c.stream));
-            const uint64_t n_obs = h_cnt[0];
+            // sort by (K, position): groups equal hashes, orders by bloom word (monotone in K) and by stream order inside a hash
+            uint64_t n_obs = 0;
+            const ulonglong2* obs = reinterpret_cast<const ulonglong2*>(sort_records_wide(obs_rec, n_s, 64, obs_tmp, obs_rec, &n_obs));
+            uint64_t* free_buf = reinterpret_cast<const uint64_t*>(obs) == obs_rec ? obs_tmp : obs_rec;   // the other buffer is scratch now
             if (n_obs) {
-                const uint64_t* K = dk.Current(); const uint32_t* P = dv.Current();
-                uint64_t* dkey = dk.Alternate(); uint64_t* dval = arena().take_n<uint64_t>(n_obs);   // the alternate key buffer is free now
-                SKA_LAUNCH(q_runs_kernel, (unsigned)((n_obs + 255) / 256), 256, 0, K, P, n_obs, dkey, dval, d_counter + 1);
+                ulonglong2* drec = reinterpret_cast<ulonglong2*>(free_buf);     // distinct entries: at most n_obs <= n_s records
+                SKA_LAUNCH(q_runs_kernel, (unsigned)((n_obs + 255) / 256), 256, 0, obs, n_obs, drec, d_counter + 1);
+                unsigned long long h_cnt[2];
                 SKA_CUDA(cudaMemcpyAsync(h_cnt, d_counter, 16, cudaMemcpyDeviceToHost, c.stream));
                 SKA_CUDA(cudaStreamSynchronize(c.stream));
                 const uint64_t n_d = h_cnt[1];
-                uint64_t* dkey2 = arena().take_n<uint64_t>(n_d); uint64_t* dval2 = arena().take_n<uint64_t>(n_d);
-                cub::DoubleBuffer<uint64_t> ek(dkey, dkey2), ev(dval, dval2);
-                size_t tmp2 = 0;
-                SKA_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp2, ek, ev, (int64_t)n_d, 0, 54, c.stream));
-                void* t2 = arena().take(tmp2);
-                SKA_CUDA(cub::DeviceRadixSort::SortPairs(t2, tmp2, ek, ev, (int64_t)n_d, 0, 54, c.stream));
-                c.launches += 8;
+                uint64_t* dtmp = arena().take_n<uint64_t>(2 * n_d);
+                uint64_t n_d2 = 0;
+                const ulonglong2* dsorted = reinterpret_cast<const ulonglong2*>(
+                    sort_records_wide(reinterpret_cast<const uint64_t*>(drec), n_d, 54, dtmp, reinterpret_cast<uint64_t*>(drec), &n_d2));
+                if (n_d2 != n_d) throw Error("internal: distinct entries lost in the sort");
                 uint8_t* fp_flag = arena().take_n<uint8_t>(n_d);
-                SKA_LAUNCH(q_bloom_kernel, (unsigned)((n_d + 255) / 256), 256, 0, ek.Current(), ev.Current(), K, n_d, fp_flag);
-                SKA_LAUNCH(q_accept_kernel, (unsigned)((n_d + 255) / 256), 256, 0, ev.Current(), fp_flag, P, n_d, (uint32_t)min_count, masks[s]);
+                uint32_t* long_list = arena().take_n<uint32_t>(n_d);
+                unsigned long long* n_long = arena().take_n<unsigned long long>(1);
+                SKA_CUDA(cudaMemsetAsync(n_long, 0, 8, c.stream));
+                SKA_LAUNCH(q_bloom_kernel, (unsigned)((n_d + 255) / 256), 256, 0, dsorted, obs, n_d, fp_flag);
+                SKA_LAUNCH(q_accept_kernel, (unsigned)((n_d + 255) / 256), 256, 0, dsorted, fp_flag, obs, n_d, (uint32_t)min_count, masks[s], long_list, n_long);
+                unsigned long long h_long = 0;
+                SKA_CUDA(cudaMemcpyAsync(&h_long, n_long, 8, cudaMemcpyDeviceToHost, c.stream));
+                SKA_CUDA(cudaStreamSynchronize(c.stream));
+                if (h_long) SKA_LAUNCH(q_accept_long_kernel, (unsigned)h_long, 256, 0, dsorted, fp_flag, obs, long_list, (uint32_t)min_count, masks[s]);
             }
             SKA_CUDA(cudaStreamSynchronize(c.stream));
             arena_rewind(mark);
@@ -409,8 +425,8 @@ void build_array_from_reads(const SeqBatch& b, uint32_t k, bool rc, uint16_t min
     for (uint64_t s = 0; s < N; s++) {
         if (!n_tiles[s]) continue;
         SKA_LAUNCH(k1q_kernel<RQ_EMIT>, (unsigned)n_tiles[s], K1_THREADS, 0, b.seq.p, b.qual.p, b.start_bits.p, b.h_sample_off[s],
-                   b.h_sample_off[s + 1], tile_lo[s], (int)k, rc ? 1 : 0, (uint32_t)min_qual, qual_filter, masks[s], (uint64_t*)nullptr,
-                   (uint32_t*)nullptr, (unsigned long long*)nullptr, (const uint64_t*)tile_offs[s], rec_c + coff[s] * rw);
+                   b.h_sample_off[s + 1], tile_lo[s], (int)k, rc ? 1 : 0, (uint32_t)min_qual, qual_filter, masks[s], (ulonglong2*)nullptr,
+                   (unsigned long long*)nullptr, (const uint64_t*)tile_offs[s], rec_c + coff[s] * rw);
     }
     timer().end();
     uint64_t* d_coff = arena().take_n<uint64_t>(N + 1);

@@ -242,6 +242,7 @@ __device__ __forceinline__ u128 ld_rec128(const uint64_t* __restrict__ p, uint64
 }
 __device__ __forceinline__ uint32_t digit128(u128 r, int pass, int shift, uint32_t mask) {
     if (pass == 1) return r == ~(u128)0 ? PT_NONE : (uint32_t)(r >> shift);
+    if (pass == 3) return r == ~(u128)0 ? PT_NONE : (uint32_t)(r >> shift) & mask;         // first pass of a plain grouping (no repacking)
     return mask ? (uint32_t)(r >> shift) & mask : 0u;
 }
 __global__ void __launch_bounds__(PT_THREADS)
@@ -316,7 +317,7 @@ part_scatter_wide_kernel(const uint64_t* __restrict__ src, uint64_t n_total, Seg
     for (int j = 0; j < SCW_I; j++) {
         const uint32_t li = j * SCW_T + threadIdx.x;
         const u128 r = rr[j];
-        const uint32_t d = li < cnt ? digit128(r, PASS, fn.shift, fn.mask) : PT_NONE;
+        const uint32_t d = li < cnt ? digit128(r, fn.pass, fn.shift, fn.mask) : PT_NONE;
         if (PASS == 1 && d != PT_NONE) {
             uint32_t s = s_sid[0];
             if (s_sid[0] != s_sid[1]) {
@@ -582,6 +583,52 @@ void partition_runs(const uint64_t* src, int n_runs, const uint64_t* h_run_off, 
     const Segs sg{d_pref, d_beg, d_end, d_region, std::max<uint32_t>(ns, 1)};
     partition_fine(src, sg, tiles, nr, pl, dst, d_bucket_off);
     SKA_CUDA(cudaStreamSynchronize(c.stream));              // the host vectors above must outlive their copies
+}
+
+// ---------------------------------------------------------------------------------------------- plain grouping of 16-byte records
+// Groups n records (two words each, compared as 128-bit integers) by the P1 + P2 bits below `top_bit` (everything above is
+// equal in all of them); all-ones records are dropped.  buf_a / buf_b: n records of room each (src may be buf_b).  -> *out (one of the two
+// buffers), *d_off [2^(P1+P2) + 1] bucket offsets on the device.  The first half of a sort: sort128.cu finishes every bucket.
+void group_wide_records(const uint64_t* src, uint64_t n, int top_bit, int P1, int P2, uint64_t* buf_a, uint64_t* buf_b, uint64_t** out,
+                        uint64_t** d_off) {
+    Context& c = ctx();
+    if (P1 < 0 || P2 < 0 || P1 > PT_MAX_BITS || P2 > PT_MAX_BITS || top_bit - P1 - P2 < 0) throw Error("internal: bad grouping plan");
+    set_scatter_attrs();
+    const uint32_t D1 = 1u << P1, D2 = 1u << P2;
+    unsigned long long* hist1 = arena().take_n<unsigned long long>(D1);
+    unsigned long long* cur1 = arena().take_n<unsigned long long>(D1);
+    uint64_t* off1 = arena().take_n<uint64_t>(D1 + 1);
+    uint64_t* tile_pref = arena().take_n<uint64_t>(D1 + 1);
+    SKA_CUDA(cudaMemsetAsync(hist1, 0, D1 * 8, c.stream));
+    const uint64_t n_tiles1 = (n + PT_TILE - 1) / PT_TILE;
+    const DigitFn f1{3, top_bit - P1, D1 - 1};
+    const Segs none{nullptr, nullptr, nullptr, nullptr, 1u};
+    const PackWide pw{0, 0, 0};
+    const unsigned hist_grid = (unsigned)std::min<uint64_t>(std::max<uint64_t>(n_tiles1, 1), (uint64_t)c.sm_count * 4);
+    if (n) SKA_LAUNCH(part_hist_wide_kernel, hist_grid, PT_THREADS, D1 * 4, src, n, n_tiles1, none, f1, P1, hist1);
+    SKA_LAUNCH(part_scan_kernel, 1, 1024, 0, (const unsigned long long*)hist1, D1, off1, cur1, tile_pref, 1);
+    if (n) SKA_LAUNCH((part_scatter_wide_kernel<2>), (unsigned)n_tiles1, SCW_T, scatter_wide_smem(P1), src, n, none, f1, P1, pw,
+                      (const uint64_t*)nullptr, 0u, cur1, buf_a);
+    if (P2 == 0) { *out = buf_a; *d_off = off1; return; }
+    uint64_t n_tiles2 = 0;
+    SKA_CUDA(cudaMemcpyAsync(&n_tiles2, tile_pref + D1, 8, cudaMemcpyDeviceToHost, c.stream));
+    SKA_CUDA(cudaStreamSynchronize(c.stream));
+    const size_t NB = (size_t)D1 * D2;
+    unsigned long long* hist2 = arena().take_n<unsigned long long>(NB);
+    unsigned long long* cur2 = arena().take_n<unsigned long long>(NB);
+    uint64_t* bucket_off = arena().take_n<uint64_t>(NB + 1);
+    SKA_CUDA(cudaMemsetAsync(hist2, 0, NB * 8, c.stream));
+    const DigitFn f2{2, top_bit - P1 - P2, D2 - 1};
+    const Segs sg{tile_pref, off1, off1 + 1, nullptr, D1};
+    if (n_tiles2) {
+        const unsigned g2 = (unsigned)std::min<uint64_t>(n_tiles2, (uint64_t)c.sm_count * 4);
+        SKA_LAUNCH(part_hist_wide_kernel, g2, PT_THREADS, D2 * 4, buf_a, (uint64_t)0, n_tiles2, sg, f2, P2, hist2);
+    }
+    SKA_LAUNCH(part_scan_kernel, 1, 1024, 0, (const unsigned long long*)hist2, (uint32_t)NB, bucket_off, cur2, (uint64_t*)nullptr, 1);
+    if (n_tiles2)
+        SKA_LAUNCH((part_scatter_wide_kernel<2>), (unsigned)n_tiles2, SCW_T, scatter_wide_smem(P2), buf_a, (uint64_t)0, sg, f2, P2, pw,
+                   (const uint64_t*)nullptr, 0u, cur2, buf_b);
+    *out = buf_b; *d_off = bucket_off;
 }
 
 }  // namespace ska

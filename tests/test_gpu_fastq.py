@@ -103,6 +103,40 @@ def test_fastq_bloom_false_positives_saturated(min_count):
     assert g.dims()["n_rows"] > 300_000
 
 
+@pytest.mark.parametrize("min_count", [2, 5, 65535])
+def test_fastq_heavy_repeats(min_count):
+    """homopolymer and tandem-repeat reads: one hash observed tens of thousands of times (the sort's oversized-bucket
+    path, the binary-searched run length, and the long accept lists of min_count == 2 / the saturated u16 count)"""
+    rng = np.random.default_rng(0x5CA2000A)
+    L, n_pairs = 150, 1000
+    genome = rng.integers(0, 4, 5000)
+    def read(i):
+        if i % 3 == 0:
+            return np.full(L, ord("A"), dtype=np.uint8)
+        if i % 3 == 1:
+            return np.frombuffer((b"ACGGT" * 40)[i % 5:i % 5 + L], dtype=np.uint8)
+        a = int(rng.integers(0, 5000 - L))
+        return np.frombuffer(b"ACGT", dtype=np.uint8)[genome[a:a + L]]
+    files = []
+    for f in range(2):
+        seqs = [read(i + f) for i in range(n_pairs)]
+        quals = [rng.integers(25, 41, L).astype(np.uint8) + 33 for _ in range(n_pairs)]
+        files.append((seqs, quals))
+    seq = np.concatenate(files[0][0] + files[1][0])
+    qual = np.concatenate(files[0][1] + files[1][1])
+    off = np.arange(0, 2 * n_pairs + 1, dtype=np.int64) * L
+    gs = S.Sample(seq, off, qual, n_rec_file1=n_pairs)
+    od = O.SampleData([(s.tobytes(), q.tobytes()) for s, q in zip(*files[0])], [(s.tobytes(), q.tobytes()) for s, q in zip(*files[1])],
+                      is_reads=True)
+    q = S.QualOpts(min_count=min_count, min_qual=20, qual_filter="strict")
+    for k in (31, 41):
+        g = S.build_from_samples([gs], ["r"], k, True, q)
+        o = O.OracleArray.build([od], ["r"], k=k, rc=True, min_count=min_count, min_qual=20, qual_filter="strict")
+        same(g, o)
+        if min_count < 65535:
+            assert g.dims()["n_rows"] > 0
+
+
 def test_fastq_samples_shard_by_rows():
     """FASTQ samples through the multi-GPU "rows" path (every 'rank' builds its own reads with the count filter, the
     owners join the partial rows), emulated on one GPU with the exchange replaced by copies: equals the oracle's array"""
