@@ -10,7 +10,7 @@ FLAGS="-gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo -Xcompil
 build() {   # name, file, defines
     $NVCC $FLAGS $3 -c $2.cu -o ../variants/$2_$1.o
     objs=""
-    for f in api k1_extract k1q_reads partition merge rowmerge filter distance verify; do
+    for f in api k1_extract k1q_reads partition merge rowmerge filter distance verify setops merge128 cov sort128; do
         if [ "$f" == "$2" ]; then objs="$objs ../variants/$2_$1.o"; else objs="$objs $f.o"; fi
     done
     $NVCC -gencode arch=compute_100a,code=sm_100a -shared -o ../variants/libskagpu_$1.so $objs

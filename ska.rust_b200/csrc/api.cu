@@ -1062,13 +1062,19 @@ void* skagpu_host_alloc(size_t bytes) {
 void skagpu_host_free(void* p) { if (p) cudaFreeHost(p); }
 
 int skagpu_last_timings(const char** names, float* ms, uint64_t* launches, int max_stages) {
-    int n = 0;
+    int n = 0;                                      // stages of the same name (one per sample of a read set) are summed
     for (auto& s : timer().stages) {
-        if (n >= max_stages) break;
         float t = 0;
         if (cudaEventSynchronize(s.end) != cudaSuccess || cudaEventElapsedTime(&t, s.beg, s.end) != cudaSuccess) t = -1.f;
-        names[n] = s.name; ms[n] = t; if (launches) launches[n] = s.launches;
-        n++;
+        int j = 0;
+        while (j < n && strcmp(names[j], s.name) != 0) j++;
+        if (j == n) {
+            if (n >= max_stages) continue;
+            names[n] = s.name; ms[n] = 0.f; if (launches) launches[n] = 0;
+            n++;
+        }
+        if (t < 0 || ms[j] < 0) ms[j] = -1.f; else ms[j] += t;
+        if (launches) launches[j] += s.launches;
     }
     return n;
 }

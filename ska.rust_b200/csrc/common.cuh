@@ -172,6 +172,8 @@ void group_wide_records(const uint64_t* src, uint64_t n, int top_bit, int P1, in
 // sort128.cu: ascending sort of n 16-byte records as 128-bit integers (all-ones records dropped); key_bits = significant bits of the
 // HIGH word.  buf_a / buf_b hold n records each (rec may be buf_b).  -> pointer to the sorted records, *n_out = records kept
 uint64_t* sort_records_wide(const uint64_t* rec, uint64_t n, int key_bits, uint64_t* buf_a, uint64_t* buf_b, uint64_t* n_out);
+// dedup.cu: one sample's K1 records -> its distinct records (see there)
+uint64_t* unique_sample_records(uint64_t* rec, uint64_t n, uint32_t k, int prefix_bits, uint64_t* n_out);
 // merge.cu
 // K1 records (n_rec entries; sample s owns entries [sample_off[s], sample_off[s+1]); REC_SENTINEL entries are
 // skipped) -> array; sample ids are sid_base + local index.  `rec` is overwritten (partition scratch).

@@ -341,28 +341,36 @@ static void arena_rewind(const ArenaMark& m) {
     for (size_t i = 0; i < sl.size(); i++) sl[i].used = i < m.used.size() ? m.used[i] : 0;
 }
 
+// prefix bits that put ~512 of a sample's accepted windows into one bucket of unique_sample_records
+static int unique_prefix_bits(uint64_t n, uint32_t k) {
+    int P = 0;
+    while ((n >> P) > 512 && P < 2 * ((int)k - 1) && P < 22) P++;
+    return P;
+}
+
 void build_array_from_reads(const SeqBatch& b, uint32_t k, bool rc, uint16_t min_count, uint8_t min_qual, int qual_filter, Array& out) {
     Context& c = ctx();
     const uint64_t N = b.n_samples;
+    const int rw = k > 31 ? 2 : 1;                                    // words per record
     const size_t obs_smem = 2 * (size_t)(K1_BYTES + 1) * 8;
     SKA_CUDA(cudaFuncSetAttribute(k1q_kernel<RQ_OBS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)obs_smem));
-    std::vector<uint32_t*> masks(N);
-    std::vector<uint64_t*> tile_offs(N);
-    std::vector<uint64_t> n_tiles(N), tile_lo(N), accepted(N);
+    std::vector<DevBuf<uint64_t>> kept(N);                            // every sample's distinct records, outside the arena
+    std::vector<uint64_t> coff(N + 1, 0);
     unsigned long long* d_counter = arena().take_n<unsigned long long>(2);
 
-    timer().begin("reads_filter");
+    // one sample at a time: the filter's working set is 32 B per base, the batch may hold hundreds of GB of reads
     for (uint64_t s = 0; s < N; s++) {
         const uint64_t lo = b.h_sample_off[s], hi = b.h_sample_off[s + 1];
-        if (hi == lo) { n_tiles[s] = 0; accepted[s] = 0; continue; }
-        tile_lo[s] = lo / K1_T;
-        n_tiles[s] = (hi - 1) / K1_T - tile_lo[s] + 1;
-        const size_t n_words = n_tiles[s] * (K1_T / 32);
-        masks[s] = arena().take_n<uint32_t>(n_words);
-        SKA_CUDA(cudaMemsetAsync(masks[s], 0, n_words * 4, c.stream));
+        if (hi == lo) throw Error("sample " + std::to_string(s) + " has no valid sequence");   // ska_dict.rs:374-376
+        const ArenaMark sample_mark = arena_mark();
+        const uint64_t tile_lo = lo / K1_T, n_tiles = (hi - 1) / K1_T - tile_lo + 1;
+        const size_t n_words = n_tiles * (K1_T / 32);
+        uint32_t* mask = arena().take_n<uint32_t>(n_words);
+        timer().begin("reads_filter");
+        SKA_CUDA(cudaMemsetAsync(mask, 0, n_words * 4, c.stream));
         if (min_count <= 1) {                                         // bloom_filter.rs:121: no filtering
-            SKA_LAUNCH(k1q_kernel<RQ_MASK>, (unsigned)n_tiles[s], K1_THREADS, 0, b.seq.p, b.qual.p, b.start_bits.p, lo, hi, tile_lo[s],
-                       (int)k, rc ? 1 : 0, (uint32_t)min_qual, qual_filter, masks[s], (ulonglong2*)nullptr,
+            SKA_LAUNCH(k1q_kernel<RQ_MASK>, (unsigned)n_tiles, K1_THREADS, 0, b.seq.p, b.qual.p, b.start_bits.p, lo, hi, tile_lo,
+                       (int)k, rc ? 1 : 0, (uint32_t)min_qual, qual_filter, mask, (ulonglong2*)nullptr,
                        (unsigned long long*)nullptr, (const uint64_t*)nullptr, (uint64_t*)nullptr);
         } else {
             const ArenaMark mark = arena_mark();
@@ -371,8 +379,8 @@ void build_array_from_reads(const SeqBatch& b, uint32_t k, bool rc, uint16_t min
             uint64_t* obs_rec = arena().take_n<uint64_t>(2 * n_s);            // 16-byte records (position, mixed hash)
             uint64_t* obs_tmp = arena().take_n<uint64_t>(2 * n_s);
             SKA_CUDA(cudaMemsetAsync(d_counter, 0, 16, c.stream));
-            SKA_LAUNCH(k1q_kernel<RQ_OBS>, (unsigned)n_tiles[s], K1_THREADS, obs_smem, b.seq.p, b.qual.p, b.start_bits.p, lo, hi, tile_lo[s],
-                       (int)k, rc ? 1 : 0, (uint32_t)min_qual, qual_filter, masks[s], reinterpret_cast<ulonglong2*>(obs_rec), d_counter,
+            SKA_LAUNCH(k1q_kernel<RQ_OBS>, (unsigned)n_tiles, K1_THREADS, obs_smem, b.seq.p, b.qual.p, b.start_bits.p, lo, hi, tile_lo,
+                       (int)k, rc ? 1 : 0, (uint32_t)min_qual, qual_filter, mask, reinterpret_cast<ulonglong2*>(obs_rec), d_counter,
                        (const uint64_t*)nullptr, (uint64_t*)nullptr);
             // sort by (K, position): groups equal hashes, orders by bloom word (monotone in K) and by stream order inside a hash
             uint64_t n_obs = 0;
@@ -395,43 +403,63 @@ void build_array_from_reads(const SeqBatch& b, uint32_t k, bool rc, uint16_t min
                 unsigned long long* n_long = arena().take_n<unsigned long long>(1);
                 SKA_CUDA(cudaMemsetAsync(n_long, 0, 8, c.stream));
                 SKA_LAUNCH(q_bloom_kernel, (unsigned)((n_d + 255) / 256), 256, 0, dsorted, obs, n_d, fp_flag);
-                SKA_LAUNCH(q_accept_kernel, (unsigned)((n_d + 255) / 256), 256, 0, dsorted, fp_flag, obs, n_d, (uint32_t)min_count, masks[s], long_list, n_long);
+                SKA_LAUNCH(q_accept_kernel, (unsigned)((n_d + 255) / 256), 256, 0, dsorted, fp_flag, obs, n_d, (uint32_t)min_count, mask, long_list, n_long);
                 unsigned long long h_long = 0;
                 SKA_CUDA(cudaMemcpyAsync(&h_long, n_long, 8, cudaMemcpyDeviceToHost, c.stream));
                 SKA_CUDA(cudaStreamSynchronize(c.stream));
-                if (h_long) SKA_LAUNCH(q_accept_long_kernel, (unsigned)h_long, 256, 0, dsorted, fp_flag, obs, long_list, (uint32_t)min_count, masks[s]);
+                if (h_long) SKA_LAUNCH(q_accept_long_kernel, (unsigned)h_long, 256, 0, dsorted, fp_flag, obs, long_list, (uint32_t)min_count, mask);
             }
             SKA_CUDA(cudaStreamSynchronize(c.stream));
             arena_rewind(mark);
         }
         // compaction offsets of the accepted windows
-        uint32_t* cnt = arena().take_n<uint32_t>(n_tiles[s]);
-        tile_offs[s] = arena().take_n<uint64_t>(n_tiles[s] + 1);
+        uint32_t* cnt = arena().take_n<uint32_t>(n_tiles);
+        uint64_t* tile_off = arena().take_n<uint64_t>(n_tiles + 1);
         uint32_t* scratch = arena().take_n<uint32_t>(1);
-        SKA_LAUNCH(tile_popc_kernel, (unsigned)((n_tiles[s] + 7) / 8), 256, 0, masks[s], (uint32_t)n_tiles[s], cnt);
-        launch_scan_counts(cnt, (uint32_t)n_tiles[s], tile_offs[s], scratch);
-        SKA_CUDA(cudaMemcpyAsync(&accepted[s], tile_offs[s] + n_tiles[s], 8, cudaMemcpyDeviceToHost, c.stream));
+        uint64_t accepted = 0;
+        SKA_LAUNCH(tile_popc_kernel, (unsigned)((n_tiles + 7) / 8), 256, 0, mask, (uint32_t)n_tiles, cnt);
+        launch_scan_counts(cnt, (uint32_t)n_tiles, tile_off, scratch);
+        SKA_CUDA(cudaMemcpyAsync(&accepted, tile_off + n_tiles, 8, cudaMemcpyDeviceToHost, c.stream));
+        timer().end();
         SKA_CUDA(cudaStreamSynchronize(c.stream));
-        if (accepted[s] == 0) throw Error("sample " + std::to_string(s) + " has no valid sequence");   // ska_dict.rs:374-376
-    }
-    timer().end();
+        if (accepted == 0) throw Error("sample " + std::to_string(s) + " has no valid sequence");     // ska_dict.rs:374-376
 
-    // compacted K1 records of the accepted windows, sample after sample
-    timer().begin("k1_extract");
-    std::vector<uint64_t> coff(N + 1, 0);
-    for (uint64_t s = 0; s < N; s++) coff[s + 1] = coff[s] + accepted[s];
-    const int rw = k > 31 ? 2 : 1;                                    // words per record
+        // the accepted windows' K1 records, then the distinct ones among them (dedup.cu)
+        const ArenaMark emit_mark = arena_mark();
+        int P = unique_prefix_bits(accepted, k);
+        for (int attempt = 0;; attempt++) {
+            uint64_t* rec_s = arena().take_n<uint64_t>(accepted * rw);
+            timer().begin("k1_extract");
+            SKA_LAUNCH(k1q_kernel<RQ_EMIT>, (unsigned)n_tiles, K1_THREADS, 0, b.seq.p, b.qual.p, b.start_bits.p, lo, hi, tile_lo, (int)k, rc ? 1 : 0,
+                       (uint32_t)min_qual, qual_filter, mask, (ulonglong2*)nullptr, (unsigned long long*)nullptr, (const uint64_t*)tile_off, rec_s);
+            timer().end();
+            uint64_t n_u = 0;
+            const uint64_t* uniq = unique_sample_records(rec_s, accepted, k, P, &n_u);
+            if (n_u != ~0ULL) {
+                kept[s].alloc(std::max<uint64_t>(n_u, 1) * rw);
+                SKA_CUDA(cudaMemcpyAsync(kept[s].p, uniq, n_u * rw * 8, cudaMemcpyDeviceToDevice, c.stream));
+                coff[s + 1] = coff[s] + n_u;
+                break;
+            }
+            const int P_max = std::min(22, 2 * ((int)k - 1));
+            if (P >= P_max || attempt > 8) throw Error("reads: a key range is too crowded for the per-sample set");
+            P = std::min(P_max, P + 2);
+            arena_rewind(emit_mark);
+        }
+        SKA_CUDA(cudaStreamSynchronize(c.stream));
+        arena_rewind(sample_mark);
+    }
+
+    // all samples' distinct records back to back -> the merge
     uint64_t* rec_c = arena().take_n<uint64_t>(std::max<uint64_t>(coff[N], 1) * rw);
     for (uint64_t s = 0; s < N; s++) {
-        if (!n_tiles[s]) continue;
-        SKA_LAUNCH(k1q_kernel<RQ_EMIT>, (unsigned)n_tiles[s], K1_THREADS, 0, b.seq.p, b.qual.p, b.start_bits.p, b.h_sample_off[s],
-                   b.h_sample_off[s + 1], tile_lo[s], (int)k, rc ? 1 : 0, (uint32_t)min_qual, qual_filter, masks[s], (ulonglong2*)nullptr,
-                   (unsigned long long*)nullptr, (const uint64_t*)tile_offs[s], rec_c + coff[s] * rw);
+        if (coff[s + 1] > coff[s])
+            SKA_CUDA(cudaMemcpyAsync(rec_c + coff[s] * rw, kept[s].p, (coff[s + 1] - coff[s]) * rw * 8, cudaMemcpyDeviceToDevice, c.stream));
     }
-    timer().end();
     uint64_t* d_coff = arena().take_n<uint64_t>(N + 1);
     SKA_CUDA(cudaMemcpyAsync(d_coff, coff.data(), (N + 1) * 8, cudaMemcpyHostToDevice, c.stream));
     SKA_CUDA(cudaStreamSynchronize(c.stream));
+    kept.clear();
     if (k > 31) build_array_from_records_wide(rec_c, coff[N], d_coff, (uint32_t)N, 0, N, k, rc, out);
     else build_array_from_records(rec_c, coff[N], d_coff, (uint32_t)N, 0, N, k, rc, out);
 }
