@@ -304,6 +304,184 @@ def run_viral(args, rank, world, local_rank):
            "cpu_baseline": {"value": G / dt, "unit": unit, "cores": threads, "kind": "port", "sample": f"the whole job, one pass, {threads} threads"}}, rank)
 
 
+# ---------------------------------------------------------------------------------------------- fastq (configs[3])
+def _gpu_reads(genome_dev, n_pairs, seed, seq_out, qual_out, read_len=150, frag_len=400, err_rate=0.005, lowq_prob=0.5):
+    """synth.paired_reads' model drawn with torch on the device -- 6e8 bases per sample is minutes of numpy --
+    and copied into the host arrays seq_out / qual_out (file 1's reads, then file 2's)."""
+    import torch
+    dev = genome_dev.device
+    g = torch.Generator(device=dev)
+    g.manual_seed(seed)
+    comp = torch.zeros(256, dtype=torch.uint8, device=dev)
+    for a, b in zip(b"ACGT", b"TGCA"):
+        comp[a] = b
+    lut = torch.tensor(list(b"ACTG"), dtype=torch.uint8, device=dev)       # code (c >> 1) & 3 -> letter
+    ar = torch.arange(read_len, device=dev)
+    chunk = 250_000
+    for f in range(2):
+        for c0 in range(0, n_pairs, chunk):
+            n = min(chunk, n_pairs - c0)
+            gg = torch.Generator(device=dev)
+            gg.manual_seed(seed * 1_000_003 + c0)                          # both files see the same fragment starts
+            starts = torch.randint(0, genome_dev.numel() - frag_len + 1, (n,), generator=gg, device=dev)
+            idx = starts[:, None] + (ar if f == 0 else (frag_len - 1 - ar))[None, :]
+            reads = genome_dev[idx]
+            if f == 1:
+                reads = comp[reads.long()]
+            err = torch.rand(reads.shape, generator=g, device=dev) < err_rate
+            codes = (reads >> 1) & 3
+            sub = (codes + torch.randint(1, 4, reads.shape, generator=g, device=dev, dtype=torch.uint8)) & 3
+            reads = torch.where(err, lut[sub.long()], reads)
+            qual = torch.full(reads.shape, ord("I"), dtype=torch.uint8, device=dev)
+            qual[err & (torch.rand(reads.shape, generator=g, device=dev) < lowq_prob)] = ord("+")
+            lo = (f * n_pairs + c0) * read_len
+            torch.from_numpy(seq_out[lo:lo + n * read_len]).copy_(reads.reshape(-1))
+            torch.from_numpy(qual_out[lo:lo + n * read_len]).copy_(qual.reshape(-1))
+
+
+def _oracle_reads_sample(seq, qual, rec_off, n_rec_file1):
+    from oracle import oracle as O
+    sd = object.__new__(O.SampleData)                                      # the flat arrays as they are (no per-record Python objects)
+    sd.seq, sd.qual, sd.rec_off = seq, qual, rec_off
+    sd.n_rec, sd.n_rec_file1, sd.is_reads = len(rec_off) - 1, n_rec_file1, True
+    return sd
+
+
+def run_fastq(args, rank, world, local_rank):
+    """ska build from paired FASTQ with the default count filter (BASELINE configs[3]: 64 samples x 2 M pairs x 150 bp,
+    --min-count 5 --min-qual 20 --qual-filter strict).  The reads are drawn on the device, copied to host arrays, and enter the
+    library the way parsed FASTQ files do (skagpu_seqbatch_upload of bases + qualities)."""
+    if rank != 0:
+        return
+    import torch
+    B = _bench()
+    from ska_rust_b200 import synth
+    NS, NP, L, RL, k = args.fastq_samples, args.fastq_pairs, args.length, 150, 31
+    metric, unit = "read pairs/sec through ska build (paired FASTQ, min-count 5)", "read pairs/s"
+    cores = os.cpu_count() or 1
+    cfg = {"workload": f"ska build from FASTQ, {NS} samples x {NP} paired {RL} bp reads of a {L} bp genome (star model), k={k}, both strands, "
+                       f"min-count 5 / min-qual 20 / strict (BASELINE configs[3])",
+           "k": k, "rc": True, "samples": NS, "pairs_per_sample": NP, "read_len": RL, "genome_bp": L,
+           "reads": "fragment 400, 0.5% substitution errors, Q40 with half of the error bases at Q10 (SURVEY 8d C4)",
+           "l2": "every sample's working set (1.2 GB of reads, 19 GB of observation records) is far larger than L2"}
+    bases = 2 * NP * RL
+    genomes = synth.star_genomes(NS, L, seed=0x5CA20004)
+    rec_off = np.arange(2 * NP + 1, dtype=np.uint64) * np.uint64(RL)
+    names = [f"r{i}" for i in range(NS)]
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+
+    def draw(i, seq_out, qual_out):
+        _gpu_reads(torch.from_numpy(np.ascontiguousarray(genomes[i])).to(dev), NP, 1000 + i, seq_out, qual_out)
+
+    if args.impl == "reference":
+        # the reference's own path on the host cores: whole samples, as many as fit a bounded run, one thread per sample
+        from oracle import oracle as O
+        n_ref = min(NS, args.fastq_ref_samples, cores)
+        seq = np.empty((n_ref, bases), dtype=np.uint8)
+        qual = np.empty((n_ref, bases), dtype=np.uint8)
+        for i in range(n_ref):
+            draw(i, seq[i], qual[i])
+        torch.cuda.empty_cache()
+        sds = [_oracle_reads_sample(seq[i], qual[i], rec_off, NP) for i in range(n_ref)]
+        threads = min(n_ref, B.host_threads_rule(cores, NS))                # what the whole job would run on
+        t0 = time.perf_counter()
+        arr = O.OracleArray.build(sds, names[:n_ref], k=k, rc=True, min_count=5, min_qual=20, qual_filter="strict", threads=threads)
+        dt = time.perf_counter() - t0
+        v = n_ref * NP / dt
+        _emit({"impl": "reference", "metric": metric, "value": v, "unit": unit, "n_gpus": 1, "steps": 1, "warmup": 0, "ms_per_step": dt * 1e3,
+               "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic", "config": cfg,
+               "cpu_baseline": {"value": v, "unit": unit, "cores": threads, "kind": "port",
+                                "sample": f"{n_ref} whole samples of the job ({n_ref * NP} pairs), one pass, {threads} threads (the reference's rule for {NS} samples); "
+                                          f"{arr.dims()['n_rows']} split k-mers"},
+               "e2e": {"value": v, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}, rank)
+        return
+
+    import ska_rust_b200 as S
+    S.set_device(local_rank)
+    q = S.QualOpts(min_count=5, min_qual=20, qual_filter="strict")
+    seq = np.empty((NS, bases), dtype=np.uint8)
+    qual = np.empty((NS, bases), dtype=np.uint8)
+    t0 = time.perf_counter()
+    for i in range(NS):
+        draw(i, seq[i], qual[i])
+    torch.cuda.synchronize()
+    torch.cuda.empty_cache()
+    t_draw = time.perf_counter() - t0
+    samples = [S.Sample(seq[i], rec_off, qual[i], n_rec_file1=NP) for i in range(NS)]
+    info = {}
+
+    def step(src):
+        arr = S.api.build_from_batch(src, names, k, True, q) if isinstance(src, S.SeqBatch) else S.build_from_samples(src, names, k, True, q)
+        info["rows"] = arr.dims()["n_rows"]
+        info["stages"] = S.api.last_timings()
+        return arr
+
+    batch = S.SeqBatch(samples)
+    warm = max(1, min(args.warmup, 3))
+    for _ in range(warm):
+        step(batch)
+    steps = max(1, args.steps)
+    l0 = S.api.launch_count()
+    with B.ClockSampler(local_rank, 0.05) as clocks:
+        S.api.timer_start()
+        for _ in range(steps):
+            step(batch)
+        ms_dev = S.api.timer_stop() / steps
+    launches = (S.api.launch_count() - l0) // steps
+    stages = {}
+    for s_, ms, _ in info["stages"]:
+        stages[s_] = round(stages.get(s_, 0.0) + ms, 3)
+    del batch
+    # end to end: host arrays of bases + qualities in, the array's dimensions out
+    e2e = None
+    if not args.no_e2e:
+        step(samples)
+        S.api.timer_start()
+        n_e2e = max(1, min(steps, 2))
+        for _ in range(n_e2e):
+            step(samples)
+        ms_e2e = S.api.timer_stop() / n_e2e
+        e2e = {"value": NS * NP / (ms_e2e * 1e-3), "unit": unit, "ms_per_step": ms_e2e, "h2d_bytes_per_step": int(2 * NS * bases + NS * rec_off.nbytes),
+               "d2h_bytes_per_step": 64, "note": "pageable host arrays (77 GB at full size), uploaded and built inside the timed region"}
+    # parity: the first samples of the job, whole, against the oracle
+    n_par = min(NS, args.fastq_parity_samples)
+    from oracle import oracle as O
+    threads = min(n_par, B.host_threads_rule(cores, NS))
+    t0 = time.perf_counter()
+    oarr = O.OracleArray.build([_oracle_reads_sample(seq[i], qual[i], rec_off, NP) for i in range(n_par)], names[:n_par], k=k, rc=True,
+                               min_count=5, min_qual=20, qual_filter="strict", threads=threads)
+    dt_cpu = time.perf_counter() - t0
+    garr = S.build_from_samples(samples[:n_par], names[:n_par], k, True, q)
+    gk, gv, gc = garr.export()
+    ok, ov, oc = oarr.export()
+    same = (len(gk) == len(ok) and np.array_equal(np.asarray(gk, dtype=np.uint64), np.asarray(ok, dtype=np.uint64))
+            and np.array_equal(gv, ov) and np.array_equal(gc, oc))
+    parity = {"checked": True, "subsample": f"the first {n_par} samples, whole ({n_par * NP} pairs): {len(ok)} split k-mers, keys / variants / counts "
+                                            + ("identical to the oracle's" if same else "DIFFER from the oracle's")}
+    if not same:
+        raise SystemExit(f"parity check FAILED: {parity}")
+    peak, peak_src = B.measured_peak()
+    n_obs = NS * 2 * NP * (RL - k + 1)
+    dom = max((s_ for s_ in stages if s_ in ("reads_hash", "obs_sort", "count_filter", "k1_extract", "sample_unique")), key=lambda s_: stages[s_])
+    alg = {"reads_hash": (2 * RL / (RL - k + 1) + 16, "2 B per base read (base + quality), 16 B observation record written per window"),
+           "obs_sort": (96, "16 B observation record read + written by each of two scatter passes and by the bucket sort"),
+           "count_filter": (16 + 16 + 1, "sorted observations read for the run heads, one 16 B distinct entry written per k-mer (upper bound: per window)"),
+           "k1_extract": (2 * RL / (RL - k + 1) + 8, "2 B per base read, 8 B record written per accepted window"),
+           "sample_unique": (40, "8 B record read + written by two scatter passes, read once by the bucket set")}[dom]
+    ach = alg[0] * n_obs / (stages[dom] * 1e-3) / 1e9
+    _emit({"metric": metric, "value": NS * NP / (ms_dev * 1e-3), "unit": unit, "n_gpus": 1, "steps": steps, "warmup": warm, "ms_per_step": ms_dev,
+           "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+           "config": dict(cfg, rows_built=info["rows"], windows=n_obs, draw_seconds=round(t_draw, 1)),
+           "e2e": e2e, "gpu_launches": launches,
+           "roofline": {"kernel": dom, "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
+                        "peak_source": peak_src, "launch_ms": stages[dom], "bytes_per_window": alg[0], "what": alg[1],
+                        "note": "stage time summed over the samples of one step"},
+           "stages_ms": stages, "clocks": clocks.summary(), "parity_checked": True, "parity": parity,
+           "cpu_baseline": {"value": n_par * NP / dt_cpu, "unit": unit, "cores": threads, "kind": "port",
+                            "sample": f"the parity subsample: {n_par} whole samples, one pass, {threads} threads"}}, rank)
+
+
 # ---------------------------------------------------------------------------------------------- cli (file to file)
 def _write_fasta_fast(path, name, seq, width=80):
     """>name + 80-column lines, written with one numpy reshape instead of a Python loop per line"""
@@ -427,7 +605,7 @@ def run_cli(args, rank, world, local_rank):
 
 
 def run(args, rank, world, local_rank):
-    fn = {"distance": run_distance, "cli": run_cli, "viral": run_viral}.get(args.workload)
+    fn = {"distance": run_distance, "cli": run_cli, "viral": run_viral, "fastq": run_fastq}.get(args.workload)
     if fn is None:
         raise SystemExit(f"workload {args.workload!r} is not built yet")
     return fn(args, rank, world, local_rank)

@@ -172,6 +172,9 @@ void group_wide_records(const uint64_t* src, uint64_t n, int top_bit, int P1, in
 // sort128.cu: ascending sort of n 16-byte records as 128-bit integers (all-ones records dropped); key_bits = significant bits of the
 // HIGH word.  buf_a / buf_b hold n records each (rec may be buf_b).  -> pointer to the sorted records, *n_out = records kept
 uint64_t* sort_records_wide(const uint64_t* rec, uint64_t n, int key_bits, uint64_t* buf_a, uint64_t* buf_b, uint64_t* n_out);
+// the observation sort of the count filter: sorted (hash, position) records + one entry per distinct hash (see sort128.cu)
+uint64_t* sort_observations(const uint64_t* rec, uint64_t n, uint64_t* buf_a, uint64_t* buf_b, uint64_t* n_obs, uint64_t** drec, uint64_t* ent,
+                            uint64_t* run_start, unsigned long long* d_n_ent, uint32_t min_count, uint32_t bloom_words, bool write_sorted);
 // dedup.cu: one sample's K1 records -> its distinct records (see there)
 uint64_t* unique_sample_records(uint64_t* rec, uint64_t n, uint32_t k, int prefix_bits, uint64_t* n_out);
 // merge.cu

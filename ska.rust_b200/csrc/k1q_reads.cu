@@ -260,26 +260,10 @@ __global__ void tile_popc_kernel(const uint32_t* __restrict__ mask, uint32_t n_t
     if (lane == 0) cnt[tile] = c;
 }
 
-// runs of equal K in the sorted observations -> one distinct entry each, as a record of the second sort:
-//   y (key)   = bloom word << 32 | first position        (the sort by (K, position) puts a run's earliest observation first)
-//   x (value) = run start << 32 | min(run length, 2^32 - 1)
-// The run's end is found by binary search (a k-mer seen millions of times must not be walked by one thread).
-__global__ void q_runs_kernel(const ulonglong2* __restrict__ obs, uint64_t n_obs, ulonglong2* __restrict__ drec,
-                              unsigned long long* __restrict__ n_distinct) {
-    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n_obs) return;
-    const uint64_t key = obs[i].y;
-    if (i > 0 && obs[i - 1].y == key) return;
-    uint64_t lo = i + 1, hi = n_obs;                                  // first index with K > key
-    while (lo < hi) { const uint64_t m = (lo + hi) >> 1; if (obs[m].y <= key) lo = m + 1; else hi = m; }
-    const uint64_t c = lo - i;
-    const unsigned long long d = atomicAdd(n_distinct, 1ULL);
-    drec[d] = make_ulonglong2((i << 32) | (c > 0xFFFFFFFFULL ? 0xFFFFFFFFULL : c), ((uint64_t)bloom_word(key) << 32) | obs[i].x);
-}
-
-// entries sorted by (word, first position): the thread at the head of a word's segment replays that word
-// of the bloom filter (bloom_filter.rs:77-86) in first-occurrence order (a word holds the ~30-40 hashes that map to it)
-__global__ void q_bloom_kernel(const ulonglong2* __restrict__ drec, const ulonglong2* __restrict__ obs, uint64_t n_distinct,
+// entries (sort128.cu: one per distinct hash, written by the warp that sorted the hash's bucket) sorted by (word, first
+// position): the thread at the head of a word's segment replays that word of the bloom filter (bloom_filter.rs:77-86) in
+// first-occurrence order (a word holds the ~30-40 hashes that map to it)
+__global__ void q_bloom_kernel(const ulonglong2* __restrict__ drec, const ulonglong2* __restrict__ ent, uint64_t n_distinct,
                                uint8_t* __restrict__ fp_flag) {
     const uint64_t d = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (d >= n_distinct) return;
@@ -287,15 +271,17 @@ __global__ void q_bloom_kernel(const ulonglong2* __restrict__ drec, const ulongl
     if (d > 0 && (uint32_t)(drec[d - 1].y >> 32) == word) return;
     uint64_t state = 0;
     for (uint64_t e = d; e < n_distinct && (uint32_t)(drec[e].y >> 32) == word; e++) {
-        const uint64_t f = fingerprint(cheap_unmix(obs[drec[e].x >> 32].y));
+        const uint64_t f = fingerprint(cheap_unmix(ent[(uint32_t)drec[e].x].x));
         const bool seen = (state & f) == f;
         if (!seen) state |= f;
         fp_flag[e] = seen;
     }
 }
 
-// which observations of every distinct k-mer reach the dictionary (bloom_filter.rs:116-148); entries that accept more than
-// Q_LONG observations (min_count == 2 or 65535 on a heavily repeated k-mer) are left to q_accept_long_kernel
+// which observations of every distinct k-mer reach the dictionary (bloom_filter.rs:116-148).  3 <= min_count < 65535: exactly
+// one, number min_count - (bloom false positive ? 1 : 0), whose position the entry carries.  min_count == 2 / 65535: every
+// observation from there on, read from the sorted observations; entries that accept more than Q_LONG of them are left to
+// q_accept_long_kernel.
 constexpr uint64_t Q_LONG = 64;
 __device__ __forceinline__ void accept_range(uint64_t c, uint64_t fp, uint32_t min_count, uint64_t& j_lo, uint64_t& j_hi) {
     if (min_count == 2) { j_lo = fp ? 1 : 2; j_hi = c; }
@@ -306,15 +292,23 @@ __device__ __forceinline__ void accept_range(uint64_t c, uint64_t fp, uint32_t m
     }
     if (j_hi > c) j_hi = c;
 }
+__global__ void q_accept_one_kernel(const ulonglong2* __restrict__ drec, const uint8_t* __restrict__ fp_flag, const ulonglong2* __restrict__ ent,
+                                    uint64_t n_distinct, uint32_t* __restrict__ mask) {
+    const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_distinct) return;
+    const uint64_t pp = ent[(uint32_t)drec[t].x].y;
+    const uint32_t p = fp_flag[t] ? (uint32_t)pp : (uint32_t)(pp >> 32);
+    if (p != 0xFFFFFFFFu) atomicOr(&mask[p >> 5], 1u << (p & 31));
+}
 __global__ void q_accept_kernel(const ulonglong2* __restrict__ drec, const uint8_t* __restrict__ fp_flag, const ulonglong2* __restrict__ obs,
-                                uint64_t n_distinct, uint32_t min_count, uint32_t* __restrict__ mask, uint32_t* __restrict__ long_list,
-                                unsigned long long* __restrict__ n_long) {
-    const uint64_t e = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (e >= n_distinct) return;
-    const uint64_t i0 = drec[e].x >> 32, c = drec[e].x & 0xFFFFFFFFULL;
+                                const uint64_t* __restrict__ run_start, uint64_t n_distinct, uint32_t min_count, uint32_t* __restrict__ mask,
+                                uint32_t* __restrict__ long_list, unsigned long long* __restrict__ n_long) {
+    const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_distinct) return;
+    const uint64_t i0 = run_start[(uint32_t)drec[t].x], c = drec[t].x >> 32;
     uint64_t j_lo, j_hi;                                              // accepted 1-based observation numbers [j_lo, j_hi]
-    accept_range(c, fp_flag[e], min_count, j_lo, j_hi);
-    if (j_hi >= j_lo && j_hi - j_lo >= Q_LONG) { long_list[atomicAdd(n_long, 1ULL)] = (uint32_t)e; return; }
+    accept_range(c, fp_flag[t], min_count, j_lo, j_hi);
+    if (j_hi >= j_lo && j_hi - j_lo >= Q_LONG) { long_list[atomicAdd(n_long, 1ULL)] = (uint32_t)t; return; }
     for (uint64_t j = j_lo; j <= j_hi; j++) {
         const uint32_t p = (uint32_t)obs[i0 + j - 1].x;
         atomicOr(&mask[p >> 5], 1u << (p & 31));
@@ -322,11 +316,11 @@ __global__ void q_accept_kernel(const ulonglong2* __restrict__ drec, const uint8
 }
 __global__ void __launch_bounds__(256)
 q_accept_long_kernel(const ulonglong2* __restrict__ drec, const uint8_t* __restrict__ fp_flag, const ulonglong2* __restrict__ obs,
-                     const uint32_t* __restrict__ long_list, uint32_t min_count, uint32_t* __restrict__ mask) {
-    const uint64_t e = long_list[blockIdx.x];
-    const uint64_t i0 = drec[e].x >> 32, c = drec[e].x & 0xFFFFFFFFULL;
+                     const uint64_t* __restrict__ run_start, const uint32_t* __restrict__ long_list, uint32_t min_count, uint32_t* __restrict__ mask) {
+    const uint64_t t = long_list[blockIdx.x];
+    const uint64_t i0 = run_start[(uint32_t)drec[t].x], c = drec[t].x >> 32;
     uint64_t j_lo, j_hi;
-    accept_range(c, fp_flag[e], min_count, j_lo, j_hi);
+    accept_range(c, fp_flag[t], min_count, j_lo, j_hi);
     for (uint64_t j = j_lo + threadIdx.x; j <= j_hi; j += 256) {
         const uint32_t p = (uint32_t)obs[i0 + j - 1].x;
         atomicOr(&mask[p >> 5], 1u << (p & 31));
@@ -366,7 +360,7 @@ void build_array_from_reads(const SeqBatch& b, uint32_t k, bool rc, uint16_t min
         const uint64_t tile_lo = lo / K1_T, n_tiles = (hi - 1) / K1_T - tile_lo + 1;
         const size_t n_words = n_tiles * (K1_T / 32);
         uint32_t* mask = arena().take_n<uint32_t>(n_words);
-        timer().begin("reads_filter");
+        timer().begin("reads_hash");
         SKA_CUDA(cudaMemsetAsync(mask, 0, n_words * 4, c.stream));
         if (min_count <= 1) {                                         // bloom_filter.rs:121: no filtering
             SKA_LAUNCH(k1q_kernel<RQ_MASK>, (unsigned)n_tiles, K1_THREADS, 0, b.seq.p, b.qual.p, b.start_bits.p, lo, hi, tile_lo,
@@ -376,41 +370,56 @@ void build_array_from_reads(const SeqBatch& b, uint32_t k, bool rc, uint16_t min
             const ArenaMark mark = arena_mark();
             const uint64_t n_s = hi - lo;
             if (n_s >= 0xFFFFFFFFull) throw Error("a read set of 2^32 bases or more per sample is beyond the 32-bit positions of the count filter");
+            const bool all_later = min_count == 2 || min_count == 65535;      // every observation past the threshold is accepted
             uint64_t* obs_rec = arena().take_n<uint64_t>(2 * n_s);            // 16-byte records (position, mixed hash)
             uint64_t* obs_tmp = arena().take_n<uint64_t>(2 * n_s);
+            uint64_t* ent = arena().take_n<uint64_t>(2 * n_s);                // one 16-byte entry per distinct hash (at most n_s)
+            uint64_t* run_start = all_later ? arena().take_n<uint64_t>(n_s) : nullptr;
             SKA_CUDA(cudaMemsetAsync(d_counter, 0, 16, c.stream));
             SKA_LAUNCH(k1q_kernel<RQ_OBS>, (unsigned)n_tiles, K1_THREADS, obs_smem, b.seq.p, b.qual.p, b.start_bits.p, lo, hi, tile_lo,
                        (int)k, rc ? 1 : 0, (uint32_t)min_qual, qual_filter, mask, reinterpret_cast<ulonglong2*>(obs_rec), d_counter,
                        (const uint64_t*)nullptr, (uint64_t*)nullptr);
-            // sort by (K, position): groups equal hashes, orders by bloom word (monotone in K) and by stream order inside a hash
+            timer().end();
+            timer().begin("obs_sort");
+            // sort by (hash, position) and one entry per distinct hash: count, bloom word, first position, candidate positions
             uint64_t n_obs = 0;
-            const ulonglong2* obs = reinterpret_cast<const ulonglong2*>(sort_records_wide(obs_rec, n_s, 64, obs_tmp, obs_rec, &n_obs));
-            uint64_t* free_buf = reinterpret_cast<const uint64_t*>(obs) == obs_rec ? obs_tmp : obs_rec;   // the other buffer is scratch now
-            if (n_obs) {
-                ulonglong2* drec = reinterpret_cast<ulonglong2*>(free_buf);     // distinct entries: at most n_obs <= n_s records
-                SKA_LAUNCH(q_runs_kernel, (unsigned)((n_obs + 255) / 256), 256, 0, obs, n_obs, drec, d_counter + 1);
-                unsigned long long h_cnt[2];
-                SKA_CUDA(cudaMemcpyAsync(h_cnt, d_counter, 16, cudaMemcpyDeviceToHost, c.stream));
-                SKA_CUDA(cudaStreamSynchronize(c.stream));
-                const uint64_t n_d = h_cnt[1];
+            uint64_t* drec = nullptr;
+            const ulonglong2* obs = reinterpret_cast<const ulonglong2*>(sort_observations(obs_rec, n_s, obs_tmp, obs_rec, &n_obs, &drec, ent, run_start,
+                                                                                          d_counter + 1, (uint32_t)min_count, (uint32_t)BLOOM_WORDS, all_later));
+            unsigned long long h_cnt[2];
+            SKA_CUDA(cudaMemcpyAsync(h_cnt, d_counter, 16, cudaMemcpyDeviceToHost, c.stream));
+            timer().end();
+            SKA_CUDA(cudaStreamSynchronize(c.stream));
+            timer().begin("count_filter");
+            const uint64_t n_d = h_cnt[1];
+            if (n_d) {
+                // entries by (bloom word, first position): the order the sequential filter met them in, word by word
                 uint64_t* dtmp = arena().take_n<uint64_t>(2 * n_d);
                 uint64_t n_d2 = 0;
-                const ulonglong2* dsorted = reinterpret_cast<const ulonglong2*>(
-                    sort_records_wide(reinterpret_cast<const uint64_t*>(drec), n_d, 54, dtmp, reinterpret_cast<uint64_t*>(drec), &n_d2));
+                const ulonglong2* dsorted = reinterpret_cast<const ulonglong2*>(sort_records_wide(drec, n_d, 54, dtmp, drec, &n_d2));
                 if (n_d2 != n_d) throw Error("internal: distinct entries lost in the sort");
                 uint8_t* fp_flag = arena().take_n<uint8_t>(n_d);
-                uint32_t* long_list = arena().take_n<uint32_t>(n_d);
-                unsigned long long* n_long = arena().take_n<unsigned long long>(1);
-                SKA_CUDA(cudaMemsetAsync(n_long, 0, 8, c.stream));
-                SKA_LAUNCH(q_bloom_kernel, (unsigned)((n_d + 255) / 256), 256, 0, dsorted, obs, n_d, fp_flag);
-                SKA_LAUNCH(q_accept_kernel, (unsigned)((n_d + 255) / 256), 256, 0, dsorted, fp_flag, obs, n_d, (uint32_t)min_count, mask, long_list, n_long);
-                unsigned long long h_long = 0;
-                SKA_CUDA(cudaMemcpyAsync(&h_long, n_long, 8, cudaMemcpyDeviceToHost, c.stream));
-                SKA_CUDA(cudaStreamSynchronize(c.stream));
-                if (h_long) SKA_LAUNCH(q_accept_long_kernel, (unsigned)h_long, 256, 0, dsorted, fp_flag, obs, long_list, (uint32_t)min_count, mask);
+                const ulonglong2* ent2 = reinterpret_cast<const ulonglong2*>(ent);
+                SKA_LAUNCH(q_bloom_kernel, (unsigned)((n_d + 255) / 256), 256, 0, dsorted, ent2, n_d, fp_flag);
+                if (!all_later) {
+                    SKA_LAUNCH(q_accept_one_kernel, (unsigned)((n_d + 255) / 256), 256, 0, dsorted, fp_flag, ent2, n_d, mask);
+                } else {
+                    uint32_t* long_list = arena().take_n<uint32_t>(n_d);
+                    unsigned long long* n_long = arena().take_n<unsigned long long>(1);
+                    SKA_CUDA(cudaMemsetAsync(n_long, 0, 8, c.stream));
+                    SKA_LAUNCH(q_accept_kernel, (unsigned)((n_d + 255) / 256), 256, 0, dsorted, fp_flag, obs, (const uint64_t*)run_start, n_d,
+                               (uint32_t)min_count, mask, long_list, n_long);
+                    unsigned long long h_long = 0;
+                    SKA_CUDA(cudaMemcpyAsync(&h_long, n_long, 8, cudaMemcpyDeviceToHost, c.stream));
+                    SKA_CUDA(cudaStreamSynchronize(c.stream));
+                    if (h_long) SKA_LAUNCH(q_accept_long_kernel, (unsigned)h_long, 256, 0, dsorted, fp_flag, obs, (const uint64_t*)run_start,
+                                           (const uint32_t*)long_list, (uint32_t)min_count, mask);
+                }
             }
+            timer().end();
             SKA_CUDA(cudaStreamSynchronize(c.stream));
             arena_rewind(mark);
+            timer().begin("mask_scan");
         }
         // compaction offsets of the accepted windows
         uint32_t* cnt = arena().take_n<uint32_t>(n_tiles);

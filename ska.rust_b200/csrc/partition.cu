@@ -361,6 +361,49 @@ part_scatter_wide_kernel(const uint64_t* __restrict__ src, uint64_t n_total, Seg
     ulonglong2* dst2 = reinterpret_cast<ulonglong2*>(dst);
     for (uint32_t slot = threadIdx.x; slot < n_valid; slot += SCW_T) dst2[s_gbase[s_sdig[slot]] + slot] = s_stage[slot];
 }
+// Plain grouping of 16-byte records without the staging buffer: with 2^11 digits a tile of 4096 records holds two records per
+// digit, so staging cannot make the global writes any wider than they are -- every record goes from its register straight to
+// digit base + rank.  Shared memory holds the counters only (24 KB at 11 bits), 512 threads x 8 records.
+constexpr int SCD_T = 512;
+constexpr int SCD_I = PT_TILE / SCD_T;
+__global__ void __launch_bounds__(SCD_T, 2)
+part_scatter_wide_direct_kernel(const uint64_t* __restrict__ src, uint64_t n_total, Segs sg, DigitFn fn, int bits,
+                                unsigned long long* __restrict__ cursor, uint64_t* __restrict__ dst) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    const uint32_t D = 1u << bits;
+    unsigned long long* s_gbase = reinterpret_cast<unsigned long long*>(smem);   // [D]
+    uint32_t* s_acnt = reinterpret_cast<uint32_t*>(s_gbase + D);                 // [D]
+    uint64_t beg, end; uint32_t region;
+    tile_range(blockIdx.x, sg, n_total, beg, end, region);
+    const uint32_t cnt = (uint32_t)(end - beg);
+    ulonglong2 rr[SCD_I]; uint32_t dp[SCD_I];
+    const ulonglong2* src2 = reinterpret_cast<const ulonglong2*>(src) + beg;
+#pragma unroll
+    for (int j = 0; j < SCD_I; j++) {
+        const uint32_t li = j * SCD_T + threadIdx.x;
+        rr[j] = li < cnt ? __ldg(src2 + li) : make_ulonglong2(~0ULL, ~0ULL);
+    }
+    for (uint32_t i = threadIdx.x; i < D; i += SCD_T) s_acnt[i] = 0;
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < SCD_I; j++) {
+        const u128 r = ((u128)rr[j].y << 64) | rr[j].x;
+        const uint32_t d = j * SCD_T + threadIdx.x < cnt ? digit128(r, fn.pass, fn.shift, fn.mask) : PT_NONE;
+        dp[j] = d != PT_NONE ? ((d << 16) | atomicAdd(&s_acnt[d], 1u)) : PT_NONE;
+    }
+    __syncthreads();
+    for (uint32_t d = threadIdx.x; d < D; d += SCD_T) {
+        const uint32_t tot = s_acnt[d];
+        if (tot) s_gbase[d] = atomicAdd(&cursor[(size_t)region * D + d], (unsigned long long)tot);
+    }
+    __syncthreads();
+    ulonglong2* dst2 = reinterpret_cast<ulonglong2*>(dst);
+#pragma unroll
+    for (int j = 0; j < SCD_I; j++)
+        if (dp[j] != PT_NONE) dst2[s_gbase[dp[j] >> 16] + (dp[j] & 0xFFFFu)] = rr[j];
+}
+static bool scatter_direct_enabled() { const char* e = getenv("SKA_SCATTER_DIRECT"); return !e || atoi(e) != 0; }
+
 static size_t scatter_wide_smem(int bits) {
     const size_t D = (size_t)1 << bits;
     return PT_TILE * 16 + D * 8 + (D + 1) * 4 + D * 4 + PT_TILE * 2 + 64;
@@ -422,6 +465,86 @@ static size_t scatter_smem(int bits) {
     return PT_TILE * 8 + D * 8 + (D + 1) * 4 + D * 4 + PT_TILE * 2 + 64;
 }
 
+// The same scan for many counters (2^20 and more buckets): every CTA sums its 4096 counters, one CTA scans the sums, every
+// CTA scans its counters again from its carry.  (The single CTA above walks 4 M counters in 1.7 ms.)
+constexpr uint32_t SCAN_CHUNK = 4096;
+__device__ __forceinline__ void cta_reduce2(uint64_t& a, uint64_t& b, uint64_t (*s_w)[32]) {
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { a += __shfl_xor_sync(0xFFFFFFFFu, a, o); b += __shfl_xor_sync(0xFFFFFFFFu, b, o); }
+    if (lane == 0) { s_w[0][warp] = a; s_w[1][warp] = b; }
+    __syncthreads();
+    a = s_w[0][lane]; b = s_w[1][lane];                      // 1024 threads: 32 warps
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { a += __shfl_xor_sync(0xFFFFFFFFu, a, o); b += __shfl_xor_sync(0xFFFFFFFFu, b, o); }
+}
+__global__ void __launch_bounds__(1024)
+part_scan_sums_kernel(const unsigned long long* __restrict__ cnt, uint32_t n, int n_copies, unsigned long long* __restrict__ sums /* [2][gridDim.x] */) {
+    __shared__ uint64_t s_w[2][32];
+    uint64_t sum = 0, tsum = 0;
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        const uint32_t i = blockIdx.x * SCAN_CHUNK + 4 * threadIdx.x + j;
+        uint64_t v = 0;
+        if (i < n) for (int cpy = 0; cpy < n_copies; cpy++) v += cnt[(size_t)cpy * n + i];
+        sum += v; tsum += (v + PT_TILE - 1) / PT_TILE;
+    }
+    cta_reduce2(sum, tsum, s_w);
+    if (threadIdx.x == 0) { sums[blockIdx.x] = sum; sums[gridDim.x + blockIdx.x] = tsum; }
+}
+__global__ void __launch_bounds__(1024)
+part_scan_apply_kernel(const unsigned long long* __restrict__ cnt, uint32_t n, int n_copies, const uint64_t* __restrict__ carry /* [2][grid + 1] */,
+                       uint64_t* __restrict__ off, unsigned long long* __restrict__ cursor, uint64_t* __restrict__ tile_pref) {
+    __shared__ uint64_t s_warp[2][32];
+    const uint32_t t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    uint64_t v[4], tl[4], sum = 0, tsum = 0;
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        const uint32_t i = blockIdx.x * SCAN_CHUNK + 4 * t + j;
+        v[j] = 0ull;
+        if (i < n) for (int cpy = 0; cpy < n_copies; cpy++) v[j] += cnt[(size_t)cpy * n + i];
+        tl[j] = (v[j] + PT_TILE - 1) / PT_TILE;
+        sum += v[j]; tsum += tl[j];
+    }
+    uint64_t inc = sum, tinc = tsum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        uint64_t u = __shfl_up_sync(0xFFFFFFFFu, inc, o), w = __shfl_up_sync(0xFFFFFFFFu, tinc, o);
+        if (lane >= (uint32_t)o) { inc += u; tinc += w; }
+    }
+    if (lane == 31) { s_warp[0][warp] = inc; s_warp[1][warp] = tinc; }
+    __syncthreads();
+    if (warp < 2) {
+        uint64_t w = s_warp[warp][lane], winc = w;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { uint64_t u = __shfl_up_sync(0xFFFFFFFFu, winc, o); if (lane >= (uint32_t)o) winc += u; }
+        s_warp[warp][lane] = winc - w;
+    }
+    __syncthreads();
+    uint64_t run = carry[blockIdx.x] + s_warp[0][warp] + (inc - sum), trun = carry[gridDim.x + 1 + blockIdx.x] + s_warp[1][warp] + (tinc - tsum);
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        const uint32_t i = blockIdx.x * SCAN_CHUNK + 4 * t + j;
+        if (i < n) { off[i] = run; if (cursor) cursor[i] = run; if (tile_pref) tile_pref[i] = trun; }
+        run += v[j]; trun += tl[j];
+    }
+    if (blockIdx.x == gridDim.x - 1 && t == 1023) { off[n] = run; if (tile_pref) tile_pref[n] = trun; }
+}
+
+static void launch_part_scan(const unsigned long long* cnt, uint32_t n, uint64_t* off, unsigned long long* cursor, uint64_t* tile_pref, int n_copies) {
+    if (n <= 4 * SCAN_CHUNK) {
+        SKA_LAUNCH(part_scan_kernel, 1, 1024, 0, cnt, n, off, cursor, tile_pref, n_copies);
+        return;
+    }
+    const uint32_t g = (n + SCAN_CHUNK - 1) / SCAN_CHUNK;
+    unsigned long long* sums = arena().take_n<unsigned long long>(2 * (size_t)g);
+    uint64_t* carry = arena().take_n<uint64_t>(2 * ((size_t)g + 1));
+    SKA_LAUNCH(part_scan_sums_kernel, g, 1024, 0, cnt, n, n_copies, sums);
+    SKA_LAUNCH(part_scan_kernel, 1, 1024, 0, (const unsigned long long*)sums, g, carry, (unsigned long long*)nullptr, (uint64_t*)nullptr, 1);
+    SKA_LAUNCH(part_scan_kernel, 1, 1024, 0, (const unsigned long long*)(sums + g), g, carry + g + 1, (unsigned long long*)nullptr, (uint64_t*)nullptr, 1);
+    SKA_LAUNCH(part_scan_apply_kernel, g, 1024, 0, cnt, n, n_copies, (const uint64_t*)carry, off, cursor, tile_pref);
+}
+
 PartPlan make_part_plan(uint32_t k, int prefix_bits, uint64_t n_samples_total) {
     PartPlan pl;
     pl.key_bits = 2 * ((int)k - 1);
@@ -471,8 +594,7 @@ void partition_coarse(const uint64_t* rec, uint64_t n_pos, const uint64_t* d_sam
         if (pl.wide) SKA_LAUNCH(part_hist_wide_kernel, hist_grid, PT_THREADS, D1 * 4, rec, n_pos, n_tiles1, none, f1, pl.P1, hist1);
         else SKA_LAUNCH(part_hist_kernel, hist_grid, PT_THREADS, D1 * 4, rec, n_pos, n_tiles1, none, f1, pl.P1, hist1);
     }
-    SKA_LAUNCH(part_scan_kernel, 1, 1024, 0, k1_hist ? k1_hist : (const unsigned long long*)hist1, D1, off1, cur1, tile_pref,
-               k1_hist ? K1_HIST_COPIES : 1);
+    launch_part_scan(k1_hist ? k1_hist : (const unsigned long long*)hist1, D1, off1, cur1, tile_pref, k1_hist ? K1_HIST_COPIES : 1);
     timer().end();
     timer().begin("scatter1");
     uint64_t* a = arena().take_n<uint64_t>(std::max<uint64_t>(n_pos, 1) * (pl.wide ? 2 : 1));
@@ -512,7 +634,7 @@ void partition_fine(const uint64_t* src, const Segs& sg, uint64_t n_tiles2, uint
         if (pl.wide) SKA_LAUNCH(part_hist_wide_kernel, g2, PT_THREADS, D2 * 4, src, (uint64_t)0, n_tiles2, sg, f2, pl.P2, hist2);
         else SKA_LAUNCH(part_hist_kernel, g2, PT_THREADS, D2 * 4, src, (uint64_t)0, n_tiles2, sg, f2, pl.P2, hist2);
     }
-    SKA_LAUNCH(part_scan_kernel, 1, 1024, 0, (const unsigned long long*)hist2, (uint32_t)NB, bucket_off, cur2, (uint64_t*)nullptr, 1);
+    launch_part_scan((const unsigned long long*)hist2, (uint32_t)NB, bucket_off, cur2, (uint64_t*)nullptr, 1);
     timer().end();
     timer().begin("scatter2");
     if (n_tiles2 && pl.wide) {
@@ -606,9 +728,11 @@ void group_wide_records(const uint64_t* src, uint64_t n, int top_bit, int P1, in
     const PackWide pw{0, 0, 0};
     const unsigned hist_grid = (unsigned)std::min<uint64_t>(std::max<uint64_t>(n_tiles1, 1), (uint64_t)c.sm_count * 4);
     if (n) SKA_LAUNCH(part_hist_wide_kernel, hist_grid, PT_THREADS, D1 * 4, src, n, n_tiles1, none, f1, P1, hist1);
-    SKA_LAUNCH(part_scan_kernel, 1, 1024, 0, (const unsigned long long*)hist1, D1, off1, cur1, tile_pref, 1);
-    if (n) SKA_LAUNCH((part_scatter_wide_kernel<2>), (unsigned)n_tiles1, SCW_T, scatter_wide_smem(P1), src, n, none, f1, P1, pw,
-                      (const uint64_t*)nullptr, 0u, cur1, buf_a);
+    launch_part_scan((const unsigned long long*)hist1, D1, off1, cur1, tile_pref, 1);
+    const bool direct = scatter_direct_enabled();
+    if (n && direct) SKA_LAUNCH(part_scatter_wide_direct_kernel, (unsigned)n_tiles1, SCD_T, (size_t)D1 * 12, src, n, none, f1, P1, cur1, buf_a);
+    else if (n) SKA_LAUNCH((part_scatter_wide_kernel<2>), (unsigned)n_tiles1, SCW_T, scatter_wide_smem(P1), src, n, none, f1, P1, pw,
+                           (const uint64_t*)nullptr, 0u, cur1, buf_a);
     if (P2 == 0) { *out = buf_a; *d_off = off1; return; }
     uint64_t n_tiles2 = 0;
     SKA_CUDA(cudaMemcpyAsync(&n_tiles2, tile_pref + D1, 8, cudaMemcpyDeviceToHost, c.stream));
@@ -624,8 +748,10 @@ void group_wide_records(const uint64_t* src, uint64_t n, int top_bit, int P1, in
         const unsigned g2 = (unsigned)std::min<uint64_t>(n_tiles2, (uint64_t)c.sm_count * 4);
         SKA_LAUNCH(part_hist_wide_kernel, g2, PT_THREADS, D2 * 4, buf_a, (uint64_t)0, n_tiles2, sg, f2, P2, hist2);
     }
-    SKA_LAUNCH(part_scan_kernel, 1, 1024, 0, (const unsigned long long*)hist2, (uint32_t)NB, bucket_off, cur2, (uint64_t*)nullptr, 1);
-    if (n_tiles2)
+    launch_part_scan((const unsigned long long*)hist2, (uint32_t)NB, bucket_off, cur2, (uint64_t*)nullptr, 1);
+    if (n_tiles2 && direct)
+        SKA_LAUNCH(part_scatter_wide_direct_kernel, (unsigned)n_tiles2, SCD_T, (size_t)D2 * 12, buf_a, (uint64_t)0, sg, f2, P2, cur2, buf_b);
+    else if (n_tiles2)
         SKA_LAUNCH((part_scatter_wide_kernel<2>), (unsigned)n_tiles2, SCW_T, scatter_wide_smem(P2), buf_a, (uint64_t)0, sg, f2, P2, pw,
                    (const uint64_t*)nullptr, 0u, cur2, buf_b);
     *out = buf_b; *d_off = bucket_off;

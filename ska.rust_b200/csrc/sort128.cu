@@ -3,10 +3,17 @@
 // (bloom word, first position); src/ska_dict/bloom_filter.rs:116-148).  Replaces the library radix sort of round 1.
 //
 // MSD: the records are grouped by their top 22 key bits with the two scatter passes of partition.cu (group_wide_records);
-// keys here are hashes / bloom words, i.e. uniform, so a bucket holds n / 2^22 records on average.  One WARP then sorts one
-// bucket in shared memory (bitonic, <= 256 records); the rare larger bucket (one k-mer repeated thousands of times) is
-// sorted by a whole CTA in shared memory (<= 8192 records) or, beyond that, in place in global memory.
-// Roofline: HBM; 16 B per record moved by each of two scatters and once by the bucket sort.
+// keys here are hashes / bloom words, i.e. uniform, so a bucket holds n / 2^22 records on average (~115 observations of a
+// 2 M-pair read set).  One WARP then sorts one bucket IN REGISTERS: a bitonic network over 32 lanes x E records per lane
+// (E = 2..16 by bucket size), compare-exchanges inside a lane for strides < E and through __shfl_xor above -- no shared
+// memory traffic, 15 of the 36 steps of a 256-record sort cross lanes.  The rare larger bucket (one k-mer repeated thousands
+// of times) is sorted by a CTA in shared memory (<= 8192 records) or, beyond that, by recursion on the next key bits.
+//
+// For the observations the same warp goes on to find the runs of equal hashes in its sorted bucket (a run never leaves its
+// bucket: the bucket is a hash prefix) and writes one ENTRY per distinct hash -- count, first position, and the positions of
+// observation number min_count - 1 and min_count, the only two the count filter can accept (bloom_filter.rs:131-146) -- so
+// the sorted observations themselves are written back only for min_count == 2 / 65535, where every later one is accepted.
+// Roofline: HBM; 16 B per record moved by each of two scatters and read once by the bucket sort.
 #include <algorithm>
 #include <vector>
 
@@ -14,45 +21,178 @@
 
 namespace ska {
 
-typedef unsigned __int128 u128s;
-constexpr int SW_PER_WARP = 256;          // records a warp sorts
-constexpr int SM_MAX = 2048;              // records a 256-thread CTA sorts in shared memory (32 KB: several CTAs per SM)
-constexpr int SB_MAX = 8192;              // records a 1024-thread CTA sorts in shared memory
+constexpr int SW_MAX_E = 16;                 // records per lane of the largest warp sort
+constexpr int SW_PER_WARP = 32 * SW_MAX_E;   // records a warp sorts
+constexpr int SM_MAX = 2048;                 // records a 256-thread CTA sorts in shared memory (32 KB: several CTAs per SM)
+constexpr int SB_MAX = 8192;                 // records a 1024-thread CTA sorts in shared memory
+constexpr uint32_t FULL = 0xFFFFFFFFu;
 
 __device__ __forceinline__ bool rec_gt(const ulonglong2& a, const ulonglong2& b) { return a.y > b.y || (a.y == b.y && a.x > b.x); }
 
-// one warp per bucket; buckets larger than SW_PER_WARP go to the big list
-__global__ void __launch_bounds__(256)
-bucket_sort_small_kernel(uint64_t* __restrict__ rec, const uint64_t* __restrict__ off, uint32_t n_buckets, uint32_t* __restrict__ big_list,
-                         uint32_t* __restrict__ n_big) {
-    __shared__ ulonglong2 s_buf[8][SW_PER_WARP];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const uint32_t b = blockIdx.x * 8 + warp;
-    if (b >= n_buckets) return;
-    const uint64_t beg = off[b], end = off[b + 1];
-    const uint32_t n = (uint32_t)min(end - beg, (uint64_t)0xFFFFFFFFu);
-    if (n < 2) return;
-    if (end - beg > SW_PER_WARP) { if (lane == 0) big_list[atomicAdd(n_big, 1u)] = b; return; }
-    ulonglong2* r2 = reinterpret_cast<ulonglong2*>(rec) + beg;
-    ulonglong2* s = s_buf[warp];
-    uint32_t np2 = 2; while (np2 < n) np2 <<= 1;
-    for (uint32_t i = lane; i < np2; i += 32) s[i] = i < n ? r2[i] : make_ulonglong2(~0ULL, ~0ULL);
-    __syncwarp();
-    for (uint32_t size = 2; size <= np2; size <<= 1)
-        for (uint32_t stride = size >> 1; stride > 0; stride >>= 1) {
-            for (uint32_t t = lane; t < np2 / 2; t += 32) {
-                const uint32_t a = 2 * t - (t & (stride - 1)), c = a + stride;
-                const bool up = (a & size) == 0;
-                const ulonglong2 x = s[a], y = s[c];
-                if (rec_gt(x, y) == up) { s[a] = y; s[c] = x; }
-            }
-            __syncwarp();
+// ascending bitonic sort of 32 * E records held as v[r] = record (lane * E + r).  Only the loops over a lane's own records are
+// unrolled (register indices must be constants); the merge sizes and the lane strides are run-time loops -- fully unrolled,
+// the five bucket sizes came to 36 K instructions (575 KB) and the warps of a CTA, each in its own variant, starved on fetch.
+__device__ __forceinline__ void cex(ulonglong2& a, ulonglong2& b, const bool up) {
+    if (rec_gt(a, b) == up) { const ulonglong2 t = a; a = b; b = t; }
+}
+template <int E>
+__device__ __forceinline__ void warp_bitonic(ulonglong2 (&v)[E], const int lane) {
+    // sizes 2 .. E: inside the lane; the direction of the last one alternates with the lane, of the smaller ones with r
+#pragma unroll
+    for (int size = 2; size <= E; size <<= 1) {
+#pragma unroll
+        for (int stride = size >> 1; stride > 0; stride >>= 1) {
+#pragma unroll
+            for (int r = 0; r < E; r++)
+                if ((r & stride) == 0) cex(v[r], v[r | stride], size == E ? (lane & 1) == 0 : (r & size) == 0);
         }
-    for (uint32_t i = lane; i < n; i += 32) r2[i] = s[i];
+    }
+    // sizes 2E .. 32E: strides >= E cross lanes (partner lane ^ stride / E, same r), then a merge inside the lane
+#pragma unroll 1
+    for (int size = 2 * E; size <= 32 * E; size <<= 1) {
+        const bool up = ((lane * E) & size) == 0;
+#pragma unroll 1
+        for (int lm = size / (2 * E); lm > 0; lm >>= 1) {
+            const bool keep_min = ((lane & lm) == 0) == up;
+#pragma unroll
+            for (int r = 0; r < E; r++) {
+                ulonglong2 o;
+                o.x = __shfl_xor_sync(FULL, v[r].x, lm);
+                o.y = __shfl_xor_sync(FULL, v[r].y, lm);
+                if (rec_gt(v[r], o) == keep_min) v[r] = o;
+            }
+        }
+#pragma unroll
+        for (int stride = E / 2; stride > 0; stride >>= 1) {
+#pragma unroll
+            for (int r = 0; r < E; r++)
+                if ((r & stride) == 0) cex(v[r], v[r | stride], up);
+        }
+    }
 }
 
-// one CTA per large bucket: shared memory up to SB_MAX records; anything larger goes to the huge list (sorted by recursing
-// on the next key bits from the host: a bucket that large is one hash seen thousands of times, told apart only by position)
+// what the run-finding epilogue writes (observation sort only)
+struct RunsOut {
+    ulonglong2* drec;                // per entry: x = count << 32 | entry index, y = bloom word << 32 | first position
+    ulonglong2* ent;                 // per entry: x = mixed hash, y = position of observation min_count << 32 | of observation min_count - 1
+    uint64_t* run_start;             // per entry: index of its first observation in the sorted array (write_sorted only)
+    unsigned long long* n_ent;
+    uint32_t min_count;
+    uint32_t bloom_words;
+    int write_sorted;
+};
+__device__ __forceinline__ uint32_t word_of(uint64_t mixed, uint32_t words) { return (uint32_t)__umul64hi(mixed, (uint64_t)words); }
+
+constexpr int SW_WARPS = 8;                  // warps per CTA of the warp-sort kernels
+
+// the runs of one sorted bucket, from its hashes and positions in shared memory (record i at s_key[i] / s_pos[i]): one entry
+// per run.  Chunks of 32 records, last chunk first, so that every run head knows where the next run starts.
+__device__ __forceinline__ void warp_emit_runs(const uint64_t* __restrict__ s_key, const uint32_t* __restrict__ s_pos, const uint32_t n,
+                                               const uint64_t beg, const int lane, const RunsOut& ro) {
+    const uint32_t chunks = (n + 31) / 32;
+    uint32_t total = 0;
+    for (uint32_t j = 0; j < chunks; j++) {
+        const uint32_t i = j * 32 + lane;
+        const bool head = i < n && (i == 0 || s_key[i - 1] != s_key[i]);
+        total += __popc(__ballot_sync(FULL, head));
+    }
+    unsigned long long base = 0;
+    if (lane == 0) base = atomicAdd(ro.n_ent, (unsigned long long)total);
+    base = __shfl_sync(FULL, base, 0);
+    uint32_t next_head = n, remaining = total;
+    const uint32_t mc = ro.min_count;
+    for (uint32_t j = chunks; j-- > 0;) {
+        const uint32_t i = j * 32 + lane;
+        const uint64_t K = i < n ? s_key[i] : 0;
+        const bool head = i < n && (i == 0 || s_key[i - 1] != K);
+        const uint32_t m = __ballot_sync(FULL, head);
+        remaining -= __popc(m);
+        if (head) {
+            const uint32_t above = lane == 31 ? 0u : m >> (lane + 1);
+            const uint32_t end = above ? i + (uint32_t)__ffs(above) : next_head;
+            const uint32_t c = end - i;
+            const unsigned long long e = base + remaining + __popc(m & ((1u << lane) - 1u));
+            const uint32_t pa = (mc >= 2 && mc - 1 <= c) ? s_pos[i + mc - 2] : 0xFFFFFFFFu;
+            const uint32_t pb = (mc >= 1 && mc <= c) ? s_pos[i + mc - 1] : 0xFFFFFFFFu;
+            ro.drec[e] = make_ulonglong2(((unsigned long long)c << 32) | e, ((unsigned long long)word_of(K, ro.bloom_words) << 32) | s_pos[i]);
+            ro.ent[e] = make_ulonglong2(K, ((unsigned long long)pb << 32) | pa);
+            if (ro.write_sorted) ro.run_start[e] = beg + i;
+        }
+        if (m) next_head = j * 32 + (uint32_t)__ffs(m) - 1;
+    }
+}
+
+template <int E, bool RUNS>
+__device__ __forceinline__ void warp_sort_bucket(ulonglong2* __restrict__ r2, const uint32_t n, const int lane, uint64_t* __restrict__ s_key,
+                                                 uint32_t* __restrict__ s_pos, const bool write_sorted) {
+    ulonglong2 v[E];
+#pragma unroll
+    for (int r = 0; r < E; r++) {
+        const uint32_t i = lane * E + r;
+        v[r] = i < n ? r2[i] : make_ulonglong2(~0ULL, ~0ULL);
+    }
+    warp_bitonic<E>(v, lane);
+    if (!RUNS || write_sorted) {
+#pragma unroll
+        for (int r = 0; r < E; r++) { const uint32_t i = lane * E + r; if (i < n) r2[i] = v[r]; }
+    }
+    if (RUNS) {
+#pragma unroll
+        for (int r = 0; r < E; r++) { const uint32_t i = lane * E + r; if (i < n) { s_key[i] = v[r].y; s_pos[i] = (uint32_t)v[r].x; } }
+    }
+}
+
+// Warps take buckets in turn (grid-stride: a warp that drew small buckets does not wait for its CTA's slowest).  EMAX = 8:
+// every bucket (list == NULL); those above 256 records go to `over_list`.  EMAX = 16: the buckets of `list` (*n_list of them),
+// 16 records per lane; those above 512 go to `over_list`.  Two kernels because the 16-per-lane network needs 128 registers.
+template <int EMAX, bool RUNS>
+__global__ void __launch_bounds__(32 * SW_WARPS, EMAX == 8 ? 3 : 2)
+bucket_sort_warp_kernel(uint64_t* __restrict__ rec, const uint64_t* __restrict__ off, uint32_t n_buckets, const uint32_t* __restrict__ list,
+                        const uint32_t* __restrict__ n_list, uint32_t* __restrict__ over_list, uint32_t* __restrict__ n_over, RunsOut ro) {
+    __shared__ uint64_t s_key_all[RUNS ? SW_WARPS * 32 * EMAX : 1];
+    __shared__ uint32_t s_pos_all[RUNS ? SW_WARPS * 32 * EMAX : 1];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint64_t* s_key = s_key_all + (RUNS ? warp * 32 * EMAX : 0);
+    uint32_t* s_pos = s_pos_all + (RUNS ? warp * 32 * EMAX : 0);
+    const uint32_t count = list ? *n_list : n_buckets;
+    for (uint32_t idx = blockIdx.x * SW_WARPS + warp; idx < count; idx += gridDim.x * SW_WARPS) {
+        const uint32_t b = list ? list[idx] : idx;
+        const uint64_t beg = off[b], end = off[b + 1];
+        if (end == beg || (!RUNS && end - beg < 2)) continue;
+        if (end - beg > 32 * EMAX) { if (lane == 0) over_list[atomicAdd(n_over, 1u)] = b; continue; }
+        const uint32_t n = (uint32_t)(end - beg);
+        ulonglong2* r2 = reinterpret_cast<ulonglong2*>(rec) + beg;
+        const bool ws = RUNS && ro.write_sorted;
+        if (EMAX == 16) warp_sort_bucket<16, RUNS>(r2, n, lane, s_key, s_pos, ws);
+        else if (n <= 32) warp_sort_bucket<1, RUNS>(r2, n, lane, s_key, s_pos, ws);
+        else if (n <= 64) warp_sort_bucket<2, RUNS>(r2, n, lane, s_key, s_pos, ws);
+        else if (n <= 128) warp_sort_bucket<4, RUNS>(r2, n, lane, s_key, s_pos, ws);
+        else warp_sort_bucket<8, RUNS>(r2, n, lane, s_key, s_pos, ws);
+        if (RUNS) {
+            __syncwarp();
+            warp_emit_runs(s_key, s_pos, n, beg, lane, ro);
+            __syncwarp();
+        }
+    }
+}
+
+// both warp kernels over the buckets of one grouping; -> big_list / cnts[0]: the buckets above 512 records
+static void launch_warp_sorts(uint64_t* data, const uint64_t* off, uint32_t nb, uint32_t* list16, uint32_t* big_list, uint32_t* cnts /* [0] big, [3] list16 */,
+                              const RunsOut* ro) {
+    Context& c = ctx();
+    const unsigned g8 = (unsigned)std::min<uint64_t>(((uint64_t)nb + SW_WARPS - 1) / SW_WARPS, (uint64_t)c.sm_count * 3 * 8);
+    const unsigned g16 = (unsigned)c.sm_count * 2;
+    if (ro) {
+        SKA_LAUNCH((bucket_sort_warp_kernel<8, true>), g8, 32 * SW_WARPS, 0, data, off, nb, (const uint32_t*)nullptr, (const uint32_t*)nullptr, list16, cnts + 3, *ro);
+        SKA_LAUNCH((bucket_sort_warp_kernel<16, true>), g16, 32 * SW_WARPS, 0, data, off, nb, (const uint32_t*)list16, (const uint32_t*)(cnts + 3), big_list, cnts, *ro);
+    } else {
+        SKA_LAUNCH((bucket_sort_warp_kernel<8, false>), g8, 32 * SW_WARPS, 0, data, off, nb, (const uint32_t*)nullptr, (const uint32_t*)nullptr, list16, cnts + 3, RunsOut{});
+        SKA_LAUNCH((bucket_sort_warp_kernel<16, false>), g16, 32 * SW_WARPS, 0, data, off, nb, (const uint32_t*)list16, (const uint32_t*)(cnts + 3), big_list, cnts, RunsOut{});
+    }
+}
+
+// one CTA per large bucket: shared memory up to MAXN records; anything larger goes to the next list (the last one is sorted
+// by recursing on the next key bits from the host: a bucket that large is one hash seen thousands of times)
 template <int T, int MAXN>
 __global__ void __launch_bounds__(T)
 bucket_sort_big_kernel(uint64_t* __restrict__ rec, const uint64_t* __restrict__ off, const uint32_t* __restrict__ big_list,
@@ -77,6 +217,31 @@ bucket_sort_big_kernel(uint64_t* __restrict__ rec, const uint64_t* __restrict__ 
             __syncthreads();
         }
     for (uint32_t i = threadIdx.x; i < n; i += T) r2[i] = s[i];
+}
+
+// the runs of the large buckets, read back from their sorted records (one CTA per bucket; the end of a run by galloping)
+__global__ void __launch_bounds__(256)
+bucket_runs_big_kernel(const uint64_t* __restrict__ rec, const uint64_t* __restrict__ off, const uint32_t* __restrict__ big_list, RunsOut ro) {
+    const uint32_t b = big_list[blockIdx.x];
+    const uint64_t beg = off[b], n = off[b + 1] - beg;
+    const ulonglong2* r2 = reinterpret_cast<const ulonglong2*>(rec) + beg;
+    for (uint64_t i = threadIdx.x; i < n; i += 256) {
+        const uint64_t K = r2[i].y;
+        if (i > 0 && r2[i - 1].y == K) continue;
+        uint64_t lo = i, step = 1;                                      // r2[lo].y == K; hi: n, or an index whose hash is larger
+        while (lo + step < n && r2[lo + step].y == K) { lo += step; step <<= 1; }
+        uint64_t hi = min(n, lo + step);
+        while (hi - lo > 1) { const uint64_t m = (lo + hi) >> 1; if (r2[m].y == K) lo = m; else hi = m; }
+        const uint64_t c = hi - i;
+        const uint32_t mc = ro.min_count;
+        const unsigned long long e = atomicAdd(ro.n_ent, 1ULL);
+        const uint32_t pa = (mc >= 2 && (uint64_t)mc - 1 <= c) ? (uint32_t)r2[i + mc - 2].x : 0xFFFFFFFFu;
+        const uint32_t pb = (mc >= 1 && (uint64_t)mc <= c) ? (uint32_t)r2[i + mc - 1].x : 0xFFFFFFFFu;
+        ro.drec[e] = make_ulonglong2(((unsigned long long)min(c, (uint64_t)0xFFFFFFFFu) << 32) | e,
+                                     ((unsigned long long)word_of(K, ro.bloom_words) << 32) | (uint32_t)r2[i].x);
+        ro.ent[e] = make_ulonglong2(K, ((unsigned long long)pb << 32) | pa);
+        if (ro.write_sorted) ro.run_start[e] = beg + i;
+    }
 }
 
 // buckets the warps left (big_list, count in cnts[0]): 256-thread CTAs up to SM_MAX records, 1024-thread CTAs up to SB_MAX;
@@ -116,6 +281,12 @@ __global__ void diff_bits_kernel(const ulonglong2* __restrict__ rec, uint64_t n,
     if ((threadIdx.x & 31) == 0) { if (dx) atomicOr(out, dx); if (dy) atomicOr(out + 1, dy); }
 }
 
+static int sort_prefix_bits(uint64_t n, int max_bits) {
+    int P = 0;
+    while ((n >> P) > 96 && P < 22 && P < max_bits) P++;
+    return P;
+}
+
 // sorts data[0, n) in place; bits at and above `top_bit` are equal in all records.  tmp: n records of scratch.
 static void sort_range_wide(uint64_t* data, uint64_t n, int top_bit, uint64_t* tmp, int depth) {
     Context& c = ctx();
@@ -133,8 +304,7 @@ static void sort_range_wide(uint64_t* data, uint64_t n, int top_bit, uint64_t* t
         if (msb < 0) return;                                         // all records equal
         top_bit = std::min(top_bit, msb + 1);
     }
-    int P = 0;
-    while ((n >> P) > 96 && P < 22 && P < top_bit) P++;
+    int P = sort_prefix_bits(n, top_bit);
     if (P == 0) P = std::min(1, top_bit);
     const int P1 = (P + 1) / 2, P2 = P - P1;
     uint64_t* grouped = nullptr; uint64_t* off = nullptr;
@@ -146,7 +316,7 @@ static void sort_range_wide(uint64_t* data, uint64_t n, int top_bit, uint64_t* t
     uint32_t* huge_list = arena().take_n<uint32_t>(nb + 1);
     uint32_t* cnts = arena().take_n<uint32_t>(4);
     SKA_CUDA(cudaMemsetAsync(cnts, 0, 16, c.stream));
-    SKA_LAUNCH(bucket_sort_small_kernel, (nb + 7) / 8, 256, 0, data, off, nb, big_list, cnts);
+    launch_warp_sorts(data, off, nb, mid_list, big_list, cnts, nullptr);
     uint32_t n_big = 0;
     SKA_CUDA(cudaMemcpyAsync(&n_big, cnts, 4, cudaMemcpyDeviceToHost, c.stream));
     SKA_CUDA(cudaStreamSynchronize(c.stream));
@@ -155,13 +325,13 @@ static void sort_range_wide(uint64_t* data, uint64_t n, int top_bit, uint64_t* t
     for (uint32_t b : h_huge) sort_range_wide(data + 2 * h_off[b], h_off[b + 1] - h_off[b], top_bit - P, tmp, depth + 1);
 }
 
-uint64_t* sort_records_wide(const uint64_t* rec, uint64_t n, int key_bits, uint64_t* buf_a, uint64_t* buf_b, uint64_t* n_out) {
+// both entry points: group, sort the buckets (warps, then the CTA tiers and the recursion for what the warps left), and with
+// `ro` the run entries of the observation sort (ro->drec is set here: the buffer the grouping left free)
+static uint64_t* sort_impl(const uint64_t* rec, uint64_t n, int key_bits, uint64_t* buf_a, uint64_t* buf_b, uint64_t* n_out, RunsOut* ro) {
     Context& c = ctx();
     *n_out = 0;
-    if (n == 0) return buf_b;
-    // first level here (it also drops the all-ones records and tells how many are left), the rest through sort_range_wide
-    int P = 0;
-    while ((n >> P) > 96 && P < 22 && P < key_bits) P++;
+    if (n == 0) { if (ro) ro->drec = reinterpret_cast<ulonglong2*>(buf_a); return buf_b; }
+    const int P = sort_prefix_bits(n, key_bits);
     const int P1 = (P + 1) / 2, P2 = P - P1;
     uint64_t* grouped = nullptr; uint64_t* off = nullptr;
     group_wide_records(rec, n, 64 + key_bits, P1, P2, buf_a, buf_b, &grouped, &off);
@@ -172,7 +342,8 @@ uint64_t* sort_records_wide(const uint64_t* rec, uint64_t n, int key_bits, uint6
     uint32_t* huge_list = arena().take_n<uint32_t>(nb + 1);
     uint32_t* cnts = arena().take_n<uint32_t>(4);
     SKA_CUDA(cudaMemsetAsync(cnts, 0, 16, c.stream));
-    SKA_LAUNCH(bucket_sort_small_kernel, (nb + 7) / 8, 256, 0, grouped, off, nb, big_list, cnts);
+    if (ro) ro->drec = reinterpret_cast<ulonglong2*>(other);
+    launch_warp_sorts(grouped, off, nb, mid_list, big_list, cnts, ro);
     uint32_t n_big = 0; uint64_t kept = 0;
     SKA_CUDA(cudaMemcpyAsync(&n_big, cnts, 4, cudaMemcpyDeviceToHost, c.stream));
     SKA_CUDA(cudaMemcpyAsync(&kept, off + nb, 8, cudaMemcpyDeviceToHost, c.stream));
@@ -180,8 +351,37 @@ uint64_t* sort_records_wide(const uint64_t* rec, uint64_t n, int key_bits, uint6
     *n_out = kept;
     std::vector<uint32_t> h_huge; std::vector<uint64_t> h_off;
     sort_big_buckets(grouped, off, nb, big_list, mid_list, huge_list, cnts, n_big, h_huge, h_off);
-    for (uint32_t b : h_huge) sort_range_wide(grouped + 2 * h_off[b], h_off[b + 1] - h_off[b], 64 + key_bits - P, other, 1);
+    if (!h_huge.empty()) {
+        uint64_t* tmp = other;                                        // scratch of the recursion; with `ro` the other buffer holds the entries
+        if (ro) {
+            uint64_t longest = 0;
+            for (uint32_t b : h_huge) longest = std::max(longest, h_off[b + 1] - h_off[b]);
+            tmp = arena().take_n<uint64_t>(2 * longest);
+        }
+        for (uint32_t b : h_huge) sort_range_wide(grouped + 2 * h_off[b], h_off[b + 1] - h_off[b], 64 + key_bits - P, tmp, 1);
+    }
+    if (ro && n_big) SKA_LAUNCH(bucket_runs_big_kernel, n_big, 256, 0, (const uint64_t*)grouped, (const uint64_t*)off, (const uint32_t*)big_list, *ro);
     return grouped;
+}
+
+uint64_t* sort_records_wide(const uint64_t* rec, uint64_t n, int key_bits, uint64_t* buf_a, uint64_t* buf_b, uint64_t* n_out) {
+    return sort_impl(rec, n, key_bits, buf_a, buf_b, n_out, nullptr);
+}
+
+// The observations of one read set: rec = n records (x = position, y = mixed hash; all-ones = none).  They are sorted by
+// (hash, position) into one of buf_a / buf_b (returned; complete only with write_sorted), and one entry per distinct hash
+// goes to *drec (the other of the two buffers) / ent (room for n entries) / run_start (n entries, write_sorted only):
+//   drec[e] = (count << 32 | e, bloom word << 32 | first position)
+//   ent[e]  = (hash, position of observation number min_count << 32 | of number min_count - 1; 0xFFFFFFFF = no such observation)
+// *d_n_ent (device) must be zero on entry and holds the number of entries afterwards.
+uint64_t* sort_observations(const uint64_t* rec, uint64_t n, uint64_t* buf_a, uint64_t* buf_b, uint64_t* n_obs, uint64_t** drec, uint64_t* ent,
+                            uint64_t* run_start, unsigned long long* d_n_ent, uint32_t min_count, uint32_t bloom_words, bool write_sorted) {
+    RunsOut ro;
+    ro.drec = nullptr; ro.ent = reinterpret_cast<ulonglong2*>(ent); ro.run_start = run_start;
+    ro.n_ent = d_n_ent; ro.min_count = min_count; ro.bloom_words = bloom_words; ro.write_sorted = write_sorted ? 1 : 0;
+    uint64_t* sorted = sort_impl(rec, n, 64, buf_a, buf_b, n_obs, &ro);
+    *drec = reinterpret_cast<uint64_t*>(ro.drec);
+    return sorted;
 }
 
 }  // namespace ska
