@@ -463,9 +463,10 @@ def run_fastq(args, rank, world, local_rank):
         raise SystemExit(f"parity check FAILED: {parity}")
     peak, peak_src = B.measured_peak()
     n_obs = NS * 2 * NP * (RL - k + 1)
-    dom = max((s_ for s_ in stages if s_ in ("reads_hash", "obs_sort", "count_filter", "k1_extract", "sample_unique")), key=lambda s_: stages[s_])
+    dom = max((s_ for s_ in stages if s_ in ("reads_hash", "obs_group", "obs_sort", "count_filter", "k1_extract", "sample_unique")), key=lambda s_: stages[s_])
     alg = {"reads_hash": (2 * RL / (RL - k + 1) + 16, "2 B per base read (base + quality), 16 B observation record written per window"),
-           "obs_sort": (96, "16 B observation record read + written by each of two scatter passes and by the bucket sort"),
+           "obs_group": (80, "16 B observation record read by two histogram passes, read + written by two scatter passes"),
+           "obs_sort": (16 + 32 * 0.2, "16 B observation record read by the warp that sorts its bucket; a 32 B entry written per distinct hash (~0.2 per window)"),
            "count_filter": (16 + 16 + 1, "sorted observations read for the run heads, one 16 B distinct entry written per k-mer (upper bound: per window)"),
            "k1_extract": (2 * RL / (RL - k + 1) + 8, "2 B per base read, 8 B record written per accepted window"),
            "sample_unique": (40, "8 B record read + written by two scatter passes, read once by the bucket set")}[dom]

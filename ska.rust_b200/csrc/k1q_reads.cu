@@ -380,7 +380,6 @@ void build_array_from_reads(const SeqBatch& b, uint32_t k, bool rc, uint16_t min
                        (int)k, rc ? 1 : 0, (uint32_t)min_qual, qual_filter, mask, reinterpret_cast<ulonglong2*>(obs_rec), d_counter,
                        (const uint64_t*)nullptr, (uint64_t*)nullptr);
             timer().end();
-            timer().begin("obs_sort");
             // sort by (hash, position) and one entry per distinct hash: count, bloom word, first position, candidate positions
             uint64_t n_obs = 0;
             uint64_t* drec = nullptr;
@@ -388,7 +387,6 @@ void build_array_from_reads(const SeqBatch& b, uint32_t k, bool rc, uint16_t min
                                                                                           d_counter + 1, (uint32_t)min_count, (uint32_t)BLOOM_WORDS, all_later));
             unsigned long long h_cnt[2];
             SKA_CUDA(cudaMemcpyAsync(h_cnt, d_counter, 16, cudaMemcpyDeviceToHost, c.stream));
-            timer().end();
             SKA_CUDA(cudaStreamSynchronize(c.stream));
             timer().begin("count_filter");
             const uint64_t n_d = h_cnt[1];

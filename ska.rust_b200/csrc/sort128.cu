@@ -15,6 +15,7 @@
 // the sorted observations themselves are written back only for min_count == 2 / 65535, where every later one is accepted.
 // Roofline: HBM; 16 B per record moved by each of two scatters and read once by the bucket sort.
 #include <algorithm>
+#include <cstdlib>
 #include <vector>
 
 #include "common.cuh"
@@ -71,6 +72,49 @@ __device__ __forceinline__ void warp_bitonic(ulonglong2 (&v)[E], const int lane)
     }
 }
 
+// The observation sort works on 96 bits per record instead of 128: inside a bucket the top P hash bits are the bucket's, and
+// the next KH (32) bits together with the position order the records unless two different hashes of one bucket agree in all
+// of those P + 32 bits -- about once in three read sets.  So the network compares k = next 32 hash bits << 32 | position (one
+// 64-bit compare) and carries the remaining hash bits t along; the epilogue sees such a pair (neighbours with equal k-part,
+// different t) and hands the whole bucket to the full-width path.
+struct Rec96 { uint64_t k; uint32_t t; };
+__device__ __forceinline__ void cex96(Rec96& a, Rec96& b, const bool up) {
+    if ((a.k > b.k) == up) { const Rec96 x = a; a = b; b = x; }
+}
+template <int E>
+__device__ __forceinline__ void warp_bitonic96(Rec96 (&v)[E], const int lane) {
+#pragma unroll
+    for (int size = 2; size <= E; size <<= 1) {
+#pragma unroll
+        for (int stride = size >> 1; stride > 0; stride >>= 1) {
+#pragma unroll
+            for (int r = 0; r < E; r++)
+                if ((r & stride) == 0) cex96(v[r], v[r | stride], size == E ? (lane & 1) == 0 : (r & size) == 0);
+        }
+    }
+#pragma unroll 1
+    for (int size = 2 * E; size <= 32 * E; size <<= 1) {
+        const bool up = ((lane * E) & size) == 0;
+#pragma unroll 1
+        for (int lm = size / (2 * E); lm > 0; lm >>= 1) {
+            const bool keep_min = ((lane & lm) == 0) == up;
+#pragma unroll
+            for (int r = 0; r < E; r++) {
+                Rec96 o;
+                o.k = __shfl_xor_sync(FULL, v[r].k, lm);
+                o.t = __shfl_xor_sync(FULL, v[r].t, lm);
+                if ((v[r].k > o.k) == keep_min) v[r] = o;              // positions are distinct: k never ties between two records
+            }
+        }
+#pragma unroll
+        for (int stride = E / 2; stride > 0; stride >>= 1) {
+#pragma unroll
+            for (int r = 0; r < E; r++)
+                if ((r & stride) == 0) cex96(v[r], v[r | stride], up);
+        }
+    }
+}
+
 // what the run-finding epilogue writes (observation sort only)
 struct RunsOut {
     ulonglong2* drec;                // per entry: x = count << 32 | entry index, y = bloom word << 32 | first position
@@ -80,6 +124,8 @@ struct RunsOut {
     uint32_t min_count;
     uint32_t bloom_words;
     int write_sorted;
+    int prefix_bits;                 // hash bits that are the bucket index
+    int kh_bits;                     // hash bits below them that the 96-bit network compares (32; fewer only to test the fallback)
 };
 __device__ __forceinline__ uint32_t word_of(uint64_t mixed, uint32_t words) { return (uint32_t)__umul64hi(mixed, (uint64_t)words); }
 
@@ -87,15 +133,19 @@ constexpr int SW_WARPS = 8;                  // warps per CTA of the warp-sort k
 
 // the runs of one sorted bucket, from its hashes and positions in shared memory (record i at s_key[i] / s_pos[i]): one entry
 // per run.  Chunks of 32 records, last chunk first, so that every run head knows where the next run starts.
-__device__ __forceinline__ void warp_emit_runs(const uint64_t* __restrict__ s_key, const uint32_t* __restrict__ s_pos, const uint32_t n,
+__device__ __forceinline__ bool warp_emit_runs(const uint64_t* __restrict__ s_key, const uint32_t* __restrict__ s_pos, const uint32_t n,
                                                const uint64_t beg, const int lane, const RunsOut& ro) {
     const uint32_t chunks = (n + 31) / 32;
+    const int amb_shift = 64 - ro.kh_bits;                                // ((Ka ^ Kb) << P) >> amb_shift == 0: equal in every compared bit
     uint32_t total = 0;
+    bool ambiguous = false;
     for (uint32_t j = 0; j < chunks; j++) {
         const uint32_t i = j * 32 + lane;
         const bool head = i < n && (i == 0 || s_key[i - 1] != s_key[i]);
+        if (head && i > 0 && (((s_key[i - 1] ^ s_key[i]) << ro.prefix_bits) >> amb_shift) == 0) ambiguous = true;
         total += __popc(__ballot_sync(FULL, head));
     }
+    if (__any_sync(FULL, ambiguous)) return false;
     unsigned long long base = 0;
     if (lane == 0) base = atomicAdd(ro.n_ent, (unsigned long long)total);
     base = __shfl_sync(FULL, base, 0);
@@ -120,25 +170,46 @@ __device__ __forceinline__ void warp_emit_runs(const uint64_t* __restrict__ s_ke
         }
         if (m) next_head = j * 32 + (uint32_t)__ffs(m) - 1;
     }
+    return true;
 }
 
 template <int E, bool RUNS>
 __device__ __forceinline__ void warp_sort_bucket(ulonglong2* __restrict__ r2, const uint32_t n, const int lane, uint64_t* __restrict__ s_key,
-                                                 uint32_t* __restrict__ s_pos, const bool write_sorted) {
-    ulonglong2 v[E];
+                                                 uint32_t* __restrict__ s_pos, const bool write_sorted, const uint32_t bucket, const int P, const int KH) {
+    if (!RUNS) {
+        ulonglong2 v[E];
+#pragma unroll
+        for (int r = 0; r < E; r++) {
+            const uint32_t i = lane * E + r;
+            v[r] = i < n ? r2[i] : make_ulonglong2(~0ULL, ~0ULL);
+        }
+        warp_bitonic<E>(v, lane);
+#pragma unroll
+        for (int r = 0; r < E; r++) { const uint32_t i = lane * E + r; if (i < n) r2[i] = v[r]; }
+        return;
+    }
+    Rec96 v[E];
 #pragma unroll
     for (int r = 0; r < E; r++) {
         const uint32_t i = lane * E + r;
-        v[r] = i < n ? r2[i] : make_ulonglong2(~0ULL, ~0ULL);
+        if (i < n) {
+            const ulonglong2 x = r2[i];                                   // x = position, y = hash
+            const uint64_t rem = x.y << P;
+            v[r].k = ((rem >> (64 - KH)) << 32) | (uint32_t)x.x;
+            v[r].t = (uint32_t)((rem << KH) >> 32);
+        } else { v[r].k = ~0ULL; v[r].t = ~0u; }
     }
-    warp_bitonic<E>(v, lane);
-    if (!RUNS || write_sorted) {
+    warp_bitonic96<E>(v, lane);
+    const uint64_t top = P ? (uint64_t)bucket << (64 - P) : 0ULL;
 #pragma unroll
-        for (int r = 0; r < E; r++) { const uint32_t i = lane * E + r; if (i < n) r2[i] = v[r]; }
-    }
-    if (RUNS) {
-#pragma unroll
-        for (int r = 0; r < E; r++) { const uint32_t i = lane * E + r; if (i < n) { s_key[i] = v[r].y; s_pos[i] = (uint32_t)v[r].x; } }
+    for (int r = 0; r < E; r++) {
+        const uint32_t i = lane * E + r;
+        if (i < n) {
+            const uint64_t rem = ((v[r].k >> 32) << (64 - KH)) | ((uint64_t)v[r].t << (32 - KH));
+            const uint64_t K = top | (P ? rem >> P : rem);
+            s_key[i] = K; s_pos[i] = (uint32_t)v[r].k;
+            if (write_sorted) r2[i] = make_ulonglong2((unsigned long long)(uint32_t)v[r].k, K);
+        }
     }
 }
 
@@ -148,7 +219,8 @@ __device__ __forceinline__ void warp_sort_bucket(ulonglong2* __restrict__ r2, co
 template <int EMAX, bool RUNS>
 __global__ void __launch_bounds__(32 * SW_WARPS, EMAX == 8 ? 3 : 2)
 bucket_sort_warp_kernel(uint64_t* __restrict__ rec, const uint64_t* __restrict__ off, uint32_t n_buckets, const uint32_t* __restrict__ list,
-                        const uint32_t* __restrict__ n_list, uint32_t* __restrict__ over_list, uint32_t* __restrict__ n_over, RunsOut ro) {
+                        const uint32_t* __restrict__ n_list, uint32_t* __restrict__ over_list, uint32_t* __restrict__ n_over,
+                        uint32_t* __restrict__ big_list, uint32_t* __restrict__ n_big, RunsOut ro) {
     __shared__ uint64_t s_key_all[RUNS ? SW_WARPS * 32 * EMAX : 1];
     __shared__ uint32_t s_pos_all[RUNS ? SW_WARPS * 32 * EMAX : 1];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -163,14 +235,16 @@ bucket_sort_warp_kernel(uint64_t* __restrict__ rec, const uint64_t* __restrict__
         const uint32_t n = (uint32_t)(end - beg);
         ulonglong2* r2 = reinterpret_cast<ulonglong2*>(rec) + beg;
         const bool ws = RUNS && ro.write_sorted;
-        if (EMAX == 16) warp_sort_bucket<16, RUNS>(r2, n, lane, s_key, s_pos, ws);
-        else if (n <= 32) warp_sort_bucket<1, RUNS>(r2, n, lane, s_key, s_pos, ws);
-        else if (n <= 64) warp_sort_bucket<2, RUNS>(r2, n, lane, s_key, s_pos, ws);
-        else if (n <= 128) warp_sort_bucket<4, RUNS>(r2, n, lane, s_key, s_pos, ws);
-        else warp_sort_bucket<8, RUNS>(r2, n, lane, s_key, s_pos, ws);
+        const int P = ro.prefix_bits, KH = ro.kh_bits;
+        if (EMAX == 16) warp_sort_bucket<16, RUNS>(r2, n, lane, s_key, s_pos, ws, b, P, KH);
+        else if (n <= 32) warp_sort_bucket<1, RUNS>(r2, n, lane, s_key, s_pos, ws, b, P, KH);
+        else if (n <= 64) warp_sort_bucket<2, RUNS>(r2, n, lane, s_key, s_pos, ws, b, P, KH);
+        else if (n <= 128) warp_sort_bucket<4, RUNS>(r2, n, lane, s_key, s_pos, ws, b, P, KH);
+        else warp_sort_bucket<8, RUNS>(r2, n, lane, s_key, s_pos, ws, b, P, KH);
         if (RUNS) {
             __syncwarp();
-            warp_emit_runs(s_key, s_pos, n, beg, lane, ro);
+            // two hashes that the 96-bit order cannot tell apart: the full-width path sorts this bucket again
+            if (!warp_emit_runs(s_key, s_pos, n, beg, lane, ro) && lane == 0) big_list[atomicAdd(n_big, 1u)] = b;
             __syncwarp();
         }
     }
@@ -183,11 +257,11 @@ static void launch_warp_sorts(uint64_t* data, const uint64_t* off, uint32_t nb, 
     const unsigned g8 = (unsigned)std::min<uint64_t>(((uint64_t)nb + SW_WARPS - 1) / SW_WARPS, (uint64_t)c.sm_count * 3 * 8);
     const unsigned g16 = (unsigned)c.sm_count * 2;
     if (ro) {
-        SKA_LAUNCH((bucket_sort_warp_kernel<8, true>), g8, 32 * SW_WARPS, 0, data, off, nb, (const uint32_t*)nullptr, (const uint32_t*)nullptr, list16, cnts + 3, *ro);
-        SKA_LAUNCH((bucket_sort_warp_kernel<16, true>), g16, 32 * SW_WARPS, 0, data, off, nb, (const uint32_t*)list16, (const uint32_t*)(cnts + 3), big_list, cnts, *ro);
+        SKA_LAUNCH((bucket_sort_warp_kernel<8, true>), g8, 32 * SW_WARPS, 0, data, off, nb, (const uint32_t*)nullptr, (const uint32_t*)nullptr, list16, cnts + 3, big_list, cnts, *ro);
+        SKA_LAUNCH((bucket_sort_warp_kernel<16, true>), g16, 32 * SW_WARPS, 0, data, off, nb, (const uint32_t*)list16, (const uint32_t*)(cnts + 3), big_list, cnts, big_list, cnts, *ro);
     } else {
-        SKA_LAUNCH((bucket_sort_warp_kernel<8, false>), g8, 32 * SW_WARPS, 0, data, off, nb, (const uint32_t*)nullptr, (const uint32_t*)nullptr, list16, cnts + 3, RunsOut{});
-        SKA_LAUNCH((bucket_sort_warp_kernel<16, false>), g16, 32 * SW_WARPS, 0, data, off, nb, (const uint32_t*)list16, (const uint32_t*)(cnts + 3), big_list, cnts, RunsOut{});
+        SKA_LAUNCH((bucket_sort_warp_kernel<8, false>), g8, 32 * SW_WARPS, 0, data, off, nb, (const uint32_t*)nullptr, (const uint32_t*)nullptr, list16, cnts + 3, big_list, cnts, RunsOut{});
+        SKA_LAUNCH((bucket_sort_warp_kernel<16, false>), g16, 32 * SW_WARPS, 0, data, off, nb, (const uint32_t*)list16, (const uint32_t*)(cnts + 3), big_list, cnts, big_list, cnts, RunsOut{});
     }
 }
 
@@ -334,7 +408,9 @@ static uint64_t* sort_impl(const uint64_t* rec, uint64_t n, int key_bits, uint64
     const int P = sort_prefix_bits(n, key_bits);
     const int P1 = (P + 1) / 2, P2 = P - P1;
     uint64_t* grouped = nullptr; uint64_t* off = nullptr;
+    if (ro) timer().begin("obs_group");                                // the observation sort reports its two halves as stages
     group_wide_records(rec, n, 64 + key_bits, P1, P2, buf_a, buf_b, &grouped, &off);
+    if (ro) { timer().end(); timer().begin("obs_sort"); }
     uint64_t* other = grouped == buf_a ? buf_b : buf_a;
     const uint32_t nb = 1u << P;
     uint32_t* big_list = arena().take_n<uint32_t>(nb + 1);
@@ -342,7 +418,12 @@ static uint64_t* sort_impl(const uint64_t* rec, uint64_t n, int key_bits, uint64
     uint32_t* huge_list = arena().take_n<uint32_t>(nb + 1);
     uint32_t* cnts = arena().take_n<uint32_t>(4);
     SKA_CUDA(cudaMemsetAsync(cnts, 0, 16, c.stream));
-    if (ro) ro->drec = reinterpret_cast<ulonglong2*>(other);
+    if (ro) {
+        ro->drec = reinterpret_cast<ulonglong2*>(other);
+        ro->prefix_bits = P;
+        const char* e = getenv("SKA_SORT_KH_BITS");                     // tests: fewer compared bits, so that the fallback does run
+        ro->kh_bits = std::min(32, std::max(e ? atoi(e) : 32, 32 - P));
+    }
     launch_warp_sorts(grouped, off, nb, mid_list, big_list, cnts, ro);
     uint32_t n_big = 0; uint64_t kept = 0;
     SKA_CUDA(cudaMemcpyAsync(&n_big, cnts, 4, cudaMemcpyDeviceToHost, c.stream));
@@ -361,6 +442,7 @@ static uint64_t* sort_impl(const uint64_t* rec, uint64_t n, int key_bits, uint64
         for (uint32_t b : h_huge) sort_range_wide(grouped + 2 * h_off[b], h_off[b + 1] - h_off[b], 64 + key_bits - P, tmp, 1);
     }
     if (ro && n_big) SKA_LAUNCH(bucket_runs_big_kernel, n_big, 256, 0, (const uint64_t*)grouped, (const uint64_t*)off, (const uint32_t*)big_list, *ro);
+    if (ro) timer().end();
     return grouped;
 }
 
@@ -378,6 +460,7 @@ uint64_t* sort_observations(const uint64_t* rec, uint64_t n, uint64_t* buf_a, ui
                             uint64_t* run_start, unsigned long long* d_n_ent, uint32_t min_count, uint32_t bloom_words, bool write_sorted) {
     RunsOut ro;
     ro.drec = nullptr; ro.ent = reinterpret_cast<ulonglong2*>(ent); ro.run_start = run_start;
+    ro.prefix_bits = 0; ro.kh_bits = 32;
     ro.n_ent = d_n_ent; ro.min_count = min_count; ro.bloom_words = bloom_words; ro.write_sorted = write_sorted ? 1 : 0;
     uint64_t* sorted = sort_impl(rec, n, 64, buf_a, buf_b, n_obs, &ro);
     *drec = reinterpret_cast<uint64_t*>(ro.drec);

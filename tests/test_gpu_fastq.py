@@ -137,6 +137,22 @@ def test_fastq_heavy_repeats(min_count):
             assert g.dims()["n_rows"] > 0
 
 
+def test_fastq_sort_fallback_for_ambiguous_buckets(monkeypatch):
+    """the 96-bit observation sort orders a bucket by (32 hash bits, position); two hashes that agree in those bits send the
+    bucket to the full-width path.  With only 12 compared bits that happens in most buckets: the result must not change."""
+    from ska_rust_b200 import synth
+    genome = synth.star_genomes(1, 100_000, seed=0x5CA20006)[0]
+    gs, os_ = make_reads_sample(genome, 120_000, 0.01, 9)            # 3.6e7 windows -> 19 prefix bits, 12 + 32 >= 64 - 19
+    q = S.QualOpts(min_count=3, min_qual=20, qual_filter="strict")
+    o = O.OracleArray.build([os_], ["r"], k=31, rc=True, min_count=3, min_qual=20, qual_filter="strict")
+    for bits in ("12", None):
+        if bits:
+            monkeypatch.setenv("SKA_SORT_KH_BITS", bits)
+        else:
+            monkeypatch.delenv("SKA_SORT_KH_BITS")
+        same(S.build_from_samples([gs], ["r"], 31, True, q), o)
+
+
 def test_fastq_samples_shard_by_rows():
     """FASTQ samples through the multi-GPU "rows" path (every 'rank' builds its own reads with the count filter, the
     owners join the partial rows), emulated on one GPU with the exchange replaced by copies: equals the oracle's array"""
