@@ -183,6 +183,31 @@ int skagpu_merge_partial_rows_dev(const void* keys_dev, const void* variants_dev
                                   const uint64_t* run_rows, const uint32_t* run_cols, const uint32_t* run_col_base,
                                   uint64_t n_samples_total, uint32_t k, int rc, ska_array_t** out);
 
+/* ---- the same exchange with the library holding the communicator (csrc/comm.cu): no torch, no host transport ---------
+ * For hosts that drive several GPUs themselves -- the C++ `ska --gpus N` (one thread per GPU) or a Rust binding with one
+ * process per GPU.  A host thread is bound to one device by skagpu_set_device; every call it makes afterwards (builds,
+ * filters, exports, these collectives) runs on that device, so N threads of one process drive N GPUs.
+ *   skagpu_comm_unique_id   rank 0 draws the NCCL id (SKAGPU_COMM_ID_BYTES bytes) and hands it to the other ranks by
+ *                           whatever the host has (shared memory between threads, MPI, a file, torchrun's store);
+ *   skagpu_comm_init        every rank, after skagpu_set_device.  NCCL is dlopen'ed here (libnccl.so.2);
+ *   skagpu_exchange_rows    collective.  `local` = the array of this rank's samples (columns [sample_base, sample_base +
+ *                           its samples) of the whole job), built by any of the build entry points.  Steps 2-4 above inside
+ *                           the library: all-gather of the key histograms, owners cut for equal row counts, ONE grouped
+ *                           send/recv of every peer's keys + variant rows + counts over NVLink, join on the key.
+ *                           -> *slab: this rank's ascending key range with all n_samples_total columns; the slabs of ranks
+ *                           0 .. world-1 concatenated are the single-GPU array (MergeSkaDict::merge, merge_ska_dict.rs:119-151).
+ *                           stats (may be NULL): rows sent, rows received, bytes sent, rows of the slab;
+ *   skagpu_allreduce_u64    sums host integers over the ranks (the distance counters and the constant-site count of
+ *                           generic_modes.rs:136-189 on slabs);
+ *   skagpu_plan_owners      the owner cut on its own (host arithmetic, no device): cuts[world + 1] region indices. */
+#define SKAGPU_COMM_ID_BYTES 128
+int skagpu_comm_unique_id(uint8_t* id);
+int skagpu_comm_init(const uint8_t* id, int world, int rank);
+int skagpu_comm_destroy(void);
+int skagpu_exchange_rows(const ska_array_t* local, uint64_t sample_base, uint64_t n_samples_total, ska_array_t** slab, uint64_t* stats);
+int skagpu_allreduce_u64(uint64_t* values, size_t n);
+int skagpu_plan_owners(const uint64_t* region_rows, uint32_t n_regions, int world, uint64_t* cuts);
+
 /* Per-pair partial sums of variant_dist (merge_ska_array.rs:599-620) over this array's rows, 4 x u64 per
  * pair {mismatches, matches, dist_int, n_both}: integers, so row shards add up exactly (all-reduce);
  * distance = dist_int (filt_ambig) or n_both - dist_int/36 (allow-ambiguous), matches += constant. */

@@ -37,6 +37,8 @@ EXPORTS = [
     "skagpu_pack_bases", "skagpu_build_packed", "skagpu_seqbatch_upload_packed", "skagpu_export_transposed_async",
     "skagpu_export_wait", "skagpu_seqbatch_upload_packed_async", "skagpu_merge_arrays", "skagpu_delete_samples", "skagpu_weed",
     "skagpu_map", "skagpu_map_dims", "skagpu_map_export", "skagpu_map_free", "skagpu_kmer_count_hist",
+    "skagpu_comm_unique_id", "skagpu_comm_init", "skagpu_comm_destroy", "skagpu_exchange_rows", "skagpu_allreduce_u64",
+    "skagpu_plan_owners",
 ]
 
 
@@ -103,6 +105,11 @@ def lib():
         L.skagpu_map_export.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.skagpu_map_free.argtypes = [C.c_void_p]
         L.skagpu_kmer_count_hist.argtypes = [C.c_void_p, C.c_uint32, C.c_int, C.c_void_p]
+        L.skagpu_comm_unique_id.argtypes = [C.c_void_p]
+        L.skagpu_comm_init.argtypes = [C.c_void_p, C.c_int, C.c_int]
+        L.skagpu_exchange_rows.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.c_void_p, C.c_void_p]
+        L.skagpu_allreduce_u64.argtypes = [C.c_void_p, C.c_size_t]
+        L.skagpu_plan_owners.argtypes = [C.c_void_p, C.c_uint32, C.c_int, C.c_void_p]
         L.skagpu_pack_bases.restype = None
         L.skagpu_pack_bases.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.c_void_p, C.c_void_p]
         L.skagpu_build_packed.argtypes = [C.c_void_p, C.c_size_t, C.c_uint32, C.c_int, C.c_void_p]
@@ -561,6 +568,49 @@ def kmer_count_hist(sample, k, rc=True):
     hist = np.zeros(1000, dtype=np.uint64)
     _check(lib().skagpu_kmer_count_hist(_inputs_array([sample]), k, int(rc), hist.ctypes.data))
     return hist
+
+
+# ---- the library's own multi-GPU transport (csrc/comm.cu): one host thread or process per GPU, no torch involved
+COMM_ID_BYTES = 128
+
+
+def comm_unique_id():
+    """rank 0: the NCCL id every rank passes to comm_init (hand it over by any means: a shared variable, a file, a store)"""
+    buf = (C.c_uint8 * COMM_ID_BYTES)()
+    _check(lib().skagpu_comm_unique_id(buf))
+    return bytes(buf)
+
+
+def comm_init(comm_id, world, rank):
+    buf = (C.c_uint8 * COMM_ID_BYTES).from_buffer_copy(comm_id)
+    _check(lib().skagpu_comm_init(buf, world, rank))
+
+
+def comm_destroy():
+    _check(lib().skagpu_comm_destroy())
+
+
+def exchange_rows(local, sample_base, names_all):
+    """collective: the array of this rank's samples -> this rank's slab of the whole job's array (skagpu_exchange_rows).
+    -> (slab, {rows_sent, rows_received, bytes_sent, slab_rows})"""
+    h = C.c_void_p()
+    st = (C.c_uint64 * 4)()
+    _check(lib().skagpu_exchange_rows(local._h, sample_base, len(names_all), C.byref(h), st))
+    return MergeSkaArray(h, list(names_all), local.ska_version), dict(zip(("rows_sent", "rows_received", "bytes_sent", "slab_rows"), map(int, st)))
+
+
+def allreduce_u64(values):
+    v = np.ascontiguousarray(values, dtype=np.uint64).copy()
+    _check(lib().skagpu_allreduce_u64(v.ctypes.data, v.size))
+    return v
+
+
+def plan_owners(region_rows, world):
+    """the owner cut of the row exchange (host arithmetic only): cuts[world + 1] region indices"""
+    c = np.ascontiguousarray(region_rows, dtype=np.uint64)
+    cuts = np.zeros(world + 1, dtype=np.uint64)
+    _check(lib().skagpu_plan_owners(c.ctypes.data, len(c), world, cuts.ctypes.data))
+    return cuts.astype(np.int64)
 
 
 def merge_arrays(a, b):

@@ -12,8 +12,59 @@
 
 namespace ska {
 
-static Context g_ctx;
-Context& ctx() { return g_ctx; }
+// ---- per-device state.  A host thread is bound to one device (skagpu_set_device; threads that never call it use the device
+// the process chose first): one process per GPU under torchrun, or one thread per GPU inside one process (`ska --gpus N`).
+namespace {
+struct DevCache {
+    std::mutex mu;
+    std::map<void*, size_t> live;                       // block -> capacity
+    std::multimap<size_t, void*> free_blocks;           // capacity -> block
+    size_t cached_bytes = 0;
+};
+struct PendingExport { DevBuf<uint8_t> t; cudaEvent_t done; };      // a transposed alignment on its way to the host (skagpu_export_transposed_async)
+struct DeviceState {
+    Context ctx;
+    Arena arena;
+    StageTimer timer;
+    DevCache cache;
+    std::vector<std::unique_ptr<PendingExport>> exports;
+    cudaStream_t d2h_stream = nullptr;
+    void* comm = nullptr;                               // multi-GPU communicator of the thread bound to this device (comm.cu)
+};
+constexpr int MAX_DEVICES = 64;
+DeviceState* g_dev[MAX_DEVICES];                        // created on first use, never destroyed: buffers may outlive static teardown
+std::mutex g_dev_mu;
+int g_default_dev = -1;
+thread_local int t_dev = -1;
+thread_local DeviceState* t_state = nullptr;
+DeviceState& state_of(int d) {
+    if (d < 0 || d >= MAX_DEVICES) throw Error("bad device index " + std::to_string(d));
+    std::lock_guard<std::mutex> lock(g_dev_mu);
+    if (!g_dev[d]) { g_dev[d] = new DeviceState(); g_dev[d]->ctx.device = d; }
+    return *g_dev[d];
+}
+DeviceState& dev_state() {
+    if (t_state) return *t_state;
+    int d = t_dev;
+    if (d < 0) {
+        std::lock_guard<std::mutex> lock(g_dev_mu);
+        if (g_default_dev < 0) g_default_dev = 0;
+        d = g_default_dev;
+    }
+    t_state = &state_of(d);
+    return *t_state;
+}
+}  // namespace
+void bind_thread_to_device(int device) {
+    {
+        std::lock_guard<std::mutex> lock(g_dev_mu);
+        if (g_default_dev < 0) g_default_dev = device;
+    }
+    t_dev = device;
+    t_state = &state_of(device);
+}
+void*& comm_slot() { return dev_state().comm; }
+Context& ctx() { return dev_state().ctx; }
 void Context::ensure() {
     static std::mutex mu;                                   // a host may create the context on a helper thread while it parses its input
     std::lock_guard<std::mutex> lock(mu);
@@ -39,15 +90,9 @@ void Context::ensure() {
     init = true;
 }
 
-// ---- DevBuf's allocator: cudaMalloc'ed blocks, cached
+// ---- DevBuf's allocator: cudaMalloc'ed blocks, cached per device
 namespace {
-struct DevCache {
-    std::mutex mu;
-    std::map<void*, size_t> live;                       // block -> capacity
-    std::multimap<size_t, void*> free_blocks;           // capacity -> block
-    size_t cached_bytes = 0;
-};
-DevCache& dev_cache() { static DevCache* c = new DevCache(); return *c; }   // never destroyed: buffers may outlive static teardown
+DevCache& dev_cache() { return dev_state().cache; }
 }  // namespace
 void* dev_alloc(size_t bytes) {
     DevCache& dc = dev_cache();
@@ -74,19 +119,26 @@ void* dev_alloc(size_t bytes) {
     dc.live[p] = want;
     return p;
 }
-void dev_free(void* p) {
-    if (!p) return;
-    DevCache& dc = dev_cache();
+static bool cache_take_back(DevCache& dc, void* p) {
     std::lock_guard<std::mutex> lock(dc.mu);
     auto it = dc.live.find(p);
-    if (it == dc.live.end()) return;
+    if (it == dc.live.end()) return false;
     dc.free_blocks.emplace(it->second, p);
     dc.cached_bytes += it->second;
     dc.live.erase(it);
+    return true;
+}
+void dev_free(void* p) {
+    if (!p) return;
+    if (cache_take_back(dev_cache(), p)) return;
+    for (int d = 0; d < MAX_DEVICES; d++) {               // a handle released by a thread bound to another device (ska --gpus N)
+        DeviceState* st;
+        { std::lock_guard<std::mutex> lock(g_dev_mu); st = g_dev[d]; }
+        if (st && cache_take_back(st->cache, p)) return;
+    }
 }
 
-static Arena g_arena;
-Arena& arena() { return g_arena; }
+Arena& arena() { return dev_state().arena; }
 void Arena::reset() {
     if (slabs.size() > 1) {             // the previous build had to grow: merge into one slab of the total size
         size_t total = 0;
@@ -113,8 +165,7 @@ void Arena::release_all() {
     slabs.clear();
 }
 
-static StageTimer g_timer;
-StageTimer& timer() { return g_timer; }
+StageTimer& timer() { return dev_state().timer; }
 void StageTimer::clear() {
     for (auto& s : stages) { cudaEventDestroy(s.beg); cudaEventDestroy(s.end); }
     stages.clear();
@@ -467,8 +518,7 @@ const char* skagpu_last_error(void) { return g_err.c_str(); }
 
 int skagpu_set_device(int device) {
     API_TRY
-    if (ctx().init && ctx().device != device) throw Error("device already initialised; one process per GPU");
-    ctx().device = device;
+    bind_thread_to_device(device);                        // one device per host thread (one process per GPU, or one thread per GPU)
     ctx().ensure();
     return 0;
     API_CATCH
@@ -748,9 +798,8 @@ push_to_host_kernel(const uint4* __restrict__ src, uint4* __restrict__ dst, size
     if (blockIdx.x == 0 && threadIdx.x < n_tail) dst_tail[threadIdx.x] = src_tail[threadIdx.x];
 }
 
-struct PendingExport { DevBuf<uint8_t> t; cudaEvent_t done; };
-static std::vector<std::unique_ptr<PendingExport>> g_exports;
-static cudaStream_t g_d2h_stream = nullptr;
+#define g_exports (dev_state().exports)
+#define g_d2h_stream (dev_state().d2h_stream)
 static void reap_exports(bool all) {
     Context& c = ctx();
     for (size_t i = 0; i < g_exports.size();) {
@@ -936,6 +985,54 @@ int skagpu_merge_partial_rows_dev(const void* keys_dev, const void* variants_dev
     API_CATCH
 }
 
+// ---- the library's own communicator (comm.cu)
+int skagpu_comm_unique_id(uint8_t* id) {
+    API_TRY
+    if (!id) throw Error("null id");
+    comm_unique_id(id);
+    return 0;
+    API_CATCH
+}
+int skagpu_comm_init(const uint8_t* id, int world, int rank) {
+    API_TRY
+    if (!id) throw Error("null id");
+    comm_init(id, world, rank);
+    return 0;
+    API_CATCH
+}
+int skagpu_comm_destroy(void) {
+    API_TRY
+    comm_destroy();
+    return 0;
+    API_CATCH
+}
+int skagpu_exchange_rows(const ska_array_t* local, uint64_t sample_base, uint64_t n_samples_total, ska_array_t** slab, uint64_t* stats) {
+    API_TRY
+    if (!local || !slab) throw Error("null argument");
+    *slab = nullptr;
+    ctx().ensure();
+    std::unique_ptr<ska_array> h(new ska_array());
+    exchange_partial_rows(local->a, sample_base, n_samples_total, h->a, stats);
+    *slab = h.release();
+    return 0;
+    API_CATCH
+}
+int skagpu_allreduce_u64(uint64_t* values, size_t n) {
+    API_TRY
+    if (!values && n) throw Error("null argument");
+    ctx().ensure();
+    allreduce_u64(values, n);
+    return 0;
+    API_CATCH
+}
+int skagpu_plan_owners(const uint64_t* region_rows, uint32_t n_regions, int world, uint64_t* cuts) {
+    API_TRY
+    if (!region_rows || !cuts || world < 1) throw Error("bad argument");
+    plan_owners(region_rows, n_regions, world, cuts);
+    return 0;
+    API_CATCH
+}
+
 int skagpu_merge_prefix_bits(uint64_t n_records_total, uint32_t k, uint64_t n_samples_total) {
     try { return make_part_plan(k, merge_prefix_bits(n_records_total, k, n_samples_total), n_samples_total).P; }
     catch (std::exception& e) { g_err = e.what(); return -1; }
@@ -1083,7 +1180,7 @@ uint64_t skagpu_launch_count(void) { return ctx().launches; }
 
 int skagpu_stream_timer(int op, float* ms) {
     API_TRY
-    static cudaEvent_t e0 = nullptr, e1 = nullptr;
+    static thread_local cudaEvent_t e0 = nullptr, e1 = nullptr;      // per host thread: a thread drives one device
     Context& c = ctx();
     c.ensure();
     if (!e0) { SKA_CUDA(cudaEventCreate(&e0)); SKA_CUDA(cudaEventCreate(&e1)); }

@@ -36,6 +36,8 @@ struct Context {
     void ensure();
 };
 Context& ctx();
+void bind_thread_to_device(int device);   // the calling host thread works on this device from now on (api.cu)
+void*& comm_slot();                       // the multi-GPU communicator of the calling thread's device (comm.cu)
 
 // Every kernel launch goes through this so the launch count claimed in bench.py is real.
 #define SKA_LAUNCH(kernel, grid, block, smem, ...)                         \
@@ -175,6 +177,15 @@ uint64_t* sort_records_wide(const uint64_t* rec, uint64_t n, int key_bits, uint6
 // the observation sort of the count filter: sorted (hash, position) records + one entry per distinct hash (see sort128.cu)
 uint64_t* sort_observations(const uint64_t* rec, uint64_t n, uint64_t* buf_a, uint64_t* buf_b, uint64_t* n_obs, uint64_t** drec, uint64_t* ent,
                             uint64_t* run_start, unsigned long long* d_n_ent, uint32_t min_count, uint32_t bloom_words, bool write_sorted);
+// comm.cu: the library's own multi-GPU transport (NCCL, dlopen'ed)
+void comm_unique_id(uint8_t* id);
+void comm_init(const uint8_t* id, int world, int rank);
+void comm_destroy();
+int comm_world();
+int comm_rank();
+void plan_owners(const uint64_t* counts, uint32_t n_regions, int world, uint64_t* cuts);
+void allreduce_u64(uint64_t* h_vals, size_t n);
+void exchange_partial_rows(const Array& local, uint64_t sample_base, uint64_t n_samples_total, Array& slab, uint64_t* stats);
 // dedup.cu: one sample's K1 records -> its distinct records (see there)
 uint64_t* unique_sample_records(uint64_t* rec, uint64_t n, uint32_t k, int prefix_bits, uint64_t* n_out);
 // merge.cu

@@ -8,6 +8,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <strings.h>
 #include <thread>
 #include <vector>
 
@@ -32,6 +33,13 @@ static Args parse(int argc, char** argv, int start, const std::vector<std::strin
     for (int i = start; i < argc; i++) {
         std::string s = argv[i];
         if (s == "-v" || s == "--verbose") { a.opts.emplace_back("--verbose", "1"); continue; }
+        if (s == "--gpus") {                                  // not in the reference: GPUs of this node to shard a build over
+            if (i + 1 >= argc) usage_error("a value is required for '--gpus'");
+            int g = atoi(argv[++i]);
+            if (g < 1 || g > 64) usage_error("invalid value for '--gpus <N>'");
+            ska::set_gpus(g);
+            continue;
+        }
         bool is_val = false, is_flag = false;
         for (auto& v : value_opts) if (s == v) is_val = true;
         for (auto& f : flag_opts) if (s == f) is_flag = true;
@@ -81,6 +89,10 @@ int main(int argc, char** argv) {
     if (argc < 2) usage_error("a subcommand is required");
     const std::string cmd = argv[1];
     fprintf(stderr, "SKA: Split K-mer Analysis (the alignment-free aligner)\n");
+    if (const char* g = getenv("SKA_GPUS")) ska::set_gpus(atoi(g));
+    // stdout carries alignments and distances: NCCL's banner must not land there (NCCL honours NCCL_DEBUG_FILE only above VERSION)
+    setenv("NCCL_DEBUG_FILE", "/dev/stderr", 0);
+    if (const char* d = getenv("NCCL_DEBUG")) if (!strcasecmp(d, "VERSION")) setenv("NCCL_DEBUG", "WARN", 1);
     auto start = std::chrono::steady_clock::now();
     // CUDA context creation (~0.4 s on a B200) runs beside the host's first phase (file parsing, .skf decoding)
     std::thread cuda_init;

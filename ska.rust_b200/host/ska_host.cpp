@@ -6,6 +6,7 @@
 #include <cmath>
 #include <cstring>
 #include <fstream>
+#include <functional>
 #include <limits>
 #include <regex>
 #include <sstream>
@@ -485,6 +486,73 @@ std::string CoverageHistogram::plot_hist() const {
 }
 
 // ------------------------------------------------------------------------------------------ build_and_merge
+static int g_gpus = 1;
+void set_gpus(int n) { g_gpus = std::max(1, n); }
+int gpus() { return g_gpus; }
+
+// `ska build --gpus N`: one host thread per GPU, each bound to its device (skagpu_set_device).  Rank r builds the array of its
+// contiguous share of the samples, the library exchanges partial rows over NVLink (skagpu_exchange_rows) and every rank ends
+// with an ascending key range of the whole array; the slabs concatenated in rank order ARE the single-GPU array, which is
+// put back on device 0 so that everything downstream (save, align, distance) is unchanged.
+// build_local(r, lo, hi, &h): builds samples [lo, hi) on the calling thread's device, returns an error text or "".
+static MergeSkaArray build_sharded(size_t n, const std::vector<std::string>& names, int world,
+                                   const std::function<std::string(int, size_t, size_t, ska_array_t**)>& build_local) {
+    uint8_t id[SKAGPU_COMM_ID_BYTES];
+    check(skagpu_set_device(0));
+    check(skagpu_comm_unique_id(id));
+    std::vector<skf::Array> slabs(world);
+    std::vector<std::string> errors(world);
+    auto rank_main = [&](int r) {
+        auto err = [&](const char* what) { errors[r] = std::string(what) + ": " + skagpu_last_error(); };
+        if (skagpu_set_device(r)) return err("device");
+        if (skagpu_comm_init(id, world, r)) return err("communicator");
+        const size_t lo = n * (size_t)r / world, hi = n * (size_t)(r + 1) / world;
+        ska_array_t* local = nullptr;
+        std::string e = build_local(r, lo, hi, &local);
+        uint64_t failed = e.empty() ? 0 : 1;                          // a rank that failed still joins the collectives
+        if (skagpu_allreduce_u64(&failed, 1)) { err("status exchange"); failed = 1; }
+        if (failed) { if (!e.empty()) errors[r] = e; if (local) skagpu_free(local); skagpu_comm_destroy(); return; }
+        ska_array_t* slab = nullptr;
+        uint64_t stats[4];
+        if (skagpu_exchange_rows(local, lo, n, &slab, stats)) { err("row exchange"); skagpu_free(local); skagpu_comm_destroy(); return; }
+        skagpu_free(local);
+        if (getenv("SKA_TIMING"))
+            fprintf(stderr, "[gpu %d] samples [%zu, %zu): %llu rows sent, %llu received, slab of %llu rows\n", r, lo, hi,
+                    (unsigned long long)stats[0], (unsigned long long)stats[1], (unsigned long long)stats[3]);
+        skf::Array& a = slabs[r];
+        uint64_t rows, keys, samples; uint32_t k, bits; int rc;
+        if (skagpu_dims(slab, &rows, &keys, &samples, &k, &rc, &bits)) { err("dims"); }
+        else {
+            a.k = k; a.rc = rc != 0; a.key_bits = bits; a.n_rows = rows; a.n_samples = samples;
+            a.keys.resize(keys * (bits / 64)); a.variants.resize(rows * samples); a.counts.resize(rows);
+            if (skagpu_export(slab, a.keys.data(), a.variants.data(), a.counts.data())) err("export");
+        }
+        skagpu_free(slab);
+        skagpu_comm_destroy();
+    };
+    std::vector<std::thread> th;
+    for (int r = 0; r < world; r++) th.emplace_back(rank_main, r);
+    for (auto& t : th) t.join();
+    for (auto& e : errors) if (!e.empty()) throw SkaError(e);
+    lap("slabs built on the devices and exported");
+    skf::Array all;
+    all.k = slabs[0].k; all.rc = slabs[0].rc; all.key_bits = slabs[0].key_bits; all.n_samples = n;
+    for (auto& a : slabs) all.n_rows += a.n_rows;
+    all.keys.reserve(all.n_rows); all.variants.resize(all.n_rows * n); all.counts.reserve(all.n_rows);
+    uint64_t row = 0;
+    for (auto& a : slabs) {
+        all.keys.insert(all.keys.end(), a.keys.begin(), a.keys.end());
+        all.counts.insert(all.counts.end(), a.counts.begin(), a.counts.end());
+        if (a.n_rows) memcpy(all.variants.data() + row * n, a.variants.data(), a.n_rows * n);
+        row += a.n_rows;
+        a = skf::Array();
+    }
+    ska_array_t* h = nullptr;
+    check(skagpu_array_from_host(all.k, all.rc, all.key_bits, all.n_rows, n, all.keys.data(), all.variants.data(), all.counts.data(), &h));
+    lap("array on device 0");
+    return MergeSkaArray(h, names);
+}
+
 MergeSkaArray build_and_merge(const std::vector<InputFastx>& input_files, size_t k, bool rc, const QualOpts& qual,
                               size_t threads, double proportion_reads) {
     if (k < 5 || k > 63 || k % 2 == 0) throw SkaError("Invalid k-mer length");                    // ska_dict.rs:342-344
@@ -537,9 +605,24 @@ MergeSkaArray build_and_merge(const std::vector<InputFastx>& input_files, size_t
         }
         throw SkaError(msg);
     };
+    const int world = (int)std::min<size_t>((size_t)g_gpus, n);
+    if (world > 1 && k > 31) throw SkaError("--gpus: k > 31 builds on one GPU only");
     if (all_packed) {
         std::vector<ska_input_packed_t> pin(n);
         for (size_t i = 0; i < n; i++) pin[i] = {packed2[i].data(), invalid[i].data(), recs[i].rec_off.data(), recs[i].n_rec(), n_file1[i]};
+        if (world > 1)
+            return build_sharded(n, names, world, [&](int, size_t lo, size_t hi, ska_array_t** h) -> std::string {
+                if (skagpu_build_packed(pin.data() + lo, hi - lo, (uint32_t)k, rc, h)) {
+                    std::string msg = skagpu_last_error();
+                    size_t p = msg.find("sample ");
+                    if (p == 0 && msg.find("has no valid sequence") != std::string::npos) {
+                        size_t idx = lo + std::stoul(msg.substr(7));
+                        if (idx < n) msg = std::get<1>(input_files[idx]) + " has no valid sequence";
+                    }
+                    return msg;
+                }
+                return "";
+            });
         ska_array_t* h = nullptr;
         if (skagpu_build_packed(pin.data(), n, (uint32_t)k, rc, &h)) fail(skagpu_last_error());
         lap("built on the device");
@@ -561,6 +644,19 @@ MergeSkaArray build_and_merge(const std::vector<InputFastx>& input_files, size_t
         in[i].n_rec = recs[i].n_rec();
         in[i].n_rec_file1 = n_file1[i];
     }
+    if (world > 1)
+        return build_sharded(n, names, world, [&](int, size_t lo, size_t hi, ska_array_t** h) -> std::string {
+            if (skagpu_build(in.data() + lo, hi - lo, (uint32_t)k, rc, qual.min_count, qual.min_qual, (int)qual.qual_filter, proportion_reads, h)) {
+                std::string msg = skagpu_last_error();
+                size_t p = msg.find("sample ");
+                if (p == 0 && msg.find("has no valid sequence") != std::string::npos) {
+                    size_t idx = lo + std::stoul(msg.substr(7));
+                    if (idx < n) msg = std::get<1>(input_files[idx]) + " has no valid sequence";
+                }
+                return msg;
+            }
+            return "";
+        });
     ska_array_t* h = nullptr;
     if (skagpu_build(in.data(), n, (uint32_t)k, rc, qual.min_count, qual.min_qual, (int)qual.qual_filter, proportion_reads, &h))
         fail(skagpu_last_error());

@@ -69,6 +69,10 @@ class MergeSkaArray {
     uint32_t k_bits_field_ = 0;      // what a loaded file said (informational; see skf::Array::k_bits_field)
 };
 
+// GPUs that build_and_merge shards the samples over (default 1; `ska --gpus N` / SKA_GPUS): see build_sharded in ska_host.cpp
+void set_gpus(int n);
+int gpus();
+
 MergeSkaArray build_and_merge(const std::vector<InputFastx>& input_files, size_t k, bool rc, const QualOpts& qual,
                               size_t threads, double proportion_reads /* <= 0: None */);
 

@@ -127,3 +127,18 @@ def test_pack_bases_matches_numpy():
     expi = np.packbits(bad, bitorder="little")
     assert np.array_equal(p2, exp2)
     assert np.array_equal(inv, expi)
+
+
+def test_owner_plan_matches_python_plan():
+    """the owner cut inside libskagpu (csrc/comm.cu, skagpu_plan_owners) is the arithmetic of distributed.plan_owners"""
+    import ska_rust_b200 as S
+    from ska_rust_b200 import distributed as D
+    rng = np.random.default_rng(7)
+    for world in (1, 2, 3, 8):
+        for case in range(20):
+            c = rng.integers(0, 1000, size=4096).astype(np.uint64)
+            if case % 3 == 0:
+                c[rng.integers(0, 4096, size=3500)] = 0
+            if case == 1:
+                c[:] = 0
+            assert np.array_equal(S.api.plan_owners(c, world), D.plan_owners(c, world))

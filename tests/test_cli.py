@@ -318,3 +318,31 @@ def test_cli_cov_and_auto_min_count(gold_in, tmp_path):
     run(["build", "-f", str(rfile), "-o", "auto", "--min-count", "auto", "-k", "9", "-v"], cwd=wd)
     assert os.path.exists(tmp_path / "auto.skf")
     assert run(["build", "-f", str(rfile), "-o", "bad", "--min-count", "70000", "-k", "9"], cwd=wd, check=False).returncode == 2
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("gpus", [2, 4])
+def test_cli_build_sharded_over_gpus_writes_the_same_skf(tmp_path, gpus):
+    """`ska build --gpus N` (one host thread per GPU, rows exchanged inside libskagpu over NCCL) writes byte for byte the
+    .skf of the single-GPU build; `ska align --gpus N` straight from the FASTA files gives the same alignment"""
+    import torch
+    if torch.cuda.device_count() < gpus:
+        pytest.skip(f"needs {gpus} GPUs")
+    from ska_rust_b200 import synth
+    genomes = synth.tree_genomes(10, 50_000, 10, seed=0x5CA20012)
+    files = []
+    for i, g in enumerate(genomes):
+        f = tmp_path / f"g{i}.fa"
+        synth.write_fasta(str(f), f"g{i}", g)
+        files.append(str(f))
+    run(["build", "-o", str(tmp_path / "one"), "-k", "31"] + files)
+    run(["build", "-o", str(tmp_path / "many"), "-k", "31", "--gpus", str(gpus)] + files)
+    assert (tmp_path / "one.skf").read_bytes() == (tmp_path / "many.skf").read_bytes()
+    a1 = run(["align"] + files).stdout
+    a2 = run(["align", "--gpus", str(gpus)] + files).stdout
+    assert a1 == a2 and len(a1) > 0
+    # a sample without sequence on one of the ranks: the reference's panic text, no hang
+    bad = tmp_path / "empty.fa"
+    bad.write_text(">x\nNNNNNNNN\n")
+    p = run(["build", "-o", str(tmp_path / "bad"), "--gpus", str(gpus)] + files + [str(bad)], check=False)
+    assert p.returncode == 101 and b"has no valid sequence" in p.stderr

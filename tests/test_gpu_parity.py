@@ -841,3 +841,65 @@ def test_wide_fastq_count_filter_k63(gold_in):
         g = gpu_build_files(files, k=63, names=["a", "b"], min_count=mc)
         o = O.OracleArray.build_from_files(files, k=63, names=["a", "b"], min_count=mc)
         assert_same_array_wide(g, o)
+
+
+# ---------------------------------------------------------------------------------- the library's own communicator (csrc/comm.cu)
+def _threads_build_slabs(samples, names, k, world, bounds=None):
+    """one host thread per device: build the rank's samples, exchange rows inside the library -> exported slabs in rank order"""
+    import threading
+    comm_id = S.api.comm_unique_id()
+    n = len(samples)
+    bounds = bounds or [(n * r // world, n * (r + 1) // world) for r in range(world)]
+    out, errs = [None] * world, [None] * world
+
+    def rank_main(r):
+        try:
+            S.set_device(r)
+            S.api.comm_init(comm_id, world, r)
+            try:
+                lo, hi = bounds[r]
+                local = S.build_from_samples(samples[lo:hi], names[lo:hi], k, True)
+                slab, stats = S.api.exchange_rows(local, lo, names)
+                tot = S.api.allreduce_u64([slab.dims()["n_rows"]])
+                out[r] = (slab.export(), stats, int(tot[0]))
+            finally:
+                S.api.comm_destroy()
+        except Exception as e:                                # noqa: BLE001 -- reported by the main thread
+            errs[r] = e
+
+    th = [threading.Thread(target=rank_main, args=(r,)) for r in range(world)]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join()
+    for e in errs:
+        if e is not None:
+            raise e
+    return out
+
+
+def _n_devices():
+    import torch
+    return torch.cuda.device_count()
+
+
+@pytest.mark.parametrize("world", [1, 2, 4])
+def test_library_communicator_slabs_equal_single_gpu(world):
+    """skagpu_comm_init + skagpu_exchange_rows with one host thread per GPU: the slabs in rank order are the single-GPU array"""
+    if _n_devices() < world:
+        pytest.skip(f"needs {world} GPUs")
+    from ska_rust_b200 import synth
+    genomes = synth.tree_genomes(12, 60_000, 12, seed=0x5CA20011)
+    samples = [S.Sample(g, np.array([0, len(g)], dtype=np.uint64)) for g in genomes]
+    names = [f"s{i}" for i in range(12)]
+    S.set_device(0)
+    ref = S.build_from_samples(samples, names, 31, True)
+    rk, rv, rc_ = ref.export()
+    parts = _threads_build_slabs(samples, names, 31, world)
+    keys = np.concatenate([np.asarray(p[0][0], dtype=np.uint64) for p in parts])
+    assert np.array_equal(keys, np.asarray(rk, dtype=np.uint64))
+    assert np.array_equal(np.concatenate([p[0][1] for p in parts]), rv)
+    assert np.array_equal(np.concatenate([p[0][2] for p in parts]), rc_)
+    assert all(p[2] == len(rk) for p in parts)              # the all-reduce of the slab sizes
+    if world > 1:
+        assert sum(p[1]["rows_sent"] for p in parts) == sum(p[1]["rows_received"] for p in parts) > 0
