@@ -280,7 +280,7 @@ def run_ours(args, rank, world, local_rank):
 
     shard_t = {}
     local_rows = [None]                                       # rows strategy: rows of this rank's local build
-    strategy = os.environ.get("BENCH_STRATEGY", "rows")       # distributed.py: "rows" (default) or "records"
+    strategy = os.environ.get("BENCH_STRATEGY", "rows_lib")   # distributed.py: "rows_lib" (exchange inside libskagpu), "rows" (torch.distributed), "records"
 
     def build_device(batch):
         if world == 1:
@@ -446,7 +446,7 @@ def run_ours(args, rank, world, local_rank):
         peak, peak_src = measured_peak()
         step_ms = ms_dev / args.steps
         st = {s_: ms for s_, ms, _ in stages}
-        n_cols = G * world if strategy != "rows" or world == 1 else G
+        n_cols = G * world if not strategy.startswith("rows") or world == 1 else G
         rows_local = local_rows[0] if local_rows[0] else rows_built
         full_size = (G == 128 and L == 5_000_000 and world == 1)   # what profiles/ was captured on
 
@@ -473,7 +473,8 @@ def run_ours(args, rank, world, local_rank):
         cfg = workload_config(args, world, population)
         cfg.update({"parallelism": "1 GPU" if world == 1 else
                     (f"{world} ranks: every rank builds its {G} samples, one NCCL exchange of partial rows by key range, "
-                     f"owners join on the key; rows sharded for filter/align ({G * world} columns per slab)" if strategy == "rows" else
+                     f"owners join on the key; rows sharded for filter/align ({G * world} columns per slab)"
+                     + ("; the exchange runs inside libskagpu (skagpu_exchange_rows)" if strategy == "rows_lib" else "") if strategy.startswith("rows") else
                      f"{world} ranks: samples sharded for extraction, one NCCL all-to-all of records by key range, "
                      f"rows sharded for merge/filter ({G * world} columns per slab)"),
                     "rows_built": rows_built, "rows_aligned": rows_aligned})

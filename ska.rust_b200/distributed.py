@@ -227,11 +227,50 @@ def build_and_merge_sharded_rows(backend, samples_local, names_all, sample_base,
     return arr
 
 
+_lib_comm = {"ready": False}
+
+
+def ensure_library_communicator(group=None):
+    """libskagpu's own NCCL communicator over the ranks of `group` (csrc/comm.cu): rank 0 draws the id, torch.distributed only
+    carries those 128 bytes.  Once per process."""
+    if _lib_comm["ready"]:
+        return
+    box = [api.comm_unique_id() if dist.get_rank(group) == 0 else None]
+    dist.broadcast_object_list(box, src=0, group=group)
+    api.comm_init(box[0], dist.get_world_size(group), dist.get_rank(group))
+    _lib_comm["ready"] = True
+
+
+def build_and_merge_sharded_rows_lib(backend, samples_local, names_all, sample_base, k, rc, group=None, timings=None, qual=None):
+    """"rows" strategy with the exchange inside the library (skagpu_exchange_rows): histogram all-gather, owner cut, one
+    grouped send/recv of keys + variant rows + counts, join -- no tensors, no host-side plan in Python."""
+    import time
+    ensure_library_communicator(group)
+    t0 = time.perf_counter()
+    n_local = samples_local.n_samples() if hasattr(samples_local, "n_samples") else len(samples_local)
+    names_local = names_all[sample_base:sample_base + n_local]
+    local = backend.build_local(samples_local, names_local, k, rc, qual) if qual is not None else backend.build_local(samples_local, names_local, k, rc)
+    if timings is not None:
+        torch.cuda.synchronize()
+        timings["local_build_ms"] = (time.perf_counter() - t0) * 1e3
+        t0 = time.perf_counter()
+    arr, stats = api.exchange_rows(local, sample_base, names_all)
+    arr.local_rows = local.dims()["n_rows"]
+    if timings is not None:
+        torch.cuda.synchronize()
+        timings["exchange_and_merge_ms"] = (time.perf_counter() - t0) * 1e3
+        timings.update(stats)
+    return arr
+
+
 def build_and_merge_sharded(backend, samples_local, names_all, sample_base, k, rc, prefix_bits=None, group=None,
                             timings=None, strategy="rows", qual=None):
     """-> this rank's slab (a MergeSkaArray with len(names_all) columns).  Collective over `group`.
     strategy "rows" (default) exchanges partial rows after a local build, "records" exchanges records between the
     two partition passes (module docstring); `prefix_bits` only concerns "records"."""
+    if strategy == "rows_lib":
+        return build_and_merge_sharded_rows_lib(backend, samples_local, names_all, sample_base, k, rc, group=group, timings=timings,
+                                                qual=qual)
     if strategy == "rows":
         return build_and_merge_sharded_rows(backend, samples_local, names_all, sample_base, k, rc, group=group, timings=timings,
                                             qual=qual)
