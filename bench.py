@@ -49,13 +49,14 @@ def ncu_traffic(kernel):
     same workload size), or None."""
     for rnd in ("r02", "r01"):
         p = os.path.join(ROOT, "profiles", f"ncu_summary_{rnd}.json")
-        try:
-            with open(p) as fh:
-                d = json.load(fh)[kernel]
-            unit = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
-            return sum(float(d[m][0]) * unit[d[m][1]] for m in ("dram__bytes_read.sum", "dram__bytes_write.sum"))
-        except Exception:
-            continue
+        for name in (kernel if isinstance(kernel, (list, tuple)) else [kernel]):
+            try:
+                with open(p) as fh:
+                    d = json.load(fh)[name]
+                unit = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+                return sum(float(d[m][0]) * unit[d[m][1]] for m in ("dram__bytes_read.sum", "dram__bytes_write.sum"))
+            except Exception:
+                continue
     return None
 
 
@@ -216,8 +217,10 @@ STAGE_KERNELS = {
     "merge": ("bucket_merge_kernel", lambda n, R, C, Rk, N: 9.0 * n + R * (16.0 + C)),
     "transpose": ("transpose_words_kernel", lambda n, R, C, Rk, N: 2.0 * Rk * N),
 }
-NCU_NAMES = {"k1_extract_kernel": "k1_extract", "part_scatter_kernel<1>": "part_scatter", "bucket_count_kernel": "bucket_count",
-             "bucket_emit_smem_kernel": "bucket_emit_smem", "transpose_words_kernel": "transpose_words"}
+# kernel -> its entries in profiles/ncu_summary_r02.json / _r01.json (the first one found is used)
+NCU_NAMES = {"k1_extract_kernel": ["k1_extract<31, 0, 1, 1, 0>", "k1_extract"], "part_scatter_kernel<1>": ["part_scatter<1, 8>", "part_scatter"],
+             "part_scatter_kernel<2>": ["part_scatter<2, 8>"], "part_hist_kernel": ["part_hist"], "bucket_count_kernel": ["bucket_count"],
+             "bucket_emit_smem_kernel": ["bucket_emit_smem"], "transpose_words_kernel": ["transpose_words"]}
 
 
 def run_ours(args, rank, world, local_rank):
@@ -455,7 +458,7 @@ def run_ours(args, rank, world, local_rank):
             ms = st.get(stage, 0.0) or 1e-9
             by = fn(float(n_bases), float(rows_local), float(n_cols), float(rows_aligned), float(G * world))
             return {"kernel": kern, "stage": stage, "bound": "hbm", "achieved": by / (ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
-                    "frac": by / (ms * 1e-3) / 1e9 / peak, "traffic": ncu_traffic(NCU_NAMES.get(kern, "")) if full_size else None,
+                    "frac": by / (ms * 1e-3) / 1e9 / peak, "traffic": ncu_traffic(NCU_NAMES.get(kern, [])) if full_size else None,
                     "peak_source": peak_src, "algorithmic_bytes_per_launch": by, "launch_ms": ms, "share_of_step": ms / step_ms}
 
         STAGE_KERNELS["k1_extract"] = ("k1_extract_kernel", lambda n, R, C, Rk, N: (10.0 if args.ascii else 9.375) * n)

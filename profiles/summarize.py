@@ -57,7 +57,7 @@ def kernel_summaries():
     out = {}
     for f in sorted(os.listdir(SRC)):
         m = re.match(rf"(.+)_{R}_raw\.csv$", f)
-        if not m:
+        if not m or m.group(1) == "kernels":
             continue
         rows = read_rows(os.path.join(SRC, f))
         if len(rows) < 3:
@@ -68,6 +68,26 @@ def kernel_summaries():
             if h in KEEP or h == "Kernel Name" or (h.startswith(STALLS) and h.endswith("_per_issue_active.ratio")):
                 d[h] = [v, u]
         out[m.group(1)] = d
+    # round 2: one raw CSV with every kernel of a build + align (capture.sh with ONE_PROCESS=1), one row per launch
+    multi = os.path.join(SRC, f"kernels_{R}_raw.csv")
+    if os.path.exists(multi):
+        rows = read_rows(multi)
+        hdr, units = rows[0], rows[1]
+        ik = hdr.index("Kernel Name")
+        seen = collections.Counter()
+        for vals in rows[2:]:
+            if len(vals) <= ik:
+                continue
+            base = re.sub(r"^void\s+", "", vals[ik]).split("(")[0].replace("ska::", "")
+            short = re.sub(r"_kernel.*", "", base)
+            tmpl = re.search(r"_kernel(<.*>)", base)
+            seen[base] += 1
+            name = short + (tmpl.group(1) if tmpl else "") + (f"#{seen[base]}" if seen[base] > 1 else "")
+            d = {}
+            for h, u, v in zip(hdr, units, vals):
+                if h in KEEP or h == "Kernel Name" or (h.startswith(STALLS) and h.endswith("_per_issue_active.ratio")):
+                    d[h] = [v, u]
+            out[name] = d
     if out:
         with open(os.path.join(OUT, f"ncu_summary_{R}.json"), "w") as fh:
             json.dump(out, fh, indent=1, sort_keys=True)

@@ -109,7 +109,7 @@ def run_distance(args, rank, world, local_rank):
             out = arr.distance(float(constant), True)
             info["stages"] = S.api.last_timings()
             return out
-        arr = D.build_and_merge_sharded(backend, src, names_all, rank * G, k, True)
+        arr = D.build_and_merge_sharded(backend, src, names_all, rank * G, k, True, strategy=os.environ.get("BENCH_STRATEGY", "rows_lib"))
         info["rows_built"] = arr.dims()["n_rows"]
         out = D.distance_sharded(arr, 0.0, True)
         info["rows_compared"] = arr.dims()["n_rows"]

@@ -29,6 +29,11 @@ struct DeviceState {
     DevCache cache;
     std::vector<std::unique_ptr<PendingExport>> exports;
     cudaStream_t d2h_stream = nullptr;
+    uint8_t* rb_host = nullptr;                         // mapped pinned staging of the small read-backs (read_back below)
+    uint8_t* rb_dev = nullptr;
+    size_t rb_used = 0;
+    struct RbItem { void* dst; size_t off, bytes; };
+    std::vector<RbItem> rb_pending;
     void* comm = nullptr;                               // multi-GPU communicator of the thread bound to this device (comm.cu)
 };
 constexpr int MAX_DEVICES = 64;
@@ -136,6 +141,50 @@ void dev_free(void* p) {
         { std::lock_guard<std::mutex> lock(g_dev_mu); st = g_dev[d]; }
         if (st && cache_take_back(st->cache, p)) return;
     }
+}
+
+// ---- small device -> host read-backs (bucket totals, flags, tile counts) that every build waits for.  As cudaMemcpyAsync
+// they go through a copy engine and queue behind the bulk transfers of a pipelined host (the next batch's upload, the
+// previous alignment's download): at 8 GPUs per host an 8-byte read-back waited 12 ms.  Here a few threads store the bytes
+// into mapped pinned memory instead; read_back_sync() synchronises the stream and hands them to their destinations.
+constexpr size_t RB_CAP = (size_t)1 << 20;
+__global__ void read_back_kernel(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst, size_t bytes, int words) {
+    const size_t stride = (size_t)gridDim.x * blockDim.x, i0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (words) for (size_t i = i0; i < bytes / 4; i += stride) reinterpret_cast<uint32_t*>(dst)[i] = reinterpret_cast<const uint32_t*>(src)[i];
+    else for (size_t i = i0; i < bytes; i += stride) dst[i] = src[i];
+}
+void read_back(void* h_dst, const void* d_src, size_t bytes) {
+    if (!bytes) return;
+    DeviceState& st = dev_state();
+    Context& c = st.ctx;
+    static const bool dma = getenv("SKA_READBACK_DMA") != nullptr;        // A/B: the copy-engine form
+    const size_t need = (bytes + 15) & ~(size_t)15;
+    if (!dma && !st.rb_host) {
+        if (cudaHostAlloc((void**)&st.rb_host, RB_CAP, cudaHostAllocMapped) != cudaSuccess ||
+            cudaHostGetDevicePointer((void**)&st.rb_dev, st.rb_host, 0) != cudaSuccess) { (void)cudaGetLastError(); st.rb_host = nullptr; }
+    }
+    if (dma || !st.rb_host || st.rb_used + need > RB_CAP) {
+        SKA_CUDA(cudaMemcpyAsync(h_dst, d_src, bytes, cudaMemcpyDeviceToHost, c.stream));
+        return;
+    }
+    const int words = ((reinterpret_cast<uintptr_t>(d_src) | bytes) & 3) == 0;
+    const unsigned grid = (unsigned)std::min<size_t>(32, (bytes + 1023) / 1024);
+    read_back_kernel<<<grid, 256, 0, c.stream>>>(static_cast<const uint8_t*>(d_src), st.rb_dev + st.rb_used, bytes, words);
+    SKA_CUDA(cudaGetLastError());
+    st.rb_pending.push_back({h_dst, st.rb_used, bytes});
+    st.rb_used += need;
+}
+void read_back_abandon() {                                  // an error unwound past a pending read-back: its destination is gone
+    if (!t_state) return;
+    t_state->rb_pending.clear();
+    t_state->rb_used = 0;
+}
+void read_back_sync() {
+    DeviceState& st = dev_state();
+    SKA_CUDA(cudaStreamSynchronize(st.ctx.stream));
+    for (auto& it : st.rb_pending) memcpy(it.dst, st.rb_host + it.off, it.bytes);
+    st.rb_pending.clear();
+    st.rb_used = 0;
 }
 
 Arena& arena() { return dev_state().arena; }
@@ -443,9 +492,10 @@ static void merge_records(uint64_t* rec, const SeqBatch& b, uint32_t k, bool rc,
 static std::unique_ptr<Array> build_from_extracted(const SeqBatch& b, uint32_t k, bool rc, const PartPlan& pl, const K1Overlap& ov) {
     Context& c = ctx();
     std::vector<uint32_t> h_valid(b.n_samples);
-    SKA_CUDA(cudaMemcpyAsync(h_valid.data(), ov.valid, b.n_samples * 4, cudaMemcpyDeviceToHost, c.stream));
+    read_back(h_valid.data(), ov.valid, b.n_samples * 4);
     std::unique_ptr<Array> a(new Array());
-    merge_records(ov.rec, b, k, rc, *a, pl, ov.hist);             // synchronises
+    merge_records(ov.rec, b, k, rc, *a, pl, ov.hist);
+    read_back_sync();
     for (size_t s = 0; s < b.n_samples; s++)
         if (h_valid[s] == 0) throw Error("sample " + std::to_string(s) + " has no valid sequence");   // ska_dict.rs:374-376
     return a;
@@ -479,9 +529,10 @@ static std::unique_ptr<Array> build_from_batch(const SeqBatch& b, uint32_t k, bo
     launch_k1(b, k, rc, false, min_qual, rec, nullptr, valid, 0, k1_hist, 4 + pl.key_bits - pl.P1, pl.P1);
     timer().end();
     std::vector<uint32_t> h_valid(b.n_samples);
-    SKA_CUDA(cudaMemcpyAsync(h_valid.data(), valid, b.n_samples * 4, cudaMemcpyDeviceToHost, c.stream));
+    read_back(h_valid.data(), valid, b.n_samples * 4);
     std::unique_ptr<Array> a(new Array());
-    merge_records(rec, b, k, rc, *a, pl, k1_hist);                 // synchronises
+    merge_records(rec, b, k, rc, *a, pl, k1_hist);
+    read_back_sync();
     for (size_t s = 0; s < b.n_samples; s++)
         if (h_valid[s] == 0) throw Error("sample " + std::to_string(s) + " has no valid sequence");   // ska_dict.rs:374-376
     return a;
@@ -495,8 +546,8 @@ static thread_local std::string g_err;
 #define API_TRY try {
 #define API_CATCH                                         \
     }                                                     \
-    catch (std::exception & e) { g_err = e.what(); return 1; } \
-    catch (...) { g_err = "unknown error"; return 1; }
+    catch (std::exception & e) { g_err = e.what(); ska::read_back_abandon(); return 1; } \
+    catch (...) { g_err = "unknown error"; ska::read_back_abandon(); return 1; }
 
 struct ska_array { Array a; };
 struct ska_seqbatch { std::unique_ptr<SeqBatch> b; };

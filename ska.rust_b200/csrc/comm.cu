@@ -149,8 +149,8 @@ void exchange_partial_rows(const Array& local, uint64_t sample_base, uint64_t n_
         DevBuf<uint64_t> d_mine(T), d_all((size_t)W * T);
         SKA_CUDA(cudaMemcpyAsync(d_mine.p, mine.data(), T * 8, cudaMemcpyHostToDevice, c.stream));
         SKA_NCCL(nccl().AllGather(d_mine.p, d_all.p, T, ncclUint64, cm.comm, c.stream));
-        SKA_CUDA(cudaMemcpyAsync(table.data(), d_all.p, (size_t)W * T * 8, cudaMemcpyDeviceToHost, c.stream));
-        SKA_CUDA(cudaStreamSynchronize(c.stream));
+        read_back(table.data(), d_all.p, (size_t)W * T * 8);
+        read_back_sync();
     }
     // owners: identical arithmetic on every rank
     std::vector<uint64_t> counts(R, 0), cuts(W + 1);

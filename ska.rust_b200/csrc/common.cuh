@@ -52,6 +52,10 @@ void*& comm_slot();                       // the multi-GPU communicator of the c
 // 13 GB cudaMalloc -- a third of what a one-shot `ska build` process takes; repeated builds hit the free list either way.
 // A block is handed out again only to work that is ordered behind its previous user (everything runs on, or is fenced
 // against, the library stream).
+// small device -> host read-back on the library stream that does not queue behind bulk DMA (api.cu); the bytes are in h_dst
+// after the next read_back_sync(), which also synchronises the stream
+void read_back(void* h_dst, const void* d_src, size_t bytes);
+void read_back_sync();
 void* dev_alloc(size_t bytes);
 void dev_free(void* p);
 

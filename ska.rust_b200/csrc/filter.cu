@@ -399,9 +399,9 @@ int32_t filter_array(Array& a, uint64_t min_count, bool filter_ambig_as_missing,
     launch_scan_counts(keep1.p, n_cta, off1.p, scratch.p);
     launch_scan_counts(keep2.p, n_cta, off2.p, scratch.p);
     uint64_t n1 = 0, n2 = 0;
-    SKA_CUDA(cudaMemcpyAsync(&n1, off1.p + n_cta, 8, cudaMemcpyDeviceToHost, c.stream));
-    SKA_CUDA(cudaMemcpyAsync(&n2, off2.p + n_cta, 8, cudaMemcpyDeviceToHost, c.stream));
-    SKA_CUDA(cudaStreamSynchronize(c.stream));
+    read_back(&n1, off1.p + n_cta, 8);
+    read_back(&n2, off2.p + n_cta, 8);
+    read_back_sync();
 
     // which key compaction applies: the filter loop's (update_kmers) wins over update_counts'
     const bool keys_match_rows = a.n_keys == a.n_rows;   // false only after an earlier update_kmers=false filter

@@ -1033,8 +1033,8 @@ static void merge_items(const uint64_t* rec, Item* items, uint32_t n_items, int 
     for (int round = 0; n_items > 0; round++) {
         SKA_CUDA(cudaMemsetAsync(flags, 0, 8, c.stream));
         SKA_LAUNCH(bucket_count_kernel, n_items, MG_THREADS, COUNT_SMEM, rec, items, sb, limit, n_rows, flags, scratch_keys);
-        SKA_CUDA(cudaMemcpyAsync(h_flags, flags, 8, cudaMemcpyDeviceToHost, c.stream));
-        SKA_CUDA(cudaStreamSynchronize(c.stream));
+        read_back(h_flags, flags, 8);
+        read_back_sync();
         if (!h_flags[0]) break;
         if (round > 40) throw Error("bucket splitting did not converge");
         std::vector<Item> h_items(n_items), next;
@@ -1069,9 +1069,9 @@ static void merge_items(const uint64_t* rec, Item* items, uint32_t n_items, int 
     uint64_t total_rows = 0;
     if (n_items) {
         launch_scan_counts(n_rows, n_items, row_off, flags + 1);
-        SKA_CUDA(cudaMemcpyAsync(h_flags, flags, 8, cudaMemcpyDeviceToHost, c.stream));
-        SKA_CUDA(cudaMemcpyAsync(&total_rows, row_off + n_items, 8, cudaMemcpyDeviceToHost, c.stream));
-        SKA_CUDA(cudaStreamSynchronize(c.stream));
+        read_back(h_flags, flags, 8);
+        read_back(&total_rows, row_off + n_items, 8);
+        read_back_sync();
     }
     timer().end();
     const uint32_t max_u = h_flags[1];
@@ -1197,8 +1197,8 @@ bool union_sorted_runs(const uint64_t* keys, int n_runs, const uint64_t* h_run_o
         SKA_LAUNCH(run_cumulative_kernel, grid, 256, 0, keys, d_run_off, n_runs, key_bits - pbits, NB + 1, cum);
         SKA_LAUNCH(bucket_sizes_kernel, (NB + 255) / 256, 256, 0, cum, n_runs, NB, sizes);
         launch_scan_counts(sizes, NB, off, flags + 1);
-        SKA_CUDA(cudaMemcpyAsync(h_flags, flags, 8, cudaMemcpyDeviceToHost, c.stream));
-        SKA_CUDA(cudaStreamSynchronize(c.stream));
+        read_back(h_flags, flags, 8);
+        read_back_sync();
         if (h_flags[1] <= (uint32_t)COUNT_LIST - 1) break;               // every bucket fits the count table
         if (pbits >= max_bits) return false;                               // a key range this crowded: let the general merge split it
         pbits = std::min(max_bits, pbits + 2);
@@ -1215,9 +1215,9 @@ bool union_sorted_runs(const uint64_t* keys, int n_runs, const uint64_t* h_run_o
     uint64_t* row_off = arena().take_n<uint64_t>(NB + 1);
     launch_scan_counts(n_rows, NB, row_off, flags + 1);
     uint64_t total = 0;
-    SKA_CUDA(cudaMemcpyAsync(h_flags, flags, 8, cudaMemcpyDeviceToHost, c.stream));
-    SKA_CUDA(cudaMemcpyAsync(&total, row_off + NB, 8, cudaMemcpyDeviceToHost, c.stream));
-    SKA_CUDA(cudaStreamSynchronize(c.stream));
+    read_back(h_flags, flags, 8);
+    read_back(&total, row_off + NB, 8);
+    read_back_sync();
     if (h_flags[0]) return false;                                          // probing ran off a table's tail (very crowded corner)
     out_keys.alloc(total);
     if (total) SKA_LAUNCH(compact_keys_kernel, NB, 128, 0, (const uint64_t*)scratch, items, row_off, out_keys.p);

@@ -665,8 +665,8 @@ void partition_records(const uint64_t* rec, uint64_t n_pos, const uint64_t* d_sa
     if (first_pass_buf) *first_pass_buf = a;
     if (pl.P2 == 0) { *out = a; *d_off = off1; return; }
     uint64_t n_tiles2 = 0;
-    SKA_CUDA(cudaMemcpyAsync(&n_tiles2, tile_pref + D1, 8, cudaMemcpyDeviceToHost, c.stream));
-    SKA_CUDA(cudaStreamSynchronize(c.stream));
+    read_back(&n_tiles2, tile_pref + D1, 8);
+    read_back_sync();
     uint64_t* b = scratch ? scratch : arena().take_n<uint64_t>(std::max<uint64_t>(n_pos, 1) * (pl.wide ? 2 : 1));
     const Segs sg{tile_pref, off1, off1 + 1, nullptr, D1};
     partition_fine(a, sg, n_tiles2, D1, pl, b, d_off);
@@ -735,8 +735,8 @@ void group_wide_records(const uint64_t* src, uint64_t n, int top_bit, int P1, in
                            (const uint64_t*)nullptr, 0u, cur1, buf_a);
     if (P2 == 0) { *out = buf_a; *d_off = off1; return; }
     uint64_t n_tiles2 = 0;
-    SKA_CUDA(cudaMemcpyAsync(&n_tiles2, tile_pref + D1, 8, cudaMemcpyDeviceToHost, c.stream));
-    SKA_CUDA(cudaStreamSynchronize(c.stream));
+    read_back(&n_tiles2, tile_pref + D1, 8);
+    read_back_sync();
     const size_t NB = (size_t)D1 * D2;
     unsigned long long* hist2 = arena().take_n<unsigned long long>(NB);
     unsigned long long* cur2 = arena().take_n<unsigned long long>(NB);

@@ -42,8 +42,8 @@ void key_cumulative(const Array& a, int region_bits, uint64_t* h_cum) {
     const uint32_t n_cuts = (1u << region_bits) + 1;
     DevBuf<uint64_t> d(n_cuts);
     SKA_LAUNCH(key_cumulative_kernel, (n_cuts + 255) / 256, 256, 0, a.keys.p, a.n_rows, key_bits - region_bits, n_cuts, d.p);
-    SKA_CUDA(cudaMemcpyAsync(h_cum, d.p, (size_t)n_cuts * 8, cudaMemcpyDeviceToHost, c.stream));
-    SKA_CUDA(cudaStreamSynchronize(c.stream));
+    read_back(h_cum, d.p, (size_t)n_cuts * 8);
+    read_back_sync();
 }
 
 __global__ void keys_to_records_kernel(const uint64_t* __restrict__ keys, uint64_t n, uint64_t* __restrict__ rec) {
@@ -168,8 +168,8 @@ void merge_partial_rows(const uint64_t* keys, const uint8_t* var, const uint32_t
         row0 += rows; byte0 += rows * run_cols[w];
     }
     uint32_t h_missing = 0;
-    SKA_CUDA(cudaMemcpyAsync(&h_missing, missing, 4, cudaMemcpyDeviceToHost, c.stream));
-    SKA_CUDA(cudaStreamSynchronize(c.stream));
+    read_back(&h_missing, missing, 4);
+    read_back_sync();
     timer().end();
     if (h_missing) throw Error("internal: " + std::to_string(h_missing) + " partial rows found no slab row");
 }
