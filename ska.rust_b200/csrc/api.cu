@@ -174,6 +174,29 @@ void read_back(void* h_dst, const void* d_src, size_t bytes) {
     st.rb_pending.push_back({h_dst, st.rb_used, bytes});
     st.rb_used += need;
 }
+// memset as a kernel on the library stream: cudaMemsetAsync may be carried out by a copy engine, where it waits behind the
+// bulk transfers of a pipelined host exactly like the read-backs above
+__global__ void dev_fill_kernel(uint8_t* __restrict__ p, uint32_t word, size_t bytes, size_t head) {
+    const size_t stride = (size_t)gridDim.x * blockDim.x, i0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t n16 = (bytes - head) / 16;
+    uint4* q = reinterpret_cast<uint4*>(p + head);
+    for (size_t i = i0; i < n16; i += stride) q[i] = make_uint4(word, word, word, word);
+    const size_t tail0 = head + n16 * 16;
+    for (size_t i = i0; i < head; i += stride) p[i] = (uint8_t)word;
+    for (size_t i = tail0 + i0; i < bytes; i += stride) p[i] = (uint8_t)word;
+}
+void dev_fill(void* p, int byte, size_t bytes) {
+    if (!bytes) return;
+    Context& c = ctx();
+    const uint32_t w = (uint32_t)(uint8_t)byte * 0x01010101u;
+    size_t head = (16 - (reinterpret_cast<uintptr_t>(p) & 15)) & 15;
+    if (head > bytes) head = bytes;
+    const unsigned grid = (unsigned)std::min<size_t>((size_t)c.sm_count * 8, (bytes / 16 + 255) / 256 + 1);
+    dev_fill_kernel<<<grid, 256, 0, c.stream>>>(static_cast<uint8_t*>(p), w, bytes, head);
+    c.launches++;
+    SKA_CUDA(cudaGetLastError());
+}
+
 void read_back_abandon() {                                  // an error unwound past a pending read-back: its destination is gone
     if (!t_state) return;
     t_state->rb_pending.clear();
@@ -283,9 +306,9 @@ static std::unique_ptr<SeqBatch> upload(const ska_input_t* in, size_t n, double 
     const size_t padded = padded_positions(b->n_pos);
     b->seq.alloc(padded);
     // pads are 'N': invalid bases, so no window can reach outside the batch
-    SKA_CUDA(cudaMemsetAsync(b->seq.p, 'N', FRONT_PAD, c.stream));
-    SKA_CUDA(cudaMemsetAsync(b->seq.p + FRONT_PAD + b->n_pos, 'N', padded - FRONT_PAD - b->n_pos, c.stream));
-    if (b->has_qual) { b->qual.alloc(padded); SKA_CUDA(cudaMemsetAsync(b->qual.p, '!', padded, c.stream)); }
+    dev_fill(b->seq.p, 'N', FRONT_PAD);
+    dev_fill(b->seq.p + FRONT_PAD + b->n_pos, 'N', padded - FRONT_PAD - b->n_pos);
+    if (b->has_qual) { b->qual.alloc(padded); dev_fill(b->qual.p, '!', padded); }
 
     size_t step = 1;
     if (proportion_reads > 0) step = (size_t)std::llround(1.0 / proportion_reads);      // ska_dict.rs:125-129
@@ -302,7 +325,7 @@ static std::unique_ptr<SeqBatch> upload(const ska_input_t* in, size_t n, double 
         }
         starts.push_back(b->n_pos);
         b->start_bits.alloc(padded / 32 + 1);
-        SKA_CUDA(cudaMemsetAsync(b->start_bits.p, 0, b->start_bits.bytes(), c.stream));
+        dev_fill(b->start_bits.p, 0, b->start_bits.bytes());
         DevBuf<uint64_t> d_starts(starts.size());
         SKA_CUDA(cudaMemcpyAsync(d_starts.p, starts.data(), starts.size() * 8, cudaMemcpyHostToDevice, c.stream));
         SKA_LAUNCH(set_start_bits_kernel, (unsigned)((starts.size() + 255) / 256), 256, 0, d_starts.p, (uint64_t)starts.size(),
@@ -350,7 +373,7 @@ static std::unique_ptr<SeqBatch> upload(const ska_input_t* in, size_t n, double 
         } else {
             // --proportion-reads: keep record i of each file iff i % step == 0 (ska_dict.rs:131-141);
             // skipped records stay in the position space as runs of 'N' (they yield no window)
-            if (len) SKA_CUDA(cudaMemsetAsync(b->seq.p + FRONT_PAD + base, 'N', len, c.stream));
+            if (len) dev_fill(b->seq.p + FRONT_PAD + base, 'N', len);
             for (uint64_t r = 0; r < in[s].n_rec; r++) {
                 uint64_t idx_in_file = r < in[s].n_rec_file1 ? r : r - in[s].n_rec_file1;
                 if (idx_in_file % step) continue;
@@ -365,7 +388,7 @@ static std::unique_ptr<SeqBatch> upload(const ska_input_t* in, size_t n, double 
     }
     starts.push_back(b->n_pos);                                   // end sentinel: "a record starts after the last base"
     b->start_bits.alloc(padded / 32 + 1);
-    SKA_CUDA(cudaMemsetAsync(b->start_bits.p, 0, b->start_bits.bytes(), c.stream));
+    dev_fill(b->start_bits.p, 0, b->start_bits.bytes());
     DevBuf<uint64_t> d_starts(starts.size());
     SKA_CUDA(cudaMemcpyAsync(d_starts.p, starts.data(), starts.size() * 8, cudaMemcpyHostToDevice, c.stream));
     SKA_LAUNCH(set_start_bits_kernel, (unsigned)((starts.size() + 255) / 256), 256, 0, d_starts.p, (uint64_t)starts.size(),
@@ -400,8 +423,8 @@ static std::unique_ptr<SeqBatch> upload_packed(const ska_input_packed_t* in, siz
     b->n_pos = b->h_sample_off[n];
     const size_t padded = padded_positions(b->n_pos);
     b->seq.alloc(padded / 4); b->qual.alloc(padded / 8);
-    SKA_CUDA(cudaMemsetAsync(b->seq.p, 0, padded / 4, c.stream));
-    SKA_CUDA(cudaMemsetAsync(b->qual.p, 0xFF, padded / 8, c.stream));          // everything invalid until a sample says otherwise
+    dev_fill(b->seq.p, 0, padded / 4);
+    dev_fill(b->qual.p, 0xFF, padded / 8);          // everything invalid until a sample says otherwise
     std::vector<uint64_t>& marks = b->h_marks;                      // lives with the batch: an asynchronous upload returns before it is copied
     marks.reserve(2 * n_rec_total + 1);
     for (size_t s = 0; s < n; s++) {
@@ -414,7 +437,7 @@ static std::unique_ptr<SeqBatch> upload_packed(const ska_input_packed_t* in, siz
     }
     marks.push_back(b->n_pos);
     b->start_bits.alloc(padded / 32 + 1);
-    SKA_CUDA(cudaMemsetAsync(b->start_bits.p, 0, b->start_bits.bytes(), c.stream));
+    dev_fill(b->start_bits.p, 0, b->start_bits.bytes());
     DevBuf<uint64_t> d_marks(marks.size());
     SKA_CUDA(cudaMemcpyAsync(d_marks.p, marks.data(), marks.size() * 8, cudaMemcpyHostToDevice, c.stream));
     SKA_LAUNCH(set_start_bits_kernel, (unsigned)((marks.size() + 255) / 256), 256, 0, d_marks.p, (uint64_t)marks.size(), b->start_bits.p);
@@ -515,7 +538,7 @@ static std::unique_ptr<Array> build_from_batch(const SeqBatch& b, uint32_t k, bo
     }
     uint64_t* rec = arena().take_n<uint64_t>(b.n_pos * (k > 31 ? 2 : 1));
     uint32_t* valid = arena().take_n<uint32_t>(b.n_samples);
-    SKA_CUDA(cudaMemsetAsync(valid, 0, b.n_samples * 4, c.stream));
+    dev_fill(valid, 0, b.n_samples * 4);
     // K1 also counts the records by the first partition digit, so that the partition never reads them for its
     // histogram.  Measured on 128 x 5 Mbp: the step gets 0.67 ms shorter (partition -0.91 ms, K1 +0.24 ms: 4096 shared-memory
     // atomics per tile at 3.6 SM-cycles per warp instruction, profiles/microbench/scatter_mb2.cu).
@@ -523,7 +546,7 @@ static std::unique_ptr<Array> build_from_batch(const SeqBatch& b, uint32_t k, bo
     unsigned long long* k1_hist = nullptr;
     if (k1_hist_enabled() && k <= 31) {                      // wide keys: the partition counts its own histogram (see launch_k1)
         k1_hist = arena().take_n<unsigned long long>((size_t)K1_HIST_COPIES << pl.P1);
-        SKA_CUDA(cudaMemsetAsync(k1_hist, 0, ((size_t)K1_HIST_COPIES << pl.P1) * 8, c.stream));
+        dev_fill(k1_hist, 0, ((size_t)K1_HIST_COPIES << pl.P1) * 8);
     }
     timer().begin("k1_extract");
     launch_k1(b, k, rc, false, min_qual, rec, nullptr, valid, 0, k1_hist, 4 + pl.key_bits - pl.P1, pl.P1);
@@ -626,8 +649,8 @@ int skagpu_build(const ska_input_t* inputs, size_t n_samples, uint32_t k, int rc
         ov.valid = arena().take_n<uint32_t>(n_samples);
         ov.hist = k > 31 ? nullptr : arena().take_n<unsigned long long>((size_t)K1_HIST_COPIES << pl.P1);
         ov.hist_shift = 4 + pl.key_bits - pl.P1; ov.hist_bits = pl.P1;
-        SKA_CUDA(cudaMemsetAsync(ov.valid, 0, n_samples * 4, ctx().stream));
-        if (ov.hist) SKA_CUDA(cudaMemsetAsync(ov.hist, 0, ((size_t)K1_HIST_COPIES << pl.P1) * 8, ctx().stream));
+        dev_fill(ov.valid, 0, n_samples * 4);
+        if (ov.hist) dev_fill(ov.hist, 0, ((size_t)K1_HIST_COPIES << pl.P1) * 8);
         timer().begin("h2d+k1");
         std::unique_ptr<SeqBatch> b = upload(inputs, n_samples, proportion_reads, &ov);
         timer().end();
@@ -663,8 +686,8 @@ static std::unique_ptr<Array> build_packed(const ska_input_packed_t* inputs, siz
     ov.valid = arena().take_n<uint32_t>(n_samples);
     ov.hist = arena().take_n<unsigned long long>((size_t)K1_HIST_COPIES << pl.P1);
     ov.hist_shift = 4 + pl.key_bits - pl.P1; ov.hist_bits = pl.P1;
-    SKA_CUDA(cudaMemsetAsync(ov.valid, 0, n_samples * 4, ctx().stream));
-    SKA_CUDA(cudaMemsetAsync(ov.hist, 0, ((size_t)K1_HIST_COPIES << pl.P1) * 8, ctx().stream));
+    dev_fill(ov.valid, 0, n_samples * 4);
+    dev_fill(ov.hist, 0, ((size_t)K1_HIST_COPIES << pl.P1) * 8);
     timer().begin("h2d+k1");
     std::unique_ptr<SeqBatch> b = upload_packed(inputs, n_samples, &ov);
     timer().end();
@@ -884,8 +907,12 @@ int skagpu_export_transposed_async(const ska_array_t* h, uint8_t* out) {
     SKA_CUDA(cudaEventCreateWithFlags(&ready, cudaEventDisableTiming));
     SKA_CUDA(cudaEventRecord(ready, c.stream));
     SKA_CUDA(cudaStreamWaitEvent(g_d2h_stream, ready, 0));
+    // The copy engine carries the alignment (55 GB/s).  Before the builds' small read-backs left the copy engines (read_back
+    // above) this transfer delayed them, and a 32-CTA kernel storing into mapped host memory took its place; that kernel moves
+    // ~10 GB/s and its stalled stores slow every other kernel by 25-30 %, which at 8 GPUs (610 MB of alignment per rank and
+    // step) made it the whole step.  SKA_EXPORT_PUSH_KERNEL=1 selects it for A/B runs.
     void* out_dev = nullptr;
-    const bool mapped = !getenv("SKA_EXPORT_COPY_ENGINE") && cudaHostGetDevicePointer(&out_dev, out, 0) == cudaSuccess && out_dev &&
+    const bool mapped = getenv("SKA_EXPORT_PUSH_KERNEL") && cudaHostGetDevicePointer(&out_dev, out, 0) == cudaSuccess && out_dev &&
                         ((uintptr_t)out_dev & 15) == 0;
     if (mapped) {
         const size_t n16 = e->t.bytes() / 16;
@@ -894,7 +921,7 @@ int skagpu_export_transposed_async(const ska_array_t* h, uint8_t* out) {
         c.launches++;
         SKA_CUDA(cudaGetLastError());
     } else {
-        (void)cudaGetLastError();                                // pageable destination: the copy engine it is
+        (void)cudaGetLastError();
         SKA_CUDA(cudaMemcpyAsync(out, e->t.p, e->t.bytes(), cudaMemcpyDeviceToHost, g_d2h_stream));
     }
     SKA_CUDA(cudaEventCreateWithFlags(&e->done, cudaEventDisableTiming));
@@ -934,7 +961,7 @@ int skagpu_extract_records(const ska_seqbatch_t* batch, uint32_t k, int rc, uint
     r->plan = make_part_plan(k, prefix_bits, n_samples_total);
     uint64_t* rec = arena().take_n<uint64_t>(b.n_pos);
     uint32_t* valid = arena().take_n<uint32_t>(b.n_samples);
-    SKA_CUDA(cudaMemsetAsync(valid, 0, b.n_samples * 4, c.stream));
+    dev_fill(valid, 0, b.n_samples * 4);
     timer().begin("k1_extract");
     launch_k1(b, k, rc != 0, false, 0, rec, nullptr, valid);
     timer().end();
@@ -1262,7 +1289,7 @@ int skagpu_k1_extract(const ska_seqbatch_t* batch, uint32_t k, int rc, uint8_t m
     // the kernel variant the build launches: FASTA batches also fill the first partition histogram
     const PartPlan pl = plan_for(k, b.n_pos, b.n_samples);
     DevBuf<unsigned long long> hist((size_t)K1_HIST_COPIES << pl.P1);
-    SKA_CUDA(cudaMemsetAsync(hist.p, 0, hist.bytes(), c.stream));
+    dev_fill(hist.p, 0, hist.bytes());
     // the extraction kernel proper; inside a build the same kernel also fills the partition histogram (stage "k1_extract")
     unsigned long long* hp = (getenv("SKA_K1_ROOFLINE_WITH_HIST") && !b.has_qual) ? hist.p : nullptr;
     const int hshift = 4 + pl.key_bits - pl.P1;

@@ -54,6 +54,7 @@ void*& comm_slot();                       // the multi-GPU communicator of the c
 // against, the library stream).
 // small device -> host read-back on the library stream that does not queue behind bulk DMA (api.cu); the bytes are in h_dst
 // after the next read_back_sync(), which also synchronises the stream
+void dev_fill(void* p, int byte, size_t bytes);   // memset on the library stream, as a kernel (api.cu)
 void read_back(void* h_dst, const void* d_src, size_t bytes);
 void read_back_sync();
 void* dev_alloc(size_t bytes);

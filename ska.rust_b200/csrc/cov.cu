@@ -135,8 +135,8 @@ void kmer_count_histogram(const SeqBatch& reads, uint32_t k, bool rc, uint64_t* 
         const PartPlan pl = make_part_plan(k, P, 1);
         uint64_t* prec = nullptr; uint64_t* off = nullptr;
         partition_records(rec, reads.n_pos, reads.sample_off.p, (uint32_t)reads.n_samples, 0, pl, rec, &prec, &off, nullptr, nullptr);
-        SKA_CUDA(cudaMemsetAsync(hist.p, 0, CV_MAX_COUNT * 8, c.stream));
-        SKA_CUDA(cudaMemsetAsync(over.p, 0, 4, c.stream));
+        dev_fill(hist.p, 0, CV_MAX_COUNT * 8);
+        dev_fill(over.p, 0, 4);
         timer().begin("count_hist");
         const unsigned n_buckets = 1u << pl.P;
         if (wide) SKA_LAUNCH(bucket_hist_wide_kernel, n_buckets, CV_THREADS, 0, prec, off, pl.sb, hist.p, over.p);

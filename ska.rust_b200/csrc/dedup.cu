@@ -137,8 +137,8 @@ uint64_t* unique_sample_records(uint64_t* rec, uint64_t n, uint32_t k, int prefi
     uint64_t* out = prec == rec ? first : rec;                          // whichever of the two buffers the grouped records are not in
     unsigned long long* cursor = arena().take_n<unsigned long long>(1);
     uint32_t* over = arena().take_n<uint32_t>(2);
-    SKA_CUDA(cudaMemsetAsync(cursor, 0, 8, c.stream));
-    SKA_CUDA(cudaMemsetAsync(over, 0, 8, c.stream));
+    dev_fill(cursor, 0, 8);
+    dev_fill(over, 0, 8);
     const unsigned n_buckets = 1u << pl.P;
     if (wide) SKA_LAUNCH(bucket_unique_wide_kernel, n_buckets, DD_THREADS, 0, prec, off, pl.sb, pl.low_bits, pl.P2, out, cursor, over);
     else SKA_LAUNCH(bucket_unique_kernel, n_buckets, DD_THREADS, 0, prec, off, pl.sb, pl.low_bits, pl.P2, out, cursor, over);

@@ -253,7 +253,7 @@ void distance_counters(const Array& a, bool filt_ambig, uint64_t* h_counters) {
         const uint64_t n_words = (R + 31) / 32;
         const uint32_t SP = (N + 63) / 64 * 64;
         DevBuf<uint32_t> planes(4 * (uint64_t)SP * n_words), odd(1);
-        SKA_CUDA(cudaMemsetAsync(odd.p, 0, 4, c.stream));
+        dev_fill(odd.p, 0, 4);
         const uint32_t wpc = std::max<uint32_t>(1, 32768u / (32u * N));      // words per CTA: a 32 KB tile
         size_t smem = (size_t)wpc * 32 * N;
         if (smem + 1024 > c.smem_optin) use_planes = false;
@@ -269,7 +269,7 @@ void distance_counters(const Array& a, bool filt_ambig, uint64_t* h_counters) {
         }
         if (use_planes) {
             DevBuf<unsigned long long> acc(3 * n_pairs);
-            SKA_CUDA(cudaMemsetAsync(acc.p, 0, acc.bytes(), c.stream));
+            dev_fill(acc.p, 0, acc.bytes());
             const bool small = N <= 256;                                   // 32 x 32 tiles waste less of the diagonal
             const uint32_t TS = small ? 32 : 64;
             const uint32_t nt = (N + TS - 1) / TS, ntp = nt * (nt + 1) / 2;
@@ -295,7 +295,7 @@ void distance_counters(const Array& a, bool filt_ambig, uint64_t* h_counters) {
     }
     // exact byte-wise path
     DevBuf<unsigned long long> acc(4 * n_pairs);
-    SKA_CUDA(cudaMemsetAsync(acc.p, 0, acc.bytes(), c.stream));
+    dev_fill(acc.p, 0, acc.bytes());
     if (R > 0) {
         uint64_t chunks = (R + BR - 1) / BR;
         uint64_t want_splits = std::max<uint64_t>(1, (4ull * c.sm_count + n_tile_pairs - 1) / n_tile_pairs);

@@ -361,7 +361,7 @@ void build_array_from_reads(const SeqBatch& b, uint32_t k, bool rc, uint16_t min
         const size_t n_words = n_tiles * (K1_T / 32);
         uint32_t* mask = arena().take_n<uint32_t>(n_words);
         timer().begin("reads_hash");
-        SKA_CUDA(cudaMemsetAsync(mask, 0, n_words * 4, c.stream));
+        dev_fill(mask, 0, n_words * 4);
         if (min_count <= 1) {                                         // bloom_filter.rs:121: no filtering
             SKA_LAUNCH(k1q_kernel<RQ_MASK>, (unsigned)n_tiles, K1_THREADS, 0, b.seq.p, b.qual.p, b.start_bits.p, lo, hi, tile_lo,
                        (int)k, rc ? 1 : 0, (uint32_t)min_qual, qual_filter, mask, (ulonglong2*)nullptr,
@@ -375,7 +375,7 @@ void build_array_from_reads(const SeqBatch& b, uint32_t k, bool rc, uint16_t min
             uint64_t* obs_tmp = arena().take_n<uint64_t>(2 * n_s);
             uint64_t* ent = arena().take_n<uint64_t>(2 * n_s);                // one 16-byte entry per distinct hash (at most n_s)
             uint64_t* run_start = all_later ? arena().take_n<uint64_t>(n_s) : nullptr;
-            SKA_CUDA(cudaMemsetAsync(d_counter, 0, 16, c.stream));
+            dev_fill(d_counter, 0, 16);
             SKA_LAUNCH(k1q_kernel<RQ_OBS>, (unsigned)n_tiles, K1_THREADS, obs_smem, b.seq.p, b.qual.p, b.start_bits.p, lo, hi, tile_lo,
                        (int)k, rc ? 1 : 0, (uint32_t)min_qual, qual_filter, mask, reinterpret_cast<ulonglong2*>(obs_rec), d_counter,
                        (const uint64_t*)nullptr, (uint64_t*)nullptr);
@@ -404,7 +404,7 @@ void build_array_from_reads(const SeqBatch& b, uint32_t k, bool rc, uint16_t min
                 } else {
                     uint32_t* long_list = arena().take_n<uint32_t>(n_d);
                     unsigned long long* n_long = arena().take_n<unsigned long long>(1);
-                    SKA_CUDA(cudaMemsetAsync(n_long, 0, 8, c.stream));
+                    dev_fill(n_long, 0, 8);
                     SKA_LAUNCH(q_accept_kernel, (unsigned)((n_d + 255) / 256), 256, 0, dsorted, fp_flag, obs, (const uint64_t*)run_start, n_d,
                                (uint32_t)min_count, mask, long_list, n_long);
                     unsigned long long h_long = 0;

@@ -961,7 +961,7 @@ static bool merge_items_fused(const uint64_t* rec, const Item* items, uint32_t n
     Item* sitems = arena().take_n<Item>(ns);
     uint32_t* s_rows = arena().take_n<uint32_t>(ns);
     uint32_t* flags = arena().take_n<uint32_t>(2);
-    SKA_CUDA(cudaMemsetAsync(flags, 0, 8, c.stream));
+    dev_fill(flags, 0, 8);
     SKA_LAUNCH(sample_items_kernel, (ns + 255) / 256, 256, 0, items, n_items, stride, ns, sitems);
     SKA_CUDA(cudaFuncSetAttribute(bucket_count_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)COUNT_SMEM));
     SKA_LAUNCH(bucket_count_kernel, ns, MG_THREADS, COUNT_SMEM, rec, sitems, sb, (uint32_t)COUNT_LIST - 1, s_rows, flags, (uint64_t*)nullptr);
@@ -989,8 +989,8 @@ static bool merge_items_fused(const uint64_t* rec, const Item* items, uint32_t n
     out.keys.alloc(cap_rows); out.variants.alloc(cap_rows * n_samples); out.counts.alloc(cap_rows);
     unsigned long long* status = arena().take_n<unsigned long long>(n_items);
     FusedCtl* ctl = arena().take_n<FusedCtl>(1);
-    SKA_CUDA(cudaMemsetAsync(status, 0, (size_t)n_items * 8, c.stream));
-    SKA_CUDA(cudaMemsetAsync(ctl, 0, sizeof(FusedCtl), c.stream));
+    dev_fill(status, 0, (size_t)n_items * 8);
+    dev_fill(ctl, 0, sizeof(FusedCtl));
     SKA_CUDA(cudaFuncSetAttribute(bucket_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     SKA_LAUNCH(bucket_merge_kernel, n_items, FM_THREADS, smem, rec, items, n_items, sb, slots, home_slots, max_keys, (uint32_t)n_samples,
                (int)k, rc ? 1 : 0, cap_rows, out.keys.p, out.variants.p, out.counts.p, status, ctl);
@@ -1031,7 +1031,7 @@ static void merge_items(const uint64_t* rec, Item* items, uint32_t n_items, int 
     uint32_t* flags = arena().take_n<uint32_t>(2);
     uint32_t h_flags[2] = {0, 0};
     for (int round = 0; n_items > 0; round++) {
-        SKA_CUDA(cudaMemsetAsync(flags, 0, 8, c.stream));
+        dev_fill(flags, 0, 8);
         SKA_LAUNCH(bucket_count_kernel, n_items, MG_THREADS, COUNT_SMEM, rec, items, sb, limit, n_rows, flags, scratch_keys);
         read_back(h_flags, flags, 8);
         read_back_sync();
@@ -1210,7 +1210,7 @@ bool union_sorted_runs(const uint64_t* keys, int n_runs, const uint64_t* h_run_o
     SKA_LAUNCH(make_items_kernel, (NB + 255) / 256, 256, 0, off, NB, (uint64_t)0, key_bits, pbits, pbits, key_bits, items);
     uint32_t* n_rows = arena().take_n<uint32_t>(NB);
     SKA_CUDA(cudaFuncSetAttribute(bucket_count_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)COUNT_SMEM));
-    SKA_CUDA(cudaMemsetAsync(flags, 0, 8, c.stream));
+    dev_fill(flags, 0, 8);
     SKA_LAUNCH(bucket_count_kernel, NB, MG_THREADS, COUNT_SMEM, prec, items, 1, (uint32_t)COUNT_LIST - 1, n_rows, flags, scratch);
     uint64_t* row_off = arena().take_n<uint64_t>(NB + 1);
     launch_scan_counts(n_rows, NB, row_off, flags + 1);

@@ -269,7 +269,7 @@ void build_array_from_records_wide(uint64_t* rec, uint64_t n_rec, const uint64_t
     uint32_t* flags = arena().take_n<uint32_t>(2);
     uint32_t h_flags[2] = {0, 0};
     for (int round = 0;; round++) {
-        SKA_CUDA(cudaMemsetAsync(flags, 0, 8, c.stream));
+        dev_fill(flags, 0, 8);
         SKA_LAUNCH(bucket_count_wide_kernel, n_items, W_THREADS, 0, prec, items, pl.sb, limit, n_rows, flags, sc);
         SKA_CUDA(cudaMemcpyAsync(h_flags, flags, 8, cudaMemcpyDeviceToHost, c.stream));
         SKA_CUDA(cudaStreamSynchronize(c.stream));

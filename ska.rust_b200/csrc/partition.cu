@@ -583,7 +583,7 @@ void partition_coarse(const uint64_t* rec, uint64_t n_pos, const uint64_t* d_sam
     unsigned long long* cur1 = arena().take_n<unsigned long long>(D1);
     uint64_t* off1 = arena().take_n<uint64_t>(D1 + 1);
     uint64_t* tile_pref = arena().take_n<uint64_t>(D1 + 1);
-    if (!k1_hist) SKA_CUDA(cudaMemsetAsync(hist1, 0, D1 * 8, c.stream));
+    if (!k1_hist) dev_fill(hist1, 0, D1 * 8);
     const uint64_t n_tiles1 = (n_pos + PT_TILE - 1) / PT_TILE;
     DigitFn f1{1, 4 + pl.key_bits - pl.P1, 0xFFFFFFFFu};
     PackFn pk{pl.sb, pl.low_bits >= 64 ? ~0ULL : ((1ULL << pl.low_bits) - 1ULL), sid_base};
@@ -625,7 +625,7 @@ void partition_fine(const uint64_t* src, const Segs& sg, uint64_t n_tiles2, uint
     unsigned long long* hist2 = arena().take_n<unsigned long long>(std::max<size_t>(NB, 1));
     unsigned long long* cur2 = arena().take_n<unsigned long long>(std::max<size_t>(NB, 1));
     uint64_t* bucket_off = arena().take_n<uint64_t>(NB + 1);
-    SKA_CUDA(cudaMemsetAsync(hist2, 0, std::max<size_t>(NB, 1) * 8, c.stream));
+    dev_fill(hist2, 0, std::max<size_t>(NB, 1) * 8);
     set_scatter_attrs();
     DigitFn f2{2, pl.sb + 2 + pl.low_bits - pl.P2, D2 - 1};
     PackFn pk{pl.sb, 0, 0};
@@ -721,7 +721,7 @@ void group_wide_records(const uint64_t* src, uint64_t n, int top_bit, int P1, in
     unsigned long long* cur1 = arena().take_n<unsigned long long>(D1);
     uint64_t* off1 = arena().take_n<uint64_t>(D1 + 1);
     uint64_t* tile_pref = arena().take_n<uint64_t>(D1 + 1);
-    SKA_CUDA(cudaMemsetAsync(hist1, 0, D1 * 8, c.stream));
+    dev_fill(hist1, 0, D1 * 8);
     const uint64_t n_tiles1 = (n + PT_TILE - 1) / PT_TILE;
     const DigitFn f1{3, top_bit - P1, D1 - 1};
     const Segs none{nullptr, nullptr, nullptr, nullptr, 1u};
@@ -741,7 +741,7 @@ void group_wide_records(const uint64_t* src, uint64_t n, int top_bit, int P1, in
     unsigned long long* hist2 = arena().take_n<unsigned long long>(NB);
     unsigned long long* cur2 = arena().take_n<unsigned long long>(NB);
     uint64_t* bucket_off = arena().take_n<uint64_t>(NB + 1);
-    SKA_CUDA(cudaMemsetAsync(hist2, 0, NB * 8, c.stream));
+    dev_fill(hist2, 0, NB * 8);
     const DigitFn f2{2, top_bit - P1 - P2, D2 - 1};
     const Segs sg{tile_pref, off1, off1 + 1, nullptr, D1};
     if (n_tiles2) {

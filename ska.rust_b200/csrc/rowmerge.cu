@@ -155,10 +155,10 @@ void merge_partial_rows(const uint64_t* keys, const uint8_t* var, const uint32_t
     out.keys = std::move(uni.keys);
     out.variants.alloc(R * n_samples);
     out.counts.alloc(R);
-    if (R * n_samples) SKA_CUDA(cudaMemsetAsync(out.variants.p, '-', R * n_samples, c.stream));
-    if (R) SKA_CUDA(cudaMemsetAsync(out.counts.p, 0, R * 4, c.stream));
+    if (R * n_samples) dev_fill(out.variants.p, '-', R * n_samples);
+    if (R) dev_fill(out.counts.p, 0, R * 4);
     uint32_t* missing = arena().take_n<uint32_t>(1);
-    SKA_CUDA(cudaMemsetAsync(missing, 0, 4, c.stream));
+    dev_fill(missing, 0, 4);
     uint64_t row0 = 0, byte0 = 0;
     for (int w = 0; w < n_runs; w++) {
         const uint64_t rows = run_rows[w];

@@ -38,7 +38,7 @@ bool keys_sorted(const Array& a) {
     Context& c = ctx();
     if (a.n_keys < 2) return true;
     DevBuf<uint32_t> bad(1);
-    SKA_CUDA(cudaMemsetAsync(bad.p, 0, 4, c.stream));
+    dev_fill(bad.p, 0, 4);
     SKA_LAUNCH(order_check_kernel, (unsigned)((a.n_keys + 255) / 256), 256, 0, a.keys.p, (int)(a.key_bits / 64), a.n_keys, bad.p);
     uint32_t h = 0;
     SKA_CUDA(cudaMemcpyAsync(&h, bad.p, 4, cudaMemcpyDeviceToHost, c.stream));
@@ -242,8 +242,8 @@ uint64_t weed_rows(Array& a, const SeqBatch& weed, bool reverse) {
     launch_k1(weed, a.k, a.rc, false, 0, rec, nullptr, nullptr);
     DevBuf<uint8_t> mark(std::max<uint64_t>(a.n_rows, 1));
     DevBuf<unsigned long long> nv(1);
-    SKA_CUDA(cudaMemsetAsync(mark.p, 0, std::max<uint64_t>(a.n_rows, 1), c.stream));
-    SKA_CUDA(cudaMemsetAsync(nv.p, 0, 8, c.stream));
+    dev_fill(mark.p, 0, std::max<uint64_t>(a.n_rows, 1));
+    dev_fill(nv.p, 0, 8);
     if (n_pos) {
         if (wide) SKA_LAUNCH((mark_records_kernel<2>), (unsigned)((n_pos + 255) / 256), 256, 0, rec, n_pos, a.keys.p, a.n_keys, mark.p, nv.p);
         else SKA_LAUNCH((mark_records_kernel<1>), (unsigned)((n_pos + 255) / 256), 256, 0, rec, n_pos, a.keys.p, a.n_keys, mark.p, nv.p);
@@ -305,14 +305,14 @@ void extend_arrays(Array& a, Array& b, Array& out) {
         if (nb >= 0xFFFFFFFFull) throw Error("too many rows");
         launch_scan_counts(m.p, (uint32_t)nb, pm.p, mx.p);
         SKA_CUDA(cudaMemcpyAsync(&n_match, pm.p + nb, 8, cudaMemcpyDeviceToHost, c.stream));
-    } else SKA_CUDA(cudaMemsetAsync(pm.p, 0, 8, c.stream));
+    } else dev_fill(pm.p, 0, 8);
     SKA_CUDA(cudaStreamSynchronize(c.stream));
     const uint64_t R = na + nb - n_match;
     out.k = a.k; out.rc = a.rc; out.key_bits = a.key_bits; out.n_samples = nt; out.n_rows = out.n_keys = R; out.sorted = true;
     out.keys.alloc(R * kw); out.variants.alloc(R * nt); out.counts.alloc(R);
     if (R) {
-        SKA_CUDA(cudaMemsetAsync(out.variants.p, '-', R * nt, c.stream));            // 0 -> '-' (merge_ska_array.rs:175)
-        SKA_CUDA(cudaMemsetAsync(out.counts.p, 0, R * 4, c.stream));
+        dev_fill(out.variants.p, '-', R * nt);            // 0 -> '-' (merge_ska_array.rs:175)
+        dev_fill(out.counts.p, 0, R * 4);
     }
     if (na) SKA_LAUNCH(place_rows_kernel, (unsigned)((na * 32 + 255) / 256), 256, 0, a.keys.p, kw, a.variants.p, a.counts.p, na, (uint32_t)a.n_samples,
                        0u, 0, b.keys.p, nb, pm.p, lb_a.p, m.p, nt, out.keys.p, out.variants.p, out.counts.p);
@@ -403,7 +403,7 @@ void map_reference(Array& a, const SeqBatch& ref, std::vector<uint64_t>& h_pos, 
     DevBuf<uint64_t> hit(std::max<uint64_t>(n_pos, 1));
     DevBuf<uint8_t> flag(std::max<uint64_t>(n_pos, 1));
     DevBuf<unsigned long long> nv(1);
-    SKA_CUDA(cudaMemsetAsync(nv.p, 0, 8, c.stream));
+    dev_fill(nv.p, 0, 8);
     if (n_pos) {
         if (wide) SKA_LAUNCH((map_lookup_kernel<2>), (unsigned)((n_pos + 255) / 256), 256, 0, rec, n_pos, ref.seq.p, h, a.keys.p, a.n_keys, hit.p, flag.p, nv.p);
         else SKA_LAUNCH((map_lookup_kernel<1>), (unsigned)((n_pos + 255) / 256), 256, 0, rec, n_pos, ref.seq.p, h, a.keys.p, a.n_keys, hit.p, flag.p, nv.p);

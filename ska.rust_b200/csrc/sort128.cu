@@ -368,7 +368,7 @@ static void sort_range_wide(uint64_t* data, uint64_t n, int top_bit, uint64_t* t
     if (depth > 8) throw Error("internal: wide sort recursion too deep");
     {   // an oversized bucket is one key seen thousands of times: skip the bits its records share
         unsigned long long* d_diff = arena().take_n<unsigned long long>(2);
-        SKA_CUDA(cudaMemsetAsync(d_diff, 0, 16, c.stream));
+        dev_fill(d_diff, 0, 16);
         SKA_LAUNCH(diff_bits_kernel, (unsigned)std::min<uint64_t>((n + 255) / 256, (uint64_t)c.sm_count * 8), 256, 0,
                    reinterpret_cast<const ulonglong2*>(data), n, d_diff);
         unsigned long long h_diff[2];
@@ -389,7 +389,7 @@ static void sort_range_wide(uint64_t* data, uint64_t n, int top_bit, uint64_t* t
     uint32_t* mid_list = arena().take_n<uint32_t>(nb + 1);
     uint32_t* huge_list = arena().take_n<uint32_t>(nb + 1);
     uint32_t* cnts = arena().take_n<uint32_t>(4);
-    SKA_CUDA(cudaMemsetAsync(cnts, 0, 16, c.stream));
+    dev_fill(cnts, 0, 16);
     launch_warp_sorts(data, off, nb, mid_list, big_list, cnts, nullptr);
     uint32_t n_big = 0;
     SKA_CUDA(cudaMemcpyAsync(&n_big, cnts, 4, cudaMemcpyDeviceToHost, c.stream));
@@ -417,7 +417,7 @@ static uint64_t* sort_impl(const uint64_t* rec, uint64_t n, int key_bits, uint64
     uint32_t* mid_list = arena().take_n<uint32_t>(nb + 1);
     uint32_t* huge_list = arena().take_n<uint32_t>(nb + 1);
     uint32_t* cnts = arena().take_n<uint32_t>(4);
-    SKA_CUDA(cudaMemsetAsync(cnts, 0, 16, c.stream));
+    dev_fill(cnts, 0, 16);
     if (ro) {
         ro->drec = reinterpret_cast<ulonglong2*>(other);
         ro->prefix_bits = P;

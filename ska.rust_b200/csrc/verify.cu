@@ -65,7 +65,7 @@ void array_checksum(const Array& a, uint32_t col_lo, uint32_t col_hi, uint64_t* 
     if (a.n_keys != a.n_rows) throw Error("array keys and rows are out of step (filtered without update_kmers)");
     if (col_hi > a.n_samples || col_lo > col_hi) throw Error("bad column range");
     DevBuf<unsigned long long> d(4);
-    SKA_CUDA(cudaMemsetAsync(d.p, 0, 32, c.stream));
+    dev_fill(d.p, 0, 32);
     if (a.n_rows) {
         const unsigned grid = (unsigned)std::min<uint64_t>((a.n_rows + 7) / 8, (uint64_t)c.sm_count * 16);
         SKA_LAUNCH(array_checksum_kernel, grid, 256, 0, a.keys.p, (int)(a.key_bits / 64), a.variants.p, a.counts.p, a.n_rows,
