@@ -530,7 +530,7 @@ def main():
     ap.add_argument("--fastq-samples", type=int, default=64, help="--workload fastq: samples (BASELINE configs[3]: 64)")
     ap.add_argument("--fastq-pairs", type=int, default=2_000_000, help="--workload fastq: read pairs per sample (configs[3]: 2 M)")
     ap.add_argument("--fastq-parity-samples", type=int, default=4, help="--workload fastq: whole samples checked against the CPU port")
-    ap.add_argument("--fastq-ref-samples", type=int, default=8, help="--workload fastq --impl reference: whole samples timed on the host")
+    ap.add_argument("--fastq-ref-samples", type=int, default=4, help="--workload fastq --impl reference: whole samples timed on the host")
     ap.add_argument("--population", default="tree", choices=["star", "tree"],
                     help="SURVEY 8d generator.  tree (default at every N, so that the 1 -> 8 GPU curve is like for like): the "
                          "samples are leaves of a balanced tree over all N x 128 genomes, every leaf 0.1%% from the root; "
