@@ -111,7 +111,7 @@ def run_distance(args, rank, world, local_rank):
             return out
         arr = D.build_and_merge_sharded(backend, src, names_all, rank * G, k, True, strategy=os.environ.get("BENCH_STRATEGY", "rows_lib"))
         info["rows_built"] = arr.dims()["n_rows"]
-        out = D.distance_sharded(arr, 0.0, True)
+        out = D.distance_sharded(arr, 0.0, True, as_array=True)
         info["rows_compared"] = arr.dims()["n_rows"]
         info["stages"] = S.api.last_timings()
         return out
@@ -173,7 +173,10 @@ def run_distance(args, rank, world, local_rank):
         if not same:
             raise SystemExit(f"parity check FAILED: {parity}")
     # invariants at full size: distance <= matches, matches + mismatches <= constant + rows, symmetric population sanity
-    d = np.array([x[0] for x in dists]); m = np.array([x[2] for x in dists]); mm = np.array([x[3] for x in dists])
+    if isinstance(dists, np.ndarray):
+        d, m, mm = dists["distance"], dists["matches"], dists["mismatches"]
+    else:
+        d = np.array([x[0] for x in dists]); m = np.array([x[2] for x in dists]); mm = np.array([x[3] for x in dists])
     parity["full_size"] = {"pairs": int(len(dists)), "distance_le_matches": bool(np.all(d <= m)), "max_distance": float(d.max()) if len(d) else 0.0,
                            "mean_distance": float(d.mean()) if len(d) else 0.0}
     if not np.all(d <= m) or len(dists) != n_pairs:

@@ -342,9 +342,9 @@ def gather_alignment(slab_t, names, group=None, dst=0):
     return b"".join(b">" + n.encode() + b"\n" + full[i].tobytes() + b"\n" for i, n in enumerate(names))
 
 
-def distance_sharded(arr, min_freq=0.0, filt_ambig=True, group=None):
+def distance_sharded(arr, min_freq=0.0, filt_ambig=True, group=None, as_array=False):
     """generic_modes.rs:136-189 on slabs: -> [(distance, mismatch_prop, matches, mismatches)] for all pairs,
-    identical on every rank."""
+    identical on every rank (`as_array`: the same as a numpy record array, no per-pair Python objects)."""
     n = arr.nsamples()
     dev = "cuda" if torch.cuda.is_available() and dist.get_backend(group) == "nccl" else "cpu"
     if min_freq * n >= 1.0:
@@ -355,14 +355,15 @@ def distance_sharded(arr, min_freq=0.0, filt_ambig=True, group=None):
     dist.all_reduce(t, group=group)
     t = t.cpu().numpy()
     cnt, constant = t[:-1].reshape(-1, 4), float(t[-1])
-    out = []
-    for mism, match, dint, nboth in cnt:
-        d = float(dint) if filt_ambig else float(nboth) - float(dint) / 36.0
-        matches = constant + float(match)                 # merge_ska_array.rs:598
-        mismatches = float(mism)
-        prop = 0.0 if matches + mismatches == 0.0 else mismatches / (matches + mismatches)
-        out.append((d, prop, int(matches), int(mismatches)))
-    return out
+    # vectorised: 1024 samples are 523 776 pairs, a Python loop over them costs more than the kernels
+    mism, match, dint, nboth = (cnt[:, i].astype(np.float64) for i in range(4))
+    d = dint if filt_ambig else nboth - dint / 36.0
+    matches = constant + match                                # merge_ska_array.rs:598
+    tot = matches + mism
+    prop = np.divide(mism, tot, out=np.zeros_like(tot), where=tot != 0.0)
+    out = np.empty(len(cnt), dtype=[("distance", "f8"), ("mismatch_prop", "f8"), ("matches", "i8"), ("mismatches", "i8")])
+    out["distance"], out["mismatch_prop"], out["matches"], out["mismatches"] = d, prop, matches.astype(np.int64), mism.astype(np.int64)
+    return out if as_array else out.tolist()
 
 
 def format_distances(names, dists):
