@@ -199,6 +199,9 @@ int skagpu_merge_partial_rows_dev(const void* keys_dev, const void* variants_dev
  *                           stats (may be NULL): rows sent, rows received, bytes sent, rows of the slab;
  *   skagpu_allreduce_u64    sums host integers over the ranks (the distance counters and the constant-site count of
  *                           generic_modes.rs:136-189 on slabs);
+ *   skagpu_distance_sharded collective.  skagpu_distance on a slab: the per-pair integer counters and `constant_local` (the
+ *                           constant sites the no-const filter removed from THIS slab) are summed over the ranks, every rank
+ *                           gets the whole job's table (generic_modes.rs:136-189, merge_ska_array.rs:416-438);
  *   skagpu_plan_owners      the owner cut on its own (host arithmetic, no device): cuts[world + 1] region indices. */
 #define SKAGPU_COMM_ID_BYTES 128
 int skagpu_comm_unique_id(uint8_t* id);
@@ -206,6 +209,7 @@ int skagpu_comm_init(const uint8_t* id, int world, int rank);
 int skagpu_comm_destroy(void);
 int skagpu_exchange_rows(const ska_array_t* local, uint64_t sample_base, uint64_t n_samples_total, ska_array_t** slab, uint64_t* stats);
 int skagpu_allreduce_u64(uint64_t* values, size_t n);
+int skagpu_distance_sharded(const ska_array_t* slab, double constant_local, int filt_ambig, ska_dist_t* out);
 int skagpu_plan_owners(const uint64_t* region_rows, uint32_t n_regions, int world, uint64_t* cuts);
 
 /* Per-pair partial sums of variant_dist (merge_ska_array.rs:599-620) over this array's rows, 4 x u64 per

@@ -38,7 +38,7 @@ EXPORTS = [
     "skagpu_export_wait", "skagpu_seqbatch_upload_packed_async", "skagpu_merge_arrays", "skagpu_delete_samples", "skagpu_weed",
     "skagpu_map", "skagpu_map_dims", "skagpu_map_export", "skagpu_map_free", "skagpu_kmer_count_hist",
     "skagpu_comm_unique_id", "skagpu_comm_init", "skagpu_comm_destroy", "skagpu_exchange_rows", "skagpu_allreduce_u64",
-    "skagpu_plan_owners",
+    "skagpu_plan_owners", "skagpu_distance_sharded",
 ]
 
 
@@ -110,6 +110,7 @@ def lib():
         L.skagpu_exchange_rows.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.c_void_p, C.c_void_p]
         L.skagpu_allreduce_u64.argtypes = [C.c_void_p, C.c_size_t]
         L.skagpu_plan_owners.argtypes = [C.c_void_p, C.c_uint32, C.c_int, C.c_void_p]
+        L.skagpu_distance_sharded.argtypes = [C.c_void_p, C.c_double, C.c_int, C.c_void_p]
         L.skagpu_pack_bases.restype = None
         L.skagpu_pack_bases.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.c_void_p, C.c_void_p]
         L.skagpu_build_packed.argtypes = [C.c_void_p, C.c_size_t, C.c_uint32, C.c_int, C.c_void_p]
@@ -437,6 +438,15 @@ class MergeSkaArray:
         out = (_Dist * max(1, n * (n - 1) // 2))()
         _check(lib().skagpu_distance(self._h, float(constant), int(filt_ambig), out))
         return [(d.distance, d.mismatch_prop, d.match_count, d.mismatch_count) for d in out[:n * (n - 1) // 2]]
+
+    def distance_sharded(self, constant_local, filt_ambig):
+        """collective (library communicator): skagpu_distance on this rank's slab, counters and the slabs' constant-site counts summed
+        over the ranks -> numpy record array (distance, mismatch_prop, matches, mismatches) of the whole job's pairs"""
+        n = self.nsamples()
+        npairs = n * (n - 1) // 2
+        out = np.zeros(max(1, npairs), dtype=[("distance", "f8"), ("mismatch_prop", "f8"), ("matches", "u8"), ("mismatches", "u8")])
+        _check(lib().skagpu_distance_sharded(self._h, float(constant_local), int(filt_ambig), out.ctypes.data))
+        return out[:npairs]
 
     def distance_counters(self, filt_ambig):
         """(n_pairs, 4) uint64 partial sums {mismatches, matches, dist_int, n_both} over this array's rows"""

@@ -1103,6 +1103,14 @@ int skagpu_allreduce_u64(uint64_t* values, size_t n) {
     return 0;
     API_CATCH
 }
+int skagpu_distance_sharded(const ska_array_t* slab, double constant_local, int filt_ambig, ska_dist_t* out) {
+    API_TRY
+    if (!slab || !out) throw Error("null argument");
+    ctx().ensure();
+    distance_array(slab->a, constant_local, filt_ambig != 0, reinterpret_cast<DistOut*>(out), true);
+    return 0;
+    API_CATCH
+}
 int skagpu_plan_owners(const uint64_t* region_rows, uint32_t n_regions, int world, uint64_t* cuts) {
     API_TRY
     if (!region_rows || !cuts || world < 1) throw Error("bad argument");

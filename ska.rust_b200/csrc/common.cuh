@@ -227,7 +227,7 @@ int32_t filter_array(Array& a, uint64_t min_count, bool filter_ambig_as_missing,
 void transpose_array(const Array& a, uint8_t* d_out);
 // distance.cu
 struct DistOut { double distance, mismatch_prop; uint64_t match_count, mismatch_count; };
-void distance_array(const Array& a, double constant, bool filt_ambig, DistOut* h_out);
+void distance_array(const Array& a, double constant, bool filt_ambig, DistOut* h_out, bool sharded = false);
 // raw per-pair counters {mismatches, matches, dist_int, n_both} (dist_int: differing unambiguous pairs, or
 // 36 x summed overlap when !filt_ambig); partial sums over this array's rows, addable across row shards
 void distance_counters(const Array& a, bool filt_ambig, uint64_t* h_counters);

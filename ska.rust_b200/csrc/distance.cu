@@ -310,12 +310,19 @@ void distance_counters(const Array& a, bool filt_ambig, uint64_t* h_counters) {
     SKA_CUDA(cudaStreamSynchronize(c.stream));
 }
 
-void distance_array(const Array& a, double constant, bool filt_ambig, DistOut* h_out) {
+// sharded: the array is one rank's slab of rows; the per-pair counters and the slabs' constant-site counts are summed over the
+// ranks of the library's communicator (comm.cu) before the table is formed, so every rank returns the whole job's table
+void distance_array(const Array& a, double constant, bool filt_ambig, DistOut* h_out, bool sharded) {
     const uint32_t N = (uint32_t)a.n_samples;
     if (N < 2) return;
     const uint64_t n_pairs = (uint64_t)N * (N - 1) / 2;
-    std::vector<uint64_t> cnt(4 * n_pairs);
+    std::vector<uint64_t> cnt(4 * n_pairs + 1);
     distance_counters(a, filt_ambig, cnt.data());
+    if (sharded) {
+        cnt[4 * n_pairs] = (uint64_t)constant;
+        allreduce_u64(cnt.data(), cnt.size());
+        constant = (double)cnt[4 * n_pairs];
+    }
     for (uint64_t p = 0; p < n_pairs; p++) {
         double d = filt_ambig ? (double)cnt[4 * p + 2]
                               : (double)cnt[4 * p + 3] - (double)cnt[4 * p + 2] / 36.0;   // sum of (1 - overlap), exact rational

@@ -350,6 +350,10 @@ def distance_sharded(arr, min_freq=0.0, filt_ambig=True, group=None, as_array=Fa
     if min_freq * n >= 1.0:
         api.apply_filters(arr, min_freq, False, "no-filter", False, False)
     constant = api.apply_filters(arr, 0.0, False, "no-const", False, False)
+    if _lib_comm["ready"] and hasattr(arr, "distance_sharded"):
+        # the slabs came from the library's own exchange: its communicator also sums the counters (skagpu_distance_sharded)
+        out = arr.distance_sharded(constant, filt_ambig)
+        return out if as_array else [(float(a), float(b), int(c_), int(d_)) for a, b, c_, d_ in out.tolist()]
     cnt = arr.distance_counters(filt_ambig).astype(np.int64)
     t = torch.from_numpy(np.concatenate([cnt.reshape(-1), np.array([constant], dtype=np.int64)])).to(dev)
     dist.all_reduce(t, group=group)

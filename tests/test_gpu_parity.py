@@ -861,7 +861,9 @@ def _threads_build_slabs(samples, names, k, world, bounds=None):
                 local = S.build_from_samples(samples[lo:hi], names[lo:hi], k, True)
                 slab, stats = S.api.exchange_rows(local, lo, names)
                 tot = S.api.allreduce_u64([slab.dims()["n_rows"]])
-                out[r] = (slab.export(), stats, int(tot[0]))
+                exported = slab.export()
+                constant = S.api.apply_filters(slab, 0.0, False, "no-const", False, False)
+                out[r] = (exported, stats, int(tot[0]), slab.distance_sharded(constant, True))
             finally:
                 S.api.comm_destroy()
         except Exception as e:                                # noqa: BLE001 -- reported by the main thread
@@ -901,5 +903,11 @@ def test_library_communicator_slabs_equal_single_gpu(world):
     assert np.array_equal(np.concatenate([p[0][1] for p in parts]), rv)
     assert np.array_equal(np.concatenate([p[0][2] for p in parts]), rc_)
     assert all(p[2] == len(rk) for p in parts)              # the all-reduce of the slab sizes
+    # ska distance on the slabs (counters summed inside the library) == on the single-GPU array
+    constant = S.api.apply_filters(ref, 0.0, False, "no-const", False, False)
+    want = ref.distance(float(constant), True)
+    for p in parts:
+        got = [(float(a), float(b), int(c), int(d)) for a, b, c, d in p[3].tolist()]
+        assert got == want
     if world > 1:
         assert sum(p[1]["rows_sent"] for p in parts) == sum(p[1]["rows_received"] for p in parts) > 0
