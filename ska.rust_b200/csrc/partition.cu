@@ -72,7 +72,13 @@ __device__ __forceinline__ void tile_range(uint64_t tile, const Segs& sg, uint64
     end = min(sg.end[lo], beg + PT_TILE);
 }
 
-__global__ void __launch_bounds__(PT_THREADS)
+#ifndef SKA_HIST_MIN_CTAS
+#define SKA_HIST_MIN_CTAS 2
+#endif
+#ifndef SKA_HIST_PREFETCH
+#define SKA_HIST_PREFETCH 1
+#endif
+__global__ void __launch_bounds__(PT_THREADS, SKA_HIST_MIN_CTAS)
 part_hist_kernel(const uint64_t* __restrict__ src, uint64_t n_total, uint64_t n_tiles, Segs sg, DigitFn fn, int bits,
                  unsigned long long* __restrict__ hist /* [n_regions or 1][1 << bits] */) {
     extern __shared__ uint32_t s_cnt[];                     // [D]
@@ -92,6 +98,41 @@ part_hist_kernel(const uint64_t* __restrict__ src, uint64_t n_total, uint64_t n_
         }
         __syncthreads();
     };
+#if SKA_HIST_PREFETCH
+    // the next tile's loads are issued before this tile's records are counted (a warp issues in order: without this the
+    // loads of tile t + 1 wait behind the atomics of tile t, which wait for the loads of tile t)
+    uint64_t nx[PT_ITEMS];
+    uint64_t nbeg = 0, nend = 0; uint32_t nregion = 0;
+    if (t_beg < t_end) {
+        tile_range(t_beg, sg, n_total, nbeg, nend, nregion);
+#pragma unroll
+        for (int j = 0; j < PT_ITEMS; j++) {
+            const uint64_t i = nbeg + (uint64_t)j * PT_THREADS + threadIdx.x;
+            nx[j] = i < nend ? __ldg(src + i) : REC_SENTINEL;
+        }
+    }
+    for (uint64_t t = t_beg; t < t_end; t++) {
+        const uint64_t beg = nbeg, end = nend; const uint32_t region = nregion;
+        uint64_t rr[PT_ITEMS];
+#pragma unroll
+        for (int j = 0; j < PT_ITEMS; j++) rr[j] = nx[j];
+        if (t + 1 < t_end) {
+            tile_range(t + 1, sg, n_total, nbeg, nend, nregion);
+#pragma unroll
+            for (int j = 0; j < PT_ITEMS; j++) {
+                const uint64_t i = nbeg + (uint64_t)j * PT_THREADS + threadIdx.x;
+                nx[j] = i < nend ? __ldg(src + i) : REC_SENTINEL;
+            }
+        }
+        if (region != cur_region) { if (cur_region != PT_NONE) flush(cur_region); cur_region = region; }
+#pragma unroll
+        for (int j = 0; j < PT_ITEMS; j++) {
+            const uint64_t i = beg + (uint64_t)j * PT_THREADS + threadIdx.x;
+            const uint32_t d = i < end ? fn(rr[j]) : PT_NONE;
+            if (d != PT_NONE) atomicAdd(&s_cnt[d], 1u);
+        }
+    }
+#else
     for (uint64_t t = t_beg; t < t_end; t++) {
         uint64_t beg, end; uint32_t region;
         tile_range(t, sg, n_total, beg, end, region);
@@ -109,6 +150,7 @@ part_hist_kernel(const uint64_t* __restrict__ src, uint64_t n_total, uint64_t n_
             if (d != PT_NONE) atomicAdd(&s_cnt[d], 1u);
         }
     }
+#endif
     if (cur_region != PT_NONE) flush(cur_region);
 }
 
@@ -231,6 +273,147 @@ part_scatter_kernel(const uint64_t* __restrict__ src, uint64_t n_total, Segs sg,
     const uint32_t n_valid = s_doff[D];
     for (uint32_t slot = threadIdx.x; slot < n_valid; slot += SC_T) dst[s_gbase[s_sdig[slot]] + slot] = s_stage[slot];
 }
+
+// Second form of the same scatter (default; SKA_SCATTER_V1=1 selects the one above).  What the ncu capture of the first
+// form showed (profiles/kernels_r02_raw.csv): 0.35 instructions per cycle and scheduler, the warps waiting on shared-memory
+// results (short scoreboard 6.7 + MIO throttle 3.2 of 22.6 cycles per instruction) and on the global atomics.  Here
+//   * no digit array: the digit of a staged record is recomputed from the record when it leaves the CTA (pass 1 stages the
+//     K1 record and repacks it on the way out), which removes one 2-byte store and one 2-byte load per record;
+//   * with one thread per digit (D == SC_T) the reservation atomicAdd is issued before the scan and its result is used
+//     after the staging stores, so its round trip to L2 is hidden; the scan runs on all warps (no 8-way bank conflicts);
+//   * a pass-1 tile that straddles samples (one in a thousand) is scattered in one round per sample, so the sample id
+//     is uniform in a round and needs no per-record lookup.
+// Shared memory 36 KB per CTA instead of 45.
+template <int PASS, int BITS>
+__global__ void __launch_bounds__(SC_T, SC_MIN_CTAS)
+part_scatter2_kernel(const uint64_t* __restrict__ src, uint64_t n_total, Segs sg, DigitFn fn, int bits_rt, PackFn pk,
+                     const uint64_t* __restrict__ sample_off, uint32_t n_samples,
+                     unsigned long long* __restrict__ cursor, uint64_t* __restrict__ dst) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    const int bits = BITS ? BITS : bits_rt;
+    const uint32_t D = 1u << bits;
+    constexpr bool PER_THREAD = BITS != 0 && (1 << BITS) == SC_T;
+    uint64_t* s_stage = reinterpret_cast<uint64_t*>(smem);                       // [PT_TILE]
+    unsigned long long* s_gbase = reinterpret_cast<unsigned long long*>(s_stage + PT_TILE);   // [D]
+    uint32_t* s_doff = reinterpret_cast<uint32_t*>(s_gbase + D);                 // [D + 1]
+    uint32_t* s_acnt = s_doff + D + 1;                                           // [D]
+    __shared__ uint32_t s_sid[2];
+    __shared__ uint32_t s_wsum[SC_T / 32];
+
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint64_t beg, end; uint32_t region;
+    tile_range(blockIdx.x, sg, n_total, beg, end, region);
+    static_assert(SC_I % 2 == 0 && PT_TILE <= 65535, "two 16-bit ranks per register");
+    uint64_t rr[SC_I]; uint32_t dp[SC_I / 2];
+    const uint32_t cnt = (uint32_t)(end - beg);
+    const uint64_t* __restrict__ sp = src + beg;
+#pragma unroll
+    for (int j = 0; j < SC_I; j++) {
+        const uint32_t li = j * SC_T + threadIdx.x;
+        rr[j] = li < cnt ? __ldg(sp + li) : REC_SENTINEL;
+    }
+    for (uint32_t i = threadIdx.x; i < D; i += SC_T) s_acnt[i] = 0;
+    if (PASS == 1 && threadIdx.x == 0) {                     // sample ids of the tile's first and last position
+        uint64_t pf = beg, pl = end - 1;
+        uint32_t lo = 0, hi = n_samples;
+        while (hi - lo > 1) { uint32_t m = (lo + hi) >> 1; if (sample_off[m] <= pf) lo = m; else hi = m; }
+        s_sid[0] = lo; hi = n_samples;
+        while (hi - lo > 1) { uint32_t m = (lo + hi) >> 1; if (sample_off[m] <= pl) lo = m; else hi = m; }
+        s_sid[1] = lo;
+    }
+    __syncthreads();
+    const uint32_t sid_lo = PASS == 1 ? s_sid[0] : 0u, sid_hi = PASS == 1 ? s_sid[1] : 0u;
+
+    for (uint32_t sid = sid_lo; sid <= sid_hi; sid++) {
+        // positions of this round inside the tile (the whole tile unless it straddles samples)
+        uint32_t a = 0, b = cnt;
+        if (PASS == 1 && sid_lo != sid_hi) {
+            const uint64_t so = sample_off[sid], se = sample_off[sid + 1];
+            a = so > beg ? (uint32_t)min((uint64_t)cnt, so - beg) : 0u;
+            b = se > beg ? (uint32_t)min((uint64_t)cnt, se - beg) : 0u;
+            if (sid != sid_lo) {                             // the previous round has left the staging buffer
+                __syncthreads();
+                for (uint32_t i = threadIdx.x; i < D; i += SC_T) s_acnt[i] = 0;
+                __syncthreads();
+            }
+        }
+        // rank among the tile's records of the digit
+#pragma unroll
+        for (int j = 0; j < SC_I; j++) {
+            const uint32_t li = j * SC_T + threadIdx.x;
+            const uint64_t r = rr[j];
+            uint32_t d;
+            if (PASS == 1) d = (r == REC_SENTINEL || li < a || li >= b) ? PT_NONE : (uint32_t)(r >> fn.shift);
+            else d = li < cnt ? (fn.mask ? (uint32_t)(r >> fn.shift) & fn.mask : 0u) : PT_NONE;
+            const uint32_t rk = d != PT_NONE ? atomicAdd(&s_acnt[d], 1u) : 0xFFFFu;          // ranks are below PT_TILE <= 65535
+            if (j & 1) dp[j >> 1] |= rk << 16; else dp[j >> 1] = rk;
+        }
+        __syncthreads();
+        unsigned long long g = 0; uint32_t excl = 0;
+        if (PER_THREAD) {
+            // one thread per digit: reserve first, scan under the atomic's latency
+            const uint32_t v = s_acnt[threadIdx.x];
+            if (v) g = atomicAdd(&cursor[(size_t)region * D + threadIdx.x], (unsigned long long)v);
+            uint32_t inc = v;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { uint32_t t = __shfl_up_sync(0xFFFFFFFFu, inc, o); if (lane >= o) inc += t; }
+            if (lane == 31) s_wsum[warp] = inc;
+            __syncthreads();
+            uint32_t w = lane < warp ? s_wsum[lane & (SC_T / 32 - 1)] : 0u;
+            w = __reduce_add_sync(0xFFFFFFFFu, w);
+            excl = w + inc - v;
+            s_doff[threadIdx.x] = excl;
+            if (threadIdx.x == SC_T - 1) s_doff[D] = excl + v;
+        } else if (warp == 0) {
+            const uint32_t per = (D + 31) / 32, b0 = lane * per, e0 = min(D, b0 + per);
+            uint32_t sum = 0;
+            for (uint32_t d = b0; d < e0; d++) sum += s_acnt[d];
+            uint32_t inc = sum;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { uint32_t v = __shfl_up_sync(0xFFFFFFFFu, inc, o); if (lane >= o) inc += v; }
+            uint32_t run = inc - sum;
+            for (uint32_t d = b0; d < e0; d++) { uint32_t t = s_acnt[d]; s_doff[d] = run; run += t; }
+            if (lane == 31) s_doff[D] = inc;
+        }
+        __syncthreads();
+        if (!PER_THREAD) {
+            for (uint32_t d = threadIdx.x; d < D; d += SC_T) {
+                uint32_t tot = s_doff[d + 1] - s_doff[d];
+                if (tot) s_gbase[d] = atomicAdd(&cursor[(size_t)region * D + d], (unsigned long long)tot) - s_doff[d];
+            }
+        }
+        // stage in digit order
+#pragma unroll
+        for (int j = 0; j < SC_I; j++) {
+            const uint32_t rk = (j & 1) ? dp[j >> 1] >> 16 : dp[j >> 1] & 0xFFFFu;
+            if (rk == 0xFFFFu) continue;
+            const uint64_t r = rr[j];
+            const uint32_t d = PASS == 1 ? (uint32_t)(r >> fn.shift) : (fn.mask ? (uint32_t)(r >> fn.shift) & fn.mask : 0u);
+            s_stage[s_doff[d] + rk] = r;
+        }
+        if (PER_THREAD) s_gbase[threadIdx.x] = g - excl;
+        __syncthreads();
+        // coalesced runs out; the digit comes back out of the record
+        const uint32_t n_valid = s_doff[D];
+        const uint64_t sid_bits = (uint64_t)(sid + pk.sid_base) << 2;
+        for (uint32_t slot = threadIdx.x; slot < n_valid; slot += SC_T) {
+            const uint64_t r = s_stage[slot];
+            if (PASS == 1) {
+                const uint32_t d = (uint32_t)(r >> fn.shift);
+                const uint32_t mid = (uint32_t)__ffs((uint32_t)(r & 0xF)) - 1u;
+                dst[s_gbase[d] + slot] = (((r >> 4) & pk.low_mask) << (pk.sb + 2)) | sid_bits | mid;
+            } else {
+                const uint32_t d = fn.mask ? (uint32_t)(r >> fn.shift) & fn.mask : 0u;
+                dst[s_gbase[d] + slot] = r;
+            }
+        }
+    }
+}
+static size_t scatter2_smem(int bits) {
+    const size_t D = (size_t)1 << bits;
+    return PT_TILE * 8 + D * 8 + (D + 1) * 4 + D * 4 + 64;
+}
+static bool scatter_v1() { static const bool v = [] { const char* e = getenv("SKA_SCATTER_V1"); return e && atoi(e) != 0; }(); return v; }
 
 // ---------------------------------------------------------------------------------------------- wide records (k > 31)
 // The same two passes on 16-byte records (key of up to 124 bits << 4 | one-hot middle from K1; packed records carry
@@ -567,6 +750,10 @@ static void set_scatter_attrs() {
     SKA_CUDA(cudaFuncSetAttribute(part_scatter_kernel<2, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)scatter_smem(PT_MAX_BITS)));
     SKA_CUDA(cudaFuncSetAttribute(part_scatter_kernel<1, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)scatter_smem(8)));
     SKA_CUDA(cudaFuncSetAttribute(part_scatter_kernel<2, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)scatter_smem(8)));
+    SKA_CUDA(cudaFuncSetAttribute(part_scatter2_kernel<1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)scatter2_smem(PT_MAX_BITS)));
+    SKA_CUDA(cudaFuncSetAttribute(part_scatter2_kernel<2, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)scatter2_smem(PT_MAX_BITS)));
+    SKA_CUDA(cudaFuncSetAttribute(part_scatter2_kernel<1, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)scatter2_smem(8)));
+    SKA_CUDA(cudaFuncSetAttribute(part_scatter2_kernel<2, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)scatter2_smem(8)));
     SKA_CUDA(cudaFuncSetAttribute(part_scatter_wide_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)scatter_wide_smem(PT_MAX_BITS)));
     SKA_CUDA(cudaFuncSetAttribute(part_scatter_wide_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)scatter_wide_smem(PT_MAX_BITS)));
     done = true;
@@ -603,11 +790,18 @@ void partition_coarse(const uint64_t* rec, uint64_t n_pos, const uint64_t* d_sam
         SKA_LAUNCH((part_scatter_wide_kernel<1>), (unsigned)n_tiles1, SCW_T, scatter_wide_smem(pl.P1), rec, n_pos, none, f1, pl.P1, pw,
                    d_sample_off, n_samples_local, cur1, a);
     } else if (n_pos) {
-        if (pl.P1 == 8)
-            SKA_LAUNCH((part_scatter_kernel<1, 8>), (unsigned)n_tiles1, SC_T, scatter_smem(pl.P1), rec, n_pos, none, f1, pl.P1, pk,
+        if (scatter_v1()) {
+            if (pl.P1 == 8)
+                SKA_LAUNCH((part_scatter_kernel<1, 8>), (unsigned)n_tiles1, SC_T, scatter_smem(pl.P1), rec, n_pos, none, f1, pl.P1, pk,
+                           d_sample_off, n_samples_local, cur1, a);
+            else
+                SKA_LAUNCH((part_scatter_kernel<1, 0>), (unsigned)n_tiles1, SC_T, scatter_smem(pl.P1), rec, n_pos, none, f1, pl.P1, pk,
+                           d_sample_off, n_samples_local, cur1, a);
+        } else if (pl.P1 == 8)
+            SKA_LAUNCH((part_scatter2_kernel<1, 8>), (unsigned)n_tiles1, SC_T, scatter2_smem(pl.P1), rec, n_pos, none, f1, pl.P1, pk,
                        d_sample_off, n_samples_local, cur1, a);
         else
-            SKA_LAUNCH((part_scatter_kernel<1, 0>), (unsigned)n_tiles1, SC_T, scatter_smem(pl.P1), rec, n_pos, none, f1, pl.P1, pk,
+            SKA_LAUNCH((part_scatter2_kernel<1, 0>), (unsigned)n_tiles1, SC_T, scatter2_smem(pl.P1), rec, n_pos, none, f1, pl.P1, pk,
                        d_sample_off, n_samples_local, cur1, a);
     }
     *out = a; *d_off1 = off1; *d_tile_pref = tile_pref;
@@ -642,11 +836,18 @@ void partition_fine(const uint64_t* src, const Segs& sg, uint64_t n_tiles2, uint
         SKA_LAUNCH((part_scatter_wide_kernel<2>), (unsigned)n_tiles2, SCW_T, scatter_wide_smem(pl.P2), src, (uint64_t)0, sg, f2, pl.P2, pw,
                    (const uint64_t*)nullptr, 0u, cur2, dst);
     } else if (n_tiles2) {
-        if (pl.P2 == 8)
-            SKA_LAUNCH((part_scatter_kernel<2, 8>), (unsigned)n_tiles2, SC_T, scatter_smem(pl.P2), src, (uint64_t)0, sg, f2, pl.P2, pk,
+        if (scatter_v1()) {
+            if (pl.P2 == 8)
+                SKA_LAUNCH((part_scatter_kernel<2, 8>), (unsigned)n_tiles2, SC_T, scatter_smem(pl.P2), src, (uint64_t)0, sg, f2, pl.P2, pk,
+                           (const uint64_t*)nullptr, 0u, cur2, dst);
+            else
+                SKA_LAUNCH((part_scatter_kernel<2, 0>), (unsigned)n_tiles2, SC_T, scatter_smem(pl.P2), src, (uint64_t)0, sg, f2, pl.P2, pk,
+                           (const uint64_t*)nullptr, 0u, cur2, dst);
+        } else if (pl.P2 == 8)
+            SKA_LAUNCH((part_scatter2_kernel<2, 8>), (unsigned)n_tiles2, SC_T, scatter2_smem(pl.P2), src, (uint64_t)0, sg, f2, pl.P2, pk,
                        (const uint64_t*)nullptr, 0u, cur2, dst);
         else
-            SKA_LAUNCH((part_scatter_kernel<2, 0>), (unsigned)n_tiles2, SC_T, scatter_smem(pl.P2), src, (uint64_t)0, sg, f2, pl.P2, pk,
+            SKA_LAUNCH((part_scatter2_kernel<2, 0>), (unsigned)n_tiles2, SC_T, scatter2_smem(pl.P2), src, (uint64_t)0, sg, f2, pl.P2, pk,
                        (const uint64_t*)nullptr, 0u, cur2, dst);
     }
     *d_bucket_off = bucket_off;
