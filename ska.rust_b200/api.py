@@ -251,7 +251,7 @@ class Sample:
             _fq2, seq2, qual2, off2 = parse_fastx(file2)
             seq = np.concatenate([seq, seq2])
             if fq:
-                qual = np.concatenate([qual, qual2 if qual2 is not None else np.full(len(seq2), ord("I"), np.uint8)])
+                qual = np.concatenate([qual, qual2 if qual2 is not None else np.full(len(seq2), 0xFF, np.uint8)])   # 0xFF: no quality, always valid
             off = np.concatenate([off, off2[1:] + off[-1]])
         return cls(seq, off, qual if fq else None, n1)
 

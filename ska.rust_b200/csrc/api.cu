@@ -300,8 +300,11 @@ static std::unique_ptr<SeqBatch> upload(const ska_input_t* in, size_t n, double 
         any_qual |= in[s].qual != nullptr; all_qual &= in[s].qual != nullptr;
         n_rec_total += in[s].n_rec;
     }
-    if (any_qual && !all_qual) throw Error("mixed FASTA and FASTQ samples in one build are not supported on the device path");
+    // FASTA and FASTQ samples may share a build: is_reads is a per-sample property (ska_dict.rs:356-366); a FASTA sample of
+    // such a batch carries quality 0xFF ("no quality": every test passes, split_kmer.rs:66-71 `None => true`) and skips the count filter
     b->has_qual = any_qual;
+    if (any_qual) { b->h_is_reads.resize(n); for (size_t s = 0; s < n; s++) b->h_is_reads[s] = in[s].qual != nullptr; }
+    (void)all_qual;
     b->n_pos = b->h_sample_off[n];
     const size_t padded = padded_positions(b->n_pos);
     b->seq.alloc(padded);
@@ -367,8 +370,10 @@ static std::unique_ptr<SeqBatch> upload(const ska_input_t* in, size_t n, double 
         if (step == 1) {
             if (len) {
                 SKA_CUDA(cudaMemcpyAsync(b->seq.p + FRONT_PAD + base, in[s].seq + r0, len, cudaMemcpyHostToDevice, c.stream));
-                if (b->has_qual)
-                    SKA_CUDA(cudaMemcpyAsync(b->qual.p + FRONT_PAD + base, in[s].qual + r0, len, cudaMemcpyHostToDevice, c.stream));
+                if (b->has_qual) {
+                    if (in[s].qual) SKA_CUDA(cudaMemcpyAsync(b->qual.p + FRONT_PAD + base, in[s].qual + r0, len, cudaMemcpyHostToDevice, c.stream));
+                    else dev_fill(b->qual.p + FRONT_PAD + base, 0xFF, len);
+                }
             }
         } else {
             // --proportion-reads: keep record i of each file iff i % step == 0 (ska_dict.rs:131-141);
@@ -380,8 +385,10 @@ static std::unique_ptr<SeqBatch> upload(const ska_input_t* in, size_t n, double 
                 uint64_t o = in[s].rec_off[r] - r0, l = in[s].rec_off[r + 1] - in[s].rec_off[r];
                 if (!l) continue;
                 SKA_CUDA(cudaMemcpyAsync(b->seq.p + FRONT_PAD + base + o, in[s].seq + r0 + o, l, cudaMemcpyHostToDevice, c.stream));
-                if (b->has_qual)
-                    SKA_CUDA(cudaMemcpyAsync(b->qual.p + FRONT_PAD + base + o, in[s].qual + r0 + o, l, cudaMemcpyHostToDevice, c.stream));
+                if (b->has_qual) {
+                    if (in[s].qual) SKA_CUDA(cudaMemcpyAsync(b->qual.p + FRONT_PAD + base + o, in[s].qual + r0 + o, l, cudaMemcpyHostToDevice, c.stream));
+                    else dev_fill(b->qual.p + FRONT_PAD + base + o, 0xFF, l);
+                }
             }
         }
         for (uint64_t r = 0; r < in[s].n_rec; r++) starts.push_back(base + (in[s].rec_off[r] - r0));

@@ -127,6 +127,7 @@ struct SeqBatch {
     DevBuf<uint32_t> start_bits;      // bit p set <=> a record starts at position p; bit n_pos set
     DevBuf<uint64_t> sample_off;      // n_samples + 1 positions
     std::vector<uint64_t> h_sample_off;
+    std::vector<uint8_t> h_is_reads;  // has_qual batches: 1 = the sample's first file is FASTQ (count filter + quality tests, ska_dict.rs:356-366)
     std::vector<uint64_t> h_marks;    // record boundaries (host copy kept while an asynchronous upload reads it)
     cudaEvent_t ready = nullptr;      // asynchronous upload: recorded behind the last copy; builds wait for it
     SeqBatch() {}

@@ -80,13 +80,14 @@ __device__ __forceinline__ uint32_t bad4(uint32_t w) {
     m |= m >> 7;
     return (m | (m >> 14)) & 0xFu;
 }
-// 4 quality bytes -> 4 bits, bit i set iff NOT (qual - 33 > min_qual)   (split_kmer.rs:66-71, u8 wrap)
+// 4 quality bytes -> 4 bits, bit i set iff NOT (qual - 33 > min_qual)   (split_kmer.rs:66-71, u8 wrap).  0xFF marks a base of a
+// record that has no quality string (a FASTA file inside a read sample): `None => true` there
 __device__ __forceinline__ uint32_t badq4(uint32_t q, uint32_t min_qual) {
     uint32_t r = 0;
 #pragma unroll
     for (int i = 0; i < 4; i++) {
         uint32_t v = ((q >> (8 * i)) - 33u) & 0xFFu;
-        r |= (v > min_qual ? 0u : 1u) << i;
+        r |= ((v > min_qual || v == 222u) ? 0u : 1u) << i;              // byte 0xFF = "record without quality": always valid
     }
     return r;
 }

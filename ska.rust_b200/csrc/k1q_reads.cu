@@ -342,7 +342,7 @@ static int unique_prefix_bits(uint64_t n, uint32_t k) {
     return P;
 }
 
-void build_array_from_reads(const SeqBatch& b, uint32_t k, bool rc, uint16_t min_count, uint8_t min_qual, int qual_filter, Array& out) {
+void build_array_from_reads(const SeqBatch& b, uint32_t k, bool rc, uint16_t min_count_reads, uint8_t min_qual_reads, int qual_filter_reads, Array& out) {
     Context& c = ctx();
     const uint64_t N = b.n_samples;
     const int rw = k > 31 ? 2 : 1;                                    // words per record
@@ -356,6 +356,11 @@ void build_array_from_reads(const SeqBatch& b, uint32_t k, bool rc, uint16_t min
     for (uint64_t s = 0; s < N; s++) {
         const uint64_t lo = b.h_sample_off[s], hi = b.h_sample_off[s + 1];
         if (hi == lo) throw Error("sample " + std::to_string(s) + " has no valid sequence");   // ska_dict.rs:374-376
+        // a FASTA sample among FASTQ ones: every valid window is kept, no quality test, no count filter (ska_dict.rs:155,167 `!is_reads ||`)
+        const bool is_reads = b.h_is_reads.empty() || b.h_is_reads[s];
+        const uint16_t min_count = is_reads ? min_count_reads : (uint16_t)1;
+        const uint8_t min_qual = is_reads ? min_qual_reads : (uint8_t)0;
+        const int qual_filter = is_reads ? qual_filter_reads : 0;
         const ArenaMark sample_mark = arena_mark();
         const uint64_t tile_lo = lo / K1_T, n_tiles = (hi - 1) / K1_T - tile_lo + 1;
         const size_t n_words = n_tiles * (K1_T / 32);

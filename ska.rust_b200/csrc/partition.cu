@@ -63,6 +63,19 @@ struct DigitFn {
 };
 struct Segs { const uint64_t* tile_pref; const uint64_t* beg; const uint64_t* end; const uint32_t* region; uint32_t n; };
 
+// consecutive tiles of one CTA: the segment index only moves forward, so after the first tile no search is needed
+__device__ __forceinline__ void tile_range_next(uint64_t tile, const Segs& sg, uint64_t n_total, uint32_t& seg, uint64_t& beg, uint64_t& end, uint32_t& region) {
+    if (!sg.tile_pref) { beg = tile * PT_TILE; end = min(n_total, beg + PT_TILE); region = 0; return; }
+    if (seg == PT_NONE) {
+        uint32_t lo = 0, hi = sg.n;
+        while (hi - lo > 1) { uint32_t m = (lo + hi) >> 1; if (sg.tile_pref[m] <= tile) lo = m; else hi = m; }
+        seg = lo;
+    }
+    while (seg + 1 < sg.n && sg.tile_pref[seg + 1] <= tile) seg++;
+    region = sg.region ? sg.region[seg] : seg;
+    beg = sg.beg[seg] + (tile - sg.tile_pref[seg]) * PT_TILE;
+    end = min(sg.end[seg], beg + PT_TILE);
+}
 __device__ __forceinline__ void tile_range(uint64_t tile, const Segs& sg, uint64_t n_total, uint64_t& beg, uint64_t& end, uint32_t& region) {
     if (!sg.tile_pref) { beg = tile * PT_TILE; end = min(n_total, beg + PT_TILE); region = 0; return; }
     uint32_t lo = 0, hi = sg.n;                             // last segment with tile_pref[segment] <= tile
@@ -102,9 +115,9 @@ part_hist_kernel(const uint64_t* __restrict__ src, uint64_t n_total, uint64_t n_
     // the next tile's loads are issued before this tile's records are counted (a warp issues in order: without this the
     // loads of tile t + 1 wait behind the atomics of tile t, which wait for the loads of tile t)
     uint64_t nx[PT_ITEMS];
-    uint64_t nbeg = 0, nend = 0; uint32_t nregion = 0;
+    uint64_t nbeg = 0, nend = 0; uint32_t nregion = 0, seg = PT_NONE;
     if (t_beg < t_end) {
-        tile_range(t_beg, sg, n_total, nbeg, nend, nregion);
+        tile_range_next(t_beg, sg, n_total, seg, nbeg, nend, nregion);
 #pragma unroll
         for (int j = 0; j < PT_ITEMS; j++) {
             const uint64_t i = nbeg + (uint64_t)j * PT_THREADS + threadIdx.x;
@@ -117,7 +130,7 @@ part_hist_kernel(const uint64_t* __restrict__ src, uint64_t n_total, uint64_t n_
 #pragma unroll
         for (int j = 0; j < PT_ITEMS; j++) rr[j] = nx[j];
         if (t + 1 < t_end) {
-            tile_range(t + 1, sg, n_total, nbeg, nend, nregion);
+            tile_range_next(t + 1, sg, n_total, seg, nbeg, nend, nregion);
 #pragma unroll
             for (int j = 0; j < PT_ITEMS; j++) {
                 const uint64_t i = nbeg + (uint64_t)j * PT_THREADS + threadIdx.x;
@@ -284,7 +297,13 @@ part_scatter_kernel(const uint64_t* __restrict__ src, uint64_t n_total, Segs sg,
 //   * a pass-1 tile that straddles samples (one in a thousand) is scattered in one round per sample, so the sample id
 //     is uniform in a round and needs no per-record lookup.
 // Shared memory 36 KB per CTA instead of 45.
-template <int PASS, int BITS>
+#ifndef SKA_SC_LOAD
+#define SKA_SC_LOAD __ldg
+#endif
+// STR (pass 1 only): 0 = every tile that lies inside one sample (tiles that straddle samples return at once),
+// 1 = the straddling tiles: CTA m - 1 looks at the boundary sample_off[m] and takes its tile if it is the first boundary
+// strictly inside that tile.  Two launches, so that the common form carries no per-sample loop.
+template <int PASS, int BITS, int STR>
 __global__ void __launch_bounds__(SC_T, SC_MIN_CTAS)
 part_scatter2_kernel(const uint64_t* __restrict__ src, uint64_t n_total, Segs sg, DigitFn fn, int bits_rt, PackFn pk,
                      const uint64_t* __restrict__ sample_off, uint32_t n_samples,
@@ -295,39 +314,74 @@ part_scatter2_kernel(const uint64_t* __restrict__ src, uint64_t n_total, Segs sg
     constexpr bool PER_THREAD = BITS != 0 && (1 << BITS) == SC_T;
     uint64_t* s_stage = reinterpret_cast<uint64_t*>(smem);                       // [PT_TILE]
     unsigned long long* s_gbase = reinterpret_cast<unsigned long long*>(s_stage + PT_TILE);   // [D]
-    uint32_t* s_doff = reinterpret_cast<uint32_t*>(s_gbase + D);                 // [D + 1]
-    uint32_t* s_acnt = s_doff + D + 1;                                           // [D]
-    __shared__ uint32_t s_sid[2];
-    __shared__ uint32_t s_wsum[SC_T / 32];
+    uint32_t* s_acnt = reinterpret_cast<uint32_t*>(s_gbase + D);                 // [D] records per digit (16-byte aligned)
+    uint32_t* s_cur = s_acnt + D;                                                // [D] first slot of the digit, then its cursor
+    __shared__ uint64_t s_tr[2];
+    __shared__ uint32_t s_sid[2], s_region, s_total;
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    uint64_t beg, end; uint32_t region;
-    tile_range(blockIdx.x, sg, n_total, beg, end, region);
-    static_assert(SC_I % 2 == 0 && PT_TILE <= 65535, "two 16-bit ranks per register");
-    uint64_t rr[SC_I]; uint32_t dp[SC_I / 2];
+    uint64_t beg, end; uint32_t region = 0;
+    if (PASS == 1) {
+        uint64_t tile = blockIdx.x;
+        if (STR) {
+            const uint32_t m = blockIdx.x + 1;
+            const uint64_t p = sample_off[m];
+            tile = p / PT_TILE;
+            if (p >= n_total || p == tile * PT_TILE || sample_off[m - 1] > tile * PT_TILE) return;
+        }
+        beg = tile * PT_TILE; end = min(n_total, beg + PT_TILE);
+    } else if (!sg.tile_pref) {
+        beg = (uint64_t)blockIdx.x * PT_TILE; end = min(n_total, beg + PT_TILE);
+    } else {
+        // which segment holds this tile: every thread looks at one segment (one round of loads instead of a binary search)
+        const uint64_t tile = blockIdx.x;
+        for (uint32_t m = threadIdx.x; m < sg.n; m += SC_T) {
+            const uint64_t p0 = sg.tile_pref[m];
+            if (p0 <= tile && tile < sg.tile_pref[m + 1]) {
+                const uint64_t b0 = sg.beg[m] + (tile - p0) * PT_TILE;
+                s_tr[0] = b0; s_tr[1] = min(sg.end[m], b0 + PT_TILE);
+                s_region = sg.region ? sg.region[m] : m;
+            }
+        }
+        __syncthreads();
+        beg = s_tr[0]; end = s_tr[1]; region = s_region;
+    }
+    uint64_t rr[SC_I];
     const uint32_t cnt = (uint32_t)(end - beg);
     const uint64_t* __restrict__ sp = src + beg;
 #pragma unroll
     for (int j = 0; j < SC_I; j++) {
         const uint32_t li = j * SC_T + threadIdx.x;
-        rr[j] = li < cnt ? __ldg(sp + li) : REC_SENTINEL;
+        rr[j] = li < cnt ? SKA_SC_LOAD(sp + li) : REC_SENTINEL;
     }
     for (uint32_t i = threadIdx.x; i < D; i += SC_T) s_acnt[i] = 0;
-    if (PASS == 1 && threadIdx.x == 0) {                     // sample ids of the tile's first and last position
-        uint64_t pf = beg, pl = end - 1;
-        uint32_t lo = 0, hi = n_samples;
-        while (hi - lo > 1) { uint32_t m = (lo + hi) >> 1; if (sample_off[m] <= pf) lo = m; else hi = m; }
-        s_sid[0] = lo; hi = n_samples;
-        while (hi - lo > 1) { uint32_t m = (lo + hi) >> 1; if (sample_off[m] <= pl) lo = m; else hi = m; }
-        s_sid[1] = lo;
+    uint32_t sid_lo = 0, sid_hi = 0;
+    if (PASS == 1) {                                         // sample ids of the tile's first and last position
+        const uint64_t pf = beg, pl = end - 1;
+        if (!STR && n_samples <= SC_T) {                     // sample_off ascends: the id is the number of offsets <= position, minus one
+            const uint64_t so = threadIdx.x < n_samples ? sample_off[threadIdx.x] : ~0ULL;
+            sid_lo = (uint32_t)__syncthreads_count(so <= pf) - 1u;
+            sid_hi = (uint32_t)__syncthreads_count(so <= pl) - 1u;
+        } else {
+            if (threadIdx.x == 0) {
+                uint32_t lo = 0, hi = n_samples;
+                while (hi - lo > 1) { uint32_t m = (lo + hi) >> 1; if (sample_off[m] <= pf) lo = m; else hi = m; }
+                s_sid[0] = lo; hi = n_samples;
+                while (hi - lo > 1) { uint32_t m = (lo + hi) >> 1; if (sample_off[m] <= pl) lo = m; else hi = m; }
+                s_sid[1] = lo;
+            }
+            __syncthreads();
+            sid_lo = s_sid[0]; sid_hi = s_sid[1];
+        }
+        if (!STR && sid_lo != sid_hi) return;                // the straddling launch takes this tile
+    } else {
+        __syncthreads();
     }
-    __syncthreads();
-    const uint32_t sid_lo = PASS == 1 ? s_sid[0] : 0u, sid_hi = PASS == 1 ? s_sid[1] : 0u;
 
     for (uint32_t sid = sid_lo; sid <= sid_hi; sid++) {
         // positions of this round inside the tile (the whole tile unless it straddles samples)
         uint32_t a = 0, b = cnt;
-        if (PASS == 1 && sid_lo != sid_hi) {
+        if (PASS == 1 && STR) {
             const uint64_t so = sample_off[sid], se = sample_off[sid + 1];
             a = so > beg ? (uint32_t)min((uint64_t)cnt, so - beg) : 0u;
             b = se > beg ? (uint32_t)min((uint64_t)cnt, se - beg) : 0u;
@@ -337,64 +391,76 @@ part_scatter2_kernel(const uint64_t* __restrict__ src, uint64_t n_total, Segs sg
                 __syncthreads();
             }
         }
-        // rank among the tile's records of the digit
-#pragma unroll
-        for (int j = 0; j < SC_I; j++) {
+        // the digit of record j of this thread, PT_NONE if it takes no part in this round (pass 1: "no window here" is the
+        // all-ones record; at k = 31 its top bits are a legal digit, so the whole word is compared)
+        auto digit = [&](int j) -> uint32_t {
             const uint32_t li = j * SC_T + threadIdx.x;
             const uint64_t r = rr[j];
-            uint32_t d;
-            if (PASS == 1) d = (r == REC_SENTINEL || li < a || li >= b) ? PT_NONE : (uint32_t)(r >> fn.shift);
-            else d = li < cnt ? (fn.mask ? (uint32_t)(r >> fn.shift) & fn.mask : 0u) : PT_NONE;
-            const uint32_t rk = d != PT_NONE ? atomicAdd(&s_acnt[d], 1u) : 0xFFFFu;          // ranks are below PT_TILE <= 65535
-            if (j & 1) dp[j >> 1] |= rk << 16; else dp[j >> 1] = rk;
-        }
-        __syncthreads();
-        unsigned long long g = 0; uint32_t excl = 0;
-        if (PER_THREAD) {
-            // one thread per digit: reserve first, scan under the atomic's latency
-            const uint32_t v = s_acnt[threadIdx.x];
-            if (v) g = atomicAdd(&cursor[(size_t)region * D + threadIdx.x], (unsigned long long)v);
-            uint32_t inc = v;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) { uint32_t t = __shfl_up_sync(0xFFFFFFFFu, inc, o); if (lane >= o) inc += t; }
-            if (lane == 31) s_wsum[warp] = inc;
-            __syncthreads();
-            uint32_t w = lane < warp ? s_wsum[lane & (SC_T / 32 - 1)] : 0u;
-            w = __reduce_add_sync(0xFFFFFFFFu, w);
-            excl = w + inc - v;
-            s_doff[threadIdx.x] = excl;
-            if (threadIdx.x == SC_T - 1) s_doff[D] = excl + v;
-        } else if (warp == 0) {
-            const uint32_t per = (D + 31) / 32, b0 = lane * per, e0 = min(D, b0 + per);
-            uint32_t sum = 0;
-            for (uint32_t d = b0; d < e0; d++) sum += s_acnt[d];
-            uint32_t inc = sum;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) { uint32_t v = __shfl_up_sync(0xFFFFFFFFu, inc, o); if (lane >= o) inc += v; }
-            uint32_t run = inc - sum;
-            for (uint32_t d = b0; d < e0; d++) { uint32_t t = s_acnt[d]; s_doff[d] = run; run += t; }
-            if (lane == 31) s_doff[D] = inc;
-        }
-        __syncthreads();
-        if (!PER_THREAD) {
-            for (uint32_t d = threadIdx.x; d < D; d += SC_T) {
-                uint32_t tot = s_doff[d + 1] - s_doff[d];
-                if (tot) s_gbase[d] = atomicAdd(&cursor[(size_t)region * D + d], (unsigned long long)tot) - s_doff[d];
-            }
-        }
-        // stage in digit order
+            if (PASS == 1) return (r == REC_SENTINEL || (STR && (li < a || li >= b))) ? PT_NONE : (uint32_t)(r >> fn.shift);
+            return li < cnt ? (fn.mask ? (uint32_t)(r >> fn.shift) & fn.mask : 0u) : PT_NONE;
+        };
+        // A. records per digit
 #pragma unroll
         for (int j = 0; j < SC_I; j++) {
-            const uint32_t rk = (j & 1) ? dp[j >> 1] >> 16 : dp[j >> 1] & 0xFFFFu;
-            if (rk == 0xFFFFu) continue;
-            const uint64_t r = rr[j];
-            const uint32_t d = PASS == 1 ? (uint32_t)(r >> fn.shift) : (fn.mask ? (uint32_t)(r >> fn.shift) & fn.mask : 0u);
-            s_stage[s_doff[d] + rk] = r;
+            const uint32_t d = digit(j);
+            if (d != PT_NONE) atomicAdd(&s_acnt[d], 1u);
         }
-        if (PER_THREAD) s_gbase[threadIdx.x] = g - excl;
         __syncthreads();
-        // coalesced runs out; the digit comes back out of the record
-        const uint32_t n_valid = s_doff[D];
+        // B. exclusive scan over digits -> s_cur (the slot cursors of phase C); slice of every destination bucket
+        uint32_t n_valid;
+        if (PER_THREAD) {
+            // one thread per digit: the reservation is issued first and its result used last, so the round trip to L2
+            // lies under the scan and the staging; every warp scans all group sums itself (no second barrier)
+            const uint32_t v = s_acnt[threadIdx.x];
+            unsigned long long g = 0;
+            if (v) g = atomicAdd(&cursor[(size_t)region * D + threadIdx.x], (unsigned long long)v);
+            const uint4 q0 = reinterpret_cast<const uint4*>(s_acnt)[2 * lane], q1 = reinterpret_cast<const uint4*>(s_acnt)[2 * lane + 1];
+            const uint32_t gs = q0.x + q0.y + q0.z + q0.w + q1.x + q1.y + q1.z + q1.w;      // digits 8 * lane .. 8 * lane + 7
+            uint32_t ginc = gs, inc = v;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, ginc, o), u = __shfl_up_sync(0xFFFFFFFFu, inc, o);
+                if (lane >= o) { ginc += t; inc += u; }
+            }
+            const uint32_t base = __shfl_sync(0xFFFFFFFFu, ginc - gs, 4 * warp);            // digits below 32 * warp
+            n_valid = __shfl_sync(0xFFFFFFFFu, ginc, 31);
+            const uint32_t excl = base + inc - v;
+            s_cur[threadIdx.x] = excl;
+            __syncthreads();
+            // C. stage in digit order
+#pragma unroll
+            for (int j = 0; j < SC_I; j++) {
+                const uint32_t d = digit(j);
+                if (d != PT_NONE) s_stage[atomicAdd(&s_cur[d], 1u)] = rr[j];
+            }
+            s_gbase[threadIdx.x] = g - excl;
+        } else {
+            if (warp == 0) {
+                const uint32_t per = (D + 31) / 32, b0 = lane * per, e0 = min(D, b0 + per);
+                uint32_t sum = 0;
+                for (uint32_t d = b0; d < e0; d++) sum += s_acnt[d];
+                uint32_t inc = sum;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) { uint32_t v = __shfl_up_sync(0xFFFFFFFFu, inc, o); if (lane >= o) inc += v; }
+                uint32_t run = inc - sum;
+                for (uint32_t d = b0; d < e0; d++) { s_cur[d] = run; run += s_acnt[d]; }
+                if (lane == 31) s_total = inc;
+            }
+            __syncthreads();
+            n_valid = s_total;
+            for (uint32_t d = threadIdx.x; d < D; d += SC_T) {
+                const uint32_t tot = s_acnt[d];
+                if (tot) s_gbase[d] = atomicAdd(&cursor[(size_t)region * D + d], (unsigned long long)tot) - s_cur[d];
+            }
+            __syncthreads();                                 // the reservations read s_cur before phase C moves it
+#pragma unroll
+            for (int j = 0; j < SC_I; j++) {
+                const uint32_t d = digit(j);
+                if (d != PT_NONE) s_stage[atomicAdd(&s_cur[d], 1u)] = rr[j];
+            }
+        }
+        __syncthreads();
+        // D. coalesced runs out; the digit comes back out of the record
         const uint64_t sid_bits = (uint64_t)(sid + pk.sid_base) << 2;
         for (uint32_t slot = threadIdx.x; slot < n_valid; slot += SC_T) {
             const uint64_t r = s_stage[slot];
@@ -411,7 +477,7 @@ part_scatter2_kernel(const uint64_t* __restrict__ src, uint64_t n_total, Segs sg
 }
 static size_t scatter2_smem(int bits) {
     const size_t D = (size_t)1 << bits;
-    return PT_TILE * 8 + D * 8 + (D + 1) * 4 + D * 4 + 64;
+    return PT_TILE * 8 + D * 8 + D * 4 + D * 4 + 64;
 }
 static bool scatter_v1() { static const bool v = [] { const char* e = getenv("SKA_SCATTER_V1"); return e && atoi(e) != 0; }(); return v; }
 
@@ -750,10 +816,12 @@ static void set_scatter_attrs() {
     SKA_CUDA(cudaFuncSetAttribute(part_scatter_kernel<2, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)scatter_smem(PT_MAX_BITS)));
     SKA_CUDA(cudaFuncSetAttribute(part_scatter_kernel<1, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)scatter_smem(8)));
     SKA_CUDA(cudaFuncSetAttribute(part_scatter_kernel<2, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)scatter_smem(8)));
-    SKA_CUDA(cudaFuncSetAttribute(part_scatter2_kernel<1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)scatter2_smem(PT_MAX_BITS)));
-    SKA_CUDA(cudaFuncSetAttribute(part_scatter2_kernel<2, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)scatter2_smem(PT_MAX_BITS)));
-    SKA_CUDA(cudaFuncSetAttribute(part_scatter2_kernel<1, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)scatter2_smem(8)));
-    SKA_CUDA(cudaFuncSetAttribute(part_scatter2_kernel<2, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)scatter2_smem(8)));
+    SKA_CUDA(cudaFuncSetAttribute(part_scatter2_kernel<1, 0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)scatter2_smem(PT_MAX_BITS)));
+    SKA_CUDA(cudaFuncSetAttribute(part_scatter2_kernel<1, 0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)scatter2_smem(PT_MAX_BITS)));
+    SKA_CUDA(cudaFuncSetAttribute(part_scatter2_kernel<2, 0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)scatter2_smem(PT_MAX_BITS)));
+    SKA_CUDA(cudaFuncSetAttribute(part_scatter2_kernel<1, 8, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)scatter2_smem(8)));
+    SKA_CUDA(cudaFuncSetAttribute(part_scatter2_kernel<1, 8, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)scatter2_smem(8)));
+    SKA_CUDA(cudaFuncSetAttribute(part_scatter2_kernel<2, 8, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)scatter2_smem(8)));
     SKA_CUDA(cudaFuncSetAttribute(part_scatter_wide_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)scatter_wide_smem(PT_MAX_BITS)));
     SKA_CUDA(cudaFuncSetAttribute(part_scatter_wide_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)scatter_wide_smem(PT_MAX_BITS)));
     done = true;
@@ -797,12 +865,19 @@ void partition_coarse(const uint64_t* rec, uint64_t n_pos, const uint64_t* d_sam
             else
                 SKA_LAUNCH((part_scatter_kernel<1, 0>), (unsigned)n_tiles1, SC_T, scatter_smem(pl.P1), rec, n_pos, none, f1, pl.P1, pk,
                            d_sample_off, n_samples_local, cur1, a);
-        } else if (pl.P1 == 8)
-            SKA_LAUNCH((part_scatter2_kernel<1, 8>), (unsigned)n_tiles1, SC_T, scatter2_smem(pl.P1), rec, n_pos, none, f1, pl.P1, pk,
+        } else if (pl.P1 == 8) {
+            SKA_LAUNCH((part_scatter2_kernel<1, 8, 0>), (unsigned)n_tiles1, SC_T, scatter2_smem(pl.P1), rec, n_pos, none, f1, pl.P1, pk,
                        d_sample_off, n_samples_local, cur1, a);
-        else
-            SKA_LAUNCH((part_scatter2_kernel<1, 0>), (unsigned)n_tiles1, SC_T, scatter2_smem(pl.P1), rec, n_pos, none, f1, pl.P1, pk,
+            if (n_samples_local > 1)
+                SKA_LAUNCH((part_scatter2_kernel<1, 8, 1>), n_samples_local - 1, SC_T, scatter2_smem(pl.P1), rec, n_pos, none, f1, pl.P1, pk,
+                           d_sample_off, n_samples_local, cur1, a);
+        } else {
+            SKA_LAUNCH((part_scatter2_kernel<1, 0, 0>), (unsigned)n_tiles1, SC_T, scatter2_smem(pl.P1), rec, n_pos, none, f1, pl.P1, pk,
                        d_sample_off, n_samples_local, cur1, a);
+            if (n_samples_local > 1)
+                SKA_LAUNCH((part_scatter2_kernel<1, 0, 1>), n_samples_local - 1, SC_T, scatter2_smem(pl.P1), rec, n_pos, none, f1, pl.P1, pk,
+                           d_sample_off, n_samples_local, cur1, a);
+        }
     }
     *out = a; *d_off1 = off1; *d_tile_pref = tile_pref;
     timer().end();
@@ -844,10 +919,10 @@ void partition_fine(const uint64_t* src, const Segs& sg, uint64_t n_tiles2, uint
                 SKA_LAUNCH((part_scatter_kernel<2, 0>), (unsigned)n_tiles2, SC_T, scatter_smem(pl.P2), src, (uint64_t)0, sg, f2, pl.P2, pk,
                            (const uint64_t*)nullptr, 0u, cur2, dst);
         } else if (pl.P2 == 8)
-            SKA_LAUNCH((part_scatter2_kernel<2, 8>), (unsigned)n_tiles2, SC_T, scatter2_smem(pl.P2), src, (uint64_t)0, sg, f2, pl.P2, pk,
+            SKA_LAUNCH((part_scatter2_kernel<2, 8, 0>), (unsigned)n_tiles2, SC_T, scatter2_smem(pl.P2), src, (uint64_t)0, sg, f2, pl.P2, pk,
                        (const uint64_t*)nullptr, 0u, cur2, dst);
         else
-            SKA_LAUNCH((part_scatter2_kernel<2, 0>), (unsigned)n_tiles2, SC_T, scatter2_smem(pl.P2), src, (uint64_t)0, sg, f2, pl.P2, pk,
+            SKA_LAUNCH((part_scatter2_kernel<2, 0, 0>), (unsigned)n_tiles2, SC_T, scatter2_smem(pl.P2), src, (uint64_t)0, sg, f2, pl.P2, pk,
                        (const uint64_t*)nullptr, 0u, cur2, dst);
     }
     *d_bucket_off = bucket_off;

@@ -146,7 +146,7 @@ void append(Records& a, const Records& b) {
     a.seq.insert(a.seq.end(), b.seq.begin(), b.seq.end());
     if (a.is_fastq) {
         if (b.is_fastq) a.qual.insert(a.qual.end(), b.qual.begin(), b.qual.end());
-        else a.qual.insert(a.qual.end(), b.seq.size(), (uint8_t)'I');
+        else a.qual.insert(a.qual.end(), b.seq.size(), (uint8_t)0xFF);   // no quality: every quality test passes (split_kmer.rs:66-71)
     }
     for (size_t i = 1; i < b.rec_off.size(); i++) a.rec_off.push_back(base + b.rec_off[i]);
 }

@@ -209,3 +209,28 @@ def test_kmer_count_histogram_matches_dictionary(gold_in, k, rc):
             exp[c - 1] += 1
     got = S.api.kmer_count_hist(big, k, rc)
     assert np.array_equal(got, exp)
+
+
+@pytest.mark.parametrize("min_count,qual_filter", [(3, "strict"), (1, "middle")])
+def test_build_mixes_fasta_and_fastq_samples(min_count, qual_filter):
+    """is_reads is a per-sample property (ska_dict.rs:356-366): an assembly next to read sets in one build keeps every
+    valid window (no count filter, no quality test), the read sets are filtered."""
+    from ska_rust_b200 import synth
+    genomes = synth.star_genomes(3, 20_000, seed=0x5CA2000C, snp_rate=0.002)
+    gs0, os0 = make_reads_sample(genomes[0], 3000, 0.01, 11)
+    gs2, os2 = make_reads_sample(genomes[2], 3000, 0.01, 12)
+    asm = genomes[1]
+    off = np.array([0, 7000, 7000 + 31, len(asm)], dtype=np.uint64)          # three contigs, one of exactly k bases
+    g_asm = S.Sample(asm, off)
+    o_asm = O.SampleData([(asm[int(off[i]):int(off[i + 1])].tobytes(), None) for i in range(3)], is_reads=False)
+    names = ["reads0", "assembly", "reads2"]
+    q = S.QualOpts(min_count=min_count, min_qual=20, qual_filter=qual_filter)
+    g = S.build_from_samples([gs0, g_asm, gs2], names, 31, True, q)
+    o = O.OracleArray.build([os0, o_asm, os2], names, k=31, rc=True, min_count=min_count, min_qual=20, qual_filter=qual_filter)
+    same(g, o)
+    # the assembly's column is what a FASTA-only build gives
+    alone = S.build_from_samples([g_asm], ["assembly"], 31, True)
+    gk, gv, _ = g.export()
+    ak, av, _ = alone.export()
+    col = {int(k_): int(v) for k_, v in zip(gk, gv[:, 1]) if v != ord("-")}
+    assert col == {int(k_): int(v) for k_, v in zip(ak, av[:, 0])}
