@@ -27,6 +27,10 @@ namespace ska {
 constexpr int MG_THREADS = 256;
 constexpr int MG_UNROLL = 4;               // records probed together by a thread (independent shared-memory loads overlap)
 constexpr int MG_PREFETCH = 8;             // records a thread keeps in flight from HBM while it works on the previous batch
+#ifndef SKA_MG_CHUNK_LOG
+#define SKA_MG_CHUNK_LOG 31
+#endif
+constexpr uint64_t MG_CHUNK = 1ULL << SKA_MG_CHUNK_LOG;   // records walked with 32-bit positions (tests build a small value to cross chunks)
 constexpr int COUNT_CAP = 4096;             // home slots of the counting pass
 constexpr int COUNT_LOG_CAP = 12;
 constexpr int COUNT_TAIL = 256;             // slots past the last home slot: probing never wraps, so slot order follows key order
@@ -38,8 +42,10 @@ static_assert(COUNT_GROUPS % (MG_THREADS / 32) == 0, "slot groups must divide ev
 constexpr size_t COUNT_SMEM = (size_t)COUNT_SLOTS * 8 + (size_t)COUNT_LIST * 2;
 constexpr uint64_t KEY_EMPTY = ~0ULL;
 
+// slot of a key in a table of 2^log_cap slots (log_cap >= 1): the top bits of a 32-bit multiplicative mix of both halves
+// (three instructions; the 64-bit golden-ratio product this replaces took five and was 5 % of the emit kernel)
 __device__ __forceinline__ uint32_t hash_slot(uint64_t key, int log_cap) {
-    return (uint32_t)((key * 0x9E3779B97F4A7C15ULL) >> (64 - log_cap));
+    return ((uint32_t)key * 0x9E3779B1u + (uint32_t)(key >> 32) * 0x85EBCA77u) >> (32 - log_cap);
 }
 
 // A work item = a contiguous record range (one prefix bucket) restricted to an inclusive key range.
@@ -86,11 +92,16 @@ bucket_count_kernel(const uint64_t* __restrict__ rec, const Item* __restrict__ i
     if (it.beg == it.end) { if (threadIdx.x == 0) n_rows[blockIdx.x] = 0; return; }
     // HBM latency is hidden by depth, not occupancy: the next MG_PREFETCH records of a thread are in flight while it
     // probes the previous ones
+    // The records are walked in chunks of at most 2^31 (one chunk, in practice), so that the positions inside a chunk are
+    // 32-bit: the 64-bit index arithmetic was 18 % of this kernel's instructions.
     uint64_t nx[MG_PREFETCH];
+    const uint64_t* __restrict__ rc = rec + it.beg;
+    uint32_t cn = (uint32_t)min(it.end - it.beg, MG_CHUNK);
+    uint64_t rem = it.end - it.beg - cn;                     // records after this chunk
 #pragma unroll
     for (int j = 0; j < MG_PREFETCH; j++) {
-        const uint64_t i = it.beg + (uint64_t)j * MG_THREADS + threadIdx.x;
-        nx[j] = i < it.end ? rec[i] : ~0ULL;
+        const uint32_t o = (uint32_t)j * MG_THREADS + threadIdx.x;
+        nx[j] = o < cn ? rc[o] : ~0ULL;
     }
     {
         uint4* t4 = reinterpret_cast<uint4*>(s_tab);
@@ -103,16 +114,17 @@ bucket_count_kernel(const uint64_t* __restrict__ rec, const Item* __restrict__ i
     const int range_bits = width ? 64 - __clzll((long long)width) : 0;
     const int shift = max(0, range_bits - COUNT_LOG_CAP);
     __syncthreads();
-    for (uint64_t b0 = it.beg; b0 < it.end; b0 += (uint64_t)MG_PREFETCH * MG_THREADS) {
+    while (true) {
+    for (uint32_t o0 = 0; o0 < cn; o0 += MG_PREFETCH * MG_THREADS) {
         uint64_t rr[MG_PREFETCH];
 #pragma unroll
         for (int j = 0; j < MG_PREFETCH; j++) rr[j] = nx[j];
-        const uint64_t b1 = b0 + (uint64_t)MG_PREFETCH * MG_THREADS;
-        if (b1 < it.end) {
+        const uint32_t o1 = o0 + MG_PREFETCH * MG_THREADS;
+        if (o1 < cn) {
 #pragma unroll
             for (int j = 0; j < MG_PREFETCH; j++) {
-                const uint64_t i = b1 + (uint64_t)j * MG_THREADS + threadIdx.x;
-                nx[j] = i < it.end ? rec[i] : ~0ULL;
+                const uint32_t o = o1 + (uint32_t)j * MG_THREADS + threadIdx.x;
+                nx[j] = o < cn ? rc[o] : ~0ULL;
             }
         }
 #pragma unroll
@@ -124,7 +136,7 @@ bucket_count_kernel(const uint64_t* __restrict__ rec, const Item* __restrict__ i
             for (int j = 0; j < MG_UNROLL; j++) {
                 kk[j] = rr[h + j] >> (sb + 2);
                 const uint64_t d = kk[j] - lo_l;                    // one unsigned compare covers both ends of the key range
-                ok[j] = (b0 + (uint64_t)(h + j) * MG_THREADS + threadIdx.x < it.end) && d <= width;
+                ok[j] = (o0 + (uint32_t)(h + j) * MG_THREADS + threadIdx.x < cn) && d <= width;
                 sl[j] = ok[j] ? (uint32_t)(d >> shift) : 0u;
             }
             // a present key sits at its home slot or, displaced once, right after it (home + 1 < COUNT_SLOTS always): both are
@@ -157,6 +169,14 @@ bucket_count_kernel(const uint64_t* __restrict__ rec, const Item* __restrict__ i
                 }
                 __syncwarp();          // lanes that inserted rejoin the others before the next record (they would otherwise stay apart)
             }
+        }
+    }
+        if (rem == 0) break;                                 // next chunk (items of 2^31 records and more only)
+        rc += cn; cn = (uint32_t)min(rem, MG_CHUNK); rem -= cn;
+#pragma unroll
+        for (int j = 0; j < MG_PREFETCH; j++) {
+            const uint32_t o = (uint32_t)j * MG_THREADS + threadIdx.x;
+            nx[j] = o < cn ? rc[o] : ~0ULL;
         }
     }
     __syncthreads();
@@ -565,10 +585,13 @@ bucket_emit_smem_kernel(const uint64_t* __restrict__ rec, const Item* __restrict
     if (threadIdx.x == 0) s_anypal = 0;
 
     uint64_t nx[MG_PREFETCH];                                     // first records: in flight while the table is set up
+    const uint64_t* __restrict__ rp = rec + beg;                  // chunks of at most 2^31 records: 32-bit positions inside (see bucket_count_kernel)
+    uint32_t n = (uint32_t)min(end - beg, MG_CHUNK);
+    uint64_t rem = end - beg - n;
 #pragma unroll
     for (int j = 0; j < MG_PREFETCH; j++) {
-        const uint64_t i = beg + (uint64_t)j * MG_THREADS + threadIdx.x;
-        nx[j] = i < end ? rec[i] : ~0ULL;
+        const uint32_t o = (uint32_t)j * MG_THREADS + threadIdx.x;
+        nx[j] = o < n ? rp[o] : ~0ULL;
     }
     {
         uint4* t4 = reinterpret_cast<uint4*>(s_tab);
@@ -594,16 +617,18 @@ bucket_emit_smem_kernel(const uint64_t* __restrict__ rec, const Item* __restrict
 
     // 2. records -> base sets
     const uint32_t sid_mask = (1u << sb) - 1u;
-    for (uint64_t b0 = beg; b0 < end; b0 += (uint64_t)MG_PREFETCH * MG_THREADS) {
+    const uint32_t word_mask = sid_mask >> 3, bit_mask = sb >= 3 ? 31u : (1u << (sb + 2)) - 1u;   // fewer than 8 samples: key bits follow at once
+    while (true) {
+    for (uint32_t o0 = 0; o0 < n; o0 += MG_PREFETCH * MG_THREADS) {
         uint64_t rr[MG_PREFETCH];
 #pragma unroll
         for (int j = 0; j < MG_PREFETCH; j++) rr[j] = nx[j];
-        const uint64_t b1 = b0 + (uint64_t)MG_PREFETCH * MG_THREADS;
-        if (b1 < end) {
+        const uint32_t o1 = o0 + MG_PREFETCH * MG_THREADS;
+        if (o1 < n) {
 #pragma unroll
             for (int j = 0; j < MG_PREFETCH; j++) {
-                const uint64_t i = b1 + (uint64_t)j * MG_THREADS + threadIdx.x;
-                nx[j] = i < end ? rec[i] : ~0ULL;
+                const uint32_t o = o1 + (uint32_t)j * MG_THREADS + threadIdx.x;
+                nx[j] = o < n ? rp[o] : ~0ULL;
             }
         }
 #pragma unroll
@@ -624,7 +649,7 @@ bucket_emit_smem_kernel(const uint64_t* __restrict__ rec, const Item* __restrict
             }
 #pragma unroll
             for (int j = 0; j < MG_UNROLL; j++) {                  // longer collision chains: walk on (rare); bounded so that a foreign key cannot hang the CTA
-                const bool live = b0 + (uint64_t)(h + j) * MG_THREADS + threadIdx.x < end;
+                const bool live = o0 + (uint32_t)(h + j) * MG_THREADS + threadIdx.x < n;
                 uint32_t probes = 0;
                 while (live && cur[j] != kk[j] && probes < cap) { sl[j] = (sl[j] + 1) & (cap - 1); cur[j] = s_tab[sl[j]]; probes++; }
                 if (!live || cur[j] != kk[j]) kk[j] = KEY_EMPTY;
@@ -635,11 +660,21 @@ bucket_emit_smem_kernel(const uint64_t* __restrict__ rec, const Item* __restrict
 #pragma unroll
             for (int j = 0; j < MG_UNROLL; j++) {
                 if (kk[j] != KEY_EMPTY) {
-                    const uint32_t smp = (uint32_t)(rr[h + j] >> 2) & sid_mask;
-                    atomicOr(&s_sets[rk[j] * stride_w + (smp >> 3)], (1u << (uint32_t)(rr[h + j] & 3)) << (4 * (smp & 7)));
+                    // record = key_low | sample << 2 | middle: its low five bits are the bit of (sample & 7, middle) inside the set
+                    // word, the next bits of the sample id the word of the row
+                    const uint32_t lo = (uint32_t)rr[h + j];
+                    atomicOr(&s_sets[rk[j] * stride_w + ((lo >> 5) & word_mask)], 1u << (lo & bit_mask));
                 }
             }
             __syncwarp();
+        }
+    }
+        if (rem == 0) break;                                      // next chunk (items of 2^31 records and more only)
+        rp += n; n = (uint32_t)min(rem, MG_CHUNK); rem -= n;
+#pragma unroll
+        for (int j = 0; j < MG_PREFETCH; j++) {
+            const uint32_t o = (uint32_t)j * MG_THREADS + threadIdx.x;
+            nx[j] = o < n ? rp[o] : ~0ULL;
         }
     }
     __syncthreads();
@@ -1081,7 +1116,13 @@ static void merge_items(const uint64_t* rec, Item* items, uint32_t n_items, int 
     out.n_rows = out.n_keys = total_rows;
     out.keys.alloc(total_rows); out.variants.alloc(total_rows * n_samples); out.counts.alloc(total_rows);
     if (total_rows) {
+        // table slots per distinct key: at 2 a key sits further than one slot from its home in ~2.5 % of the cases, which sends
+        // more than half of the warps' probes into the chain walk (16 % of the kernel's instructions, profiles/); sparser
+        // tables cost 10 B of shared memory per slot
+        uint32_t cap_factor = 4;
+        if (const char* e = getenv("SKA_EMIT_CAP_FACTOR")) cap_factor = (uint32_t)std::max(2, atoi(e));
         int log_cap = 6;
+        while ((1u << log_cap) < cap_factor * max_u && log_cap < max_log_cap) log_cap++;
         while ((1u << log_cap) < 2 * max_u) log_cap++;
         if (log_cap > max_log_cap) throw Error("internal: item larger than the shared-memory table");
         const uint32_t stride_w = (uint32_t)((n_samples + 7) / 8) | 1u;    // odd: rows fall on different banks
@@ -1099,7 +1140,7 @@ static void merge_items(const uint64_t* rec, Item* items, uint32_t n_items, int 
             if (const char* e = getenv("SKA_EMIT_SMALL_BYTES")) small_bytes = (size_t)std::max(0, atoi(e));   // tests: classes at small sizes
             if (smem_sets > small_bytes + small_bytes / 6 && !(getenv("SKA_EMIT_ONE_CLASS") && atoi(getenv("SKA_EMIT_ONE_CLASS")))) {
                 for (int lc = 6; lc <= log_cap; lc++) {
-                    const uint32_t uu = 1u << (lc - 1);                        // table at most half full
+                    const uint32_t uu = (1u << lc) / cap_factor;               // table at most 1 / cap_factor full
                     if (uu < max_u && emit_smem_bytes(lc, uu, stride_w) <= small_bytes) { u_small = uu; log_cap_small = lc; }
                 }
             }
