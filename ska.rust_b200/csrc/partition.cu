@@ -85,6 +85,25 @@ __device__ __forceinline__ void tile_range(uint64_t tile, const Segs& sg, uint64
     end = min(sg.end[lo], beg + PT_TILE);
 }
 
+// The tile's range found by the whole CTA: every thread looks at one segment, so the lookup is one round of loads (a binary
+// search is log2(segments) dependent loads in front of the tile's own loads).  Contains a barrier: call it from every thread.
+template <int THREADS>
+__device__ __forceinline__ void tile_range_coop(uint64_t tile, const Segs& sg, uint64_t n_total, uint64_t& beg, uint64_t& end, uint32_t& region) {
+    if (!sg.tile_pref) { beg = tile * PT_TILE; end = min(n_total, beg + PT_TILE); region = 0; return; }
+    __shared__ uint64_t s_tr[2];
+    __shared__ uint32_t s_trr;
+    for (uint32_t m = threadIdx.x; m < sg.n; m += THREADS) {
+        const uint64_t p0 = sg.tile_pref[m];
+        if (p0 <= tile && tile < sg.tile_pref[m + 1]) {
+            const uint64_t b0 = sg.beg[m] + (tile - p0) * PT_TILE;
+            s_tr[0] = b0; s_tr[1] = min(sg.end[m], b0 + PT_TILE);
+            s_trr = sg.region ? sg.region[m] : m;
+        }
+    }
+    __syncthreads();
+    beg = s_tr[0]; end = s_tr[1]; region = s_trr;
+}
+
 #ifndef SKA_HIST_MIN_CTAS
 #define SKA_HIST_MIN_CTAS 2
 #endif
@@ -316,8 +335,7 @@ part_scatter2_kernel(const uint64_t* __restrict__ src, uint64_t n_total, Segs sg
     unsigned long long* s_gbase = reinterpret_cast<unsigned long long*>(s_stage + PT_TILE);   // [D]
     uint32_t* s_acnt = reinterpret_cast<uint32_t*>(s_gbase + D);                 // [D] records per digit (16-byte aligned)
     uint32_t* s_cur = s_acnt + D;                                                // [D] first slot of the digit, then its cursor
-    __shared__ uint64_t s_tr[2];
-    __shared__ uint32_t s_sid[2], s_region, s_total;
+    __shared__ uint32_t s_sid[2], s_total;
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     uint64_t beg, end; uint32_t region = 0;
@@ -330,21 +348,8 @@ part_scatter2_kernel(const uint64_t* __restrict__ src, uint64_t n_total, Segs sg
             if (p >= n_total || p == tile * PT_TILE || sample_off[m - 1] > tile * PT_TILE) return;
         }
         beg = tile * PT_TILE; end = min(n_total, beg + PT_TILE);
-    } else if (!sg.tile_pref) {
-        beg = (uint64_t)blockIdx.x * PT_TILE; end = min(n_total, beg + PT_TILE);
     } else {
-        // which segment holds this tile: every thread looks at one segment (one round of loads instead of a binary search)
-        const uint64_t tile = blockIdx.x;
-        for (uint32_t m = threadIdx.x; m < sg.n; m += SC_T) {
-            const uint64_t p0 = sg.tile_pref[m];
-            if (p0 <= tile && tile < sg.tile_pref[m + 1]) {
-                const uint64_t b0 = sg.beg[m] + (tile - p0) * PT_TILE;
-                s_tr[0] = b0; s_tr[1] = min(sg.end[m], b0 + PT_TILE);
-                s_region = sg.region ? sg.region[m] : m;
-            }
-        }
-        __syncthreads();
-        beg = s_tr[0]; end = s_tr[1]; region = s_region;
+        tile_range_coop<SC_T>(blockIdx.x, sg, n_total, beg, end, region);
     }
     uint64_t rr[SC_I];
     const uint32_t cnt = (uint32_t)(end - beg);
@@ -513,12 +518,36 @@ part_hist_wide_kernel(const uint64_t* __restrict__ src, uint64_t n_total, uint64
         }
         __syncthreads();
     };
-    for (uint64_t t = t_beg; t < t_end; t++) {
-        uint64_t beg, end; uint32_t region;
-        tile_range(t, sg, n_total, beg, end, region);
+    // as in part_hist_kernel: the next records are in flight while these are counted, and the segment index walks forward.
+    // The unit is half a tile (four 16-byte records per thread in flight + four being counted: 32 registers).
+    constexpr int WI = PT_ITEMS / 2;
+    constexpr uint32_t HALF = PT_TILE / 2;
+    static_assert(WI * PT_THREADS == (int)HALF, "half tiles");
+    ulonglong2 nx[WI];
+    uint64_t nbeg = 0, nend = 0; uint32_t nregion = 0, seg = PT_NONE;
+    auto next_unit = [&](uint64_t u) {
+        uint64_t b, e;
+        tile_range_next(u >> 1, sg, n_total, seg, b, e, nregion);
+        nbeg = min(e, b + (u & 1) * HALF); nend = min(e, nbeg + HALF);
+#pragma unroll
+        for (int j = 0; j < WI; j++) {
+            const uint64_t i = nbeg + (uint64_t)j * PT_THREADS + threadIdx.x;
+            nx[j] = i < nend ? __ldg(reinterpret_cast<const ulonglong2*>(src) + i) : make_ulonglong2(~0ULL, ~0ULL);
+        }
+    };
+    const uint64_t u_beg = 2 * t_beg, u_end = 2 * t_end;
+    if (u_beg < u_end) next_unit(u_beg);
+    for (uint64_t u = u_beg; u < u_end; u++) {
+        const uint64_t beg = nbeg, end = nend; const uint32_t region = nregion;
+        ulonglong2 rr[WI];
+#pragma unroll
+        for (int j = 0; j < WI; j++) rr[j] = nx[j];
+        if (u + 1 < u_end) next_unit(u + 1);
         if (region != cur_region) { if (cur_region != PT_NONE) flush(cur_region); cur_region = region; }
-        for (uint64_t i = beg + threadIdx.x; i < end; i += PT_THREADS) {
-            const uint32_t d = digit128(ld_rec128(src, i), fn.pass, fn.shift, fn.mask);
+#pragma unroll
+        for (int j = 0; j < WI; j++) {
+            const uint64_t i = beg + (uint64_t)j * PT_THREADS + threadIdx.x;
+            const uint32_t d = i < end ? digit128(((u128)rr[j].y << 64) | rr[j].x, fn.pass, fn.shift, fn.mask) : PT_NONE;
             if (d != PT_NONE) atomicAdd(&s_cnt[d], 1u);
         }
     }
@@ -543,7 +572,7 @@ part_scatter_wide_kernel(const uint64_t* __restrict__ src, uint64_t n_total, Seg
     __shared__ uint32_t s_sid[2];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     uint64_t beg, end; uint32_t region;
-    tile_range(blockIdx.x, sg, n_total, beg, end, region);
+    tile_range_coop<SCW_T>(blockIdx.x, sg, n_total, beg, end, region);
     const uint32_t cnt = (uint32_t)(end - beg);
     u128 rr[SCW_I]; uint32_t dp[SCW_I];
 #pragma unroll
@@ -623,7 +652,7 @@ part_scatter_wide_direct_kernel(const uint64_t* __restrict__ src, uint64_t n_tot
     unsigned long long* s_gbase = reinterpret_cast<unsigned long long*>(smem);   // [D]
     uint32_t* s_acnt = reinterpret_cast<uint32_t*>(s_gbase + D);                 // [D]
     uint64_t beg, end; uint32_t region;
-    tile_range(blockIdx.x, sg, n_total, beg, end, region);
+    tile_range_coop<SCD_T>(blockIdx.x, sg, n_total, beg, end, region);
     const uint32_t cnt = (uint32_t)(end - beg);
     ulonglong2 rr[SCD_I]; uint32_t dp[SCD_I];
     const ulonglong2* src2 = reinterpret_cast<const ulonglong2*>(src) + beg;
