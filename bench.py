@@ -47,7 +47,7 @@ K1_ALGO_BYTES_PER_BASE = 10.0     # read 1 B ASCII + write 9 B (u6
 def ncu_traffic(kernel):
     """DRAM bytes per launch of `kernel` from the newest committed ncu --set full capture (profiles/ncu_summary_r*.json,
     same workload size), or None."""
-    for rnd in ("r02", "r01"):
+    for rnd in ("r02b", "r02", "r01"):
         p = os.path.join(ROOT, "profiles", f"ncu_summary_{rnd}.json")
         for name in (kernel if isinstance(kernel, (list, tuple)) else [kernel]):
             try:
@@ -209,17 +209,17 @@ def bind_to_gpu_numa_node(local_rank):
 STAGE_KERNELS = {
     "k1_extract": ("k1_extract_kernel", lambda n, R, C, Rk, N: 10.0 * n),
     "hist1": ("part_hist_kernel", lambda n, R, C, Rk, N: 8.0 * n),
-    "scatter1": ("part_scatter_kernel<1>", lambda n, R, C, Rk, N: 16.0 * n),
+    "scatter1": ("part_scatter2_kernel<1>", lambda n, R, C, Rk, N: 16.0 * n),
     "hist2": ("part_hist_kernel", lambda n, R, C, Rk, N: 8.0 * n),
-    "scatter2": ("part_scatter_kernel<2>", lambda n, R, C, Rk, N: 16.0 * n),
+    "scatter2": ("part_scatter2_kernel<2>", lambda n, R, C, Rk, N: 16.0 * n),
     "count": ("bucket_count_kernel", lambda n, R, C, Rk, N: 8.0 * n + 8.0 * R),
     "emit": ("bucket_emit_smem_kernel", lambda n, R, C, Rk, N: 9.0 * n + R * (16.0 + C)),
     "merge": ("bucket_merge_kernel", lambda n, R, C, Rk, N: 9.0 * n + R * (16.0 + C)),
     "transpose": ("transpose_words_kernel", lambda n, R, C, Rk, N: 2.0 * Rk * N),
 }
 # kernel -> its entries in profiles/ncu_summary_r02.json / _r01.json (the first one found is used)
-NCU_NAMES = {"k1_extract_kernel": ["k1_extract<31, 0, 1, 1, 0>", "k1_extract"], "part_scatter_kernel<1>": ["part_scatter<1, 8>", "part_scatter"],
-             "part_scatter_kernel<2>": ["part_scatter<2, 8>"], "part_hist_kernel": ["part_hist"], "bucket_count_kernel": ["bucket_count"],
+NCU_NAMES = {"k1_extract_kernel": ["k1_extract<31, 0, 1, 1, 0>", "k1_extract"], "part_scatter2_kernel<1>": ["part_scatter2<1, 8, 0>", "part_scatter<1, 8>"],
+             "part_scatter2_kernel<2>": ["part_scatter2<2, 8, 0>", "part_scatter<2, 8>"], "part_hist_kernel": ["part_hist"], "bucket_count_kernel": ["bucket_count"],
              "bucket_emit_smem_kernel": ["bucket_emit_smem"], "transpose_words_kernel": ["transpose_words"]}
 
 

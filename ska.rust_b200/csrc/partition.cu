@@ -339,6 +339,8 @@ part_scatter2_kernel(const uint64_t* __restrict__ src, uint64_t n_total, Segs sg
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     uint64_t beg, end; uint32_t region = 0;
+    for (uint32_t i = threadIdx.x; i < D; i += SC_T) s_acnt[i] = 0;     // visible after the first barrier below
+    bool synced = false;
     if (PASS == 1) {
         uint64_t tile = blockIdx.x;
         if (STR) {
@@ -349,6 +351,7 @@ part_scatter2_kernel(const uint64_t* __restrict__ src, uint64_t n_total, Segs sg
         }
         beg = tile * PT_TILE; end = min(n_total, beg + PT_TILE);
     } else {
+        synced = sg.tile_pref != nullptr;                    // the lookup over segments contains a barrier
         tile_range_coop<SC_T>(blockIdx.x, sg, n_total, beg, end, region);
     }
     uint64_t rr[SC_I];
@@ -359,14 +362,13 @@ part_scatter2_kernel(const uint64_t* __restrict__ src, uint64_t n_total, Segs sg
         const uint32_t li = j * SC_T + threadIdx.x;
         rr[j] = li < cnt ? SKA_SC_LOAD(sp + li) : REC_SENTINEL;
     }
-    for (uint32_t i = threadIdx.x; i < D; i += SC_T) s_acnt[i] = 0;
     uint32_t sid_lo = 0, sid_hi = 0;
     if (PASS == 1) {                                         // sample ids of the tile's first and last position
         const uint64_t pf = beg, pl = end - 1;
         if (!STR && n_samples <= SC_T) {                     // sample_off ascends: the id is the number of offsets <= position, minus one
             const uint64_t so = threadIdx.x < n_samples ? sample_off[threadIdx.x] : ~0ULL;
-            sid_lo = (uint32_t)__syncthreads_count(so <= pf) - 1u;
             sid_hi = (uint32_t)__syncthreads_count(so <= pl) - 1u;
+            sid_lo = sample_off[sid_hi] <= pf ? sid_hi : sid_hi - 1u;     // only "the same sample or not" matters here
         } else {
             if (threadIdx.x == 0) {
                 uint32_t lo = 0, hi = n_samples;
@@ -379,7 +381,7 @@ part_scatter2_kernel(const uint64_t* __restrict__ src, uint64_t n_total, Segs sg
             sid_lo = s_sid[0]; sid_hi = s_sid[1];
         }
         if (!STR && sid_lo != sid_hi) return;                // the straddling launch takes this tile
-    } else {
+    } else if (!synced) {
         __syncthreads();
     }
 
