@@ -210,7 +210,7 @@ STAGE_KERNELS = {
     "k1_extract": ("k1_extract_kernel", lambda n, R, C, Rk, N: 10.0 * n),
     "hist1": ("part_hist_kernel", lambda n, R, C, Rk, N: 8.0 * n),
     "scatter1": ("part_scatter2_kernel<1>", lambda n, R, C, Rk, N: 16.0 * n),
-    "hist2": ("part_hist_kernel", lambda n, R, C, Rk, N: 8.0 * n),
+    "hist2": ("part_hist_bytes_kernel", lambda n, R, C, Rk, N: 1.0 * n),     # reads the digit bytes the first scatter wrote (SKA_HIST2_BYTES=0: 8 B)
     "scatter2": ("part_scatter2_kernel<2>", lambda n, R, C, Rk, N: 16.0 * n),
     "count": ("bucket_count_kernel", lambda n, R, C, Rk, N: 8.0 * n + 8.0 * R),
     "emit": ("bucket_emit_smem_kernel", lambda n, R, C, Rk, N: 9.0 * n + R * (16.0 + C)),
@@ -219,7 +219,7 @@ STAGE_KERNELS = {
 }
 # kernel -> its entries in profiles/ncu_summary_r02.json / _r01.json (the first one found is used)
 NCU_NAMES = {"k1_extract_kernel": ["k1_extract<31, 0, 1, 1, 0>", "k1_extract"], "part_scatter2_kernel<1>": ["part_scatter2<1, 8, 0>", "part_scatter<1, 8>"],
-             "part_scatter2_kernel<2>": ["part_scatter2<2, 8, 0>", "part_scatter<2, 8>"], "part_hist_kernel": ["part_hist"], "bucket_count_kernel": ["bucket_count"],
+             "part_scatter2_kernel<2>": ["part_scatter2<2, 8, 0>", "part_scatter<2, 8>"], "part_hist_kernel": ["part_hist"], "part_hist_bytes_kernel": ["part_hist_bytes"], "bucket_count_kernel": ["bucket_count"],
              "bucket_emit_smem_kernel": ["bucket_emit_smem"], "transpose_words_kernel": ["transpose_words"]}
 
 

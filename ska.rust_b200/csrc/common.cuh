@@ -171,7 +171,8 @@ void partition_records(const uint64_t* rec, uint64_t n_pos, const uint64_t* d_sa
                        const unsigned long long* k1_hist = nullptr);
 // first pass only (what a rank does before the exchange) / second pass over received runs (what the owner does after it)
 void partition_coarse(const uint64_t* rec, uint64_t n_pos, const uint64_t* d_sample_off, uint32_t n_samples_local, uint32_t sid_base,
-                      const PartPlan& pl, uint64_t** out, uint64_t** d_off1, uint64_t** d_tile_pref, const unsigned long long* k1_hist = nullptr);
+                      const PartPlan& pl, uint64_t** out, uint64_t** d_off1, uint64_t** d_tile_pref, const unsigned long long* k1_hist = nullptr,
+                      uint8_t** d_next_digit = nullptr /* -> one byte per record: its second-pass digit (NULL when not produced) */);
 void partition_runs(const uint64_t* src, int n_runs, const uint64_t* h_run_off, uint32_t n_regions, const PartPlan& pl, uint64_t* dst,
                     uint64_t** d_bucket_off);
 // plain MSD grouping of 16-byte records by P1 + P2 bits below `top_bit` (all-ones records dropped); sort128.cu finishes the sort

@@ -186,6 +186,52 @@ part_hist_kernel(const uint64_t* __restrict__ src, uint64_t n_total, uint64_t n_
     if (cur_region != PT_NONE) flush(cur_region);
 }
 
+// The second pass's histogram from the digit bytes the first scatter left beside its records (one byte per record instead
+// of the 8-byte record: 0.64 GB instead of 5.1 GB for 128 x 5 Mbp).  blockIdx.y = region, the CTAs of a region take its 16 KB
+// chunks in turn; a thread has four aligned 16-byte loads in flight, bytes outside the region are skipped at its two ends.
+constexpr int HB_THREADS = 256, HB_WORDS = 4;
+__global__ void __launch_bounds__(HB_THREADS)
+part_hist_bytes_kernel(const uint8_t* __restrict__ dig, const uint64_t* __restrict__ region_off, int bits, unsigned long long* __restrict__ hist) {
+    extern __shared__ uint32_t s_cnt[];
+    const uint32_t D = 1u << bits;
+    const uint32_t region = blockIdx.y;
+    const uint64_t beg = region_off[region], end = region_off[region + 1];
+    if (beg >= end) return;
+    for (uint32_t i = threadIdx.x; i < D; i += HB_THREADS) s_cnt[i] = 0;
+    __syncthreads();
+    const uint4* __restrict__ w4 = reinterpret_cast<const uint4*>(dig);
+    const uint64_t w_beg = beg >> 4, w_end = (end + 15) >> 4;                     // 16-byte words that touch the region
+    constexpr uint64_t CH = (uint64_t)HB_THREADS * HB_WORDS;
+    for (uint64_t w0 = w_beg + (uint64_t)blockIdx.x * CH; w0 < w_end; w0 += (uint64_t)gridDim.x * CH) {
+        uint4 v[HB_WORDS];
+#pragma unroll
+        for (int j = 0; j < HB_WORDS; j++) {
+            const uint64_t w = w0 + (uint64_t)j * HB_THREADS + threadIdx.x;
+            v[j] = w < w_end ? __ldg(w4 + w) : make_uint4(0, 0, 0, 0);
+        }
+#pragma unroll
+        for (int j = 0; j < HB_WORDS; j++) {
+            const uint64_t w = w0 + (uint64_t)j * HB_THREADS + threadIdx.x;
+            if (w >= w_end) continue;
+            const uint64_t p = w << 4;
+            const uint32_t x[4] = {v[j].x, v[j].y, v[j].z, v[j].w};
+            if (p >= beg && p + 16 <= end) {
+#pragma unroll
+                for (int b = 0; b < 16; b++) atomicAdd(&s_cnt[(x[b >> 2] >> (8 * (b & 3))) & 0xFFu], 1u);
+            } else {
+#pragma unroll
+                for (int b = 0; b < 16; b++)
+                    if (p + b >= beg && p + b < end) atomicAdd(&s_cnt[(x[b >> 2] >> (8 * (b & 3))) & 0xFFu], 1u);
+            }
+        }
+    }
+    __syncthreads();
+    for (uint32_t d = threadIdx.x; d < D; d += HB_THREADS) {
+        const uint32_t tot = s_cnt[d];
+        if (tot) atomicAdd(&hist[(size_t)region * D + d], (unsigned long long)tot);
+    }
+}
+
 // ---------------------------------------------------------------------------------------------- scatter
 struct PackFn {               // pass 1: K1 record -> packed record (needs the sample id of the position)
     int sb;                   // bits of a sample id
@@ -326,7 +372,9 @@ template <int PASS, int BITS, int STR>
 __global__ void __launch_bounds__(SC_T, SC_MIN_CTAS)
 part_scatter2_kernel(const uint64_t* __restrict__ src, uint64_t n_total, Segs sg, DigitFn fn, int bits_rt, PackFn pk,
                      const uint64_t* __restrict__ sample_off, uint32_t n_samples,
-                     unsigned long long* __restrict__ cursor, uint64_t* __restrict__ dst) {
+                     unsigned long long* __restrict__ cursor, uint64_t* __restrict__ dst,
+                     uint8_t* __restrict__ next_digit /* pass 1, may be null: the record's pass-2 digit, same order as dst */,
+                     int nd_shift, uint32_t nd_mask) {
     extern __shared__ __align__(16) uint8_t smem[];
     const int bits = BITS ? BITS : bits_rt;
     const uint32_t D = 1u << bits;
@@ -474,7 +522,10 @@ part_scatter2_kernel(const uint64_t* __restrict__ src, uint64_t n_total, Segs sg
             if (PASS == 1) {
                 const uint32_t d = (uint32_t)(r >> fn.shift);
                 const uint32_t mid = (uint32_t)__ffs((uint32_t)(r & 0xF)) - 1u;
-                dst[s_gbase[d] + slot] = (((r >> 4) & pk.low_mask) << (pk.sb + 2)) | sid_bits | mid;
+                const uint64_t prec = (((r >> 4) & pk.low_mask) << (pk.sb + 2)) | sid_bits | mid;
+                const unsigned long long g = s_gbase[d] + slot;
+                dst[g] = prec;
+                if (next_digit) next_digit[g] = (uint8_t)((uint32_t)(prec >> nd_shift) & nd_mask);
             } else {
                 const uint32_t d = fn.mask ? (uint32_t)(r >> fn.shift) & fn.mask : 0u;
                 dst[s_gbase[d] + slot] = r;
@@ -861,7 +912,8 @@ static void set_scatter_attrs() {
 // pass 1.  rec: K1 output (n_pos entries, linear) -> packed records grouped by the top P1 key bits in `*out`
 // (arena), region offsets `*d_off1` [2^P1 + 1] and tiles-before-region `*d_tile_pref` [2^P1 + 1] on the device.
 void partition_coarse(const uint64_t* rec, uint64_t n_pos, const uint64_t* d_sample_off, uint32_t n_samples_local, uint32_t sid_base,
-                      const PartPlan& pl, uint64_t** out, uint64_t** d_off1, uint64_t** d_tile_pref, const unsigned long long* k1_hist) {
+                      const PartPlan& pl, uint64_t** out, uint64_t** d_off1, uint64_t** d_tile_pref, const unsigned long long* k1_hist,
+                      uint8_t** d_next_digit) {
     Context& c = ctx();
     timer().begin("hist1");
     const uint32_t D1 = 1u << pl.P1;
@@ -884,6 +936,15 @@ void partition_coarse(const uint64_t* rec, uint64_t n_pos, const uint64_t* d_sam
     timer().end();
     timer().begin("scatter1");
     uint64_t* a = arena().take_n<uint64_t>(std::max<uint64_t>(n_pos, 1) * (pl.wide ? 2 : 1));
+    // the second pass's digit of every record, one byte each, in the order of `a`: its histogram then reads n bytes, not 8 n
+    uint8_t* nd = nullptr;
+    const int nd_shift = pl.sb + 2 + pl.low_bits - pl.P2;
+    const uint32_t nd_mask = (1u << pl.P2) - 1u;
+    static const bool nd_enabled = [] { const char* e = getenv("SKA_HIST2_BYTES"); return !e || atoi(e) != 0; }();
+    if (d_next_digit) {
+        if (nd_enabled && !pl.wide && !scatter_v1() && pl.P2 >= 1 && pl.P2 <= 8 && n_pos) nd = arena().take_n<uint8_t>(n_pos + 16);     // + 16: the histogram reads whole 16-byte words
+        *d_next_digit = nd;
+    }
     if (n_pos && pl.wide) {
         const PackWide pw{pl.sb, pl.low_bits, sid_base};
         SKA_LAUNCH((part_scatter_wide_kernel<1>), (unsigned)n_tiles1, SCW_T, scatter_wide_smem(pl.P1), rec, n_pos, none, f1, pl.P1, pw,
@@ -898,16 +959,16 @@ void partition_coarse(const uint64_t* rec, uint64_t n_pos, const uint64_t* d_sam
                            d_sample_off, n_samples_local, cur1, a);
         } else if (pl.P1 == 8) {
             SKA_LAUNCH((part_scatter2_kernel<1, 8, 0>), (unsigned)n_tiles1, SC_T, scatter2_smem(pl.P1), rec, n_pos, none, f1, pl.P1, pk,
-                       d_sample_off, n_samples_local, cur1, a);
+                       d_sample_off, n_samples_local, cur1, a, nd, nd_shift, nd_mask);
             if (n_samples_local > 1)
                 SKA_LAUNCH((part_scatter2_kernel<1, 8, 1>), n_samples_local - 1, SC_T, scatter2_smem(pl.P1), rec, n_pos, none, f1, pl.P1, pk,
-                           d_sample_off, n_samples_local, cur1, a);
+                           d_sample_off, n_samples_local, cur1, a, nd, nd_shift, nd_mask);
         } else {
             SKA_LAUNCH((part_scatter2_kernel<1, 0, 0>), (unsigned)n_tiles1, SC_T, scatter2_smem(pl.P1), rec, n_pos, none, f1, pl.P1, pk,
-                       d_sample_off, n_samples_local, cur1, a);
+                       d_sample_off, n_samples_local, cur1, a, nd, nd_shift, nd_mask);
             if (n_samples_local > 1)
                 SKA_LAUNCH((part_scatter2_kernel<1, 0, 1>), n_samples_local - 1, SC_T, scatter2_smem(pl.P1), rec, n_pos, none, f1, pl.P1, pk,
-                           d_sample_off, n_samples_local, cur1, a);
+                           d_sample_off, n_samples_local, cur1, a, nd, nd_shift, nd_mask);
         }
     }
     *out = a; *d_off1 = off1; *d_tile_pref = tile_pref;
@@ -917,7 +978,7 @@ void partition_coarse(const uint64_t* rec, uint64_t n_pos, const uint64_t* d_sam
 // pass 2.  src: packed records; the segments (device arrays) say where the pieces of each of the `n_regions`
 // regions lie.  -> dst grouped by (region, next P2 key bits), `*d_bucket_off` [n_regions * 2^P2 + 1] on the device.
 void partition_fine(const uint64_t* src, const Segs& sg, uint64_t n_tiles2, uint32_t n_regions, const PartPlan& pl, uint64_t* dst,
-                    uint64_t** d_bucket_off) {
+                    uint64_t** d_bucket_off, const uint8_t* next_digit = nullptr /* the first scatter's digit bytes, in the order of src */) {
     Context& c = ctx();
     timer().begin("hist2");
     const uint32_t D2 = 1u << pl.P2;
@@ -932,6 +993,8 @@ void partition_fine(const uint64_t* src, const Segs& sg, uint64_t n_tiles2, uint
     if (n_tiles2) {
         const unsigned g2 = (unsigned)std::min<uint64_t>(n_tiles2, (uint64_t)c.sm_count * 4);
         if (pl.wide) SKA_LAUNCH(part_hist_wide_kernel, g2, PT_THREADS, D2 * 4, src, (uint64_t)0, n_tiles2, sg, f2, pl.P2, hist2);
+        else if (next_digit && sg.tile_pref && !sg.region && sg.end == sg.beg + 1)      // segments = whole regions, back to back
+            SKA_LAUNCH(part_hist_bytes_kernel, dim3(8, n_regions), HB_THREADS, 256 * 4, next_digit, sg.beg, pl.P2, hist2);
         else SKA_LAUNCH(part_hist_kernel, g2, PT_THREADS, D2 * 4, src, (uint64_t)0, n_tiles2, sg, f2, pl.P2, hist2);
     }
     launch_part_scan((const unsigned long long*)hist2, (uint32_t)NB, bucket_off, cur2, (uint64_t*)nullptr, 1);
@@ -951,10 +1014,10 @@ void partition_fine(const uint64_t* src, const Segs& sg, uint64_t n_tiles2, uint
                            (const uint64_t*)nullptr, 0u, cur2, dst);
         } else if (pl.P2 == 8)
             SKA_LAUNCH((part_scatter2_kernel<2, 8, 0>), (unsigned)n_tiles2, SC_T, scatter2_smem(pl.P2), src, (uint64_t)0, sg, f2, pl.P2, pk,
-                       (const uint64_t*)nullptr, 0u, cur2, dst);
+                       (const uint64_t*)nullptr, 0u, cur2, dst, (uint8_t*)nullptr, 0, 0u);
         else
             SKA_LAUNCH((part_scatter2_kernel<2, 0, 0>), (unsigned)n_tiles2, SC_T, scatter2_smem(pl.P2), src, (uint64_t)0, sg, f2, pl.P2, pk,
-                       (const uint64_t*)nullptr, 0u, cur2, dst);
+                       (const uint64_t*)nullptr, 0u, cur2, dst, (uint8_t*)nullptr, 0, 0u);
     }
     *d_bucket_off = bucket_off;
     timer().end();
@@ -968,7 +1031,8 @@ void partition_records(const uint64_t* rec, uint64_t n_pos, const uint64_t* d_sa
     Context& c = ctx();
     const uint32_t D1 = 1u << pl.P1;
     uint64_t *a = nullptr, *off1 = nullptr, *tile_pref = nullptr;
-    partition_coarse(rec, n_pos, d_sample_off, n_samples_local, sid_base, pl, &a, &off1, &tile_pref, k1_hist);
+    uint8_t* next_digit = nullptr;
+    partition_coarse(rec, n_pos, d_sample_off, n_samples_local, sid_base, pl, &a, &off1, &tile_pref, k1_hist, &next_digit);
     if (first_pass_buf) *first_pass_buf = a;
     if (pl.P2 == 0) { *out = a; *d_off = off1; return; }
     uint64_t n_tiles2 = 0;
@@ -976,7 +1040,7 @@ void partition_records(const uint64_t* rec, uint64_t n_pos, const uint64_t* d_sa
     read_back_sync();
     uint64_t* b = scratch ? scratch : arena().take_n<uint64_t>(std::max<uint64_t>(n_pos, 1) * (pl.wide ? 2 : 1));
     const Segs sg{tile_pref, off1, off1 + 1, nullptr, D1};
-    partition_fine(a, sg, n_tiles2, D1, pl, b, d_off);
+    partition_fine(a, sg, n_tiles2, D1, pl, b, d_off, next_digit);
     *out = b;
 }
 
