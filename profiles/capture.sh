@@ -3,7 +3,7 @@
 #   launches_rNN.csv     every launch of one short bench run with its device time (cold-cache, serialised: compare shares)
 #   <kernel>_rNN_raw.csv ncu --set full raw metrics of the top kernels (one launch each, 128 x 5 Mbp)
 R=${1:-r01}
-KERNELS=${2:-"k1_extract bucket_emit_smem bucket_count part_scatter filter_flags_rows transpose_words"}
+KERNELS=${2:-"k1_extract bucket_emit_smem bucket_count part_scatter part_hist filter_flags_rows filter_scatter transpose_words"}
 mkdir -p gpurun_out
 if [ -z "$SKIP_LAUNCH_LIST" ]; then
 timeout 600 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none --csv \

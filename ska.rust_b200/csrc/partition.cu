@@ -537,7 +537,7 @@ static size_t scatter2_smem(int bits) {
     const size_t D = (size_t)1 << bits;
     return PT_TILE * 8 + D * 8 + D * 4 + D * 4 + 64;
 }
-static bool scatter_v1() { static const bool v = [] { const char* e = getenv("SKA_SCATTER_V1"); return e && atoi(e) != 0; }(); return v; }
+static bool scatter_v1() { const char* e = getenv("SKA_SCATTER_V1"); return e && atoi(e) != 0; }   // read per build: tests switch it
 
 // ---------------------------------------------------------------------------------------------- wide records (k > 31)
 // The same two passes on 16-byte records (key of up to 124 bits << 4 | one-hot middle from K1; packed records carry
@@ -940,7 +940,8 @@ void partition_coarse(const uint64_t* rec, uint64_t n_pos, const uint64_t* d_sam
     uint8_t* nd = nullptr;
     const int nd_shift = pl.sb + 2 + pl.low_bits - pl.P2;
     const uint32_t nd_mask = (1u << pl.P2) - 1u;
-    static const bool nd_enabled = [] { const char* e = getenv("SKA_HIST2_BYTES"); return !e || atoi(e) != 0; }();
+    const char* nd_env = getenv("SKA_HIST2_BYTES");
+    const bool nd_enabled = !nd_env || atoi(nd_env) != 0;
     if (d_next_digit) {
         if (nd_enabled && !pl.wide && !scatter_v1() && pl.P2 >= 1 && pl.P2 <= 8 && n_pos) nd = arena().take_n<uint8_t>(n_pos + 16);     // + 16: the histogram reads whole 16-byte words
         *d_next_digit = nd;

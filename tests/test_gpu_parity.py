@@ -231,6 +231,23 @@ def test_build_synthetic_matches_oracle(n, length, k, rc):
     assert_same_array(g, o)
 
 
+@pytest.mark.parametrize("switch", [{"SKA_SCATTER_V1": "1"}, {"SKA_HIST2_BYTES": "0"}, {"SKA_PREFIX_BITS": "13"}, {"SKA_EMIT_CAP_FACTOR": "2"}])
+@pytest.mark.parametrize("n,length,k,rc", [(5, 60_000, 31, True), (130, 3_001, 21, False), (300, 1_500, 31, True)])
+def test_build_partition_forms(n, length, k, rc, switch, monkeypatch):
+    """the partition's alternative forms give the same array: the first scatter kernel (staged digits), the second
+    histogram from the records instead of the digit bytes, a digit split other than 8 + 8 (run-time digit widths: the
+    warp-0 scan and the record histogram), a denser emit table.  Many short samples put several sample boundaries into one
+    scatter tile (the per-sample rounds of the straddling launch); 300 samples take the sample search of thread 0."""
+    from ska_rust_b200 import synth
+    for k_, v in switch.items():
+        monkeypatch.setenv(k_, v)
+    genomes = synth.star_genomes(n, length, seed=0x5CA20700 + n, snp_rate=0.003)
+    samples = [S.Sample.from_records([g.tobytes()]) for g in genomes]
+    names = [f"s{i}" for i in range(n)]
+    g = S.build_from_samples(samples, names, k, rc)
+    assert_same_array(g, ora_from_gpu_samples(samples, names, k, rc))
+
+
 MERGE_PATHS = {"fused": ("1", "0"), "two-pass": ("0", "0"), "two-pass-global": ("0", "1")}   # SKA_MERGE_FUSED, SKA_EMIT_GLOBAL
 
 
