@@ -490,7 +490,7 @@ def run_ours(args, rank, world, local_rank):
             "roofline_k1": k1,
             "roofline_step": {"bound": "hbm", "algorithmic_bytes": step_bytes, "achieved": step_bytes / (step_ms * 1e-3) / 1e9,
                               "peak": peak, "unit": "GB/s", "frac": step_bytes / (step_ms * 1e-3) / 1e9 / peak},
-            "roofline_stages": {s_: round(roof(s_)["frac"], 3) for s_ in st if s_ in STAGE_KERNELS},
+            "roofline_stages": {s_: round(roof(s_)["frac"], 3) for s_ in st if s_ in STAGE_KERNELS and st[s_] >= 0.05},   # hist1 is a scan only when K1 counted
             "stages_ms": {s_: round(ms, 3) for s_, ms, _ in stages},
             "clocks": clocks.summary(),
             "parity_checked": True, "parity": parity,
