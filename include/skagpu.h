@@ -36,7 +36,10 @@ typedef struct ska_mapping ska_mapping_t;
 
 /* One sample = InputFastx (merge_ska_dict.rs:25) after host-side parsing (needletail's job,
  * ska_dict.rs:131-147): all records of file 1 followed by all records of file 2, newlines
- * stripped, concatenated; rec_off has n_rec+1 entries.  qual == NULL <=> FASTA input. */
+ * stripped, concatenated; rec_off has n_rec+1 entries.  qual == NULL <=> the sample's first file is
+ * FASTA (is_reads = false, ska_dict.rs:356-366); FASTA and FASTQ samples may share one build.  A
+ * record without a quality string inside a read sample (a FASTA second file) carries quality bytes
+ * 0xFF, which every quality test passes (split_kmer.rs:66-71, `None => true`). */
 typedef struct {
     const uint8_t* seq;
     const uint8_t* qual;
