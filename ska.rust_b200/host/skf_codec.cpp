@@ -312,6 +312,8 @@ Array decode(const uint8_t* data, size_t len, int threads) {
     Reader r{payload.p.get(), payload.n};
     Array a;
     std::vector<uint64_t> lo, hi;
+    // an array header cannot announce more elements than the payload has bytes left (every element takes at least one)
+    auto bounded = [&](uint64_t n) { if (n > r.n - r.pos) throw std::runtime_error("skf: array longer than the payload"); return n; };
     bool wide = false;
     uint64_t fields = r.map();
     for (uint64_t f = 0; f < fields; f++) {
@@ -320,7 +322,7 @@ Array decode(const uint8_t* data, size_t len, int threads) {
         else if (key == "rc") a.rc = r.boolean();
         else if (key == "names") { uint64_t n = r.array(); for (uint64_t i = 0; i < n; i++) a.names.push_back(r.text()); }
         else if (key == "split_kmers") {
-            uint64_t n = r.array(); lo.resize(n); hi.resize(n);
+            uint64_t n = bounded(r.array()); lo.resize(n); hi.resize(n);
             for (uint64_t i = 0; i < n; i++) { r.key128(lo[i], hi[i]); wide |= hi[i] != 0; }
         } else if (key == "variants") {
             uint64_t m = r.map();
@@ -329,7 +331,7 @@ Array decode(const uint8_t* data, size_t len, int threads) {
                 if (vk == "v") { if (r.uint_() != 1) throw std::runtime_error("skf: unexpected ndarray version"); }
                 else if (vk == "dim") { if (r.array() != 2) throw std::runtime_error("skf: bad dim"); a.n_rows = r.uint_(); a.n_samples = r.uint_(); }
                 else if (vk == "data") {
-                    uint64_t n = r.array(); a.variants.resize(n);
+                    uint64_t n = bounded(r.array()); a.variants.resize(n);
                     // every middle-base byte written by ska is '-' or a letter (>= 24): exactly `18 xx` each.  Check and
                     // take that form with all threads; anything else goes through the general integer reader.
                     bool fixed = r.pos + 2 * n <= r.n;
@@ -353,13 +355,17 @@ Array decode(const uint8_t* data, size_t len, int threads) {
                     else for (uint64_t i = 0; i < n; i++) a.variants[i] = (uint8_t)r.uint_();
                 } else throw std::runtime_error("skf: unexpected key in variants");
             }
-        } else if (key == "variant_count") { uint64_t n = r.array(); a.counts.resize(n); for (uint64_t i = 0; i < n; i++) a.counts[i] = r.uint_(); }
+        } else if (key == "variant_count") { uint64_t n = bounded(r.array()); a.counts.resize(n); for (uint64_t i = 0; i < n; i++) a.counts[i] = r.uint_(); }
         else if (key == "ska_version") a.ska_version = r.text();
         else if (key == "k_bits") a.k_bits_field = (uint32_t)r.uint_();   // informational (merge_ska_array.rs:124-125); width follows the values
         else throw std::runtime_error("skf: unexpected field " + key);
     }
     if (a.variants.size() != a.n_rows * a.n_samples || a.counts.size() != a.n_rows || a.names.size() != a.n_samples)
         throw std::runtime_error("skf: inconsistent dimensions");
+    // every command that saves an array compacts its split k-mers with the rows (generic_modes.rs:252: update_kmers = true),
+    // and the device copy reads n_rows keys: a file with another number of keys is damaged
+    if (lo.size() != a.n_rows || (wide && hi.size() != lo.size()))
+        throw std::runtime_error("skf: the number of split k-mers differs from the number of variant rows");
     // the reference tries MergeSkaArray::<u64>::load first and falls back to u128 (lib.rs:635-661)
     a.key_bits = wide ? 128 : 64;
     if (wide) { a.keys.resize(2 * lo.size()); for (size_t i = 0; i < lo.size(); i++) { a.keys[2 * i] = lo[i]; a.keys[2 * i + 1] = hi[i]; } }

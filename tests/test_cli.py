@@ -32,6 +32,29 @@ def test_cpp_codec_recode_matches_python_decoder(gold_in, tmp_path, fixture):
         assert skf_py.snappy_frame_decode(f1.read()) == skf_py.snappy_frame_decode(f2.read())
 
 
+def test_cpp_codec_rejects_damaged_files(tmp_path):
+    """a .skf whose arrays disagree (fewer split k-mers than rows would make the device copy read past the key array) or
+    whose array header announces more elements than the payload holds is refused with a message, not loaded"""
+    good = skf_py.dump_skf_bytes(9, True, ["a", "b"], [5, 9, 12], b"ACGTAC", 3, 2, [2, 2, 2])
+    ok = tmp_path / "ok.skf"
+    ok.write_bytes(good)
+    run(["recode", str(ok), str(tmp_path / "ok2.skf")])
+    assert skf_py.load_skf(str(tmp_path / "ok2.skf")) == skf_py.load_skf(str(ok))
+    short = tmp_path / "short.skf"
+    short.write_bytes(skf_py.dump_skf_bytes(9, True, ["a", "b"], [5, 9], b"ACGTAC", 3, 2, [2, 2, 2]))
+    p = run(["recode", str(short), str(tmp_path / "x.skf")], check=False)
+    assert p.returncode != 0 and b"split k-mers" in p.stderr
+    # an array head that promises 2^40 variant bytes in a payload of a few dozen
+    payload = bytearray(skf_py.snappy_frame_decode(good))
+    i = payload.index(b"ddata") + 5
+    assert payload[i] == 0x86                                      # array(6)
+    payload[i:i + 1] = b"\x9b" + (1 << 40).to_bytes(8, "big")
+    huge = tmp_path / "huge.skf"
+    huge.write_bytes(skf_py.snappy_frame_encode_raw(bytes(payload)))
+    p = run(["recode", str(huge), str(tmp_path / "y.skf")], check=False)
+    assert p.returncode != 0 and b"longer than the payload" in p.stderr
+
+
 def test_cpp_codec_large_random_roundtrip(tmp_path):
     """several 64 KiB chunks, compressible and incompressible regions, u128 keys"""
     rng = np.random.default_rng(1)
