@@ -10,6 +10,8 @@ import numpy as np
 import pytest
 
 import ska_rust_b200 as S
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 from oracle import oracle as O
 from oracle import skf_py
 
@@ -246,6 +248,32 @@ def test_build_partition_forms(n, length, k, rc, switch, monkeypatch):
     names = [f"s{i}" for i in range(n)]
     g = S.build_from_samples(samples, names, k, rc)
     assert_same_array(g, ora_from_gpu_samples(samples, names, k, rc))
+
+
+def test_merge_kernels_cross_their_record_chunks():
+    """bucket_count / bucket_emit walk a bucket's records in chunks of 2^31 with 32-bit positions inside a chunk; the
+    library variant built by __graft_entry__.build() with chunks of 4096 records crosses that boundary in every
+    bucket (another process: a library is bound once per process)."""
+    import subprocess
+    import sys
+    lib = os.path.join(ROOT, "ska.rust_b200", "variants", "libskagpu_chunk12.so")
+    if not os.path.exists(lib):
+        pytest.skip("variants/libskagpu_chunk12.so not built (python -c 'import __graft_entry__ as g; g.build()')")
+    code = (
+        "import numpy as np, ska_rust_b200 as S\n"
+        "from oracle import oracle as O\n"
+        "from ska_rust_b200 import synth\n"
+        "for n, length, k in ((40, 30000, 31), (8, 150000, 15)):\n"
+        "    gs = synth.star_genomes(n, length, seed=0x5CA20900 + n, snp_rate=0.002)\n"
+        "    names = [f's{i}' for i in range(n)]\n"
+        "    g = S.build_from_samples([S.Sample.from_records([x.tobytes()]) for x in gs], names, k, True)\n"
+        "    o = O.OracleArray.build([O.SampleData([(x.tobytes(), None)]) for x in gs], names, k=k, rc=True)\n"
+        "    gk, gv, gc = g.export(); ok, ov, oc = o.export()\n"
+        "    assert [int(x) for x in gk] == ok and np.array_equal(gv, ov) and np.array_equal(gc, oc)\n"
+        "print('chunks ok')\n")
+    env = dict(os.environ, SKAGPU_LIB=lib)                            # buckets hold ~10 k records: two to three chunks each
+    p = subprocess.run([sys.executable, "-c", code], cwd=ROOT, env=env, capture_output=True, text=True, timeout=600)
+    assert p.returncode == 0 and "chunks ok" in p.stdout, p.stderr[-2000:]
 
 
 MERGE_PATHS = {"fused": ("1", "0"), "two-pass": ("0", "0"), "two-pass-global": ("0", "1")}   # SKA_MERGE_FUSED, SKA_EMIT_GLOBAL

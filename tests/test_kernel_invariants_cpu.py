@@ -91,3 +91,86 @@ def test_iupac_letters_by_two_byte_permutes():
         mask = ((v >> 3) & 0x01010101) * 0xFF
         word = (hi & mask) | (lo & ~mask & 0xFFFFFFFF)
         assert [(word >> (8 * i)) & 0xFF for i in range(4)] == [letters[s] for s in sets]
+
+
+def test_scatter_tiles_are_claimed_exactly_once_by_the_two_launches():
+    """part_scatter2_kernel<1, *, STR> (csrc/partition.cu): the common launch takes every tile whose first and last
+    position lie in one sample; launch STR = 1 has one CTA per sample boundary m and takes the boundary's tile iff the
+    boundary is strictly inside the tile and is the first such boundary of that tile.  Together: every tile once, and
+    inside a straddling tile the per-sample rounds [a, b) tile the tile's positions."""
+    rng = np.random.default_rng(7)
+    T = 4096
+    for trial in range(200):
+        n_samples = int(rng.integers(1, 40))
+        lens = rng.integers(0 if trial % 5 == 0 else 1, 3 * T, size=n_samples)
+        if trial % 3 == 0:
+            lens = (lens // T) * T + (rng.integers(0, 2, size=n_samples) * rng.integers(0, T, size=n_samples))   # many boundaries on tile starts
+        off = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
+        n_pos = int(off[-1])
+        if n_pos == 0:
+            continue
+        n_tiles = (n_pos + T - 1) // T
+        claimed = np.zeros(n_tiles, dtype=np.int64)
+        sid = lambda p: int(np.searchsorted(off[:n_samples], p, side="right")) - 1      # last s with off[s] <= p
+        for t in range(n_tiles):                                                          # STR = 0
+            beg, end = t * T, min(n_pos, (t + 1) * T)
+            hi = sid(end - 1)
+            lo = hi if off[hi] <= beg else hi - 1                                         # the kernel only needs "same or not"
+            assert (lo == hi) == (sid(beg) == hi)
+            if lo == hi:
+                claimed[t] += 1
+        for m in range(1, n_samples):                                                     # STR = 1, CTA m - 1
+            p = int(off[m])
+            t = p // T
+            if p >= n_pos or p == t * T or off[m - 1] > t * T:
+                continue
+            claimed[t] += 1
+            beg, end = t * T, min(n_pos, (t + 1) * T)
+            cnt = end - beg
+            covered = np.zeros(cnt, dtype=np.int64)
+            for s in range(sid(beg), sid(end - 1) + 1):
+                a = min(cnt, off[s] - beg) if off[s] > beg else 0
+                b = min(cnt, off[s + 1] - beg) if off[s + 1] > beg else 0
+                covered[a:b] += 1
+                assert all(sid(beg + i) == s for i in (a, b - 1) if a < b)
+            assert (covered == 1).all()
+        assert (claimed == 1).all(), (trial, off, claimed)
+
+
+def test_byte_histogram_counts_exactly_the_region():
+    """part_hist_bytes_kernel: a region [beg, end) of the digit-byte array is read as aligned 16-byte words; whole words
+    inside the region take the unchecked path, the two ragged ends are checked byte by byte -- every byte once."""
+    rng = np.random.default_rng(11)
+    data = rng.integers(0, 256, size=5000, dtype=np.uint8)
+    for _ in range(300):
+        beg = int(rng.integers(0, 4900))
+        end = int(rng.integers(beg, 5000))
+        hist = np.zeros(256, dtype=np.int64)
+        for w in range(beg >> 4, (end + 15) >> 4):
+            p = w << 4
+            word = np.zeros(16, dtype=np.uint8)
+            word[:max(0, min(16, len(data) - p))] = data[p:p + 16]                          # (the array is allocated 16 bytes longer)
+            if p >= beg and p + 16 <= end:
+                np.add.at(hist, word, 1)
+            else:
+                for b in range(16):
+                    if beg <= p + b < end:
+                        hist[word[b]] += 1
+        assert np.array_equal(hist, np.bincount(data[beg:end], minlength=256))
+
+
+def test_emit_set_bit_comes_straight_from_the_record():
+    """bucket_emit_smem_kernel: record = key_low << (sb + 2) | sample << 2 | middle; the set word of a row holds eight
+    samples x four bits, so bit = (sample & 7) * 4 + middle = record & 31 and word = sample >> 3 = (record >> 5) & (sid_mask >> 3);
+    with fewer than eight samples the key bits that follow at once are masked off."""
+    rng = np.random.default_rng(13)
+    for sb in range(1, 13):
+        sid_mask = (1 << sb) - 1
+        word_mask = sid_mask >> 3
+        bit_mask = 31 if sb >= 3 else (1 << (sb + 2)) - 1
+        for _ in range(2000):
+            sample = int(rng.integers(0, 1 << sb)); mid = int(rng.integers(0, 4)); key_low = int(rng.integers(0, 1 << 40))
+            rec = (key_low << (sb + 2)) | (sample << 2) | mid
+            lo = rec & 0xFFFFFFFF
+            assert (lo >> 5) & word_mask == sample >> 3
+            assert lo & bit_mask == 4 * (sample & 7) + mid
