@@ -8,7 +8,7 @@ for spec in "$@"; do
   v=${spec%%:*}; envs=""; [ "$spec" != "$v" ] && envs=${spec#*:}
   lib=""; [ "$v" != "base" ] && lib="ska.rust_b200/variants/libskagpu_$v.so"
   name=$(echo "$spec" | tr ':=,' '___')
-  env SKAGPU_LIB=$lib $(echo "$envs" | tr ',' ' ') python bench.py --steps 5 --warmup 3 --no-cpu-baseline --no-e2e > gpurun_out/ab_${tag}_$name.json 2> gpurun_out/ab_${tag}_$name.err
+  env SKAGPU_LIB=$lib $(echo "$envs" | tr ',' ' ') python bench.py --steps 5 --warmup 3 --no-cpu-baseline --no-e2e $AB_ARGS > gpurun_out/ab_${tag}_$name.json 2> gpurun_out/ab_${tag}_$name.err
   echo "== $spec: $(grep -o 'device warm-up done.*' gpurun_out/ab_${tag}_$name.err | cut -c1-600)"
   grep -o 'device arm:.*' gpurun_out/ab_${tag}_$name.err
 done

@@ -378,7 +378,7 @@ part_scatter2_kernel(const uint64_t* __restrict__ src, uint64_t n_total, Segs sg
     extern __shared__ __align__(16) uint8_t smem[];
     const int bits = BITS ? BITS : bits_rt;
     const uint32_t D = 1u << bits;
-    constexpr bool PER_THREAD = BITS != 0 && (1 << BITS) == SC_T;
+    constexpr bool PER_THREAD = BITS >= 3 && (1 << BITS) <= SC_T;        // one thread per digit (threads beyond D idle in phase B)
     uint64_t* s_stage = reinterpret_cast<uint64_t*>(smem);                       // [PT_TILE]
     unsigned long long* s_gbase = reinterpret_cast<unsigned long long*>(s_stage + PT_TILE);   // [D]
     uint32_t* s_acnt = reinterpret_cast<uint32_t*>(s_gbase + D);                 // [D] records per digit (16-byte aligned)
@@ -466,11 +466,14 @@ part_scatter2_kernel(const uint64_t* __restrict__ src, uint64_t n_total, Segs sg
         if (PER_THREAD) {
             // one thread per digit: the reservation is issued first and its result used last, so the round trip to L2
             // lies under the scan and the staging; every warp scans all group sums itself (no second barrier)
-            const uint32_t v = s_acnt[threadIdx.x];
+            const uint32_t v = threadIdx.x < D ? s_acnt[threadIdx.x] : 0u;
             unsigned long long g = 0;
             if (v) g = atomicAdd(&cursor[(size_t)region * D + threadIdx.x], (unsigned long long)v);
-            const uint4 q0 = reinterpret_cast<const uint4*>(s_acnt)[2 * lane], q1 = reinterpret_cast<const uint4*>(s_acnt)[2 * lane + 1];
-            const uint32_t gs = q0.x + q0.y + q0.z + q0.w + q1.x + q1.y + q1.z + q1.w;      // digits 8 * lane .. 8 * lane + 7
+            uint32_t gs = 0;                                                                // digits 8 * lane .. 8 * lane + 7
+            if (8u * lane < D) {
+                const uint4 q0 = reinterpret_cast<const uint4*>(s_acnt)[2 * lane], q1 = reinterpret_cast<const uint4*>(s_acnt)[2 * lane + 1];
+                gs = q0.x + q0.y + q0.z + q0.w + q1.x + q1.y + q1.z + q1.w;
+            }
             uint32_t ginc = gs, inc = v;
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) {
@@ -480,7 +483,7 @@ part_scatter2_kernel(const uint64_t* __restrict__ src, uint64_t n_total, Segs sg
             const uint32_t base = __shfl_sync(0xFFFFFFFFu, ginc - gs, 4 * warp);            // digits below 32 * warp
             n_valid = __shfl_sync(0xFFFFFFFFu, ginc, 31);
             const uint32_t excl = base + inc - v;
-            s_cur[threadIdx.x] = excl;
+            if (threadIdx.x < D) s_cur[threadIdx.x] = excl;
             __syncthreads();
             // C. stage in digit order
 #pragma unroll
@@ -488,7 +491,7 @@ part_scatter2_kernel(const uint64_t* __restrict__ src, uint64_t n_total, Segs sg
                 const uint32_t d = digit(j);
                 if (d != PT_NONE) s_stage[atomicAdd(&s_cur[d], 1u)] = rr[j];
             }
-            s_gbase[threadIdx.x] = g - excl;
+            if (threadIdx.x < D) s_gbase[threadIdx.x] = g - excl;
         } else {
             if (warp == 0) {
                 const uint32_t per = (D + 31) / 32, b0 = lane * per, e0 = min(D, b0 + per);
@@ -885,6 +888,7 @@ PartPlan make_part_plan(uint32_t k, int prefix_bits, uint64_t n_samples_total) {
     pl.P = std::min(std::max(prefix_bits, need1), pl.key_bits);
     if (pl.P > 2 * PT_MAX_BITS) pl.P = 2 * PT_MAX_BITS;
     pl.P1 = std::max((pl.P + 1) / 2, need1);
+    if (const char* e = getenv("SKA_P1_BITS")) { const int v = atoi(e); if (v >= need1 && v <= pl.P && v <= PT_MAX_BITS && pl.P - v <= PT_MAX_BITS) pl.P1 = v; }   // tuning/tests
     if (pl.P1 > PT_MAX_BITS || pl.P1 > pl.P) throw Error("too many samples for the packed record format at this k");
     pl.P2 = pl.P - pl.P1;
     pl.low_bits = pl.key_bits - pl.P1;
@@ -901,6 +905,9 @@ static void set_scatter_attrs() {
     SKA_CUDA(cudaFuncSetAttribute(part_scatter2_kernel<1, 0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)scatter2_smem(PT_MAX_BITS)));
     SKA_CUDA(cudaFuncSetAttribute(part_scatter2_kernel<1, 0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)scatter2_smem(PT_MAX_BITS)));
     SKA_CUDA(cudaFuncSetAttribute(part_scatter2_kernel<2, 0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)scatter2_smem(PT_MAX_BITS)));
+    SKA_CUDA(cudaFuncSetAttribute(part_scatter2_kernel<1, 7, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)scatter2_smem(8)));
+    SKA_CUDA(cudaFuncSetAttribute(part_scatter2_kernel<1, 7, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)scatter2_smem(8)));
+    SKA_CUDA(cudaFuncSetAttribute(part_scatter2_kernel<2, 7, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)scatter2_smem(8)));
     SKA_CUDA(cudaFuncSetAttribute(part_scatter2_kernel<1, 8, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)scatter2_smem(8)));
     SKA_CUDA(cudaFuncSetAttribute(part_scatter2_kernel<1, 8, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)scatter2_smem(8)));
     SKA_CUDA(cudaFuncSetAttribute(part_scatter2_kernel<2, 8, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)scatter2_smem(8)));
@@ -964,6 +971,12 @@ void partition_coarse(const uint64_t* rec, uint64_t n_pos, const uint64_t* d_sam
             if (n_samples_local > 1)
                 SKA_LAUNCH((part_scatter2_kernel<1, 8, 1>), n_samples_local - 1, SC_T, scatter2_smem(pl.P1), rec, n_pos, none, f1, pl.P1, pk,
                            d_sample_off, n_samples_local, cur1, a, nd, nd_shift, nd_mask);
+        } else if (pl.P1 == 7) {
+            SKA_LAUNCH((part_scatter2_kernel<1, 7, 0>), (unsigned)n_tiles1, SC_T, scatter2_smem(pl.P1), rec, n_pos, none, f1, pl.P1, pk,
+                       d_sample_off, n_samples_local, cur1, a, nd, nd_shift, nd_mask);
+            if (n_samples_local > 1)
+                SKA_LAUNCH((part_scatter2_kernel<1, 7, 1>), n_samples_local - 1, SC_T, scatter2_smem(pl.P1), rec, n_pos, none, f1, pl.P1, pk,
+                           d_sample_off, n_samples_local, cur1, a, nd, nd_shift, nd_mask);
         } else {
             SKA_LAUNCH((part_scatter2_kernel<1, 0, 0>), (unsigned)n_tiles1, SC_T, scatter2_smem(pl.P1), rec, n_pos, none, f1, pl.P1, pk,
                        d_sample_off, n_samples_local, cur1, a, nd, nd_shift, nd_mask);
@@ -1015,6 +1028,9 @@ void partition_fine(const uint64_t* src, const Segs& sg, uint64_t n_tiles2, uint
                            (const uint64_t*)nullptr, 0u, cur2, dst);
         } else if (pl.P2 == 8)
             SKA_LAUNCH((part_scatter2_kernel<2, 8, 0>), (unsigned)n_tiles2, SC_T, scatter2_smem(pl.P2), src, (uint64_t)0, sg, f2, pl.P2, pk,
+                       (const uint64_t*)nullptr, 0u, cur2, dst, (uint8_t*)nullptr, 0, 0u);
+        else if (pl.P2 == 7)
+            SKA_LAUNCH((part_scatter2_kernel<2, 7, 0>), (unsigned)n_tiles2, SC_T, scatter2_smem(pl.P2), src, (uint64_t)0, sg, f2, pl.P2, pk,
                        (const uint64_t*)nullptr, 0u, cur2, dst, (uint8_t*)nullptr, 0, 0u);
         else
             SKA_LAUNCH((part_scatter2_kernel<2, 0, 0>), (unsigned)n_tiles2, SC_T, scatter2_smem(pl.P2), src, (uint64_t)0, sg, f2, pl.P2, pk,
