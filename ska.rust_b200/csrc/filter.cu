@@ -445,7 +445,10 @@ transpose_kernel(const uint8_t* __restrict__ in, uint64_t n_rows, uint32_t n_sam
 // reads two 64-byte row pieces), 4 x 4 byte blocks are transposed in registers with byte permutes, and every
 // sample's 128 output bytes leave as aligned 4-byte words (the first and last word of a run byte by byte, because
 // sample s starts at byte s * n_rows of the output, which is aligned only by chance).
-constexpr int TR_ROWS = 128, TR_COLS = 64;
+// TR_COLS = 128: a CTA takes whole 128-byte lines of a row (with 64 columns two CTAs read each line: 1.2x the algorithmic
+// traffic in the ncu captures) -- measured slower, see transpose_array.
+constexpr int TR_ROWS = 128;
+template <int TR_COLS>
 __global__ void __launch_bounds__(256)
 transpose_words_kernel(const uint8_t* __restrict__ in, uint64_t n_rows, uint32_t n_samples, uint8_t* __restrict__ out) {
     __shared__ uint32_t s_in[TR_ROWS][TR_COLS / 4 + 1];
@@ -496,9 +499,15 @@ transpose_words_kernel(const uint8_t* __restrict__ in, uint64_t n_rows, uint32_t
 void transpose_array(const Array& a, uint8_t* d_out) {
     if (a.n_rows == 0 || a.n_samples == 0) return;
     if ((a.n_samples & 3u) == 0 && (reinterpret_cast<uintptr_t>(d_out) & 3u) == 0) {
-        dim3 grid((unsigned)((a.n_rows + TR_ROWS - 1) / TR_ROWS), (unsigned)((a.n_samples + TR_COLS - 1) / TR_COLS));
+        // measured on 3.06 M rows x 128 samples: 0.39 ms with 64 columns, 0.44 ms with 128 (34 KB of shared memory per CTA cost
+        // more than the second read of each line, which mostly hits L2): 64 stays the default, SKA_TRANSPOSE_COLS=128 selects the other
+        const char* e = getenv("SKA_TRANSPOSE_COLS");
+        const bool wide_tile = a.n_samples >= 128 && e && atoi(e) == 128;
+        const unsigned cols = wide_tile ? 128u : 64u;
+        dim3 grid((unsigned)((a.n_rows + TR_ROWS - 1) / TR_ROWS), (unsigned)((a.n_samples + cols - 1) / cols));
         timer().begin("transpose");
-        SKA_LAUNCH(transpose_words_kernel, grid, 256, 0, a.variants.p, a.n_rows, (uint32_t)a.n_samples, d_out);
+        if (wide_tile) SKA_LAUNCH(transpose_words_kernel<128>, grid, 256, 0, a.variants.p, a.n_rows, (uint32_t)a.n_samples, d_out);
+        else SKA_LAUNCH(transpose_words_kernel<64>, grid, 256, 0, a.variants.p, a.n_rows, (uint32_t)a.n_samples, d_out);
         timer().end();
         return;
     }

@@ -549,7 +549,11 @@ def test_filter_random_arrays_match_oracle(n_rows, n_samples):
                             assert_same_array(g, o)
 
 
-def test_transpose_matches_write_fasta():
+@pytest.mark.parametrize("cols", [None, "128"])
+def test_transpose_matches_write_fasta(cols, monkeypatch):
+    """both tile widths of transpose_words_kernel (64 columns by default; whole 128-byte row lines on request)"""
+    if cols:
+        monkeypatch.setenv("SKA_TRANSPOSE_COLS", cols)
     rng = np.random.default_rng(3)
     for n_rows, n_samples in ((1, 1), (63, 5), (64, 64), (1000, 129), (4097, 128), (1, 4), (3, 8), (130, 68), (1027, 200),
                               (12_345, 128), (517, 256), (2, 1024)):
